@@ -1,0 +1,3 @@
+class TestTubeLogger(object):
+    def __init__(self, *a, **k):
+        pass

@@ -1,0 +1,57 @@
+"""Case table shared by the golden generator (make_golden.py, runs the reference) and the tests
+(which rebuild the same inputs for the oracle and for the CUDA path)."""
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def dataset_path(name):
+    return os.path.join(HERE, "data", name)
+
+
+def _c(name, module, dataset="tiny", D=128, n_bases=128, L=4, t_list=(9, 5, 2, 0), rec_only_last_layer=True,
+       use_time_embedding=True, **kw):
+    d = dict(name=name, module=module, dataset=dataset, D=D, n_bases=n_bases, L=L, t_list=list(t_list),
+             rec_only_last_layer=rec_only_last_layer, use_time_embedding=use_time_embedding)
+    d.update(kw)
+    return d
+
+
+CASES = [
+    # --- config 1: static RGCN, seq_len 1 (order of t_list is kept, baselines/StaticRGCN.py:23-28)
+    _c("srgcn_tiny_d128", "SRGCN", L=1, t_list=(3, 9, 0, 5)),
+    _c("srgcn_tiny_d32_nb8_note", "SRGCN", D=32, n_bases=8, L=1, t_list=(4, 1), use_time_embedding=False),
+    # --- config 2 family: GRU recurrence, uni-directional
+    _c("grrgcn_tiny_d128_last", "GRRGCN"),
+    _c("grrgcn_tiny_d128_last_note", "GRRGCN", use_time_embedding=False, t_list=(8, 8, 3)),
+    _c("grrgcn_tiny_d128_full", "GRRGCN", rec_only_last_layer=False),
+    _c("grrgcn_tiny_d128_full_note", "GRRGCN", rec_only_last_layer=False, use_time_embedding=False),
+    _c("grrgcn_tiny_d32_nb8_type1", "GRRGCN", D=32, n_bases=8, type1=True),
+    _c("grrgcn_tiny_d128_lambda", "GRRGCN", learnable_lambda=True, L=5),
+    _c("grrgcn_tiny_d200_nb100", "GRRGCN", D=200, n_bases=100),
+    _c("grrgcn_tiny_d128_L1", "GRRGCN", L=1, t_list=(6, 2)),
+    # --- linear recurrence flavour
+    _c("rrgcn_tiny_d128_full", "RRGCN", rec_only_last_layer=False),
+    _c("rrgcn_tiny_d128_last", "RRGCN"),
+    # --- config 3 family: bidirectional
+    _c("bigrrgcn_tiny_d128_last", "BiGRRGCN"),
+    _c("bigrrgcn_tiny_d128_full", "BiGRRGCN", rec_only_last_layer=False, t_list=(9, 6, 1)),
+    _c("bigrrgcn_tiny_d200_nb100", "BiGRRGCN", D=200, n_bases=100, t_list=(7, 4)),
+    _c("birrgcn_tiny_d128_full", "BiRRGCN", rec_only_last_layer=False),
+    # --- config 4 family: attention over the time axis
+    _c("sargcn_tiny_d128_last", "SARGCN"),
+    _c("sargcn_tiny_d128_full", "SARGCN", rec_only_last_layer=False),
+    _c("sargcn_tiny_d128_lambda", "SARGCN", learnable_lambda=True),
+    _c("bisargcn_tiny_d128_last", "BiSARGCN"),
+    _c("bisargcn_tiny_d64_full", "BiSARGCN", D=64, n_bases=64, rec_only_last_layer=False, t_list=(8, 5, 0)),
+    # --- real ICEWS14 snapshots (first 12 timestamps), reference shapes D=128, n_bases=128, L=8
+    _c("grrgcn_icews_d128_L8", "GRRGCN", dataset="icews14_head", L=8, t_list=(11, 10, 3)),
+    _c("bigrrgcn_icews_d128_L8", "BiGRRGCN", dataset="icews14_head", L=8, t_list=(11, 6, 3)),
+    _c("bisargcn_icews_d128_L8", "BiSARGCN", dataset="icews14_head", L=8, t_list=(11, 5)),
+]
+
+SAMPLER_CASES = [
+    dict(name="sampler_tiny_seed123", dataset="tiny", times=[0, 4, 7], seed=123, negative_rate=5, num_pos_facts=3000),
+    dict(name="sampler_tiny_subsample", dataset="tiny", times=[2, 9], seed=7, negative_rate=6, num_pos_facts=10),
+    dict(name="sampler_icews_seed123", dataset="icews14_head", times=[3], seed=123, negative_rate=500, num_pos_facts=3000),
+]

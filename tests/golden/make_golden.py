@@ -1,0 +1,176 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (JiapengWu/TeMP) here.
+
+The reference's python files are imported from /root/reference on top of oracle/_stubs (a
+restatement of the DGL 0.4.1 / pytorch-lightning 0.5.2 API slices it calls -- those packages are
+not installable in this container).  Model parameters are overwritten with oracle.fill_values (an
+exact-integer hash), so the golden files hold OUTPUTS only and any implementation can rebuild the
+inputs from (case config, dataset files under tests/golden/data).
+
+Run from the repo root (needs /root/reference; the committed .npz files do not):
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+import warnings
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from tests.golden.cases import CASES, SAMPLER_CASES, dataset_path  # noqa: E402
+from oracle.temp_oracle import fill_values  # noqa: E402
+
+
+def reference_on_path():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_stubs"))
+    sys.path.insert(0, "/root/reference")
+
+
+def ref_args(case):
+    return Namespace(
+        dataset_dir="interpolation", dataset=dataset_path(case["dataset"]), score_function="complex",
+        module=case["module"], n_gpu=-1, use_cuda=False, hidden_size=case["D"], embed_size=case["D"],
+        dropout=0.1, num_layers=1, lr=1e-3, n_bases=case["n_bases"], rgcn_layers=2,
+        train_seq_len=case["L"], test_seq_len=case["L"], batch_size=len(case["t_list"]), seed=123,
+        negative_rate=case.get("negative_rate", 5), num_pos_facts=case.get("num_pos_facts", 3000),
+        debug=False, rec_only_last_layer=case["rec_only_last_layer"], use_time_embedding=case["use_time_embedding"],
+        inv_temperature=0.1, use_embed_for_non_active=False, edge_dropout=False, random_dropout=False,
+        type1=case.get("type1", False), post_ensemble=False, post_aggregation=False,
+        learnable_lambda=case.get("learnable_lambda", False), impute=False, EMA=False,
+        rate_lower=0.2, rate_upper=0.8, lambda_1=2, lambda_2=10, lambda_3=20)
+
+
+def ref_graph_dicts(args):
+    """utils/dataset.py:268-290 of the reference minus the pickle cache (dataset dir is read-only
+    for the real files and we do not want cache files in the fixtures)."""
+    from utils.dataset import (get_total_number, get_train_val_test_graph_at_t, load_quadruples,
+                               load_quadruples_interpolation)
+    _, total_times = load_quadruples(args.dataset, "train.txt", "valid.txt", "test.txt")
+    t2t = load_quadruples_interpolation(args.dataset, "train.txt", "valid.txt", "test.txt", total_times)
+    num_e, num_r = get_total_number(args.dataset, "stat.txt")
+    gtr, gva, gte = {}, {}, {}
+    for tim in total_times:
+        gtr[tim], gva[tim], gte[tim] = get_train_val_test_graph_at_t(t2t[tim], num_r)
+    return num_e, num_r, gtr, gva, gte
+
+
+def ref_model(case):
+    from baselines.StaticRGCN import StaticRGCN
+    from models.BiDynamicRGCN import BiDynamicRGCN
+    from models.BiSelfAttentionRGCN import BiSelfAttentionRGCN
+    from models.DynamicRGCN import DynamicRGCN
+    from models.SelfAttentionRGCN import SelfAttentionRGCN
+    cls = {"SRGCN": StaticRGCN, "GRRGCN": DynamicRGCN, "RRGCN": DynamicRGCN, "BiGRRGCN": BiDynamicRGCN,
+           "BiRRGCN": BiDynamicRGCN, "SARGCN": SelfAttentionRGCN, "BiSARGCN": BiSelfAttentionRGCN}[case["module"]]
+    args = ref_args(case)
+    num_e, num_r, gtr, gva, gte = ref_graph_dicts(args)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        model = cls(args, num_e, num_r, gtr, gva, gte)
+        for name, prm in model.state_dict().items():
+            prm.copy_(torch.from_numpy(fill_values(name, tuple(prm.shape))))
+    model.eval()
+    return model, (gtr, gva, gte)
+
+
+def run_case(case):
+    model, _ = ref_model(case)
+    t_list = torch.tensor(case["t_list"], dtype=torch.long)
+    L = case["L"]
+    mod = case["module"]
+    out = {}
+    with torch.no_grad():
+        if mod == "SRGCN":
+            per_graph, g_list = model.evaluate_embed(t_list, val=True)
+            times = [int(t) for t in case["t_list"]]
+            alls = [model.get_all_embeds_Gt(t_list[i], g_list[i], per_graph[i]) for i in range(len(times))]
+        elif mod in ("GRRGCN", "RRGCN"):
+            per_graph, test_graphs, time_list, hist, start = model.evaluate_embed(t_list, val=True)
+            times = [int(t) for t in time_list[-1]]
+            alls = [model.get_all_embeds_Gt(per_graph[i], test_graphs[i], time_list[-1][i], hist[i][0], hist[i][1],
+                                            L - 1 - start[i]) for i in range(len(times))]
+            out["start"] = start.numpy()
+            out["hist_abs_sum"] = hist.abs().sum(dim=(2, 3)).numpy()
+            out["hist_rows_nonzero"] = (hist.abs().sum(-1) != 0).sum(-1).numpy()
+        elif mod in ("BiGRRGCN", "BiRRGCN"):
+            per_graph, test_graphs, tl, hf, sf, hb, sb = model.evaluate_embed(t_list, val=True)
+            times = [int(t) for t in tl]
+            alls = [model.get_all_embeds_Gt(per_graph[i], test_graphs[i], tl[i], hf[i][0], hf[i][1], L - 1 - sf[i],
+                                            hb[i][0], hb[i][1], L - 1 - sb[i]) for i in range(len(times))]
+            out["start_f"], out["start_b"] = sf.numpy(), sb.numpy()
+        else:                                    # SARGCN / BiSARGCN: evaluate() inlined up to calc_metrics
+            from models.BiDynamicRGCN import BiDynamicRGCN
+            if mod == "SARGCN":
+                g_tr, time_list = model.get_batch_graph_list(t_list, L, model.graph_dict_train)
+                hist, mask = model.pre_forward(g_tr, time_list, val=True)
+                train_graphs, tl = g_tr[-1], time_list[-1]
+            else:
+                gf, tf, gb, tb = BiDynamicRGCN.get_batch_graph_list(t_list, L, model.graph_dict_train)
+                hfw, mfw = model.pre_forward(gf, tf, forward=True)
+                hbw, mbw = model.pre_forward(gb, tb, forward=False)
+                train_graphs, tl = gf[-1], tf[-1]
+                hist = torch.cat([hfw, hbw], dim=0)
+                mask = torch.cat([mfw, mbw, mfw.new_zeros(1, *mfw.shape[1:])], dim=0)
+            sizes = [len(g.nodes()) for g in train_graphs]
+            if mod == "SARGCN":
+                per_graph = model.get_final_graph_embeds(train_graphs, tl, sizes, hist, mask, full=True, val=True)
+            else:
+                per_graph = model.get_final_graph_embeds(train_graphs, tl, sizes, hist, mask, full=True)
+            times = [int(t) for t in tl]
+            alls = [model.get_all_embeds_Gt(per_graph[i], train_graphs[i], tl[i], hist[:, i, 0], hist[:, i, 1],
+                                            mask[:, i], val=True) for i in range(len(times))]
+    out["times"] = np.asarray(times, dtype=np.int64)
+    out["sizes"] = np.asarray([p.shape[0] for p in per_graph], dtype=np.int64)
+    out["per_graph"] = torch.cat(list(per_graph), dim=0).numpy()
+    rows = np.asarray(case_rows(case, alls[0].shape[0]), dtype=np.int64)
+    out["all_rows"] = rows
+    out["all_embeds"] = torch.stack(alls, dim=0)[:, rows].numpy()
+    return out
+
+
+def case_rows(case, M):
+    """Row subset of the all-entity table stored in the golden file (all rows when M is small)."""
+    if M <= 512:
+        return list(range(M))
+    return sorted(set(range(0, M, 29)) | set(range(0, 64)))
+
+
+def run_sampler_case(case):
+    """Negative-sample index streams of the reference's CorruptTriples under fixed seeds
+    (utils/CorrptTriples.py:26-85) -- the bit-exact contract of SURVEY section 8(a) row N."""
+    from utils.CorrptTriples import CorruptTriples
+    args = ref_args(dict(case, module="GRRGCN", D=8, n_bases=8, L=2, rec_only_last_layer=True,
+                         use_time_embedding=True, t_list=case["times"]))
+    num_e, num_r, gtr, _, _ = ref_graph_dicts(args)
+    cor = CorruptTriples(args, gtr)
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    out = {}
+    for t in case["times"]:
+        tri, nt, nh, lab = cor.single_graph_negative_sampling(torch.tensor(t), gtr[t], num_e)
+        out["triples_%d" % t] = tri.numpy()
+        out["neg_tail_%d" % t] = nt.numpy()
+        out["neg_head_%d" % t] = nh.numpy()
+    return out
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    reference_on_path()
+    for case in CASES:
+        res = run_case(case)
+        path = os.path.join(HERE, case["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print("%-40s rows=%d  %.1f KB" % (case["name"], res["per_graph"].shape[0], os.path.getsize(path) / 1024))
+    for case in SAMPLER_CASES:
+        res = run_sampler_case(case)
+        path = os.path.join(HERE, case["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print("%-40s %.1f KB" % (case["name"], os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,43 @@
+"""Shared test plumbing: rebuild a golden case's inputs for the oracle (and for the CUDA path)."""
+import functools
+import os
+
+import numpy as np
+
+from oracle import temp_oracle as orc
+from tests.golden.cases import CASES, SAMPLER_CASES, dataset_path
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASE_BY_NAME = {c["name"]: c for c in CASES}
+
+
+@functools.lru_cache(maxsize=None)
+def oracle_graphs(dataset):
+    path = dataset_path(dataset)
+    m, r = orc.read_stat(path)
+    train, valid, test = orc.build_graph_dicts(path)
+    return m, r, train, valid, test
+
+
+def oracle_config(case):
+    m, r, train, _, _ = oracle_graphs(case["dataset"])
+    return orc.OracleConfig(module=case["module"], num_ents=m, num_rels=r, num_times=len(train),
+                            embed_size=case["D"], n_bases=case["n_bases"], seq_len=case["L"],
+                            rec_only_last_layer=case["rec_only_last_layer"],
+                            use_time_embedding=True if case["module"].endswith("SARGCN") else case["use_time_embedding"],
+                            type1=case.get("type1", False), learnable_lambda=case.get("learnable_lambda", False))
+
+
+def oracle_model(case):
+    cfg = oracle_config(case)
+    _, _, train, _, _ = oracle_graphs(case["dataset"])
+    return orc.OracleModel(cfg, orc.make_params(cfg), train)
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

@@ -1,0 +1,77 @@
+"""CPU: pins the oracle (oracle/temp_oracle.py) to outputs of the reference itself
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import temp_oracle as orc
+from tests.golden.cases import CASES, SAMPLER_CASES
+from tests.helpers import load_golden, oracle_graphs, oracle_model, rel_err
+
+# same torch CPU kernels on both sides; only the op grouping differs slightly
+TOL = 2e-6
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_forward_matches_reference(case):
+    gold = load_golden(case["name"])
+    model = oracle_model(case)
+    with torch.no_grad():
+        res = model.evaluate_embed(case["t_list"])
+        assert res["times"] == gold["times"].tolist()
+        assert [p.shape[0] for p in res["per_graph"]] == gold["sizes"].tolist()
+        got = torch.cat(res["per_graph"], dim=0).numpy()
+        assert rel_err(got, gold["per_graph"]) < TOL
+        rows = gold["all_rows"]
+        alls = np.stack([model.all_embeds(res, i).numpy()[rows] for i in range(len(res["times"]))])
+        assert rel_err(alls, gold["all_embeds"]) < TOL
+        if "start" in gold:
+            assert np.array_equal(res["start"].numpy(), gold["start"])
+            assert rel_err(res["hist"].abs().sum(dim=(2, 3)).numpy(), gold["hist_abs_sum"]) < 1e-5
+            assert np.array_equal((res["hist"].abs().sum(-1) != 0).sum(-1).numpy(), gold["hist_rows_nonzero"])
+        if "start_f" in gold:
+            assert np.array_equal(res["start_f"].numpy(), gold["start_f"])
+            assert np.array_equal(res["start_b"].numpy(), gold["start_b"])
+
+
+@pytest.mark.parametrize("case", SAMPLER_CASES, ids=[c["name"] for c in SAMPLER_CASES])
+def test_negative_sampler_bit_exact(case):
+    gold = load_golden(case["name"])
+    m, _, train, _, _ = oracle_graphs(case["dataset"])
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    for t in case["times"]:
+        tri, nt, nh, lab = orc.negative_samples(train[t], m, case["negative_rate"], case["num_pos_facts"])
+        assert np.array_equal(tri, gold["triples_%d" % t])
+        assert np.array_equal(nt, gold["neg_tail_%d" % t])
+        assert np.array_equal(nh, gold["neg_head_%d" % t])
+        assert lab.shape[0] == tri.shape[0] and not lab.any()
+
+
+def test_gru_closed_form_is_torch_gru():
+    """the closed form used by the oracle equals torch.nn.GRU (1 layer, seq 1)."""
+    torch.manual_seed(0)
+    D, N = 32, 17
+    gru = torch.nn.GRU(D, D, 1)
+    cfg = orc.OracleConfig(embed_size=D)
+    p = {"x." + k: v.detach() for k, v in gru.state_dict().items()}
+    x, h0 = torch.randn(N, D), torch.randn(N, D)
+    with torch.no_grad():
+        want = gru(x.unsqueeze(0), h0.unsqueeze(0))[1][-1]
+        got = orc.gru_step(p, "x.", cfg, x, h0)
+    assert rel_err(got.numpy(), want.numpy()) < 1e-6
+
+
+def test_hand_computed_micro_graph():
+    """3 nodes, edges 0->2 (rel 0), 1->2 (rel 1), 2->2 dup x2 (rel 0), node 0/1 have in-degree 0:
+    agg_2 = (1/4)^2 * sum(msg), agg_0 = agg_1 = 0 (norm applied twice)."""
+    D = 4
+    h = torch.arange(12, dtype=torch.float32).view(3, D) + 1
+    W = torch.tensor([[1., 2., 3., 4.], [0.5, 0.5, 0.5, 0.5]])
+    src = torch.tensor([0, 1, 2, 2]); dst = torch.tensor([2, 2, 2, 2]); rel = torch.tensor([0, 1, 0, 0])
+    norm = torch.from_numpy(orc.in_degree_norm(dst.numpy(), 3))
+    assert norm.tolist() == [0.0, 0.0, 0.25]
+    agg = orc.rgcn_aggregate(W, D, h, src, dst, rel, norm)
+    want2 = (h[0] * W[0] + h[1] * W[1] + 2 * h[2] * W[0]) / 16.0
+    assert torch.equal(agg[0], torch.zeros(D)) and torch.equal(agg[1], torch.zeros(D))
+    assert torch.allclose(agg[2], want2, rtol=1e-6)
