@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: edges/sec through the RGCN+GRU forward (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at N=1 (BASELINE.json configs[1]): GRRGCN (--rec-only-last-layer --use-time-embedding, torch GRU
+cell), ICEWS14-shaped synthetic snapshot sequence (SURVEY.md section 8d generator), train_seq_len 8,
+batch_size 8 target timestamps, embed=hidden=128, n_bases=128, fp32.  A "step" is one forward of
+region R1 (what ``evaluate_embed`` computes: 7 history steps + the final step -> per-graph
+final-layer entity states) over one batch of 8 windows = 64 snapshot instances.
+
+  value : device-resident inputs; per-step CUDA events on the launching stream, L2 flushed between steps
+  e2e   : the same forward through the public API with HOST buffers: the packed plan is copied
+          from pinned host memory, the final states are read back to pinned host memory, host wall clock
+          around each step (stream-synchronised); window planning is pre-built, as the reference
+          pre-builds its graph dictionaries -- its cost per step is reported separately as plan_ms
+  N > 1 : one process per GPU (torchrun); every rank runs its own batch of windows (weak scaling, the
+          reference's DistributedSampler sharding of target timestamps) and the step ends with an NCCL
+          all-gather of the final-layer states of all ranks; value = edges of all ranks / max time.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(module="GRRGCN", shape="icews14", seq_len=8, batch=8, D=128, n_bases=128, num_times=40)
+SEED = 20201116 + 1          # default_rng(20201116 + config_index), config index 1
+
+
+def make_args(module="GRRGCN"):
+    from argparse import Namespace
+    return Namespace(module=module, embed_size=WORKLOAD["D"], hidden_size=WORKLOAD["D"], n_bases=WORKLOAD["n_bases"],
+                     train_seq_len=WORKLOAD["seq_len"], test_seq_len=WORKLOAD["seq_len"], dropout=0.1, num_layers=1,
+                     lr=1e-3, rec_only_last_layer=True, use_time_embedding=True, inv_temperature=0.1, type1=False,
+                     learnable_lambda=False, score_function="complex", negative_rate=500, num_pos_facts=3000,
+                     use_cuda=True, impute=False, post_ensemble=False, post_aggregation=False)
+
+
+def batches(store, n_batches, rank=0):
+    """Deterministic batches of 8 consecutive target timestamps with full-length windows."""
+    L, B = WORKLOAD["seq_len"], WORKLOAD["batch"]
+    times = store.times
+    out = []
+    lo = L - 1
+    span = len(times) - lo - B + 1
+    for k in range(n_batches):
+        start = lo + (k * 5 + rank * 3) % max(span, 1)
+        out.append([times[start + j] for j in range(B)])
+    return out
+
+
+def oracle_model_for(store, model_state):
+    """The CPU oracle on the SAME snapshots and parameters (test infrastructure; cpu_baseline leg only)."""
+    from oracle import temp_oracle as orc
+    cfg = orc.OracleConfig(module=WORKLOAD["module"], num_ents=store.num_ents, num_rels=store.num_rels,
+                           num_times=len(store.times), embed_size=WORKLOAD["D"], n_bases=WORKLOAD["n_bases"],
+                           seq_len=WORKLOAD["seq_len"], rec_only_last_layer=True, use_time_embedding=True)
+    gd = {t: orc.SnapGraph(ids=g.node_ids, src=g.src, dst=g.dst, rel=g.rel, norm=g.norm, time=t)
+          for t, g in store.train.items()}
+    params = {k: v.detach().float().cpu() for k, v in model_state.items()}
+    return orc.OracleModel(cfg, params, gd)
+
+
+def init_state(store):
+    """Random-init parameters of the architecture (reference initialisers), torch.manual_seed(123)."""
+    import torch
+    from temp_b200.models import build_module
+    torch.manual_seed(123)
+    model = build_module(make_args(), store.num_ents, store.num_rels, store.train)
+    return model
+
+
+def cpu_baseline(store, state, t_lists, budget_s=12.0, threads=None):
+    import torch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    oracle = oracle_model_for(store, state)
+    edges = []
+    with torch.no_grad():
+        oracle.evaluate_embed(t_lists[0])                      # warm-up
+        t_used, n, i = 0.0, 0, 0
+        while t_used < budget_s and n < 200:
+            tl = t_lists[i % len(t_lists)]
+            t0 = time.perf_counter()
+            res = oracle.evaluate_embed(tl)
+            t_used += time.perf_counter() - t0
+            n += 1
+            i += 1
+            edges.append(count_edges(store, tl))
+    return dict(value=float(sum(edges) / t_used), unit="edges/s", cores=int(threads), kind="port",
+                sample="%d forwards of the bench workload (B=8 windows, L=8) in %.1f s, torch CPU fp32, "
+                       "dense-history orchestration kept" % (n, t_used)), t_used / n
+
+
+def count_edges(store, t_list):
+    from temp_b200.planner import plan_window
+    return plan_window(store.train, t_list, WORKLOAD["seq_len"]).E
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (DGL 0.4.1 /
+    pytorch-lightning 0.5.2 are not installable here, so the reference itself cannot travel), all host
+    threads, same config / metric / unit."""
+    if rank != 0:
+        return
+    from temp_b200.snapshot import SnapshotStore
+    store = SnapshotStore.synthetic(WORKLOAD["shape"], num_times=WORKLOAD["num_times"], scale=1, seed=SEED)
+    model = init_state(store)
+    t_lists = batches(store, 8)
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    oracle = oracle_model_for(store, model.state_dict())
+    with torch.no_grad():
+        for w in range(max(args.warmup, 1)):
+            oracle.evaluate_embed(t_lists[w % len(t_lists)])
+        steps = min(args.steps, 60)              # bounded sample: each step is one full forward of the workload
+        edges, t0 = 0, time.perf_counter()
+        for k in range(steps):
+            tl = t_lists[k % len(t_lists)]
+            oracle.evaluate_embed(tl)
+            edges += count_edges(store, tl)
+        dt = time.perf_counter() - t0
+    val = edges / dt
+    line = {"impl": "reference", "metric": "edges_per_sec_rgcn_gru_forward", "value": val, "unit": "edges/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bench_config(1),
+            "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port",
+                             "sample": "%d forwards (oracle port of the reference's DGL-CPU path; the reference "
+                                       "needs dgl==0.4.1 + pytorch_lightning==0.5.2, not installable)" % steps},
+            "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def bench_config(world):
+    return {"workload": "GRRGCN rec-only-last-layer + time-embedding, ICEWS14-shaped synthetic x1, seq_len=8, "
+                        "batch=8 windows (64 snapshot instances), D=128, n_bases=128, region R1 (evaluate_embed)",
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": "dp%d over target timestamps" % world,
+            "seed": SEED}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from temp_b200 import lib
+    from temp_b200.snapshot import SnapshotStore
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    store = SnapshotStore.synthetic(WORKLOAD["shape"], num_times=WORKLOAD["num_times"], scale=1, seed=SEED + 1000 * rank)
+    model = init_state(store).to(dev).eval()
+    rt = model.runtime
+    t_lists = batches(store, 8, rank)
+    t0 = time.perf_counter()
+    plans = [model.plan(tl) for tl in t_lists]
+    plan_ms = 1e3 * (time.perf_counter() - t0) / len(plans)
+
+    # one program per distinct batch; separate workspaces would only change addresses, so programs are
+    # rebuilt (cheap) per step group: build all, each with its own plan blob
+    results = []
+    for i, p in enumerate(plans):
+        prog = lib.Program()
+        dptr = rt.stage_plan(p, prog, tag="plan%d" % i)
+        h2d = prog.ops[0]
+        prog.ops = []
+        res = rt._build_recurrent(p, prog, dptr)
+        nf = p.final.row1 - p.final.row0
+        host_out = torch.empty(nf, WORKLOAD["D"], dtype=torch.float32, pin_memory=True)
+        d2h = lib.Op()
+        d2h.kind = lib.OP_D2H
+        d2h.u.copy = lib.CopyArgs(host_out.data_ptr(), res.out.data_ptr(), nf * WORKLOAD["D"] * 4)
+        e2e_prog = lib.Program()
+        e2e_prog.ops = [h2d] + list(res.program.ops) + [d2h]
+        e2e_prog.keepalive = list(res.program.keepalive) + [host_out]
+        # make the plan resident for the device-timed arm
+        up = lib.Program()
+        up.ops = [h2d]
+        up.run()
+        results.append((res, e2e_prog, host_out, h2d.u.copy.bytes, nf * WORKLOAD["D"] * 4))
+    torch.cuda.synchronize()
+
+    # all-gather buffer of the final-layer states (N > 1)
+    if world > 1:
+        max_rows = max(r[0].plan.final.row1 - r[0].plan.final.row0 for r in results)
+        rows_t = torch.tensor([max_rows], device=dev)
+        dist.all_reduce(rows_t, op=dist.ReduceOp.MAX)
+        max_rows = int(rows_t.item())
+        send = torch.zeros(max_rows, WORKLOAD["D"], device=dev)
+        recv = torch.empty(world * max_rows, WORKLOAD["D"], device=dev)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step_device(i):
+        res = results[i % len(results)][0]
+        res.program.run()
+        if world > 1:
+            nf = res.out.shape[0]
+            send[:nf].copy_(res.out)
+            dist.all_gather_into_tensor(recv, send)
+
+    def step_e2e(i):
+        results[i % len(results)][1].run()
+        if world > 1:
+            res = results[i % len(results)][0]
+            nf = res.out.shape[0]
+            send[:nf].copy_(res.out)
+            dist.all_gather_into_tensor(recv, send)
+
+    for i in range(W):
+        step_device(i)
+        step_e2e(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-timed arm -----------------------------------------------------------------------
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(float(i))
+        starts[i].record()
+        step_device(i)
+        ends[i].record()
+    torch.cuda.synchronize()
+    wall_dev = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    edges_local = sum(results[i % len(results)][0].plan.E for i in range(K))
+    launches = sum(results[i % len(results)][0].program.count() for i in range(K))
+
+    # ---- e2e arm (host buffers, copies inside the timed region) ----------------------------------
+    e2e_s = 0.0
+    for i in range(K):
+        flush.fill_(float(i))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e(i)
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+
+    # ---- dominant kernel, timed alone with CUDA events on its stream (roofline) ------------------
+    res0 = results[0][0]
+    layer_ops = [o for o in res0.program.ops if o.kind == lib.OP_LAYER]
+    dom = lib.Program()
+    dom.ops = [layer_ops[-1]]                 # layer-2 aggregation + self loop + GRU input gates, all rows
+    reps = 50
+    ks = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+    ke = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+    for i in range(reps):
+        flush.fill_(1.0)
+        ks[i].record()
+        dom.run()
+        ke[i].record()
+    torch.cuda.synchronize()
+    dom_ms = float(np.median([s.elapsed_time(e) for s, e in zip(ks, ke)]))
+    D = WORKLOAD["D"]
+    p0 = res0.plan
+    w_bytes = 4 * (model.ent_encoder.layer_2.weight.numel() + D * D + D * 3 * D + 3 * D)
+    dom_bytes = p0.R * (4 * D + 12 * D + 12) + 8 * p0.E + w_bytes   # read h1, write gi, row_ptr/norm/..., edges, weights
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    step_bytes = 2588 * p0.R + 16 * p0.E + 900000               # SURVEY section 8d whole-forward figure
+
+    # ---- reduce over ranks ------------------------------------------------------------------------
+    tot_edges, max_dev_ms, max_e2e = float(edges_local), dev_ms, e2e_s
+    if world > 1:
+        t = torch.tensor([float(edges_local)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        tot_edges = float(t.item())
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_dev_ms, max_e2e = float(t[0].item()), float(t[1].item())
+
+    if rank == 0:
+        line = {
+            "metric": "edges_per_sec_rgcn_gru_forward", "value": tot_edges / (max_dev_ms * 1e-3), "unit": "edges/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_dev_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(world),
+            "e2e": {"value": tot_edges / max_e2e, "unit": "edges/s", "h2d_bytes_per_step": int(results[0][3]),
+                    "d2h_bytes_per_step": int(results[0][4]), "ms_per_step": 1e3 * max_e2e / K,
+                    "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms},
+            "gpu_launches": int(launches),
+            "launches_per_step": results[0][0].program.count(),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "rgcn_layer_kernel (layer-2 aggregation + self loop + GRU input gates)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "algorithmic_bytes": int(dom_bytes), "kernel_ms": dom_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "note": "x1 shapes are L2-resident and FFMA/latency bound; see roofline_scaled",
+                         "whole_step": {"algorithmic_bytes": int(step_bytes),
+                                        "achieved": step_bytes / (max_dev_ms / K * 1e-3) / 1e9, "unit": "GB/s"}},
+            "rows_per_step": int(p0.R), "edges_per_step": int(p0.E),
+            "wall_s_device_arm": wall_dev,
+        }
+        if args.scaled and world == 1:
+            try:
+                line["roofline_scaled"] = scaled_roofline(args.scaled, dev, peak)
+            except Exception as ex:      # never lose the headline line
+                line["roofline_scaled"] = {"error": repr(ex)}
+        if not args.no_cpu_baseline and world == 1:
+            base, _ = cpu_baseline(store, model.state_dict(), t_lists)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def scaled_roofline(scale, dev, peak):
+    """Same workload with M, N_t, E_t multiplied by ``scale``: the working set exceeds the 126 MB L2, which is
+    where an HBM roofline fraction is meaningful."""
+    import torch
+    from temp_b200 import lib
+    from temp_b200.snapshot import SnapshotStore
+    store = SnapshotStore.synthetic(WORKLOAD["shape"], num_times=16, scale=scale, seed=SEED)
+    model = init_state(store).to(dev).eval()
+    tl = batches(store, 1)[0]
+    res = model.encode(tl)
+    torch.cuda.synchronize()
+    out = {"scale": scale, "rows": int(res.plan.R), "edges": int(res.plan.E)}
+    prog = lib.Program()
+    prog.ops = [o for o in res.program.ops if o.kind != lib.OP_H2D]
+    reps = 10
+    s = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+    for i in range(reps):
+        s[i].record()
+        prog.run()
+        e[i].record()
+    torch.cuda.synchronize()
+    ms = float(np.median([a.elapsed_time(b) for a, b in zip(s, e)]))
+    out["forward_ms"] = ms
+    out["edges_per_s"] = res.plan.E / (ms * 1e-3)
+    step_bytes = 2588 * res.plan.R + 16 * res.plan.E + 900000
+    out["whole_step"] = {"algorithmic_bytes": int(step_bytes), "achieved": step_bytes / (ms * 1e-3) / 1e9,
+                         "frac": step_bytes / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s"}
+    layer_ops = [o for o in prog.ops if o.kind == lib.OP_LAYER]
+    D = WORKLOAD["D"]
+    for name, op, nbytes in (("layer1", layer_ops[0], res.plan.R * (8 * D + 12) + 8 * res.plan.E),
+                             ("layer2_gi", layer_ops[-1], res.plan.R * (16 * D + 12) + 8 * res.plan.E)):
+        one = lib.Program()
+        one.ops = [op]
+        for i in range(reps):
+            s[i].record()
+            one.run()
+            e[i].record()
+        torch.cuda.synchronize()
+        kms = float(np.median([a.elapsed_time(b) for a, b in zip(s, e)]))
+        out[name] = {"kernel_ms": kms, "algorithmic_bytes": int(nbytes), "achieved": nbytes / (kms * 1e-3) / 1e9,
+                     "frac": nbytes / (kms * 1e-3) / 1e9 / peak, "unit": "GB/s"}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,200 @@
+/*
+ * temp_b200 -- C ABI of the B200-native RGCN + GRU/BiGRU/attention forward path of TeMP.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * Every entry point replaces a call the reference makes into third-party native code
+ * (DGL 0.4.1 libdgl, cuBLAS, cuDNN) -- the reference line each one stands in for is cited on it.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer;
+ *   - all floating point is fp32, all indices int32;
+ *   - kernels are enqueued on the cudaStream_t passed in (as void*), never synchronise, never
+ *     allocate; no global mutable state other than the thread-local last-error string;
+ *   - every function returns TEMP_OK (0) or a negative TEMP_E* code; no exception crosses the ABI.
+ *
+ * "packed rows": the nodes of all snapshot instances of a window batch are laid out back to back,
+ * step-major (temp_b200/planner.py); a row index addresses one (instance, node).
+ */
+#ifndef TEMP_B200_H_
+#define TEMP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEMP_ABI_VERSION 3
+
+#define TEMP_OK 0
+#define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
+#define TEMP_ECUDA (-2)    /* a CUDA runtime call / launch failed; see last error     */
+#define TEMP_EUNSUPPORTED (-3)
+
+#define TEMP_MAX_D 256     /* embed_size == hidden_size upper bound of the SIMT path  */
+#define TEMP_MAX_TERMS 3
+
+#define TEMP_ACT_NONE 0
+#define TEMP_ACT_RELU 1
+
+#define TEMP_CELL_TORCH_GRU 0 /* torch.nn.GRU equations, reference models/RRGCN.py:75,84      */
+#define TEMP_CELL_TYPE1 1     /* reference models/GRU_cell.py:18-31 (--type1)                 */
+
+/* One dense term  acc += scale_row(A[gather(row)]) . W   of the fused layer kernel.
+ *   a        [*, d]   source rows
+ *   a_index  nullable: source row of packed row r is a[a_index[r]]; a negative index is a zero row.
+ *            When null the source row is r itself.
+ *   a_dt     nullable: per-row time gap; the gathered row is multiplied by
+ *              exp(-a_dt[r] * inv_temperature)                     (decay_wb == null)
+ *              exp(-max(decay_wb[0] * a_dt[r] + decay_wb[1], 0))   (learnable lambda)
+ *            reference models/RRGCN.py:83, models/RGCN.py:106-107.
+ *   w        [d, d] row-major (in x out), e.g. loop_weight / time_weight as stored.            */
+typedef struct {
+  const float* a;
+  const int32_t* a_index;
+  const float* a_dt;
+  const float* decay_wb;
+  const float* w;
+} TempDenseTerm;
+
+/* Fused RGCN layer over packed rows [row0, row1):
+ *   agg_v  = norm_v * sum_{e: dst_e = v} norm_v * blockdiag(W[rel_e]) . x[src_e]      (RGCN.py:91-104)
+ *   out_v  = act( agg_v (or x_v when residual) + sum_t term_t(v) + h_bias )           (RGCN.py:53-70, 78-86)
+ *   h_out  = out_v (+ time_embed[row_time[v]] if te_out)                              (RGCN.py:47-51, RRGCN.py:202-203)
+ *   chain  = (out_v (+ te if te_chain)) . chain_w + chain_b                           (input half of the GRU:
+ *            RRGCN.py:84 gi = x W_ih^T + b_ih; attention q/k/v: SARGCN.py:30-32)
+ * Replaces: torch index_select + bmm + DGL update_all/fn.sum/apply (RGCN.py:92-104), torch.mm self
+ * loop (RGCN.py:57), and the input GEMM of torch.nn.GRU.                                       */
+typedef struct {
+  int32_t row0, row1;
+  int32_t d;                 /* feature width (in == out)                                        */
+  /* graph part (row_ptr == null: no aggregation, e.g. forward_isolated)                         */
+  const int32_t* row_ptr;    /* [rows+1] CSR by destination over packed rows (absolute offsets)  */
+  const int32_t* e_src;      /* [E] feature row of the edge source inside x                       */
+  const int32_t* e_rel;      /* [E]                                                               */
+  const float* norm;         /* [rows] 1/in_degree (0 when in_degree is 0)                        */
+  const float* x;            /* [*, d] source features for the aggregation                        */
+  const float* weight;       /* [2*num_rels, n_bases*si*so] block-diagonal relation weights        */
+  int32_t n_bases, si, so;
+  int32_t residual;          /* 1: acc starts from the row's own term-0 input (RGCN.py:83)        */
+  int32_t n_terms;
+  TempDenseTerm terms[TEMP_MAX_TERMS];
+  const float* h_bias;       /* nullable [d]                                                      */
+  int32_t activation;
+  const float* time_embed;   /* nullable [T, d]                                                   */
+  const int32_t* row_time;   /* [rows] time_embed row per packed row (needed when te_* set)       */
+  int32_t row_time_scalar;   /* used instead of row_time when row_time == null (isolated pass)    */
+  int32_t te_out, te_chain;
+  float* h_out;              /* nullable [rows, d]                                                */
+  const float* chain_w;      /* nullable [d, chain_n] row-major (i.e. W_ih transposed)            */
+  const float* chain_b;      /* nullable [chain_n]                                                */
+  float* chain_out;          /* [rows, chain_ld]; columns [0, chain_n) are written                */
+  int32_t chain_n, chain_ld;
+  float inv_temperature;
+} TempRgcnLayerArgs;
+
+/* Recurrent half of the GRU for packed rows [row0, row1), fused with the gates:
+ *   h0 = decay(state[prev_row[r]])  (zero when prev_row[r] < 0)                       (RRGCN.py:79-83)
+ *   gh = h0 . whh_t + b_hh ; gates with gi (precomputed by the layer kernel's chain)   (Appendix A.3)
+ *   out[r] (+)= h' (+ time_embed[row_time[r]])                                        (RRGCN.py:85, 202-203)
+ * Replaces torch.nn.GRU / cuDNN RNN forward (RRGCN.py:84, BiRRGCN.py:34-43) and models/GRU_cell.py. */
+typedef struct {
+  int32_t row0, row1;
+  int32_t d;
+  const float* gi;           /* [rows, gi_ld]; this cell's input pre-activations start at gi_off   */
+  int32_t gi_ld, gi_off;
+  const float* state;        /* [*, d] rows addressed by prev_row                                 */
+  const int32_t* prev_row;   /* [rows] or null (no previous state at all)                         */
+  const float* dt;           /* [rows] nullable                                                   */
+  const float* decay_wb;     /* nullable (learnable lambda: weight, bias)                         */
+  float inv_temperature;
+  const float* whh_t;        /* [d, 3d] row-major = weight_hh transposed                          */
+  const float* b_hh;         /* [3d]                                                              */
+  int32_t cell_type;
+  const float* time_embed;   /* nullable                                                          */
+  const int32_t* row_time;
+  int32_t row_time_scalar;
+  int32_t accumulate;        /* 1: out += h' (second direction of the Bi centre step)             */
+  float* out;                /* [rows, d]                                                         */
+  int32_t out_index_is_row;  /* reserved, must be 1                                               */
+} TempGruArgs;
+
+/* Multi-head attention over the time axis for packed rows [row0, row1) (SARGCN.py:25-53):
+ *   q, k_cur, v_cur = qkv[r, 0:d], [d:2d], [2d:3d]; history slot s of row r lives at
+ *   kv_hist[slot_row[r*n_slots + s]] (k | v), negative = entity inactive (mask -1e10 -> weight 0);
+ *   out[r, j*heads + head] = softmax_s(q.k_s / sqrt(dk) - decay_s) . v_s          (Appendix A.5)     */
+typedef struct {
+  int32_t row0, row1;
+  int32_t d, heads;
+  const float* qkv;          /* [rows, 3d]                                                        */
+  const float* kv_hist;      /* [*, 2d]                                                           */
+  const int32_t* slot_row;   /* [rows, n_slots]                                                   */
+  int32_t n_slots;
+  const float* tau;          /* [n_slots + 1] slot ages (last = current slot)                     */
+  const float* decay_wb;     /* nullable                                                          */
+  int32_t combine_max;       /* 1: out = max(out, result) (JK max over layers, SARGCN.py:117)     */
+  float* out;                /* [rows, d]                                                         */
+} TempAttnArgs;
+
+/* out[i] = table[index[i]] rows, or zero rows for negative indices. */
+typedef struct {
+  int32_t n, d;
+  const float* table;
+  const int32_t* index;
+  float* out;
+} TempGatherArgs;
+
+/* dst[index[i]] = src[i]  (scatter of active rows into the all-entity table, DynamicRGCN.py:62-63;
+ * optional "+ te_row" broadcast used by the zero-history de-duplication of the isolated pass).     */
+typedef struct {
+  int32_t n, d;
+  const float* src;
+  const int32_t* src_index;  /* nullable: read src[src_index[i]]                                   */
+  const int32_t* dst_index;  /* nullable: write dst[i]                                             */
+  const float* add_row;      /* nullable [d] added to every written row                            */
+  float* dst;
+} TempScatterArgs;
+
+enum { TEMP_OP_LAYER = 1, TEMP_OP_GRU = 2, TEMP_OP_ATTN = 3, TEMP_OP_GATHER = 4, TEMP_OP_SCATTER = 5,
+       TEMP_OP_MEMCPY_H2D = 6, TEMP_OP_MEMCPY_D2H = 7 };
+
+typedef struct {
+  void* dst;
+  const void* src;
+  uint64_t bytes;
+} TempCopyArgs;
+
+/* One entry of a launch program (a static work list built once per window plan). */
+typedef struct {
+  int32_t kind;
+  int32_t reserved;
+  union {
+    TempRgcnLayerArgs layer;
+    TempGruArgs gru;
+    TempAttnArgs attn;
+    TempGatherArgs gather;
+    TempScatterArgs scatter;
+    TempCopyArgs copy;
+  } u;
+} TempOp;
+
+int temp_abi_version(void);
+const char* temp_last_error_string(void);
+/* sm count, max dynamic shared memory per block, compute capability (major*10+minor) */
+int temp_device_info(int32_t* sm_count, int32_t* max_smem, int32_t* cc);
+
+int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream);
+int temp_gru_fwd(const TempGruArgs* args, void* stream);
+int temp_attention_fwd(const TempAttnArgs* args, void* stream);
+int temp_gather_rows(const TempGatherArgs* args, void* stream);
+int temp_scatter_rows(const TempScatterArgs* args, void* stream);
+/* out[c, r] = in[r, c]  (weight preparation: weight_ih / weight_hh / q,k,v -> K-major-first)     */
+int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream);
+/* Runs ops[0..n) back to back on one stream (memcpy ops use cudaMemcpyAsync; host pointers must be
+ * pinned for the copies to be asynchronous).  Returns the first failure.                          */
+int temp_run_program(const TempOp* ops_host, int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEMP_B200_H_ */

@@ -1,0 +1,755 @@
+// temp_b200 -- sm_100a kernels + C ABI for the TeMP RGCN + GRU/BiGRU/attention forward.
+//
+// FP32 SIMT path (exact fp32 FFMA arithmetic, deterministic summation order).  See DESIGN.md for
+// the data layout and the per-kernel roofline; include/temp_b200.h for the ABI contract and the
+// reference call sites each entry point replaces.
+//
+//   rgcn_layer_kernel : CSR-by-destination gather with the block-diagonal relation projection
+//                       applied in registers  ->  self-loop / recurrent dense terms (smem-tiled
+//                       GEMM, cp.async double-buffered weights)  ->  bias / activation / time
+//                       embedding epilogue  ->  chained GEMM (GRU input gates or attention q|k|v)
+//   gru_kernel        : h0 = decay(prev state gather); gh = h0 . W_hh^T; gates; state write
+//   attn_kernel       : per-entity multi-head attention over the time slots (online softmax)
+#include "temp_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTM = 64;    // packed rows per CTA in the layer kernel
+constexpr int kNC = 128;   // output columns per accumulation pass
+constexpr int kKC = 32;    // weight rows per cp.async stage
+constexpr int kGJ = 32;    // hidden columns per CTA in the GRU kernel
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return TEMP_ECUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// exp(-dt * inv_temperature)  or  exp(-max(w * dt + b, 0))   (RRGCN.py:83 / RGCN.py:106-107)
+__device__ __forceinline__ float decay_factor(float dt, const float* wb, float inv_temperature) {
+  if (wb != nullptr) return expf(-fmaxf(fmaf(__ldg(wb), dt, __ldg(wb + 1)), 0.f));
+  return expf(-dt * inv_temperature);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Stage kKC x kNC weights  W[k0 + kk][col0 + c]  into ws (row-major [kKC][kNC]); zero outside.
+__device__ __forceinline__ void stage_weights(float* ws, const float* __restrict__ w, int ldw, int K, int N,
+                                              int k0, int col0) {
+#pragma unroll
+  for (int q = 0; q < (kKC * kNC / 4) / kThreads; ++q) {
+    const int idx = threadIdx.x + q * kThreads;
+    const int kk = idx / (kNC / 4);
+    const int c4 = idx % (kNC / 4);
+    const int k = k0 + kk;
+    const int col = col0 + c4 * 4;
+    float* dst = ws + kk * kNC + c4 * 4;
+    if (k < K && col < N) {
+      cp_async16(dst, w + static_cast<size_t>(k) * ldw + col);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// acc[i][0..3] += As[ty*8 + i][0..K) . W[0..K)[col0 + tx*4 .. +3]      (K padded to Kp in smem)
+__device__ __forceinline__ void gemm_accumulate(float4 (&acc)[8], const float* __restrict__ As, int lda, int Kp,
+                                                float* Ws, const float* __restrict__ w, int ldw, int K, int N,
+                                                int col0) {
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  const int nk = Kp / kKC;
+  int buf = 0;
+  stage_weights(Ws, w, ldw, K, N, 0, col0);
+  cp_async_commit();
+  for (int kc = 0; kc < nk; ++kc) {
+    if (kc + 1 < nk) stage_weights(Ws + (buf ^ 1) * (kKC * kNC), w, ldw, K, N, (kc + 1) * kKC, col0);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* wsb = Ws + buf * (kKC * kNC) + tx * 4;
+    const float* asb = As + (ty * 8) * lda + kc * kKC;
+#pragma unroll
+    for (int kk = 0; kk < kKC; kk += 4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(asb + i * lda + kk);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = *reinterpret_cast<const float4*>(wsb + (kk + q) * kNC);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = q == 0 ? a[i].x : (q == 1 ? a[i].y : (q == 2 ? a[i].z : a[i].w));
+          acc[i].x = fmaf(av, wv.x, acc[i].x);
+          acc[i].y = fmaf(av, wv.y, acc[i].y);
+          acc[i].z = fmaf(av, wv.z, acc[i].z);
+          acc[i].w = fmaf(av, wv.w, acc[i].w);
+        }
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused RGCN layer
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) rgcn_layer_kernel(const TempRgcnLayerArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.d;
+  const int Kp = (D + kKC - 1) / kKC * kKC;
+  const int lda = Kp + 4;
+  const bool has_chain = p.chain_w != nullptr;
+  float* As = smem;
+  float* Xs = As + kTM * lda;
+  float* Ws = has_chain ? Xs + kTM * lda : Xs;
+
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  const int rbase = p.row0 + blockIdx.x * kTM;
+  const int nvec = D >> 2;
+
+  // zero the K padding columns once (loads below only touch columns < D)
+  if (Kp > D) {
+    const int padw = Kp - D;
+    for (int idx = threadIdx.x; idx < kTM * padw; idx += kThreads) {
+      const int m = idx / padw, c = D + idx % padw;
+      As[m * lda + c] = 0.f;
+      if (has_chain) Xs[m * lda + c] = 0.f;
+    }
+  }
+
+  const int n_chunks = (D + kNC - 1) / kNC;
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int c = chunk * kNC + tx * 4;  // this lane's first output column
+    float4 acc[8];
+
+    // ---- 1. aggregation: one warp per destination row, lanes across channels ----------------
+    if (p.row_ptr != nullptr) {
+      const bool diag = (p.si == 1 && p.so == 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // unrolled: acc[] must stay in registers
+        const int r = rbase + ty * 8 + i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < p.row1 && c < D) {
+          const int p0 = __ldg(p.row_ptr + r), p1 = __ldg(p.row_ptr + r + 1);
+          const float nrm = __ldg(p.norm + r);
+          if (diag) {
+            for (int e = p0; e < p1; e += 4) {
+              int s[4], rl[4];
+              float4 hv[4], wv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int ee = min(e + u, p1 - 1);
+                s[u] = __ldg(p.e_src + ee);
+                rl[u] = __ldg(p.e_rel + ee);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                hv[u] = ldg4(p.x + static_cast<size_t>(s[u]) * D + c);
+                wv[u] = ldg4(p.weight + static_cast<size_t>(rl[u]) * D + c);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (e + u < p1) {  // msg = (h * w) * norm_e, summed in edge order (RGCN.py:92-97)
+                  a.x += (hv[u].x * wv[u].x) * nrm;
+                  a.y += (hv[u].y * wv[u].y) * nrm;
+                  a.z += (hv[u].z * wv[u].z) * nrm;
+                  a.w += (hv[u].w * wv[u].w) * nrm;
+                }
+              }
+            }
+          } else {
+            const int si = p.si, so = p.so;
+            const int wrow = p.n_bases * si * so;
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int e = p0; e < p1; ++e) {
+              const float* hs = p.x + static_cast<size_t>(__ldg(p.e_src + e)) * D;
+              const float* wr = p.weight + static_cast<size_t>(__ldg(p.e_rel + e)) * wrow;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int co = c + q;
+                const int b = co / so, j = co - b * so;
+                float m = 0.f;
+                for (int ii = 0; ii < si; ++ii)
+                  m = fmaf(__ldg(hs + b * si + ii), __ldg(wr + (b * si + ii) * so + j), m);
+                av[q] += m * nrm;
+              }
+            }
+            a = make_float4(av[0], av[1], av[2], av[3]);
+          }
+          a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;  // apply_func (RGCN.py:103-104)
+        }
+        acc[i] = a;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // ---- 2. dense terms: self loop, recurrent projections -------------------------------------
+    for (int t = 0; t < p.n_terms; ++t) {
+      const TempDenseTerm& tm = p.terms[t];
+      __syncthreads();  // previous readers of As are done
+      for (int idx = threadIdx.x; idx < kTM * nvec; idx += kThreads) {
+        const int m = idx / nvec, c4 = idx - m * nvec;
+        const int r = rbase + m;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < p.row1) {
+          const int srow = tm.a_index != nullptr ? __ldg(tm.a_index + r) : r;
+          if (srow >= 0) {
+            v = ldg4(tm.a + static_cast<size_t>(srow) * D + c4 * 4);
+            if (tm.a_dt != nullptr) {
+              const float f = decay_factor(__ldg(tm.a_dt + r), tm.decay_wb, p.inv_temperature);
+              v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(As + m * lda + c4 * 4) = v;
+      }
+      __syncthreads();
+      if (t == 0 && p.residual && c < D) {  // forward_isolated: x + x.W_loop (RGCN.py:83)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(As + (ty * 8 + i) * lda + c);
+          acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+        }
+      }
+      gemm_accumulate(acc, As, lda, Kp, Ws, tm.w, D, D, D, chunk * kNC);
+    }
+
+    // ---- 3. epilogue ------------------------------------------------------------------------
+    if (c < D) {
+      float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.h_bias != nullptr) bias = ldg4(p.h_bias + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = ty * 8 + i;
+        const int r = rbase + m;
+        if (r >= p.row1) continue;
+        float4 v = acc[i];
+        v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+        if (p.activation == TEMP_ACT_RELU) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        float4 te = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.te_out || p.te_chain) {
+          const int trow = p.row_time != nullptr ? __ldg(p.row_time + r) : p.row_time_scalar;
+          te = ldg4(p.time_embed + static_cast<size_t>(trow) * D + c);
+        }
+        if (p.h_out != nullptr) {
+          float4 o = v;
+          if (p.te_out) { o.x += te.x; o.y += te.y; o.z += te.z; o.w += te.w; }
+          *reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(r) * D + c) = o;
+        }
+        if (has_chain) {
+          float4 o = v;
+          if (p.te_chain) { o.x += te.x; o.y += te.y; o.z += te.z; o.w += te.w; }
+          *reinterpret_cast<float4*>(Xs + m * lda + c) = o;
+        }
+      }
+    } else if (has_chain) {
+      // rows past row1 never get written above; keep chain input finite
+    }
+  }
+
+  // ---- 4. chained GEMM on the tile that is still in shared memory ------------------------------
+  if (has_chain) {
+    // rows >= row1 of Xs were never written: zero them so the FMAs stay finite
+    for (int idx = threadIdx.x; idx < kTM * nvec; idx += kThreads) {
+      const int m = idx / nvec, c4 = idx - m * nvec;
+      if (rbase + m >= p.row1) *reinterpret_cast<float4*>(Xs + m * lda + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int NCn = p.chain_n;
+    const int chunks2 = (NCn + kNC - 1) / kNC;
+    for (int ch = 0; ch < chunks2; ++ch) {
+      const int c = ch * kNC + tx * 4;
+      float4 acc[8];
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.chain_b != nullptr && c < NCn) b = ldg4(p.chain_b + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = b;
+      gemm_accumulate(acc, Xs, lda, Kp, Ws, p.chain_w, NCn, D, NCn, ch * kNC);
+      if (c < NCn) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rbase + ty * 8 + i;
+          if (r < p.row1) *reinterpret_cast<float4*>(p.chain_out + static_cast<size_t>(r) * p.chain_ld + c) = acc[i];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU recurrent half + gates.  CTA = (RPW*8 rows) x (kGJ hidden columns, all three gates)
+// ------------------------------------------------------------------------------------------------
+template <int RPW>
+__global__ void __launch_bounds__(kThreads, 2) gru_kernel(const TempGruArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TM = RPW * 8;
+  const int D = p.d;
+  const int lda = D + 4;
+  float* As = smem;             // [TM][lda]   decayed previous state rows
+  float* Ws = As + TM * lda;    // [D][3*kGJ]  this CTA's slice of W_hh^T
+
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  const int rbase = p.row0 + blockIdx.x * TM;
+  const int jb = blockIdx.y * kGJ;
+  const int nvec = D >> 2;
+
+  int any_prev = 0;
+  for (int idx = threadIdx.x; idx < TM * nvec; idx += kThreads) {
+    const int m = idx / nvec, c4 = idx - m * nvec;
+    const int r = rbase + m;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < p.row1 && p.prev_row != nullptr) {
+      const int pr = __ldg(p.prev_row + r);
+      if (pr >= 0) {
+        any_prev = 1;
+        v = ldg4(p.state + static_cast<size_t>(pr) * D + c4 * 4);
+        if (p.dt != nullptr) {
+          const float f = decay_factor(__ldg(p.dt + r), p.decay_wb, p.inv_temperature);
+          v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(As + m * lda + c4 * 4) = v;
+  }
+  any_prev = __syncthreads_or(any_prev);
+
+  float acc[RPW][3];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+
+  if (any_prev) {
+    const int per_k = 3 * kGJ / 4;  // float4 per k row
+    for (int idx = threadIdx.x; idx < D * per_k; idx += kThreads) {
+      const int k = idx / per_k, v = idx - k * per_k;
+      const int g = v / (kGJ / 4), c4 = v - g * (kGJ / 4);
+      const int col = jb + c4 * 4;
+      float* dst = Ws + k * (3 * kGJ) + g * kGJ + c4 * 4;
+      if (col < D) cp_async16(dst, p.whh_t + static_cast<size_t>(k) * (3 * D) + g * D + col);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const float* asb = As + (ty * RPW) * lda;
+    const float* wsb = Ws + tx;
+#pragma unroll 2
+    for (int k = 0; k < D; k += 4) {
+      float4 a[RPW];
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) a[i] = *reinterpret_cast<const float4*>(asb + i * lda + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float w0 = wsb[(k + q) * (3 * kGJ)];
+        const float w1 = wsb[(k + q) * (3 * kGJ) + kGJ];
+        const float w2 = wsb[(k + q) * (3 * kGJ) + 2 * kGJ];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const float av = q == 0 ? a[i].x : (q == 1 ? a[i].y : (q == 2 ? a[i].z : a[i].w));
+          acc[i][0] = fmaf(av, w0, acc[i][0]);
+          acc[i][1] = fmaf(av, w1, acc[i][1]);
+          acc[i][2] = fmaf(av, w2, acc[i][2]);
+        }
+      }
+    }
+  }
+
+  const int j = jb + tx;
+  if (j < D) {
+    const float br = __ldg(p.b_hh + j), bz = __ldg(p.b_hh + D + j), bn = __ldg(p.b_hh + 2 * D + j);
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int m = ty * RPW + i;
+      const int r = rbase + m;
+      if (r >= p.row1) continue;
+      const float h0 = As[m * lda + j];
+      const float hr = acc[i][0] + br, hz = acc[i][1] + bz, hn = acc[i][2] + bn;
+      const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off;
+      float hy;
+      if (p.cell_type == TEMP_CELL_TYPE1) {  // GRU_cell.py:22-29
+        const float rg = sigmoidf_(hr), zg = sigmoidf_(hz);
+        const float ng = tanhf(__ldg(gi + j) + rg * hn);
+        hy = ng + zg * (h0 - ng);
+      } else {  // torch.nn.GRU, gate order r, z, n
+        const float rg = sigmoidf_(__ldg(gi + j) + hr);
+        const float zg = sigmoidf_(__ldg(gi + D + j) + hz);
+        const float ng = tanhf(__ldg(gi + 2 * D + j) + rg * hn);
+        hy = (1.f - zg) * ng + zg * h0;
+      }
+      if (p.time_embed != nullptr) {
+        const int trow = p.row_time != nullptr ? __ldg(p.row_time + r) : p.row_time_scalar;
+        hy += __ldg(p.time_embed + static_cast<size_t>(trow) * D + j);
+      }
+      float* o = p.out + static_cast<size_t>(r) * D + j;
+      *o = p.accumulate ? (*o + hy) : hy;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention over time slots: one warp per packed row, 32/heads lanes per head
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnMaxT = 16;  // channels per lane: dk / lanes_per_head
+
+__global__ void __launch_bounds__(kThreads) attn_kernel(const TempAttnArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int r = p.row0 + blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (r >= p.row1) return;
+  const int D = p.d, H = p.heads;
+  const int dk = D / H;
+  const int lph = 32 / H;  // lanes per head
+  const int head = lane / lph, sub = lane - head * lph;
+  const int nt = (dk - sub + lph - 1) / lph;  // channels j = sub + lph*t < dk
+  const float inv_sqrt = 1.f / sqrtf(static_cast<float>(dk));
+
+  const float* qrow = p.qkv + static_cast<size_t>(r) * 3 * D;
+  float q[kAttnMaxT], o[kAttnMaxT];
+#pragma unroll
+  for (int t = 0; t < kAttnMaxT; ++t) {
+    q[t] = t < nt ? __ldg(qrow + head * dk + sub + lph * t) : 0.f;
+    o[t] = 0.f;
+  }
+  float mx = -INFINITY, den = 0.f;
+  for (int s = 0; s <= p.n_slots; ++s) {
+    const float* kp;
+    const float* vp;
+    if (s < p.n_slots) {
+      const int hr = __ldg(p.slot_row + static_cast<size_t>(r) * p.n_slots + s);
+      if (hr < 0) continue;  // inactive slot: mask -1e10 -> softmax weight exactly 0 (SARGCN.py:50)
+      kp = p.kv_hist + static_cast<size_t>(hr) * 2 * D;
+      vp = kp + D;
+    } else {
+      kp = qrow + D;
+      vp = qrow + 2 * D;
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int t = 0; t < kAttnMaxT; ++t)
+      if (t < nt) part = fmaf(q[t], __ldg(kp + head * dk + sub + lph * t), part);
+    for (int off = lph >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    float sc = part * inv_sqrt;
+    if (p.decay_wb != nullptr) sc -= fmaxf(fmaf(__ldg(p.decay_wb), __ldg(p.tau + s), __ldg(p.decay_wb + 1)), 0.f);
+    const float mnew = fmaxf(mx, sc);
+    const float scale = expf(mx - mnew);  // exp(-inf) = 0 on the first slot
+    const float w = expf(sc - mnew);
+    den = den * scale + w;
+#pragma unroll
+    for (int t = 0; t < kAttnMaxT; ++t)
+      if (t < nt) o[t] = fmaf(w, __ldg(vp + head * dk + sub + lph * t), o[t] * scale);
+    mx = mnew;
+  }
+  const float inv = 1.f / den;
+  float* orow = p.out + static_cast<size_t>(r) * D;
+#pragma unroll
+  for (int t = 0; t < kAttnMaxT; ++t) {
+    if (t < nt) {
+      const int j = sub + lph * t;
+      float v = o[t] * inv;
+      float* dst = orow + j * H + head;  // [d_k major, head minor]
+      if (p.combine_max) v = fmaxf(v, *dst);
+      *dst = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small data-movement kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const TempGatherArgs p) {
+  const int nvec = p.d >> 2;
+  const size_t total = static_cast<size_t>(p.n) * nvec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx / nvec), c4 = static_cast<int>(idx - static_cast<size_t>(i) * nvec);
+    const int s = __ldg(p.index + i);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s >= 0) v = ldg4(p.table + static_cast<size_t>(s) * p.d + c4 * 4);
+    *reinterpret_cast<float4*>(p.out + static_cast<size_t>(i) * p.d + c4 * 4) = v;
+  }
+}
+
+__global__ void scatter_rows_kernel(const TempScatterArgs p) {
+  const int nvec = p.d >> 2;
+  const size_t total = static_cast<size_t>(p.n) * nvec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx / nvec), c4 = static_cast<int>(idx - static_cast<size_t>(i) * nvec);
+    const int s = p.src_index != nullptr ? __ldg(p.src_index + i) : i;
+    const int t = p.dst_index != nullptr ? __ldg(p.dst_index + i) : i;
+    if (s < 0 || t < 0) continue;
+    float4 v = ldg4(p.src + static_cast<size_t>(s) * p.d + c4 * 4);
+    if (p.add_row != nullptr) {
+      const float4 a = ldg4(p.add_row + c4 * 4);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(p.dst + static_cast<size_t>(t) * p.d + c4 * 4) = v;
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out,
+                                 int out_ld) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = by + i, c = bx + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = bx + i, r = by + threadIdx.x;
+    if (c < cols && r < rows) out[static_cast<size_t>(c) * out_ld + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_d(int d) {
+  if (d <= 0 || d > TEMP_MAX_D || (d & 3)) return fail(TEMP_EINVAL, "d must be a multiple of 4 in (0, %s%ld]", "", TEMP_MAX_D);
+  return TEMP_OK;
+}
+
+template <int Tag, typename K>
+int ensure_smem(K kernel, size_t bytes, const char* name) {
+  static size_t configured = 0;  // one instance per Tag (= per kernel); one device per process
+  if (bytes <= configured) return TEMP_OK;
+  int dev = 0, lim = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (bytes > static_cast<size_t>(lim)) return fail(TEMP_EUNSUPPORTED, "%s needs %ld B shared memory", name, static_cast<long>(bytes));
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  configured = bytes;
+  return TEMP_OK;
+}
+
+int launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
+  if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
+  if (int rc = check_d(a->d)) return rc;
+  const int rows = a->row1 - a->row0;
+  if (rows < 0) return fail(TEMP_EINVAL, "row1 < row0%s", "");
+  if (rows == 0) return TEMP_OK;
+  if (a->n_terms < 0 || a->n_terms > TEMP_MAX_TERMS) return fail(TEMP_EINVAL, "n_terms out of range%s", "");
+  if (a->row_ptr != nullptr) {
+    if (!a->e_src || !a->e_rel || !a->norm || !a->x || !a->weight) return fail(TEMP_EINVAL, "graph part has null pointers%s", "");
+    if (a->n_bases <= 0 || a->si <= 0 || a->so <= 0 || a->n_bases * a->so != a->d || a->n_bases * a->si != a->d)
+      return fail(TEMP_EINVAL, "n_bases*si and n_bases*so must equal d%s", "");
+    if (!aligned16(a->x) || !aligned16(a->weight)) return fail(TEMP_EINVAL, "x / weight must be 16-byte aligned%s", "");
+  }
+  for (int t = 0; t < a->n_terms; ++t) {
+    if (!a->terms[t].a || !a->terms[t].w) return fail(TEMP_EINVAL, "dense term %s%ld has null pointers", "", t);
+    if (!aligned16(a->terms[t].a) || !aligned16(a->terms[t].w)) return fail(TEMP_EINVAL, "dense term %s%ld misaligned", "", t);
+  }
+  if (a->residual && a->n_terms == 0) return fail(TEMP_EINVAL, "residual needs term 0%s", "");
+  if ((a->te_out || a->te_chain) && a->time_embed == nullptr) return fail(TEMP_EINVAL, "time_embed is null%s", "");
+  if (a->chain_w != nullptr) {
+    if (a->chain_out == nullptr || a->chain_n <= 0 || (a->chain_n & 3) || a->chain_ld < a->chain_n || (a->chain_ld & 3))
+      return fail(TEMP_EINVAL, "bad chain output%s", "");
+    if (!aligned16(a->chain_w) || !aligned16(a->chain_out)) return fail(TEMP_EINVAL, "chain buffers misaligned%s", "");
+  } else if (a->h_out == nullptr) {
+    return fail(TEMP_EINVAL, "layer has no output%s", "");
+  }
+  if (a->h_out != nullptr && !aligned16(a->h_out)) return fail(TEMP_EINVAL, "h_out misaligned%s", "");
+  const int Kp = (a->d + kKC - 1) / kKC * kKC;
+  const size_t smem = (static_cast<size_t>(kTM) * (Kp + 4) * (a->chain_w ? 2 : 1) + 2 * kKC * kNC) * sizeof(float);
+  if (int rc = ensure_smem<0>(rgcn_layer_kernel, smem, "rgcn_layer_kernel")) return rc;
+  const int grid = (rows + kTM - 1) / kTM;
+  rgcn_layer_kernel<<<grid, kThreads, smem, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_kernel launch");
+  return TEMP_OK;
+}
+
+int launch_gru(const TempGruArgs* a, cudaStream_t st) {
+  if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
+  if (int rc = check_d(a->d)) return rc;
+  const int rows = a->row1 - a->row0;
+  if (rows < 0) return fail(TEMP_EINVAL, "row1 < row0%s", "");
+  if (rows == 0) return TEMP_OK;
+  if (!a->gi || !a->whh_t || !a->b_hh || !a->out) return fail(TEMP_EINVAL, "gru has null pointers%s", "");
+  if (a->prev_row != nullptr && a->state == nullptr) return fail(TEMP_EINVAL, "prev_row without state%s", "");
+  if (!aligned16(a->whh_t) || (a->state && !aligned16(a->state))) return fail(TEMP_EINVAL, "gru buffers misaligned%s", "");
+  if (a->cell_type != TEMP_CELL_TORCH_GRU && a->cell_type != TEMP_CELL_TYPE1) return fail(TEMP_EINVAL, "bad cell_type%s", "");
+  const int jblocks = (a->d + kGJ - 1) / kGJ;
+  cudaError_t e;
+  // small steps: 32-row tiles so that the step still spreads over all SMs
+  if (rows <= 148 * 32) {
+    const size_t smem = (static_cast<size_t>(32) * (a->d + 4) + static_cast<size_t>(a->d) * 3 * kGJ) * sizeof(float);
+    if (int rc = ensure_smem<1>(gru_kernel<4>, smem, "gru_kernel<4>")) return rc;
+    dim3 grid((rows + 31) / 32, jblocks);
+    gru_kernel<4><<<grid, kThreads, smem, st>>>(*a);
+  } else {
+    const size_t smem = (static_cast<size_t>(64) * (a->d + 4) + static_cast<size_t>(a->d) * 3 * kGJ) * sizeof(float);
+    if (int rc = ensure_smem<2>(gru_kernel<8>, smem, "gru_kernel<8>")) return rc;
+    dim3 grid((rows + 63) / 64, jblocks);
+    gru_kernel<8><<<grid, kThreads, smem, st>>>(*a);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gru_kernel launch");
+  return TEMP_OK;
+}
+
+int launch_attn(const TempAttnArgs* a, cudaStream_t st) {
+  if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
+  if (int rc = check_d(a->d)) return rc;
+  const int rows = a->row1 - a->row0;
+  if (rows < 0) return fail(TEMP_EINVAL, "row1 < row0%s", "");
+  if (rows == 0) return TEMP_OK;
+  if (a->heads <= 0 || 32 % a->heads != 0 || a->d % a->heads != 0) return fail(TEMP_EINVAL, "heads must divide 32 and d%s", "");
+  const int dk = a->d / a->heads, lph = 32 / a->heads;
+  if ((dk + lph - 1) / lph > kAttnMaxT) return fail(TEMP_EUNSUPPORTED, "head dim too large%s", "");
+  if (!a->qkv || !a->out || a->n_slots < 0) return fail(TEMP_EINVAL, "attention has null pointers%s", "");
+  if (a->n_slots > 0 && (!a->kv_hist || !a->slot_row)) return fail(TEMP_EINVAL, "attention history is null%s", "");
+  if (a->decay_wb != nullptr && a->tau == nullptr) return fail(TEMP_EINVAL, "decay without tau%s", "");
+  const int rows_per_cta = kThreads / 32;
+  attn_kernel<<<(rows + rows_per_cta - 1) / rows_per_cta, kThreads, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "attn_kernel launch");
+  return TEMP_OK;
+}
+
+int grid_for(size_t work_items) {
+  size_t g = (work_items + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  return static_cast<int>(g == 0 ? 1 : g);
+}
+
+int launch_gather(const TempGatherArgs* a, cudaStream_t st) {
+  if (a == nullptr || a->n < 0) return fail(TEMP_EINVAL, "bad gather args%s", "");
+  if (a->n == 0) return TEMP_OK;
+  if (a->d <= 0 || (a->d & 3)) return fail(TEMP_EINVAL, "gather width must be a positive multiple of 4%s", "");
+  if (!a->table || !a->index || !a->out) return fail(TEMP_EINVAL, "gather has null pointers%s", "");
+  gather_rows_kernel<<<grid_for(static_cast<size_t>(a->n) * (a->d / 4)), 256, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gather_rows_kernel launch");
+  return TEMP_OK;
+}
+
+int launch_scatter(const TempScatterArgs* a, cudaStream_t st) {
+  if (a == nullptr || a->n < 0) return fail(TEMP_EINVAL, "bad scatter args%s", "");
+  if (a->n == 0) return TEMP_OK;
+  if (a->d <= 0 || (a->d & 3)) return fail(TEMP_EINVAL, "scatter width must be a positive multiple of 4%s", "");
+  if (!a->src || !a->dst) return fail(TEMP_EINVAL, "scatter has null pointers%s", "");
+  scatter_rows_kernel<<<grid_for(static_cast<size_t>(a->n) * (a->d / 4)), 256, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "scatter_rows_kernel launch");
+  return TEMP_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int temp_abi_version(void) { return TEMP_ABI_VERSION; }
+
+const char* temp_last_error_string(void) { return g_err; }
+
+int temp_device_info(int32_t* sm_count, int32_t* max_smem, int32_t* cc) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  int sm = 0, smem = 0, major = 0, minor = 0;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (sm_count) *sm_count = sm;
+  if (max_smem) *max_smem = smem;
+  if (cc) *cc = major * 10 + minor;
+  return TEMP_OK;
+}
+
+int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream) {
+  return launch_layer(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_gru_fwd(const TempGruArgs* args, void* stream) { return launch_gru(args, static_cast<cudaStream_t>(stream)); }
+
+int temp_attention_fwd(const TempAttnArgs* args, void* stream) {
+  return launch_attn(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_gather_rows(const TempGatherArgs* args, void* stream) {
+  return launch_gather(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_scatter_rows(const TempScatterArgs* args, void* stream) {
+  return launch_scatter(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream) {
+  if (!in || !out || rows <= 0 || cols <= 0 || out_ld < rows) return fail(TEMP_EINVAL, "bad transpose args%s", "");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, rows, cols, out, out_ld);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
+  return TEMP_OK;
+}
+
+int temp_run_program(const TempOp* ops, int32_t n, void* stream) {
+  if (ops == nullptr || n < 0) return fail(TEMP_EINVAL, "bad program%s", "");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n; ++i) {
+    int rc = TEMP_OK;
+    switch (ops[i].kind) {
+      case TEMP_OP_LAYER: rc = launch_layer(&ops[i].u.layer, st); break;
+      case TEMP_OP_GRU: rc = launch_gru(&ops[i].u.gru, st); break;
+      case TEMP_OP_ATTN: rc = launch_attn(&ops[i].u.attn, st); break;
+      case TEMP_OP_GATHER: rc = launch_gather(&ops[i].u.gather, st); break;
+      case TEMP_OP_SCATTER: rc = launch_scatter(&ops[i].u.scatter, st); break;
+      case TEMP_OP_MEMCPY_H2D:
+      case TEMP_OP_MEMCPY_D2H: {
+        if (ops[i].u.copy.bytes == 0) break;
+        cudaError_t e = cudaMemcpyAsync(ops[i].u.copy.dst, ops[i].u.copy.src, ops[i].u.copy.bytes,
+                                        ops[i].kind == TEMP_OP_MEMCPY_H2D ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync");
+        break;
+      }
+      default: rc = fail(TEMP_EINVAL, "unknown op kind at index %s%ld", "", i);
+    }
+    if (rc != TEMP_OK) return rc;
+  }
+  return TEMP_OK;
+}
+
+}  // extern "C"

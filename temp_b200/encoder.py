@@ -1,0 +1,157 @@
+"""Parameter containers of the encoder, named exactly like the reference's modules so that
+``state_dict`` keys match (checkpoint compatibility):
+
+  ent_encoder.layer_{1,2}.{time_embed, weight, loop_weight[, h_bias][, exponential_decay.*]}
+  GRRGCN   : layer_k.rnn.{weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0}   (torch.nn.GRU)
+             layer_k.rnn.{weight_ih, weight_hh, bias_ih, bias_hh}               (--type1, GRU_cell.py)
+  BiGRRGCN : layer_k.{forward_rnn, backward_rnn}.*
+  RRGCN    : layer_k.time_weight         BiRRGCN: layer_k.time_weight_{forward, backward}
+  SARGCN   : layer_k.{q_linear, v_linear, k_linear}.weight
+
+These classes only OWN parameters (initialised like the reference: models/RGCN.py:15-44,
+models/RRGCN.py:64-75, 120-128, models/BiRRGCN.py:9-25, 102-113, models/SARGCN.py:10-23,
+models/GRU_cell.py:7-15).  The arithmetic is done by the CUDA kernels of libtemp_b200.so, driven by
+the launch programs built in temp_b200/models.py -- none of these modules has a torch forward.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+_GAIN = nn.init.calculate_gain("relu")
+
+
+class GRUCell(nn.Module):
+    """Parameters of the ``--type1`` cell (reference models/GRU_cell.py:7-15)."""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.weight_ih = nn.Parameter(torch.randn(hidden_size, input_size))
+        self.weight_hh = nn.Parameter(torch.randn(3 * hidden_size, hidden_size))
+        self.bias_ih = nn.Parameter(torch.randn(hidden_size))
+        self.bias_hh = nn.Parameter(torch.randn(3 * hidden_size))
+
+
+def _rnn(args, in_feat, out_feat):
+    if getattr(args, "type1", False):
+        return GRUCell(in_feat, out_feat)
+    return nn.GRU(input_size=in_feat, hidden_size=out_feat, num_layers=getattr(args, "num_layers", 1))
+
+
+class RGCNLayer(nn.Module):
+    def __init__(self, args, in_feat, out_feat, num_rels, num_bases, total_times, bias=True, activation=None,
+                 self_loop=False, dropout=0.0):
+        super().__init__()
+        assert num_bases > 0
+        self.bias, self.activation, self.self_loop = bool(bias), activation, self_loop
+        self.num_rels, self.num_bases = num_rels, num_bases
+        self.in_feat, self.out_feat = in_feat, out_feat
+        self.submat_in, self.submat_out = in_feat // num_bases, out_feat // num_bases
+        self.time_embed = nn.Parameter(torch.empty(len(total_times), in_feat))
+        nn.init.xavier_uniform_(self.time_embed, gain=_GAIN)
+        self.weight = nn.Parameter(torch.empty(num_rels, num_bases * self.submat_in * self.submat_out))
+        nn.init.xavier_uniform_(self.weight, gain=_GAIN)
+        if self.bias:
+            self.h_bias = nn.Parameter(torch.zeros(out_feat))
+        if self.self_loop:
+            self.loop_weight = nn.Parameter(torch.empty(in_feat, out_feat))
+            nn.init.xavier_uniform_(self.loop_weight, gain=_GAIN)
+        self.dropout_p = float(dropout or 0.0)
+        self.inv_temperature = args.inv_temperature
+        self.learnable_lambda = bool(getattr(args, "learnable_lambda", False))
+        if self.learnable_lambda:
+            self.exponential_decay = nn.Linear(1, 1)
+
+
+class GRRGCNLayer(RGCNLayer):
+    def __init__(self, args, in_feat, out_feat, *a, **k):
+        super().__init__(args, in_feat, out_feat, *a, **k)
+        self.rnn = _rnn(args, in_feat, out_feat)
+
+
+class RRGCNLayer(RGCNLayer):
+    def __init__(self, args, in_feat, out_feat, *a, **k):
+        super().__init__(args, in_feat, out_feat, *a, **k)
+        self.time_weight = nn.Parameter(torch.empty(in_feat, out_feat))
+        nn.init.xavier_uniform_(self.time_weight, gain=_GAIN)
+
+
+class BiGRRGCNLayer(RGCNLayer):
+    def __init__(self, args, in_feat, out_feat, *a, **k):
+        super().__init__(args, in_feat, out_feat, *a, **k)
+        self.forward_rnn = _rnn(args, in_feat, out_feat)
+        self.backward_rnn = _rnn(args, in_feat, out_feat)
+
+
+class BiRRGCNLayer(RGCNLayer):
+    def __init__(self, args, in_feat, out_feat, *a, **k):
+        super().__init__(args, in_feat, out_feat, *a, **k)
+        self.time_weight_forward = nn.Parameter(torch.empty(in_feat, out_feat))
+        nn.init.xavier_uniform_(self.time_weight_forward, gain=_GAIN)
+        self.time_weight_backward = nn.Parameter(torch.empty(in_feat, out_feat))
+        nn.init.xavier_uniform_(self.time_weight_backward, gain=_GAIN)
+
+
+class SARGCNLayer(RGCNLayer):
+    def __init__(self, args, in_feat, out_feat, *a, **k):
+        super().__init__(args, in_feat, out_feat, *a, **k)
+        self.q_linear = nn.Linear(in_feat, in_feat, bias=False)
+        self.v_linear = nn.Linear(in_feat, in_feat, bias=False)
+        self.k_linear = nn.Linear(in_feat, in_feat, bias=False)
+        self.h = 8
+        self.d_k = in_feat // self.h
+
+
+class _TwoLayer(nn.Module):
+    def __init__(self, args, l1_cls, l2_cls, hidden_size, embed_size, num_rels, total_times, bias, act2):
+        super().__init__()
+        self.rec_only_last_layer = bool(args.rec_only_last_layer)
+        self.use_time_embedding = bool(args.use_time_embedding)
+        kw = dict(bias=bias, self_loop=True, dropout=args.dropout)
+        self.layer_1 = l1_cls(args, embed_size, hidden_size, 2 * num_rels, args.n_bases, total_times,
+                              activation=None, **kw)
+        self.layer_2 = l2_cls(args, hidden_size, hidden_size, 2 * num_rels, args.n_bases, total_times,
+                              activation=act2, **kw)
+
+
+class RGCN(_TwoLayer):
+    """models/RGCN.py:145-152 (static encoder of SRGCN)."""
+
+    def __init__(self, args, hidden_size, embed_size, num_rels, total_times):
+        args.rec_only_last_layer = getattr(args, "rec_only_last_layer", False)
+        super().__init__(args, RGCNLayer, RGCNLayer, hidden_size, embed_size, num_rels, total_times, True, "relu")
+
+
+class RRGCN(_TwoLayer):
+    """models/RRGCN.py:170-190."""
+
+    def __init__(self, args, hidden_size, embed_size, num_rels, total_times):
+        rec = {"GRRGCN": GRRGCNLayer, "RRGCN": RRGCNLayer}[args.module]
+        l1 = RGCNLayer if args.rec_only_last_layer else rec
+        super().__init__(args, l1, rec, hidden_size, embed_size, num_rels, total_times, False, None)
+        self.impute = bool(getattr(args, "impute", False))
+        if self.impute:
+            self.impute_weight = nn.Linear(1, 1)
+
+
+class BiRRGCN(_TwoLayer):
+    """models/BiRRGCN.py:188-208 (layer 2 uses relu, unlike RRGCN)."""
+
+    def __init__(self, args, hidden_size, embed_size, num_rels, total_times):
+        rec = {"BiGRRGCN": BiGRRGCNLayer, "BiRRGCN": BiRRGCNLayer}[args.module]
+        l1 = RGCNLayer if args.rec_only_last_layer else rec
+        super().__init__(args, l1, rec, hidden_size, embed_size, num_rels, total_times, False, "relu")
+        self.impute = bool(getattr(args, "impute", False))
+        if self.impute:
+            self.impute_weight_forward = nn.Linear(1, 1)
+            self.impute_weight_backward = nn.Linear(1, 1)
+
+
+class SARGCN(_TwoLayer):
+    """models/SARGCN.py:86-101 (forces use_time_embedding, line 92)."""
+
+    def __init__(self, args, hidden_size, embed_size, num_rels, total_time):
+        args.use_time_embedding = True
+        l1 = RGCNLayer if args.rec_only_last_layer else SARGCNLayer
+        super().__init__(args, l1, SARGCNLayer, hidden_size, embed_size, num_rels, total_time, True, "relu")

@@ -1,0 +1,178 @@
+"""ctypes binding of libtemp_b200.so (the C ABI declared in include/temp_b200.h).
+
+This is the thin layer BASELINE.json's north star prescribes: PyTorch tensors in, PyTorch tensors
+out, raw device pointers across the boundary.  There is NO fallback: if the shared library is
+missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
+
+ABI_VERSION = 3
+MAX_TERMS = 3
+ACT_NONE, ACT_RELU = 0, 1
+CELL_TORCH_GRU, CELL_TYPE1 = 0, 1
+OP_LAYER, OP_GRU, OP_ATTN, OP_GATHER, OP_SCATTER, OP_H2D, OP_D2H = 1, 2, 3, 4, 5, 6, 7
+
+_i32 = C.c_int32
+_p = C.c_void_p
+
+
+class DenseTerm(C.Structure):
+    _fields_ = [("a", _p), ("a_index", _p), ("a_dt", _p), ("decay_wb", _p), ("w", _p)]
+
+
+class RgcnLayerArgs(C.Structure):
+    _fields_ = [
+        ("row0", _i32), ("row1", _i32), ("d", _i32),
+        ("row_ptr", _p), ("e_src", _p), ("e_rel", _p), ("norm", _p), ("x", _p), ("weight", _p),
+        ("n_bases", _i32), ("si", _i32), ("so", _i32), ("residual", _i32), ("n_terms", _i32),
+        ("terms", DenseTerm * MAX_TERMS),
+        ("h_bias", _p), ("activation", _i32),
+        ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32), ("te_out", _i32), ("te_chain", _i32),
+        ("h_out", _p), ("chain_w", _p), ("chain_b", _p), ("chain_out", _p), ("chain_n", _i32), ("chain_ld", _i32),
+        ("inv_temperature", C.c_float),
+    ]
+
+
+class GruArgs(C.Structure):
+    _fields_ = [
+        ("row0", _i32), ("row1", _i32), ("d", _i32),
+        ("gi", _p), ("gi_ld", _i32), ("gi_off", _i32),
+        ("state", _p), ("prev_row", _p), ("dt", _p), ("decay_wb", _p), ("inv_temperature", C.c_float),
+        ("whh_t", _p), ("b_hh", _p), ("cell_type", _i32),
+        ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32),
+        ("accumulate", _i32), ("out", _p), ("out_index_is_row", _i32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("row0", _i32), ("row1", _i32), ("d", _i32), ("heads", _i32),
+        ("qkv", _p), ("kv_hist", _p), ("slot_row", _p), ("n_slots", _i32),
+        ("tau", _p), ("decay_wb", _p), ("combine_max", _i32), ("out", _p),
+    ]
+
+
+class GatherArgs(C.Structure):
+    _fields_ = [("n", _i32), ("d", _i32), ("table", _p), ("index", _p), ("out", _p)]
+
+
+class ScatterArgs(C.Structure):
+    _fields_ = [("n", _i32), ("d", _i32), ("src", _p), ("src_index", _p), ("dst_index", _p), ("add_row", _p),
+                ("dst", _p)]
+
+
+class CopyArgs(C.Structure):
+    _fields_ = [("dst", _p), ("src", _p), ("bytes", C.c_uint64)]
+
+
+class _OpUnion(C.Union):
+    _fields_ = [("layer", RgcnLayerArgs), ("gru", GruArgs), ("attn", AttnArgs), ("gather", GatherArgs),
+                ("scatter", ScatterArgs), ("copy", CopyArgs)]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", _i32), ("reserved", _i32), ("u", _OpUnion)]
+
+
+EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
+           "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program")
+
+_lib = None
+
+
+def load(path: Optional[str] = None):
+    """Load the shared library (once).  Raises RuntimeError when it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError("temp_b200: %s not found -- build it with `python -m temp_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError("temp_b200: %s does not export %s" % (path, name))
+    lib.temp_abi_version.restype = C.c_int
+    lib.temp_last_error_string.restype = C.c_char_p
+    lib.temp_device_info.argtypes = [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]
+    lib.temp_rgcn_layer_fwd.argtypes = [C.POINTER(RgcnLayerArgs), _p]
+    lib.temp_gru_fwd.argtypes = [C.POINTER(GruArgs), _p]
+    lib.temp_attention_fwd.argtypes = [C.POINTER(AttnArgs), _p]
+    lib.temp_gather_rows.argtypes = [C.POINTER(GatherArgs), _p]
+    lib.temp_scatter_rows.argtypes = [C.POINTER(ScatterArgs), _p]
+    lib.temp_transpose.argtypes = [_p, _i32, _i32, _p, _i32, _p]
+    lib.temp_run_program.argtypes = [C.POINTER(Op), _i32, _p]
+    if lib.temp_abi_version() != ABI_VERSION:
+        raise RuntimeError("temp_b200: ABI version mismatch (library %d, binding %d) -- rebuild"
+                           % (lib.temp_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().temp_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError("temp_b200 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def device_info():
+    sm, smem, cc = _i32(), _i32(), _i32()
+    check(load().temp_device_info(C.byref(sm), C.byref(smem), C.byref(cc)), "temp_device_info")
+    return {"sm_count": sm.value, "max_smem": smem.value, "cc": cc.value}
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, byte_offset: int = 0) -> Optional[int]:
+    """Device (or pinned host) address of a tensor, None for None."""
+    if t is None:
+        return None
+    return t.data_ptr() + byte_offset
+
+
+class Program(object):
+    """A static launch list (TempOp[]) executed by one ``temp_run_program`` call."""
+
+    def __init__(self):
+        self.ops = []
+        self._arr = None
+        self.keepalive = []
+
+    def add(self, kind: int, args) -> None:
+        op = Op()
+        op.kind = kind
+        field = {OP_LAYER: "layer", OP_GRU: "gru", OP_ATTN: "attn", OP_GATHER: "gather", OP_SCATTER: "scatter",
+                 OP_H2D: "copy", OP_D2H: "copy"}[kind]
+        setattr(op.u, field, args)
+        self.ops.append(op)
+        self._arr = None
+
+    def extend(self, other: "Program") -> None:
+        self.ops.extend(other.ops)
+        self.keepalive.extend(other.keepalive)
+        self._arr = None
+
+    def __len__(self):
+        return len(self.ops)
+
+    def count(self, kinds=(OP_LAYER, OP_GRU, OP_ATTN, OP_GATHER, OP_SCATTER)) -> int:
+        return sum(1 for o in self.ops if o.kind in kinds)
+
+    def run(self, stream: Optional[int] = None) -> None:
+        if not self.ops:
+            return
+        if self._arr is None:
+            self._arr = (Op * len(self.ops))(*self.ops)
+        st = current_stream() if stream is None else stream
+        check(load().temp_run_program(self._arr, len(self.ops), _p(st)), "temp_run_program")

@@ -1,0 +1,342 @@
+"""Model shells with the reference's ``TKG_Module`` API (models/TKG_Module.py), backed by the CUDA path.
+
+Constructor and method names follow the reference so that a caller written against
+``module(args, num_ents, num_rels, graph_dict_train, graph_dict_val, graph_dict_test)`` (main.py:82)
+keeps working: ``forward(t_list) -> loss``, ``evaluate(t_list, val) -> (ranks, loss)``,
+``evaluate_embed``, ``train_embed``, ``get_all_embeds_Gt``, ``calc_metrics``, ``train_link_prediction``,
+``link_classification_loss``, ``get_batch_graph_list``, ``ent_embeds`` / ``rel_embeds`` /
+``ent_encoder`` and identical ``state_dict`` keys.  ``graph_dict_*`` are ``time -> Snapshot``
+(temp_b200.snapshot) instead of DGLGraphs.  pytorch-lightning 0.5.2 is not required: the shells are
+plain ``nn.Module``s that also answer the Lightning hook names.
+
+What differs on purpose: no per-step host batching, no dense history tensor on the
+hot path -- ``encode(t_list)`` runs one launch program over a packed window plan.  The dense
+``hist_embeddings`` / ``start_time_tensor`` tensors of the reference API are materialised only when a
+caller asks for them (``evaluate_embed``).
+
+Scope note: the accelerated path is the deterministic forward (eval mode; dropout off, full graphs).
+``forward`` (the training loss) runs the same encoder forward under ``torch.no_grad`` for the
+encoder part; back-propagation through the encoder kernels is not implemented in this round.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import encoder as enc_mod
+from . import lib
+from .planner import WindowPlan, plan_static, plan_window
+from .runtime import EncodeResult, EncoderRuntime
+from .sampler import CorruptTriples
+from .scores import complex_score, distmult, transE
+from .snapshot import Snapshot
+
+_GAIN = nn.init.calculate_gain("relu")
+
+
+def _as_int_list(t_list) -> List[int]:
+    if isinstance(t_list, torch.Tensor):
+        return [int(t) for t in t_list.tolist()]
+    return [int(t) for t in t_list]
+
+
+class TKG_Module(nn.Module):
+    family = "recurrent"
+
+    def __init__(self, args, num_ents, num_rels, graph_dict_train, graph_dict_val=None, graph_dict_test=None,
+                 evaluater_type=None):
+        super().__init__()
+        self.args = self.hparams = args
+        self.graph_dict_train = graph_dict_train
+        self.graph_dict_val = graph_dict_val if graph_dict_val is not None else {}
+        self.graph_dict_test = graph_dict_test if graph_dict_test is not None else {}
+        self.total_time = np.array(list(graph_dict_train.keys()))
+        self.num_rels, self.num_ents = num_rels, num_ents
+        self.embed_size, self.hidden_size = args.embed_size, args.hidden_size
+        if self.embed_size != self.hidden_size:
+            raise ValueError("hidden_size must equal embed_size (the reference's history views require it, "
+                             "models/DynamicRGCN.py:41-48)")
+        if self.embed_size % args.n_bases != 0:
+            raise ValueError("n_bases must divide embed_size (models/RGCN.py:25-26)")
+        self.use_cuda = getattr(args, "use_cuda", True)
+        self.num_pos_facts = getattr(args, "num_pos_facts", 3000)
+        self.negative_rate = getattr(args, "negative_rate", 500)
+        self.train_seq_len = args.train_seq_len
+        self.test_seq_len = args.train_seq_len                      # models/DynamicRGCN.py:17-18
+        self.calc_score = {"distmult": distmult, "complex": complex_score, "transE": transE}[
+            getattr(args, "score_function", "complex")]
+        self.ent_embeds = nn.Parameter(torch.empty(num_ents, self.embed_size))
+        self.rel_embeds = nn.Parameter(torch.empty(num_rels * 2, self.embed_size))
+        nn.init.xavier_uniform_(self.ent_embeds, gain=_GAIN)
+        nn.init.xavier_uniform_(self.rel_embeds, gain=_GAIN)
+        self.build_model()
+        self._runtime: Optional[EncoderRuntime] = None
+        self._corrupter = None
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def build_model(self):
+        raise NotImplementedError
+
+    @property
+    def runtime(self) -> EncoderRuntime:
+        if self._runtime is None or self._runtime.device != self.ent_embeds.device:
+            self._runtime = EncoderRuntime(self)
+        return self._runtime
+
+    @property
+    def corrupter(self) -> CorruptTriples:
+        if self._corrupter is None:
+            self._corrupter = CorruptTriples(self.args, self.graph_dict_train)
+        return self._corrupter
+
+    def plan(self, t_list, seq_len: Optional[int] = None) -> WindowPlan:
+        return plan_window(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len,
+                           bidirectional=self.bidirectional, attention=self.family == "attention")
+
+    bidirectional = False
+
+    def time_diff(self, plan: WindowPlan):
+        L = plan.seq_len
+        if plan.bidirectional:                                        # BiSelfAttentionRGCN.py:19-20
+            return list(range(L - 1, 0, -1)) * 2 + [0.0]
+        return [float(x) for x in range(L - 1, -1, -1)]               # SelfAttentionRGCN.py:22-23
+
+    @torch.no_grad()
+    def encode(self, t_list=None, plan: Optional[WindowPlan] = None) -> EncodeResult:
+        """The hot path (region R1 of SURVEY section 8d): history steps + final step -> per-graph states."""
+        if plan is None:
+            plan = self.plan(t_list)
+        res = self.runtime.build(plan)
+        res.program.run()
+        return res
+
+    # ---- reference API ----------------------------------------------------------------------------
+    def get_batch_graph_list(self, t_list, seq_len, graph_dict):
+        """models/TKG_Module.py:232-250 (kept for callers; the hot path uses the planner instead)."""
+        times = list(graph_dict.keys())
+        order = sorted(_as_int_list(t_list), reverse=True)
+        time_list, g_list = [], []
+        for tim in order:
+            length = times.index(tim) + 1
+            seq = times[length - seq_len:length] if seq_len <= length else times[:length]
+            time_list.append([None] * (seq_len - len(seq)) + list(seq))
+            g_list.append([None] * (seq_len - len(seq)) + [graph_dict[t] for t in seq])
+        return [list(x) for x in zip(*g_list)], [list(x) for x in zip(*time_list)]
+
+    def train_link_prediction(self, ent_embed, triplets, neg_samples, labels, all_embeds_g, corrupt_tail=True):
+        """models/TKG_Module.py:202-213."""
+        r = self.rel_embeds[triplets[:, 1]]
+        if corrupt_tail:
+            s = ent_embed[triplets[:, 0]]
+            score = self.calc_score(s, r, all_embeds_g[neg_samples], mode="tail")
+        else:
+            o = ent_embed[triplets[:, 2]]
+            score = self.calc_score(all_embeds_g[neg_samples], r, o, mode="head")
+        return F.cross_entropy(score, labels)
+
+    def link_classification_loss(self, ent_embed, rel_embeds, triplets, labels):
+        """models/TKG_Module.py:215-223."""
+        s, r, o = ent_embed[triplets[:, 0]], rel_embeds[triplets[:, 1]], ent_embed[triplets[:, 2]]
+        return F.binary_cross_entropy_with_logits(self.calc_score(s, r, o), labels)
+
+    def get_metrics(self, ranks):
+        """models/TKG_Module.py:147-152."""
+        rf = ranks.float()
+        return torch.mean(1.0 / rf), torch.mean((ranks <= 1).float()), torch.mean((ranks <= 3).float()), \
+            torch.mean((ranks <= 10).float())
+
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.parameters(), lr=self.args.lr, weight_decay=0.0001)
+
+    # Lightning hook names (models/TKG_Module.py:43-131) -- thin, trainer-agnostic versions
+    def training_step(self, batch_time, batch_idx=0):
+        loss = self.forward(batch_time)
+        return OrderedDict(loss=loss, progress_bar={"train_loss": loss}, log={"train_loss": loss})
+
+    def validation_step(self, batch_time, batch_idx=0):
+        ranks, loss = self.evaluate(batch_time)
+        return OrderedDict(ranks=ranks, val_loss=loss)
+
+    def test_step(self, batch_time, batch_idx=0):
+        ranks, loss = self.evaluate(batch_time, val=True)
+        return OrderedDict(ranks=ranks, test_loss=loss, batch_time=batch_time)
+
+    def validation_end(self, outputs):
+        mrr, h1, h3, h10 = self.get_metrics(torch.cat([x["ranks"] for x in outputs]))
+        return {"mrr": mrr, "avg_val_loss": np.mean([x["val_loss"] for x in outputs]), "hit_10": h10, "hit_3": h3,
+                "hit_1": h1}
+
+    # ---- all-entity table (region R2) ---------------------------------------------------------------
+    @torch.no_grad()
+    def all_embeds(self, res: EncodeResult, i: int) -> torch.Tensor:
+        """``get_all_embeds_Gt`` for batch item i from the compact window state."""
+        from .isolated import all_embeds_item
+        return all_embeds_item(self, res, i)
+
+    def _targets(self, res: EncodeResult, graph_dict):
+        return [graph_dict[t] for t in res.plan.final_times]
+
+    @torch.no_grad()
+    def forward(self, t_list, reverse=False):
+        """Training loss of the reference (models/DynamicRGCN.py:176-194) on FULL graphs: negative
+        sampling stays host-side and bit-exact; the encoder runs the CUDA forward (no autograd)."""
+        res = self.encode(t_list)
+        dev = self.ent_embeds.device
+        loss = 0
+        for i, (t, g, ent_embed) in enumerate(zip(res.plan.final_times, res.plan.final_snapshots, res.per_graph)):
+            triplets, neg_tail, neg_head, labels = self.corrupter.single_graph_negative_sampling(t, g, self.num_ents)
+            triplets, neg_tail, neg_head, labels = (x.to(dev) for x in (triplets, neg_tail, neg_head, labels))
+            all_g = self.all_embeds(res, i)
+            loss = loss + self.train_link_prediction(ent_embed, triplets, neg_tail, labels, all_g, corrupt_tail=True)
+            loss = loss + self.train_link_prediction(ent_embed, triplets, neg_head, labels, all_g, corrupt_tail=False)
+        return loss
+
+    @torch.no_grad()
+    def evaluate(self, t_list, val=True):
+        """(ranks, mean loss) as models/DynamicRGCN.py:118-130, 196-220 with the filtered ranking of
+        utils/evaluation.py:34-106."""
+        from .evaluation import EvaluationFilter
+        if getattr(self, "evaluater", None) is None:
+            self.evaluater = EvaluationFilter(self.args, self.calc_score, self.graph_dict_train, self.graph_dict_val,
+                                              self.graph_dict_test)
+        res = self.encode(t_list)
+        graph_dict = self.graph_dict_val if val else self.graph_dict_test
+        dev = self.ent_embeds.device
+        ranks, losses = [], []
+        for i, (t, ent_embed) in enumerate(zip(res.plan.final_times, res.per_graph)):
+            g = graph_dict[t]
+            if g.num_edges == 0:
+                continue
+            all_g = self.all_embeds(res, i)
+            src, dst = g.edges()
+            index_sample = torch.stack([src, g.edata["type_s"], dst]).transpose(0, 1).to(dev)
+            label = torch.ones(index_sample.shape[0], device=dev)
+            ranks.append(self.evaluater.calc_metrics_single_graph(ent_embed, self.rel_embeds, all_g, index_sample, g, t))
+            losses.append(self.link_classification_loss(ent_embed, self.rel_embeds, index_sample, label).item())
+        ranks = torch.cat(ranks) if ranks else torch.zeros(0, dtype=torch.long, device=dev)
+        return ranks, (float(np.mean(losses)) if losses else float("nan"))
+
+
+class DynamicRGCN(TKG_Module):
+    """GRRGCN / RRGCN shell (reference models/DynamicRGCN.py)."""
+
+    def build_model(self):
+        self.ent_encoder = enc_mod.RRGCN(self.args, self.hidden_size, self.embed_size, self.num_rels, self.total_time)
+
+    @torch.no_grad()
+    def dense_history(self, res: EncodeResult, direction: str = "f"):
+        """Materialises the reference's ``hist_embeddings [B,2,M,D]`` / ``start_time_tensor [B,M]``
+        (models/DynamicRGCN.py:47-54) from the compact state -- API compatibility only."""
+        plan, D = res.plan, self.embed_size
+        B, L = plan.batch, plan.seq_len
+        hist = self.ent_embeds.new_zeros(B, 2, self.num_ents, D)
+        start = self.ent_embeds.new_zeros(B, self.num_ents)
+        for seg in plan.segments:
+            if seg.kind != "hist_" + direction:
+                continue
+            for inst in seg.instances:
+                ids = torch.from_numpy(inst.snapshot.node_ids).to(hist.device)
+                start[inst.item][ids] = float(inst.step)
+        lasts = plan.last_hist_f if direction == "f" else plan.last_hist_b
+        gru = self.args.module in ("GRRGCN", "BiGRRGCN")
+        for i, inst in enumerate(lasts):
+            if inst is None:
+                continue
+            # "history forgets": only the state of the immediately previous step survives, and only if
+            # that step is the last history step that ran
+            ids = torch.from_numpy(inst.snapshot.node_ids).to(hist.device)
+            second = res.state[inst.row0:inst.row0 + inst.n]
+            if gru:
+                first = second                                         # aliasing, Appendix B-2
+            elif "state1" in res.bufs:
+                first = res.bufs["state1"][inst.row0:inst.row0 + inst.n]
+            else:
+                first = res.bufs["h1"][inst.row0:inst.row0 + inst.n]
+            hist[i][0][ids] = first
+            hist[i][1][ids] = second
+        return hist, start
+
+    @torch.no_grad()
+    def evaluate_embed(self, t_list, val=True):
+        """models/DynamicRGCN.py:132-144: (per_graph_ent_embeds, test_graphs, time_list,
+        hist_embeddings, start_time_tensor)."""
+        res = self.encode(t_list)
+        graph_dict = self.graph_dict_val if val else self.graph_dict_test
+        _, time_list = self.get_batch_graph_list(t_list, self.test_seq_len, self.graph_dict_train)
+        hist, start = self.dense_history(res)
+        self.last_result = res
+        return res.per_graph, [graph_dict.get(t) for t in res.plan.final_times], time_list, hist, start
+
+    @torch.no_grad()
+    def train_embed(self, t_list):
+        """models/DynamicRGCN.py:146-154."""
+        res = self.encode(t_list)
+        _, time_list = self.get_batch_graph_list(t_list, self.test_seq_len, self.graph_dict_train)
+        hist, start = self.dense_history(res)
+        self.last_result = res
+        return res.per_graph, list(res.plan.final_snapshots), time_list, hist, start
+
+
+class BiDynamicRGCN(DynamicRGCN):
+    """BiGRRGCN / BiRRGCN shell (reference models/BiDynamicRGCN.py)."""
+    bidirectional = True
+
+    def build_model(self):
+        self.ent_encoder = enc_mod.BiRRGCN(self.args, self.hidden_size, self.embed_size, self.num_rels, self.total_time)
+
+    @torch.no_grad()
+    def evaluate_embed(self, t_list, val=True):
+        """models/BiDynamicRGCN.py:151-163 (7-tuple)."""
+        res = self.encode(t_list)
+        graph_dict = self.graph_dict_val if val else self.graph_dict_test
+        hf, sf = self.dense_history(res, "f")
+        hb, sb = self.dense_history(res, "b")
+        self.last_result = res
+        return (res.per_graph, [graph_dict.get(t) for t in res.plan.final_times], list(res.plan.final_times),
+                hf, sf, hb, sb)
+
+
+class SelfAttentionRGCN(TKG_Module):
+    """SARGCN shell (reference models/SelfAttentionRGCN.py)."""
+    family = "attention"
+
+    def build_model(self):
+        self.ent_encoder = enc_mod.SARGCN(self.args, self.hidden_size, self.embed_size, self.num_rels, self.total_time)
+
+
+class BiSelfAttentionRGCN(SelfAttentionRGCN):
+    """BiSARGCN shell (reference models/BiSelfAttentionRGCN.py)."""
+    bidirectional = True
+
+
+class StaticRGCN(TKG_Module):
+    """SRGCN shell (reference baselines/StaticRGCN.py): one snapshot per target, no recurrence."""
+    family = "static"
+
+    def build_model(self):
+        self.ent_encoder = enc_mod.RGCN(self.args, self.hidden_size, self.embed_size, self.num_rels, self.total_time)
+
+    def plan(self, t_list, seq_len=None) -> WindowPlan:
+        return plan_static(self.graph_dict_train, _as_int_list(t_list))
+
+    @torch.no_grad()
+    def evaluate_embed(self, t_list, val=True):
+        """baselines/StaticRGCN.py:23-28."""
+        res = self.encode(t_list)
+        graph_dict = self.graph_dict_val if val else self.graph_dict_test
+        self.last_result = res
+        return res.per_graph, [graph_dict.get(t) for t in res.plan.final_times]
+
+
+MODULES = {"SRGCN": StaticRGCN, "GRRGCN": DynamicRGCN, "RRGCN": DynamicRGCN, "BiGRRGCN": BiDynamicRGCN,
+           "BiRRGCN": BiDynamicRGCN, "SARGCN": SelfAttentionRGCN, "BiSARGCN": BiSelfAttentionRGCN}
+
+
+def build_module(args, num_ents, num_rels, graph_dict_train, graph_dict_val=None, graph_dict_test=None):
+    """The module table of main.py:42-55 restricted to the families on the hot path."""
+    return MODULES[args.module](args, num_ents, num_rels, graph_dict_train, graph_dict_val, graph_dict_test)

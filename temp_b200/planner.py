@@ -1,0 +1,283 @@
+"""Window planner: turns a batch of target timestamps into ONE packed, device-ready work list.
+
+The reference rebuilds a batched DGL graph on the host and copies it to the GPU at every time step
+(models/DynamicRGCN.py:76-110, utils/utils.py:9-11) and carries the recurrent state in a dense
+``(B, 2, num_ents, D)`` tensor that is re-zeroed every step (DynamicRGCN.py:47-54).  Here the whole
+window batch is laid out once as "packed rows" -- the nodes of every snapshot instance back to
+back, step-major -- with
+
+  * one CSR-by-destination over all packed rows (edge order inside a row = edge-id order),
+  * ``prev_row``: for every row the packed row of the SAME entity in the SAME batch item at the
+    previous step, or -1.  This is exactly what the dense history encodes, including the
+    "history forgets" quirk: an entity absent from step k-1 has zero state at k,
+  * ``slot_row`` (attention models): the packed history row of the entity per time slot, or -1.
+
+Window construction follows models/TKG_Module.py:232-250 (forward: items sorted descending, the last
+``seq_len`` timestamps <= t, None-padded at the front) and models/BiDynamicRGCN.py:17-49 (backward:
+items sorted ascending, timestamps t .. t+L-1 reversed so that t comes last).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .snapshot import Snapshot
+
+__all__ = ["Instance", "Segment", "WindowPlan", "plan_window", "plan_static"]
+
+_ALIGN = 256
+
+
+@dataclass
+class Instance:
+    item: int          # batch position in forward (descending-time) order
+    step: int
+    direction: str     # 'f' | 'b' | 'c' (centre / final step)
+    time: int
+    row0: int
+    n: int
+    snapshot: Snapshot
+
+
+@dataclass
+class Segment:
+    kind: str          # 'hist_f' | 'hist_b' | 'final'
+    step: int
+    row0: int
+    row1: int
+    instances: List[Instance] = field(default_factory=list)
+
+
+class WindowPlan(object):
+    """Packed arrays (numpy, int32 / float32) + segment table.  ``to_blob`` concatenates them into
+    one byte buffer so that the host->device traffic of a forward is a single copy."""
+
+    ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a",
+              "prev_b", "dt_b", "slot_row")
+
+    def __init__(self):
+        self.segments: List[Segment] = []
+        self.seq_len = 0
+        self.batch = 0
+        self.bidirectional = False
+        self.R = 0
+        self.E = 0
+        self.n_slots = 0
+        self.final_times: List[int] = []
+        self.final_sizes: List[int] = []
+        self.final_snapshots: List[Snapshot] = []
+        # per item: Instance of the last history step (step L-2), forward / backward, or None
+        self.last_hist_f: List[Optional[Instance]] = []
+        self.last_hist_b: List[Optional[Instance]] = []
+        for name in self.ARRAYS:
+            setattr(self, name, None)
+
+    @property
+    def final(self) -> Segment:
+        return self.segments[-1]
+
+    @property
+    def hist_rows(self) -> int:
+        return self.final.row0
+
+    def edges_processed(self) -> int:
+        return int(self.E)
+
+    def blob_layout(self):
+        off, lay = 0, {}
+        for name in self.ARRAYS:
+            arr = getattr(self, name)
+            if arr is None:
+                continue
+            lay[name] = (off, arr.nbytes)
+            off = (off + arr.nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        return lay, off
+
+    def to_blob(self, out: Optional[np.ndarray] = None):
+        lay, total = self.blob_layout()
+        if out is None:
+            out = np.zeros(total, dtype=np.uint8)
+        assert out.nbytes >= total
+        for name, (off, nb) in lay.items():
+            out[off:off + nb] = getattr(self, name).view(np.uint8).reshape(-1)
+        return out, lay, total
+
+
+def _window_times(t_list: Sequence[int], seq_len: int, times: List[int], backward: bool):
+    pos = {t: i for i, t in enumerate(times)}
+    order = sorted((int(t) for t in t_list), reverse=not backward)
+    rows = []
+    for tim in order:
+        p = pos[tim]
+        if backward:
+            seq = list(reversed(times[p:p + seq_len]))
+        else:
+            seq = times[max(0, p + 1 - seq_len):p + 1]
+        rows.append([None] * (seq_len - len(seq)) + list(seq))
+    return rows  # rows[item][step]
+
+
+class _Packer(object):
+    def __init__(self):
+        self.ent, self.rtime, self.norm, self.deg = [], [], [], []
+        self.esrc, self.esrc_ent, self.erel = [], [], []
+        self.prev_a, self.dt_a, self.prev_b, self.dt_b = [], [], [], []
+        self.R = 0
+        self.E = 0
+
+    def add(self, snap: Snapshot) -> int:
+        row0 = self.R
+        n = snap.num_nodes
+        self.ent.append(snap.node_ids.astype(np.int32))
+        self.rtime.append(np.full(n, snap.time, dtype=np.int32))
+        self.norm.append(snap.norm)
+        self.deg.append(np.diff(snap.row_ptr))
+        self.esrc.append(snap.csr_src + np.int32(row0))
+        self.esrc_ent.append(snap.node_ids[snap.csr_src].astype(np.int32))
+        self.erel.append(snap.csr_rel)
+        self.R += n
+        self.E += snap.num_edges
+        return row0
+
+    def add_prev(self, n: int, prev: Optional[np.ndarray], dt_val: float, which: str = "a"):
+        pv = prev if prev is not None else np.full(n, -1, dtype=np.int32)
+        dt = np.full(n, dt_val, dtype=np.float32)
+        (self.prev_a if which == "a" else self.prev_b).append(pv.astype(np.int32))
+        (self.dt_a if which == "a" else self.dt_b).append(dt)
+
+    def finish(self, plan: WindowPlan):
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dtype=dt)
+        plan.R, plan.E = self.R, self.E
+        plan.ent_id = cat(self.ent, np.int32)
+        plan.row_time = cat(self.rtime, np.int32)
+        plan.norm = cat(self.norm, np.float32)
+        rp = np.zeros(self.R + 1, dtype=np.int64)
+        if self.deg:
+            np.cumsum(np.concatenate(self.deg), out=rp[1:])
+        plan.row_ptr = rp.astype(np.int32)
+        plan.e_src = cat(self.esrc, np.int32)
+        plan.e_src_ent = cat(self.esrc_ent, np.int32)
+        plan.e_rel = cat(self.erel, np.int32)
+        plan.prev_a = cat(self.prev_a, np.int32)
+        plan.dt_a = cat(self.dt_a, np.float32)
+        if self.prev_b:
+            plan.prev_b = cat(self.prev_b, np.int32)
+            plan.dt_b = cat(self.dt_b, np.float32)
+
+
+def _match_prev(cur: Snapshot, prev_inst: Optional[Instance]) -> Optional[np.ndarray]:
+    """Packed row of each node of ``cur`` in the previous instance of the same item, -1 if absent."""
+    if prev_inst is None:
+        return None
+    pid = prev_inst.snapshot.node_ids
+    pos = np.searchsorted(pid, cur.node_ids)
+    pos_c = np.minimum(pos, pid.shape[0] - 1)
+    hit = pid[pos_c] == cur.node_ids
+    return np.where(hit, pos_c + prev_inst.row0, -1).astype(np.int32)
+
+
+def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len: int, bidirectional: bool = False,
+                attention: bool = False) -> WindowPlan:
+    """Plan the forward of (Bi)DynamicRGCN / (Bi)SelfAttentionRGCN for the target timestamps ``t_list``.
+
+    Row order: forward history steps 0..L-2, then (Bi) backward history steps 0..L-2, then the final
+    (centre) step whose graphs are the targets in descending-time order."""
+    times = list(graph_dict.keys())
+    L, B = int(seq_len), len(t_list)
+    plan = WindowPlan()
+    plan.seq_len, plan.batch, plan.bidirectional = L, B, bidirectional
+    pk = _Packer()
+    fwd = _window_times(t_list, L, times, backward=False)            # [item][step], items descending
+    bwd = _window_times(t_list, L, times, backward=True) if bidirectional else None   # items ascending
+
+    def history(rows, kind, flip):
+        last: List[Optional[Instance]] = [None] * B
+        by_step: List[Dict[int, Instance]] = []
+        for k in range(L - 1):
+            seg = Segment(kind, k, pk.R, pk.R)
+            cur: Dict[int, Instance] = {}
+            for j in range(B):
+                tim = rows[j][k]
+                if tim is None:
+                    continue
+                snap = graph_dict[tim]
+                item = (B - 1 - j) if flip else j                     # BiDynamicRGCN.py:97-99 (flip)
+                prev = _match_prev(snap, last[j])
+                inst = Instance(item, k, kind[-1], tim, pk.add(snap), snap.num_nodes, snap)
+                # dt = cur_t - start_time; it only multiplies a non-zero state, i.e. rows whose
+                # entity was active at step k-1, where it equals 1
+                pk.add_prev(snap.num_nodes, prev, 1.0 if prev is not None else float(k))
+                if bidirectional:
+                    pk.add_prev(snap.num_nodes, None, float(k), "b")
+                cur[j] = inst
+                seg.instances.append(inst)
+            seg.row1 = pk.R
+            for j, inst in cur.items():
+                last[j] = inst
+            by_step.append(cur)
+            if seg.row1 > seg.row0:
+                plan.segments.append(seg)
+        return last, by_step
+
+    last_f, steps_f = history(fwd, "hist_f", flip=False)
+    last_b, steps_b = (history(bwd, "hist_b", flip=True) if bidirectional else ([None] * B, []))
+
+    seg = Segment("final", L - 1, pk.R, pk.R)
+    slot_rows = []
+    for i in range(B):
+        tim = fwd[i][L - 1]
+        snap = graph_dict[tim]
+        inst = Instance(i, L - 1, "c", tim, pk.add(snap), snap.num_nodes, snap)
+        pf = _match_prev(snap, last_f[i])
+        pk.add_prev(snap.num_nodes, pf, 1.0 if pf is not None else float(L - 1))
+        if bidirectional:
+            pb = _match_prev(snap, last_b[B - 1 - i])
+            pk.add_prev(snap.num_nodes, pb, 1.0 if pb is not None else float(L - 1), "b")
+        seg.instances.append(inst)
+        plan.final_times.append(tim)
+        plan.final_sizes.append(snap.num_nodes)
+        plan.final_snapshots.append(snap)
+        if attention:
+            cols = []
+            for k in range(L - 1):
+                m = _match_prev(snap, steps_f[k].get(i))
+                cols.append(m if m is not None else np.full(snap.num_nodes, -1, dtype=np.int32))
+            if bidirectional:
+                for k in range(L - 1):
+                    m = _match_prev(snap, steps_b[k].get(B - 1 - i))
+                    cols.append(m if m is not None else np.full(snap.num_nodes, -1, dtype=np.int32))
+            slot_rows.append(np.stack(cols, axis=1) if cols else np.zeros((snap.num_nodes, 0), dtype=np.int32))
+    seg.row1 = pk.R
+    plan.segments.append(seg)
+    plan.last_hist_f = list(last_f)
+    plan.last_hist_b = [last_b[B - 1 - i] for i in range(B)] if bidirectional else [None] * B
+    pk.finish(plan)
+    if attention:
+        plan.n_slots = (L - 1) * (2 if bidirectional else 1)
+        plan.slot_row = np.ascontiguousarray(np.concatenate(slot_rows, axis=0), dtype=np.int32)
+        plan.steps_f, plan.steps_b = steps_f, steps_b
+    return plan
+
+
+def plan_static(graph_dict: Dict[int, Snapshot], t_list: Sequence[int]) -> WindowPlan:
+    """StaticRGCN (baselines/StaticRGCN.py:23-28): one snapshot per target, t_list order kept."""
+    plan = WindowPlan()
+    plan.seq_len, plan.batch = 1, len(t_list)
+    pk = _Packer()
+    seg = Segment("final", 0, 0, 0)
+    for i, t in enumerate(t_list):
+        snap = graph_dict[int(t)]
+        inst = Instance(i, 0, "c", int(t), pk.add(snap), snap.num_nodes, snap)
+        pk.add_prev(snap.num_nodes, None, 0.0)
+        seg.instances.append(inst)
+        plan.final_times.append(int(t))
+        plan.final_sizes.append(snap.num_nodes)
+        plan.final_snapshots.append(snap)
+    seg.row1 = pk.R
+    plan.segments.append(seg)
+    plan.last_hist_f = [None] * len(t_list)
+    plan.last_hist_b = [None] * len(t_list)
+    pk.finish(plan)
+    return plan

@@ -1,0 +1,414 @@
+"""Launch-program builder: turns (model parameters, WindowPlan) into a static list of kernel
+launches (lib.Program) executed by ONE ``temp_run_program`` C call.
+
+Per forward the reference issues, for every time step, a python loop over graphs, ``dgl.batch``,
+host->device copies, ~40 torch/DGL kernels and a dense history re-zero.  Here the
+whole window batch is:
+
+    [H2D of the packed plan]  ->  recurrence-free work for ALL snapshot instances at once
+    (layer 1, and with --rec-only-last-layer also the layer-2 aggregation + self loop + GRU input
+    gates)  ->  one small GRU launch per time step (only h0 . W_hh^T and the gates are serial).
+
+Families (reference file:line of what each program restates):
+    SRGCN                models/RGCN.py:154-159
+    GRRGCN / RRGCN       models/RRGCN.py:192-204 driven by models/DynamicRGCN.py:156-174, 132-144
+    BiGRRGCN / BiRRGCN   models/BiRRGCN.py:210-240 driven by models/BiDynamicRGCN.py:77-121, 151-163
+    SARGCN / BiSARGCN    models/SARGCN.py:103-117 driven by models/SelfAttentionRGCN.py:86-120 and
+                         models/BiSelfAttentionRGCN.py:25-46, 71-87
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import lib
+from .planner import WindowPlan
+
+_F32 = 4
+
+
+class Workspace(object):
+    """Grow-only device buffers keyed by name (no allocation on the steady-state path)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, numel: int, dtype=torch.float32) -> torch.Tensor:
+        t = self._bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            cap = int(numel * 1.25) + 64
+            t = torch.empty(cap, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def pinned(self, name: str, numel: int, dtype=torch.uint8) -> torch.Tensor:
+        t = self._pinned.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            cap = int(numel * 1.25) + 64
+            t = torch.empty(cap, dtype=dtype, pin_memory=True)
+            self._pinned[name] = t
+        return t
+
+
+class PreparedWeights(object):
+    """Kernel-layout views of the parameters: transposed GRU / attention weights ([in, out] row-major,
+    concatenated along out where one chained GEMM feeds several consumers) and the (w, b) pair of the
+    learnable decay.  Rebuilt only when a parameter's version counter changes."""
+
+    def __init__(self, model):
+        self.model = model
+        self._cache = {}
+
+    def _key(self, tensors):
+        return tuple((t.data_ptr(), t._version) for t in tensors)
+
+    def cat_t(self, name: str, weights: List[torch.Tensor]) -> torch.Tensor:
+        """cat([w.T for w in weights], dim=1) -- [in, sum(out)] row-major."""
+        key = self._key(weights)
+        hit = self._cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                val = torch.cat([w.detach().t() for w in weights], dim=1).contiguous()
+            hit = (key, val)
+            self._cache[name] = hit
+        return hit[1]
+
+    def cat(self, name: str, vecs: List[torch.Tensor]) -> torch.Tensor:
+        key = self._key(vecs)
+        hit = self._cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                val = torch.cat([v.detach().reshape(-1) for v in vecs]).contiguous()
+            hit = (key, val)
+            self._cache[name] = hit
+        return hit[1]
+
+
+class EncodeResult(object):
+    def __init__(self, plan: WindowPlan, out: torch.Tensor, state: Optional[torch.Tensor], program: lib.Program,
+                 bufs: dict):
+        self.plan, self.out, self.state, self.program, self.bufs = plan, out, state, program, bufs
+
+    @property
+    def per_graph(self):
+        return tuple(self.out.split(self.plan.final_sizes))
+
+
+def _p(t, off_bytes=0):
+    return None if t is None else C.c_void_p(t.data_ptr() + off_bytes)
+
+
+class EncoderRuntime(object):
+    """Owns the workspace + prepared weights of one model and builds / runs launch programs."""
+
+    def __init__(self, model):
+        self.model = model
+        self.device = model.ent_embeds.device
+        if self.device.type != "cuda":
+            raise RuntimeError("temp_b200: the encoder runs on CUDA only (no CPU fallback); move the model to "
+                               "a cuda device")
+        lib.load()
+        self.ws = Workspace(self.device)
+        self.prep = PreparedWeights(model)
+
+    # ---- plan upload -----------------------------------------------------------------------------
+    def stage_plan(self, plan: WindowPlan, program: lib.Program, tag: str = "plan"):
+        """Packs the plan into pinned host memory and appends the single H2D copy to ``program``.
+        Returns name -> device pointer (int) of every plan array."""
+        lay, total = plan.blob_layout()
+        host = self.ws.pinned(tag + "_host", total)
+        plan.to_blob(host.numpy())
+        dev = self.ws.get(tag + "_dev", total, torch.uint8)
+        program.add(lib.OP_H2D, lib.CopyArgs(dev.data_ptr(), host.data_ptr(), total))
+        program.keepalive += [host, dev]
+        program.h2d_bytes = getattr(program, "h2d_bytes", 0) + total
+        return {name: dev.data_ptr() + off for name, (off, _) in lay.items()}
+
+    # ---- op constructors ---------------------------------------------------------------------------
+    def _layer(self, layer, rows, dptr, *, x, x_is_embed, terms, act, h_out=None, chain=None, te_out=False,
+               te_chain=False, graph=True, residual=False, row_time_scalar=None):
+        m = self.model
+        a = lib.RgcnLayerArgs()
+        a.row0, a.row1, a.d = int(rows[0]), int(rows[1]), m.embed_size
+        if graph:
+            a.row_ptr = dptr["row_ptr"]
+            a.e_src = dptr["e_src_ent"] if x_is_embed else dptr["e_src"]
+            a.e_rel = dptr["e_rel"]
+            a.norm = dptr["norm"]
+            a.x = x.data_ptr()
+            a.weight = layer.weight.data_ptr()
+            a.n_bases, a.si, a.so = layer.num_bases, layer.submat_in, layer.submat_out
+        a.residual = int(residual)
+        a.n_terms = len(terms)
+        for i, t in enumerate(terms):
+            a.terms[i] = t
+        if layer.bias:
+            a.h_bias = layer.h_bias.data_ptr()
+        a.activation = lib.ACT_RELU if act else lib.ACT_NONE
+        if te_out or te_chain:
+            a.time_embed = layer.time_embed.data_ptr()
+            if row_time_scalar is None:
+                a.row_time = dptr["row_time"]
+            else:
+                a.row_time_scalar = int(row_time_scalar)
+        a.te_out, a.te_chain = int(te_out), int(te_chain)
+        if h_out is not None:
+            a.h_out = h_out.data_ptr()
+        if chain is not None:
+            w, b, out, ld = chain
+            a.chain_w = w.data_ptr()
+            a.chain_b = None if b is None else b.data_ptr()
+            a.chain_out = out.data_ptr()
+            a.chain_n, a.chain_ld = int(w.shape[1]), int(ld)
+        a.inv_temperature = float(m.args.inv_temperature)
+        return a
+
+    def _term(self, a, w, index=None, dt=None, decay_wb=None):
+        t = lib.DenseTerm()
+        t.a, t.w = a.data_ptr(), w.data_ptr()
+        t.a_index = index
+        t.a_dt = dt
+        t.decay_wb = None if decay_wb is None else decay_wb.data_ptr()
+        return t
+
+    def _decay_wb(self, layer, name):
+        if not layer.learnable_lambda:
+            return None
+        return self.prep.cat(name + ".decay_wb", [layer.exponential_decay.weight, layer.exponential_decay.bias])
+
+    def _gru(self, layer, rnn, rnn_name, rows, *, gi, gi_ld, gi_off, state, prev, dt, out, te, accumulate=False,
+             dptr=None, row_time_scalar=None, layer_name=""):
+        m = self.model
+        type1 = bool(getattr(m.args, "type1", False))
+        a = lib.GruArgs()
+        a.row0, a.row1, a.d = int(rows[0]), int(rows[1]), m.embed_size
+        a.gi, a.gi_ld, a.gi_off = gi.data_ptr(), int(gi_ld), int(gi_off)
+        a.state = None if state is None else state.data_ptr()
+        a.prev_row, a.dt = prev, dt
+        wb = self._decay_wb(layer, layer_name)
+        a.decay_wb = None if wb is None else wb.data_ptr()
+        a.inv_temperature = float(m.args.inv_temperature)
+        whh = rnn.weight_hh if type1 else rnn.weight_hh_l0
+        bhh = rnn.bias_hh if type1 else rnn.bias_hh_l0
+        a.whh_t = self.prep.cat_t(layer_name + "." + rnn_name + ".whh_t", [whh]).data_ptr()
+        a.b_hh = bhh.data_ptr()
+        a.cell_type = lib.CELL_TYPE1 if type1 else lib.CELL_TORCH_GRU
+        if te:
+            a.time_embed = layer.time_embed.data_ptr()
+            if row_time_scalar is None:
+                a.row_time = dptr["row_time"]
+            else:
+                a.row_time_scalar = int(row_time_scalar)
+        a.accumulate = int(accumulate)
+        a.out = out.data_ptr()
+        a.out_index_is_row = 1
+        return a
+
+    def _wih(self, layer_name, rnns):
+        """chained-GEMM operands for the input half of one or two GRUs: ([D, sum 3D|D], bias)."""
+        type1 = bool(getattr(self.model.args, "type1", False))
+        ws = [(r.weight_ih if type1 else r.weight_ih_l0) for _, r in rnns]
+        bs = [(r.bias_ih if type1 else r.bias_ih_l0) for _, r in rnns]
+        tag = layer_name + "." + "+".join(n for n, _ in rnns)
+        return self.prep.cat_t(tag + ".wih_t", ws), self.prep.cat(tag + ".b_ih", bs)
+
+    # ---- programs ----------------------------------------------------------------------------------
+    def build(self, plan: WindowPlan, with_h2d: bool = True) -> EncodeResult:
+        m = self.model
+        fam = m.family
+        prog = lib.Program()
+        dptr = self.stage_plan(plan, prog)
+        if not with_h2d:
+            prog.ops = [o for o in prog.ops if o.kind != lib.OP_H2D]
+        if fam == "static":
+            return self._build_static(plan, prog, dptr)
+        if fam == "attention":
+            return self._build_attention(plan, prog, dptr)
+        return self._build_recurrent(plan, prog, dptr)
+
+    def _build_static(self, plan, prog, dptr):
+        m, D, R = self.model, self.model.embed_size, plan.R
+        enc = m.ent_encoder
+        h1 = self.ws.get("h1", R * D).view(-1)[:R * D].view(R, D)
+        out = self.ws.get("out", R * D).view(-1)[:R * D].view(R, D)
+        rows = (0, R)
+        prog.add(lib.OP_LAYER, self._layer(enc.layer_1, rows, dptr, x=m.ent_embeds, x_is_embed=True, act=False,
+                                           terms=[self._term(m.ent_embeds, enc.layer_1.loop_weight, index=dptr["ent_id"])],
+                                           h_out=h1))
+        prog.add(lib.OP_LAYER, self._layer(enc.layer_2, rows, dptr, x=h1, x_is_embed=False, act=True,
+                                           terms=[self._term(h1, enc.layer_2.loop_weight)], h_out=out,
+                                           te_out=enc.use_time_embedding))
+        return EncodeResult(plan, out, None, prog, {"h1": h1})
+
+    def _build_recurrent(self, plan, prog, dptr):
+        m, D, R = self.model, self.model.embed_size, plan.R
+        enc = m.ent_encoder
+        l1, l2 = enc.layer_1, enc.layer_2
+        gru = m.args.module in ("GRRGCN", "BiGRRGCN")
+        bi = plan.bidirectional
+        use_te = enc.use_time_embedding
+        relu2 = bi                                         # BiRRGCN.py:202-203 vs RRGCN.py:186-187
+        type1 = bool(getattr(m.args, "type1", False))
+        G = D if type1 else 3 * D                          # gi width of one cell
+        final = plan.final
+        h1 = self.ws.get("h1", R * D)[:R * D].view(R, D)
+        S = self.ws.get("state", R * D)[:R * D].view(R, D)
+        S1 = None
+        bufs = {"h1": h1}
+
+        def rnn_of(layer, direction):
+            if not bi:
+                return ("rnn", layer.rnn) if gru else ("time_weight", layer.time_weight)
+            if gru:
+                return ("forward_rnn", layer.forward_rnn) if direction == "f" else ("backward_rnn", layer.backward_rnn)
+            return (("time_weight_forward", layer.time_weight_forward) if direction == "f"
+                    else ("time_weight_backward", layer.time_weight_backward))
+
+        def dirs_of(seg):
+            return ["f", "b"] if (seg.kind == "final" and bi) else [seg.kind[-1] if seg.kind != "final" else "f"]
+
+        def prev_ptrs(direction, seg):
+            which = "b" if (direction == "b" and seg.kind == "final") else "a"
+            return dptr["prev_" + which], dptr["dt_" + which]
+
+        # ---- recurrent layer over one row range (segment): GRU flavour or linear flavour ------------
+        def rec_layer(layer, lname, rows, seg, x_in, x_is_embed, index, state_prev, out, relu, te):
+            dirs = dirs_of(seg)
+            if gru:
+                rnns = [rnn_of(layer, d) for d in dirs]
+                w, b = self._wih(lname, rnns)
+                gi = self.ws.get("gi_" + lname, R * 2 * G)[:R * 2 * G].view(R, 2 * G)
+                prog.add(lib.OP_LAYER, self._layer(layer, rows, dptr, x=x_in, x_is_embed=x_is_embed, act=relu,
+                                                   terms=[self._term(x_in, layer.loop_weight, index=index)],
+                                                   chain=(w, b, gi, 2 * G)))
+                for j, d in enumerate(dirs):
+                    pv, dt = prev_ptrs(d, seg)
+                    prog.add(lib.OP_GRU, self._gru(layer, rnns[j][1], rnns[j][0], rows, gi=gi, gi_ld=2 * G, gi_off=j * G,
+                                                   state=state_prev, prev=pv, dt=dt, out=out,
+                                                   te=te and j == len(dirs) - 1, accumulate=j > 0, dptr=dptr,
+                                                   layer_name=lname))
+            else:
+                terms = [self._term(x_in, layer.loop_weight, index=index)]
+                for d in dirs:
+                    pv, dt = prev_ptrs(d, seg)
+                    terms.append(self._term(state_prev, rnn_of(layer, d)[1], index=pv, dt=dt))
+                prog.add(lib.OP_LAYER, self._layer(layer, rows, dptr, x=x_in, x_is_embed=x_is_embed, act=relu, terms=terms,
+                                                   h_out=out, te_out=te))
+
+        if enc.rec_only_last_layer:
+            # layer 1 for every snapshot instance at once
+            prog.add(lib.OP_LAYER, self._layer(l1, (0, R), dptr, x=m.ent_embeds, x_is_embed=True, act=False,
+                                               terms=[self._term(m.ent_embeds, l1.loop_weight, index=dptr["ent_id"])],
+                                               h_out=h1))
+            if gru:
+                # layer-2 aggregation + self loop + GRU input gates: also recurrence free.  Row groups
+                # that share the same chained weights are launched together.
+                gi = self.ws.get("gi_l2", R * 2 * G)[:R * 2 * G].view(R, 2 * G)
+                groups = {}
+                for seg in plan.segments:
+                    key = tuple(dirs_of(seg))
+                    lo, hi = groups.get(key, (seg.row0, seg.row1))
+                    groups[key] = (min(lo, seg.row0), max(hi, seg.row1))
+                for dirs, rows in groups.items():
+                    rnns = [rnn_of(l2, d) for d in dirs]
+                    w, b = self._wih("layer_2", rnns)
+                    prog.add(lib.OP_LAYER, self._layer(l2, rows, dptr, x=h1, x_is_embed=False, act=relu2,
+                                                       terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, 2 * G)))
+                for seg in plan.segments:
+                    rows = (seg.row0, seg.row1)
+                    dirs = dirs_of(seg)
+                    for j, d in enumerate(dirs):
+                        name, rnn = rnn_of(l2, d)
+                        pv, dt = prev_ptrs(d, seg)
+                        prog.add(lib.OP_GRU, self._gru(l2, rnn, name, rows, gi=gi, gi_ld=2 * G, gi_off=j * G, state=S,
+                                                       prev=pv, dt=dt, out=S, te=use_te and j == len(dirs) - 1,
+                                                       accumulate=j > 0, dptr=dptr, layer_name="layer_2"))
+            else:
+                for seg in plan.segments:
+                    rec_layer(l2, "layer_2", (seg.row0, seg.row1), seg, h1, False, None, S, S, relu2, use_te)
+        else:
+            # both layers recurrent: strictly serial in the step index.  For the GRU flavours the
+            # reference's graph aliasing feeds layer 1 with the previous LAYER-2 state (Appendix B-2);
+            # the linear flavours keep separate first / second states.
+            S1 = self.ws.get("state1", R * D)[:R * D].view(R, D)
+            bufs["state1"] = S1
+            prev1 = S if gru else S1
+            for seg in plan.segments:
+                rows = (seg.row0, seg.row1)
+                rec_layer(l1, "layer_1", rows, seg, m.ent_embeds, True, dptr["ent_id"], prev1, S1, False, use_te)
+                rec_layer(l2, "layer_2", rows, seg, S1, False, None, S, S, relu2, use_te)
+        out = S[final.row0:final.row1]
+        bufs["state"] = S
+        return EncodeResult(plan, out, S, prog, bufs)
+
+    def _build_attention(self, plan, prog, dptr):
+        m, D, R = self.model, self.model.embed_size, plan.R
+        enc = m.ent_encoder
+        l1, l2 = enc.layer_1, enc.layer_2
+        final = plan.final
+        Rh = final.row0
+        nf = final.row1 - final.row0
+        h1 = self.ws.get("h1", R * D)[:R * D].view(R, D)
+        out = self.ws.get("out", max(nf, 1) * D)[:nf * D].view(nf, D)
+        out_base = out.data_ptr() - final.row0 * D * _F32          # kernels address rows absolutely
+        tau = torch.tensor(m.time_diff(plan), dtype=torch.float32, device=self.device)
+        prog.keepalive.append(tau)
+
+        def chains(layer, lname):
+            kv = self.prep.cat_t(lname + ".kv_t", [layer.k_linear.weight, layer.v_linear.weight])
+            qkv = self.prep.cat_t(lname + ".qkv_t", [layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight])
+            kvb = self.ws.get("kv_" + lname, max(Rh, 1) * 2 * D)[:Rh * 2 * D].view(Rh, 2 * D)
+            qkvb = self.ws.get("qkv_" + lname, max(nf, 1) * 3 * D)[:nf * 3 * D].view(nf, 3 * D)
+            return kv, qkv, kvb, qkvb
+
+        def attend(layer, lname, kvb, qkvb, combine):
+            a = lib.AttnArgs()
+            a.row0, a.row1, a.d, a.heads = final.row0, final.row1, D, layer.h
+            a.qkv = qkvb.data_ptr() - final.row0 * 3 * D * _F32
+            a.kv_hist = kvb.data_ptr() if Rh > 0 else None
+            a.slot_row = dptr["slot_row"] - final.row0 * plan.n_slots * 4 if plan.n_slots > 0 else None
+            a.n_slots = plan.n_slots if Rh > 0 else 0
+            a.tau = tau.data_ptr()
+            wb = self._decay_wb(layer, lname)
+            a.decay_wb = None if wb is None else wb.data_ptr()
+            a.combine_max = int(combine)
+            a.out = out_base
+            prog.add(lib.OP_ATTN, a)
+
+        class _Abs(object):   # tensor stand-in whose data_ptr is shifted so that row r maps to r - row0
+            def __init__(self, t, shift):
+                self._p = t.data_ptr() - shift
+            def data_ptr(self):
+                return self._p
+
+        bufs = {"h1": h1}
+        emb_term = [self._term(m.ent_embeds, l1.loop_weight, index=dptr["ent_id"])]
+        if enc.rec_only_last_layer:
+            prog.add(lib.OP_LAYER, self._layer(l1, (0, R), dptr, x=m.ent_embeds, x_is_embed=True, act=False,
+                                               terms=emb_term, h_out=h1))
+        else:
+            kv1, qkv1, kvb1, qkvb1 = chains(l1, "layer_1")
+            if Rh > 0:
+                prog.add(lib.OP_LAYER, self._layer(l1, (0, Rh), dptr, x=m.ent_embeds, x_is_embed=True, act=False,
+                                                   terms=emb_term, h_out=h1, te_chain=True,
+                                                   chain=(kv1, None, kvb1, 2 * D)))
+            prog.add(lib.OP_LAYER, self._layer(l1, (Rh, R), dptr, x=m.ent_embeds, x_is_embed=True, act=False,
+                                               terms=emb_term, h_out=h1, te_chain=True,
+                                               chain=(qkv1, None, _Abs(qkvb1, Rh * 3 * D * _F32), 3 * D)))
+            attend(l1, "layer_1", kvb1, qkvb1, combine=False)
+            bufs["kv1"] = kvb1
+        kv2, qkv2, kvb2, qkvb2 = chains(l2, "layer_2")
+        t2 = [self._term(h1, l2.loop_weight)]
+        if Rh > 0:
+            prog.add(lib.OP_LAYER, self._layer(l2, (0, Rh), dptr, x=h1, x_is_embed=False, act=True, terms=t2,
+                                               te_chain=True, chain=(kv2, None, kvb2, 2 * D)))
+        prog.add(lib.OP_LAYER, self._layer(l2, (Rh, R), dptr, x=h1, x_is_embed=False, act=True, terms=t2,
+                                           te_chain=True, chain=(qkv2, None, _Abs(qkvb2, Rh * 3 * D * _F32), 3 * D)))
+        attend(l2, "layer_2", kvb2, qkvb2, combine=not enc.rec_only_last_layer)   # JK max, SARGCN.py:117
+        bufs.update(kv2=kvb2, qkv2=qkvb2)
+        return EncodeResult(plan, out, None, prog, bufs)

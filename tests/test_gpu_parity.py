@@ -1,0 +1,59 @@
+"""GPU: the CUDA path (through the C ABI) against the golden outputs of the reference and against
+the oracle, on identical inputs.  Tolerance: 1e-4 relative fp32 (BASELINE.json north star)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.cases import CASES
+from tests.helpers import load_golden, oracle_model, product_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _close(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(np.abs(want).max(), 1e-30)
+    assert np.abs(got - want).max() / scale < RTOL, "max rel-to-scale err %.3e" % (np.abs(got - want).max() / scale)
+    assert np.allclose(got, want, rtol=RTOL, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_encoder_matches_reference_golden(case):
+    gold = load_golden(case["name"])
+    model = product_model(case)
+    res = model.encode(case["t_list"])
+    torch.cuda.synchronize()
+    assert res.plan.final_times == gold["times"].tolist()
+    assert res.plan.final_sizes == gold["sizes"].tolist()
+    _close(res.out.cpu().numpy(), gold["per_graph"])
+    rows = gold["all_rows"]
+    alls = np.stack([model.all_embeds(res, i).cpu().numpy()[rows] for i in range(len(res.plan.final_times))])
+    _close(alls, gold["all_embeds"])
+
+
+@pytest.mark.parametrize("name", ["grrgcn_tiny_d128_last", "bigrrgcn_tiny_d128_full", "sargcn_tiny_d128_full"])
+def test_encoder_matches_oracle_and_is_deterministic(name):
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME[name]
+    model = product_model(case)
+    a = model.encode(case["t_list"]).out.clone()
+    b = model.encode(case["t_list"]).out.clone()
+    assert torch.equal(a, b), "the CUDA path must be run-to-run deterministic (no atomics)"
+    with torch.no_grad():
+        want = torch.cat(oracle_model(case).evaluate_embed(case["t_list"])["per_graph"]).numpy()
+    _close(a.cpu().numpy(), want)
+
+
+def test_dense_history_api_matches_oracle():
+    """evaluate_embed's reference-shaped outputs (hist_embeddings [B,2,M,D], start_time_tensor [B,M])."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME["grrgcn_tiny_d128_last"]
+    model = product_model(case)
+    per_graph, test_graphs, time_list, hist, start = model.evaluate_embed(torch.tensor(case["t_list"]))
+    with torch.no_grad():
+        ref = oracle_model(case).evaluate_embed(case["t_list"])
+    assert np.array_equal(start.cpu().numpy(), ref["start"].numpy())
+    _close(hist.cpu().numpy(), ref["hist"].numpy())
+    assert time_list[-1] == ref["times"]

@@ -1,0 +1,171 @@
+"""CPU: host-side logic of the product (snapshots, planner, sampler, ABI surface) against the oracle
+and the golden vectors.  No compute call is made without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import temp_oracle as orc
+from tests.golden.cases import CASES, SAMPLER_CASES
+from tests.helpers import load_golden, oracle_graphs, oracle_model, product_store
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("dataset", ["tiny", "icews14_head"])
+def test_snapshot_store_equals_reference_graph_construction(dataset):
+    m, r, train, valid, test = oracle_graphs(dataset)
+    store = product_store(dataset)
+    assert (store.num_ents, store.num_rels) == (m, r)
+    assert list(store.train.keys()) == list(train.keys())
+    for split_p, split_o in ((store.train, train), (store.valid, valid), (store.test, test)):
+        for t, g in split_o.items():
+            s = split_p[t]
+            assert np.array_equal(s.node_ids, g.ids)
+            assert np.array_equal(s.src, g.src) and np.array_equal(s.dst, g.dst) and np.array_equal(s.rel, g.rel)
+            assert np.array_equal(s.norm, g.norm)
+            # CSR view: stable by destination => per-row edge order == edge-id order
+            order = np.argsort(g.dst, kind="stable")
+            assert np.array_equal(s.csr_src, g.src[order]) and np.array_equal(s.csr_rel, g.rel[order])
+            assert np.array_equal(np.diff(s.row_ptr), np.bincount(g.dst, minlength=g.num_nodes))
+
+
+def _plan_for(case):
+    from temp_b200.planner import plan_static, plan_window
+    store = product_store(case["dataset"])
+    if case["module"] == "SRGCN":
+        return plan_static(store.train, case["t_list"])
+    return plan_window(store.train, case["t_list"], case["L"], bidirectional=case["module"].startswith("Bi"),
+                       attention=case["module"].endswith("SARGCN"))
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["module"] in ("GRRGCN", "BiGRRGCN")],
+                         ids=lambda c: c["name"])
+def test_prev_row_encodes_the_dense_history(case):
+    """prev_row >= 0 exactly where the oracle's dense history row is non-zero (history forgets)."""
+    plan = _plan_for(case)
+    model = oracle_model(case)
+    with torch.no_grad():
+        res = model.evaluate_embed(case["t_list"])
+    assert plan.final_times == res["times"]
+    hists = [res["hist"]] if "hist" in res else [res["hist_f"], res["hist_b"]]
+    prevs = [plan.prev_a] if len(hists) == 1 else [plan.prev_a, plan.prev_b]
+    for hist, prev in zip(hists, prevs):
+        for i, inst in enumerate(plan.final.instances):
+            nz = (hist[i][1][torch.from_numpy(inst.snapshot.node_ids)].abs().sum(-1) != 0).numpy()
+            assert np.array_equal(prev[inst.row0:inst.row0 + inst.n] >= 0, nz)
+
+
+def test_plan_blob_roundtrip_and_alignment():
+    plan = _plan_for(CASES[2])
+    blob, lay, total = plan.to_blob()
+    assert blob.nbytes == total
+    for name, (off, nb) in lay.items():
+        assert off % 256 == 0
+        arr = getattr(plan, name)
+        assert np.array_equal(blob[off:off + nb].view(arr.dtype).reshape(arr.shape), arr)
+    assert plan.row_ptr[-1] == plan.E and plan.e_src.max() < plan.R
+    assert plan.E == sum(i.snapshot.num_edges for s in plan.segments for i in s.instances)
+
+
+def test_attention_slot_rows_match_oracle_mask():
+    case = [c for c in CASES if c["name"] == "bisargcn_tiny_d128_last"][0]
+    plan = _plan_for(case)
+    with torch.no_grad():
+        res = oracle_model(case).evaluate_embed(case["t_list"])
+    mask = res["mask"]                                              # [2L-1, B, M]
+    off = 0
+    for i, inst in enumerate(plan.final.instances):
+        active = (mask[:-1, i][:, torch.from_numpy(inst.snapshot.node_ids)] == 0).numpy().T    # [n, slots]
+        assert np.array_equal(plan.slot_row[off:off + inst.n] >= 0, active)
+        off += inst.n
+
+
+@pytest.mark.parametrize("case", SAMPLER_CASES, ids=[c["name"] for c in SAMPLER_CASES])
+def test_product_sampler_bit_exact_with_reference(case):
+    from argparse import Namespace
+    from temp_b200.sampler import CorruptTriples
+    gold = load_golden(case["name"])
+    store = product_store(case["dataset"])
+    cor = CorruptTriples(Namespace(negative_rate=case["negative_rate"], num_pos_facts=case["num_pos_facts"]), store.train)
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    for t in case["times"]:
+        tri, nt, nh, lab = cor.single_graph_negative_sampling(t, store.train[t], store.num_ents)
+        assert np.array_equal(tri.numpy(), gold["triples_%d" % t])
+        assert np.array_equal(nt.numpy(), gold["neg_tail_%d" % t])
+        assert np.array_equal(nh.numpy(), gold["neg_head_%d" % t])
+
+
+def test_synthetic_generator_shape_statistics():
+    from temp_b200.snapshot import SnapshotStore
+    st = SnapshotStore.synthetic("icews14", num_times=12, scale=1, seed=1)
+    e = np.mean([g.num_edges for g in st.train.values()])
+    n = np.mean([g.num_nodes for g in st.train.values()])
+    zero = np.mean([(g.norm == 0).mean() for g in st.train.values()])
+    assert 120 < e < 280 and 140 < n < 320 and 0.3 < zero < 0.6
+    st2 = SnapshotStore.synthetic("icews14", num_times=12, scale=1, seed=1)
+    assert all(np.array_equal(st.train[t].src, st2.train[t].src) for t in st.train)
+    gd = SnapshotStore.synthetic("gdelt", num_times=3, scale=1, seed=2)
+    assert max(np.diff(g.row_ptr).max() for g in gd.train.values()) > 300
+
+
+# ---- ABI surface -------------------------------------------------------------------------------
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "temp_b200.h")).read()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(temp_\w+)\(", text, flags=re.M)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from temp_b200 import build, lib
+    build.build()
+    cdll = ctypes.CDLL(build.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 10
+    for name in names:
+        assert hasattr(cdll, name), name
+    assert sorted(lib.EXPORTS) == names
+    assert lib.load().temp_abi_version() == lib.ABI_VERSION
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof/offsetof of every ABI struct as seen by gcc == the ctypes mirror."""
+    from temp_b200 import lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "temp_b200.h"\nint main(){'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(TempDenseTerm), sizeof(TempRgcnLayerArgs),'
+                   'sizeof(TempGruArgs), sizeof(TempAttnArgs), sizeof(TempGatherArgs), sizeof(TempScatterArgs), sizeof(TempOp),'
+                   'offsetof(TempRgcnLayerArgs, chain_ld), offsetof(TempGruArgs, out), offsetof(TempOp, u));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(lib.DenseTerm), ctypes.sizeof(lib.RgcnLayerArgs), ctypes.sizeof(lib.GruArgs),
+            ctypes.sizeof(lib.AttnArgs), ctypes.sizeof(lib.GatherArgs), ctypes.sizeof(lib.ScatterArgs),
+            ctypes.sizeof(lib.Op), lib.RgcnLayerArgs.chain_ld.offset, lib.GruArgs.out.offset, lib.Op.u.offset]
+    assert got == want
+
+
+def test_encoder_refuses_to_run_without_cuda():
+    """No CPU fallback: the product path must fail loudly."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only process")
+    from tests.helpers import product_model
+    model = product_model(CASES[2], device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        model.encode(CASES[2]["t_list"])
+
+
+def test_state_dict_keys_match_the_reference_shapes():
+    from tests.helpers import oracle_config, product_args
+    from temp_b200.models import build_module
+    for case in CASES:
+        cfg = oracle_config(case)
+        store = product_store(case["dataset"])
+        model = build_module(product_args(case), store.num_ents, store.num_rels, store.train)
+        got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        assert got == orc.param_shapes(cfg), case["name"]
