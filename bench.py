@@ -111,7 +111,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
@@ -143,7 +143,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=1.0)
         med = float(np.median(self.samples)) if self.samples else None
