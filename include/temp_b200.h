@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 3
+#define TEMP_ABI_VERSION 4
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -33,6 +33,7 @@ extern "C" {
 
 #define TEMP_MAX_D 256     /* embed_size == hidden_size upper bound of the SIMT path  */
 #define TEMP_MAX_TERMS 3
+#define TEMP_MAX_SCAN_STEPS 16
 
 #define TEMP_ACT_NONE 0
 #define TEMP_ACT_RELU 1
@@ -119,6 +120,18 @@ typedef struct {
   int32_t out_index_is_row;  /* reserved, must be 1                                               */
 } TempGruArgs;
 
+/* All GRU steps of a window in ONE cooperative launch (persistent CTAs, W_hh^T slices resident in
+ * shared memory across steps, grid-wide barrier between steps).  Replaces the python time-step loop
+ * of pre_forward (DynamicRGCN.py:163-173) for the serial half of the recurrence.
+ *   barrier: 8 bytes of device memory, zero before the first use; the kernel leaves it zeroed.
+ *            Launches sharing one barrier word must not run concurrently.                         */
+typedef struct {
+  int32_t n_steps;
+  int32_t reserved;
+  uint32_t* barrier;
+  TempGruArgs steps[TEMP_MAX_SCAN_STEPS];
+} TempGruScanArgs;
+
 /* Multi-head attention over the time axis for packed rows [row0, row1) (SARGCN.py:25-53):
  *   q, k_cur, v_cur = qkv[r, 0:d], [d:2d], [2d:3d]; history slot s of row r lives at
  *   kv_hist[slot_row[r*n_slots + s]] (k | v), negative = entity inactive (mask -1e10 -> weight 0);
@@ -156,7 +169,7 @@ typedef struct {
 } TempScatterArgs;
 
 enum { TEMP_OP_LAYER = 1, TEMP_OP_GRU = 2, TEMP_OP_ATTN = 3, TEMP_OP_GATHER = 4, TEMP_OP_SCATTER = 5,
-       TEMP_OP_MEMCPY_H2D = 6, TEMP_OP_MEMCPY_D2H = 7 };
+       TEMP_OP_MEMCPY_H2D = 6, TEMP_OP_MEMCPY_D2H = 7, TEMP_OP_GRU_SCAN = 8 };
 
 typedef struct {
   void* dst;
@@ -171,6 +184,7 @@ typedef struct {
   union {
     TempRgcnLayerArgs layer;
     TempGruArgs gru;
+    TempGruScanArgs scan;
     TempAttnArgs attn;
     TempGatherArgs gather;
     TempScatterArgs scatter;
@@ -185,6 +199,7 @@ int temp_device_info(int32_t* sm_count, int32_t* max_smem, int32_t* cc);
 
 int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream);
 int temp_gru_fwd(const TempGruArgs* args, void* stream);
+int temp_gru_scan_fwd(const TempGruScanArgs* args, void* stream);
 int temp_attention_fwd(const TempAttnArgs* args, void* stream);
 int temp_gather_rows(const TempGatherArgs* args, void* stream);
 int temp_scatter_rows(const TempScatterArgs* args, void* stream);

@@ -312,63 +312,143 @@ __global__ void __launch_bounds__(kThreads, 2) rgcn_layer_kernel(const TempRgcnL
 }
 
 // ------------------------------------------------------------------------------------------------
-// GRU recurrent half + gates.  CTA = (RPW*8 rows) x (kGJ hidden columns, all three gates)
+// GRU recurrent half + gates.  Work item = (RPW*8 rows) x (kGJ hidden columns, all three gates)
 // ------------------------------------------------------------------------------------------------
+// this CTA's [D][3*kGJ] slice of W_hh^T -> shared memory (cp.async; caller commits / waits)
+__device__ __forceinline__ void gru_stage_weights(float* Ws, const float* __restrict__ whh_t, int D, int jb) {
+  const int per_k = 3 * kGJ / 4;  // float4 per k row
+  for (int idx = threadIdx.x; idx < D * per_k; idx += kThreads) {
+    const int k = idx / per_k, v = idx - k * per_k;
+    const int g = v / (kGJ / 4), c4 = v - g * (kGJ / 4);
+    const int col = jb + c4 * 4;
+    float* dst = Ws + k * (3 * kGJ) + g * kGJ + c4 * 4;
+    if (col < D) cp_async16(dst, whh_t + static_cast<size_t>(k) * (3 * D) + g * D + col);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ---- one GRU work item, split so that everything that does NOT depend on the recurrence (indices,
+// decay factors, the precomputed input gates, time-embedding rows) is in flight BEFORE the step's
+// dependency point (kernel start / grid barrier) --------------------------------------------------
+constexpr int kGruPre = 4;  // gather elements per thread whose indices are prefetched (TM*D/4 <= 4*256)
+
 template <int RPW>
-__global__ void __launch_bounds__(kThreads, 2) gru_kernel(const TempGruArgs p) {
-  extern __shared__ __align__(16) float smem[];
+struct GruPrefetch {
+  int pr[kGruPre];        // previous-state row per gather element (-1: zero state)
+  float decay[kGruPre];
+  float gi[RPW][3];       // input-gate pre-activations of this thread's rows at its hidden column
+  float te[RPW];          // time-embedding value to add
+  float br, bz, bn;
+};
+
+template <int RPW>
+__device__ __forceinline__ void gru_phase_a(const TempGruArgs& p, int rbase, int jb, GruPrefetch<RPW>& f) {
   constexpr int TM = RPW * 8;
-  const int D = p.d;
-  const int lda = D + 4;
-  float* As = smem;             // [TM][lda]   decayed previous state rows
-  float* Ws = As + TM * lda;    // [D][3*kGJ]  this CTA's slice of W_hh^T
-
-  const int tx = threadIdx.x & 31;
-  const int ty = threadIdx.x >> 5;
-  const int rbase = p.row0 + blockIdx.x * TM;
-  const int jb = blockIdx.y * kGJ;
-  const int nvec = D >> 2;
-
-  int any_prev = 0;
-  for (int idx = threadIdx.x; idx < TM * nvec; idx += kThreads) {
-    const int m = idx / nvec, c4 = idx - m * nvec;
-    const int r = rbase + m;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < p.row1 && p.prev_row != nullptr) {
-      const int pr = __ldg(p.prev_row + r);
-      if (pr >= 0) {
-        any_prev = 1;
-        v = ldg4(p.state + static_cast<size_t>(pr) * D + c4 * 4);
-        if (p.dt != nullptr) {
-          const float f = decay_factor(__ldg(p.dt + r), p.decay_wb, p.inv_temperature);
-          v.x *= f; v.y *= f; v.z *= f; v.w *= f;
-        }
+  const int D = p.d, nvec = D >> 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (TM * nvec <= kGruPre * kThreads) {
+#pragma unroll
+    for (int u = 0; u < kGruPre; ++u) {
+      const int idx = threadIdx.x + u * kThreads;
+      const int r = rbase + idx / nvec;
+      int pr = -1;
+      float dec = 1.f;
+      if (idx < TM * nvec && r < p.row1 && p.prev_row != nullptr) {
+        pr = __ldg(p.prev_row + r);
+        if (p.dt != nullptr) dec = decay_factor(__ldg(p.dt + r), p.decay_wb, p.inv_temperature);
+      }
+      f.pr[u] = pr;
+      f.decay[u] = dec;
+    }
+  }
+  const int j = jb + tx;
+  const bool jok = j < D;
+  f.br = jok ? __ldg(p.b_hh + j) : 0.f;
+  f.bz = jok ? __ldg(p.b_hh + D + j) : 0.f;
+  f.bn = jok ? __ldg(p.b_hh + 2 * D + j) : 0.f;
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = rbase + ty * RPW + i;
+    f.gi[i][0] = f.gi[i][1] = f.gi[i][2] = 0.f;
+    f.te[i] = 0.f;
+    if (jok && r < p.row1) {
+      const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off;
+      f.gi[i][0] = __ldg(gi + j);
+      if (p.cell_type != TEMP_CELL_TYPE1) {
+        f.gi[i][1] = __ldg(gi + D + j);
+        f.gi[i][2] = __ldg(gi + 2 * D + j);
+      }
+      if (p.time_embed != nullptr) {
+        const int trow = p.row_time != nullptr ? __ldg(p.row_time + r) : p.row_time_scalar;
+        f.te[i] = __ldg(p.time_embed + static_cast<size_t>(trow) * D + j);
       }
     }
-    *reinterpret_cast<float4*>(As + m * lda + c4 * 4) = v;
+  }
+}
+
+// previous-state gather (the only loads that depend on the previous step) -> GEMM -> gates -> store
+template <int RPW, bool kCoherent>
+__device__ __forceinline__ void gru_phase_b(const TempGruArgs& p, float* As, int lda, const float* Ws, int rbase,
+                                            int jb, const GruPrefetch<RPW>& f, bool& w_pending) {
+  constexpr int TM = RPW * 8;
+  const int D = p.d, nvec = D >> 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int any_prev = 0;
+  if (TM * nvec <= kGruPre * kThreads) {
+    float4 v[kGruPre];
+#pragma unroll
+    for (int u = 0; u < kGruPre; ++u) {
+      const int idx = threadIdx.x + u * kThreads;
+      const int c4 = idx % nvec;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f.pr[u] >= 0) {
+        any_prev = 1;
+        const float4* src = reinterpret_cast<const float4*>(p.state + static_cast<size_t>(f.pr[u]) * D + c4 * 4);
+        v[u] = kCoherent ? __ldcg(src) : __ldg(src);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGruPre; ++u) {
+      const int idx = threadIdx.x + u * kThreads;
+      if (idx < TM * nvec) {
+        const int m = idx / nvec, c4 = idx - m * nvec;
+        const float d = f.decay[u];
+        *reinterpret_cast<float4*>(As + m * lda + c4 * 4) = make_float4(v[u].x * d, v[u].y * d, v[u].z * d, v[u].w * d);
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < TM * nvec; idx += kThreads) {
+      const int m = idx / nvec, c4 = idx - m * nvec;
+      const int r = rbase + m;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < p.row1 && p.prev_row != nullptr) {
+        const int pr = __ldg(p.prev_row + r);
+        if (pr >= 0) {
+          any_prev = 1;
+          const float4* src = reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * D + c4 * 4);
+          v = kCoherent ? __ldcg(src) : __ldg(src);
+          if (p.dt != nullptr) {
+            const float d = decay_factor(__ldg(p.dt + r), p.decay_wb, p.inv_temperature);
+            v.x *= d; v.y *= d; v.z *= d; v.w *= d;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(As + m * lda + c4 * 4) = v;
+    }
+  }
+  if (w_pending) {
+    cp_async_wait<0>();
+    w_pending = false;
   }
   any_prev = __syncthreads_or(any_prev);
 
   float acc[RPW][3];
 #pragma unroll
   for (int i = 0; i < RPW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
-
   if (any_prev) {
-    const int per_k = 3 * kGJ / 4;  // float4 per k row
-    for (int idx = threadIdx.x; idx < D * per_k; idx += kThreads) {
-      const int k = idx / per_k, v = idx - k * per_k;
-      const int g = v / (kGJ / 4), c4 = v - g * (kGJ / 4);
-      const int col = jb + c4 * 4;
-      float* dst = Ws + k * (3 * kGJ) + g * kGJ + c4 * 4;
-      if (col < D) cp_async16(dst, p.whh_t + static_cast<size_t>(k) * (3 * D) + g * D + col);
-      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
     const float* asb = As + (ty * RPW) * lda;
     const float* wsb = Ws + tx;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < D; k += 4) {
       float4 a[RPW];
 #pragma unroll
@@ -391,32 +471,125 @@ __global__ void __launch_bounds__(kThreads, 2) gru_kernel(const TempGruArgs p) {
 
   const int j = jb + tx;
   if (j < D) {
-    const float br = __ldg(p.b_hh + j), bz = __ldg(p.b_hh + D + j), bn = __ldg(p.b_hh + 2 * D + j);
+    float hy[RPW];
 #pragma unroll
     for (int i = 0; i < RPW; ++i) {
       const int m = ty * RPW + i;
-      const int r = rbase + m;
-      if (r >= p.row1) continue;
       const float h0 = As[m * lda + j];
-      const float hr = acc[i][0] + br, hz = acc[i][1] + bz, hn = acc[i][2] + bn;
-      const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off;
-      float hy;
+      const float hr = acc[i][0] + f.br, hz = acc[i][1] + f.bz, hn = acc[i][2] + f.bn;
       if (p.cell_type == TEMP_CELL_TYPE1) {  // GRU_cell.py:22-29
         const float rg = sigmoidf_(hr), zg = sigmoidf_(hz);
-        const float ng = tanhf(__ldg(gi + j) + rg * hn);
-        hy = ng + zg * (h0 - ng);
+        const float ng = tanhf(f.gi[i][0] + rg * hn);
+        hy[i] = ng + zg * (h0 - ng);
       } else {  // torch.nn.GRU, gate order r, z, n
-        const float rg = sigmoidf_(__ldg(gi + j) + hr);
-        const float zg = sigmoidf_(__ldg(gi + D + j) + hz);
-        const float ng = tanhf(__ldg(gi + 2 * D + j) + rg * hn);
-        hy = (1.f - zg) * ng + zg * h0;
+        const float rg = sigmoidf_(f.gi[i][0] + hr);
+        const float zg = sigmoidf_(f.gi[i][1] + hz);
+        const float ng = tanhf(f.gi[i][2] + rg * hn);
+        hy[i] = (1.f - zg) * ng + zg * h0;
       }
-      if (p.time_embed != nullptr) {
-        const int trow = p.row_time != nullptr ? __ldg(p.row_time + r) : p.row_time_scalar;
-        hy += __ldg(p.time_embed + static_cast<size_t>(trow) * D + j);
+      hy[i] += f.te[i];
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = rbase + ty * RPW + i;
+      if (r < p.row1) {
+        float* o = p.out + static_cast<size_t>(r) * D + j;
+        *o = p.accumulate ? (__ldcg(o) + hy[i]) : hy[i];
       }
-      float* o = p.out + static_cast<size_t>(r) * D + j;
-      *o = p.accumulate ? (*o + hy) : hy;
+    }
+  }
+}
+
+template <int RPW>
+__global__ void __launch_bounds__(kThreads, 2) gru_kernel(const TempGruArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TM = RPW * 8;
+  const int D = p.d;
+  const int lda = D + 4;
+  float* As = smem;             // [TM][lda]   decayed previous state rows
+  float* Ws = As + TM * lda;    // [D][3*kGJ]  this CTA's slice of W_hh^T
+  const int rbase = p.row0 + blockIdx.x * TM;
+  const int jb = blockIdx.y * kGJ;
+  bool w_pending = false;
+  if (p.prev_row != nullptr) {
+    gru_stage_weights(Ws, p.whh_t, D, jb);
+    cp_async_commit();
+    w_pending = true;
+  }
+  GruPrefetch<RPW> f;
+  gru_phase_a<RPW>(p, rbase, jb, f);
+  gru_phase_b<RPW, false>(p, As, lda, Ws, rbase, jb, f, w_pending);
+  if (w_pending) cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent scan: every GRU step of a window in ONE cooperative launch.  CTA c owns hidden-column
+// block (c % JB) for the whole scan (its W_hh^T slice stays in shared memory across steps) and walks
+// row tiles c / JB, c / JB + Q, ...; steps are separated by a grid-wide barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
+    } while (static_cast<int>(v - target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int RPW>
+__global__ void __launch_bounds__(kThreads, 2) gru_scan_kernel(const TempGruScanArgs P) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TM = RPW * 8;
+  const int D = P.steps[0].d;
+  const int lda = D + 4;
+  float* As = smem;
+  float* Ws = As + TM * lda;
+  const int JB = (D + kGJ - 1) / kGJ;
+  const int jb = (blockIdx.x % JB) * kGJ;
+  const int q = blockIdx.x / JB;
+  const int Q = gridDim.x / JB;
+  const float* cur_w = nullptr;
+  unsigned n_bar = 0;
+
+  for (int s = 0; s < P.n_steps; ++s) {
+    const TempGruArgs p = P.steps[s];
+    bool w_pending = false;
+    if (p.whh_t != cur_w && p.prev_row != nullptr) {  // weights are static: stage before the dependency point
+      gru_stage_weights(Ws, p.whh_t, D, jb);
+      cp_async_commit();
+      cur_w = p.whh_t;
+      w_pending = true;
+    }
+    bool need_bar = s > 0;
+    const int ntiles = (p.row1 - p.row0 + TM - 1) / TM;
+    for (int tile = q; tile < ntiles || need_bar; tile += Q) {
+      const bool has = tile < ntiles;
+      const int rbase = p.row0 + tile * TM;
+      GruPrefetch<RPW> f;
+      if (has) gru_phase_a<RPW>(p, rbase, jb, f);
+      if (need_bar) {
+        grid_barrier(P.barrier, (++n_bar) * gridDim.x);
+        need_bar = false;
+      }
+      if (!has) break;
+      gru_phase_b<RPW, true>(p, As, lda, Ws, rbase, jb, f, w_pending);
+      __syncthreads();  // As (and possibly Ws) are rewritten next
+    }
+    if (w_pending) cp_async_wait<0>();
+    __syncthreads();
+  }
+  // self-cleaning barrier words: the last CTA to leave resets them for the next launch
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(P.barrier + 1, 1u);
+    if (done == gridDim.x - 1) {
+      P.barrier[0] = 0u;
+      P.barrier[1] = 0u;
+      __threadfence();
     }
   }
 }
@@ -626,6 +799,62 @@ int launch_gru(const TempGruArgs* a, cudaStream_t st) {
   return TEMP_OK;
 }
 
+int check_gru(const TempGruArgs* a) {
+  if (int rc = check_d(a->d)) return rc;
+  if (a->row1 < a->row0) return fail(TEMP_EINVAL, "row1 < row0%s", "");
+  if (!a->gi || !a->whh_t || !a->b_hh || !a->out) return fail(TEMP_EINVAL, "gru has null pointers%s", "");
+  if (a->prev_row != nullptr && a->state == nullptr) return fail(TEMP_EINVAL, "prev_row without state%s", "");
+  if (!aligned16(a->whh_t) || (a->state && !aligned16(a->state))) return fail(TEMP_EINVAL, "gru buffers misaligned%s", "");
+  if (a->cell_type != TEMP_CELL_TORCH_GRU && a->cell_type != TEMP_CELL_TYPE1) return fail(TEMP_EINVAL, "bad cell_type%s", "");
+  return TEMP_OK;
+}
+
+template <int RPW, int Tag>
+int launch_scan_t(const TempGruScanArgs* a, int max_rows, cudaStream_t st) {
+  const int D = a->steps[0].d;
+  const int TM = RPW * 8;
+  const size_t smem = (static_cast<size_t>(TM) * (D + 4) + static_cast<size_t>(D) * 3 * kGJ) * sizeof(float);
+  if (int rc = ensure_smem<Tag>(gru_scan_kernel<RPW>, smem, "gru_scan_kernel")) return rc;
+  static int sm_count = 0, per_sm = 0;
+  static size_t occ_smem = 0;
+  if (sm_count == 0 || occ_smem != smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_scan_kernel<RPW>, kThreads, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy query");
+    occ_smem = smem;
+  }
+  if (per_sm < 1) return fail(TEMP_EUNSUPPORTED, "gru_scan_kernel does not fit on an SM%s", "");
+  const int JB = (D + kGJ - 1) / kGJ;
+  int want = ((max_rows + TM - 1) / TM) * JB;
+  int cap = (sm_count * per_sm) / JB * JB;
+  int grid = want < cap ? want : cap;
+  if (grid < JB) grid = JB;
+  void* params[] = {const_cast<TempGruScanArgs*>(a)};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gru_scan_kernel<RPW>), dim3(grid), dim3(kThreads),
+                                              params, smem, st);
+  if (e != cudaSuccess) return cuda_fail(e, "gru_scan_kernel launch");
+  return TEMP_OK;
+}
+
+int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
+  if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
+  if (a->n_steps < 0 || a->n_steps > TEMP_MAX_SCAN_STEPS) return fail(TEMP_EINVAL, "n_steps out of range%s", "");
+  if (a->n_steps == 0) return TEMP_OK;
+  if (a->barrier == nullptr) return fail(TEMP_EINVAL, "scan needs a zero-initialised 8-byte barrier word%s", "");
+  int max_rows = 0;
+  for (int s = 0; s < a->n_steps; ++s) {
+    if (int rc = check_gru(&a->steps[s])) return rc;
+    if (a->steps[s].d != a->steps[0].d) return fail(TEMP_EINVAL, "all scan steps must share d%s", "");
+    const int rows = a->steps[s].row1 - a->steps[s].row0;
+    if (rows > max_rows) max_rows = rows;
+  }
+  if (max_rows == 0) return TEMP_OK;
+  if (max_rows <= 148 * 64) return launch_scan_t<4, 3>(a, max_rows, st);
+  return launch_scan_t<8, 4>(a, max_rows, st);
+}
+
 int launch_attn(const TempAttnArgs* a, cudaStream_t st) {
   if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
   if (int rc = check_d(a->d)) return rc;
@@ -705,6 +934,10 @@ int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream) {
 
 int temp_gru_fwd(const TempGruArgs* args, void* stream) { return launch_gru(args, static_cast<cudaStream_t>(stream)); }
 
+int temp_gru_scan_fwd(const TempGruScanArgs* args, void* stream) {
+  return launch_scan(args, static_cast<cudaStream_t>(stream));
+}
+
 int temp_attention_fwd(const TempAttnArgs* args, void* stream) {
   return launch_attn(args, static_cast<cudaStream_t>(stream));
 }
@@ -734,6 +967,7 @@ int temp_run_program(const TempOp* ops, int32_t n, void* stream) {
     switch (ops[i].kind) {
       case TEMP_OP_LAYER: rc = launch_layer(&ops[i].u.layer, st); break;
       case TEMP_OP_GRU: rc = launch_gru(&ops[i].u.gru, st); break;
+      case TEMP_OP_GRU_SCAN: rc = launch_scan(&ops[i].u.scan, st); break;
       case TEMP_OP_ATTN: rc = launch_attn(&ops[i].u.attn, st); break;
       case TEMP_OP_GATHER: rc = launch_gather(&ops[i].u.gather, st); break;
       case TEMP_OP_SCATTER: rc = launch_scatter(&ops[i].u.scatter, st); break;

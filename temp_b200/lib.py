@@ -13,11 +13,12 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
 CELL_TORCH_GRU, CELL_TYPE1 = 0, 1
-OP_LAYER, OP_GRU, OP_ATTN, OP_GATHER, OP_SCATTER, OP_H2D, OP_D2H = 1, 2, 3, 4, 5, 6, 7
+OP_LAYER, OP_GRU, OP_ATTN, OP_GATHER, OP_SCATTER, OP_H2D, OP_D2H, OP_GRU_SCAN = 1, 2, 3, 4, 5, 6, 7, 8
 
 _i32 = C.c_int32
 _p = C.c_void_p
@@ -51,6 +52,10 @@ class GruArgs(C.Structure):
     ]
 
 
+class GruScanArgs(C.Structure):
+    _fields_ = [("n_steps", _i32), ("reserved", _i32), ("barrier", _p), ("steps", GruArgs * MAX_SCAN_STEPS)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("row0", _i32), ("row1", _i32), ("d", _i32), ("heads", _i32),
@@ -73,7 +78,7 @@ class CopyArgs(C.Structure):
 
 
 class _OpUnion(C.Union):
-    _fields_ = [("layer", RgcnLayerArgs), ("gru", GruArgs), ("attn", AttnArgs), ("gather", GatherArgs),
+    _fields_ = [("layer", RgcnLayerArgs), ("gru", GruArgs), ("scan", GruScanArgs), ("attn", AttnArgs), ("gather", GatherArgs),
                 ("scatter", ScatterArgs), ("copy", CopyArgs)]
 
 
@@ -82,7 +87,7 @@ class Op(C.Structure):
 
 
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
-           "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program")
+           "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program")
 
 _lib = None
 
@@ -105,6 +110,7 @@ def load(path: Optional[str] = None):
     lib.temp_device_info.argtypes = [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]
     lib.temp_rgcn_layer_fwd.argtypes = [C.POINTER(RgcnLayerArgs), _p]
     lib.temp_gru_fwd.argtypes = [C.POINTER(GruArgs), _p]
+    lib.temp_gru_scan_fwd.argtypes = [C.POINTER(GruScanArgs), _p]
     lib.temp_attention_fwd.argtypes = [C.POINTER(AttnArgs), _p]
     lib.temp_gather_rows.argtypes = [C.POINTER(GatherArgs), _p]
     lib.temp_scatter_rows.argtypes = [C.POINTER(ScatterArgs), _p]
@@ -152,7 +158,7 @@ class Program(object):
     def add(self, kind: int, args) -> None:
         op = Op()
         op.kind = kind
-        field = {OP_LAYER: "layer", OP_GRU: "gru", OP_ATTN: "attn", OP_GATHER: "gather", OP_SCATTER: "scatter",
+        field = {OP_LAYER: "layer", OP_GRU: "gru", OP_GRU_SCAN: "scan", OP_ATTN: "attn", OP_GATHER: "gather", OP_SCATTER: "scatter",
                  OP_H2D: "copy", OP_D2H: "copy"}[kind]
         setattr(op.u, field, args)
         self.ops.append(op)
@@ -166,7 +172,37 @@ class Program(object):
     def __len__(self):
         return len(self.ops)
 
-    def count(self, kinds=(OP_LAYER, OP_GRU, OP_ATTN, OP_GATHER, OP_SCATTER)) -> int:
+    def fuse_gru_scans(self, barrier_ptr: int) -> None:
+        """Replaces every run of >= 2 consecutive GRU ops by ONE cooperative scan launch."""
+        out, run = [], []
+
+        def flush():
+            while run:
+                chunk, rest = run[:MAX_SCAN_STEPS], run[MAX_SCAN_STEPS:]
+                if len(chunk) == 1:
+                    out.append(chunk[0])
+                else:
+                    a = GruScanArgs()
+                    a.n_steps, a.barrier = len(chunk), barrier_ptr
+                    for i, o in enumerate(chunk):
+                        a.steps[i] = o.u.gru
+                    op = Op()
+                    op.kind = OP_GRU_SCAN
+                    op.u.scan = a
+                    out.append(op)
+                run[:] = rest
+
+        for o in self.ops:
+            if o.kind == OP_GRU:
+                run.append(o)
+            else:
+                flush()
+                out.append(o)
+        flush()
+        self.ops = out
+        self._arr = None
+
+    def count(self, kinds=(OP_LAYER, OP_GRU, OP_GRU_SCAN, OP_ATTN, OP_GATHER, OP_SCATTER)) -> int:
         return sum(1 for o in self.ops if o.kind in kinds)
 
     def run(self, stream: Optional[int] = None) -> None:

@@ -115,6 +115,7 @@ class EncoderRuntime(object):
         lib.load()
         self.ws = Workspace(self.device)
         self.prep = PreparedWeights(model)
+        self.fuse_scan = True      # consecutive GRU steps -> one cooperative persistent launch
 
     # ---- plan upload -----------------------------------------------------------------------------
     def stage_plan(self, plan: WindowPlan, program: lib.Program, tag: str = "plan"):
@@ -231,6 +232,12 @@ class EncoderRuntime(object):
             return self._build_attention(plan, prog, dptr)
         return self._build_recurrent(plan, prog, dptr)
 
+    def scan_barrier(self) -> int:
+        """8 zeroed bytes for the cooperative scan's grid barrier (self-cleaning, see temp_b200.h)."""
+        if getattr(self, "_barrier", None) is None:
+            self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
+        return self._barrier.data_ptr()
+
     def _build_static(self, plan, prog, dptr):
         m, D, R = self.model, self.model.embed_size, plan.R
         enc = m.ent_encoder
@@ -344,6 +351,8 @@ class EncoderRuntime(object):
                 rec_layer(l2, "layer_2", rows, seg, S1, False, None, S, S, relu2, use_te)
         out = S[final.row0:final.row1]
         bufs["state"] = S
+        if self.fuse_scan:
+            prog.fuse_gru_scans(self.scan_barrier())
         return EncodeResult(plan, out, S, prog, bufs)
 
     def _build_attention(self, plan, prog, dptr):
