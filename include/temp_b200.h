@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 4
+#define TEMP_ABI_VERSION 5
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -49,13 +49,17 @@ extern "C" {
  *              exp(-a_dt[r] * inv_temperature)                     (decay_wb == null)
  *              exp(-max(decay_wb[0] * a_dt[r] + decay_wb[1], 0))   (learnable lambda)
  *            reference models/RRGCN.py:83, models/RGCN.py:106-107.
- *   w        [d, d] row-major (in x out), e.g. loop_weight / time_weight as stored.            */
+ *   w        [d, d] row-major (in x out), e.g. loop_weight / time_weight as stored.
+ *   w_packed nullable: the same matrix in the tensor-core operand image written by temp_pack_weights
+ *            (d == 128 only).  When every operand of a launch has its packed image the layer runs on the
+ *            tcgen05 path (3xTF32 split, fp32-level accuracy); otherwise on the fp32 SIMT path.         */
 typedef struct {
   const float* a;
   const int32_t* a_index;
   const float* a_dt;
   const float* decay_wb;
   const float* w;
+  const void* w_packed;
 } TempDenseTerm;
 
 /* Fused RGCN layer over packed rows [row0, row1):
@@ -73,6 +77,7 @@ typedef struct {
   const int32_t* row_ptr;    /* [rows+1] CSR by destination over packed rows (absolute offsets)  */
   const int32_t* e_src;      /* [E] feature row of the edge source inside x                       */
   const int32_t* e_rel;      /* [E]                                                               */
+  const int32_t* e_dst;      /* [E] nullable: destination packed row of the edge (needed by the tcgen05 path) */
   const float* norm;         /* [rows] 1/in_degree (0 when in_degree is 0)                        */
   const float* x;            /* [*, d] source features for the aggregation                        */
   const float* weight;       /* [2*num_rels, n_bases*si*so] block-diagonal relation weights        */
@@ -91,6 +96,7 @@ typedef struct {
   const float* chain_b;      /* nullable [chain_n]                                                */
   float* chain_out;          /* [rows, chain_ld]; columns [0, chain_n) are written                */
   int32_t chain_n, chain_ld;
+  const void* chain_w_packed; /* nullable: chain_w in the temp_pack_weights image (chain_n % 128 == 0) */
   float inv_temperature;
 } TempRgcnLayerArgs;
 
@@ -110,6 +116,7 @@ typedef struct {
   const float* decay_wb;     /* nullable (learnable lambda: weight, bias)                         */
   float inv_temperature;
   const float* whh_t;        /* [d, 3d] row-major = weight_hh transposed                          */
+  const void* whh_packed;    /* nullable: whh_t in the temp_pack_gru_weights image (d == 128)     */
   const float* b_hh;         /* [3d]                                                              */
   int32_t cell_type;
   const float* time_embed;   /* nullable                                                          */
@@ -205,6 +212,14 @@ int temp_gather_rows(const TempGatherArgs* args, void* stream);
 int temp_scatter_rows(const TempScatterArgs* args, void* stream);
 /* out[c, r] = in[r, c]  (weight preparation: weight_ih / weight_hh / q,k,v -> K-major-first)     */
 int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream);
+/* Tensor-core operand images (d == 128).  A [k, n] row-major fp32 matrix (k == 128, n % 128 == 0) is split
+ * into tf32 hi / lo parts and stored, per 128 output features x 32 k, in the K-major SWIZZLE_128B
+ * shared-memory layout the tcgen05 kernels fetch with cp.async.bulk (temp_b200/csrc/tc_common.cuh).
+ * temp_pack_gru_weights packs whh_t [128, 384] per block of 32 hidden columns (rows r|z|n|zero pad).  */
+int64_t temp_packed_weights_bytes(int32_t k, int32_t n);
+int temp_pack_weights(const float* w_kn, int32_t k, int32_t n, void* packed, void* stream);
+int64_t temp_packed_gru_bytes(int32_t d);
+int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* stream);
 /* Runs ops[0..n) back to back on one stream (memcpy ops use cudaMemcpyAsync; host pointers must be
  * pinned for the copies to be asynchronous).  Returns the first failure.                          */
 int temp_run_program(const TempOp* ops_host, int32_t n, void* stream);

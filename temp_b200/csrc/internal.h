@@ -1,0 +1,24 @@
+// temp_b200 -- declarations shared by the translation units of libtemp_b200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "temp_b200.h"
+
+namespace temp_internal {
+
+// thread-local last-error string behind temp_last_error_string()
+int fail(int code, const char* fmt, const char* a = "", long b = 0);
+int cuda_fail(cudaError_t e, const char* what);
+
+// tcgen05 path (tc_kernels.cu).  *_supported() say whether a launch meets the path's preconditions
+// (d == 128, 1x1 relation blocks, one un-decayed dense term, packed operand images present ...);
+// launches that do not are run by the fp32 SIMT kernels of temp_kernels.cu.
+bool tc_layer_supported(const TempRgcnLayerArgs* a);
+int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st);
+bool tc_scan_supported(const TempGruScanArgs* a);
+int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
+int tc_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st);
+int tc_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st);
+
+}  // namespace temp_internal

@@ -12,10 +12,27 @@
 //   attn_kernel       : per-entity multi-head attention over the time slots (online softmax)
 #include "temp_b200.h"
 
+#include "internal.h"
+
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+
+namespace {
+extern thread_local char g_err[512];
+}
+
+namespace temp_internal {
+int fail(int code, const char* fmt, const char* a, long b) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return TEMP_ECUDA;
+}
+}  // namespace temp_internal
 
 namespace {
 
@@ -27,15 +44,8 @@ constexpr int kGJ = 32;    // hidden columns per CTA in the GRU kernel
 
 thread_local char g_err[512] = "";
 
-int fail(int code, const char* fmt, const char* a = "", long b = 0) {
-  snprintf(g_err, sizeof(g_err), fmt, a, b);
-  return code;
-}
-
-int cuda_fail(cudaError_t e, const char* what) {
-  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
-  return TEMP_ECUDA;
-}
+using temp_internal::cuda_fail;
+using temp_internal::fail;
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -760,6 +770,7 @@ int launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
     return fail(TEMP_EINVAL, "layer has no output%s", "");
   }
   if (a->h_out != nullptr && !aligned16(a->h_out)) return fail(TEMP_EINVAL, "h_out misaligned%s", "");
+  if (temp_internal::tc_layer_supported(a)) return temp_internal::tc_launch_layer(a, st);
   const int Kp = (a->d + kKC - 1) / kKC * kKC;
   const size_t smem = (static_cast<size_t>(kTM) * (Kp + 4) * (a->chain_w ? 2 : 1) + 2 * kKC * kNC) * sizeof(float);
   if (int rc = ensure_smem<0>(rgcn_layer_kernel, smem, "rgcn_layer_kernel")) return rc;
@@ -780,6 +791,13 @@ int launch_gru(const TempGruArgs* a, cudaStream_t st) {
   if (a->prev_row != nullptr && a->state == nullptr) return fail(TEMP_EINVAL, "prev_row without state%s", "");
   if (!aligned16(a->whh_t) || (a->state && !aligned16(a->state))) return fail(TEMP_EINVAL, "gru buffers misaligned%s", "");
   if (a->cell_type != TEMP_CELL_TORCH_GRU && a->cell_type != TEMP_CELL_TYPE1) return fail(TEMP_EINVAL, "bad cell_type%s", "");
+  if (a->d == 128 && (a->prev_row == nullptr || a->whh_packed != nullptr)) {
+    TempGruScanArgs one;
+    memset(&one, 0, sizeof(one));
+    one.n_steps = 1;
+    one.steps[0] = *a;
+    if (temp_internal::tc_scan_supported(&one)) return temp_internal::tc_launch_scan(&one, st);
+  }
   const int jblocks = (a->d + kGJ - 1) / kGJ;
   cudaError_t e;
   // small steps: 32-row tiles so that the step still spreads over all SMs
@@ -851,6 +869,7 @@ int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
     if (rows > max_rows) max_rows = rows;
   }
   if (max_rows == 0) return TEMP_OK;
+  if (temp_internal::tc_scan_supported(a)) return temp_internal::tc_launch_scan(a, st);
   if (max_rows <= 148 * 64) return launch_scan_t<4, 3>(a, max_rows, st);
   return launch_scan_t<8, 4>(a, max_rows, st);
 }
@@ -957,6 +976,21 @@ int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int3
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
   return TEMP_OK;
+}
+
+int64_t temp_packed_weights_bytes(int32_t k, int32_t n) {
+  if (k != 128 || n <= 0 || (n & 127)) return -1;
+  return static_cast<int64_t>(n / 128) * 4 * 2 * 128 * 128;
+}
+
+int temp_pack_weights(const float* w_kn, int32_t k, int32_t n, void* packed, void* stream) {
+  return temp_internal::tc_pack_weights(w_kn, k, n, packed, static_cast<cudaStream_t>(stream));
+}
+
+int64_t temp_packed_gru_bytes(int32_t d) { return d == 128 ? static_cast<int64_t>(4) * 4 * 2 * 128 * 128 : -1; }
+
+int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* stream) {
+  return temp_internal::tc_pack_gru_weights(whh_t, d, packed, static_cast<cudaStream_t>(stream));
 }
 
 int temp_run_program(const TempOp* ops, int32_t n, void* stream) {

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -25,19 +25,19 @@ _p = C.c_void_p
 
 
 class DenseTerm(C.Structure):
-    _fields_ = [("a", _p), ("a_index", _p), ("a_dt", _p), ("decay_wb", _p), ("w", _p)]
+    _fields_ = [("a", _p), ("a_index", _p), ("a_dt", _p), ("decay_wb", _p), ("w", _p), ("w_packed", _p)]
 
 
 class RgcnLayerArgs(C.Structure):
     _fields_ = [
         ("row0", _i32), ("row1", _i32), ("d", _i32),
-        ("row_ptr", _p), ("e_src", _p), ("e_rel", _p), ("norm", _p), ("x", _p), ("weight", _p),
+        ("row_ptr", _p), ("e_src", _p), ("e_rel", _p), ("e_dst", _p), ("norm", _p), ("x", _p), ("weight", _p),
         ("n_bases", _i32), ("si", _i32), ("so", _i32), ("residual", _i32), ("n_terms", _i32),
         ("terms", DenseTerm * MAX_TERMS),
         ("h_bias", _p), ("activation", _i32),
         ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32), ("te_out", _i32), ("te_chain", _i32),
         ("h_out", _p), ("chain_w", _p), ("chain_b", _p), ("chain_out", _p), ("chain_n", _i32), ("chain_ld", _i32),
-        ("inv_temperature", C.c_float),
+        ("chain_w_packed", _p), ("inv_temperature", C.c_float),
     ]
 
 
@@ -46,7 +46,7 @@ class GruArgs(C.Structure):
         ("row0", _i32), ("row1", _i32), ("d", _i32),
         ("gi", _p), ("gi_ld", _i32), ("gi_off", _i32),
         ("state", _p), ("prev_row", _p), ("dt", _p), ("decay_wb", _p), ("inv_temperature", C.c_float),
-        ("whh_t", _p), ("b_hh", _p), ("cell_type", _i32),
+        ("whh_t", _p), ("whh_packed", _p), ("b_hh", _p), ("cell_type", _i32),
         ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32),
         ("accumulate", _i32), ("out", _p), ("out_index_is_row", _i32),
     ]
@@ -87,7 +87,8 @@ class Op(C.Structure):
 
 
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
-           "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program")
+           "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
+           "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights")
 
 _lib = None
 
@@ -116,6 +117,12 @@ def load(path: Optional[str] = None):
     lib.temp_scatter_rows.argtypes = [C.POINTER(ScatterArgs), _p]
     lib.temp_transpose.argtypes = [_p, _i32, _i32, _p, _i32, _p]
     lib.temp_run_program.argtypes = [C.POINTER(Op), _i32, _p]
+    lib.temp_packed_weights_bytes.argtypes = [_i32, _i32]
+    lib.temp_packed_weights_bytes.restype = C.c_int64
+    lib.temp_pack_weights.argtypes = [_p, _i32, _i32, _p, _p]
+    lib.temp_packed_gru_bytes.argtypes = [_i32]
+    lib.temp_packed_gru_bytes.restype = C.c_int64
+    lib.temp_pack_gru_weights.argtypes = [_p, _i32, _p, _p]
     if lib.temp_abi_version() != ABI_VERSION:
         raise RuntimeError("temp_b200: ABI version mismatch (library %d, binding %d) -- rebuild"
                            % (lib.temp_abi_version(), ABI_VERSION))

@@ -54,7 +54,7 @@ class WindowPlan(object):
     """Packed arrays (numpy, int32 / float32) + segment table.  ``to_blob`` concatenates them into
     one byte buffer so that the host->device traffic of a forward is a single copy."""
 
-    ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a",
+    ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "e_dst", "prev_a", "dt_a",
               "prev_b", "dt_b", "slot_row")
 
     def __init__(self):
@@ -160,6 +160,8 @@ class _Packer(object):
         plan.e_src = cat(self.esrc, np.int32)
         plan.e_src_ent = cat(self.esrc_ent, np.int32)
         plan.e_rel = cat(self.erel, np.int32)
+        # destination packed row per edge (CSR is by destination, so this is non-decreasing)
+        plan.e_dst = np.repeat(np.arange(self.R, dtype=np.int32), np.diff(rp).astype(np.int64)).astype(np.int32)
         plan.prev_a = cat(self.prev_a, np.int32)
         plan.dt_a = cat(self.dt_a, np.float32)
         if self.prev_b:

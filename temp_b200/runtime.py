@@ -78,6 +78,39 @@ class PreparedWeights(object):
             self._cache[name] = hit
         return hit[1]
 
+    def packed(self, name: str, w_kn: torch.Tensor, src: List[torch.Tensor]) -> Optional[torch.Tensor]:
+        """tcgen05 operand image of a [128, n] row-major matrix (temp_pack_weights), None when the shape has no
+        tensor-core path (the launch then runs on the fp32 SIMT kernels)."""
+        k, n = int(w_kn.shape[0]), int(w_kn.shape[1])
+        nbytes = lib.load().temp_packed_weights_bytes(k, n)
+        if nbytes <= 0:
+            return None
+        key = self._key(src)
+        hit = self._cache.get(name)
+        if hit is None or hit[0] != key:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=w_kn.device)
+            w = w_kn.detach().contiguous()
+            lib.check(lib.load().temp_pack_weights(C.c_void_p(w.data_ptr()), k, n, C.c_void_p(buf.data_ptr()),
+                                                   C.c_void_p(lib.current_stream())), "temp_pack_weights")
+            hit = (key, buf, w)
+            self._cache[name] = hit
+        return hit[1]
+
+    def packed_gru(self, name: str, whh_t: torch.Tensor, src: List[torch.Tensor]) -> Optional[torch.Tensor]:
+        d = int(whh_t.shape[0])
+        nbytes = lib.load().temp_packed_gru_bytes(d)
+        if nbytes <= 0 or int(whh_t.shape[1]) != 3 * d:
+            return None
+        key = self._key(src)
+        hit = self._cache.get(name)
+        if hit is None or hit[0] != key:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=whh_t.device)
+            lib.check(lib.load().temp_pack_gru_weights(C.c_void_p(whh_t.data_ptr()), d, C.c_void_p(buf.data_ptr()),
+                                                       C.c_void_p(lib.current_stream())), "temp_pack_gru_weights")
+            hit = (key, buf)
+            self._cache[name] = hit
+        return hit[1]
+
     def cat(self, name: str, vecs: List[torch.Tensor]) -> torch.Tensor:
         key = self._key(vecs)
         hit = self._cache.get(name)
@@ -115,7 +148,9 @@ class EncoderRuntime(object):
         lib.load()
         self.ws = Workspace(self.device)
         self.prep = PreparedWeights(model)
+        self._chain_packed = {}
         self.fuse_scan = True      # consecutive GRU steps -> one cooperative persistent launch
+        self.use_tc = True         # tcgen05 path where the shapes allow it (d == 128); False: fp32 SIMT kernels only
 
     # ---- plan upload -----------------------------------------------------------------------------
     def stage_plan(self, plan: WindowPlan, program: lib.Program, tag: str = "plan"):
@@ -140,6 +175,7 @@ class EncoderRuntime(object):
             a.row_ptr = dptr["row_ptr"]
             a.e_src = dptr["e_src_ent"] if x_is_embed else dptr["e_src"]
             a.e_rel = dptr["e_rel"]
+            a.e_dst = dptr.get("e_dst")
             a.norm = dptr["norm"]
             a.x = x.data_ptr()
             a.weight = layer.weight.data_ptr()
@@ -161,7 +197,10 @@ class EncoderRuntime(object):
         if h_out is not None:
             a.h_out = h_out.data_ptr()
         if chain is not None:
-            w, b, out, ld = chain
+            w, b, out, ld = chain[:4]
+            pk = self._chain_packed.get(w.data_ptr())
+            if pk is not None:
+                a.chain_w_packed = pk.data_ptr()
             a.chain_w = w.data_ptr()
             a.chain_b = None if b is None else b.data_ptr()
             a.chain_out = out.data_ptr()
@@ -172,6 +211,10 @@ class EncoderRuntime(object):
     def _term(self, a, w, index=None, dt=None, decay_wb=None):
         t = lib.DenseTerm()
         t.a, t.w = a.data_ptr(), w.data_ptr()
+        if self.use_tc and dt is None and tuple(w.shape) == (128, 128):
+            pk = self.prep.packed("term.%d" % w.data_ptr(), w, [w])
+            if pk is not None:
+                t.w_packed = pk.data_ptr()
         t.a_index = index
         t.a_dt = dt
         t.decay_wb = None if decay_wb is None else decay_wb.data_ptr()
@@ -196,7 +239,12 @@ class EncoderRuntime(object):
         a.inv_temperature = float(m.args.inv_temperature)
         whh = rnn.weight_hh if type1 else rnn.weight_hh_l0
         bhh = rnn.bias_hh if type1 else rnn.bias_hh_l0
-        a.whh_t = self.prep.cat_t(layer_name + "." + rnn_name + ".whh_t", [whh]).data_ptr()
+        whh_t = self.prep.cat_t(layer_name + "." + rnn_name + ".whh_t", [whh])
+        a.whh_t = whh_t.data_ptr()
+        if self.use_tc:
+            pk = self.prep.packed_gru(layer_name + "." + rnn_name + ".whh_packed", whh_t, [whh])
+            if pk is not None:
+                a.whh_packed = pk.data_ptr()
         a.b_hh = bhh.data_ptr()
         a.cell_type = lib.CELL_TYPE1 if type1 else lib.CELL_TORCH_GRU
         if te:
@@ -216,7 +264,9 @@ class EncoderRuntime(object):
         ws = [(r.weight_ih if type1 else r.weight_ih_l0) for _, r in rnns]
         bs = [(r.bias_ih if type1 else r.bias_ih_l0) for _, r in rnns]
         tag = layer_name + "." + "+".join(n for n, _ in rnns)
-        return self.prep.cat_t(tag + ".wih_t", ws), self.prep.cat(tag + ".b_ih", bs)
+        w = self.prep.cat_t(tag + ".wih_t", ws)
+        self._chain_packed[w.data_ptr()] = self.prep.packed(tag + ".wih_packed", w, ws) if self.use_tc else None
+        return w, self.prep.cat(tag + ".b_ih", bs)
 
     # ---- programs ----------------------------------------------------------------------------------
     def build(self, plan: WindowPlan, with_h2d: bool = True) -> EncodeResult:
@@ -369,8 +419,13 @@ class EncoderRuntime(object):
         prog.keepalive.append(tau)
 
         def chains(layer, lname):
-            kv = self.prep.cat_t(lname + ".kv_t", [layer.k_linear.weight, layer.v_linear.weight])
-            qkv = self.prep.cat_t(lname + ".qkv_t", [layer.q_linear.weight, layer.k_linear.weight, layer.v_linear.weight])
+            kvw = [layer.k_linear.weight, layer.v_linear.weight]
+            qkvw = [layer.q_linear.weight] + kvw
+            kv = self.prep.cat_t(lname + ".kv_t", kvw)
+            qkv = self.prep.cat_t(lname + ".qkv_t", qkvw)
+            if self.use_tc:
+                self._chain_packed[kv.data_ptr()] = self.prep.packed(lname + ".kv_packed", kv, kvw)
+                self._chain_packed[qkv.data_ptr()] = self.prep.packed(lname + ".qkv_packed", qkv, qkvw)
             kvb = self.ws.get("kv_" + lname, max(Rh, 1) * 2 * D)[:Rh * 2 * D].view(Rh, 2 * D)
             qkvb = self.ws.get("qkv_" + lname, max(nf, 1) * 3 * D)[:nf * 3 * D].view(nf, 3 * D)
             return kv, qkv, kvb, qkvb

@@ -118,7 +118,7 @@ def test_synthetic_generator_shape_statistics():
 # ---- ABI surface -------------------------------------------------------------------------------
 def _header_functions():
     text = open(os.path.join(ROOT, "include", "temp_b200.h")).read()
-    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(temp_\w+)\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(temp_\w+)\(", text, flags=re.M)))
 
 
 def test_library_builds_loads_and_exports_every_declared_symbol():
