@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 5
+#define TEMP_ABI_VERSION 6
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -77,7 +77,7 @@ typedef struct {
   const int32_t* row_ptr;    /* [rows+1] CSR by destination over packed rows (absolute offsets)  */
   const int32_t* e_src;      /* [E] feature row of the edge source inside x                       */
   const int32_t* e_rel;      /* [E]                                                               */
-  const int32_t* e_dst;      /* [E] nullable: destination packed row of the edge (needed by the tcgen05 path) */
+  const int32_t* e_dst;      /* [E] nullable: destination packed row of the edge (unused by the current kernels)   */
   const float* norm;         /* [rows] 1/in_degree (0 when in_degree is 0)                        */
   const float* x;            /* [*, d] source features for the aggregation                        */
   const float* weight;       /* [2*num_rels, n_bases*si*so] block-diagonal relation weights        */
@@ -98,6 +98,8 @@ typedef struct {
   int32_t chain_n, chain_ld;
   const void* chain_w_packed; /* nullable: chain_w in the temp_pack_weights image (chain_n % 128 == 0) */
   float inv_temperature;
+  float* agg_scratch;        /* nullable [>= row1 rows, d] scratch indexed by packed row: the tcgen05 path runs the
+                                aggregation as its own HBM-bound launch and hands it over through this buffer      */
 } TempRgcnLayerArgs;
 
 /* Recurrent half of the GRU for packed rows [row0, row1), fused with the gates:
@@ -125,17 +127,28 @@ typedef struct {
   int32_t accumulate;        /* 1: out += h' (second direction of the Bi centre step)             */
   float* out;                /* [rows, d]                                                         */
   int32_t out_index_is_row;  /* reserved, must be 1                                               */
+  int32_t part_col;          /* column of this step in the scan's chain-partition table (see below) */
 } TempGruArgs;
 
-/* All GRU steps of a window in ONE cooperative launch (persistent CTAs, W_hh^T slices resident in
- * shared memory across steps, grid-wide barrier between steps).  Replaces the python time-step loop
- * of pre_forward (DynamicRGCN.py:163-173) for the serial half of the recurrence.
- *   barrier: 8 bytes of device memory, zero before the first use; the kernel leaves it zeroed.
- *            Launches sharing one barrier word must not run concurrently.                         */
+/* All GRU steps of a window in ONE launch (persistent CTAs, W_hh^T slices resident in shared memory
+ * across steps).  Replaces the python time-step loop of pre_forward (DynamicRGCN.py:163-173) for the
+ * serial half of the recurrence.
+ *   parts  : chain-partition table [n_parts][part_stride][2] int32 (temp_b200/planner.py).  The recurrence
+ *            couples a packed row only with the row of the same entity in the same batch item at the previous
+ *            step (DynamicRGCN.py:35-54), so a batch item cut into entity-id ranges gives independent
+ *            chains: entry (p, steps[s].part_col) = the packed-row range [lo, hi) of partition p at step s,
+ *            at most 96 rows (lo == hi: nothing).  The tcgen05 path (d == 128) gives every partition to
+ *            one 4-CTA cluster and separates steps by a cluster barrier; without the table (or d != 128)
+ *            steps are separated by a grid-wide barrier (cooperative launch).
+ *   barrier: 8 bytes of device memory for the grid-wide barrier, zero before the first use; the kernel
+ *            leaves it zeroed.  Launches sharing one barrier word must not run concurrently.        */
 typedef struct {
   int32_t n_steps;
-  int32_t reserved;
+  int32_t n_parts;
   uint32_t* barrier;
+  const int32_t* parts;
+  int32_t part_stride;
+  int32_t reserved;
   TempGruArgs steps[TEMP_MAX_SCAN_STEPS];
 } TempGruScanArgs;
 
@@ -223,6 +236,8 @@ int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* str
 /* Runs ops[0..n) back to back on one stream (memcpy ops use cudaMemcpyAsync; host pointers must be
  * pinned for the copies to be asynchronous).  Returns the first failure.                          */
 int temp_run_program(const TempOp* ops_host, int32_t n, void* stream);
+/* Number of kernel launches temp_run_program(ops, n) issues (copies excluded); negative on a bad program. */
+int temp_program_kernel_count(const TempOp* ops_host, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@
 //   gru_scan_tc_kernel   : persistent cooperative scan over the GRU steps of a window; CTA = (block of 32 hidden
 //        columns, row tiles of 64); its W_hh slice (r|z|n rows, hi/lo) stays in shared memory for the whole scan.
 #include <stdio.h>
+#include <string.h>
 
 #include "internal.h"
 #include "tc_common.cuh"
@@ -39,6 +40,30 @@ __device__ __forceinline__ float decay_factor(float dt, const float* wb, float i
   return expf(-dt * inv_temperature);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Development-only phase timeline (tools/probe_timeline.py builds a separate library with -DTEMP_TIMELINE):
+// lane 0 of every warp stores clock64() per phase slot; slot 63 holds %globaltimer at kernel entry.
+#ifdef TEMP_TIMELINE
+__device__ unsigned long long* g_timeline = nullptr;
+constexpr int kTlWarps = 12, kTlSlots = 64;
+__device__ __forceinline__ void tl_mark(int slot) {
+  if (g_timeline != nullptr && (threadIdx.x & 31) == 0)
+    g_timeline[(static_cast<size_t>(blockIdx.x) * kTlWarps + (threadIdx.x >> 5)) * kTlSlots + slot] = clock64();
+}
+__device__ __forceinline__ void tl_start() {
+  if (g_timeline != nullptr && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_timeline[(static_cast<size_t>(blockIdx.x) * kTlWarps + (threadIdx.x >> 5)) * kTlSlots + 63] = t;
+  }
+  tl_mark(0);
+}
+#define TL(slot) tl_mark(slot)
+#define TL_START() tl_start()
+#else
+#define TL(slot)
+#define TL_START()
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // weight packing (once per parameter version)
@@ -79,13 +104,66 @@ __global__ void pack_gru_kernel(const float* __restrict__ whh_t, uint8_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// RGCN aggregation (1x1 relation blocks, d == 128): the CSR-by-destination gather
+// ------------------------------------------------------------------------------------------------
+// agg[v] = norm_v * sum_{e: dst_e = v} norm_v * W[rel_e] (.) x[src_e]      (RGCN.py:91-104, diagonal blocks)
+// One warp per destination row, a lane per 4 channels (one 512-byte feature row per load instruction), edge
+// indices fetched lane-parallel, 4 feature-row pairs in flight per warp (32 warps per SM), edges summed in edge-id order (deterministic, no
+// atomics).  Rows without in-edges are not written (the consumer tests row_ptr).  No shared memory, 32 resident
+// warps per SM: this is the HBM / L2-bound part of the layer, kept out of the one-CTA-per-SM tensor-core kernel.
+constexpr int kGatherWarps = 8;
+
+__global__ void __launch_bounds__(kGatherWarps * 32, 4) rgcn_gather_kernel(const TempRgcnLayerArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int r = p.row0 + blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
+  if (r >= p.row1) return;
+  const int p0 = __ldg(p.row_ptr + r), p1 = __ldg(p.row_ptr + r + 1);
+  if (p1 <= p0) return;
+  const float nrm = __ldg(p.norm + r);
+  const float4* x4 = reinterpret_cast<const float4*>(p.x) + lane;
+  const float4* w4 = reinterpret_cast<const float4*>(p.weight) + lane;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = p0; base < p1; base += 32) {
+    const int cnt = min(32, p1 - base);
+    int s = 0, rl = 0;
+    if (lane < cnt) {
+      s = __ldg(p.e_src + base + lane);
+      rl = __ldg(p.e_rel + base + lane);
+    }
+#pragma unroll 1
+    for (int u0 = 0; u0 < cnt; u0 += 4) {
+      float4 hv[4], wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int su = __shfl_sync(kFull, s, (u0 + u) & 31), ru = __shfl_sync(kFull, rl, (u0 + u) & 31);
+        if (u0 + u < cnt) {
+          hv[u] = __ldg(x4 + static_cast<size_t>(su) * (kD / 4));
+          wv[u] = __ldg(w4 + static_cast<size_t>(ru) * (kD / 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u0 + u < cnt) {  // msg = (h * w) * norm_e, summed in edge order (RGCN.py:92-97)
+          a.x += (hv[u].x * wv[u].x) * nrm;
+          a.y += (hv[u].y * wv[u].y) * nrm;
+          a.z += (hv[u].z * wv[u].z) * nrm;
+          a.w += (hv[u].w * wv[u].w) * nrm;
+        }
+      }
+    }
+  }
+  a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;  // apply_func (RGCN.py:103-104)
+  reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * kD)[lane] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused RGCN layer, tcgen05
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileRows = 128;
 constexpr int kWorkerWarps = 8;
 constexpr int kWorkers = kWorkerWarps * 32;
 // Registers are allocated per 4 warps: 3 warpgroups of 168.  The control warpgroup (TMA warp 8, MMA warp 9, two idle
-// warps) hands its registers to the two worker warpgroups with setmaxnreg (56 / 224).
+// warps) hands registers to the two worker warpgroups with setmaxnreg (88 / 208; 56 made the MMA issue loop spill).
 constexpr int kLayerThreads = kWorkers + 128;
 constexpr int kStages = 3;
 constexpr int kBImage = kTileRows * kD * 4;             // 64 KB: one hi (or lo) image of the activation tile
@@ -109,6 +187,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rbase = p.row0 + blockIdx.x * kTileRows;
   const int n_mb = p.chain_w_packed != nullptr ? p.chain_n >> 7 : 0;
+  TL_START();
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -129,9 +208,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = S.tmem_base;
+  TL(1);
 
   if (warp >= kWorkerWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 8 && lane == 0) {
       // ===== TMA producer: GEMM1 weight chunks, then the chain's, in the order the MMA warp consumes them =====
       {
@@ -155,6 +235,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
       int i = 0;
       mbar_wait(&S.b_ready, 0);
       tc_fence_after();
+      TL(2);
       for (int ka = 0; ka < kKAtoms; ++ka, ++i) {
         const int st = i % kStages;
         mbar_wait(&S.w_full[st], (i / kStages) & 1);
@@ -163,9 +244,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
         umma_commit(&S.w_empty[st]);
       }
       umma_commit(&S.d1_full);
+      TL(3);
       if (n_mb > 0) {
         mbar_wait(&S.x_ready, 0);
         tc_fence_after();
+        TL(5);
         for (int mb = 0; mb < n_mb; ++mb) {
           const int slot = mb % 3;
           if (mb >= 3) {
@@ -181,134 +264,65 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
             umma_commit(&S.w_empty[st]);
           }
           umma_commit(&S.d2_full[slot]);
+          TL(6 + (mb < 3 ? mb : 3));
         }
       }
     }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ===== workers: warp (q, hf) owns feature block q (TMEM lane quadrant) of rows [64 hf, 64 hf + 64) =====
     const int q = warp & 3, hf = warp >> 2;
     const int f = 32 * q + lane;
     const int R0 = rbase + 64 * hf;
     const uint32_t my_off = static_cast<uint32_t>(q) * (kTileRows * 128);  // k-atom q of the activation tile
+    const uint32_t sb_hi = smem_u32(b_hi) + my_off, sb_lo = smem_u32(b_lo) + my_off;
+    const uint32_t lane_base = tbase + (static_cast<uint32_t>(32 * q) << 16);
 
-    // ---- 1. self-loop operand rows -> shared memory (hi / lo) ---------------------------------------
+    // ---- 1. self-loop operand rows -> shared memory (hi / lo), 32 row loads in flight ---------------------
     {
       const TempDenseTerm& tm = p.terms[0];
       const int ra = R0 + lane, rb = R0 + 32 + lane;
       const int idxA = ra < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + ra) : ra) : -1;
       const int idxB = rb < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + rb) : rb) : -1;
-#pragma unroll
+      // (loops are kept rolled on purpose: the fully unrolled kernel was instruction-fetch bound)
+#pragma unroll 1
       for (int b = 0; b < 4; ++b) {
         float v[16];
+        const int idx = b < 2 ? idxA : idxB;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int j = 16 * b + i;
-          const int s = __shfl_sync(kFull, j < 32 ? idxA : idxB, j & 31);
-          v[i] = s >= 0 ? __ldg(tm.a + static_cast<size_t>(s) * kD + f) : 0.f;
+          const int sr = __shfl_sync(kFull, idx, (16 * b + i) & 31);
+          v[i] = sr >= 0 ? __ldg(tm.a + static_cast<size_t>(sr) * kD + f) : 0.f;
         }
+        // rows 64 hf + 16 b + i: 8-row group (2 b + (i >> 3)), row in group (i & 7)
+        const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * b)) * 1024u;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int j = 16 * b + i;
           float hi, lo;
           split_tf32(v[i], hi, lo);
-          const uint32_t off = my_off + sw128_off(64 * hf + j, lane);
-          *reinterpret_cast<float*>(b_hi + off) = hi;
-          *reinterpret_cast<float*>(b_lo + off) = lo;
+          const uint32_t off = grp + sw128_off(i, lane);
+          sts_f32(sb_hi + off, hi);
+          sts_f32(sb_lo + off, lo);
         }
       }
       fence_proxy_async();
       mbar_arrive(&S.b_ready);
+      TL(2);
     }
 
-    // ---- 2. aggregation: agg[j] = norm_j * sum_e (x[src_e] * W[rel_e]) * norm_j  (RGCN.py:91-104) -------
-    // Edges of the warp's 64 rows are one contiguous CSR range, walked in order (= the reference's
-    // summation order); indices are fetched lane-parallel 32 at a time, feature rows 8 edges at a time.
-    float agg[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) agg[j] = 0.f;
+    // ---- 2. the aggregate agg[r] = norm_r * sum_e (x[src_e] * W[rel_e]) * norm_r was written by rgcn_gather_kernel
+    // (rows with in-edges only): bit j of `has` = row R0 + j has in-edges.
+    unsigned long long has = 0ull;
     if (p.row_ptr != nullptr) {
       const int ra = min(R0 + lane, p.row1), rb = min(R0 + 32 + lane, p.row1);
-      const float nA = ra < p.row1 ? __ldg(p.norm + ra) : 0.f;
-      const float nB = rb < p.row1 ? __ldg(p.norm + rb) : 0.f;
-      const int e_begin = __ldg(p.row_ptr + min(R0, p.row1));
-      const int e_end = __ldg(p.row_ptr + min(R0 + 64, p.row1));
-      float a8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a8[i] = 0.f;
-      int cur_grp = 0;
-
-      auto flush = [&](int g) {  // g is warp-uniform
-        float nr[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = 8 * g + i;
-          const float x0 = __shfl_sync(kFull, nA, j & 31), x1 = __shfl_sync(kFull, nB, j & 31);
-          nr[i] = j < 32 ? x0 : x1;
-        }
-        switch (g) {
-#define TEMP_FLUSH_CASE(G)                                       \
-  case G:                                                        \
-    _Pragma("unroll") for (int i = 0; i < 8; ++i) agg[8 * G + i] = a8[i] * nr[i]; \
-    break;
-          TEMP_FLUSH_CASE(0)
-          TEMP_FLUSH_CASE(1)
-          TEMP_FLUSH_CASE(2)
-          TEMP_FLUSH_CASE(3)
-          TEMP_FLUSH_CASE(4)
-          TEMP_FLUSH_CASE(5)
-          TEMP_FLUSH_CASE(6)
-          TEMP_FLUSH_CASE(7)
-#undef TEMP_FLUSH_CASE
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a8[i] = 0.f;
-      };
-
-      for (int base = e_begin; base < e_end; base += 32) {
-        const int me = base + lane;
-        const bool ok = me < e_end;
-        const int s = ok ? __ldg(p.e_src + me) : 0;
-        const int rl = ok ? __ldg(p.e_rel + me) : 0;
-        const int dj = ok ? __ldg(p.e_dst + me) - R0 : 0;  // local destination row, 0..63, non-decreasing
-        const float t0 = __shfl_sync(kFull, nA, dj & 31), t1 = __shfl_sync(kFull, nB, dj & 31);
-        const float en = dj < 32 ? t0 : t1;                // edge norm = norm of the destination (utils.py:23-28)
-        const int cnt = min(32, e_end - base);
-        for (int u0 = 0; u0 < cnt; u0 += 8) {
-          float xv[8], wv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int uu = u0 + u;
-            const int su = __shfl_sync(kFull, s, uu & 31), ru = __shfl_sync(kFull, rl, uu & 31);
-            const bool v = uu < cnt;
-            xv[u] = v ? __ldg(p.x + static_cast<size_t>(su) * kD + f) : 0.f;
-            wv[u] = v ? __ldg(p.weight + static_cast<size_t>(ru) * kD + f) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int uu = u0 + u;
-            const int dju = __shfl_sync(kFull, dj, uu & 31);
-            const float nu = __shfl_sync(kFull, en, uu & 31);
-            if (uu < cnt) {
-              const float m = (xv[u] * wv[u]) * nu;
-              const int grp = dju >> 3, i8 = dju & 7;
-              while (cur_grp != grp) {
-                flush(cur_grp);
-                ++cur_grp;
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a8[i] += (i == i8) ? m : 0.f;
-            }
-          }
-        }
-      }
-      while (cur_grp < 8) {
-        flush(cur_grp);
-        ++cur_grp;
-      }
+      const int pa0 = __ldg(p.row_ptr + ra), pa1 = __ldg(p.row_ptr + min(ra + 1, p.row1));
+      const int pb0 = __ldg(p.row_ptr + rb), pb1 = __ldg(p.row_ptr + min(rb + 1, p.row1));
+      has = static_cast<unsigned long long>(__ballot_sync(kFull, pa1 > pa0)) |
+            (static_cast<unsigned long long>(__ballot_sync(kFull, pb1 > pb0)) << 32);
     }
 
+    TL(3);
     // ---- 3. epilogue 1: out = act(agg (+x) + x . W_loop + bias) ; h_out ; chain operand X ---------------
     const float bias = p.h_bias != nullptr ? __ldg(p.h_bias + f) : 0.f;
     const bool need_te = (p.te_out | p.te_chain) != 0;
@@ -317,29 +331,36 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
       rtA = __ldg(p.row_time + min(R0 + lane, p.row1 - 1));
       rtB = __ldg(p.row_time + min(R0 + 32 + lane, p.row1 - 1));
     }
+    // rows of a tile mostly share a snapshot, i.e. a time-embedding row: reload on change only
+    int cur_trow = need_te ? __shfl_sync(kFull, rtA, 0) : -1;
+    float cur_te = need_te ? __ldg(p.time_embed + static_cast<size_t>(cur_trow) * kD + f) : 0.f;
     mbar_wait(&S.d1_full, 0);
     tc_fence_after();
-    int cur_trow = -1;       // rows of a tile mostly share a snapshot, i.e. a time-embedding row: reload on change only
-    float cur_te = 0.f;
+    TL(4);
+    const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * kD + f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float v[16], ag[16];
+      const unsigned h16 = static_cast<unsigned>(has >> (16 * c)) & 0xffffu;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(tbase + (static_cast<uint32_t>(32 * q) << 16) + 64 * hf + 32 * c, v);
+      for (int i = 0; i < 16; ++i) ag[i] = ((h16 >> i) & 1u) ? __ldg(agg_col + (16 * c + i) * kD) : 0.f;
+      tmem_ld16(lane_base + 64 * hf + 16 * c, v);
       tmem_ld_wait();
+      const int rt = c < 2 ? rtA : rtB;
+      const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * c)) * 1024u;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int j = 32 * c + i;
-        const int r = R0 + j;
-        const uint32_t off = my_off + sw128_off(64 * hf + j, lane);
+      for (int i = 0; i < 16; ++i) {
+        const int r = R0 + 16 * c + i;
+        const uint32_t off = grp + sw128_off(i, lane);
         if (need_te) {
-          const int trow = __shfl_sync(kFull, c == 0 ? rtA : rtB, i);  // warp-uniform
+          const int trow = __shfl_sync(kFull, rt, (16 * c + i) & 31);  // warp-uniform
           if (trow != cur_trow) {
             cur_trow = trow;
             cur_te = __ldg(p.time_embed + static_cast<size_t>(trow) * kD + f);
           }
         }
-        float val = agg[j];
-        if (p.residual) val += *reinterpret_cast<const float*>(b_hi + off) + *reinterpret_cast<const float*>(b_lo + off);
+        float val = ag[i];
+        if (p.residual) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
         val += v[i];
         val += bias;
         if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
@@ -348,12 +369,13 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
           const float xx = r < p.row1 ? (p.te_chain ? val + cur_te : val) : 0.f;
           float hi, lo;
           split_tf32(xx, hi, lo);
-          *reinterpret_cast<float*>(b_hi + off) = hi;
-          *reinterpret_cast<float*>(b_lo + off) = lo;
+          sts_f32(sb_hi + off, hi);
+          sts_f32(sb_lo + off, lo);
         }
       }
     }
 
+    TL(5);
     // ---- 4. chain epilogues: chain_out[r, 128 mb + f] = D2 + chain_b -----------------------------------
     if (n_mb > 0) {
       fence_proxy_async();
@@ -363,19 +385,21 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
         const float cbias = p.chain_b != nullptr ? __ldg(p.chain_b + 128 * mb + f) : 0.f;
         mbar_wait(&S.d2_full[slot], (mb / 3) & 1);
         tc_fence_after();
-#pragma unroll
+        TL(6 + 2 * (mb < 3 ? mb : 3));
+        float* orow = p.chain_out + static_cast<size_t>(R0) * p.chain_ld + 128 * mb + f;
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           float v[32];
-          tmem_ld32(tbase + (static_cast<uint32_t>(32 * q) << 16) + 128 + 128 * slot + 64 * hf + 32 * c, v);
+          tmem_ld32(lane_base + 128 + 128 * slot + 64 * hf + 32 * c, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int r = R0 + 32 * c + i;
-            if (r < p.row1) p.chain_out[static_cast<size_t>(r) * p.chain_ld + 128 * mb + f] = v[i] + cbias;
+            if (R0 + 32 * c + i < p.row1) orow[static_cast<size_t>(32 * c + i) * p.chain_ld] = v[i] + cbias;
           }
         }
         tc_fence_before();
         mbar_arrive(&S.d2_empty[slot]);
+        TL(7 + 2 * (mb < 3 ? mb : 3));
       }
     }
   }
@@ -386,70 +410,145 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
 }
 
 // ------------------------------------------------------------------------------------------------
-// persistent GRU scan, tcgen05
+// chain-partitioned GRU scan, tcgen05
 // ------------------------------------------------------------------------------------------------
-constexpr int kScanN = 64;                     // packed rows per tile (UMMA N)
+// The recurrence couples a packed row only with the row of the SAME entity in the SAME batch item at the previous
+// step (prev_row), never with other rows.  The planner therefore cuts every batch item into "chain partitions"
+// (entity-id ranges): per scan step a partition owns one contiguous row range of at most kScanN rows and no
+// dependency ever crosses a partition.  One cluster of 4 CTAs (one per block of 32 hidden columns, its W_hh
+// slice resident in shared memory) walks all steps of a partition; steps are separated by a hardware cluster
+// barrier (release / acquire, ~0.2 us) instead of a grid-wide barrier, and different partitions never synchronise.
+constexpr int kScanN = 96;                     // max packed rows per partition step (UMMA N)
+constexpr int kScanCluster = 4;                // CTAs per cluster = blocks of 32 hidden columns
 constexpr int kScanThreads = kWorkers + 128;   // 8 worker warps + control warp (TMA + MMA issue) + 3 idle (register
                                                // allocation is per 4 warps anyway)
+constexpr int kScanU = kScanN / kWorkerWarps;  // rows per worker thread and step
 constexpr int kScanAImage = kKAtoms * kWChunkBytes;   // 128 KB: this CTA's W_hh slice (r|z|n|pad rows, hi + lo)
-constexpr int kScanBImage = kScanN * kD * 4;   // 32 KB per hi / lo
-constexpr int kScanExBytes = 3 * kScanN * 32 * 4;
-constexpr int kScanSmem = kScanAImage + 2 * kScanBImage + kScanExBytes + 1024;
+constexpr int kScanBImage = kScanN * kD * 4;   // 48 KB per hi / lo
+constexpr int kScanExBytes = 3 * kScanN * 32 * 4;     // gate exchange buffer, aliased onto the hi operand image
+constexpr int kScanSmem = kScanAImage + 2 * kScanBImage + 1024;
+static_assert(kScanExBytes <= kScanBImage, "the exchange buffer lives in the (dead) hi operand image");
+static_assert(kScanN % 16 == 0 && kScanN % kWorkerWarps == 0 && kScanU <= 32, "tile shape");
 
 struct ScanBars {
   uint64_t w_full, mma_done;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
-    } while (static_cast<int>(v - target) < 0);
-    __threadfence();
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// fast gate math: ex2.approx / rcp.approx based, absolute error ~1e-7 (the parity bar is 1e-4 relative)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// What the gather of a step needs, fetched one step ahead (while the previous step's MMA runs) so that the serial
+// chain per step is only: cluster barrier -> L2 gather of the previous state -> MMA -> gates -> state write.
+struct ScanPre {
+  int prv;      // lanes 0..kScanU-1: previous-state row of tile row (warp + 8 * lane), -1 = zero state
+  float dt;     // lanes 0..kScanU-1: its time gap (the decay factor is computed at use)
+};
+
+__device__ __forceinline__ void scan_prefetch(const TempGruArgs& p, int rb, int r1, int warp, int lane, ScanPre& f) {
+  f.prv = -1;
+  f.dt = 0.f;
+  if (lane < kScanU) {
+    const int r = rb + warp + 8 * lane;
+    if (r < r1 && p.prev_row != nullptr) {
+      f.prv = __ldg(p.prev_row + r);
+      if (p.dt != nullptr) f.dt = __ldg(p.dt + r);
+    }
   }
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kScanThreads, 1) gru_scan_tc_kernel(const TempGruScanArgs P) {
+__global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThreads, 1)
+    gru_scan_tc_kernel(const TempGruScanArgs P, const int n_parts) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* a_img = smem;
   uint8_t* b_hi = a_img + kScanAImage;
   uint8_t* b_lo = b_hi + kScanBImage;
-  float* ex = reinterpret_cast<float*>(b_lo + kScanBImage);  // [3 gates][64 rows][32 hidden]
+  float* ex = reinterpret_cast<float*>(b_hi);  // [3 gates][kScanN rows][32 hidden], valid between mma_done and the next gather
   __shared__ ScanBars S;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool worker = warp < kWorkerWarps;
-  const int cb = blockIdx.x & 3, jb = 32 * cb;
-  const int tq = blockIdx.x >> 2, Q = gridDim.x >> 2;
+  const int cb = blockIdx.x & (kScanCluster - 1), jb = 32 * cb;   // == %cluster_ctarank for a 1-D grid
+  const int cid = blockIdx.x / kScanCluster, n_clusters = gridDim.x / kScanCluster;
 
   if (tid == 0) {
     mbar_init(&S.w_full, 1);
     mbar_init(&S.mma_done, 1);
     fence_mbar_init();
   }
-  if (warp == kWorkerWarps) tmem_alloc(&S.tmem_base, kScanN);
+  if (warp == kWorkerWarps) tmem_alloc(&S.tmem_base, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = S.tmem_base;
-  const uint32_t idesc = umma_idesc_tf32(128, kScanN);
+  TL_START();
+
+  // Row range of (partition, step); lane s of every warp keeps the range of step s of the current partition.
+  auto load_ranges = [&](int part) -> int2 {
+    int2 mine = make_int2(0, 0);
+    if (part < n_parts) {
+      for (int s = 0; s < P.n_steps; ++s) {
+        int2 rg;
+        if (P.parts != nullptr) {
+          rg = __ldg(reinterpret_cast<const int2*>(P.parts) + static_cast<size_t>(part) * P.part_stride + P.steps[s].part_col);
+        } else {  // single step without a partition table: plain row tiles
+          rg.x = P.steps[s].row0 + part * kScanN;
+          rg.y = min(rg.x + kScanN, P.steps[s].row1);
+        }
+        if (lane == s) mine = rg;
+      }
+    }
+    return mine;
+  };
+  // first step >= s of the partition that has rows (n_steps when none)
+  auto next_step = [&](int2 ranges, int s) -> int {
+    const unsigned has = __ballot_sync(kFull, ranges.y > ranges.x) & ~((1u << s) - 1u);
+    return has != 0u ? __ffs(has) - 1 : P.n_steps;
+  };
 
   const void* cur_w = nullptr;
   uint32_t w_phase = 0, mma_phase = 0;
   bool w_pending = false;
-  unsigned n_bar = 0;
+  bool arrived = false;  // a cluster-barrier arrive that has not been waited on yet
 
-  for (int s = 0; s < P.n_steps; ++s) {
-    const TempGruArgs p = P.steps[s];
+  int part = cid;
+  int2 ranges = load_ranges(part);
+  int s = next_step(ranges, 0);
+  while (part < n_parts && s >= P.n_steps) {  // skip empty partitions
+    part += n_clusters;
+    ranges = load_ranges(part);
+    s = next_step(ranges, 0);
+  }
+  ScanPre cur;
+  if (part < n_parts && worker)
+    scan_prefetch(P.steps[s], __shfl_sync(kFull, ranges.x, s), __shfl_sync(kFull, ranges.y, s), warp, lane, cur);
+
+#pragma unroll 1
+  while (part < n_parts) {
+    const TempGruArgs& p = P.steps[s];
+    const int rb = __shfl_sync(kFull, ranges.x, s), r1 = __shfl_sync(kFull, ranges.y, s);
+    // successor in the (partition, step) sequence of this cluster
+    int n_part = part, n_s = s + 1 < P.n_steps ? next_step(ranges, s + 1) : P.n_steps;
+    int2 n_ranges = ranges;
+    while (n_s >= P.n_steps) {
+      n_part += n_clusters;
+      if (n_part >= n_parts) break;
+      n_ranges = load_ranges(n_part);
+      n_s = next_step(n_ranges, 0);
+    }
+
     if (p.prev_row != nullptr && p.whh_packed != cur_w) {
-      // every MMA that read the old image has completed (mma_done is waited on inside each tile)
+      // every MMA that read the old image has completed (mma_done is waited on inside each step); a copy that
+      // no step consumed (its steps had no previous state at all) is drained before the buffer is refilled
+      if (w_pending) {
+        if (tid == kWorkers) mbar_wait(&S.w_full, w_phase);
+        w_phase ^= 1;
+      }
       if (tid == kWorkers) {
         const uint8_t* src = static_cast<const uint8_t*>(p.whh_packed) + static_cast<size_t>(cb) * kScanAImage;
         mbar_expect_tx(&S.w_full, kScanAImage);
@@ -459,173 +558,191 @@ __global__ void __launch_bounds__(kScanThreads, 1) gru_scan_tc_kernel(const Temp
       w_pending = true;
     }
     const bool type1 = p.cell_type == TEMP_CELL_TYPE1;
-    bool need_bar = s > 0;
-    const int ntiles = (p.row1 - p.row0 + kScanN - 1) / kScanN;
-    for (int tile = tq; tile < ntiles || need_bar; tile += Q) {
-      const bool has = tile < ntiles;
-      const int rb = p.row0 + tile * kScanN;
+    TL(2 + 6 * (s & 7));
+    if (arrived) {  // the other column blocks' state writes of the previous step become visible here; also every
+      cluster_wait();  // thread of this CTA is past its reads of the operand tile and of the exchange buffer
+      arrived = false;
+    }
+    TL(3 + 6 * (s & 7));
 
-      // ---- phase A: everything that does not depend on the previous step ---------------------------
-      // worker (w, lane): gate math for hidden column jb + lane of rows rb + w + 8u (u = 0..7); the same rows
-      // are the ones whose previous state this warp gathers (lane = 4 feature columns).
-      float gi_r[8], gi_z[8], gi_n[8], tev[8];
-      float br = 0.f, bz = 0.f, bn = 0.f;
-      int prv = -1;
-      float dec = 1.f;
-      if (has && worker) {
-        const int j = jb + lane;
-        br = __ldg(p.b_hh + j);
-        bz = __ldg(p.b_hh + kD + j);
-        bn = __ldg(p.b_hh + 2 * kD + j);
-        if (lane < 8) {
-          const int r = rb + warp + 8 * lane;
-          if (r < p.row1 && p.prev_row != nullptr) {
-            prv = __ldg(p.prev_row + r);
-            if (p.dt != nullptr) dec = decay_factor(__ldg(p.dt + r), p.decay_wb, p.inv_temperature);
+    // ---- previous-state rows -> smem operand (hi / lo) ------------------------------------------------------
+    // worker (w, lane) gathers rows rb + w + 8u (lane = 4 feature columns) and later does the gate math for
+    // hidden column jb + lane of the same rows.
+    int any_prev = 0;
+    if (worker) {
+      float4 v[kScanU];
+      const float dec = p.dt != nullptr ? decay_factor(cur.dt, p.decay_wb, p.inv_temperature) : 1.f;
+#pragma unroll
+      for (int u = 0; u < kScanU; ++u) {
+        const int pr = __shfl_sync(kFull, cur.prv, u);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pr >= 0) {
+          any_prev = 1;
+          v[u] = __ldcg(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD + 4 * lane));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kScanU; ++u) {
+        const int i = warp + 8 * u;
+        const float dv = __shfl_sync(kFull, dec, u);
+        float4 hi, lo;
+        split_tf32(v[u].x * dv, hi.x, lo.x);
+        split_tf32(v[u].y * dv, hi.y, lo.y);
+        split_tf32(v[u].z * dv, hi.z, lo.z);
+        split_tf32(v[u].w * dv, hi.w, lo.w);
+        const uint32_t off = static_cast<uint32_t>(lane >> 3) * (kScanN * 128) + (i >> 3) * 1024u + (i & 7) * 128u +
+                             (((lane & 7) ^ (i & 7)) << 4);
+        *reinterpret_cast<float4*>(b_hi + off) = hi;
+        *reinterpret_cast<float4*>(b_lo + off) = lo;
+      }
+      fence_proxy_async();
+    }
+    any_prev = __syncthreads_or(any_prev);
+    TL(4 + 6 * (s & 7));
+    if (any_prev && tid == kWorkers) {
+      if (w_pending) mbar_wait(&S.w_full, w_phase);
+      tc_fence_after();
+      // N = the step's rows rounded up to 16: operand rows / accumulator columns beyond it are never read
+      const uint32_t idesc = umma_idesc_tf32(128, min(kScanN, (r1 - rb + 15) & ~15));
+      const uint32_t ai = smem_u32(a_img), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      for (int ka = 0; ka < kKAtoms; ++ka)
+        umma_katom_3x(tbase, ai + ka * kWChunkBytes, bh + ka * (kScanN * 128), bl + ka * (kScanN * 128), idesc, ka == 0);
+      umma_commit(&S.mma_done);
+    }
+    if (any_prev && w_pending) {
+      w_pending = false;
+      w_phase ^= 1;
+    }
+    // ---- while the MMA runs: this thread's h0 values and input-gate pre-activations; the NEXT step's indices ----
+    float h0[kScanU], gi_r[kScanU], gi_z[kScanU], gi_n[kScanU], tev[kScanU];
+    float br = 0.f, bz = 0.f, bn = 0.f;
+    ScanPre nxt;
+    if (worker) {
+      const int j = jb + lane;
+#pragma unroll
+      for (int u = 0; u < kScanU; ++u) {
+        h0[u] = 0.f;
+        if (any_prev) {
+          const uint32_t off = static_cast<uint32_t>(cb) * (kScanN * 128) + sw128_off(warp + 8 * u, lane);
+          h0[u] = *reinterpret_cast<const float*>(b_hi + off) + *reinterpret_cast<const float*>(b_lo + off);
+        }
+      }
+      br = __ldg(p.b_hh + j);
+      bz = __ldg(p.b_hh + kD + j);
+      bn = __ldg(p.b_hh + 2 * kD + j);
+      // rows of one partition step belong to one snapshot instance: a single time-embedding row (checked)
+      int trow0 = p.row_time_scalar, trow1 = p.row_time_scalar;
+      if (p.time_embed != nullptr && p.row_time != nullptr) {
+        trow0 = __ldg(p.row_time + rb);
+        trow1 = __ldg(p.row_time + r1 - 1);
+      }
+#pragma unroll
+      for (int u = 0; u < kScanU; ++u) {
+        const int r = rb + warp + 8 * u;
+        gi_r[u] = gi_z[u] = gi_n[u] = 0.f;
+        if (r < r1) {
+          const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
+          if (type1) {
+            gi_n[u] = __ldg(gi);
+          } else {
+            gi_r[u] = __ldg(gi);
+            gi_z[u] = __ldg(gi + kD);
+            gi_n[u] = __ldg(gi + 2 * kD);
           }
         }
+      }
+      if (n_part < n_parts)
+        scan_prefetch(P.steps[n_s], __shfl_sync(kFull, n_ranges.x, n_s), __shfl_sync(kFull, n_ranges.y, n_s), warp, lane, nxt);
+      if (p.time_embed == nullptr) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kScanU; ++u) tev[u] = 0.f;
+      } else if (trow0 == trow1) {
+        const float t = __ldg(p.time_embed + static_cast<size_t>(trow0) * kD + j);
+#pragma unroll
+        for (int u = 0; u < kScanU; ++u) tev[u] = t;
+      } else {
+#pragma unroll
+        for (int u = 0; u < kScanU; ++u) {
           const int r = rb + warp + 8 * u;
-          gi_r[u] = gi_z[u] = gi_n[u] = tev[u] = 0.f;
-          if (r < p.row1) {
-            const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
-            if (type1) {
-              gi_n[u] = __ldg(gi);
-            } else {
-              gi_r[u] = __ldg(gi);
-              gi_z[u] = __ldg(gi + kD);
-              gi_n[u] = __ldg(gi + 2 * kD);
-            }
-            if (p.time_embed != nullptr) {
-              const int trow = p.row_time != nullptr ? __ldg(p.row_time + r) : p.row_time_scalar;
-              tev[u] = __ldg(p.time_embed + static_cast<size_t>(trow) * kD + j);
-            }
-          }
+          tev[u] = r < r1 ? __ldg(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j) : 0.f;
         }
       }
-      if (need_bar) {
-        grid_barrier(P.barrier, (++n_bar) * gridDim.x);
-        need_bar = false;
-      }
-      if (!has) break;
-
-      // ---- phase B: previous-state rows -> smem operand ; gh^T = W_hh . h0^T ; gates ; state write -------
-      int any_prev = 0;
-      if (worker) {
-        float4 v[8];
-        float dv[8];
+    }
+    if (any_prev) {
+      __syncthreads();  // every h0 read of the hi image is done before the exchange buffer overwrites it
+      mbar_wait(&S.mma_done, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+      TL(5 + 6 * (s & 7));
+      if (worker && (warp & 3) < 3) {  // TMEM lane quadrant = gate; columns = rows of the tile
+        const int gate = warp & 3, hf = warp >> 2;
+        constexpr int kHalf = kScanN / 2;
+        const uint32_t ta = tbase + (static_cast<uint32_t>(32 * gate) << 16) + kHalf * hf;
+        float* exw = ex + (gate * kScanN + kHalf * hf) * 32 + lane;
+        float v[32];
+        tmem_ld32(ta, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int pr = __shfl_sync(kFull, prv, u);
-          dv[u] = __shfl_sync(kFull, dec, u);
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pr >= 0) {
-            any_prev = 1;
-            v[u] = __ldcg(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD + 4 * lane));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = warp + 8 * u;
-          float4 hi, lo;
-          split_tf32(v[u].x * dv[u], hi.x, lo.x);
-          split_tf32(v[u].y * dv[u], hi.y, lo.y);
-          split_tf32(v[u].z * dv[u], hi.z, lo.z);
-          split_tf32(v[u].w * dv[u], hi.w, lo.w);
-          const uint32_t off = static_cast<uint32_t>(lane >> 3) * (kScanN * 128) + (i >> 3) * 1024u + (i & 7) * 128u +
-                               (((lane & 7) ^ (i & 7)) << 4);
-          *reinterpret_cast<float4*>(b_hi + off) = hi;
-          *reinterpret_cast<float4*>(b_lo + off) = lo;
-        }
-        fence_proxy_async();
-      }
-      any_prev = __syncthreads_or(any_prev);
-      if (any_prev) {
-        if (tid == kWorkers) {
-          if (w_pending) mbar_wait(&S.w_full, w_phase);
-          tc_fence_after();
-          const uint32_t ai = smem_u32(a_img), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-          for (int ka = 0; ka < kKAtoms; ++ka)
-            umma_katom_3x(tbase, ai + ka * kWChunkBytes, bh + ka * (kScanN * 128), bl + ka * (kScanN * 128), idesc, ka == 0);
-          umma_commit(&S.mma_done);
-        }
-        if (w_pending) {
-          w_pending = false;
-          w_phase ^= 1;
-        }
-        mbar_wait(&S.mma_done, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-        if (worker && (warp & 3) < 3) {  // TMEM lane quadrant = gate; columns = rows of the tile
-          const int gate = warp & 3, hf = warp >> 2;
-          float v[32];
-          tmem_ld32(tbase + (static_cast<uint32_t>(32 * gate) << 16) + 32 * hf, v);
+        for (int i = 0; i < 32; ++i) exw[i * 32] = v[i];
+        if (kHalf > 32) {
+          float w[16];
+          tmem_ld16(ta + 32, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) ex[(gate * kScanN + 32 * hf + i) * 32 + lane] = v[i];
+          for (int i = 0; i < kHalf - 32; ++i) exw[(32 + i) * 32] = w[i];
         }
-        tc_fence_before();
       }
+      tc_fence_before();
       __syncthreads();
+    }
+    TL(6 + 6 * (s & 7));
 
-      if (worker) {
-        const int j = jb + lane;
+    if (worker) {
+      const int j = jb + lane;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = warp + 8 * u;
-          const int r = rb + i;
-          float hr = br, hz = bz, hn = bn, h0 = 0.f;
+      for (int u = 0; u < kScanU; ++u) {
+        const int i = warp + 8 * u;
+        const int r = rb + i;
+        if (r < r1) {  // warp-uniform
+          float hr = br, hz = bz, hn = bn;
           if (any_prev) {
             hr += ex[(0 * kScanN + i) * 32 + lane];
             hz += ex[(1 * kScanN + i) * 32 + lane];
             hn += ex[(2 * kScanN + i) * 32 + lane];
-            const uint32_t off = static_cast<uint32_t>(cb) * (kScanN * 128) + sw128_off(i, lane);
-            h0 = *reinterpret_cast<const float*>(b_hi + off) + *reinterpret_cast<const float*>(b_lo + off);
           }
           float hy;
           if (type1) {  // GRU_cell.py:22-29
-            const float rg = sigmoidf_(hr), zg = sigmoidf_(hz);
-            const float ng = tanhf(gi_n[u] + rg * hn);
-            hy = ng + zg * (h0 - ng);
+            const float rg = fast_sigmoid(hr), zg = fast_sigmoid(hz);
+            const float ng = fast_tanh(gi_n[u] + rg * hn);
+            hy = ng + zg * (h0[u] - ng);
           } else {      // torch.nn.GRU, gate order r, z, n
-            const float rg = sigmoidf_(gi_r[u] + hr);
-            const float zg = sigmoidf_(gi_z[u] + hz);
-            const float ng = tanhf(gi_n[u] + rg * hn);
-            hy = (1.f - zg) * ng + zg * h0;
+            const float rg = fast_sigmoid(gi_r[u] + hr);
+            const float zg = fast_sigmoid(gi_z[u] + hz);
+            const float ng = fast_tanh(gi_n[u] + rg * hn);
+            hy = (1.f - zg) * ng + zg * h0[u];
           }
           hy += tev[u];
-          if (r < p.row1) {
-            float* o = p.out + static_cast<size_t>(r) * kD + j;
-            *o = p.accumulate ? (__ldcg(o) + hy) : hy;
-          }
+          float* o = p.out + static_cast<size_t>(r) * kD + j;
+          *o = p.accumulate ? (__ldcg(o) + hy) : hy;
         }
       }
-      __syncthreads();  // the operand tile and the exchange buffer are rewritten by the next tile
     }
-    if (w_pending && tid == kWorkers) {
-      // the image was requested but no tile of this CTA needed it: drain the copy before a possible reload
-      mbar_wait(&S.w_full, w_phase);
-    }
-    if (w_pending) {
-      w_pending = false;
-      w_phase ^= 1;
-    }
-    __syncthreads();
+    TL(7 + 6 * (s & 7));
+    // publishes this step's state columns to the cluster (release); the matching wait of the next step also
+    // orders the reuse of the operand tile and of the exchange buffer
+    cluster_arrive();
+    arrived = true;
+    cur = nxt;
+    part = n_part;
+    s = n_s;
+    ranges = n_ranges;
   }
+  if (w_pending && tid == kWorkers) mbar_wait(&S.w_full, w_phase);  // drain a copy no step consumed
+  if (arrived) cluster_wait();
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWorkerWarps) tmem_dealloc(tbase, kScanN);
-  // self-cleaning barrier words: the last CTA to leave resets them for the next launch
-  if (tid == 0 && P.barrier != nullptr) {
-    const unsigned done = atomicAdd(P.barrier + 1, 1u);
-    if (done == gridDim.x - 1) {
-      P.barrier[0] = 0u;
-      P.barrier[1] = 0u;
-      __threadfence();
-    }
-  }
+  if (warp == kWorkerWarps) tmem_dealloc(tbase, 128);
 }
 
 template <typename K>
@@ -639,13 +756,20 @@ int ensure_smem_once(K kernel, int bytes, const char* name, bool& done) {
 
 }  // namespace
 
+#ifdef TEMP_TIMELINE
+extern "C" int temp_debug_timeline(void* device_buffer) {  // [ctas][12 warps][64 slots] u64, or null to disable
+  unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+  return cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 namespace temp_internal {
 
 bool tc_layer_supported(const TempRgcnLayerArgs* a) {
   if (a->d != kD || a->n_terms != 1) return false;
   const TempDenseTerm& t = a->terms[0];
   if (t.w_packed == nullptr || t.a_dt != nullptr) return false;
-  if (a->row_ptr != nullptr && (a->si != 1 || a->so != 1 || a->e_dst == nullptr)) return false;
+  if (a->row_ptr != nullptr && (a->si != 1 || a->so != 1 || a->agg_scratch == nullptr)) return false;
   if (a->chain_w != nullptr && (a->chain_w_packed == nullptr || (a->chain_n & 127) != 0)) return false;
   return true;
 }
@@ -654,6 +778,11 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   static bool configured = false;
   if (int rc = ensure_smem_once(rgcn_layer_tc_kernel, kLayerSmem, "rgcn_layer_tc_kernel", configured)) return rc;
   const int rows = a->row1 - a->row0;
+  if (a->row_ptr != nullptr) {
+    rgcn_gather_kernel<<<(rows + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, 0, st>>>(*a);
+    cudaError_t eg = cudaGetLastError();
+    if (eg != cudaSuccess) return cuda_fail(eg, "rgcn_gather_kernel launch");
+  }
   const int grid = (rows + kTileRows - 1) / kTileRows;
   rgcn_layer_tc_kernel<<<grid, kLayerThreads, kLayerSmem, st>>>(*a);
   cudaError_t e = cudaGetLastError();
@@ -662,32 +791,40 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
 }
 
 bool tc_scan_supported(const TempGruScanArgs* a) {
+  if (a->n_steps <= 0) return false;
+  if (a->parts == nullptr && a->n_steps != 1) return false;  // several steps need the chain partition table
   for (int s = 0; s < a->n_steps; ++s) {
     const TempGruArgs& g = a->steps[s];
     if (g.d != kD) return false;
     if (g.prev_row != nullptr && g.whh_packed == nullptr) return false;
+    if (a->parts != nullptr && (g.part_col < 0 || g.part_col >= a->part_stride)) return false;
   }
-  return a->n_steps > 0;
+  return true;
 }
 
 int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   static bool configured = false;
   if (int rc = ensure_smem_once(gru_scan_tc_kernel, kScanSmem, "gru_scan_tc_kernel", configured)) return rc;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  int n_parts = a->n_parts;
+  if (a->parts == nullptr) n_parts = (a->steps[0].row1 - a->steps[0].row0 + kScanN - 1) / kScanN;
+  if (n_parts <= 0) return TEMP_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kScanThreads);
+  cfg.dynamicSmemBytes = kScanSmem;
+  cfg.stream = st;
+  static int max_clusters = 0;  // co-resident clusters of 4 (one CTA per SM: 216 KB of shared memory)
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3(kScanCluster * 64);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, gru_scan_tc_kernel, &cfg);
+    if (e != cudaSuccess || max_clusters <= 0) {
+      cudaGetLastError();
+      max_clusters = 32;
+    }
   }
-  int max_rows = 0;
-  for (int s = 0; s < a->n_steps; ++s) max_rows = max(max_rows, a->steps[s].row1 - a->steps[s].row0);
-  if (max_rows == 0) return TEMP_OK;
-  int want = ((max_rows + kScanN - 1) / kScanN) * 4;
-  int cap = sm_count / 4 * 4;  // one CTA per SM (216 KB of shared memory), all co-resident
-  int grid = want < cap ? want : cap;
-  void* params[] = {const_cast<TempGruScanArgs*>(a)};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gru_scan_tc_kernel), dim3(grid), dim3(kScanThreads), params,
-                                              kScanSmem, st);
+  const int clusters = n_parts < max_clusters ? n_parts : max_clusters;
+  cfg.gridDim = dim3(kScanCluster * clusters);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tc_kernel, *a, n_parts);
   if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tc_kernel launch");
   return TEMP_OK;
 }

@@ -860,7 +860,7 @@ int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
   if (a->n_steps < 0 || a->n_steps > TEMP_MAX_SCAN_STEPS) return fail(TEMP_EINVAL, "n_steps out of range%s", "");
   if (a->n_steps == 0) return TEMP_OK;
-  if (a->barrier == nullptr) return fail(TEMP_EINVAL, "scan needs a zero-initialised 8-byte barrier word%s", "");
+  if (a->parts != nullptr && (a->n_parts < 0 || a->part_stride <= 0)) return fail(TEMP_EINVAL, "bad chain-partition table%s", "");
   int max_rows = 0;
   for (int s = 0; s < a->n_steps; ++s) {
     if (int rc = check_gru(&a->steps[s])) return rc;
@@ -870,6 +870,7 @@ int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   }
   if (max_rows == 0) return TEMP_OK;
   if (temp_internal::tc_scan_supported(a)) return temp_internal::tc_launch_scan(a, st);
+  if (a->barrier == nullptr) return fail(TEMP_EINVAL, "scan needs a zero-initialised 8-byte barrier word%s", "");
   if (max_rows <= 148 * 64) return launch_scan_t<4, 3>(a, max_rows, st);
   return launch_scan_t<8, 4>(a, max_rows, st);
 }
@@ -991,6 +992,29 @@ int64_t temp_packed_gru_bytes(int32_t d) { return d == 128 ? static_cast<int64_t
 
 int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* stream) {
   return temp_internal::tc_pack_gru_weights(whh_t, d, packed, static_cast<cudaStream_t>(stream));
+}
+
+int temp_program_kernel_count(const TempOp* ops, int32_t n) {
+  if (ops == nullptr || n < 0) return TEMP_EINVAL;
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    switch (ops[i].kind) {
+      case TEMP_OP_LAYER: {
+        const TempRgcnLayerArgs& a = ops[i].u.layer;
+        if (a.row1 > a.row0) k += (temp_internal::tc_layer_supported(&a) && a.row_ptr != nullptr) ? 2 : 1;
+        break;
+      }
+      case TEMP_OP_GRU: k += ops[i].u.gru.row1 > ops[i].u.gru.row0 ? 1 : 0; break;
+      case TEMP_OP_GRU_SCAN: k += ops[i].u.scan.n_steps > 0 ? 1 : 0; break;
+      case TEMP_OP_ATTN: k += ops[i].u.attn.row1 > ops[i].u.attn.row0 ? 1 : 0; break;
+      case TEMP_OP_GATHER: k += ops[i].u.gather.n > 0 ? 1 : 0; break;
+      case TEMP_OP_SCATTER: k += ops[i].u.scatter.n > 0 ? 1 : 0; break;
+      case TEMP_OP_MEMCPY_H2D:
+      case TEMP_OP_MEMCPY_D2H: break;
+      default: return TEMP_EINVAL;
+    }
+  }
+  return k;
 }
 
 int temp_run_program(const TempOp* ops, int32_t n, void* stream) {

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -37,7 +37,7 @@ class RgcnLayerArgs(C.Structure):
         ("h_bias", _p), ("activation", _i32),
         ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32), ("te_out", _i32), ("te_chain", _i32),
         ("h_out", _p), ("chain_w", _p), ("chain_b", _p), ("chain_out", _p), ("chain_n", _i32), ("chain_ld", _i32),
-        ("chain_w_packed", _p), ("inv_temperature", C.c_float),
+        ("chain_w_packed", _p), ("inv_temperature", C.c_float), ("agg_scratch", _p),
     ]
 
 
@@ -48,12 +48,13 @@ class GruArgs(C.Structure):
         ("state", _p), ("prev_row", _p), ("dt", _p), ("decay_wb", _p), ("inv_temperature", C.c_float),
         ("whh_t", _p), ("whh_packed", _p), ("b_hh", _p), ("cell_type", _i32),
         ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32),
-        ("accumulate", _i32), ("out", _p), ("out_index_is_row", _i32),
+        ("accumulate", _i32), ("out", _p), ("out_index_is_row", _i32), ("part_col", _i32),
     ]
 
 
 class GruScanArgs(C.Structure):
-    _fields_ = [("n_steps", _i32), ("reserved", _i32), ("barrier", _p), ("steps", GruArgs * MAX_SCAN_STEPS)]
+    _fields_ = [("n_steps", _i32), ("n_parts", _i32), ("barrier", _p), ("parts", _p), ("part_stride", _i32),
+                ("reserved", _i32), ("steps", GruArgs * MAX_SCAN_STEPS)]
 
 
 class AttnArgs(C.Structure):
@@ -88,7 +89,8 @@ class Op(C.Structure):
 
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
-           "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights")
+           "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
+           "temp_program_kernel_count")
 
 _lib = None
 
@@ -117,6 +119,7 @@ def load(path: Optional[str] = None):
     lib.temp_scatter_rows.argtypes = [C.POINTER(ScatterArgs), _p]
     lib.temp_transpose.argtypes = [_p, _i32, _i32, _p, _i32, _p]
     lib.temp_run_program.argtypes = [C.POINTER(Op), _i32, _p]
+    lib.temp_program_kernel_count.argtypes = [C.POINTER(Op), _i32]
     lib.temp_packed_weights_bytes.argtypes = [_i32, _i32]
     lib.temp_packed_weights_bytes.restype = C.c_int64
     lib.temp_pack_weights.argtypes = [_p, _i32, _i32, _p, _p]
@@ -179,8 +182,9 @@ class Program(object):
     def __len__(self):
         return len(self.ops)
 
-    def fuse_gru_scans(self, barrier_ptr: int) -> None:
-        """Replaces every run of >= 2 consecutive GRU ops by ONE cooperative scan launch."""
+    def fuse_gru_scans(self, barrier_ptr: int, parts_ptr: Optional[int] = None, n_parts: int = 0, part_stride: int = 0) -> None:
+        """Replaces every run of >= 2 consecutive GRU ops by ONE scan launch (chain-partitioned when the plan's
+        partition table is given, see TempGruScanArgs)."""
         out, run = [], []
 
         def flush():
@@ -191,6 +195,8 @@ class Program(object):
                 else:
                     a = GruScanArgs()
                     a.n_steps, a.barrier = len(chunk), barrier_ptr
+                    if parts_ptr is not None:
+                        a.parts, a.n_parts, a.part_stride = parts_ptr, n_parts, part_stride
                     for i, o in enumerate(chunk):
                         a.steps[i] = o.u.gru
                     op = Op()
@@ -211,6 +217,17 @@ class Program(object):
 
     def count(self, kinds=(OP_LAYER, OP_GRU, OP_GRU_SCAN, OP_ATTN, OP_GATHER, OP_SCATTER)) -> int:
         return sum(1 for o in self.ops if o.kind in kinds)
+
+    def kernel_count(self) -> int:
+        """Kernel launches one ``run`` issues (a tensor-core layer with a graph part is two: gather + tile kernel)."""
+        if not self.ops:
+            return 0
+        if self._arr is None:
+            self._arr = (Op * len(self.ops))(*self.ops)
+        n = load().temp_program_kernel_count(self._arr, len(self.ops))
+        if n < 0:
+            raise RuntimeError("temp_b200: bad program")
+        return int(n)
 
     def run(self, stream: Optional[int] = None) -> None:
         if not self.ops:

@@ -55,7 +55,7 @@ class WindowPlan(object):
     one byte buffer so that the host->device traffic of a forward is a single copy."""
 
     ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "e_dst", "prev_a", "dt_a",
-              "prev_b", "dt_b", "slot_row")
+              "prev_b", "dt_b", "slot_row", "scan_parts")
 
     def __init__(self):
         self.segments: List[Segment] = []
@@ -256,11 +256,53 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
     plan.last_hist_f = list(last_f)
     plan.last_hist_b = [last_b[B - 1 - i] for i in range(B)] if bidirectional else [None] * B
     pk.finish(plan)
+    if not attention:
+        plan.scan_parts = chain_partitions(plan)
     if attention:
         plan.n_slots = (L - 1) * (2 if bidirectional else 1)
         plan.slot_row = np.ascontiguousarray(np.concatenate(slot_rows, axis=0), dtype=np.int32)
         plan.steps_f, plan.steps_b = steps_f, steps_b
     return plan
+
+
+SCAN_TILE = 96   # rows per chain partition and step (UMMA N of the scan kernel, temp_b200/csrc/tc_kernels.cu)
+
+
+def chain_partitions(plan: WindowPlan, tile: int = SCAN_TILE) -> np.ndarray:
+    """Cuts every batch item into entity-id ranges such that no step of a range has more than ``tile`` rows.
+
+    The recurrence links a row only to the row of the SAME entity in the SAME batch item at the previous step
+    (``prev_row``; reference models/DynamicRGCN.py:35-54), and the rows of a snapshot instance are sorted by entity
+    id (utils/dataset.py:168), so an entity-id range owns one contiguous packed-row range per segment and no
+    dependency leaves it.  Returns int32 ``[P, len(plan.segments), 2]`` row ranges ``[lo, hi)`` (lo == hi: the
+    partition has no rows in that segment), partitions with the most rows first."""
+    n_seg = len(plan.segments)
+    per_item: Dict[int, list] = {}
+    for g, seg in enumerate(plan.segments):
+        for inst in seg.instances:
+            per_item.setdefault(inst.item, []).append((g, inst))
+    parts = []
+    big = np.iinfo(np.int64).max
+    for item in sorted(per_item):
+        insts = per_item[item]
+        ids = [inst.snapshot.node_ids for _, inst in insts]
+        pos = [0] * len(insts)
+        while any(pos[k] < ids[k].shape[0] for k in range(len(insts))):
+            cut = big
+            for k in range(len(insts)):
+                if pos[k] + tile < ids[k].shape[0]:
+                    cut = min(cut, int(ids[k][pos[k] + tile]))
+            row = np.zeros((n_seg, 2), dtype=np.int32)
+            for k, (g, inst) in enumerate(insts):
+                new = ids[k].shape[0] if cut == big else int(np.searchsorted(ids[k], cut, side="left"))
+                row[g] = (inst.row0 + pos[k], inst.row0 + new)
+                pos[k] = new
+            parts.append(row)
+    if not parts:
+        return np.zeros((0, n_seg, 2), dtype=np.int32)
+    out = np.stack(parts)
+    order = np.argsort(-(out[:, :, 1] - out[:, :, 0]).sum(axis=1), kind="stable")
+    return np.ascontiguousarray(out[order])
 
 
 def plan_static(graph_dict: Dict[int, Snapshot], t_list: Sequence[int]) -> WindowPlan:

@@ -150,12 +150,14 @@ class EncoderRuntime(object):
         self.prep = PreparedWeights(model)
         self._chain_packed = {}
         self.fuse_scan = True      # consecutive GRU steps -> one cooperative persistent launch
+        self._agg_rows = 1
         self.use_tc = True         # tcgen05 path where the shapes allow it (d == 128); False: fp32 SIMT kernels only
 
     # ---- plan upload -----------------------------------------------------------------------------
     def stage_plan(self, plan: WindowPlan, program: lib.Program, tag: str = "plan"):
         """Packs the plan into pinned host memory and appends the single H2D copy to ``program``.
         Returns name -> device pointer (int) of every plan array."""
+        self._agg_rows = max(int(plan.R), 1)
         lay, total = plan.blob_layout()
         host = self.ws.pinned(tag + "_host", total)
         plan.to_blob(host.numpy())
@@ -180,6 +182,8 @@ class EncoderRuntime(object):
             a.x = x.data_ptr()
             a.weight = layer.weight.data_ptr()
             a.n_bases, a.si, a.so = layer.num_bases, layer.submat_in, layer.submat_out
+            if self.use_tc and m.embed_size == 128:
+                a.agg_scratch = self.ws.get("agg", self._agg_rows * m.embed_size).data_ptr()
         a.residual = int(residual)
         a.n_terms = len(terms)
         for i, t in enumerate(terms):
@@ -226,7 +230,7 @@ class EncoderRuntime(object):
         return self.prep.cat(name + ".decay_wb", [layer.exponential_decay.weight, layer.exponential_decay.bias])
 
     def _gru(self, layer, rnn, rnn_name, rows, *, gi, gi_ld, gi_off, state, prev, dt, out, te, accumulate=False,
-             dptr=None, row_time_scalar=None, layer_name=""):
+             dptr=None, row_time_scalar=None, layer_name="", part_col=0):
         m = self.model
         type1 = bool(getattr(m.args, "type1", False))
         a = lib.GruArgs()
@@ -256,6 +260,7 @@ class EncoderRuntime(object):
         a.accumulate = int(accumulate)
         a.out = out.data_ptr()
         a.out_index_is_row = 1
+        a.part_col = int(part_col)
         return a
 
     def _wih(self, layer_name, rnns):
@@ -376,7 +381,7 @@ class EncoderRuntime(object):
                     w, b = self._wih("layer_2", rnns)
                     prog.add(lib.OP_LAYER, self._layer(l2, rows, dptr, x=h1, x_is_embed=False, act=relu2,
                                                        terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, 2 * G)))
-                for seg in plan.segments:
+                for g, seg in enumerate(plan.segments):
                     rows = (seg.row0, seg.row1)
                     dirs = dirs_of(seg)
                     for j, d in enumerate(dirs):
@@ -384,7 +389,7 @@ class EncoderRuntime(object):
                         pv, dt = prev_ptrs(d, seg)
                         prog.add(lib.OP_GRU, self._gru(l2, rnn, name, rows, gi=gi, gi_ld=2 * G, gi_off=j * G, state=S,
                                                        prev=pv, dt=dt, out=S, te=use_te and j == len(dirs) - 1,
-                                                       accumulate=j > 0, dptr=dptr, layer_name="layer_2"))
+                                                       accumulate=j > 0, dptr=dptr, layer_name="layer_2", part_col=g))
             else:
                 for seg in plan.segments:
                     rec_layer(l2, "layer_2", (seg.row0, seg.row1), seg, h1, False, None, S, S, relu2, use_te)
@@ -402,7 +407,11 @@ class EncoderRuntime(object):
         out = S[final.row0:final.row1]
         bufs["state"] = S
         if self.fuse_scan:
-            prog.fuse_gru_scans(self.scan_barrier())
+            parts = plan.scan_parts if (self.use_tc and enc.rec_only_last_layer and gru) else None
+            if parts is not None and parts.shape[0] > 0:
+                prog.fuse_gru_scans(self.scan_barrier(), dptr["scan_parts"], int(parts.shape[0]), int(parts.shape[1]))
+            else:
+                prog.fuse_gru_scans(self.scan_barrier())
         return EncodeResult(plan, out, S, prog, bufs)
 
     def _build_attention(self, plan, prog, dptr):

@@ -61,6 +61,35 @@ def test_prev_row_encodes_the_dense_history(case):
             assert np.array_equal(prev[inst.row0:inst.row0 + inst.n] >= 0, nz)
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if c["module"] in ("GRRGCN", "BiGRRGCN", "RRGCN")],
+                         ids=lambda c: c["name"])
+@pytest.mark.parametrize("tile", [64, 5])
+def test_chain_partitions_are_closed_and_cover_every_row(case, tile):
+    """Every packed row belongs to exactly one chain partition, a partition has at most ``tile`` rows per segment
+    and the recurrence never leaves it: prev_row of a row lies in a range of the same partition."""
+    from temp_b200.planner import chain_partitions
+    plan = _plan_for(case)
+    parts = chain_partitions(plan, tile)
+    assert parts.dtype == np.int32 and parts.shape[1:] == (len(plan.segments), 2)
+    owner = np.full(plan.R, -1, dtype=np.int64)
+    for p in range(parts.shape[0]):
+        for g, seg in enumerate(plan.segments):
+            lo, hi = parts[p, g]
+            assert 0 <= hi - lo <= tile
+            if hi > lo:
+                assert seg.row0 <= lo and hi <= seg.row1
+                assert (owner[lo:hi] == -1).all()
+                owner[lo:hi] = p
+    assert (owner >= 0).all()
+    for prev in (plan.prev_a, plan.prev_b):
+        if prev is None:
+            continue
+        has = prev >= 0
+        assert np.array_equal(owner[prev[has]], owner[has])
+    sizes = (parts[:, :, 1] - parts[:, :, 0]).sum(axis=1)
+    assert (np.diff(sizes) <= 0).all()            # heaviest first
+
+
 def test_plan_blob_roundtrip_and_alignment():
     plan = _plan_for(CASES[2])
     blob, lay, total = plan.to_blob()
