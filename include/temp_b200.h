@@ -100,6 +100,14 @@ typedef struct {
   float inv_temperature;
   float* agg_scratch;        /* nullable [>= row1 rows, d] scratch indexed by packed row: the tcgen05 path runs the
                                 aggregation as its own HBM-bound launch and hands it over through this buffer      */
+  /* Work lists of that launch (agg_lists != 0; otherwise every row of [row0, row1) is tested through row_ptr and
+   * gets one warp): entries (packed row, first edge, end edge) of the rows of [row0, row1) with in-edges --
+   * agg_rows: one warp per row; agg_heavy: high in-degree rows, one thread block per row (its 8 warps sum
+   * contiguous edge chunks, the partial sums are added in chunk order: deterministic, no atomics).            */
+  const int32_t* agg_rows;   /* [n_agg_rows, 3]  */
+  const int32_t* agg_heavy;  /* [n_agg_heavy, 3] */
+  int32_t n_agg_rows, n_agg_heavy;
+  int32_t agg_lists;
 } TempRgcnLayerArgs;
 
 /* Recurrent half of the GRU for packed rows [row0, row1), fused with the gates:

@@ -16,6 +16,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // launches that do not are run by the fp32 SIMT kernels of temp_kernels.cu.
 bool tc_layer_supported(const TempRgcnLayerArgs* a);
 int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st);
+int tc_gather_grid(const TempRgcnLayerArgs* a);
 bool tc_scan_supported(const TempGruScanArgs* a);
 int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
 int tc_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st);

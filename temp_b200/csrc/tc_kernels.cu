@@ -108,33 +108,28 @@ __global__ void pack_gru_kernel(const float* __restrict__ whh_t, uint8_t* __rest
 // ------------------------------------------------------------------------------------------------
 // agg[v] = norm_v * sum_{e: dst_e = v} norm_v * W[rel_e] (.) x[src_e]      (RGCN.py:91-104, diagonal blocks)
 // One warp per destination row, a lane per 4 channels (one 512-byte feature row per load instruction), edge
-// indices fetched lane-parallel, 4 feature-row pairs in flight per warp (32 warps per SM), edges summed in edge-id order (deterministic, no
-// atomics).  Rows without in-edges are not written (the consumer tests row_ptr).  No shared memory, 32 resident
+// indices fetched lane-parallel, 2 feature-row pairs in flight per warp (40 warps per SM), edges summed in edge-id order (deterministic, no
+// atomics).  Rows without in-edges are not written (the consumer tests row_ptr).  No shared memory, 40 resident
 // warps per SM: this is the HBM / L2-bound part of the layer, kept out of the one-CTA-per-SM tensor-core kernel.
 constexpr int kGatherWarps = 8;
 
-__global__ void __launch_bounds__(kGatherWarps * 32, 4) rgcn_gather_kernel(const TempRgcnLayerArgs p) {
-  const int lane = threadIdx.x & 31;
-  const int r = p.row0 + blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
-  if (r >= p.row1) return;
-  const int p0 = __ldg(p.row_ptr + r), p1 = __ldg(p.row_ptr + r + 1);
-  if (p1 <= p0) return;
-  const float nrm = __ldg(p.norm + r);
+// sum_{e in [e0, e1)} (x[src_e] * W[rel_e]) * nrm for this lane's 4 channels, in edge order
+__device__ __forceinline__ float4 gather_edges(const TempRgcnLayerArgs& p, int e0, int e1, float nrm, int lane) {
   const float4* x4 = reinterpret_cast<const float4*>(p.x) + lane;
   const float4* w4 = reinterpret_cast<const float4*>(p.weight) + lane;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = p0; base < p1; base += 32) {
-    const int cnt = min(32, p1 - base);
+  for (int base = e0; base < e1; base += 32) {
+    const int cnt = min(32, e1 - base);
     int s = 0, rl = 0;
     if (lane < cnt) {
       s = __ldg(p.e_src + base + lane);
       rl = __ldg(p.e_rel + base + lane);
     }
 #pragma unroll 1
-    for (int u0 = 0; u0 < cnt; u0 += 4) {
-      float4 hv[4], wv[4];
+    for (int u0 = 0; u0 < cnt; u0 += 2) {
+      float4 hv[2], wv[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int su = __shfl_sync(kFull, s, (u0 + u) & 31), ru = __shfl_sync(kFull, rl, (u0 + u) & 31);
         if (u0 + u < cnt) {
           hv[u] = __ldg(x4 + static_cast<size_t>(su) * (kD / 4));
@@ -142,7 +137,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 4) rgcn_gather_kernel(const
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         if (u0 + u < cnt) {  // msg = (h * w) * norm_e, summed in edge order (RGCN.py:92-97)
           a.x += (hv[u].x * wv[u].x) * nrm;
           a.y += (hv[u].y * wv[u].y) * nrm;
@@ -152,6 +147,50 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 4) rgcn_gather_kernel(const
       }
     }
   }
+  return a;
+}
+
+__global__ void __launch_bounds__(kGatherWarps * 32, 5) rgcn_gather_kernel(const TempRgcnLayerArgs p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.agg_lists != 0 && static_cast<int>(blockIdx.x) < p.n_agg_heavy) {
+    // ---- a high in-degree row: the block's 8 warps sum contiguous edge chunks, partials added in chunk order ----
+    __shared__ float4 part[kGatherWarps][32];
+    const int t = lane < 3 ? __ldg(p.agg_heavy + 3 * static_cast<size_t>(blockIdx.x) + lane) : 0;
+    const int r = __shfl_sync(kFull, t, 0), p0 = __shfl_sync(kFull, t, 1), p1 = __shfl_sync(kFull, t, 2);
+    const float nrm = __ldg(p.norm + r);
+    const int chunk = (p1 - p0 + kGatherWarps - 1) / kGatherWarps;
+    const int e0 = min(p0 + warp * chunk, p1), e1 = min(e0 + chunk, p1);
+    part[warp][lane] = gather_edges(p, e0, e1, nrm, lane);
+    __syncthreads();
+    if (warp == 0) {
+      float4 a = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < kGatherWarps; ++w) {
+        const float4 b = part[w][lane];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;  // apply_func (RGCN.py:103-104)
+      reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * kD)[lane] = a;
+    }
+    return;
+  }
+  int r, p0, p1;
+  if (p.agg_lists != 0) {  // compact work list: rows with in-edges only, CSR range inline
+    const int item = (static_cast<int>(blockIdx.x) - p.n_agg_heavy) * kGatherWarps + warp;
+    if (item >= p.n_agg_rows) return;
+    const int t = lane < 3 ? __ldg(p.agg_rows + 3 * static_cast<size_t>(item) + lane) : 0;
+    r = __shfl_sync(kFull, t, 0);
+    p0 = __shfl_sync(kFull, t, 1);
+    p1 = __shfl_sync(kFull, t, 2);
+  } else {
+    r = p.row0 + blockIdx.x * kGatherWarps + warp;
+    if (r >= p.row1) return;
+    p0 = __ldg(p.row_ptr + r);
+    p1 = __ldg(p.row_ptr + r + 1);
+    if (p1 <= p0) return;
+  }
+  const float nrm = __ldg(p.norm + r);
+  float4 a = gather_edges(p, p0, p1, nrm, lane);
   a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;  // apply_func (RGCN.py:103-104)
   reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * kD)[lane] = a;
 }
@@ -279,32 +318,34 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     const uint32_t sb_hi = smem_u32(b_hi) + my_off, sb_lo = smem_u32(b_lo) + my_off;
     const uint32_t lane_base = tbase + (static_cast<uint32_t>(32 * q) << 16);
 
-    // ---- 1. self-loop operand rows -> shared memory (hi / lo), 32 row loads in flight ---------------------
+    // ---- 1. self-loop operand rows -> shared memory (hi / lo) ---------------------------------------------
+    // (any thread mapping works here: warp w stages rows 16 w .. 16 w + 15, a lane per 4 features, so that one load
+    // instruction fetches a whole 512-byte row and one 16-byte store fills a swizzle chunk)
     {
       const TempDenseTerm& tm = p.terms[0];
-      const int ra = R0 + lane, rb = R0 + 32 + lane;
-      const int idxA = ra < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + ra) : ra) : -1;
-      const int idxB = rb < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + rb) : rb) : -1;
-      // (loops are kept rolled on purpose: the fully unrolled kernel was instruction-fetch bound)
-#pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
-        float v[16];
-        const int idx = b < 2 ? idxA : idxB;
+      const int rr = rbase + 16 * warp + (lane & 15);
+      const int idx = rr < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + rr) : rr) : -1;
+      float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int sr = __shfl_sync(kFull, idx, (16 * b + i) & 31);
-          v[i] = sr >= 0 ? __ldg(tm.a + static_cast<size_t>(sr) * kD + f) : 0.f;
-        }
-        // rows 64 hf + 16 b + i: 8-row group (2 b + (i >> 3)), row in group (i & 7)
-        const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * b)) * 1024u;
+      for (int i = 0; i < 16; ++i) {
+        const int sr = __shfl_sync(kFull, idx, i);
+        v[i] = sr >= 0 ? __ldg(reinterpret_cast<const float4*>(tm.a + static_cast<size_t>(sr) * kD) + lane)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // row 16 w + i: 8-row group 2 w + (i >> 3), row in group i & 7; k-atom lane >> 3, 16-byte chunk (lane & 7) ^ (i & 7)
+      const uint32_t base_off = static_cast<uint32_t>(lane >> 3) * (kTileRows * 128) + static_cast<uint32_t>(2 * warp) * 1024u;
+      const uint32_t s_hi = smem_u32(b_hi) + base_off, s_lo = smem_u32(b_lo) + base_off;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float hi, lo;
-          split_tf32(v[i], hi, lo);
-          const uint32_t off = grp + sw128_off(i, lane);
-          sts_f32(sb_hi + off, hi);
-          sts_f32(sb_lo + off, lo);
-        }
+      for (int i = 0; i < 16; ++i) {
+        float4 hi, lo;
+        split_tf32(v[i].x, hi.x, lo.x);
+        split_tf32(v[i].y, hi.y, lo.y);
+        split_tf32(v[i].z, hi.z, lo.z);
+        split_tf32(v[i].w, hi.w, lo.w);
+        const uint32_t off = static_cast<uint32_t>(i >> 3) * 1024u + static_cast<uint32_t>(i & 7) * 128u +
+                             (static_cast<uint32_t>((lane & 7) ^ (i & 7)) << 4);
+        sts_f32x4(s_hi + off, hi);
+        sts_f32x4(s_lo + off, lo);
       }
       fence_proxy_async();
       mbar_arrive(&S.b_ready);
@@ -334,16 +375,17 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     // rows of a tile mostly share a snapshot, i.e. a time-embedding row: reload on change only
     int cur_trow = need_te ? __shfl_sync(kFull, rtA, 0) : -1;
     float cur_te = need_te ? __ldg(p.time_embed + static_cast<size_t>(cur_trow) * kD + f) : 0.f;
+    // the aggregate rows of this thread's 64 rows: all loads in flight while the self-loop MMA completes
+    const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * kD + f;
+    float ag[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) ag[j] = ((has >> j) & 1ull) ? __ldg(agg_col + j * kD) : 0.f;
     mbar_wait(&S.d1_full, 0);
     tc_fence_after();
     TL(4);
-    const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * kD + f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[16], ag[16];
-      const unsigned h16 = static_cast<unsigned>(has >> (16 * c)) & 0xffffu;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) ag[i] = ((h16 >> i) & 1u) ? __ldg(agg_col + (16 * c + i) * kD) : 0.f;
+    for (int c = 0; c < 4; ++c) {
+      float v[16];
       tmem_ld16(lane_base + 64 * hf + 16 * c, v);
       tmem_ld_wait();
       const int rt = c < 2 ? rtA : rtB;
@@ -359,7 +401,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
             cur_te = __ldg(p.time_embed + static_cast<size_t>(trow) * kD + f);
           }
         }
-        float val = ag[i];
+        float val = ag[16 * c + i];
         if (p.residual) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
         val += v[i];
         val += bias;
@@ -765,11 +807,21 @@ extern "C" int temp_debug_timeline(void* device_buffer) {  // [ctas][12 warps][6
 
 namespace temp_internal {
 
+// thread blocks of the aggregation launch that precedes the tile kernel (0: no launch)
+int tc_gather_grid(const TempRgcnLayerArgs* a) {
+  if (a->row_ptr == nullptr || a->row1 <= a->row0) return 0;
+  if (a->agg_lists != 0) return a->n_agg_heavy + (a->n_agg_rows + kGatherWarps - 1) / kGatherWarps;
+  return (a->row1 - a->row0 + kGatherWarps - 1) / kGatherWarps;
+}
+
 bool tc_layer_supported(const TempRgcnLayerArgs* a) {
   if (a->d != kD || a->n_terms != 1) return false;
   const TempDenseTerm& t = a->terms[0];
   if (t.w_packed == nullptr || t.a_dt != nullptr) return false;
   if (a->row_ptr != nullptr && (a->si != 1 || a->so != 1 || a->agg_scratch == nullptr)) return false;
+  if (a->agg_lists != 0 && (a->n_agg_rows < 0 || a->n_agg_heavy < 0 || (a->n_agg_rows > 0 && a->agg_rows == nullptr) ||
+                            (a->n_agg_heavy > 0 && a->agg_heavy == nullptr)))
+    return false;
   if (a->chain_w != nullptr && (a->chain_w_packed == nullptr || (a->chain_n & 127) != 0)) return false;
   return true;
 }
@@ -778,8 +830,9 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   static bool configured = false;
   if (int rc = ensure_smem_once(rgcn_layer_tc_kernel, kLayerSmem, "rgcn_layer_tc_kernel", configured)) return rc;
   const int rows = a->row1 - a->row0;
-  if (a->row_ptr != nullptr) {
-    rgcn_gather_kernel<<<(rows + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, 0, st>>>(*a);
+  const int gather_grid = tc_gather_grid(a);
+  if (gather_grid > 0) {
+    rgcn_gather_kernel<<<gather_grid, kGatherWarps * 32, 0, st>>>(*a);
     cudaError_t eg = cudaGetLastError();
     if (eg != cudaSuccess) return cuda_fail(eg, "rgcn_gather_kernel launch");
   }

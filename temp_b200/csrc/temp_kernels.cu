@@ -1001,7 +1001,8 @@ int temp_program_kernel_count(const TempOp* ops, int32_t n) {
     switch (ops[i].kind) {
       case TEMP_OP_LAYER: {
         const TempRgcnLayerArgs& a = ops[i].u.layer;
-        if (a.row1 > a.row0) k += (temp_internal::tc_layer_supported(&a) && a.row_ptr != nullptr) ? 2 : 1;
+        if (a.row1 > a.row0)
+          k += (temp_internal::tc_layer_supported(&a) && temp_internal::tc_gather_grid(&a) > 0) ? 2 : 1;
         break;
       }
       case TEMP_OP_GRU: k += ops[i].u.gru.row1 > ops[i].u.gru.row0 ? 1 : 0; break;

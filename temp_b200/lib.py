@@ -37,7 +37,8 @@ class RgcnLayerArgs(C.Structure):
         ("h_bias", _p), ("activation", _i32),
         ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32), ("te_out", _i32), ("te_chain", _i32),
         ("h_out", _p), ("chain_w", _p), ("chain_b", _p), ("chain_out", _p), ("chain_n", _i32), ("chain_ld", _i32),
-        ("chain_w_packed", _p), ("inv_temperature", C.c_float), ("agg_scratch", _p),
+        ("chain_w_packed", _p), ("inv_temperature", C.c_float), ("agg_scratch", _p), ("agg_rows", _p), ("agg_heavy", _p), ("n_agg_rows", _i32), ("n_agg_heavy", _i32),
+        ("agg_lists", _i32),
     ]
 
 

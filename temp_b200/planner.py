@@ -28,6 +28,7 @@ from .snapshot import Snapshot
 __all__ = ["Instance", "Segment", "WindowPlan", "plan_window", "plan_static"]
 
 _ALIGN = 256
+AGG_HEAVY_DEGREE = 8   # in-degree above which the aggregation kernel gives a destination row a whole thread block
 
 
 @dataclass
@@ -55,7 +56,7 @@ class WindowPlan(object):
     one byte buffer so that the host->device traffic of a forward is a single copy."""
 
     ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "e_dst", "prev_a", "dt_a",
-              "prev_b", "dt_b", "slot_row", "scan_parts")
+              "prev_b", "dt_b", "slot_row", "scan_parts", "agg_rows", "agg_heavy")
 
     def __init__(self):
         self.segments: List[Segment] = []
@@ -162,6 +163,14 @@ class _Packer(object):
         plan.e_rel = cat(self.erel, np.int32)
         # destination packed row per edge (CSR is by destination, so this is non-decreasing)
         plan.e_dst = np.repeat(np.arange(self.R, dtype=np.int32), np.diff(rp).astype(np.int64)).astype(np.int32)
+        # work list of the aggregation kernel: (packed row, first edge, end edge) of every row WITH in-edges
+        # (a warp each), split by in-degree: rows above AGG_HEAVY_DEGREE get a whole thread block
+        deg = rp[1:] - rp[:-1]
+        for name, nz in (("agg_rows", np.nonzero((deg > 0) & (deg <= AGG_HEAVY_DEGREE))[0]),
+                         ("agg_heavy", np.nonzero(deg > AGG_HEAVY_DEGREE)[0])):
+            setattr(plan, name, np.ascontiguousarray(np.stack([nz, rp[nz], rp[nz + 1]], axis=1), dtype=np.int32)
+                    if nz.size else np.zeros((0, 3), dtype=np.int32))
+            setattr(plan, name + "_ids", nz.astype(np.int64))
         plan.prev_a = cat(self.prev_a, np.int32)
         plan.dt_a = cat(self.dt_a, np.float32)
         if self.prev_b:

@@ -158,6 +158,7 @@ class EncoderRuntime(object):
         """Packs the plan into pinned host memory and appends the single H2D copy to ``program``.
         Returns name -> device pointer (int) of every plan array."""
         self._agg_rows = max(int(plan.R), 1)
+        self._plan = plan
         lay, total = plan.blob_layout()
         host = self.ws.pinned(tag + "_host", total)
         plan.to_blob(host.numpy())
@@ -184,6 +185,13 @@ class EncoderRuntime(object):
             a.n_bases, a.si, a.so = layer.num_bases, layer.submat_in, layer.submat_out
             if self.use_tc and m.embed_size == 128:
                 a.agg_scratch = self.ws.get("agg", self._agg_rows * m.embed_size).data_ptr()
+                if "agg_rows" in dptr:          # work lists of the aggregation launch, cut to [row0, row1)
+                    a.agg_lists = 1
+                    for name in ("agg_rows", "agg_heavy"):
+                        ids = getattr(self._plan, name + "_ids")
+                        lo, hi = int(np.searchsorted(ids, a.row0)), int(np.searchsorted(ids, a.row1))
+                        setattr(a, name, dptr[name] + 12 * lo)
+                        setattr(a, "n_" + name, hi - lo)
         a.residual = int(residual)
         a.n_terms = len(terms)
         for i, t in enumerate(terms):
