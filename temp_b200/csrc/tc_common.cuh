@@ -98,6 +98,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // one fp32 per lane -> column `taddr` of the warp's 32 TMEM lanes (warp-collective)
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
@@ -176,19 +183,35 @@ constexpr int kAtomK = 32;                          // fp32 elements of K per 12
 constexpr int kUmmaK = 8;                           // K per tcgen05.mma kind::tf32
 constexpr int kWChunkBytes = 2 * 128 * 128;         // packed weight chunk: 128 features x 32 k, hi image then lo image
 
+// The descriptors of one kernel differ only in the 14-bit address field of the low word, so the issuing thread
+// keeps 32-bit low words and pairs them with the constant high word (the MMA issue loop of a single thread is on the
+// critical path of the small-N GEMMs: 64-bit descriptor arithmetic per MMA made it issue-bound).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+
 // D^T[128, N] (+)= A_chunk . B_katom^T for one k-atom: 4 k-steps x 3 split passes = 12 MMAs.
 // a_chunk: smem address of a packed weight chunk (hi image, lo image 16 KB later);
 // b_hi / b_lo: smem addresses of this k-atom's block of the activation tile (hi, lo).
 __device__ __forceinline__ void umma_katom_3x(uint32_t tmem_d, uint32_t a_chunk, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
                                               bool first) {
-  const uint64_t ah = umma_desc(a_chunk), al = umma_desc(a_chunk + 128 * 128);
-  const uint64_t bh = umma_desc(b_hi), bl = umma_desc(b_lo);
+  const uint32_t ah = umma_desc_lo(a_chunk), al = ah + ((128u * 128u) >> 4);
+  const uint32_t bh = umma_desc_lo(b_hi), bl = umma_desc_lo(b_lo);
 #pragma unroll
   for (int ks = 0; ks < kAtomK / kUmmaK; ++ks) {
-    const uint64_t adv = static_cast<uint64_t>(ks * kUmmaK * 4 >> 4);  // +32 B per k-step inside the atom
-    umma_tf32(tmem_d, al + adv, bh + adv, idesc, (first && ks == 0) ? 0u : 1u);   // small terms first
-    umma_tf32(tmem_d, ah + adv, bl + adv, idesc, 1u);
-    umma_tf32(tmem_d, ah + adv, bh + adv, idesc, 1u);
+    const uint32_t adv = static_cast<uint32_t>(ks * kUmmaK * 4) >> 4;  // +32 B per k-step inside the atom
+    umma_tf32_lo(tmem_d, al + adv, bh + adv, idesc, (first && ks == 0) ? 0u : 1u);   // small terms first
+    umma_tf32_lo(tmem_d, ah + adv, bl + adv, idesc, 1u);
+    umma_tf32_lo(tmem_d, ah + adv, bh + adv, idesc, 1u);
   }
 }
 

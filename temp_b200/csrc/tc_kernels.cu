@@ -45,7 +45,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // lane 0 of every warp stores clock64() per phase slot; slot 63 holds %globaltimer at kernel entry.
 #ifdef TEMP_TIMELINE
 __device__ unsigned long long* g_timeline = nullptr;
-constexpr int kTlWarps = 12, kTlSlots = 64;
+constexpr int kTlWarps = 20, kTlSlots = 64;
 __device__ __forceinline__ void tl_mark(int slot) {
   if (g_timeline != nullptr && (threadIdx.x & 31) == 0)
     g_timeline[(static_cast<size_t>(blockIdx.x) * kTlWarps + (threadIdx.x >> 5)) * kTlSlots + slot] = clock64();
@@ -460,25 +460,32 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
 // dependency ever crosses a partition.  One cluster of 4 CTAs (one per block of 32 hidden columns, its W_hh
 // slice resident in shared memory) walks all steps of a partition; steps are separated by a hardware cluster
 // barrier (release / acquire, ~0.2 us) instead of a grid-wide barrier, and different partitions never synchronise.
-constexpr int kScanN = 96;                     // max packed rows per partition step (UMMA N)
+constexpr int kScanN = 96;                     // max packed rows per partition step
+constexpr int kScanHalf = kScanN / 2;          // rows per worker group = UMMA N of one MMA batch
 constexpr int kScanCluster = 4;                // CTAs per cluster = blocks of 32 hidden columns
-constexpr int kScanThreads = kWorkers + 128;   // 8 worker warps + control warp (TMA + MMA issue) + 3 idle (register
-                                               // allocation is per 4 warps anyway)
-constexpr int kScanU = kScanN / kWorkerWarps;  // rows per worker thread and step
+// 16 warps = 4 per SM sub-partition = 128 registers per thread: worker group 0 = warps 0..7 (tile rows gw + 8u),
+// worker group 1 = warps 8..14 (tile rows 48 + gw + 7u), warp 15 = control (TMEM allocation, bulk copies, MMA issue).
+// (A 17th warp capped the kernel at 96 registers and the spills sat on the per-step critical path.)
+constexpr int kScanCtlWarp = 15;
+constexpr int kScanThreads = 16 * 32;
+constexpr int kScanCtlTid = kScanCtlWarp * 32;
+constexpr int kScanU = 7;                      // row slots per worker thread and step (group 0 uses 6 of them)
 constexpr int kScanAImage = kKAtoms * kWChunkBytes;   // 128 KB: this CTA's W_hh slice (r|z|n|pad rows, hi + lo)
 constexpr int kScanBImage = kScanN * kD * 4;   // 48 KB per hi / lo
-constexpr int kScanExBytes = 3 * kScanN * 32 * 4;     // gate exchange buffer, aliased onto the hi operand image
 constexpr int kScanSmem = kScanAImage + 2 * kScanBImage + 1024;
-static_assert(kScanExBytes <= kScanBImage, "the exchange buffer lives in the (dead) hi operand image");
-static_assert(kScanN % 16 == 0 && kScanN % kWorkerWarps == 0 && kScanU <= 32, "tile shape");
+static_assert(kScanHalf == 48, "the worker groups' row maps (8 x 6 and 7 x 7 slots) assume 48-row half tiles");
+static_assert(kScanHalf * 32 * 4 == kScanHalf * 128, "the gate exchange rows alias operand rows one to one");
 
 struct ScanBars {
-  uint64_t w_full, mma_done;
+  uint64_t w_full, mma_done[2];
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int group) {  // the 8 (group 0) or 7 (group 1) warps of one worker group
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(group == 0 ? 256 : 224) : "memory");
+}
 
 // fast gate math: ex2.approx / rcp.approx based, absolute error ~1e-7 (the parity bar is 1e-4 relative)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -487,16 +494,19 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 // What the gather of a step needs, fetched one step ahead (while the previous step's MMA runs) so that the serial
 // chain per step is only: cluster barrier -> L2 gather of the previous state -> MMA -> gates -> state write.
 struct ScanPre {
-  int prv;      // lanes 0..kScanU-1: previous-state row of tile row (warp + 8 * lane), -1 = zero state
+  int prv;      // lanes 0..kScanU-1: previous-state row of this thread's u-th tile row, -1 = zero state
   float dt;     // lanes 0..kScanU-1: its time gap (the decay factor is computed at use)
 };
 
-__device__ __forceinline__ void scan_prefetch(const TempGruArgs& p, int rb, int r1, int warp, int lane, ScanPre& f) {
+// tile row of slot u of worker warp gw of group g: g * 48 + gw + stride * u (stride 8 / 7), valid while gw + stride * u < 48
+__device__ __forceinline__ void scan_prefetch(const TempGruArgs& p, int rb, int r1, int row0, int stride, int lim, int lane,
+                                              ScanPre& f) {
   f.prv = -1;
   f.dt = 0.f;
   if (lane < kScanU) {
-    const int r = rb + warp + 8 * lane;
-    if (r < r1 && p.prev_row != nullptr) {
+    const int i = row0 + stride * lane;
+    const int r = rb + i;
+    if (i < lim && r < r1 && p.prev_row != nullptr) {
       f.prv = __ldg(p.prev_row + r);
       if (p.dt != nullptr) f.dt = __ldg(p.dt + r);
     }
@@ -510,20 +520,28 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   uint8_t* a_img = smem;
   uint8_t* b_hi = a_img + kScanAImage;
   uint8_t* b_lo = b_hi + kScanBImage;
-  float* ex = reinterpret_cast<float*>(b_hi);  // [3 gates][kScanN rows][32 hidden], valid between mma_done and the next gather
   __shared__ ScanBars S;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool worker = warp < kWorkerWarps;
+  const bool worker = warp < kScanCtlWarp;
+  const int grp = warp >> 3, gw = warp & 7;                 // (the control warp computes with grp 1, gw 7: unused)
+  const int stride = grp == 0 ? 8 : 7;
+  const int row0 = grp * kScanHalf + gw;                    // this thread's tile rows: row0 + stride * u, below `lim`
+  const int lim = (grp + 1) * kScanHalf;
   const int cb = blockIdx.x & (kScanCluster - 1), jb = 32 * cb;   // == %cluster_ctarank for a 1-D grid
   const int cid = blockIdx.x / kScanCluster, n_clusters = gridDim.x / kScanCluster;
+  // Gate exchange buffer of a group: gate g, tile row i -> 32 floats at operand row i of k-atom g of the hi image.
+  // Those bytes are dead once the group's MMA batch has completed (the other batch reads other rows only).
+  float* ex = reinterpret_cast<float*>(b_hi);
+  constexpr int kExGate = kScanN * 32;  // floats between gates (= one k-atom block)
 
   if (tid == 0) {
     mbar_init(&S.w_full, 1);
-    mbar_init(&S.mma_done, 1);
+    mbar_init(&S.mma_done[0], 1);
+    mbar_init(&S.mma_done[1], 1);
     fence_mbar_init();
   }
-  if (warp == kWorkerWarps) tmem_alloc(&S.tmem_base, 128);
+  if (warp == kScanCtlWarp) tmem_alloc(&S.tmem_base, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -554,7 +572,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   };
 
   const void* cur_w = nullptr;
-  uint32_t w_phase = 0, mma_phase = 0;
+  uint32_t w_phase = 0, mma_phase[2] = {0, 0};  // the second batch's barrier only completes on steps with two halves
   bool w_pending = false;
   bool arrived = false;  // a cluster-barrier arrive that has not been waited on yet
 
@@ -568,7 +586,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   }
   ScanPre cur;
   if (part < n_parts && worker)
-    scan_prefetch(P.steps[s], __shfl_sync(kFull, ranges.x, s), __shfl_sync(kFull, ranges.y, s), warp, lane, cur);
+    scan_prefetch(P.steps[s], __shfl_sync(kFull, ranges.x, s), __shfl_sync(kFull, ranges.y, s), row0, stride, lim, lane, cur);
 
 #pragma unroll 1
   while (part < n_parts) {
@@ -588,10 +606,10 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
       // every MMA that read the old image has completed (mma_done is waited on inside each step); a copy that
       // no step consumed (its steps had no previous state at all) is drained before the buffer is refilled
       if (w_pending) {
-        if (tid == kWorkers) mbar_wait(&S.w_full, w_phase);
+        if (tid == kScanCtlTid) mbar_wait(&S.w_full, w_phase);
         w_phase ^= 1;
       }
-      if (tid == kWorkers) {
+      if (tid == kScanCtlTid) {
         const uint8_t* src = static_cast<const uint8_t*>(p.whh_packed) + static_cast<size_t>(cb) * kScanAImage;
         mbar_expect_tx(&S.w_full, kScanAImage);
         for (int c = 0; c < kKAtoms; ++c) bulk_g2s(a_img + c * kWChunkBytes, src + c * kWChunkBytes, kWChunkBytes, &S.w_full);
@@ -600,6 +618,8 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
       w_pending = true;
     }
     const bool type1 = p.cell_type == TEMP_CELL_TYPE1;
+    const int rows = r1 - rb;
+    const bool two = rows > kScanHalf;  // the second half tile has rows (cluster-uniform)
     TL(2 + 6 * (s & 7));
     if (arrived) {  // the other column blocks' state writes of the previous step become visible here; also every
       cluster_wait();  // thread of this CTA is past its reads of the operand tile and of the exchange buffer
@@ -608,8 +628,8 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
     TL(3 + 6 * (s & 7));
 
     // ---- previous-state rows -> smem operand (hi / lo) ------------------------------------------------------
-    // worker (w, lane) gathers rows rb + w + 8u (lane = 4 feature columns) and later does the gate math for
-    // hidden column jb + lane of the same rows.
+    // worker (group, gw, lane) gathers tile rows row0 + 8u (lane = 4 feature columns) and later does the gate
+    // math for hidden column jb + lane of the same rows.
     int any_prev = 0;
     if (worker) {
       float4 v[kScanU];
@@ -625,8 +645,9 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
       }
 #pragma unroll
       for (int u = 0; u < kScanU; ++u) {
-        const int i = warp + 8 * u;
+        const int i = row0 + stride * u;
         const float dv = __shfl_sync(kFull, dec, u);
+        if (i >= lim) continue;  // warp-uniform: slot beyond the group's half tile
         float4 hi, lo;
         split_tf32(v[u].x * dv, hi.x, lo.x);
         split_tf32(v[u].y * dv, hi.y, lo.y);
@@ -641,31 +662,36 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
     }
     any_prev = __syncthreads_or(any_prev);
     TL(4 + 6 * (s & 7));
-    if (any_prev && tid == kWorkers) {
+    if (any_prev && tid == kScanCtlTid) {
       if (w_pending) mbar_wait(&S.w_full, w_phase);
       tc_fence_after();
-      // N = the step's rows rounded up to 16: operand rows / accumulator columns beyond it are never read
-      const uint32_t idesc = umma_idesc_tf32(128, min(kScanN, (r1 - rb + 15) & ~15));
       const uint32_t ai = smem_u32(a_img), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      // ONE MMA batch over the whole tile (N = rows rounded up to 16): every tcgen05.mma re-reads its 4 KB weight
+      // slice from shared memory, so fewer, wider MMAs are cheaper than one batch per half tile
+      const uint32_t idesc = umma_idesc_tf32(128, min(kScanN, (rows + 15) & ~15));
       for (int ka = 0; ka < kKAtoms; ++ka)
         umma_katom_3x(tbase, ai + ka * kWChunkBytes, bh + ka * (kScanN * 128), bl + ka * (kScanN * 128), idesc, ka == 0);
-      umma_commit(&S.mma_done);
+      umma_commit(&S.mma_done[0]);
+      if (two) umma_commit(&S.mma_done[1]);
+
     }
     if (any_prev && w_pending) {
       w_pending = false;
       w_phase ^= 1;
     }
     // ---- while the MMA runs: this thread's h0 values and input-gate pre-activations; the NEXT step's indices ----
-    float h0[kScanU], gi_r[kScanU], gi_z[kScanU], gi_n[kScanU], tev[kScanU];
-    float br = 0.f, bz = 0.f, bn = 0.f;
+    const bool active = worker && (grp == 0 || two);  // this group's half tile has rows
+    float h0[kScanU], gi_r[kScanU], gi_z[kScanU], gi_n[kScanU];
+    float br = 0.f, bz = 0.f, bn = 0.f, te_uni = 0.f;
+    bool te_rows = false;
     ScanPre nxt;
     if (worker) {
       const int j = jb + lane;
 #pragma unroll
       for (int u = 0; u < kScanU; ++u) {
         h0[u] = 0.f;
-        if (any_prev) {
-          const uint32_t off = static_cast<uint32_t>(cb) * (kScanN * 128) + sw128_off(warp + 8 * u, lane);
+        if (any_prev && row0 + stride * u < lim) {
+          const uint32_t off = static_cast<uint32_t>(cb) * (kScanN * 128) + sw128_off(row0 + stride * u, lane);
           h0[u] = *reinterpret_cast<const float*>(b_hi + off) + *reinterpret_cast<const float*>(b_lo + off);
         }
       }
@@ -680,9 +706,9 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
       }
 #pragma unroll
       for (int u = 0; u < kScanU; ++u) {
-        const int r = rb + warp + 8 * u;
+        const int r = rb + row0 + stride * u;
         gi_r[u] = gi_z[u] = gi_n[u] = 0.f;
-        if (r < r1) {
+        if (row0 + stride * u < lim && r < r1) {
           const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
           if (type1) {
             gi_n[u] = __ldg(gi);
@@ -694,63 +720,53 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
         }
       }
       if (n_part < n_parts)
-        scan_prefetch(P.steps[n_s], __shfl_sync(kFull, n_ranges.x, n_s), __shfl_sync(kFull, n_ranges.y, n_s), warp, lane, nxt);
-      if (p.time_embed == nullptr) {
-#pragma unroll
-        for (int u = 0; u < kScanU; ++u) tev[u] = 0.f;
-      } else if (trow0 == trow1) {
-        const float t = __ldg(p.time_embed + static_cast<size_t>(trow0) * kD + j);
-#pragma unroll
-        for (int u = 0; u < kScanU; ++u) tev[u] = t;
-      } else {
-#pragma unroll
-        for (int u = 0; u < kScanU; ++u) {
-          const int r = rb + warp + 8 * u;
-          tev[u] = r < r1 ? __ldg(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j) : 0.f;
-        }
-      }
+        scan_prefetch(P.steps[n_s], __shfl_sync(kFull, n_ranges.x, n_s), __shfl_sync(kFull, n_ranges.y, n_s), row0, stride, lim,
+                      lane, nxt);
+      te_rows = p.time_embed != nullptr && trow0 != trow1;  // tiles of a launch without partition table may mix snapshots
+      if (p.time_embed != nullptr && !te_rows) te_uni = __ldg(p.time_embed + static_cast<size_t>(trow0) * kD + j);
     }
-    if (any_prev) {
-      __syncthreads();  // every h0 read of the hi image is done before the exchange buffer overwrites it
-      mbar_wait(&S.mma_done, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after();
-      TL(5 + 6 * (s & 7));
-      if (worker && (warp & 3) < 3) {  // TMEM lane quadrant = gate; columns = rows of the tile
-        const int gate = warp & 3, hf = warp >> 2;
-        constexpr int kHalf = kScanN / 2;
-        const uint32_t ta = tbase + (static_cast<uint32_t>(32 * gate) << 16) + kHalf * hf;
-        float* exw = ex + (gate * kScanN + kHalf * hf) * 32 + lane;
-        float v[32];
-        tmem_ld32(ta, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) exw[i * 32] = v[i];
-        if (kHalf > 32) {
-          float w[16];
-          tmem_ld16(ta + 32, w);
+    if (any_prev && worker) {
+      group_sync(grp);  // every h0 read of this group's operand rows is done before the exchange overwrites them
+      if (active) {
+        mbar_wait(&S.mma_done[grp], grp == 0 ? mma_phase[0] : mma_phase[1]);
+        tc_fence_after();
+        TL(5 + 6 * (s & 7));
+        if ((gw & 3) < 3) {  // TMEM lane quadrant = gate; columns = rows of the half tile, 24 per warp
+          const int gate = gw & 3, hf = gw >> 2;
+          constexpr int kQ = kScanHalf / 2;  // 24
+          const uint32_t ta = tbase + (static_cast<uint32_t>(32 * gate) << 16) + grp * kScanHalf + kQ * hf;
+          float* exw = ex + gate * kExGate + (grp * kScanHalf + kQ * hf) * 32 + lane;
+          float v[16], w[8];
+          tmem_ld16(ta, v);
+          tmem_ld8(ta + 16, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < kHalf - 32; ++i) exw[(32 + i) * 32] = w[i];
+          for (int i = 0; i < 16; ++i) exw[i * 32] = v[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) exw[(16 + i) * 32] = w[i];
         }
+        tc_fence_before();
       }
-      tc_fence_before();
-      __syncthreads();
+      group_sync(grp);
+    }
+    if (any_prev) {
+      mma_phase[0] ^= 1;
+      if (two) mma_phase[1] ^= 1;
     }
     TL(6 + 6 * (s & 7));
 
-    if (worker) {
+    if (active) {
       const int j = jb + lane;
 #pragma unroll
       for (int u = 0; u < kScanU; ++u) {
-        const int i = warp + 8 * u;
+        const int i = row0 + stride * u;
         const int r = rb + i;
-        if (r < r1) {  // warp-uniform
+        if (i < lim && r < r1) {  // warp-uniform
           float hr = br, hz = bz, hn = bn;
           if (any_prev) {
-            hr += ex[(0 * kScanN + i) * 32 + lane];
-            hz += ex[(1 * kScanN + i) * 32 + lane];
-            hn += ex[(2 * kScanN + i) * 32 + lane];
+            hr += ex[0 * kExGate + i * 32 + lane];
+            hz += ex[1 * kExGate + i * 32 + lane];
+            hn += ex[2 * kExGate + i * 32 + lane];
           }
           float hy;
           if (type1) {  // GRU_cell.py:22-29
@@ -763,7 +779,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
             const float ng = fast_tanh(gi_n[u] + rg * hn);
             hy = (1.f - zg) * ng + zg * h0[u];
           }
-          hy += tev[u];
+          hy += te_rows ? __ldg(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j) : te_uni;
           float* o = p.out + static_cast<size_t>(r) * kD + j;
           *o = p.accumulate ? (__ldcg(o) + hy) : hy;
         }
@@ -779,12 +795,12 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
     s = n_s;
     ranges = n_ranges;
   }
-  if (w_pending && tid == kWorkers) mbar_wait(&S.w_full, w_phase);  // drain a copy no step consumed
+  if (w_pending && tid == kScanCtlTid) mbar_wait(&S.w_full, w_phase);  // drain a copy no step consumed
   if (arrived) cluster_wait();
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWorkerWarps) tmem_dealloc(tbase, 128);
+  if (warp == kScanCtlWarp) tmem_dealloc(tbase, 128);
 }
 
 template <typename K>
@@ -799,7 +815,7 @@ int ensure_smem_once(K kernel, int bytes, const char* name, bool& done) {
 }  // namespace
 
 #ifdef TEMP_TIMELINE
-extern "C" int temp_debug_timeline(void* device_buffer) {  // [ctas][12 warps][64 slots] u64, or null to disable
+extern "C" int temp_debug_timeline(void* device_buffer) {  // [ctas][20 warps][64 slots] u64, or null to disable
   unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
   return cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
 }

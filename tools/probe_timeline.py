@@ -36,7 +36,7 @@ model = bench.init_state(store).to(dev).eval()
 tl = bench.batches(store, 1)[0]
 res = model.encode(tl)
 torch.cuda.synchronize()
-WARPS, SLOTS = 12, 64
+WARPS, SLOTS = 20, 64  # kTlWarps, kTlSlots of the probe build
 MAXCTA = 4096
 buf = torch.zeros(MAXCTA * WARPS * SLOTS, dtype=torch.int64, device=dev)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -71,7 +71,7 @@ for cold in (True, False):
         g0 = t[:, :, 63].astype(np.float64)
         g0 = g0[g0 > 0]
         print("   CTA start spread (globaltimer): %.2f us" % ((g0.max() - g0.min()) / 1e3))
-        for w, label in ((0, "worker warp 0"), (7, "worker warp 7"), (9, "mma warp (layer)"), (8, "control warp")):
+        for w, label in ((0, "worker warp 0"), (7, "worker warp 7"), (9, "mma warp (layer)"), (8, "warp 8"), (15, "scan control warp")):
             rel = t[:, w, :63].astype(np.float64) - t[:, w, 0:1].astype(np.float64)
             ok = t[:, w, :63] != 0
             line = []
