@@ -115,6 +115,28 @@ class TKG_Module(nn.Module):
         res.program.run()
         return res
 
+    @torch.no_grad()
+    def encode_sharded(self, t_list=None, plan: Optional[WindowPlan] = None, group=None, prepared=None) -> EncodeResult:
+        """``encode`` with ONE window batch cut over the ranks of ``group`` (temp_b200/sharding.py): snapshot
+        instances for the RGCN layers, chain partitions for the GRU scan, two exchanges.  Every rank calls it with
+        the same ``t_list`` and ends up with the complete final-layer states in ``res.out``."""
+        import torch.distributed as dist
+        from .sharding import exchange_blocks, exchange_rows, make_shard_plan
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if prepared is None:
+            if plan is None:
+                plan = self.plan(t_list)
+            shard = make_shard_plan(plan, world)
+            res = self.runtime.build_sharded(plan, shard, rank)
+            res.shard = shard
+        else:
+            res, shard = prepared, prepared.shard
+        res.programs[0].run()
+        exchange_blocks(res.bufs["gi"], shard.row_bounds, group)
+        res.programs[1].run()
+        exchange_rows(res.state, shard.final_rows, rank, group, shard.cache)
+        return res
+
     # ---- reference API ----------------------------------------------------------------------------
     def get_batch_graph_list(self, t_list, seq_len, graph_dict):
         """models/TKG_Module.py:232-250 (kept for callers; the hot path uses the planner instead)."""

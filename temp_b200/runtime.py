@@ -315,8 +315,38 @@ class EncoderRuntime(object):
                                            te_out=enc.use_time_embedding))
         return EncodeResult(plan, out, None, prog, {"h1": h1})
 
-    def _build_recurrent(self, plan, prog, dptr):
+    def build_sharded(self, plan: WindowPlan, shard, rank: int) -> EncodeResult:
+        """The rank's share of a snapshot-sharded forward (temp_b200/sharding.py): ``res.programs`` = [both RGCN
+        layers for the rank's block of snapshot instances, the GRU scan over the rank's chain partitions]; the caller
+        runs the two exchanges in between / after."""
+        m = self.model
+        if not (m.family == "recurrent" and m.ent_encoder.rec_only_last_layer and m.args.module in ("GRRGCN", "BiGRRGCN")
+                and self.use_tc and m.embed_size == 128 and self.fuse_scan):
+            raise RuntimeError("temp_b200: snapshot sharding covers the --rec-only-last-layer GRU families at D = 128; "
+                               "other configurations shard over target timestamps only (SURVEY.md section 8e)")
+        plan.scan_parts = shard.parts                       # same partitions, rank-major order
+        prog = lib.Program()
+        dptr = self.stage_plan(plan, prog)
+        res = self._build_recurrent(plan, prog, dptr, shard=shard, rank=rank)
+        ops = res.program.ops
+        first_scan = next(i for i, o in enumerate(ops) if o.kind in (lib.OP_GRU, lib.OP_GRU_SCAN))
+        res.programs = []
+        for part in (ops[:first_scan], ops[first_scan:]):
+            pr = lib.Program()
+            pr.ops = list(part)
+            pr.keepalive = res.program.keepalive
+            res.programs.append(pr)
+        return res
+
+    def _build_recurrent(self, plan, prog, dptr, shard=None, rank=0):
         m, D, R = self.model, self.model.embed_size, plan.R
+
+        def mine(rows):                                     # a launch's row range cut to this rank's block
+            if shard is None:
+                return rows
+            lo, hi = shard.rows_of(rank)
+            return (max(rows[0], lo), max(min(rows[1], hi), max(rows[0], lo)))
+
         enc = m.ent_encoder
         l1, l2 = enc.layer_1, enc.layer_2
         gru = m.args.module in ("GRRGCN", "BiGRRGCN")
@@ -372,13 +402,14 @@ class EncoderRuntime(object):
 
         if enc.rec_only_last_layer:
             # layer 1 for every snapshot instance at once
-            prog.add(lib.OP_LAYER, self._layer(l1, (0, R), dptr, x=m.ent_embeds, x_is_embed=True, act=False,
+            prog.add(lib.OP_LAYER, self._layer(l1, mine((0, R)), dptr, x=m.ent_embeds, x_is_embed=True, act=False,
                                                terms=[self._term(m.ent_embeds, l1.loop_weight, index=dptr["ent_id"])],
                                                h_out=h1))
             if gru:
                 # layer-2 aggregation + self loop + GRU input gates: also recurrence free.  Row groups
                 # that share the same chained weights are launched together.
                 gi = self.ws.get("gi_l2", R * 2 * G)[:R * 2 * G].view(R, 2 * G)
+                bufs["gi"] = gi
                 groups = {}
                 for seg in plan.segments:
                     key = tuple(dirs_of(seg))
@@ -387,7 +418,7 @@ class EncoderRuntime(object):
                 for dirs, rows in groups.items():
                     rnns = [rnn_of(l2, d) for d in dirs]
                     w, b = self._wih("layer_2", rnns)
-                    prog.add(lib.OP_LAYER, self._layer(l2, rows, dptr, x=h1, x_is_embed=False, act=relu2,
+                    prog.add(lib.OP_LAYER, self._layer(l2, mine(rows), dptr, x=h1, x_is_embed=False, act=relu2,
                                                        terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, 2 * G)))
                 for g, seg in enumerate(plan.segments):
                     rows = (seg.row0, seg.row1)
@@ -417,7 +448,9 @@ class EncoderRuntime(object):
         if self.fuse_scan:
             parts = plan.scan_parts if (self.use_tc and enc.rec_only_last_layer and gru) else None
             if parts is not None and parts.shape[0] > 0:
-                prog.fuse_gru_scans(self.scan_barrier(), dptr["scan_parts"], int(parts.shape[0]), int(parts.shape[1]))
+                p_lo, p_hi = (0, int(parts.shape[0])) if shard is None else shard.parts_of(rank)
+                stride = int(parts.shape[1])
+                prog.fuse_gru_scans(self.scan_barrier(), dptr["scan_parts"] + 8 * stride * p_lo, p_hi - p_lo, stride)
             else:
                 prog.fuse_gru_scans(self.scan_barrier())
         return EncodeResult(plan, out, S, prog, bufs)

@@ -75,3 +75,52 @@ def test_cooperative_scan_equals_per_step_launches(name):
     assert torch.equal(a, b.out)
     for _ in range(3):                      # the barrier word is self-cleaning: repeated launches stay correct
         assert torch.equal(a, model.encode(case["t_list"]).out)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8"])
+def test_snapshot_sharded_forward_equals_unsharded(name, world):
+    """SURVEY section 8e on one GPU: the per-rank launch programs of a snapshot-sharded forward (RGCN layers cut by
+    snapshot instance, GRU scan cut by chain partition), with the two exchanges emulated by device copies, reproduce
+    the unsharded forward bit for bit."""
+    from tests.helpers import CASE_BY_NAME
+    from temp_b200.sharding import make_shard_plan
+    case = CASE_BY_NAME[name]
+    ref_model = product_model(case)
+    want = ref_model.encode(case["t_list"]).out.clone()
+    shard = make_shard_plan(ref_model.plan(case["t_list"]), world)
+    models = [product_model(case) for _ in range(world)]
+    res = [m.runtime.build_sharded(m.plan(case["t_list"]), shard, r) for r, m in enumerate(models)]
+    for r in res:
+        r.programs[0].run()
+    torch.cuda.synchronize()
+    for src in range(world):                                            # exchange 1: gi blocks
+        lo, hi = shard.rows_of(src)
+        for dst in range(world):
+            if dst != src:
+                res[dst].bufs["gi"][lo:hi] = res[src].bufs["gi"][lo:hi]
+    for r in res:
+        r.programs[1].run()
+    torch.cuda.synchronize()
+    for src in range(world):                                            # exchange 2: final-layer states
+        rows = torch.as_tensor(shard.final_rows[src], device="cuda")
+        for dst in range(world):
+            if dst != src:
+                res[dst].state[rows] = res[src].state[rows]
+    for r in res:
+        assert torch.equal(r.out, want)
+
+
+def test_snapshot_sharded_forward_over_nccl():
+    """The same through torch.distributed / NCCL, one process per GPU (needs >= 2 GPUs on the box)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tools", "check_sharded.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sharded ok" in out.stdout

@@ -198,3 +198,72 @@ def test_state_dict_keys_match_the_reference_shapes():
         model = build_module(product_args(case), store.num_ents, store.num_rels, store.train)
         got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
         assert got == orc.param_shapes(cfg), case["name"]
+
+
+# ---- snapshot sharding: host logic + the two exchanges over gloo, world_size 2 ------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8", "grrgcn_tiny_d128_last"])
+def test_shard_plan_cuts_instances_and_partitions(name, world):
+    from tests.helpers import CASE_BY_NAME
+    from temp_b200.sharding import make_shard_plan
+    plan = _plan_for(CASE_BY_NAME[name])
+    sp = make_shard_plan(plan, world)
+    assert sp.row_bounds[0] == 0 and sp.row_bounds[-1] == plan.R and (np.diff(sp.row_bounds) >= 0).all()
+    starts = {inst.row0 for seg in plan.segments for inst in seg.instances} | {plan.R}
+    assert all(int(b) in starts for b in sp.row_bounds)                 # blocks are whole snapshot instances
+    assert sp.parts.shape == plan.scan_parts.shape and sp.part_offset[-1] == plan.scan_parts.shape[0]
+    key = lambda t: sorted(map(tuple, t.reshape(t.shape[0], -1).tolist()))
+    assert key(sp.parts) == key(plan.scan_parts)                        # same partitions, rank-major order
+    fin = plan.final
+    got = np.sort(np.concatenate(sp.final_rows))
+    assert np.array_equal(got, np.arange(fin.row0, fin.row1))           # every final row has exactly one owner
+
+
+def _gloo_worker(rank, world, port, name, out_q):
+    import torch.distributed as dist
+    from tests.helpers import CASE_BY_NAME
+    from temp_b200.sharding import exchange_blocks, exchange_rows, make_shard_plan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = _plan_for(CASE_BY_NAME[name])
+        sp = make_shard_plan(plan, world)
+        truth = torch.arange(plan.R * 6, dtype=torch.float32).reshape(plan.R, 6) * 0.5 + 1.0
+        # exchange 1: every rank fills only its block of rows
+        gi = torch.full((plan.R, 6), float("nan"))
+        lo, hi = sp.rows_of(rank)
+        gi[lo:hi] = truth[lo:hi]
+        exchange_blocks(gi, sp.row_bounds)
+        ok1 = bool(torch.equal(gi, truth))
+        # exchange 2: every rank fills only the final rows of its chain partitions
+        state = torch.full((plan.R, 6), -7.0)
+        mine = torch.as_tensor(sp.final_rows[rank])
+        state[mine] = truth[mine]
+        for _ in range(2):                                              # second call goes through the cache
+            exchange_rows(state, sp.final_rows, rank, None, sp.cache)
+        fin = plan.final
+        ok2 = bool(torch.equal(state[fin.row0:fin.row1], truth[fin.row0:fin.row1]))
+        ok3 = bool((state[:fin.row0] == -7.0).all())                    # nothing else is touched
+        out_q.put((rank, ok1, ok2, ok3))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8"])
+def test_shard_exchanges_over_gloo_world_size_2(name):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True, True), (1, True, True, True)]
