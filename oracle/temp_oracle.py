@@ -168,6 +168,13 @@ def edge_subgraph(g: SnapGraph, edge_idx: np.ndarray) -> SnapGraph:
 # --------------------------------------------------------------------------------------------
 # layers
 # --------------------------------------------------------------------------------------------
+def sample_edges(g: SnapGraph, rate: float) -> SnapGraph:
+    """models/DynamicRGCN.py:82-89: np.random.choice(arange(E), size=int(rate * E), replace=False) -> edge_subgraph with
+    the drawn order kept and norms recomputed."""
+    idx = np.random.choice(np.arange(g.num_edges), size=int(rate * g.num_edges), replace=False)
+    return edge_subgraph(g, idx)
+
+
 def batch_graphs(graphs: Sequence[SnapGraph]):
     """dgl.batch as used at models/DynamicRGCN.py:92: block-diagonal union, node ids offset by the
     running node count, edges concatenated in list order."""
@@ -476,7 +483,7 @@ class OracleModel:
             dt.append((cur_t - start[i][idx]).view(-1, 1))
         return torch.cat(f), torch.cat(s), torch.cat(dt)
 
-    def _scan(self, time_batched, direction: str):
+    def _scan(self, time_batched, direction: str, sample_rate: Optional[float] = None):
         cfg = self.cfg
         L, bsz = cfg.seq_len, len(time_batched[0])
         hist = torch.zeros(bsz, 2, self.M, self.D)
@@ -486,6 +493,8 @@ class OracleModel:
             if not ts:
                 continue
             graphs = [self.gd[t] for t in ts]
+            if sample_rate is not None:                                    # --random-dropout, DynamicRGCN.py:161,171
+                graphs = [sample_edges(g, sample_rate) for g in graphs]
             p1, p2, dt = self._gather_prev(graphs, hist, start, k)
             first, second = self.enc_recurrent(graphs, ts, [p1], [p2], [dt], direction)
             hist = torch.zeros(bsz, 2, self.M, self.D)                   # DynamicRGCN.py:48 (fresh zeros)
@@ -544,6 +553,38 @@ class OracleModel:
             res.update(hist=hist, start=start)
         res["per_graph"] = list(out.split(sizes))
         return res
+
+    def train_loss(self, t_list: Sequence[int], negative_rate: int, num_pos_facts: int,
+                   random_dropout: bool = False) -> Tensor:
+        """The training forward of models/DynamicRGCN.py:176-194 (GRRGCN / RRGCN) with dropout p = 0: history steps
+        on full graphs (or np.random.choice 80 % edge subsets with --random-dropout), the final step on a 50 % edge
+        subset with recomputed norms (DynamicRGCN.py:76-94), then per target graph the negative sampler on the FULL
+        graph and the tail + head cross-entropy (TKG_Module.py:202-213).  Global NumPy / torch RNG order as in the
+        reference."""
+        cfg = self.cfg
+        assert not cfg.bidirectional and not cfg.attention and cfg.module != "SRGCN"
+        L = cfg.seq_len
+        tb = window_forward(t_list, L, self.times)
+        ts = tb[-1]
+        full_graphs = [self.gd[t] for t in ts]
+        hist, start = self._scan(tb, "forward", sample_rate=0.8 if random_dropout else None)
+        p1, p2, dt = self._gather_prev(full_graphs, hist, start, L - 1)
+        graphs = [sample_edges(g, 0.5) for g in full_graphs]
+        _, out = self.enc_recurrent(graphs, ts, [p1], [p2], [dt], "forward")
+        res = {"times": ts, "graphs": full_graphs, "hist": hist, "start": start,
+               "per_graph": list(out.split([g.num_nodes for g in full_graphs]))}
+        score = {"complex": score_complex, "distmult": score_distmult, "transE": score_transe}["complex"]
+        rel = self.p["rel_embeds"]
+        loss = torch.zeros(())
+        for i, g in enumerate(full_graphs):
+            tri, neg_t, neg_h, lab = negative_samples(g, self.M, negative_rate, num_pos_facts)
+            tri, neg_t, neg_h, lab = (torch.from_numpy(np.asarray(x)).long() for x in (tri, neg_t, neg_h, lab))
+            ent = res["per_graph"][i]
+            alls = self.all_embeds(res, i)
+            r = rel[tri[:, 1]]
+            loss = loss + torch.nn.functional.cross_entropy(score(ent[tri[:, 0]], r, alls[neg_t], mode="tail"), lab)
+            loss = loss + torch.nn.functional.cross_entropy(score(alls[neg_h], r, ent[tri[:, 2]], mode="head"), lab)
+        return loss
 
     def _tau(self) -> Tensor:
         L = self.cfg.seq_len

@@ -94,9 +94,24 @@ class TKG_Module(nn.Module):
             self._corrupter = CorruptTriples(self.args, self.graph_dict_train)
         return self._corrupter
 
-    def plan(self, t_list, seq_len: Optional[int] = None) -> WindowPlan:
+    def plan(self, t_list, seq_len: Optional[int] = None, transform=None) -> WindowPlan:
         return plan_window(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len,
-                           bidirectional=self.bidirectional, attention=self.family == "attention")
+                           bidirectional=self.bidirectional, attention=self.family == "attention", transform=transform)
+
+    def train_edge_sampler(self):
+        """Training-mode edge sub-sampling of the window (models/DynamicRGCN.py:76-94, 161-171): the final step keeps
+        ``int(0.5 E)`` edges, history steps ``int(0.8 E)`` with ``--random-dropout``; indices come from the GLOBAL
+        NumPy stream in the reference's call order, the drawn order is the new edge order and the
+        norms are recomputed on the sub-graph."""
+        random_dropout = bool(getattr(self.args, "random_dropout", False))
+
+        def transform(kind, snap):
+            if kind == "hist" and not random_dropout:
+                return snap
+            rate = 0.5 if kind == "final" else 0.8
+            idx = np.random.choice(np.arange(snap.num_edges), size=int(rate * snap.num_edges), replace=False)
+            return snap.edge_subset(idx)
+        return transform
 
     bidirectional = False
 
@@ -205,9 +220,17 @@ class TKG_Module(nn.Module):
 
     @torch.no_grad()
     def forward(self, t_list, reverse=False):
-        """Training loss of the reference (models/DynamicRGCN.py:176-194) on FULL graphs: negative
-        sampling stays host-side and bit-exact; the encoder runs the CUDA forward (no autograd)."""
-        res = self.encode(t_list)
+        """Training loss of the reference (models/DynamicRGCN.py:176-194).  In ``train()`` mode the window is
+        edge-sub-sampled like the reference (``train_edge_sampler``); in ``eval()`` mode it runs on full graphs.
+        Negative sampling stays host-side and bit-exact; the encoder runs the CUDA forward (no autograd)."""
+        if self.training:
+            if self.family != "recurrent" or self.bidirectional:
+                raise NotImplementedError("temp_b200: the training-mode edge sub-sampling is implemented for DynamicRGCN "
+                                          "(GRRGCN / RRGCN); call .eval() for the deterministic forward of this family")
+            # (the self-loop dropout of models/RGCN.py:58-59 is not applied by the CUDA forward: parity holds at p = 0)
+            res = self.encode(plan=self.plan(t_list, transform=self.train_edge_sampler()))
+        else:
+            res = self.encode(t_list)
         dev = self.ent_embeds.device
         loss = 0
         for i, (t, g, ent_embed) in enumerate(zip(res.plan.final_times, res.plan.final_snapshots, res.per_graph)):

@@ -190,11 +190,16 @@ def _match_prev(cur: Snapshot, prev_inst: Optional[Instance]) -> Optional[np.nda
 
 
 def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len: int, bidirectional: bool = False,
-                attention: bool = False) -> WindowPlan:
+                attention: bool = False, transform=None) -> WindowPlan:
     """Plan the forward of (Bi)DynamicRGCN / (Bi)SelfAttentionRGCN for the target timestamps ``t_list``.
 
     Row order: forward history steps 0..L-2, then (Bi) backward history steps 0..L-2, then the final
-    (centre) step whose graphs are the targets in descending-time order."""
+    (centre) step whose graphs are the targets in descending-time order.
+
+    ``transform(kind, snapshot) -> snapshot`` (kind 'hist' | 'final') substitutes the graph an instance is computed
+    on -- the training-mode edge sub-sampling of models/DynamicRGCN.py:76-94 -- and is called in the reference's
+    order: history steps outer, batch items inner, then the final step's items.  ``plan.final_snapshots`` keeps the
+    full graphs (the negative sampler works on them, DynamicRGCN.py:185-187)."""
     times = list(graph_dict.keys())
     L, B = int(seq_len), len(t_list)
     plan = WindowPlan()
@@ -214,6 +219,8 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
                 if tim is None:
                     continue
                 snap = graph_dict[tim]
+                if transform is not None:
+                    snap = transform("hist", snap)
                 item = (B - 1 - j) if flip else j                     # BiDynamicRGCN.py:97-99 (flip)
                 prev = _match_prev(snap, last[j])
                 inst = Instance(item, k, kind[-1], tim, pk.add(snap), snap.num_nodes, snap)
@@ -239,7 +246,8 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
     slot_rows = []
     for i in range(B):
         tim = fwd[i][L - 1]
-        snap = graph_dict[tim]
+        full_snap = graph_dict[tim]
+        snap = transform("final", full_snap) if transform is not None else full_snap
         inst = Instance(i, L - 1, "c", tim, pk.add(snap), snap.num_nodes, snap)
         pf = _match_prev(snap, last_f[i])
         pk.add_prev(snap.num_nodes, pf, 1.0 if pf is not None else float(L - 1))
@@ -249,7 +257,7 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
         seg.instances.append(inst)
         plan.final_times.append(tim)
         plan.final_sizes.append(snap.num_nodes)
-        plan.final_snapshots.append(snap)
+        plan.final_snapshots.append(full_snap)
         if attention:
             cols = []
             for k in range(L - 1):

@@ -355,6 +355,7 @@ class EncoderRuntime(object):
         relu2 = bi                                         # BiRRGCN.py:202-203 vs RRGCN.py:186-187
         type1 = bool(getattr(m.args, "type1", False))
         G = D if type1 else 3 * D                          # gi width of one cell
+        GL = G * (2 if bi else 1)                          # row pitch of gi: one cell, two for the Bi centre step
         final = plan.final
         h1 = self.ws.get("h1", R * D)[:R * D].view(R, D)
         S = self.ws.get("state", R * D)[:R * D].view(R, D)
@@ -382,13 +383,13 @@ class EncoderRuntime(object):
             if gru:
                 rnns = [rnn_of(layer, d) for d in dirs]
                 w, b = self._wih(lname, rnns)
-                gi = self.ws.get("gi_" + lname, R * 2 * G)[:R * 2 * G].view(R, 2 * G)
+                gi = self.ws.get("gi_" + lname, R * GL)[:R * GL].view(R, GL)
                 prog.add(lib.OP_LAYER, self._layer(layer, rows, dptr, x=x_in, x_is_embed=x_is_embed, act=relu,
                                                    terms=[self._term(x_in, layer.loop_weight, index=index)],
-                                                   chain=(w, b, gi, 2 * G)))
+                                                   chain=(w, b, gi, GL)))
                 for j, d in enumerate(dirs):
                     pv, dt = prev_ptrs(d, seg)
-                    prog.add(lib.OP_GRU, self._gru(layer, rnns[j][1], rnns[j][0], rows, gi=gi, gi_ld=2 * G, gi_off=j * G,
+                    prog.add(lib.OP_GRU, self._gru(layer, rnns[j][1], rnns[j][0], rows, gi=gi, gi_ld=GL, gi_off=j * G,
                                                    state=state_prev, prev=pv, dt=dt, out=out,
                                                    te=te and j == len(dirs) - 1, accumulate=j > 0, dptr=dptr,
                                                    layer_name=lname))
@@ -408,7 +409,7 @@ class EncoderRuntime(object):
             if gru:
                 # layer-2 aggregation + self loop + GRU input gates: also recurrence free.  Row groups
                 # that share the same chained weights are launched together.
-                gi = self.ws.get("gi_l2", R * 2 * G)[:R * 2 * G].view(R, 2 * G)
+                gi = self.ws.get("gi_l2", R * GL)[:R * GL].view(R, GL)
                 bufs["gi"] = gi
                 groups = {}
                 for seg in plan.segments:
@@ -419,14 +420,14 @@ class EncoderRuntime(object):
                     rnns = [rnn_of(l2, d) for d in dirs]
                     w, b = self._wih("layer_2", rnns)
                     prog.add(lib.OP_LAYER, self._layer(l2, mine(rows), dptr, x=h1, x_is_embed=False, act=relu2,
-                                                       terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, 2 * G)))
+                                                       terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, GL)))
                 for g, seg in enumerate(plan.segments):
                     rows = (seg.row0, seg.row1)
                     dirs = dirs_of(seg)
                     for j, d in enumerate(dirs):
                         name, rnn = rnn_of(l2, d)
                         pv, dt = prev_ptrs(d, seg)
-                        prog.add(lib.OP_GRU, self._gru(l2, rnn, name, rows, gi=gi, gi_ld=2 * G, gi_off=j * G, state=S,
+                        prog.add(lib.OP_GRU, self._gru(l2, rnn, name, rows, gi=gi, gi_ld=GL, gi_off=j * G, state=S,
                                                        prev=pv, dt=dt, out=S, te=use_te and j == len(dirs) - 1,
                                                        accumulate=j > 0, dptr=dptr, layer_name="layer_2", part_col=g))
             else:

@@ -55,3 +55,12 @@ SAMPLER_CASES = [
     dict(name="sampler_tiny_subsample", dataset="tiny", times=[2, 9], seed=7, negative_rate=6, num_pos_facts=10),
     dict(name="sampler_icews_seed123", dataset="icews14_head", times=[3], seed=123, negative_rate=500, num_pos_facts=3000),
 ]
+
+# Training-mode forward (models/DynamicRGCN.py:176-194) with dropout p = 0: edge sub-sampling of the final step (and of
+# the history steps with --random-dropout), negative sampling, tail + head cross-entropy -> the scalar loss.
+TRAIN_CASES = [
+    dict(name="train_grrgcn_tiny", base="grrgcn_tiny_d128_last", seed=11, random_dropout=False),
+    dict(name="train_grrgcn_tiny_random_dropout", base="grrgcn_tiny_d128_last", seed=12, random_dropout=True),
+    dict(name="train_rrgcn_tiny", base="rrgcn_tiny_d128_last", seed=13, random_dropout=False),
+    dict(name="train_grrgcn_icews", base="grrgcn_icews_d128_L8", seed=5, random_dropout=True, negative_rate=20),
+]

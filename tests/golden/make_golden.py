@@ -20,7 +20,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from tests.golden.cases import CASES, SAMPLER_CASES, dataset_path  # noqa: E402
+from tests.golden.cases import CASES, SAMPLER_CASES, TRAIN_CASES, dataset_path  # noqa: E402
 from oracle.temp_oracle import fill_values  # noqa: E402
 
 
@@ -57,7 +57,20 @@ def ref_graph_dicts(args):
     return num_e, num_r, gtr, gva, gte
 
 
-def ref_model(case):
+def run_train_case(tc):
+    """loss = model.forward(t_list) of the unmodified reference in train mode, dropout p = 0, fixed global seeds."""
+    base = dict(next(c for c in CASES if c["name"] == tc["base"]))
+    base.update({k: v for k, v in tc.items() if k in ("negative_rate", "num_pos_facts")})
+    model, _ = ref_model(base, dropout=0.0, random_dropout=tc["random_dropout"])
+    model.train()
+    np.random.seed(tc["seed"])
+    torch.manual_seed(tc["seed"])
+    with torch.no_grad():
+        loss = model.forward(torch.tensor(base["t_list"], dtype=torch.long))
+    return {"loss": np.asarray(float(loss), dtype=np.float64)}
+
+
+def ref_model(case, dropout=None, random_dropout=False):
     from baselines.StaticRGCN import StaticRGCN
     from models.BiDynamicRGCN import BiDynamicRGCN
     from models.BiSelfAttentionRGCN import BiSelfAttentionRGCN
@@ -66,6 +79,9 @@ def ref_model(case):
     cls = {"SRGCN": StaticRGCN, "GRRGCN": DynamicRGCN, "RRGCN": DynamicRGCN, "BiGRRGCN": BiDynamicRGCN,
            "BiRRGCN": BiDynamicRGCN, "SARGCN": SelfAttentionRGCN, "BiSARGCN": BiSelfAttentionRGCN}[case["module"]]
     args = ref_args(case)
+    if dropout is not None:
+        args.dropout = dropout
+    args.random_dropout = random_dropout
     num_e, num_r, gtr, gva, gte = ref_graph_dicts(args)
     torch.manual_seed(123)
     with torch.no_grad():
@@ -160,11 +176,17 @@ def run_sampler_case(case):
 def main():
     warnings.filterwarnings("ignore")
     reference_on_path()
-    for case in CASES:
+    only_train = "--train-only" in sys.argv
+    for case in ([] if only_train else CASES):
         res = run_case(case)
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **res)
         print("%-40s rows=%d  %.1f KB" % (case["name"], res["per_graph"].shape[0], os.path.getsize(path) / 1024))
+    for case in TRAIN_CASES:
+        res = run_train_case(case)
+        path = os.path.join(HERE, case["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print("%-40s loss=%.9g" % (case["name"], float(res["loss"])))
     for case in SAMPLER_CASES:
         res = run_sampler_case(case)
         path = os.path.join(HERE, case["name"] + ".npz")

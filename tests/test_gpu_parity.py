@@ -124,3 +124,22 @@ def test_snapshot_sharded_forward_over_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "sharded ok" in out.stdout
+
+
+@pytest.mark.parametrize("tc", __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES,
+                         ids=lambda c: c["name"])
+def test_training_forward_loss_matches_reference(tc):
+    """forward() in train mode: edge sub-sampled window (global NumPy stream, reference call order), CUDA encoder,
+    bit-exact negative sampling, tail + head cross-entropy -> the reference's loss under the same seeds (p = 0)."""
+    from tests.helpers import CASE_BY_NAME
+    case = dict(CASE_BY_NAME[tc["base"]])
+    case.update({k: v for k, v in tc.items() if k in ("negative_rate", "num_pos_facts")})
+    gold = load_golden(tc["name"])
+    model = product_model(case)
+    model.args.dropout = 0.0
+    model.args.random_dropout = tc["random_dropout"]
+    model.train()
+    np.random.seed(tc["seed"])
+    torch.manual_seed(tc["seed"])
+    loss = float(model.forward(torch.tensor(case["t_list"])))
+    assert abs(loss - float(gold["loss"])) <= RTOL * abs(float(gold["loss"]))

@@ -75,3 +75,21 @@ def test_hand_computed_micro_graph():
     want2 = (h[0] * W[0] + h[1] * W[1] + 2 * h[2] * W[0]) / 16.0
     assert torch.equal(agg[0], torch.zeros(D)) and torch.equal(agg[1], torch.zeros(D))
     assert torch.allclose(agg[2], want2, rtol=1e-6)
+
+
+@pytest.mark.parametrize("tc", __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES,
+                         ids=lambda c: c["name"])
+def test_training_forward_loss_matches_reference(tc):
+    """Training-mode forward (edge sub-sampling of the window, negative sampling, tail + head cross-entropy) against
+    the loss of the unmodified reference under the same global seeds (dropout p = 0)."""
+    from tests.helpers import CASE_BY_NAME
+    case = dict(CASE_BY_NAME[tc["base"]])
+    gold = load_golden(tc["name"])
+    model = oracle_model(case)
+    np.random.seed(tc["seed"])
+    torch.manual_seed(tc["seed"])
+    with torch.no_grad():
+        loss = model.train_loss(case["t_list"], tc.get("negative_rate", case.get("negative_rate", 5)),
+                                tc.get("num_pos_facts", case.get("num_pos_facts", 3000)),
+                                random_dropout=tc["random_dropout"])
+    assert abs(float(loss) - float(gold["loss"])) <= 2e-5 * abs(float(gold["loss"]))
