@@ -324,32 +324,25 @@ def main():
         dist.barrier()
     clocks = sampler.stop()
 
-    # ---- dominant kernel, timed alone with CUDA events on its stream (roofline) ------------------
-    res0 = results[0][0]
-    layer_ops = [o for o in res0.program.ops if o.kind == lib.OP_LAYER]
-    dom = lib.Program()
-    dom.ops = [layer_ops[-1]]                 # layer-2 aggregation + self loop + GRU input gates, all rows
-    reps = 50
-    ks = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
-    ke = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
-    for i in range(reps):
-        flush.fill_(1.0)
-        ks[i].record()
-        dom.run()
-        ke[i].record()
-    torch.cuda.synchronize()
-    dom_ms = float(np.median([s.elapsed_time(e) for s, e in zip(ks, ke)]))
+    # ---- every kernel of the step timed alone with CUDA events on its stream (roofline) -------------------------
     D = WORKLOAD["D"]
-    p0 = res0.plan
-    w_bytes = 4 * (model.ent_encoder.layer_2.weight.numel() + D * D + D * 3 * D + 3 * D)
-    dom_bytes = p0.R * (4 * D + 12 * D + 12) + 8 * p0.E + w_bytes   # read h1, write gi, row_ptr/norm/..., edges, weights
+    res0 = results[0][0]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    kernels = kernel_rooflines(res0, model, flush, peak, flush_l2=True)
+    dom_name = max(kernels, key=lambda k: kernels[k]["kernel_ms"])
+    dom = kernels[dom_name]
+    traffic = None
+    try:                                                        # per-launch DRAM bytes of that kernel from the committed
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))   # ncu --set full capture
+        traffic = tr.get(dom_name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    p0 = res0.plan
     step_bytes = 2588 * p0.R + 16 * p0.E + 900000               # SURVEY section 8d whole-forward figure
 
     # ---- reduce over ranks ------------------------------------------------------------------------
@@ -373,11 +366,13 @@ def main():
             "gpu_launches": int(launches),
             "launches_per_step": results[0][0].program.kernel_count(),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "rgcn_layer_kernel (layer-2 aggregation + self loop + GRU input gates)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "algorithmic_bytes": int(dom_bytes), "kernel_ms": dom_ms,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                         "note": "x1 shapes are L2-resident and FFMA/latency bound; see roofline_scaled",
+            "roofline": {"bound": "hbm", "kernel": dom_name + " -- " + dom["what"], "achieved": dom["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["achieved"] / peak, "traffic": traffic,
+                         "algorithmic_bytes": dom["algorithmic_bytes"], "kernel_ms": dom["kernel_ms"],
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "note": "dominant kernel = largest share of the step; x1 shapes are L2-resident and latency bound "
+                                 "(8 serial GRU steps), see roofline_scaled for the HBM-resident shapes",
+                         "kernels": kernels,
                          "whole_step": {"algorithmic_bytes": int(step_bytes),
                                         "achieved": step_bytes / (max_dev_ms / K * 1e-3) / 1e9, "unit": "GB/s"}},
             "rows_per_step": int(p0.R), "edges_per_step": int(p0.E),
@@ -394,6 +389,65 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_rooflines(res, model, flush, peak, flush_l2=True, reps=30):
+    """Per-kernel roofline of one forward: every op of the launch program run alone (CUDA events on the launching
+    stream, L2 flushed before each run when ``flush_l2``), its ALGORITHMIC bytes over that time.
+    A layer op is two launches (aggregation + tile kernel); they are separated by also timing the tile kernel with
+    the aggregation launch removed (row_ptr = null reads no aggregate: same tile work minus the agg row loads)."""
+    import torch
+    from temp_b200 import lib
+    D = WORKLOAD["D"]
+    plan = res.plan
+    R, E = plan.R, plan.E
+    nz = int(plan.agg_rows.shape[0] + plan.agg_heavy.shape[0])
+    G = 3 * D
+    rel_rows = int(model.ent_encoder.layer_2.weight.shape[0])
+    ops = [o for o in res.program.ops if o.kind != lib.OP_H2D]
+    layer_ops = [o for o in ops if o.kind == lib.OP_LAYER]
+    scan_ops = [o for o in ops if o.kind in (lib.OP_GRU_SCAN, lib.OP_GRU)]
+
+    def time_ops(op_list):
+        prog = lib.Program()
+        prog.ops = list(op_list)
+        s = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        for i in range(reps):
+            if flush_l2:
+                flush.fill_(1.0)
+            s[i].record()
+            prog.run()
+            e[i].record()
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in zip(s, e)]))
+
+    def no_graph(op):                       # the same tile launch without its aggregation launch
+        o2 = lib.Op()
+        o2.kind = op.kind
+        o2.u.layer = lib.RgcnLayerArgs.from_buffer_copy(op.u.layer)
+        o2.u.layer.row_ptr = None
+        return o2
+
+    out = {}
+    l2 = layer_ops[-1]                      # layer 2: aggregation, then self loop + GRU input gates (tile kernel)
+    t_both, t_tile = time_ops([l2]), time_ops([no_graph(l2)])
+    w_tile = 4 * (D * D + D * G + G)
+    out["rgcn_layer_tc_kernel"] = dict(
+        what="layer-2 self loop + bias/act + chained GRU input gates (tcgen05 3xTF32), all packed rows",
+        kernel_ms=t_tile, algorithmic_bytes=int(R * (4 * D + 4 * G + 8) + nz * 4 * D + w_tile))
+    out["rgcn_gather_kernel"] = dict(
+        what="layer-2 CSR aggregation with in-register 1x1 relation projection (time = layer op - tile kernel alone)",
+        kernel_ms=max(t_both - t_tile, 1e-6), algorithmic_bytes=int(E * (4 * D + 8) + nz * (4 * D + 12 + 4) + rel_rows * 4 * D))
+    if scan_ops:
+        out["gru_scan_tc_kernel"] = dict(
+            what="chain-partitioned GRU scan, all %d steps of the window in one launch" % plan.seq_len,
+            kernel_ms=time_ops(scan_ops), algorithmic_bytes=int(R * (4 * G + 8 * D + 8) + 4 * (D * G + G) + 8 * plan.scan_parts.size))
+    for k in out.values():
+        k["achieved"] = k["algorithmic_bytes"] / (k["kernel_ms"] * 1e-3) / 1e9
+        k["frac"] = k["achieved"] / peak
+        k["unit"] = "GB/s"
+    return out
 
 
 def scaled_roofline(scale, dev, peak):
@@ -424,20 +478,7 @@ def scaled_roofline(scale, dev, peak):
     step_bytes = 2588 * res.plan.R + 16 * res.plan.E + 900000
     out["whole_step"] = {"algorithmic_bytes": int(step_bytes), "achieved": step_bytes / (ms * 1e-3) / 1e9,
                          "frac": step_bytes / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s"}
-    layer_ops = [o for o in prog.ops if o.kind == lib.OP_LAYER]
-    D = WORKLOAD["D"]
-    for name, op, nbytes in (("layer1", layer_ops[0], res.plan.R * (8 * D + 12) + 8 * res.plan.E),
-                             ("layer2_gi", layer_ops[-1], res.plan.R * (16 * D + 12) + 8 * res.plan.E)):
-        one = lib.Program()
-        one.ops = [op]
-        for i in range(reps):
-            s[i].record()
-            one.run()
-            e[i].record()
-        torch.cuda.synchronize()
-        kms = float(np.median([a.elapsed_time(b) for a, b in zip(s, e)]))
-        out[name] = {"kernel_ms": kms, "algorithmic_bytes": int(nbytes), "achieved": nbytes / (kms * 1e-3) / 1e9,
-                     "frac": nbytes / (kms * 1e-3) / 1e9 / peak, "unit": "GB/s"}
+    out["kernels"] = kernel_rooflines(res, model, None, peak, flush_l2=False, reps=10)
     return out
 
 
