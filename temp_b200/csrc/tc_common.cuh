@@ -59,6 +59,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------
+// The kernels of a forward are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel lets its
+// successor start launching at once (pdl_launch_dependents at entry: the successor's CTAs become eligible once every
+// CTA of this grid has started, i.e. they never starve it) and does everything that does not depend on the
+// predecessor's output -- barrier init, TMEM allocation, weight prefetch, plan indices -- before pdl_wait(), which
+// returns when the predecessor grid has completed and its memory is visible.  No global write precedes pdl_wait().
+// Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
+
 #include "internal.h"
 #include "tc_common.cuh"
 
@@ -39,7 +41,6 @@ __device__ __forceinline__ float decay_factor(float dt, const float* wb, float i
   if (wb != nullptr) return expf(-fmaxf(fmaf(__ldg(wb), dt, __ldg(wb + 1)), 0.f));
   return expf(-dt * inv_temperature);
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // Development-only phase timeline (tools/probe_timeline.py builds a separate library with -DTEMP_TIMELINE):
 // lane 0 of every warp stores clock64() per phase slot; slot 63 holds %globaltimer at kernel entry.
@@ -114,14 +115,21 @@ __global__ void pack_gru_kernel(const float* __restrict__ whh_t, uint8_t* __rest
 constexpr int kGatherWarps = 8;
 
 // sum_{e in [e0, e1)} (x[src_e] * W[rel_e]) * nrm for this lane's 4 channels, in edge order
+// (the first chunk's indices are plan data: they are fetched BEFORE pdl_wait(), the feature rows x after it)
 __device__ __forceinline__ float4 gather_edges(const TempRgcnLayerArgs& p, int e0, int e1, float nrm, int lane) {
   const float4* x4 = reinterpret_cast<const float4*>(p.x) + lane;
   const float4* w4 = reinterpret_cast<const float4*>(p.weight) + lane;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s0 = 0, rl0 = 0;
+  if (e0 + lane < e1) {
+    s0 = __ldg(p.e_src + e0 + lane);
+    rl0 = __ldg(p.e_rel + e0 + lane);
+  }
+  pdl_wait();
   for (int base = e0; base < e1; base += 32) {
     const int cnt = min(32, e1 - base);
-    int s = 0, rl = 0;
-    if (lane < cnt) {
+    int s = s0, rl = rl0;
+    if (base != e0 && lane < cnt) {
       s = __ldg(p.e_src + base + lane);
       rl = __ldg(p.e_rel + base + lane);
     }
@@ -152,6 +160,7 @@ __device__ __forceinline__ float4 gather_edges(const TempRgcnLayerArgs& p, int e
 
 __global__ void __launch_bounds__(kGatherWarps * 32, 5) rgcn_gather_kernel(const TempRgcnLayerArgs p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
   if (p.agg_lists != 0 && static_cast<int>(blockIdx.x) < p.n_agg_heavy) {
     // ---- a high in-degree row: the block's 8 warps sum contiguous edge chunks, partials added in chunk order ----
     __shared__ float4 part[kGatherWarps][32];
@@ -226,6 +235,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rbase = p.row0 + blockIdx.x * kTileRows;
   const int n_mb = p.chain_w_packed != nullptr ? p.chain_n >> 7 : 0;
+  pdl_launch_dependents();
   TL_START();
 
   if (tid == 0) {
@@ -325,6 +335,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
       const TempDenseTerm& tm = p.terms[0];
       const int rr = rbase + 16 * warp + (lane & 15);
       const int idx = rr < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + rr) : rr) : -1;
+      pdl_wait();  // everything above (barriers, TMEM, packed-weight prefetch, plan indices) overlapped the predecessor
       float4 v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -481,7 +492,13 @@ struct ScanBars {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// Publishing a step: every thread's state stores are ordered before ONE thread's cluster-scope release fence by a CTA
+// barrier (cumulativity), then all threads arrive relaxed -- one memory barrier per CTA and step instead of one per warp.
+__device__ __forceinline__ void cluster_publish() {
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int group) {  // the 8 (group 0) or 7 (group 1) warps of one worker group
   asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(group == 0 ? 256 : 224) : "memory");
@@ -532,8 +549,9 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   const int cid = blockIdx.x / kScanCluster, n_clusters = gridDim.x / kScanCluster;
   // Gate exchange buffer of a group: gate g, tile row i -> 32 floats at operand row i of k-atom g of the hi image.
   // Those bytes are dead once the group's MMA batch has completed (the other batch reads other rows only).
-  float* ex = reinterpret_cast<float*>(b_hi);
-  constexpr int kExGate = kScanN * 32;  // floats between gates (= one k-atom block)
+  const uint32_t s_bhi = smem_u32(b_hi), s_blo = smem_u32(b_lo);
+  const uint32_t ex = s_bhi;            // shared-space byte address of the exchange buffer
+  constexpr int kExGate = kScanN * 128; // bytes between gates (= one k-atom block)
 
   if (tid == 0) {
     mbar_init(&S.w_full, 1);
@@ -546,6 +564,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = S.tmem_base;
+  pdl_launch_dependents();
   TL_START();
 
   // Row range of (partition, step); lane s of every warp keeps the range of step s of the current partition.
@@ -587,6 +606,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   ScanPre cur;
   if (part < n_parts && worker)
     scan_prefetch(P.steps[s], __shfl_sync(kFull, ranges.x, s), __shfl_sync(kFull, ranges.y, s), row0, stride, lim, lane, cur);
+  pdl_wait();  // gi (and, for a single step, the previous state) come from the predecessor kernels
 
 #pragma unroll 1
   while (part < n_parts) {
@@ -655,8 +675,8 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
         split_tf32(v[u].w * dv, hi.w, lo.w);
         const uint32_t off = static_cast<uint32_t>(lane >> 3) * (kScanN * 128) + (i >> 3) * 1024u + (i & 7) * 128u +
                              (((lane & 7) ^ (i & 7)) << 4);
-        *reinterpret_cast<float4*>(b_hi + off) = hi;
-        *reinterpret_cast<float4*>(b_lo + off) = lo;
+        sts_f32x4(s_bhi + off, hi);
+        sts_f32x4(s_blo + off, lo);
       }
       fence_proxy_async();
     }
@@ -692,7 +712,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
         h0[u] = 0.f;
         if (any_prev && row0 + stride * u < lim) {
           const uint32_t off = static_cast<uint32_t>(cb) * (kScanN * 128) + sw128_off(row0 + stride * u, lane);
-          h0[u] = *reinterpret_cast<const float*>(b_hi + off) + *reinterpret_cast<const float*>(b_lo + off);
+          h0[u] = lds_f32(s_bhi + off) + lds_f32(s_blo + off);
         }
       }
       br = __ldg(p.b_hh + j);
@@ -735,15 +755,15 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
           const int gate = gw & 3, hf = gw >> 2;
           constexpr int kQ = kScanHalf / 2;  // 24
           const uint32_t ta = tbase + (static_cast<uint32_t>(32 * gate) << 16) + grp * kScanHalf + kQ * hf;
-          float* exw = ex + gate * kExGate + (grp * kScanHalf + kQ * hf) * 32 + lane;
+          const uint32_t exw = ex + gate * kExGate + (grp * kScanHalf + kQ * hf) * 128 + lane * 4;
           float v[16], w[8];
           tmem_ld16(ta, v);
           tmem_ld8(ta + 16, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) exw[i * 32] = v[i];
+          for (int i = 0; i < 16; ++i) sts_f32(exw + i * 128, v[i]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) exw[(16 + i) * 32] = w[i];
+          for (int i = 0; i < 8; ++i) sts_f32(exw + (16 + i) * 128, w[i]);
         }
         tc_fence_before();
       }
@@ -764,9 +784,10 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
         if (i < lim && r < r1) {  // warp-uniform
           float hr = br, hz = bz, hn = bn;
           if (any_prev) {
-            hr += ex[0 * kExGate + i * 32 + lane];
-            hz += ex[1 * kExGate + i * 32 + lane];
-            hn += ex[2 * kExGate + i * 32 + lane];
+            const uint32_t ea = ex + i * 128 + lane * 4;
+            hr += lds_f32(ea);
+            hz += lds_f32(ea + kExGate);
+            hn += lds_f32(ea + 2 * kExGate);
           }
           float hy;
           if (type1) {  // GRU_cell.py:22-29
@@ -788,7 +809,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
     TL(7 + 6 * (s & 7));
     // publishes this step's state columns to the cluster (release); the matching wait of the next step also
     // orders the reuse of the operand tile and of the exchange buffer
-    cluster_arrive();
+    cluster_publish();
     arrived = true;
     cur = nxt;
     part = n_part;
@@ -801,6 +822,23 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
   tc_fence_before();
   __syncthreads();
   if (warp == kScanCtlWarp) tmem_dealloc(tbase, 128);
+}
+
+// cudaLaunchKernelEx with programmatic stream serialization (see pdl_wait in tc_common.cuh)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <typename K>
@@ -848,13 +886,11 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   const int rows = a->row1 - a->row0;
   const int gather_grid = tc_gather_grid(a);
   if (gather_grid > 0) {
-    rgcn_gather_kernel<<<gather_grid, kGatherWarps * 32, 0, st>>>(*a);
-    cudaError_t eg = cudaGetLastError();
+    cudaError_t eg = launch_pdl(rgcn_gather_kernel, gather_grid, kGatherWarps * 32, 0, st, *a);
     if (eg != cudaSuccess) return cuda_fail(eg, "rgcn_gather_kernel launch");
   }
   const int grid = (rows + kTileRows - 1) / kTileRows;
-  rgcn_layer_tc_kernel<<<grid, kLayerThreads, kLayerSmem, st>>>(*a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(rgcn_layer_tc_kernel, grid, kLayerThreads, kLayerSmem, st, *a);
   if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_tc_kernel launch");
   return TEMP_OK;
 }
@@ -893,6 +929,11 @@ int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   }
   const int clusters = n_parts < max_clusters ? n_parts : max_clusters;
   cfg.gridDim = dim3(kScanCluster * clusters);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tc_kernel, *a, n_parts);
   if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tc_kernel launch");
   return TEMP_OK;

@@ -55,7 +55,7 @@ class WindowPlan(object):
     """Packed arrays (numpy, int32 / float32) + segment table.  ``to_blob`` concatenates them into
     one byte buffer so that the host->device traffic of a forward is a single copy."""
 
-    ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "e_dst", "prev_a", "dt_a",
+    ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a",
               "prev_b", "dt_b", "slot_row", "scan_parts", "agg_rows", "agg_heavy")
 
     def __init__(self):
@@ -161,8 +161,6 @@ class _Packer(object):
         plan.e_src = cat(self.esrc, np.int32)
         plan.e_src_ent = cat(self.esrc_ent, np.int32)
         plan.e_rel = cat(self.erel, np.int32)
-        # destination packed row per edge (CSR is by destination, so this is non-decreasing)
-        plan.e_dst = np.repeat(np.arange(self.R, dtype=np.int32), np.diff(rp).astype(np.int64)).astype(np.int32)
         # work list of the aggregation kernel: (packed row, first edge, end edge) of every row WITH in-edges
         # (a warp each), split by in-degree: rows above AGG_HEAVY_DEGREE get a whole thread block
         deg = rp[1:] - rp[:-1]
