@@ -131,12 +131,13 @@ class _Packer(object):
     def add(self, snap: Snapshot) -> int:
         row0 = self.R
         n = snap.num_nodes
-        self.ent.append(snap.node_ids.astype(np.int32))
-        self.rtime.append(np.full(n, snap.time, dtype=np.int32))
+        ids32, rtime, deg, esrc_ent, _ = snap.packed_parts()
+        self.ent.append(ids32)
+        self.rtime.append(rtime)
         self.norm.append(snap.norm)
-        self.deg.append(np.diff(snap.row_ptr))
+        self.deg.append(deg)
         self.esrc.append(snap.csr_src + np.int32(row0))
-        self.esrc_ent.append(snap.node_ids[snap.csr_src].astype(np.int32))
+        self.esrc_ent.append(esrc_ent)
         self.erel.append(snap.csr_rel)
         self.R += n
         self.E += snap.num_edges
@@ -300,19 +301,24 @@ def chain_partitions(plan: WindowPlan, tile: int = SCAN_TILE) -> np.ndarray:
     big = np.iinfo(np.int64).max
     for item in sorted(per_item):
         insts = per_item[item]
-        ids = [inst.snapshot.node_ids for _, inst in insts]
-        pos = [0] * len(insts)
-        while any(pos[k] < ids[k].shape[0] for k in range(len(insts))):
-            cut = big
-            for k in range(len(insts)):
-                if pos[k] + tile < ids[k].shape[0]:
-                    cut = min(cut, int(ids[k][pos[k] + tile]))
+        K = len(insts)
+        sizes = np.array([inst.n for _, inst in insts], dtype=np.int64)
+        segs = np.array([g for g, _ in insts], dtype=np.int64)
+        row0 = np.array([inst.row0 for _, inst in insts], dtype=np.int64)
+        ids = np.full((K, int(sizes.max()) + 1), big, dtype=np.int64)        # entity ids per instance, padded with +inf
+        for k, (_, inst) in enumerate(insts):
+            ids[k, :inst.n] = inst.snapshot.node_ids
+        pos = np.zeros(K, dtype=np.int64)
+        rows_k = np.arange(K)
+        while (pos < sizes).any():
+            # the first entity id that would make some instance exceed `tile` rows; everything below it joins the partition
+            cut = ids[rows_k, np.minimum(pos + tile, sizes)].min()
+            new = sizes if cut == big else (ids < cut).sum(axis=1)
             row = np.zeros((n_seg, 2), dtype=np.int32)
-            for k, (g, inst) in enumerate(insts):
-                new = ids[k].shape[0] if cut == big else int(np.searchsorted(ids[k], cut, side="left"))
-                row[g] = (inst.row0 + pos[k], inst.row0 + new)
-                pos[k] = new
+            row[segs, 0] = row0 + pos
+            row[segs, 1] = row0 + new
             parts.append(row)
+            pos = new
     if not parts:
         return np.zeros((0, n_seg, 2), dtype=np.int32)
     out = np.stack(parts)

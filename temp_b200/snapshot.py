@@ -23,7 +23,7 @@ __all__ = ["Snapshot", "SnapshotStore", "SHAPES"]
 
 class Snapshot(object):
     __slots__ = ("time", "node_ids", "src", "dst", "rel", "norm", "row_ptr", "csr_src", "csr_rel", "_ids",
-                 "_torch")
+                 "_torch", "_packed")
 
     def __init__(self, time: int, node_ids: np.ndarray, src: np.ndarray, dst: np.ndarray, rel: np.ndarray):
         n = int(node_ids.shape[0])
@@ -44,6 +44,15 @@ class Snapshot(object):
         self.csr_rel = self.rel[order].astype(np.int32)
         self._ids = None
         self._torch = None
+        self._packed = None
+
+    def packed_parts(self):
+        """Per-snapshot arrays the window planner concatenates (cached: a snapshot appears in many windows)."""
+        if self._packed is None:
+            ids32 = self.node_ids.astype(np.int32)
+            self._packed = (ids32, np.full(self.num_nodes, self.time, dtype=np.int32), np.diff(self.row_ptr),
+                            ids32[self.csr_src], np.full(self.num_nodes, -1, dtype=np.int32))
+        return self._packed
 
     # ---- sizes ------------------------------------------------------------------------------
     @property
