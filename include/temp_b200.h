@@ -196,6 +196,28 @@ typedef struct {
   float* dst;
 } TempScatterArgs;
 
+#define TEMP_SCORE_DISTMULT 0   /* utils/scores.py:4-11   */
+#define TEMP_SCORE_COMPLEX 1    /* utils/scores.py:27-44  */
+#define TEMP_SCORE_TRANSE 2     /* utils/scores.py:46-55  */
+
+/* Training-time link prediction of one target graph, fused:
+ *   loss[p] = logsumexp_c score(p, c) - score(p, 0)     for the positive triples p = 0..n_pos-1
+ * where candidate c of triple p is row cand[p * n_cand + c] of the all-entity table (column 0 = the true entity,
+ * models/TKG_Module.py:202-213 with the all-zero labels of utils/CorrptTriples.py:40); corrupt_tail: the candidates
+ * replace the object (score mode 'tail'), else the subject (mode 'head').  The mean over p is F.cross_entropy.
+ * Replaces the [n_pos, n_cand, d] gather all_embeds_g[neg_samples], calc_score and F.cross_entropy -- the gather is
+ * never materialised (770 MB per direction at 3000 positives x 501 candidates).  d % 32 == 0.               */
+typedef struct {
+  int32_t n_pos, n_cand, d;
+  int32_t score_fn, corrupt_tail;
+  const float* ent_embed;    /* [n_nodes, d] states of the target graph's nodes (local ids)                  */
+  const float* rel_embeds;   /* [2 * num_rels, d]                                                            */
+  const float* table;        /* [num_ents, d] all-entity table of the graph (get_all_embeds_Gt)              */
+  const int64_t* triples;    /* [n_pos, 3] (subject, relation, object), local node ids                       */
+  const int64_t* cand;       /* [n_pos, n_cand] global entity ids                                            */
+  float* loss;               /* [n_pos]                                                                      */
+} TempScoreLossArgs;
+
 enum { TEMP_OP_LAYER = 1, TEMP_OP_GRU = 2, TEMP_OP_ATTN = 3, TEMP_OP_GATHER = 4, TEMP_OP_SCATTER = 5,
        TEMP_OP_MEMCPY_H2D = 6, TEMP_OP_MEMCPY_D2H = 7, TEMP_OP_GRU_SCAN = 8 };
 
@@ -232,6 +254,7 @@ int temp_attention_fwd(const TempAttnArgs* args, void* stream);
 int temp_gather_rows(const TempGatherArgs* args, void* stream);
 int temp_scatter_rows(const TempScatterArgs* args, void* stream);
 /* out[c, r] = in[r, c]  (weight preparation: weight_ih / weight_hh / q,k,v -> K-major-first)     */
+int temp_score_loss_fwd(const TempScoreLossArgs* args, void* stream);
 int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream);
 /* Tensor-core operand images (d == 128).  A [k, n] row-major fp32 matrix (k == 128, n % 128 == 0) is split
  * into tf32 hi / lo parts and stored, per 128 output features x 32 k, in the K-major SWIZZLE_128B

@@ -671,6 +671,94 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const TempAttnArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused training-time scorer: candidate gather + ComplEx / DistMult / TransE + cross-entropy (label 0)
+// ------------------------------------------------------------------------------------------------
+// One warp per positive triple; 8 lanes per candidate (a lane owns d/8 consecutive channels of the query and of the
+// gathered candidate row: 4 candidates per warp iteration, each row read once as 8 x (d/8 x 4) contiguous bytes),
+// 3 shuffles reduce a candidate's score, an online logsumexp runs per 8-lane group and the 4 groups are merged at the
+// end.  Every score is linear in the candidate (or an L1 distance to a query), so the triple's query vector is formed
+// once:  ComplEx tail  q = [re_s re_r - im_s im_r ; re_s im_r + im_s re_r],  head  q = [re_r re_o + im_r im_o ;
+// re_r im_o - im_r re_o];  DistMult  q = s r | r o;  TransE  score = -|cand - q|_1 with q = o - r (head) and
+// score = -|q - cand|_1 with q = s + r (tail).
+constexpr int kScoreMaxPerLane = 32;  // d / 8 <= 32, i.e. d <= 256
+
+__global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLossArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (pos >= p.n_pos) return;
+  const int D = p.d, per = D >> 3, half = D >> 1;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int c0 = sub * per;                      // this lane's first channel
+  const long long s_id = p.triples[3 * pos], r_id = p.triples[3 * pos + 1], o_id = p.triples[3 * pos + 2];
+  const float* fixed = p.ent_embed + static_cast<size_t>(p.corrupt_tail ? s_id : o_id) * D;
+  const float* rel = p.rel_embeds + static_cast<size_t>(r_id) * D;
+  float q[kScoreMaxPerLane];
+#pragma unroll
+  for (int t = 0; t < kScoreMaxPerLane; ++t) {
+    q[t] = 0.f;
+    if (t < per) {
+      const int c = c0 + t;
+      if (p.score_fn == TEMP_SCORE_COMPLEX) {
+        const bool im = c >= half;               // the second half of the channels is the imaginary part
+        const int k = im ? c - half : c;
+        const float re_e = __ldg(fixed + k), im_e = __ldg(fixed + half + k);
+        const float re_r = __ldg(rel + k), im_r = __ldg(rel + half + k);
+        if (p.corrupt_tail) q[t] = im ? re_e * im_r + im_e * re_r : re_e * re_r - im_e * im_r;
+        else q[t] = im ? re_r * im_e - im_r * re_e : re_r * re_e + im_r * im_e;
+      } else if (p.score_fn == TEMP_SCORE_DISTMULT) {
+        q[t] = __ldg(fixed + c) * __ldg(rel + c);
+      } else {
+        q[t] = p.corrupt_tail ? __ldg(fixed + c) + __ldg(rel + c) : __ldg(fixed + c) - __ldg(rel + c);
+      }
+    }
+  }
+  const bool l1 = p.score_fn == TEMP_SCORE_TRANSE;
+  float mx = -INFINITY, den = 0.f, first = 0.f;
+  const int64_t* cand = p.cand + static_cast<size_t>(pos) * p.n_cand;
+  for (int base = 0; base < p.n_cand; base += 4) {
+    const int c = base + grp;
+    float part = 0.f;
+    if (c < p.n_cand) {
+      const float4* row = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(cand[c]) * D + c0);
+#pragma unroll
+      for (int t4 = 0; t4 < kScoreMaxPerLane / 4; ++t4) {
+        if (4 * t4 < per) {
+          const float4 v = __ldg(row + t4);
+          if (l1) {  // head: |cand + r - o| = |cand - q| ; tail: |s + r - cand| = |q - cand|
+            part += fabsf(v.x - q[4 * t4]) + fabsf(v.y - q[4 * t4 + 1]) + fabsf(v.z - q[4 * t4 + 2]) + fabsf(v.w - q[4 * t4 + 3]);
+          } else {
+            part = fmaf(v.x, q[4 * t4], part);
+            part = fmaf(v.y, q[4 * t4 + 1], part);
+            part = fmaf(v.z, q[4 * t4 + 2], part);
+            part = fmaf(v.w, q[4 * t4 + 3], part);
+          }
+        }
+      }
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    if (c < p.n_cand) {
+      const float sc = l1 ? -part : part;
+      if (c == 0) first = sc;
+      const float mnew = fmaxf(mx, sc);
+      den = den * expf(mx - mnew) + expf(sc - mnew);
+      mx = mnew;
+    }
+  }
+  // merge the 4 groups' (max, sum) pairs; candidate 0 lives in group 0
+#pragma unroll
+  for (int off = 16; off >= 8; off >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, off), oden = __shfl_xor_sync(0xffffffffu, den, off);
+    const float mnew = fmaxf(mx, omx);
+    den = (mx == -INFINITY ? 0.f : den * expf(mx - mnew)) + (omx == -INFINITY ? 0.f : oden * expf(omx - mnew));
+    mx = mnew;
+  }
+  first = __shfl_sync(0xffffffffu, first, 0);
+  if (lane == 0) p.loss[pos] = (mx + logf(den)) - first;
+}
+
+// ------------------------------------------------------------------------------------------------
 // small data-movement kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const TempGatherArgs p) {
@@ -894,6 +982,20 @@ int launch_attn(const TempAttnArgs* a, cudaStream_t st) {
   return TEMP_OK;
 }
 
+int launch_score_loss(const TempScoreLossArgs* a, cudaStream_t st) {
+  if (a == nullptr || a->n_pos < 0 || a->n_cand <= 0) return fail(TEMP_EINVAL, "bad score args%s", "");
+  if (a->n_pos == 0) return TEMP_OK;
+  if (a->d <= 0 || (a->d & 31) || a->d / 8 > kScoreMaxPerLane) return fail(TEMP_EUNSUPPORTED, "score: d must be a multiple of 32 up to %s%ld", "", 8L * kScoreMaxPerLane);
+  if (a->score_fn < TEMP_SCORE_DISTMULT || a->score_fn > TEMP_SCORE_TRANSE) return fail(TEMP_EINVAL, "bad score_fn%s", "");
+  if (!a->ent_embed || !a->rel_embeds || !a->table || !a->triples || !a->cand || !a->loss) return fail(TEMP_EINVAL, "score has null pointers%s", "");
+  if (!aligned16(a->table)) return fail(TEMP_EINVAL, "score table misaligned%s", "");
+  const int per_cta = kThreads / 32;
+  score_loss_kernel<<<(a->n_pos + per_cta - 1) / per_cta, kThreads, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "score_loss_kernel launch");
+  return TEMP_OK;
+}
+
 int grid_for(size_t work_items) {
   size_t g = (work_items + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -968,6 +1070,10 @@ int temp_gather_rows(const TempGatherArgs* args, void* stream) {
 
 int temp_scatter_rows(const TempScatterArgs* args, void* stream) {
   return launch_scatter(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_score_loss_fwd(const TempScoreLossArgs* args, void* stream) {
+  return launch_score_loss(args, static_cast<cudaStream_t>(stream));
 }
 
 int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream) {

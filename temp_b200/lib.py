@@ -75,6 +75,14 @@ class ScatterArgs(C.Structure):
                 ("dst", _p)]
 
 
+class ScoreLossArgs(C.Structure):
+    _fields_ = [("n_pos", _i32), ("n_cand", _i32), ("d", _i32), ("score_fn", _i32), ("corrupt_tail", _i32),
+                ("ent_embed", _p), ("rel_embeds", _p), ("table", _p), ("triples", _p), ("cand", _p), ("loss", _p)]
+
+
+SCORE_FN = {"distmult": 0, "complex": 1, "transE": 2}
+
+
 class CopyArgs(C.Structure):
     _fields_ = [("dst", _p), ("src", _p), ("bytes", C.c_uint64)]
 
@@ -91,7 +99,7 @@ class Op(C.Structure):
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
-           "temp_program_kernel_count")
+           "temp_program_kernel_count", "temp_score_loss_fwd")
 
 _lib = None
 
@@ -121,6 +129,7 @@ def load(path: Optional[str] = None):
     lib.temp_transpose.argtypes = [_p, _i32, _i32, _p, _i32, _p]
     lib.temp_run_program.argtypes = [C.POINTER(Op), _i32, _p]
     lib.temp_program_kernel_count.argtypes = [C.POINTER(Op), _i32]
+    lib.temp_score_loss_fwd.argtypes = [C.POINTER(ScoreLossArgs), _p]
     lib.temp_packed_weights_bytes.argtypes = [_i32, _i32]
     lib.temp_packed_weights_bytes.restype = C.c_int64
     lib.temp_pack_weights.argtypes = [_p, _i32, _i32, _p, _p]

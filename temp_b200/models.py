@@ -166,7 +166,12 @@ class TKG_Module(nn.Module):
         return [list(x) for x in zip(*g_list)], [list(x) for x in zip(*time_list)]
 
     def train_link_prediction(self, ent_embed, triplets, neg_samples, labels, all_embeds_g, corrupt_tail=True):
-        """models/TKG_Module.py:202-213."""
+        """models/TKG_Module.py:202-213.  On CUDA (d % 32 == 0) the gather + score + cross-entropy run fused in one
+        kernel (``scores.fused_link_prediction_loss``; the labels of the reference's sampler are all zero)."""
+        if all_embeds_g.is_cuda and self.embed_size % 32 == 0 and not torch.is_grad_enabled():
+            from .scores import fused_link_prediction_loss
+            return fused_link_prediction_loss(ent_embed, self.rel_embeds, triplets, neg_samples, all_embeds_g,
+                                              getattr(self.args, "score_function", "complex"), corrupt_tail)
         r = self.rel_embeds[triplets[:, 1]]
         if corrupt_tail:
             s = ent_embed[triplets[:, 0]]

@@ -1,6 +1,28 @@
-"""Decoders of the reference (utils/scores.py:4-55).  Scoring is a "next" row of the scope table
-(SURVEY.md section 8f rank 2): it stays in torch for now and is not part of the timed encoder region."""
+"""Decoders of the reference (utils/scores.py:4-55) in torch (used by evaluation / link classification) and the fused
+training-time scorer on the CUDA path: candidate gather + score + cross-entropy in one
+kernel behind ``temp_score_loss_fwd`` -- the [P, 1 + negatives, D] gather of models/TKG_Module.py:202-213 is never
+materialised."""
+import ctypes as C
+
 import torch
+
+
+def fused_link_prediction_loss(ent_embed, rel_embeds, triplets, cand, table, score_function="complex", corrupt_tail=True):
+    """mean_p [ logsumexp_c score(p, c) - score(p, 0) ]  ==  F.cross_entropy(calc_score(...), zeros)  of
+    TKG_Module.train_link_prediction.  ``triplets`` [P, 3] and ``cand`` [P, 1 + neg] are int64 CUDA tensors."""
+    from . import lib
+    P, n_cand = int(cand.shape[0]), int(cand.shape[1])
+    D = int(table.shape[1])
+    if P == 0:
+        return table.new_zeros(())
+    ent_embed, rel_embeds, table = ent_embed.contiguous(), rel_embeds.detach().contiguous(), table.contiguous()
+    triplets, cand = triplets.contiguous(), cand.contiguous()
+    assert triplets.dtype == torch.int64 and cand.dtype == torch.int64 and table.is_cuda
+    loss = torch.empty(P, dtype=torch.float32, device=table.device)
+    a = lib.ScoreLossArgs(P, n_cand, D, lib.SCORE_FN[score_function], int(bool(corrupt_tail)), ent_embed.data_ptr(),
+                          rel_embeds.data_ptr(), table.data_ptr(), triplets.data_ptr(), cand.data_ptr(), loss.data_ptr())
+    lib.check(lib.load().temp_score_loss_fwd(C.byref(a), C.c_void_p(lib.current_stream())), "temp_score_loss_fwd")
+    return loss.mean()
 
 
 def distmult(s, r, o, mode="single"):

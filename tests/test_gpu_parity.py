@@ -143,3 +143,31 @@ def test_training_forward_loss_matches_reference(tc):
     torch.manual_seed(tc["seed"])
     loss = float(model.forward(torch.tensor(case["t_list"])))
     assert abs(loss - float(gold["loss"])) <= RTOL * abs(float(gold["loss"]))
+
+
+@pytest.mark.parametrize("score_fn", ["complex", "distmult", "transE"])
+@pytest.mark.parametrize("corrupt_tail", [True, False])
+@pytest.mark.parametrize("shape", [(37, 11, 128, 300), (1, 501, 128, 7128), (513, 64, 64, 50)])
+def test_fused_scorer_matches_torch_reference_path(score_fn, corrupt_tail, shape):
+    """temp_score_loss_fwd (gather + score + cross-entropy fused) against the reference's formulation
+    (TKG_Module.train_link_prediction: materialised gather, utils/scores.py, F.cross_entropy) in torch fp32."""
+    import torch.nn.functional as F
+    from temp_b200 import scores
+    P, n_cand, D, M = shape
+    g = torch.Generator().manual_seed(1234 + P)
+    n_nodes, n_rel = 97, 23
+    ent = torch.randn(n_nodes, D, generator=g).cuda()
+    rel = torch.randn(2 * n_rel, D, generator=g).cuda()
+    table = torch.randn(M, D, generator=g).cuda()
+    tri = torch.stack([torch.randint(0, n_nodes, (P,), generator=g), torch.randint(0, 2 * n_rel, (P,), generator=g),
+                       torch.randint(0, n_nodes, (P,), generator=g)], dim=1).cuda()
+    cand = torch.randint(0, M, (P, n_cand), generator=g).cuda()
+    got = scores.fused_link_prediction_loss(ent, rel, tri, cand, table, score_fn, corrupt_tail)
+    fn = {"complex": scores.complex_score, "distmult": scores.distmult, "transE": scores.transE}[score_fn]
+    r = rel[tri[:, 1]]
+    if corrupt_tail:
+        sc = fn(ent[tri[:, 0]], r, table[cand], mode="tail")
+    else:
+        sc = fn(table[cand], r, ent[tri[:, 2]], mode="head")
+    want = F.cross_entropy(sc.double(), torch.zeros(P, dtype=torch.long, device="cuda"))
+    assert abs(float(got) - float(want)) <= 1e-5 * max(abs(float(want)), 1.0)
