@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -355,6 +356,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         max_dev_ms, max_e2e = float(t[0].item()), float(t[1].item())
 
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        try:
+            sharded = snapshot_sharded_arm(dev, world)
+        except Exception as ex:          # never lose the headline line
+            sharded = {"error": repr(ex)}
+
     if rank == 0:
         line = {
             "metric": "edges_per_sec_rgcn_gru_forward", "value": tot_edges / (max_dev_ms * 1e-3), "unit": "edges/s",
@@ -378,6 +386,8 @@ def main():
             "rows_per_step": int(p0.R), "edges_per_step": int(p0.E),
             "wall_s_device_arm": wall_dev,
         }
+        if sharded is not None:
+            line["snapshot_sharded"] = sharded
         if args.scaled and world == 1:
             try:
                 line["roofline_scaled"] = scaled_roofline(args.scaled, dev, peak)
@@ -389,6 +399,53 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def snapshot_sharded_arm(dev, world):
+    """N > 1, secondary: ONE GDELT-shaped batch (BASELINE config 5: GRRGCN, seq_len 15, B = 2) cut over the ranks by
+    snapshot instance / chain partition (temp_b200/sharding.py) against the same batch on one GPU; device time, max
+    over ranks.  Every rank calls this."""
+    import torch
+    import torch.distributed as dist
+    from temp_b200.models import build_module
+    from temp_b200.snapshot import SnapshotStore
+    store = SnapshotStore.synthetic("gdelt", num_times=24, scale=1, seed=20201116 + 4)
+    a = make_args()
+    a.train_seq_len = a.test_seq_len = 15
+    torch.manual_seed(123)
+    model = build_module(a, store.num_ents, store.num_rels, store.train).to(dev).eval()
+    t_list = [store.times[20], store.times[21]]
+    single = model.encode(t_list)
+    want = single.out.clone()
+    res = model.encode_sharded(t_list)
+    torch.cuda.synchronize()
+    same = torch.tensor([int(torch.equal(res.out, want))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+
+    def timed(fn, reps=30):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    single = model.encode(t_list)
+    ms_one = timed(lambda: single.program.run())
+    ms_sh = timed(lambda: model.encode_sharded(prepared=res))
+    return {"workload": "GRRGCN rec-only-last-layer, GDELT-shaped synthetic x1, seq_len=15, B=2 (BASELINE config 5)",
+            "bit_identical_to_unsharded": bool(int(same.item())), "rows": int(res.plan.R), "edges": int(res.plan.E),
+            "ms_unsharded_one_gpu": ms_one, "ms_snapshot_sharded": ms_sh,
+            "edges_per_s_sharded": res.plan.E / (ms_sh * 1e-3),
+            "note": "exchange 1 (gi blocks, one broadcast per rank) + exchange 2 (NCCL all-gather of the final states) "
+                    "are NCCL calls between launches; at this size the exchanges cost more than the sharded compute saves"}
 
 
 def kernel_rooflines(res, model, flush, peak, flush_l2=True, reps=30):
