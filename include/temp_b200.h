@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 6
+#define TEMP_ABI_VERSION 7
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -241,6 +241,40 @@ typedef struct {
     TempCopyArgs copy;
   } u;
 } TempOp;
+
+/* ---- native window planner (temp_b200/csrc/planner.cpp) ------------------------------------------------------------
+ * Host side: packs a batch of windows into the arrays above.  Replaces the per-step dgl.batch / history dictionary
+ * work of models/DynamicRGCN.py:35-110, models/BiDynamicRGCN.py:17-100, models/TKG_Module.py:232-250.               */
+typedef struct {
+  int32_t time, n_nodes, n_edges;
+  const int32_t* node_ids;   /* [n_nodes] global entity ids, ascending (utils/dataset.py:168)                     */
+  const int32_t* row_ptr;    /* [n_nodes + 1] CSR by destination                                                  */
+  const int32_t* csr_src;    /* [n_edges] local source node, edges of a destination in edge-id order               */
+  const int32_t* csr_rel;    /* [n_edges]                                                                         */
+  const float* norm;         /* [n_nodes] 1 / in_degree, 0 for in_degree 0 (utils/utils.py:74-79)                 */
+} TempSnapshotView;
+
+typedef struct {
+  int32_t rows, edges, n_segments, n_instances, n_parts, n_agg_rows, n_agg_heavy, n_slots, batch, seq_len;
+} TempPlanCounts;
+
+enum { TEMP_PLAN_ENT_ID = 0, TEMP_PLAN_ROW_TIME, TEMP_PLAN_NORM, TEMP_PLAN_ROW_PTR, TEMP_PLAN_E_SRC, TEMP_PLAN_E_SRC_ENT,
+       TEMP_PLAN_E_REL, TEMP_PLAN_PREV_A, TEMP_PLAN_DT_A, TEMP_PLAN_PREV_B, TEMP_PLAN_DT_B, TEMP_PLAN_SLOT_ROW,
+       TEMP_PLAN_SCAN_PARTS, TEMP_PLAN_AGG_ROWS, TEMP_PLAN_AGG_HEAVY,
+       TEMP_PLAN_INSTANCES /* int32 [n_instances][7] = item, step, dir (0 f, 1 b, 2 centre), time, row0, n, snapshot */,
+       TEMP_PLAN_SEGMENTS  /* int32 [n_segments][6] = kind (0 hist_f, 1 hist_b, 2 final), step, row0, row1, inst0, inst1 */,
+       TEMP_PLAN_LAST_F, TEMP_PLAN_LAST_B /* int32 [batch] instance of the last history step per item, -1 */,
+       TEMP_PLAN_STEPS_F, TEMP_PLAN_STEPS_B /* int32 [seq_len - 1][batch] instance per (step, window row), -1 */ };
+
+typedef struct TempPlan TempPlan;
+/* snaps: every snapshot of the split in graph_dict order (ascending time); targets: snapshot index of each target
+ * timestamp (any order).  Returns null on bad arguments.  The plan owns host memory until temp_plan_destroy.      */
+TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const int32_t* targets, int32_t batch,
+                           int32_t seq_len, int32_t bidirectional, int32_t attention, int32_t scan_tile,
+                           int32_t heavy_degree);
+void temp_plan_destroy(TempPlan* plan);
+int temp_plan_counts(const TempPlan* plan, TempPlanCounts* out);
+const void* temp_plan_array(const TempPlan* plan, int32_t which, int64_t* n_bytes);
 
 int temp_abi_version(void);
 const char* temp_last_error_string(void);

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -83,6 +83,21 @@ class ScoreLossArgs(C.Structure):
 SCORE_FN = {"distmult": 0, "complex": 1, "transE": 2}
 
 
+class SnapshotView(C.Structure):
+    _fields_ = [("time", _i32), ("n_nodes", _i32), ("n_edges", _i32), ("node_ids", _p), ("row_ptr", _p), ("csr_src", _p),
+                ("csr_rel", _p), ("norm", _p)]
+
+
+class PlanCounts(C.Structure):
+    _fields_ = [(n, _i32) for n in ("rows", "edges", "n_segments", "n_instances", "n_parts", "n_agg_rows", "n_agg_heavy",
+                                    "n_slots", "batch", "seq_len")]
+
+
+PLAN_ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a", "prev_b", "dt_b",
+               "slot_row", "scan_parts", "agg_rows", "agg_heavy", "instances", "segments", "last_f", "last_b", "steps_f",
+               "steps_b")
+
+
 class CopyArgs(C.Structure):
     _fields_ = [("dst", _p), ("src", _p), ("bytes", C.c_uint64)]
 
@@ -99,7 +114,8 @@ class Op(C.Structure):
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
-           "temp_program_kernel_count", "temp_score_loss_fwd")
+           "temp_program_kernel_count", "temp_score_loss_fwd", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
+           "temp_plan_array")
 
 _lib = None
 
@@ -130,6 +146,13 @@ def load(path: Optional[str] = None):
     lib.temp_run_program.argtypes = [C.POINTER(Op), _i32, _p]
     lib.temp_program_kernel_count.argtypes = [C.POINTER(Op), _i32]
     lib.temp_score_loss_fwd.argtypes = [C.POINTER(ScoreLossArgs), _p]
+    lib.temp_plan_window.argtypes = [C.POINTER(SnapshotView), _i32, C.POINTER(_i32), _i32, _i32, _i32, _i32, _i32, _i32]
+    lib.temp_plan_window.restype = _p
+    lib.temp_plan_destroy.argtypes = [_p]
+    lib.temp_plan_destroy.restype = None
+    lib.temp_plan_counts.argtypes = [_p, C.POINTER(PlanCounts)]
+    lib.temp_plan_array.argtypes = [_p, _i32, C.POINTER(C.c_int64)]
+    lib.temp_plan_array.restype = _p
     lib.temp_packed_weights_bytes.argtypes = [_i32, _i32]
     lib.temp_packed_weights_bytes.restype = C.c_int64
     lib.temp_pack_weights.argtypes = [_p, _i32, _i32, _p, _p]

@@ -95,8 +95,15 @@ class TKG_Module(nn.Module):
         return self._corrupter
 
     def plan(self, t_list, seq_len: Optional[int] = None, transform=None) -> WindowPlan:
-        return plan_window(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len,
-                           bidirectional=self.bidirectional, attention=self.family == "attention", transform=transform)
+        """Packs the window batch: the native planner of libtemp_b200.so, or its python statement when the graphs are
+        transformed on the fly (training-mode edge sub-sampling)."""
+        from .planner import plan_window_native
+        kw = dict(bidirectional=self.bidirectional, attention=self.family == "attention")
+        if transform is None and self.use_native_planner:
+            return plan_window_native(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len, **kw)
+        return plan_window(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len, transform=transform, **kw)
+
+    use_native_planner = True
 
     def train_edge_sampler(self):
         """Training-mode edge sub-sampling of the window (models/DynamicRGCN.py:76-94, 161-171): the final step keeps

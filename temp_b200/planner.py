@@ -326,6 +326,103 @@ def chain_partitions(plan: WindowPlan, tile: int = SCAN_TILE) -> np.ndarray:
     return np.ascontiguousarray(out[order])
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# native planner (temp_b200/csrc/planner.cpp): same algorithm, same arrays, ~20x faster than the numpy statement above
+# ---------------------------------------------------------------------------------------------------------------------
+_VIEW_CACHE: Dict[int, tuple] = {}
+
+
+def _snapshot_views(graph_dict: Dict[int, Snapshot]):
+    """ctypes table of TempSnapshotView for every snapshot of ``graph_dict`` (cached per dict object)."""
+    import ctypes as C
+    from . import lib
+    key = id(graph_dict)
+    hit = _VIEW_CACHE.get(key)
+    if hit is not None and hit[0] is graph_dict and hit[1] == len(graph_dict):
+        return hit[2], hit[3]
+    times = list(graph_dict.keys())
+    views = (lib.SnapshotView * len(times))()
+    keep = []
+    for i, t in enumerate(times):
+        s = graph_dict[t]
+        ids32 = s.packed_parts()[0]
+        keep.append(ids32)
+        v = views[i]
+        v.time, v.n_nodes, v.n_edges = int(s.time), s.num_nodes, s.num_edges
+        v.node_ids, v.row_ptr = ids32.ctypes.data, s.row_ptr.ctypes.data
+        v.csr_src, v.csr_rel, v.norm = s.csr_src.ctypes.data, s.csr_rel.ctypes.data, s.norm.ctypes.data
+    index = {t: i for i, t in enumerate(times)}
+    _VIEW_CACHE[key] = (graph_dict, len(times), (views, keep, times), index)
+    return (views, keep, times), index
+
+
+_PLAN_DTYPES = {"norm": np.float32, "dt_a": np.float32, "dt_b": np.float32}
+_KINDS = ("hist_f", "hist_b", "final")
+_DIRS = ("f", "b", "c")
+
+
+def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len: int, bidirectional: bool = False,
+                       attention: bool = False) -> WindowPlan:
+    """``plan_window`` through the native planner of libtemp_b200.so (no ``transform``: the training-mode edge
+    sub-sampling builds new snapshots and goes through the python planner)."""
+    import ctypes as C
+    from . import lib
+    L = lib.load()
+    (views, _keep, times), index = _snapshot_views(graph_dict)
+    B = len(t_list)
+    targets = (C.c_int32 * B)(*[index[int(t)] for t in t_list])
+    handle = L.temp_plan_window(views, len(times), targets, B, int(seq_len), int(bidirectional), int(attention), SCAN_TILE,
+                                AGG_HEAVY_DEGREE)
+    if not handle:
+        raise RuntimeError("temp_b200: temp_plan_window rejected its arguments")
+    try:
+        cnt = lib.PlanCounts()
+        lib.check(L.temp_plan_counts(handle, C.byref(cnt)), "temp_plan_counts")
+        arr = {}
+        nb = C.c_int64()
+        for which, name in enumerate(lib.PLAN_ARRAYS):
+            ptr = L.temp_plan_array(handle, which, C.byref(nb))
+            dt = _PLAN_DTYPES.get(name, np.int32)
+            n = nb.value // 4
+            arr[name] = (np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int32 if dt == np.int32 else C.c_float)), shape=(n,)).copy()
+                         if n else np.zeros(0, dtype=dt))
+    finally:
+        L.temp_plan_destroy(handle)
+    plan = WindowPlan()
+    plan.seq_len, plan.batch, plan.bidirectional = int(seq_len), B, bool(bidirectional)
+    plan.R, plan.E = int(cnt.rows), int(cnt.edges)
+    for name in ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a"):
+        setattr(plan, name, arr[name])
+    if bidirectional:
+        plan.prev_b, plan.dt_b = arr["prev_b"], arr["dt_b"]
+    insts_raw = arr["instances"].reshape(-1, 7)
+    insts = [Instance(int(r[0]), int(r[1]), _DIRS[int(r[2])], int(r[3]), int(r[4]), int(r[5]), graph_dict[times[int(r[6])]])
+             for r in insts_raw]
+    for r in arr["segments"].reshape(-1, 6):
+        plan.segments.append(Segment(_KINDS[int(r[0])], int(r[1]), int(r[2]), int(r[3]), insts[int(r[4]):int(r[5])]))
+    for inst in plan.segments[-1].instances:
+        plan.final_times.append(inst.time)
+        plan.final_sizes.append(inst.n)
+        plan.final_snapshots.append(inst.snapshot)
+    pick = lambda a: [insts[i] if i >= 0 else None for i in a.tolist()]
+    plan.last_hist_f = pick(arr["last_f"])
+    plan.last_hist_b = pick(arr["last_b"]) if bidirectional else [None] * B
+    for name in ("agg_rows", "agg_heavy"):
+        setattr(plan, name, arr[name].reshape(-1, 3))
+        setattr(plan, name + "_ids", arr[name].reshape(-1, 3)[:, 0].astype(np.int64))
+    if attention:
+        plan.n_slots = int(cnt.n_slots)
+        nf = plan.final.row1 - plan.final.row0
+        plan.slot_row = arr["slot_row"].reshape(nf, plan.n_slots)
+        to_dicts = lambda a: [{j: insts[i] for j, i in enumerate(row) if i >= 0} for row in a.reshape(-1, B).tolist()] \
+            if a.size else [dict() for _ in range(max(int(seq_len) - 1, 0))]
+        plan.steps_f = to_dicts(arr["steps_f"])
+        plan.steps_b = to_dicts(arr["steps_b"]) if bidirectional else []
+    else:
+        plan.scan_parts = arr["scan_parts"].reshape(int(cnt.n_parts), len(plan.segments), 2)
+    return plan
+
+
 def plan_static(graph_dict: Dict[int, Snapshot], t_list: Sequence[int]) -> WindowPlan:
     """StaticRGCN (baselines/StaticRGCN.py:23-28): one snapshot per target, t_list order kept."""
     plan = WindowPlan()

@@ -147,7 +147,7 @@ def test_synthetic_generator_shape_statistics():
 # ---- ABI surface -------------------------------------------------------------------------------
 def _header_functions():
     text = open(os.path.join(ROOT, "include", "temp_b200.h")).read()
-    return sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(temp_\w+)\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|int64_t|const char\*|TempPlan\*|void|const void\*)\s+(temp_\w+)\(", text, flags=re.M)))
 
 
 def test_library_builds_loads_and_exports_every_declared_symbol():
@@ -167,15 +167,19 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     from temp_b200 import lib
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "temp_b200.h"\nint main(){'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(TempDenseTerm), sizeof(TempRgcnLayerArgs),'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(TempDenseTerm), sizeof(TempRgcnLayerArgs),'
                    'sizeof(TempGruArgs), sizeof(TempAttnArgs), sizeof(TempGatherArgs), sizeof(TempScatterArgs), sizeof(TempOp),'
-                   'offsetof(TempRgcnLayerArgs, chain_ld), offsetof(TempGruArgs, out), offsetof(TempOp, u));return 0;}')
+                   'offsetof(TempRgcnLayerArgs, chain_ld), offsetof(TempGruArgs, out), offsetof(TempOp, u),'
+                   'sizeof(TempGruScanArgs), offsetof(TempGruScanArgs, steps), sizeof(TempScoreLossArgs), sizeof(TempSnapshotView),'
+                   'sizeof(TempPlanCounts), offsetof(TempRgcnLayerArgs, agg_lists));return 0;}')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(lib.DenseTerm), ctypes.sizeof(lib.RgcnLayerArgs), ctypes.sizeof(lib.GruArgs),
             ctypes.sizeof(lib.AttnArgs), ctypes.sizeof(lib.GatherArgs), ctypes.sizeof(lib.ScatterArgs),
-            ctypes.sizeof(lib.Op), lib.RgcnLayerArgs.chain_ld.offset, lib.GruArgs.out.offset, lib.Op.u.offset]
+            ctypes.sizeof(lib.Op), lib.RgcnLayerArgs.chain_ld.offset, lib.GruArgs.out.offset, lib.Op.u.offset,
+            ctypes.sizeof(lib.GruScanArgs), lib.GruScanArgs.steps.offset, ctypes.sizeof(lib.ScoreLossArgs),
+            ctypes.sizeof(lib.SnapshotView), ctypes.sizeof(lib.PlanCounts), lib.RgcnLayerArgs.agg_lists.offset]
     assert got == want
 
 
@@ -267,3 +271,49 @@ def test_shard_exchanges_over_gloo_world_size_2(name):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, True, True), (1, True, True, True)]
+
+
+# ---- native planner (temp_b200/csrc/planner.cpp) == its python statement, array for array ---------------------------
+def _plans_equal(a, b):
+    for name in ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a", "prev_b", "dt_b",
+                 "slot_row", "scan_parts", "agg_rows", "agg_heavy"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y), name
+    assert (a.R, a.E, a.n_slots, a.final_times, a.final_sizes) == (b.R, b.E, b.n_slots, b.final_times, b.final_sizes)
+    assert len(a.segments) == len(b.segments)
+    key = lambda i: None if i is None else (i.item, i.step, i.direction, i.time, i.row0, i.n, id(i.snapshot))
+    for sa, sb in zip(a.segments, b.segments):
+        assert (sa.kind, sa.step, sa.row0, sa.row1) == (sb.kind, sb.step, sb.row0, sb.row1)
+        assert [key(i) for i in sa.instances] == [key(i) for i in sb.instances]
+    assert [key(i) for i in a.last_hist_f] == [key(i) for i in b.last_hist_f]
+    assert [key(i) for i in a.last_hist_b] == [key(i) for i in b.last_hist_b]
+    assert [id(s) for s in a.final_snapshots] == [id(s) for s in b.final_snapshots]
+    if a.n_slots:
+        for da, db in zip(a.steps_f + list(getattr(a, "steps_b", [])), b.steps_f + list(getattr(b, "steps_b", []))):
+            assert {k: key(v) for k, v in da.items()} == {k: key(v) for k, v in db.items()}
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["module"] != "SRGCN"], ids=lambda c: c["name"])
+def test_native_planner_equals_python_planner(case):
+    from temp_b200.planner import plan_window, plan_window_native
+    store = product_store(case["dataset"])
+    kw = dict(bidirectional=case["module"].startswith("Bi"), attention=case["module"].endswith("SARGCN"))
+    _plans_equal(plan_window_native(store.train, case["t_list"], case["L"], **kw),
+                 plan_window(store.train, case["t_list"], case["L"], **kw))
+
+
+@pytest.mark.parametrize("shape,L,B,bi,att", [("icews14", 8, 8, False, False), ("icews05-15", 8, 8, True, False),
+                                               ("icews14", 8, 8, True, True), ("gdelt", 15, 2, False, False),
+                                               ("icews14", 3, 5, False, True)])
+def test_native_planner_equals_python_planner_on_synthetic_shapes(shape, L, B, bi, att):
+    from temp_b200.planner import plan_window, plan_window_native
+    from temp_b200.snapshot import SnapshotStore
+    store = SnapshotStore.synthetic(shape, num_times=2 * L + B + 3, scale=1, seed=99)
+    rng = np.random.default_rng(5)
+    hi = len(store.times) - (L if bi else 1)
+    for _ in range(3):
+        t_list = [int(store.times[i]) for i in rng.choice(np.arange(0, hi + 1), size=B, replace=False)]
+        _plans_equal(plan_window_native(store.train, t_list, L, bidirectional=bi, attention=att),
+                     plan_window(store.train, t_list, L, bidirectional=bi, attention=att))
