@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the fused peer stores")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
     args = ap.parse_args()
@@ -259,32 +260,74 @@ def main():
         results.append((res, e2e_prog, host_out, h2d.u.copy.bytes, nf * WORKLOAD["D"] * 4))
     torch.cuda.synchronize()
 
-    # all-gather buffer of the final-layer states (N > 1)
+    # all-gather of the final-layer states (N > 1): fused into the scan kernel as NVLink stores into every peer's
+    # slab of a symmetric buffer + one cross-GPU barrier; NCCL all_gather_into_tensor when symmetric memory is unavailable
+    # (and once, to verify the fused path)
+    exchange = "none"
+    symm_hdl = None
     if world > 1:
+        D = WORKLOAD["D"]
         max_rows = max(r[0].plan.final.row1 - r[0].plan.final.row0 for r in results)
         rows_t = torch.tensor([max_rows], device=dev)
         dist.all_reduce(rows_t, op=dist.ReduceOp.MAX)
         max_rows = int(rows_t.item())
-        send = torch.zeros(max_rows, WORKLOAD["D"], device=dev)
-        recv = torch.empty(world * max_rows, WORKLOAD["D"], device=dev)
+        send = torch.zeros(max_rows, D, device=dev)
+        recv = torch.empty(world * max_rows, D, device=dev)
+        exchange = "nccl all_gather_into_tensor"
+        if not args.nccl_exchange:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                sym_recv = symm.empty((world, max_rows, D), dtype=torch.float32, device=dev)
+                sym_recv.zero_()
+                symm_hdl = symm.rendezvous(sym_recv, group=dist.group.WORLD)
+                peer_ptrs = torch.tensor([int(p) for p in symm_hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+                for res, e2e_prog, _, _, _ in results:
+                    fin = res.plan.final
+                    res.program.enable_peer_push(peer_ptrs.data_ptr(), world, rank * max_rows * D, fin.row0, fin.row1)
+                    e2e_prog._arr = None
+                # verify once against NCCL
+                torch.cuda.synchronize()
+                symm_hdl.barrier()
+                results[0][0].program.run()
+                symm_hdl.barrier()
+                nf0 = results[0][0].out.shape[0]
+                send.zero_()
+                send[:nf0].copy_(results[0][0].out)
+                dist.all_gather_into_tensor(recv, send)
+                torch.cuda.synchronize()
+                nfs = [torch.zeros(1, dtype=torch.long, device=dev) for _ in range(world)]
+                dist.all_gather(nfs, torch.tensor([nf0], device=dev))
+                ok = all(torch.equal(sym_recv[k, :int(nfs[k])], recv.view(world, max_rows, D)[k, :int(nfs[k])]) for k in range(world))
+                flag = torch.tensor([int(ok)], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) != 1:
+                    raise RuntimeError("fused peer all-gather differs from the NCCL all-gather")
+                exchange = "fused into the scan kernel: NVLink peer stores into symmetric memory + cross-GPU barrier (verified against NCCL)"
+            except Exception as ex:
+                if symm_hdl is not None:
+                    raise
+                exchange = "nccl all_gather_into_tensor (symmetric memory unavailable: %r)" % (ex,)
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def gather_states(res):
+        if symm_hdl is not None:
+            symm_hdl.barrier()            # every rank's scan (and its peer stores) has completed
+        else:
+            nf = res.out.shape[0]
+            send[:nf].copy_(res.out)
+            dist.all_gather_into_tensor(recv, send)
 
     def step_device(i):
         res = results[i % len(results)][0]
         res.program.run()
         if world > 1:
-            nf = res.out.shape[0]
-            send[:nf].copy_(res.out)
-            dist.all_gather_into_tensor(recv, send)
+            gather_states(res)
 
     def step_e2e(i):
         results[i % len(results)][1].run()
         if world > 1:
-            res = results[i % len(results)][0]
-            nf = res.out.shape[0]
-            send[:nf].copy_(res.out)
-            dist.all_gather_into_tensor(recv, send)
+            gather_states(results[i % len(results)][0])
 
     for i in range(W):
         step_device(i)
@@ -368,7 +411,7 @@ def main():
         line = {
             "metric": "edges_per_sec_rgcn_gru_forward", "value": tot_edges / (max_dev_ms * 1e-3), "unit": "edges/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_dev_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(world),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(bench_config(world), exchange=exchange),
             "e2e": {"value": tot_edges / max_e2e, "unit": "edges/s", "h2d_bytes_per_step": int(results[0][3]),
                     "d2h_bytes_per_step": int(results[0][4]), "ms_per_step": 1e3 * max_e2e / K,
                     "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms},

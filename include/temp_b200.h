@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 7
+#define TEMP_ABI_VERSION 8
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -34,6 +34,7 @@ extern "C" {
 #define TEMP_MAX_D 256     /* embed_size == hidden_size upper bound of the SIMT path  */
 #define TEMP_MAX_TERMS 3
 #define TEMP_MAX_SCAN_STEPS 16
+#define TEMP_MAX_PUSH_PEERS 8
 
 #define TEMP_ACT_NONE 0
 #define TEMP_ACT_RELU 1
@@ -136,6 +137,7 @@ typedef struct {
   float* out;                /* [rows, d]                                                         */
   int32_t out_index_is_row;  /* reserved, must be 1                                               */
   int32_t part_col;          /* column of this step in the scan's chain-partition table (see below) */
+  int32_t push;              /* 1: the values this step writes are also stored to every peer (TempGruScanArgs.push_*) */
 } TempGruArgs;
 
 /* All GRU steps of a window in ONE launch (persistent CTAs, W_hh^T slices resident in shared memory
@@ -156,7 +158,15 @@ typedef struct {
   uint32_t* barrier;
   const int32_t* parts;
   int32_t part_stride;
-  int32_t reserved;
+  /* Fused all-gather of the final-layer states over NVLink peer memory (tcgen05 path): steps with `push` set store
+   * every value they write to row r also to  push_bufs[k] + push_offset + (r - push_row0) * d  for all k <
+   * push_world, where push_bufs is a DEVICE array of peer-mapped buffer bases (this rank's own buffer included), e.g.
+   * from torch.distributed._symmetric_memory.  The caller separates the launch from the consumers on the other GPUs
+   * with a cross-GPU barrier.  push_bufs == null: no peer stores.                                                  */
+  int32_t push_world;
+  float* const* push_bufs;
+  int64_t push_offset;
+  int32_t push_row0, reserved;
   TempGruArgs steps[TEMP_MAX_SCAN_STEPS];
 } TempGruScanArgs;
 

@@ -490,6 +490,7 @@ static_assert(kScanHalf * 32 * 4 == kScanHalf * 128, "the gate exchange rows ali
 struct ScanBars {
   uint64_t w_full, mma_done[2];
   uint32_t tmem_base;
+  float* push[TEMP_MAX_PUSH_PEERS];  // peer-mapped buffer bases of the fused all-gather (offset applied)
 };
 
 // Publishing a step: every thread's state stores are ordered before ONE thread's cluster-scope release fence by a CTA
@@ -560,6 +561,7 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
     fence_mbar_init();
   }
   if (warp == kScanCtlWarp) tmem_alloc(&S.tmem_base, 128);
+  if (P.push_bufs != nullptr && tid < P.push_world) S.push[tid] = P.push_bufs[tid] + P.push_offset;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -836,7 +838,12 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
           }
           hy += te_rows ? __ldg(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j) : te_uni;
           float* o = p.out + static_cast<size_t>(r) * kD + j;
-          *o = p.accumulate ? (__ldcg(o) + hy) : hy;
+          if (p.accumulate) hy += __ldcg(o);
+          *o = hy;
+          if (p.push != 0 && P.push_bufs != nullptr) {  // fused all-gather: NVLink stores into every peer's slab
+            const size_t po = static_cast<size_t>(r - P.push_row0) * kD + j;
+            for (int k = 0; k < P.push_world; ++k) S.push[k][po] = hy;
+          }
         }
       }
     }
@@ -940,6 +947,7 @@ bool tc_scan_supported(const TempGruScanArgs* a) {
     if (g.prev_row != nullptr && g.whh_packed == nullptr) return false;
     if (a->parts != nullptr && (g.part_col < 0 || g.part_col >= a->part_stride)) return false;
   }
+  if (a->push_bufs != nullptr && (a->push_world <= 0 || a->push_world > TEMP_MAX_PUSH_PEERS)) return false;
   return true;
 }
 

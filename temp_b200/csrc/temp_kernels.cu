@@ -958,6 +958,7 @@ int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   }
   if (max_rows == 0) return TEMP_OK;
   if (temp_internal::tc_scan_supported(a)) return temp_internal::tc_launch_scan(a, st);
+  if (a->push_bufs != nullptr) return fail(TEMP_EUNSUPPORTED, "the fused peer all-gather needs the tcgen05 scan (d == 128, partition table)%s", "");
   if (a->barrier == nullptr) return fail(TEMP_EINVAL, "scan needs a zero-initialised 8-byte barrier word%s", "");
   if (max_rows <= 148 * 64) return launch_scan_t<4, 3>(a, max_rows, st);
   return launch_scan_t<8, 4>(a, max_rows, st);

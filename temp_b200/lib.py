@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -49,13 +49,14 @@ class GruArgs(C.Structure):
         ("state", _p), ("prev_row", _p), ("dt", _p), ("decay_wb", _p), ("inv_temperature", C.c_float),
         ("whh_t", _p), ("whh_packed", _p), ("b_hh", _p), ("cell_type", _i32),
         ("time_embed", _p), ("row_time", _p), ("row_time_scalar", _i32),
-        ("accumulate", _i32), ("out", _p), ("out_index_is_row", _i32), ("part_col", _i32),
+        ("accumulate", _i32), ("out", _p), ("out_index_is_row", _i32), ("part_col", _i32), ("push", _i32),
     ]
 
 
 class GruScanArgs(C.Structure):
     _fields_ = [("n_steps", _i32), ("n_parts", _i32), ("barrier", _p), ("parts", _p), ("part_stride", _i32),
-                ("reserved", _i32), ("steps", GruArgs * MAX_SCAN_STEPS)]
+                ("push_world", _i32), ("push_bufs", _p), ("push_offset", C.c_int64), ("push_row0", _i32), ("reserved", _i32),
+                ("steps", GruArgs * MAX_SCAN_STEPS)]
 
 
 class AttnArgs(C.Structure):
@@ -250,6 +251,22 @@ class Program(object):
 
     def count(self, kinds=(OP_LAYER, OP_GRU, OP_GRU_SCAN, OP_ATTN, OP_GATHER, OP_SCATTER)) -> int:
         return sum(1 for o in self.ops if o.kind in kinds)
+
+    def enable_peer_push(self, bufs_dev_ptr: int, world: int, offset_elems: int, row0: int, row1: int) -> None:
+        """Fused all-gather: the scan steps that write the FINAL value of rows [row0, row1) (the last op over exactly that
+        range) also store it into every peer's buffer (TempGruScanArgs.push_*)."""
+        scans = [o for o in self.ops if o.kind == OP_GRU_SCAN]
+        if not scans:
+            raise RuntimeError("temp_b200: peer push needs the fused GRU scan")
+        sc = scans[-1].u.scan
+        last = [i for i in range(sc.n_steps) if sc.steps[i].row0 == row0 and sc.steps[i].row1 == row1]
+        if not last:
+            raise RuntimeError("temp_b200: no scan step covers the pushed row range")
+        for i in range(sc.n_steps):
+            sc.steps[i].push = 0
+        sc.steps[last[-1]].push = 1
+        sc.push_bufs, sc.push_world, sc.push_offset, sc.push_row0 = bufs_dev_ptr, int(world), int(offset_elems), int(row0)
+        self._arr = None
 
     def kernel_count(self) -> int:
         """Kernel launches one ``run`` issues (a tensor-core layer with a graph part is two: gather + tile kernel)."""

@@ -171,3 +171,22 @@ def test_fused_scorer_matches_torch_reference_path(score_fn, corrupt_tail, shape
         sc = fn(table[cand], r, ent[tri[:, 2]], mode="head")
     want = F.cross_entropy(sc.double(), torch.zeros(P, dtype=torch.long, device="cuda"))
     assert abs(float(got) - float(want)) <= 1e-5 * max(abs(float(want)), 1.0)
+
+
+def test_fused_peer_all_gather_matches_nccl():
+    """N = 2 (needs 2 GPUs): the scan kernel's NVLink peer stores into symmetric memory deliver the same final-layer
+    states as the NCCL all-gather (bench.py verifies the fused exchange against NCCL before timing)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "5", "--warmup", "3",
+           "--no-sharded"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert "verified against NCCL" in line["config"]["exchange"]
