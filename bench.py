@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="one CUDA graph per launch program instead of direct launches "
+                                                         "(measured: no gain, the step is bound on the device)")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the fused peer stores")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
@@ -333,6 +335,15 @@ def main():
         step_device(i)
         step_e2e(i)
     torch.cuda.synchronize()
+    # each launch program (copies + kernels, cluster and programmatic-dependent-launch edges included) as ONE CUDA graph
+    graphed = 0
+    if args.graph:
+        for res, e2e_prog, _, _, _ in results:
+            graphed += int(res.program.capture()) + int(e2e_prog.capture())
+        for i in range(W):
+            step_device(i)
+            step_e2e(i)
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
 
@@ -417,6 +428,7 @@ def main():
                     "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms},
             "gpu_launches": int(launches),
             "launches_per_step": results[0][0].program.kernel_count(),
+            "cuda_graph": "one graph per launch program (%d of %d captured)" % (graphed, 2 * len(results)) if graphed else "off",
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom_name + " -- " + dom["what"], "achieved": dom["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": dom["achieved"] / peak, "traffic": traffic,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 8
+#define TEMP_ABI_VERSION 9
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -311,6 +311,12 @@ int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* str
 /* Runs ops[0..n) back to back on one stream (memcpy ops use cudaMemcpyAsync; host pointers must be
  * pinned for the copies to be asynchronous).  Returns the first failure.                          */
 int temp_run_program(const TempOp* ops_host, int32_t n, void* stream);
+/* The same program as ONE CUDA graph (copies, cluster launch and programmatic-dependent-launch edges included): captured
+ * once on a private stream, launched into any stream with a single driver call.  The caller keeps every buffer the ops
+ * point to alive and unchanged in address; run the program once with temp_run_program first (lazy kernel attributes). */
+int temp_graph_create(const TempOp* ops_host, int32_t n, void** graph_exec_out);
+int temp_graph_launch(void* graph_exec, void* stream);
+int temp_graph_destroy(void* graph_exec);
 /* Number of kernel launches temp_run_program(ops, n) issues (copies excluded); negative on a bad program. */
 int temp_program_kernel_count(const TempOp* ops_host, int32_t n);
 

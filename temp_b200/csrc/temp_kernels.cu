@@ -1152,4 +1152,47 @@ int temp_run_program(const TempOp* ops, int32_t n, void* stream) {
   return TEMP_OK;
 }
 
+int temp_graph_create(const TempOp* ops, int32_t n, void** graph_exec_out) {
+  if (ops == nullptr || n <= 0 || graph_exec_out == nullptr) return fail(TEMP_EINVAL, "bad graph args%s", "");
+  *graph_exec_out = nullptr;
+  cudaStream_t cap = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(cap);
+    return cuda_fail(e, "cudaStreamBeginCapture");
+  }
+  const int rc = temp_run_program(ops, n, cap);
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(cap, &graph);
+  cudaStreamDestroy(cap);
+  if (rc != TEMP_OK) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc;
+  }
+  if (e != cudaSuccess || graph == nullptr) return cuda_fail(e, "cudaStreamEndCapture");
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+  *graph_exec_out = exec;
+  return TEMP_OK;
+}
+
+int temp_graph_launch(void* graph_exec, void* stream) {
+  if (graph_exec == nullptr) return fail(TEMP_EINVAL, "null graph%s", "");
+  cudaError_t e = cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+  return TEMP_OK;
+}
+
+int temp_graph_destroy(void* graph_exec) {
+  if (graph_exec == nullptr) return TEMP_OK;
+  cudaError_t e = cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphExecDestroy");
+  return TEMP_OK;
+}
+
 }  // extern "C"

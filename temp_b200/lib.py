@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -116,7 +116,7 @@ EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "te
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
            "temp_program_kernel_count", "temp_score_loss_fwd", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
-           "temp_plan_array")
+           "temp_plan_array", "temp_graph_create", "temp_graph_launch", "temp_graph_destroy")
 
 _lib = None
 
@@ -147,6 +147,9 @@ def load(path: Optional[str] = None):
     lib.temp_run_program.argtypes = [C.POINTER(Op), _i32, _p]
     lib.temp_program_kernel_count.argtypes = [C.POINTER(Op), _i32]
     lib.temp_score_loss_fwd.argtypes = [C.POINTER(ScoreLossArgs), _p]
+    lib.temp_graph_create.argtypes = [C.POINTER(Op), _i32, C.POINTER(_p)]
+    lib.temp_graph_launch.argtypes = [_p, _p]
+    lib.temp_graph_destroy.argtypes = [_p]
     lib.temp_plan_window.argtypes = [C.POINTER(SnapshotView), _i32, C.POINTER(_i32), _i32, _i32, _i32, _i32, _i32, _i32]
     lib.temp_plan_window.restype = _p
     lib.temp_plan_destroy.argtypes = [_p]
@@ -279,10 +282,42 @@ class Program(object):
             raise RuntimeError("temp_b200: bad program")
         return int(n)
 
+    def capture(self) -> bool:
+        """Instantiates the program as one CUDA graph (``run`` then costs a single driver call).  The program must have
+        run once directly; its ops must not change afterwards.  Returns False (and keeps direct launches) when the
+        driver refuses the capture."""
+        if not self.ops:
+            return False
+        self.release_graph()
+        if self._arr is None:
+            self._arr = (Op * len(self.ops))(*self.ops)
+        out = _p()
+        rc = load().temp_graph_create(self._arr, len(self.ops), C.byref(out))
+        if rc != 0 or not out.value:
+            return False
+        self._graph = out
+        return True
+
+    def release_graph(self) -> None:
+        g = getattr(self, "_graph", None)
+        if g is not None:
+            load().temp_graph_destroy(g)
+            self._graph = None
+
+    def __del__(self):
+        try:
+            self.release_graph()
+        except Exception:
+            pass
+
     def run(self, stream: Optional[int] = None) -> None:
         if not self.ops:
             return
+        st = current_stream() if stream is None else stream
+        g = getattr(self, "_graph", None)
+        if g is not None and self._arr is not None:
+            check(load().temp_graph_launch(g, _p(st)), "temp_graph_launch")
+            return
         if self._arr is None:
             self._arr = (Op * len(self.ops))(*self.ops)
-        st = current_stream() if stream is None else stream
         check(load().temp_run_program(self._arr, len(self.ops), _p(st)), "temp_run_program")

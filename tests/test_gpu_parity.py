@@ -190,3 +190,20 @@ def test_fused_peer_all_gather_matches_nccl():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert "verified against NCCL" in line["config"]["exchange"]
+
+
+def test_launch_program_as_cuda_graph_is_bit_identical():
+    """temp_graph_create / temp_graph_launch: the captured program (copies, cluster launch, PDL edges) reproduces the
+    directly launched one."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    model = product_model(case)
+    res = model.encode(case["t_list"])
+    want = res.out.clone()
+    assert res.program.capture()
+    res.out.zero_()
+    for _ in range(3):
+        res.program.run()
+    torch.cuda.synchronize()
+    assert torch.equal(res.out, want)
+    res.program.release_graph()
