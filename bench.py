@@ -279,19 +279,32 @@ def main():
         if not args.nccl_exchange:
             try:
                 import torch.distributed._symmetric_memory as symm
-                sym_recv = symm.empty((world, max_rows, D), dtype=torch.float32, device=dev)
+                # two slabs per peer, used alternately: a rank may start pushing step s + 1 while a slower peer still
+                # reads step s (it cannot get further ahead: the barrier of step s + 1 needs that peer's signal)
+                sym_recv = symm.empty((2, world, max_rows, D), dtype=torch.float32, device=dev)
                 sym_recv.zero_()
                 symm_hdl = symm.rendezvous(sym_recv, group=dist.group.WORLD)
                 peer_ptrs = torch.tensor([int(p) for p in symm_hdl.buffer_ptrs], dtype=torch.int64, device=dev)
-                for res, e2e_prog, _, _, _ in results:
-                    fin = res.plan.final
-                    res.program.enable_peer_push(peer_ptrs.data_ptr(), world, rank * max_rows * D, fin.row0, fin.row1)
-                    e2e_prog._arr = None
-                # verify once against NCCL
+                sym_flags = symm.empty((32,), dtype=torch.int32, device=dev)
+                sym_flags.zero_()
+                flag_hdl = symm.rendezvous(sym_flags, group=dist.group.WORLD)
+                flag_ptrs = torch.tensor([int(p) for p in flag_hdl.buffer_ptrs], dtype=torch.int64, device=dev)
                 torch.cuda.synchronize()
                 symm_hdl.barrier()
+                for k, (res, e2e_prog, _, _, _) in enumerate(results):
+                    fin = res.plan.final
+                    res.program.enable_peer_push(peer_ptrs.data_ptr(), world, ((k & 1) * world + rank) * max_rows * D,
+                                                 fin.row0, fin.row1)
+                    e2e_prog._arr = None
+                barrier_seq = [0]
+
+                def peer_barrier():
+                    barrier_seq[0] += 1
+                    lib.check(lib.load().temp_peer_barrier(sym_flags.data_ptr(), flag_ptrs.data_ptr(), world, rank,
+                                                           barrier_seq[0], lib.current_stream()), "temp_peer_barrier")
+                # verify once against NCCL
                 results[0][0].program.run()
-                symm_hdl.barrier()
+                peer_barrier()
                 nf0 = results[0][0].out.shape[0]
                 send.zero_()
                 send[:nf0].copy_(results[0][0].out)
@@ -299,12 +312,13 @@ def main():
                 torch.cuda.synchronize()
                 nfs = [torch.zeros(1, dtype=torch.long, device=dev) for _ in range(world)]
                 dist.all_gather(nfs, torch.tensor([nf0], device=dev))
-                ok = all(torch.equal(sym_recv[k, :int(nfs[k])], recv.view(world, max_rows, D)[k, :int(nfs[k])]) for k in range(world))
+                ok = all(torch.equal(sym_recv[0, k, :int(nfs[k])], recv.view(world, max_rows, D)[k, :int(nfs[k])]) for k in range(world))
                 flag = torch.tensor([int(ok)], device=dev)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 if int(flag.item()) != 1:
                     raise RuntimeError("fused peer all-gather differs from the NCCL all-gather")
-                exchange = "fused into the scan kernel: NVLink peer stores into symmetric memory + cross-GPU barrier (verified against NCCL)"
+                exchange = ("fused into the scan kernel: NVLink peer stores into double-buffered symmetric memory + one "
+                            "signal/wait launch (temp_peer_barrier); verified against NCCL")
             except Exception as ex:
                 if symm_hdl is not None:
                     raise
@@ -314,7 +328,7 @@ def main():
 
     def gather_states(res):
         if symm_hdl is not None:
-            symm_hdl.barrier()            # every rank's scan (and its peer stores) has completed
+            peer_barrier()                # every rank's scan (and its peer stores) has completed
         else:
             nf = res.out.shape[0]
             send[:nf].copy_(res.out)

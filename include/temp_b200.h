@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 9
+#define TEMP_ABI_VERSION 10
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -311,6 +311,12 @@ int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* str
 /* Runs ops[0..n) back to back on one stream (memcpy ops use cudaMemcpyAsync; host pointers must be
  * pinned for the copies to be asynchronous).  Returns the first failure.                          */
 int temp_run_program(const TempOp* ops_host, int32_t n, void* stream);
+/* Cross-GPU completion barrier of the fused all-gather (one tiny launch): stores `seq` into slot `rank` of every peer's
+ * flag array (st.release.sys through the peer-mapped pointers flag_peers[0..world)), then waits until all `world` slots
+ * of this GPU's own array flags_local hold a value >= seq (ld.acquire.sys).  seq must grow by one per step; the kernels
+ * whose peer stores it publishes precede it on `stream`.                                                              */
+int temp_peer_barrier(uint32_t* flags_local, uint32_t* const* flag_peers, int32_t world, int32_t rank, uint32_t seq,
+                      void* stream);
 /* The same program as ONE CUDA graph (copies, cluster launch and programmatic-dependent-launch edges included): captured
  * once on a private stream, launched into any stream with a single driver call.  The caller keeps every buffer the ops
  * point to alive and unchanged in address; run the program once with temp_run_program first (lazy kernel attributes). */

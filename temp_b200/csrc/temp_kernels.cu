@@ -759,6 +759,23 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
 }
 
 // ------------------------------------------------------------------------------------------------
+// cross-GPU barrier of the fused all-gather (signal every peer, wait for every peer)
+// ------------------------------------------------------------------------------------------------
+__global__ void peer_barrier_kernel(uint32_t* flags_local, uint32_t* const* flag_peers, int world, int rank, uint32_t seq) {
+  const int k = threadIdx.x;
+  if (k >= world) return;
+  uint32_t* remote = flag_peers[k] + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(seq) : "memory");
+  const uint32_t* mine = flags_local + k;
+  uint32_t v;
+  unsigned spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (++spins > (1u << 28)) __trap();  // a peer that never arrives is a bug in the caller: do not hang the device
+  } while (static_cast<int32_t>(v - seq) < 0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // small data-movement kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const TempGatherArgs p) {
@@ -1149,6 +1166,16 @@ int temp_run_program(const TempOp* ops, int32_t n, void* stream) {
     }
     if (rc != TEMP_OK) return rc;
   }
+  return TEMP_OK;
+}
+
+int temp_peer_barrier(uint32_t* flags_local, uint32_t* const* flag_peers, int32_t world, int32_t rank, uint32_t seq,
+                      void* stream) {
+  if (flags_local == nullptr || flag_peers == nullptr || world <= 0 || world > 32 || rank < 0 || rank >= world)
+    return fail(TEMP_EINVAL, "bad peer barrier args%s", "");
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags_local, flag_peers, world, rank, seq);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "peer_barrier_kernel launch");
   return TEMP_OK;
 }
 
