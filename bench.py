@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="one CUDA graph per launch program instead of direct launches "
                                                          "(measured: no gain, the step is bound on the device)")
+    ap.add_argument("--multimem", action="store_true", help="N > 1: NVLS multimem.st instead of one store per peer (measured "
+                                                            "slower at 4 bytes per lane: 0.152 vs 0.143 ms per step at N = 8)")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the fused peer stores")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
@@ -291,10 +293,17 @@ def main():
                 flag_ptrs = torch.tensor([int(p) for p in flag_hdl.buffer_ptrs], dtype=torch.int64, device=dev)
                 torch.cuda.synchronize()
                 symm_hdl.barrier()
+                mc_ptr = 0
+                if args.multimem:
+                    try:
+                        if symm_hdl.has_multicast_support:
+                            mc_ptr = int(symm_hdl.multicast_ptr)
+                    except Exception:
+                        mc_ptr = 0
                 for k, (res, e2e_prog, _, _, _) in enumerate(results):
                     fin = res.plan.final
                     res.program.enable_peer_push(peer_ptrs.data_ptr(), world, ((k & 1) * world + rank) * max_rows * D,
-                                                 fin.row0, fin.row1)
+                                                 fin.row0, fin.row1, multicast_ptr=mc_ptr)
                     e2e_prog._arr = None
                 barrier_seq = [0]
 
@@ -317,8 +326,9 @@ def main():
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 if int(flag.item()) != 1:
                     raise RuntimeError("fused peer all-gather differs from the NCCL all-gather")
-                exchange = ("fused into the scan kernel: NVLink peer stores into double-buffered symmetric memory + one "
-                            "signal/wait launch (temp_peer_barrier); verified against NCCL")
+                exchange = ("fused into the scan kernel: %s into double-buffered symmetric memory + one signal/wait launch "
+                            "(temp_peer_barrier); verified against NCCL"
+                            % ("NVLS multimem.st (one store, switch-replicated)" if mc_ptr else "one NVLink store per peer"))
             except Exception as ex:
                 if symm_hdl is not None:
                     raise

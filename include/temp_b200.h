@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 10
+#define TEMP_ABI_VERSION 11
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -167,6 +167,8 @@ typedef struct {
   float* const* push_bufs;
   int64_t push_offset;
   int32_t push_row0, reserved;
+  float* push_multicast;     /* nullable: NVLS multicast address of the same symmetric buffer -- one multimem.st per
+                                value instead of one store per peer (the switch replicates it to every GPU)           */
   TempGruArgs steps[TEMP_MAX_SCAN_STEPS];
 } TempGruScanArgs;
 

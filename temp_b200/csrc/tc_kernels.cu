@@ -842,7 +842,12 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
           *o = hy;
           if (p.push != 0 && P.push_bufs != nullptr) {  // fused all-gather: NVLink stores into every peer's slab
             const size_t po = static_cast<size_t>(r - P.push_row0) * kD + j;
-            for (int k = 0; k < P.push_world; ++k) S.push[k][po] = hy;
+            if (P.push_multicast != nullptr) {  // one store, replicated to every GPU by the NVSwitch (NVLS)
+              asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.push_multicast + P.push_offset + po), "f"(hy)
+                           : "memory");
+            } else {
+              for (int k = 0; k < P.push_world; ++k) S.push[k][po] = hy;
+            }
           }
         }
       }

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -56,7 +56,7 @@ class GruArgs(C.Structure):
 class GruScanArgs(C.Structure):
     _fields_ = [("n_steps", _i32), ("n_parts", _i32), ("barrier", _p), ("parts", _p), ("part_stride", _i32),
                 ("push_world", _i32), ("push_bufs", _p), ("push_offset", C.c_int64), ("push_row0", _i32), ("reserved", _i32),
-                ("steps", GruArgs * MAX_SCAN_STEPS)]
+                ("push_multicast", _p), ("steps", GruArgs * MAX_SCAN_STEPS)]
 
 
 class AttnArgs(C.Structure):
@@ -256,7 +256,8 @@ class Program(object):
     def count(self, kinds=(OP_LAYER, OP_GRU, OP_GRU_SCAN, OP_ATTN, OP_GATHER, OP_SCATTER)) -> int:
         return sum(1 for o in self.ops if o.kind in kinds)
 
-    def enable_peer_push(self, bufs_dev_ptr: int, world: int, offset_elems: int, row0: int, row1: int) -> None:
+    def enable_peer_push(self, bufs_dev_ptr: int, world: int, offset_elems: int, row0: int, row1: int,
+                         multicast_ptr: int = 0) -> None:
         """Fused all-gather: the scan steps that write the FINAL value of rows [row0, row1) (the last op over exactly that
         range) also store it into every peer's buffer (TempGruScanArgs.push_*)."""
         scans = [o for o in self.ops if o.kind == OP_GRU_SCAN]
@@ -270,6 +271,7 @@ class Program(object):
             sc.steps[i].push = 0
         sc.steps[last[-1]].push = 1
         sc.push_bufs, sc.push_world, sc.push_offset, sc.push_row0 = bufs_dev_ptr, int(world), int(offset_elems), int(row0)
+        sc.push_multicast = multicast_ptr or None
         self._arr = None
 
     def kernel_count(self) -> int:
