@@ -230,11 +230,19 @@ class TKG_Module(nn.Module):
     def _targets(self, res: EncodeResult, graph_dict):
         return [graph_dict[t] for t in res.plan.final_times]
 
-    @torch.no_grad()
     def forward(self, t_list, reverse=False):
         """Training loss of the reference (models/DynamicRGCN.py:176-194).  In ``train()`` mode the window is
         edge-sub-sampled like the reference (``train_edge_sampler``); in ``eval()`` mode it runs on full graphs.
-        Negative sampling stays host-side and bit-exact; the encoder runs the CUDA forward (no autograd)."""
+        Negative sampling stays host-side and bit-exact.  Without gradients the encoder is the CUDA forward; WITH
+        gradients enabled (``loss.backward()`` for training) the loss is computed by the differentiable torch statement
+        of ``temp_b200/autograd_path.py`` -- the documented, not accelerated autograd fallback of SURVEY section 8b."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd_path import training_loss
+            return training_loss(self, t_list)
+        with torch.no_grad():
+            return self._forward_no_grad(t_list)
+
+    def _forward_no_grad(self, t_list):
         if self.training:
             if self.family != "recurrent" or self.bidirectional:
                 raise NotImplementedError("temp_b200: the training-mode edge sub-sampling is implemented for DynamicRGCN "

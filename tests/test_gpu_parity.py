@@ -207,3 +207,65 @@ def test_launch_program_as_cuda_graph_is_bit_identical():
     torch.cuda.synchronize()
     assert torch.equal(res.out, want)
     res.program.release_graph()
+
+
+@pytest.mark.parametrize("name", ["grrgcn_tiny_d128_last", "rrgcn_tiny_d128_last", "grrgcn_icews_d128_L8",
+                                  "grrgcn_tiny_d128_lambda"])
+def test_autograd_fallback_loss_equals_cuda_forward(name):
+    """forward() with gradients enabled (the torch autograd fallback of SURVEY section 8b) computes the same loss as the
+    CUDA forward under no_grad on the same inputs and seeds (eval mode: full graphs, no dropout)."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME[name]
+    model = product_model(case).eval()
+    tl = torch.tensor(case["t_list"])
+    np.random.seed(3)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        want = float(model.forward(tl))
+    np.random.seed(3)
+    torch.manual_seed(3)
+    got = model.forward(tl)
+    assert got.requires_grad
+    assert abs(float(got) - want) <= RTOL * abs(want)
+
+
+@pytest.mark.parametrize("tc", [c for c in __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES
+                                if "icews" not in c["name"]], ids=lambda c: c["name"])
+def test_autograd_fallback_gradients_match_oracle(tc):
+    """loss.backward() through the fallback gives the gradients of the (reference-pinned) oracle's training loss:
+    train mode, sub-sampled window, dropout p = 0, same global seeds."""
+    from tests.helpers import CASE_BY_NAME
+    case = dict(CASE_BY_NAME[tc["base"]])
+    gold = load_golden(tc["name"])
+    oracle = oracle_model(case)
+    for v in oracle.p.values():
+        v.requires_grad_(True)
+    np.random.seed(tc["seed"])
+    torch.manual_seed(tc["seed"])
+    lo = oracle.train_loss(case["t_list"], case.get("negative_rate", 5), case.get("num_pos_facts", 3000),
+                           random_dropout=tc["random_dropout"])
+    lo.backward()
+    model = product_model(case)
+    model.args.dropout = 0.0
+    for layer in (model.ent_encoder.layer_1, model.ent_encoder.layer_2):
+        layer.dropout_p = 0.0
+    model.args.random_dropout = tc["random_dropout"]
+    model.train()
+    np.random.seed(tc["seed"])
+    torch.manual_seed(tc["seed"])
+    loss = model.forward(torch.tensor(case["t_list"]))
+    assert abs(float(loss) - float(gold["loss"])) <= RTOL * abs(float(gold["loss"]))
+    loss.backward()
+    checked = 0
+    for name, prm in model.named_parameters():
+        go = oracle.p[name].grad
+        if go is None:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        g = prm.grad.detach().cpu().double().numpy()
+        w = go.double().numpy()
+        scale = max(np.abs(w).max(), 1e-12)
+        assert np.abs(g - w).max() / scale < 1e-3, (name, np.abs(g - w).max() / scale)
+        checked += 1
+    assert checked >= 6
+    torch.optim.Adam(model.parameters(), lr=1e-3).step()       # a main.py-style update runs
