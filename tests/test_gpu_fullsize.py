@@ -37,12 +37,12 @@ def _args(module, D, n_bases, L, **kw):
     return Namespace(**a)
 
 
-def _build(cfg):
+def _build(cfg, scale=1):
     from temp_b200.models import build_module
     from temp_b200.snapshot import SnapshotStore
     name, module, shape, D, nb, L, B, extra = cfg
     T = 2 * L + B + 2
-    store = SnapshotStore.synthetic(shape, num_times=T, scale=1, seed=20201116 + CONFIGS.index(cfg))
+    store = SnapshotStore.synthetic(shape, num_times=T, scale=scale, seed=20201116 + CONFIGS.index(cfg))
     torch.manual_seed(123)
     model = build_module(_args(module, D, nb, L, **extra), store.num_ents, store.num_rels, store.train).cuda().eval()
     lo = L - 1 if not module.startswith("Bi") else L - 1
@@ -97,3 +97,20 @@ def test_gdelt_shaped_heavy_rows_use_the_block_path():
     deg = np.diff(plan.row_ptr)
     assert plan.agg_heavy.shape[0] == int((deg > 8).sum()) and deg.max() > 256
     assert plan.agg_rows.shape[0] == int(((deg > 0) & (deg <= 8)).sum())
+
+
+@pytest.mark.parametrize("cfg_index,scale", [(1, 6), (3, 10), (5, 8)], ids=["grrgcn_icews14_x6", "bigrrgcn_icews0515_x10",
+                                                                           "grrgcn_gdelt_x8"])
+def test_scaled_shapes_with_many_partitions_per_cluster(cfg_index, scale):
+    """Shapes with far more chain partitions than clusters: a cluster then walks several partitions in step-major order
+    with the next tile step's previous-state rows and input gates fetched ahead (the path the x16 roofline numbers of
+    bench.py run on) -- held to the oracle like the x1 shapes."""
+    cfg = CONFIGS[cfg_index]
+    model, oracle, t_list = _build(cfg, scale=scale)
+    res = model.encode(t_list)
+    got = res.out.clone()
+    assert res.plan.scan_parts.shape[0] > 2 * 37        # more than two partitions per cluster on a 148-SM part
+    with torch.no_grad():
+        ref = oracle.evaluate_embed(t_list)
+    _close(got.cpu().numpy(), torch.cat(ref["per_graph"]).numpy())
+    assert torch.equal(got, model.encode(t_list).out)
