@@ -7,14 +7,17 @@
 // consecutive features of one packed row -- global activations are read and written as coalesced 128-byte
 // lines and the thread that gathered agg[row][feature] is the thread that later reads D^T[feature][row].
 //
+//   rgcn_gather_kernel   : the CSR-by-destination aggregation with the in-register 1x1 relation projection as its own
+//        HBM / L2-bound launch (compact work lists, a warp per row, a thread block per high in-degree row).
 //   rgcn_layer_tc_kernel : one CTA per 128 packed rows.
-//        workers (8 warps) : self-loop operand rows -> smem (hi/lo, SWIZZLE_128B) ; CSR gather into registers ;
+//        workers (8 warps) : self-loop operand rows -> smem (hi/lo, SWIZZLE_128B) ; aggregate rows prefetched ;
 //                            epilogue 1 (agg + D1 + bias, act, time embedding, h_out) ; chain operand X written
 //                            in place over the self-loop operand ; chain epilogues (gi / q|k|v + bias)
 //        TMA warp          : packed weight chunks (32 KB = 128 features x 32 k, hi + lo) through a 3-stage ring
 //        MMA warp          : D1 = W_loop^T . x^T, then per 128 chain features D2 = W_chain . X^T (TMEM ring of 3)
-//   gru_scan_tc_kernel   : persistent cooperative scan over the GRU steps of a window; CTA = (block of 32 hidden
-//        columns, row tiles of 64); its W_hh slice (r|z|n rows, hi/lo) stays in shared memory for the whole scan.
+//   gru_scan_tc_kernel   : persistent chain-partitioned scan over the GRU steps of a window; CTA = (block of 32 hidden
+//        columns) of a 4-CTA cluster, tiles of <= 96 rows per partition step; its W_hh slice (r|z|n rows, hi/lo) stays
+//        in shared memory for the whole scan; steps are separated by the hardware cluster barrier.
 #include <stdio.h>
 #include <string.h>
 

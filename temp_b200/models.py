@@ -14,9 +14,9 @@ hot path -- ``encode(t_list)`` runs one launch program over a packed window plan
 ``hist_embeddings`` / ``start_time_tensor`` tensors of the reference API are materialised only when a
 caller asks for them (``evaluate_embed``).
 
-Scope note: the accelerated path is the deterministic forward (eval mode; dropout off, full graphs).
-``forward`` (the training loss) runs the same encoder forward under ``torch.no_grad`` for the
-encoder part; back-propagation through the encoder kernels is not implemented in this round.
+Scope note: the accelerated path is the forward.  ``forward`` (the training loss) runs the CUDA encoder under
+``torch.no_grad``; with gradients enabled it goes through the torch autograd fallback of ``temp_b200/autograd_path.py``
+(GRRGCN / RRGCN with --rec-only-last-layer) -- back-propagation through the encoder KERNELS is not implemented.
 """
 from __future__ import annotations
 

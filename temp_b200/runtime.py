@@ -149,7 +149,7 @@ class EncoderRuntime(object):
         self.ws = Workspace(self.device)
         self.prep = PreparedWeights(model)
         self._chain_packed = {}
-        self.fuse_scan = True      # consecutive GRU steps -> one cooperative persistent launch
+        self.fuse_scan = True      # consecutive GRU steps -> one persistent scan launch (chain-partitioned on the tcgen05 path)
         self._agg_rows = 1
         self.use_tc = True         # tcgen05 path where the shapes allow it (d == 128); False: fp32 SIMT kernels only
 
@@ -178,7 +178,6 @@ class EncoderRuntime(object):
             a.row_ptr = dptr["row_ptr"]
             a.e_src = dptr["e_src_ent"] if x_is_embed else dptr["e_src"]
             a.e_rel = dptr["e_rel"]
-            a.e_dst = dptr.get("e_dst")
             a.norm = dptr["norm"]
             a.x = x.data_ptr()
             a.weight = layer.weight.data_ptr()
@@ -296,7 +295,7 @@ class EncoderRuntime(object):
         return self._build_recurrent(plan, prog, dptr)
 
     def scan_barrier(self) -> int:
-        """8 zeroed bytes for the cooperative scan's grid barrier (self-cleaning, see temp_b200.h)."""
+        """8 zeroed bytes for the grid barrier of the SIMT scan (D != 128; self-cleaning, see temp_b200.h)."""
         if getattr(self, "_barrier", None) is None:
             self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
         return self._barrier.data_ptr()
