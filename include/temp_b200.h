@@ -10,7 +10,9 @@
  *   - all floating point is fp32, all indices int32;
  *   - kernels are enqueued on the cudaStream_t passed in (as void*), never synchronise, never
  *     allocate; no global mutable state other than the thread-local last-error string;
- *   - every function returns TEMP_OK (0) or a negative TEMP_E* code; no exception crosses the ABI.
+ *   - every function returns TEMP_OK (0) or a negative TEMP_E* code; no exception crosses the ABI;
+ *   - one CUDA device per process (the launchers cache per-kernel attributes and occupancy once per process), which is
+ *     how the path is deployed: one process per GPU under torch.distributed.
  *
  * "packed rows": the nodes of all snapshot instances of a window batch are laid out back to back,
  * step-major (temp_b200/planner.py); a row index addresses one (instance, node).

@@ -151,6 +151,7 @@ class EncoderRuntime(object):
         self._chain_packed = {}
         self.fuse_scan = True      # consecutive GRU steps -> one persistent scan launch (chain-partitioned on the tcgen05 path)
         self._agg_rows = 1
+        self._live = []
         self.use_tc = True         # tcgen05 path where the shapes allow it (d == 128); False: fp32 SIMT kernels only
 
     # ---- plan upload -----------------------------------------------------------------------------
@@ -159,6 +160,7 @@ class EncoderRuntime(object):
         Returns name -> device pointer (int) of every plan array."""
         self._agg_rows = max(int(plan.R), 1)
         self._plan = plan
+        self._live = program.keepalive
         lay, total = plan.blob_layout()
         host = self.ws.pinned(tag + "_host", total)
         plan.to_blob(host.numpy())
@@ -183,7 +185,9 @@ class EncoderRuntime(object):
             a.weight = layer.weight.data_ptr()
             a.n_bases, a.si, a.so = layer.num_bases, layer.submat_in, layer.submat_out
             if self.use_tc and m.embed_size == 128:
-                a.agg_scratch = self.ws.get("agg", self._agg_rows * m.embed_size).data_ptr()
+                agg = self.ws.get("agg", self._agg_rows * m.embed_size)
+                self._live.append(agg)               # programs hold raw pointers: keep the buffer they were built on
+                a.agg_scratch = agg.data_ptr()
                 if "agg_rows" in dptr:          # work lists of the aggregation launch, cut to [row0, row1)
                     a.agg_lists = 1
                     for name in ("agg_rows", "agg_heavy"):
