@@ -556,23 +556,35 @@ class OracleModel:
 
     def train_loss(self, t_list: Sequence[int], negative_rate: int, num_pos_facts: int,
                    random_dropout: bool = False) -> Tensor:
-        """The training forward of models/DynamicRGCN.py:176-194 (GRRGCN / RRGCN) with dropout p = 0: history steps
+        """The training forward of models/DynamicRGCN.py:176-194 (GRRGCN / RRGCN) and models/BiDynamicRGCN.py:165-187
+        (BiGRRGCN / BiRRGCN) with dropout p = 0: history steps
         on full graphs (or np.random.choice 80 % edge subsets with --random-dropout), the final step on a 50 % edge
         subset with recomputed norms (DynamicRGCN.py:76-94), then per target graph the negative sampler on the FULL
         graph and the tail + head cross-entropy (TKG_Module.py:202-213).  Global NumPy / torch RNG order as in the
         reference."""
         cfg = self.cfg
-        assert not cfg.bidirectional and not cfg.attention and cfg.module != "SRGCN"
+        assert not cfg.attention and cfg.module != "SRGCN"
         L = cfg.seq_len
+        rate_hist = 0.8 if random_dropout else None
         tb = window_forward(t_list, L, self.times)
         ts = tb[-1]
         full_graphs = [self.gd[t] for t in ts]
-        hist, start = self._scan(tb, "forward", sample_rate=0.8 if random_dropout else None)
-        p1, p2, dt = self._gather_prev(full_graphs, hist, start, L - 1)
-        graphs = [sample_edges(g, 0.5) for g in full_graphs]
-        _, out = self.enc_recurrent(graphs, ts, [p1], [p2], [dt], "forward")
-        res = {"times": ts, "graphs": full_graphs, "hist": hist, "start": start,
-               "per_graph": list(out.split([g.num_nodes for g in full_graphs]))}
+        sizes = [g.num_nodes for g in full_graphs]
+        if cfg.bidirectional:                       # models/BiDynamicRGCN.py:165-174: forward scan, backward scan, centre
+            hist_f, start_f = self._scan(tb, "forward", sample_rate=rate_hist)
+            hist_b, start_b = self._scan(window_backward(t_list, L, self.times), "backward", sample_rate=rate_hist)
+            f1, f2, dtf = self._gather_prev(full_graphs, hist_f, start_f, L - 1)
+            b1, b2, dtb = self._gather_prev(full_graphs, hist_b, start_b, L - 1)
+            graphs = [sample_edges(g, 0.5) for g in full_graphs]
+            _, out = self.enc_recurrent(graphs, ts, [f1, b1], [f2, b2], [dtf, dtb], direction=None)
+            res = {"times": ts, "graphs": full_graphs, "hist_f": hist_f, "start_f": start_f, "hist_b": hist_b,
+                   "start_b": start_b, "per_graph": list(out.split(sizes))}
+        else:
+            hist, start = self._scan(tb, "forward", sample_rate=rate_hist)
+            p1, p2, dt = self._gather_prev(full_graphs, hist, start, L - 1)
+            graphs = [sample_edges(g, 0.5) for g in full_graphs]
+            _, out = self.enc_recurrent(graphs, ts, [p1], [p2], [dt], "forward")
+            res = {"times": ts, "graphs": full_graphs, "hist": hist, "start": start, "per_graph": list(out.split(sizes))}
         score = {"complex": score_complex, "distmult": score_distmult, "transE": score_transe}["complex"]
         rel = self.p["rel_embeds"]
         loss = torch.zeros(())

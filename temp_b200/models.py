@@ -244,9 +244,9 @@ class TKG_Module(nn.Module):
 
     def _forward_no_grad(self, t_list):
         if self.training:
-            if self.family != "recurrent" or self.bidirectional:
-                raise NotImplementedError("temp_b200: the training-mode edge sub-sampling is implemented for DynamicRGCN "
-                                          "(GRRGCN / RRGCN); call .eval() for the deterministic forward of this family")
+            if self.family != "recurrent":
+                raise NotImplementedError("temp_b200: the training-mode edge sub-sampling is implemented for the recurrent "
+                                          "families ((Bi)GRRGCN / (Bi)RRGCN); call .eval() for the deterministic forward")
             # (the self-loop dropout of models/RGCN.py:58-59 is not applied by the CUDA forward: parity holds at p = 0)
             res = self.encode(plan=self.plan(t_list, transform=self.train_edge_sampler()))
         else:

@@ -63,4 +63,7 @@ TRAIN_CASES = [
     dict(name="train_grrgcn_tiny_random_dropout", base="grrgcn_tiny_d128_last", seed=12, random_dropout=True),
     dict(name="train_rrgcn_tiny", base="rrgcn_tiny_d128_last", seed=13, random_dropout=False),
     dict(name="train_grrgcn_icews", base="grrgcn_icews_d128_L8", seed=5, random_dropout=True, negative_rate=20),
+    # bidirectional (models/BiDynamicRGCN.py:165-187): forward history, backward history, centre step
+    dict(name="train_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last", seed=21, random_dropout=False),
+    dict(name="train_bigrrgcn_tiny_random_dropout", base="bigrrgcn_tiny_d128_last", seed=22, random_dropout=True),
 ]
