@@ -215,6 +215,75 @@ class TKG_Module(nn.Module):
         ranks, loss = self.evaluate(batch_time, val=True)
         return OrderedDict(ranks=ranks, test_loss=loss, batch_time=batch_time)
 
+    def test_end(self, outputs):
+        """models/TKG_Module.py:116-131."""
+        mrr, h1, h3, h10 = self.get_metrics(torch.cat([x["ranks"] for x in outputs]))
+        res = {"mrr": mrr.item(), "avg_test_loss": float(np.mean([x["test_loss"] for x in outputs])), "hit_10": h10.item(),
+               "hit_3": h3.item(), "hit_1": h1.item()}
+        res["batch_times"] = [x["batch_time"] for x in outputs]
+        res["all_ranks"] = [x["ranks"] for x in outputs]
+        return res
+
+    # ---- data loaders (models/TKG_Module.py:166-200): batches of target timestamps -----------------------------------
+    def _dataloader(self, times):
+        from torch.utils.data import DataLoader, Dataset
+        from torch.utils.data.distributed import DistributedSampler
+
+        class TimeDataset(Dataset):                       # utils/dataset.py TimeDataset
+            def __init__(self, times):
+                self.times = times
+
+            def __len__(self):
+                return len(self.times)
+
+            def __getitem__(self, idx):
+                return self.times[idx]
+
+        dataset = TimeDataset(times)
+        sampler = DistributedSampler(dataset) if getattr(self, "use_ddp", False) else None
+        return DataLoader(dataset=dataset, batch_size=self.args.batch_size, shuffle=sampler is None, sampler=sampler,
+                          num_workers=0)
+
+    def train_dataloader(self):
+        return self._dataloader(self.total_time)
+
+    def val_dataloader(self):
+        return self._dataloader(self.total_time)
+
+    def test_dataloader(self):
+        return self._dataloader(self.total_time)
+
+    def _item_of(self, t) -> int:
+        """Batch position of timestamp ``t`` in the last evaluate_embed / train_embed result."""
+        res = getattr(self, "last_result", None)
+        t = int(t)
+        if res is None or t not in res.plan.final_times:
+            raise RuntimeError("temp_b200: get_all_embeds_Gt serves timestamps of the last evaluate_embed / train_embed "
+                               "call (the all-entity table is built from its compact window state)")
+        return res.plan.final_times.index(t)
+
+    @torch.no_grad()
+    def calc_metrics(self, per_graph_ent_embeds, g_list, t_list, *history):
+        """models/DynamicRGCN.py:196-220 / models/BiDynamicRGCN.py:189-209: filtered ranks + mean classification loss of
+        the given target graphs (their all-entity tables come from the last evaluate_embed / train_embed call)."""
+        from .evaluation import EvaluationFilter
+        if getattr(self, "evaluater", None) is None:
+            self.evaluater = EvaluationFilter(self.args, self.calc_score, self.graph_dict_train, self.graph_dict_val,
+                                              self.graph_dict_test)
+        dev = self.ent_embeds.device
+        ranks, losses = [], []
+        for g, t, ent_embed in zip(g_list, t_list, per_graph_ent_embeds):
+            if g is None or g.num_edges == 0:
+                continue
+            all_g = self.all_embeds(self.last_result, self._item_of(t))
+            src, dst = g.edges()
+            index_sample = torch.stack([src, g.edata["type_s"], dst]).transpose(0, 1).to(dev)
+            label = torch.ones(index_sample.shape[0], device=dev)
+            ranks.append(self.evaluater.calc_metrics_single_graph(ent_embed, self.rel_embeds, all_g, index_sample, g, t))
+            losses.append(self.link_classification_loss(ent_embed, self.rel_embeds, index_sample, label).item())
+        ranks = torch.cat(ranks) if ranks else torch.zeros(0, dtype=torch.long, device=dev)
+        return ranks, (float(np.mean(losses)) if losses else float("nan"))
+
     def validation_end(self, outputs):
         mrr, h1, h3, h10 = self.get_metrics(torch.cat([x["ranks"] for x in outputs]))
         return {"mrr": mrr, "avg_val_loss": np.mean([x["val_loss"] for x in outputs]), "hit_10": h10, "hit_3": h3,
@@ -338,6 +407,12 @@ class DynamicRGCN(TKG_Module):
         return res.per_graph, [graph_dict.get(t) for t in res.plan.final_times], time_list, hist, start
 
     @torch.no_grad()
+    def get_all_embeds_Gt(self, convoluted_embeds, g, t, *history):
+        """models/DynamicRGCN.py:56-64 / models/BiDynamicRGCN.py:102-112 (the reference passes its dense history tensors
+        as ``*history``; here the table comes from the compact state of the same evaluate_embed / train_embed call)."""
+        return self.all_embeds(self.last_result, self._item_of(t))
+
+    @torch.no_grad()
     def train_embed(self, t_list):
         """models/DynamicRGCN.py:146-154."""
         res = self.encode(t_list)
@@ -388,6 +463,11 @@ class StaticRGCN(TKG_Module):
 
     def plan(self, t_list, seq_len=None) -> WindowPlan:
         return plan_static(self.graph_dict_train, _as_int_list(t_list))
+
+    @torch.no_grad()
+    def get_all_embeds_Gt(self, t, g, convoluted_embeds):
+        """baselines/StaticRGCN.py:48-58 (argument order of the static model)."""
+        return self.all_embeds(self.last_result, self._item_of(t))
 
     @torch.no_grad()
     def evaluate_embed(self, t_list, val=True):

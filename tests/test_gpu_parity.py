@@ -270,3 +270,20 @@ def test_autograd_fallback_gradients_match_oracle(tc):
         checked += 1
     assert checked >= 6
     torch.optim.Adam(model.parameters(), lr=1e-3).step()       # a main.py-style update runs
+
+
+def test_reference_style_eval_calls_agree_with_the_fast_entry():
+    """evaluate_embed -> get_all_embeds_Gt / calc_metrics with the reference's call shapes (models/DynamicRGCN.py:118-144,
+    196-220) give what evaluate() / all_embeds() give."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    model = product_model(case)
+    tl = torch.tensor(case["t_list"])
+    per_graph, graphs, time_list, hist, start = model.evaluate_embed(tl, val=True)
+    times = time_list[-1]
+    L = model.test_seq_len
+    table = model.get_all_embeds_Gt(per_graph[1], graphs[1], times[1], hist[1][0], hist[1][1], L - 1 - start[1])
+    assert torch.equal(table, model.all_embeds(model.last_result, 1))
+    ranks, loss = model.calc_metrics(per_graph, graphs, times, hist, start, L - 1)
+    ranks2, loss2 = model.evaluate(tl, val=True)
+    assert torch.equal(ranks, ranks2) and abs(loss - loss2) < 1e-6

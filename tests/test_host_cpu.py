@@ -317,3 +317,25 @@ def test_native_planner_equals_python_planner_on_synthetic_shapes(shape, L, B, b
         t_list = [int(store.times[i]) for i in rng.choice(np.arange(0, hi + 1), size=B, replace=False)]
         _plans_equal(plan_window_native(store.train, t_list, L, bidirectional=bi, attention=att),
                      plan_window(store.train, t_list, L, bidirectional=bi, attention=att))
+
+
+def test_model_shell_answers_the_reference_hook_names_and_loaders():
+    """The hook / loader surface PL and test.py call on a TKG_Module (models/TKG_Module.py:43-200) exists on the shells;
+    the loaders yield batches of ``batch_size`` target timestamps."""
+    from tests.helpers import CASE_BY_NAME, product_args
+    from temp_b200.models import build_module
+    case = CASE_BY_NAME["grrgcn_tiny_d128_last"]
+    store = product_store(case["dataset"])
+    args = product_args(case)
+    args.batch_size = 4
+    model = build_module(args, store.num_ents, store.num_rels, store.train, store.valid, store.test)
+    for name in ("forward", "evaluate", "evaluate_embed", "train_embed", "get_all_embeds_Gt", "calc_metrics", "training_step",
+                 "validation_step", "test_step", "validation_end", "test_end", "configure_optimizers", "train_dataloader",
+                 "val_dataloader", "test_dataloader", "train_link_prediction", "link_classification_loss",
+                 "get_batch_graph_list", "get_metrics"):
+        assert callable(getattr(model, name)), name
+    batches = list(model.val_dataloader())
+    assert sum(int(b.numel()) for b in batches) == len(store.times) and all(int(b.numel()) <= 4 for b in batches)
+    assert sorted(int(t) for b in batches for t in b) == sorted(int(t) for t in store.times)
+    out = model.test_end([{"ranks": torch.tensor([1, 2, 10]), "test_loss": 0.5, "batch_time": batches[0]}])
+    assert abs(out["mrr"] - (1 + 0.5 + 0.1) / 3) < 1e-6 and out["hit_1"] == pytest.approx(1 / 3)
