@@ -404,6 +404,27 @@ def main():
         dist.barrier()
     clocks = sampler.stop()
 
+    # ---- the same through the user-facing call, nothing pre-built: model.encode(t_list) plans the window batch (native
+    # planner), builds the launch program, copies the plan, runs, and the result is read back to pinned host memory ----
+    api_ms = None
+    if world == 1:
+        nf_max = max(r[4] for r in results) // (4 * WORKLOAD["D"])
+        api_out = torch.empty(nf_max, WORKLOAD["D"], dtype=torch.float32, pin_memory=True)
+        reps = min(K, 60)
+        for i in range(3):
+            model.encode(t_lists[i % len(t_lists)])
+        torch.cuda.synchronize()
+        t_api = 0.0
+        for i in range(reps):
+            flush.fill_(float(i))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r_ = model.encode(t_lists[i % len(t_lists)])
+            api_out[:r_.out.shape[0]].copy_(r_.out, non_blocking=True)
+            torch.cuda.synchronize()
+            t_api += time.perf_counter() - t0
+        api_ms = 1e3 * t_api / reps
+
     # ---- every kernel of the step timed alone with CUDA events on its stream (roofline) -------------------------
     D = WORKLOAD["D"]
     res0 = results[0][0]
@@ -449,7 +470,12 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(bench_config(world), exchange=exchange),
             "e2e": {"value": tot_edges / max_e2e, "unit": "edges/s", "h2d_bytes_per_step": int(results[0][3]),
                     "d2h_bytes_per_step": int(results[0][4]), "ms_per_step": 1e3 * max_e2e / K,
-                    "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms},
+                    "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms,
+                    "encode_call_ms_per_step": api_ms,
+                    "encode_call_edges_per_s": (edges_local / K) / (api_ms * 1e-3) if api_ms else None,
+                    "encode_call_note": "model.encode(t_list) with NOTHING pre-built: window planning + launch-program "
+                                        "construction in python + H2D + kernels + D2H (the reference also batches its "
+                                        "graphs per step inside its forward)"},
             "gpu_launches": int(launches),
             "launches_per_step": results[0][0].program.kernel_count(),
             "cuda_graph": "one graph per launch program (%d of %d captured)" % (graphed, 2 * len(results)) if graphed else "off",

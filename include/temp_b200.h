@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 11
+#define TEMP_ABI_VERSION 12
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -289,6 +289,10 @@ TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const
 void temp_plan_destroy(TempPlan* plan);
 int temp_plan_counts(const TempPlan* plan, TempPlanCounts* out);
 const void* temp_plan_array(const TempPlan* plan, int32_t which, int64_t* n_bytes);
+/* Device blob of a plan: arrays TEMP_PLAN_ENT_ID .. TEMP_PLAN_AGG_HEAVY back to back, starts aligned to `align` bytes;
+ * offsets[i] = -1 for arrays the plan does not have.  Returns the blob size (negative on bad arguments).           */
+int64_t temp_plan_blob_layout(const TempPlan* plan, int64_t* offsets, int64_t* sizes, int32_t align);
+int temp_plan_write_blob(const TempPlan* plan, uint8_t* dst, int32_t align);
 
 int temp_abi_version(void);
 const char* temp_last_error_string(void);

@@ -36,6 +36,7 @@ struct TempPlan {
   std::vector<int32_t> last_f, last_b;    // per item: instance index of the last history step, -1 = none
   std::vector<int32_t> steps_f, steps_b;  // [L-1][B] instance index per (step, window row j), -1 = none
   TempPlanCounts c;
+  bool bi = false, attention = false;
 };
 
 namespace {
@@ -287,6 +288,8 @@ TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const
     n_parts = static_cast<int32_t>(parts.size());
   }
 
+  P->bi = b.bi;
+  P->attention = attention != 0;
   TempPlanCounts& c = P->c;
   memset(&c, 0, sizeof(c));
   c.rows = b.R;
@@ -347,6 +350,42 @@ const void* temp_plan_array(const TempPlan* plan, int32_t which, int64_t* n_byte
 #undef TEMP_ARR
   *n_bytes = n;
   return p;
+}
+
+// The device blob of a plan: arrays TEMP_PLAN_ENT_ID .. TEMP_PLAN_AGG_HEAVY back to back, each start aligned to `align`
+// bytes (the layout temp_b200/planner.py::WindowPlan.blob_layout produces); offsets[i] = -1 for arrays the plan does not
+// have (prev_b / dt_b of uni-directional plans, slot_row without attention, scan_parts with it).
+int64_t temp_plan_blob_layout(const TempPlan* plan, int64_t* offsets, int64_t* sizes, int32_t align) {
+  if (plan == nullptr || offsets == nullptr || sizes == nullptr || align <= 0) return -1;
+  int64_t off = 0;
+  for (int32_t i = 0; i <= TEMP_PLAN_AGG_HEAVY; ++i) {
+    const bool absent = ((i == TEMP_PLAN_PREV_B || i == TEMP_PLAN_DT_B) && !plan->bi) ||
+                        (i == TEMP_PLAN_SLOT_ROW && !plan->attention) || (i == TEMP_PLAN_SCAN_PARTS && plan->attention);
+    int64_t nb = 0;
+    if (absent || temp_plan_array(plan, i, &nb) == nullptr && nb != 0) {
+      offsets[i] = -1;
+      sizes[i] = 0;
+      continue;
+    }
+    temp_plan_array(plan, i, &nb);
+    offsets[i] = off;
+    sizes[i] = nb;
+    off = (off + nb + align - 1) / align * align;
+  }
+  return off;
+}
+
+int temp_plan_write_blob(const TempPlan* plan, uint8_t* dst, int32_t align) {
+  if (plan == nullptr || dst == nullptr) return TEMP_EINVAL;
+  int64_t offsets[TEMP_PLAN_AGG_HEAVY + 1], sizes[TEMP_PLAN_AGG_HEAVY + 1];
+  if (temp_plan_blob_layout(plan, offsets, sizes, align) < 0) return TEMP_EINVAL;
+  for (int32_t i = 0; i <= TEMP_PLAN_AGG_HEAVY; ++i) {
+    if (offsets[i] < 0 || sizes[i] == 0) continue;
+    int64_t nb = 0;
+    const void* src = temp_plan_array(plan, i, &nb);
+    memcpy(dst + offsets[i], src, static_cast<size_t>(nb));
+  }
+  return TEMP_OK;
 }
 
 }  // extern "C"

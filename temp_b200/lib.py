@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -116,7 +116,8 @@ EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "te
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
            "temp_program_kernel_count", "temp_score_loss_fwd", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
-           "temp_plan_array", "temp_graph_create", "temp_graph_launch", "temp_graph_destroy", "temp_peer_barrier")
+           "temp_plan_array", "temp_graph_create", "temp_graph_launch", "temp_graph_destroy", "temp_peer_barrier", "temp_plan_blob_layout",
+           "temp_plan_write_blob")
 
 _lib = None
 
@@ -158,6 +159,9 @@ def load(path: Optional[str] = None):
     lib.temp_plan_counts.argtypes = [_p, C.POINTER(PlanCounts)]
     lib.temp_plan_array.argtypes = [_p, _i32, C.POINTER(C.c_int64)]
     lib.temp_plan_array.restype = _p
+    lib.temp_plan_blob_layout.argtypes = [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i32]
+    lib.temp_plan_blob_layout.restype = C.c_int64
+    lib.temp_plan_write_blob.argtypes = [_p, _p, _i32]
     lib.temp_packed_weights_bytes.argtypes = [_i32, _i32]
     lib.temp_packed_weights_bytes.restype = C.c_int64
     lib.temp_pack_weights.argtypes = [_p, _i32, _i32, _p, _p]

@@ -361,6 +361,91 @@ _KINDS = ("hist_f", "hist_b", "final")
 _DIRS = ("f", "b", "c")
 
 
+class NativeWindowPlan(WindowPlan):
+    """A WindowPlan whose arrays live in the native planner's memory: the device blob is written straight from C
+    (``to_blob``), numpy views are materialised only when somebody asks for an array by name (tests, the dense-history
+    API, the autograd fallback)."""
+
+    _LAZY = {name: i for i, name in enumerate(("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a",
+                                               "dt_a", "prev_b", "dt_b", "slot_row", "scan_parts", "agg_rows", "agg_heavy"))}
+
+    def __init__(self, handle, lib_mod):
+        self.__dict__["_handle"] = handle
+        self.__dict__["_lib"] = lib_mod
+        WindowPlan.__init__(self)
+        for name in self.ARRAYS:               # WindowPlan.__init__ set them to None: make them lazy again
+            self.__dict__.pop(name, None)
+        self._absent = set()
+
+    def __del__(self):
+        h = self.__dict__.get("_handle")
+        if h:
+            try:
+                self._lib.load().temp_plan_destroy(h)
+            except Exception:
+                pass
+            self.__dict__["_handle"] = None
+
+    def _fetch(self, which, dtype):
+        import ctypes as C
+        nb = C.c_int64()
+        ptr = self._lib.load().temp_plan_array(self._handle, which, C.byref(nb))
+        n = nb.value // 4
+        if not n:
+            return np.zeros(0, dtype=dtype)
+        ct = C.c_float if dtype == np.float32 else C.c_int32
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+    def __setattr__(self, name, value):        # an array replaced from python (e.g. the rank-major partition table of a
+        if name in type(self)._LAZY and "_absent" in self.__dict__:   # sharded forward) overrides the native copy
+            self.__dict__.setdefault("_dirty", set()).add(name)
+        self.__dict__[name] = value
+
+    def __getattr__(self, name):               # only called when the attribute is not in __dict__
+        lazy = type(self)._LAZY
+        if name in lazy:
+            if name in self.__dict__.get("_absent", ()):
+                val = None
+            else:
+                val = self._fetch(lazy[name], _PLAN_DTYPES.get(name, np.int32))
+                if name in ("agg_rows", "agg_heavy"):
+                    val = val.reshape(-1, 3)
+                elif name == "slot_row":
+                    val = val.reshape(self.final.row1 - self.final.row0, self.n_slots)
+                elif name == "scan_parts":
+                    val = val.reshape(self._n_parts, len(self.segments), 2)
+            self.__dict__[name] = val
+            return val
+        if name in ("agg_rows_ids", "agg_heavy_ids"):
+            val = getattr(self, name[:-4])[:, 0].astype(np.int64)
+            self.__dict__[name] = val
+            return val
+        raise AttributeError(name)
+
+    def blob_layout(self):
+        import ctypes as C
+        n = len(self._LAZY)
+        offs, sizes = (C.c_int64 * n)(), (C.c_int64 * n)()
+        total = self._lib.load().temp_plan_blob_layout(self._handle, offs, sizes, _ALIGN)
+        if total < 0:
+            raise RuntimeError("temp_b200: temp_plan_blob_layout failed")
+        lay = {name: (int(offs[i]), int(sizes[i])) for name, i in self._LAZY.items() if offs[i] >= 0}
+        return lay, int(total)
+
+    def to_blob(self, out: Optional[np.ndarray] = None):
+        lay, total = self.blob_layout()
+        if out is None:
+            out = np.zeros(total, dtype=np.uint8)
+        assert out.nbytes >= total and out.flags["C_CONTIGUOUS"]
+        self._lib.check(self._lib.load().temp_plan_write_blob(self._handle, out.ctypes.data, _ALIGN), "temp_plan_write_blob")
+        for name in self.__dict__.get("_dirty", ()):
+            arr = self.__dict__[name]
+            off, nb = lay[name]
+            assert arr is not None and arr.nbytes == nb, "a replaced plan array must keep its size"
+            out[off:off + nb] = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        return out, lay, total
+
+
 def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len: int, bidirectional: bool = False,
                        attention: bool = False) -> WindowPlan:
     """``plan_window`` through the native planner of libtemp_b200.so (no ``transform``: the training-mode edge
@@ -375,51 +460,33 @@ def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], s
                                 AGG_HEAVY_DEGREE)
     if not handle:
         raise RuntimeError("temp_b200: temp_plan_window rejected its arguments")
-    try:
-        cnt = lib.PlanCounts()
-        lib.check(L.temp_plan_counts(handle, C.byref(cnt)), "temp_plan_counts")
-        arr = {}
-        nb = C.c_int64()
-        for which, name in enumerate(lib.PLAN_ARRAYS):
-            ptr = L.temp_plan_array(handle, which, C.byref(nb))
-            dt = _PLAN_DTYPES.get(name, np.int32)
-            n = nb.value // 4
-            arr[name] = (np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int32 if dt == np.int32 else C.c_float)), shape=(n,)).copy()
-                         if n else np.zeros(0, dtype=dt))
-    finally:
-        L.temp_plan_destroy(handle)
-    plan = WindowPlan()
+    plan = NativeWindowPlan(handle, lib)
+    cnt = lib.PlanCounts()
+    lib.check(L.temp_plan_counts(handle, C.byref(cnt)), "temp_plan_counts")
     plan.seq_len, plan.batch, plan.bidirectional = int(seq_len), B, bool(bidirectional)
     plan.R, plan.E = int(cnt.rows), int(cnt.edges)
-    for name in ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a"):
-        setattr(plan, name, arr[name])
-    if bidirectional:
-        plan.prev_b, plan.dt_b = arr["prev_b"], arr["dt_b"]
-    insts_raw = arr["instances"].reshape(-1, 7)
-    insts = [Instance(int(r[0]), int(r[1]), _DIRS[int(r[2])], int(r[3]), int(r[4]), int(r[5]), graph_dict[times[int(r[6])]])
-             for r in insts_raw]
-    for r in arr["segments"].reshape(-1, 6):
-        plan.segments.append(Segment(_KINDS[int(r[0])], int(r[1]), int(r[2]), int(r[3]), insts[int(r[4]):int(r[5])]))
+    plan._n_parts = int(cnt.n_parts)
+    if not bidirectional:
+        plan._absent.update(("prev_b", "dt_b"))
+    plan._absent.add("scan_parts" if attention else "slot_row")
+    which = {name: i for i, name in enumerate(lib.PLAN_ARRAYS)}
+    insts_raw = plan._fetch(which["instances"], np.int32).reshape(-1, 7).tolist()
+    insts = [Instance(r[0], r[1], _DIRS[r[2]], r[3], r[4], r[5], graph_dict[times[r[6]]]) for r in insts_raw]
+    for r in plan._fetch(which["segments"], np.int32).reshape(-1, 6).tolist():
+        plan.segments.append(Segment(_KINDS[r[0]], r[1], r[2], r[3], insts[r[4]:r[5]]))
     for inst in plan.segments[-1].instances:
         plan.final_times.append(inst.time)
         plan.final_sizes.append(inst.n)
         plan.final_snapshots.append(inst.snapshot)
     pick = lambda a: [insts[i] if i >= 0 else None for i in a.tolist()]
-    plan.last_hist_f = pick(arr["last_f"])
-    plan.last_hist_b = pick(arr["last_b"]) if bidirectional else [None] * B
-    for name in ("agg_rows", "agg_heavy"):
-        setattr(plan, name, arr[name].reshape(-1, 3))
-        setattr(plan, name + "_ids", arr[name].reshape(-1, 3)[:, 0].astype(np.int64))
+    plan.last_hist_f = pick(plan._fetch(which["last_f"], np.int32))
+    plan.last_hist_b = pick(plan._fetch(which["last_b"], np.int32)) if bidirectional else [None] * B
     if attention:
         plan.n_slots = int(cnt.n_slots)
-        nf = plan.final.row1 - plan.final.row0
-        plan.slot_row = arr["slot_row"].reshape(nf, plan.n_slots)
         to_dicts = lambda a: [{j: insts[i] for j, i in enumerate(row) if i >= 0} for row in a.reshape(-1, B).tolist()] \
             if a.size else [dict() for _ in range(max(int(seq_len) - 1, 0))]
-        plan.steps_f = to_dicts(arr["steps_f"])
-        plan.steps_b = to_dicts(arr["steps_b"]) if bidirectional else []
-    else:
-        plan.scan_parts = arr["scan_parts"].reshape(int(cnt.n_parts), len(plan.segments), 2)
+        plan.steps_f = to_dicts(plan._fetch(which["steps_f"], np.int32))
+        plan.steps_b = to_dicts(plan._fetch(which["steps_b"], np.int32)) if bidirectional else []
     return plan
 
 
