@@ -287,3 +287,31 @@ def test_reference_style_eval_calls_agree_with_the_fast_entry():
     ranks, loss = model.calc_metrics(per_graph, graphs, times, hist, start, L - 1)
     ranks2, loss2 = model.evaluate(tl, val=True)
     assert torch.equal(ranks, ranks2) and abs(loss - loss2) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8"])
+def test_fused_peer_push_and_barrier_on_one_gpu(name):
+    """The fused all-gather path with this GPU as its only peer: the scan step that writes the final states also stores
+    them into the 'peer' slab (TempGruScanArgs.push_*), and temp_peer_barrier signals / waits on its own flag."""
+    from tests.helpers import CASE_BY_NAME
+    from temp_b200 import lib
+    case = CASE_BY_NAME[name]
+    model = product_model(case)
+    res = model.encode(case["t_list"])
+    want = res.out.clone()
+    fin = res.plan.final
+    nf, D = fin.row1 - fin.row0, model.embed_size
+    slab = torch.full((2, nf + 3, D), -5.0, device="cuda")
+    ptrs = torch.tensor([slab.data_ptr()], dtype=torch.int64, device="cuda")
+    res.program.enable_peer_push(ptrs.data_ptr(), 1, (nf + 3) * D, fin.row0, fin.row1)     # second slab
+    flags = torch.zeros(32, dtype=torch.int32, device="cuda")
+    flag_ptrs = torch.tensor([flags.data_ptr()], dtype=torch.int64, device="cuda")
+    for seq in (1, 2):
+        res.out.zero_()
+        res.program.run()
+        lib.check(lib.load().temp_peer_barrier(flags.data_ptr(), flag_ptrs.data_ptr(), 1, 0, seq, lib.current_stream()),
+                  "temp_peer_barrier")
+        torch.cuda.synchronize()
+        assert int(flags[0]) == seq
+        assert torch.equal(res.out, want) and torch.equal(slab[1, :nf], want)
+        assert bool((slab[0] == -5.0).all()) and bool((slab[1, nf:] == -5.0).all())
