@@ -424,15 +424,22 @@ class EncoderRuntime(object):
                     w, b = self._wih("layer_2", rnns)
                     prog.add(lib.OP_LAYER, self._layer(l2, mine(rows), dptr, x=h1, x_is_embed=False, act=relu2,
                                                        terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, GL)))
+                protos = {}          # one fully built GruArgs per (cell, variant); the steps copy it and patch the rows
                 for g, seg in enumerate(plan.segments):
-                    rows = (seg.row0, seg.row1)
                     dirs = dirs_of(seg)
                     for j, d in enumerate(dirs):
-                        name, rnn = rnn_of(l2, d)
                         pv, dt = prev_ptrs(d, seg)
-                        prog.add(lib.OP_GRU, self._gru(l2, rnn, name, rows, gi=gi, gi_ld=GL, gi_off=j * G, state=S,
-                                                       prev=pv, dt=dt, out=S, te=use_te and j == len(dirs) - 1,
-                                                       accumulate=j > 0, dptr=dptr, layer_name="layer_2", part_col=g))
+                        key = (d, j, len(dirs), pv, dt)
+                        proto = protos.get(key)
+                        if proto is None:
+                            name, rnn = rnn_of(l2, d)
+                            proto = self._gru(l2, rnn, name, (0, 0), gi=gi, gi_ld=GL, gi_off=j * G, state=S, prev=pv, dt=dt,
+                                              out=S, te=use_te and j == len(dirs) - 1, accumulate=j > 0, dptr=dptr,
+                                              layer_name="layer_2")
+                            protos[key] = proto
+                        a = lib.GruArgs.from_buffer_copy(proto)
+                        a.row0, a.row1, a.part_col = seg.row0, seg.row1, g
+                        prog.add(lib.OP_GRU, a)
             else:
                 for seg in plan.segments:
                     rec_layer(l2, "layer_2", (seg.row0, seg.row1), seg, h1, False, None, S, S, relu2, use_te)
