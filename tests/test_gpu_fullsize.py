@@ -25,6 +25,12 @@ CONFIGS = [
     ("config3b_bigrrgcn_icews0515_d128", "BiGRRGCN", "icews05-15", 128, 128, 8, 8, {}),
     ("config4_bisargcn_icews14_L8", "BiSARGCN", "icews14", 128, 128, 8, 8, {}),
     ("config5_grrgcn_gdelt_L15", "GRRGCN", "gdelt", 128, 128, 15, 2, {}),
+    # variants of the shipped flags on the tensor-core path (D = 128)
+    ("grrgcn_icews14_type1", "GRRGCN", "icews14", 128, 128, 8, 8, {"type1": True}),
+    ("grrgcn_icews14_lambda_note", "GRRGCN", "icews14", 128, 128, 8, 8, {"learnable_lambda": True, "use_time_embedding": False}),
+    ("bigrrgcn_icews14_type1", "BiGRRGCN", "icews14", 128, 128, 4, 5, {"type1": True}),
+    ("rrgcn_icews14", "RRGCN", "icews14", 128, 128, 8, 8, {}),
+    ("grrgcn_icews14_all_layers_recurrent", "GRRGCN", "icews14", 128, 128, 6, 4, {"rec_only_last_layer": False}),
 ]
 
 
@@ -50,18 +56,35 @@ def _build(cfg, scale=1):
     t_list = [store.times[lo + (i * (hi - lo)) // B] for i in range(B)] if module != "SRGCN" else store.times[2:2 + B]
     t_list = sorted(set(int(t) for t in t_list))
     ocfg = orc.OracleConfig(module=module, num_ents=store.num_ents, num_rels=store.num_rels, num_times=len(store.times),
-                            embed_size=D, n_bases=nb, seq_len=L, rec_only_last_layer=True, use_time_embedding=True)
+                            embed_size=D, n_bases=nb, seq_len=L, rec_only_last_layer=extra.get("rec_only_last_layer", True),
+                            use_time_embedding=extra.get("use_time_embedding", True), type1=extra.get("type1", False),
+                            learnable_lambda=extra.get("learnable_lambda", False))
     gd = {t: orc.SnapGraph(ids=g.node_ids, src=g.src, dst=g.dst, rel=g.rel, norm=g.norm, time=t)
           for t, g in store.train.items()}
     oracle = orc.OracleModel(ocfg, {k: v.detach().float().cpu() for k, v in model.state_dict().items()}, gd)
     return model, oracle, t_list
 
 
-def _close(got, want):
+def _close(got, want, tol=RTOL):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     scale = max(np.abs(want).max(), 1e-30)
     err = np.abs(got - want).max() / scale
-    assert err < RTOL, "max rel-to-scale err %.3e" % err
+    assert err < tol, "max rel-to-scale err %.3e (tolerance %.1e)" % (err, tol)
+
+
+def _conditioning_tolerance(oracle, t_list, ref_rows):
+    """1e-4, unless fp32 arithmetic itself cannot reach it on this input: the oracle is evaluated once more in float64 and
+    the tolerance is widened to 4x the fp32-vs-fp64 discrepancy of the ORACLE (the --type1 cell with its torch.randn
+    parameters is ill-conditioned over 8 steps; every well-conditioned configuration keeps 1e-4)."""
+    torch.set_default_dtype(torch.float64)
+    try:
+        o64 = type(oracle)(oracle.cfg, {k: v.double() for k, v in oracle.p.items()}, oracle.gd)
+        with torch.no_grad():
+            r64 = torch.cat(o64.evaluate_embed(t_list)["per_graph"]).numpy()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    noise = np.abs(ref_rows.astype(np.float64) - r64).max() / max(np.abs(r64).max(), 1e-30)
+    return max(RTOL, 4.0 * float(noise))
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
@@ -72,7 +95,9 @@ def test_baseline_config_matches_oracle_and_invariants(cfg):
     with torch.no_grad():
         ref = oracle.evaluate_embed(t_list)
     assert res.plan.final_times == [int(t) for t in ref["times"]]
-    _close(got.cpu().numpy(), torch.cat(ref["per_graph"]).numpy())
+    want = torch.cat(ref["per_graph"]).numpy()
+    tol = _conditioning_tolerance(oracle, t_list, want) if cfg[7].get("type1") else RTOL
+    _close(got.cpu().numpy(), want, tol)
     # determinism, and independence of the order of the target timestamps (windows are sorted by the planner)
     again = model.encode(list(reversed(t_list)))
     if cfg[1] == "SRGCN":                          # the static model keeps the caller's order (StaticRGCN.py:23-28)
@@ -83,7 +108,7 @@ def test_baseline_config_matches_oracle_and_invariants(cfg):
     i = len(res.plan.final_times) // 2
     table = model.all_embeds(model.encode(t_list), i)
     with torch.no_grad():
-        _close(table.cpu().numpy(), oracle.all_embeds(ref, i).numpy())
+        _close(table.cpu().numpy(), oracle.all_embeds(ref, i).numpy(), tol)
     ids = torch.from_numpy(res.plan.final_snapshots[i].node_ids).cuda()
     assert torch.equal(table[ids], res.per_graph[i])
 
@@ -91,7 +116,7 @@ def test_baseline_config_matches_oracle_and_invariants(cfg):
 def test_gdelt_shaped_heavy_rows_use_the_block_path():
     """GDELT-shaped snapshots have in-degrees in the hundreds: the aggregation work lists must route them to the
     block-per-row path and the sum must stay within tolerance of the edge-ordered oracle sum."""
-    cfg = CONFIGS[-1]
+    cfg = CONFIGS[5]
     model, oracle, t_list = _build(cfg)
     plan = model.plan(t_list)
     deg = np.diff(plan.row_ptr)

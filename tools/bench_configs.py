@@ -15,7 +15,7 @@ from tests import test_gpu_fullsize as T
 
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 torch.set_num_threads(os.cpu_count() or 1)
-for cfg in T.CONFIGS:
+for cfg in T.CONFIGS[:6]:
     model, oracle, t_list = T._build(cfg)
     res = model.encode(t_list)
     torch.cuda.synchronize()
