@@ -124,8 +124,8 @@ def test_gdelt_shaped_heavy_rows_use_the_block_path():
     assert plan.agg_rows.shape[0] == int(((deg > 0) & (deg <= 8)).sum())
 
 
-@pytest.mark.parametrize("cfg_index,scale", [(1, 6), (3, 10), (5, 8)], ids=["grrgcn_icews14_x6", "bigrrgcn_icews0515_x10",
-                                                                           "grrgcn_gdelt_x8"])
+@pytest.mark.parametrize("cfg_index,scale", [(1, 6), (3, 10), (5, 8)],
+                         ids=["grrgcn_icews14_x6", "bigrrgcn_icews0515_x10", "grrgcn_gdelt_x8"])
 def test_scaled_shapes_with_many_partitions_per_cluster(cfg_index, scale):
     """Shapes with far more chain partitions than clusters: a cluster then walks several partitions in step-major order
     with the next tile step's previous-state rows and input gates fetched ahead (the path the x16 roofline numbers of
@@ -139,3 +139,18 @@ def test_scaled_shapes_with_many_partitions_per_cluster(cfg_index, scale):
         ref = oracle.evaluate_embed(t_list)
     _close(got.cpu().numpy(), torch.cat(ref["per_graph"]).numpy())
     assert torch.equal(got, model.encode(t_list).out)
+
+
+def test_scan_walks_more_than_32_partitions_per_cluster_in_rounds():
+    """A partition table with far more than 32 partitions per cluster (the same batch re-partitioned with an 8-row tile):
+    the scan kernel then takes its partitions in rounds of 32; the result does not depend on the partitioning."""
+    from temp_b200.planner import chain_partitions, plan_window
+    model, oracle, t_list = _build(CONFIGS[1], scale=4)
+    want = model.encode(t_list).out.clone()
+    plan = plan_window(model.graph_dict_train, t_list, model.train_seq_len)       # the python planner: arrays are plain numpy
+    plan.scan_parts = chain_partitions(plan, tile=8)
+    assert plan.scan_parts.shape[0] > 32 * 37
+    got = model.encode(plan=plan).out
+    assert torch.equal(got, want)
+    with torch.no_grad():
+        _close(got.cpu().numpy(), torch.cat(oracle.evaluate_embed(t_list)["per_graph"]).numpy())
