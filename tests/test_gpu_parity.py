@@ -315,3 +315,36 @@ def test_fused_peer_push_and_barrier_on_one_gpu(name):
         assert int(flags[0]) == seq
         assert torch.equal(res.out, want) and torch.equal(slab[1, :nf], want)
         assert bool((slab[0] == -5.0).all()) and bool((slab[1, nf:] == -5.0).all())
+
+
+def test_layer_without_aggregation_work_lists_and_transpose_entry():
+    """Direct users of the C ABI may call temp_rgcn_layer_fwd without the planner's work lists (every row is then tested
+    through row_ptr) -- same result; temp_transpose writes the [in, out] weight layout the kernels consume."""
+    import ctypes as C
+    from tests.helpers import CASE_BY_NAME
+    from temp_b200 import lib
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    model = product_model(case)
+    res = model.encode(case["t_list"])
+    want = res.out.clone()
+    n_layers = 0
+    for op in res.program.ops:
+        if op.kind == lib.OP_LAYER and op.u.layer.agg_lists:
+            op.u.layer.agg_lists = 0
+            op.u.layer.agg_rows, op.u.layer.agg_heavy = None, None
+            n_layers += 1
+    assert n_layers == 2
+    res.program._arr = None
+    res.out.zero_()
+    res.program.run()
+    torch.cuda.synchronize()
+    # not bit-identical: without the lists a high in-degree row is summed by ONE warp in edge order, with them by 8 warps in
+    # chunk order (both deterministic)
+    _close(res.out.cpu().numpy(), want.cpu().numpy())
+    assert float((res.out - want).abs().max()) < 1e-5 * float(want.abs().max())
+    w = torch.randn(37, 53, device="cuda")
+    out = torch.zeros(53, 40, device="cuda")
+    lib.check(lib.load().temp_transpose(C.c_void_p(w.data_ptr()), 37, 53, C.c_void_p(out.data_ptr()), 40,
+                                        C.c_void_p(lib.current_stream())), "temp_transpose")
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :37], w.t()) and bool((out[:, 37:] == 0).all())
