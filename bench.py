@@ -476,7 +476,7 @@ def main():
                     "encode_call_note": "model.encode(t_list) with NOTHING pre-built: window planning + launch-program "
                                         "construction in python + H2D + kernels + D2H (the reference also batches its "
                                         "graphs per step inside its forward)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) + (K if symm_hdl is not None else 0),   # + the peer-barrier launch per step at N > 1
             "launches_per_step": results[0][0].program.kernel_count(),
             "cuda_graph": "one graph per launch program (%d of %d captured)" % (graphed, 2 * len(results)) if graphed else "off",
             "clocks": clocks,
