@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--d2h-copy", action="store_true", help="e2e arm: cudaMemcpyAsync of the result after the kernels instead "
+                                                            "of stores to pinned host memory from inside the scan kernel")
     ap.add_argument("--graph", action="store_true", help="one CUDA graph per launch program instead of direct launches "
                                                          "(measured: no gain, the step is bound on the device)")
     ap.add_argument("--multimem", action="store_true", help="N > 1: NVLS multimem.st instead of one store per peer (measured "
@@ -255,7 +257,8 @@ def main():
         d2h.kind = lib.OP_D2H
         d2h.u.copy = lib.CopyArgs(host_out.data_ptr(), res.out.data_ptr(), nf * WORKLOAD["D"] * 4)
         e2e_prog = lib.Program()
-        e2e_prog.ops = [h2d] + list(res.program.ops) + [d2h]
+        # own copies of the ops: the e2e program gets the host buffer as an extra "peer" of the fused all-gather below
+        e2e_prog.ops = [h2d] + [lib.Op.from_buffer_copy(o) for o in res.program.ops] + ([d2h] if args.d2h_copy else [])
         e2e_prog.keepalive = list(res.program.keepalive) + [host_out]
         # make the plan resident for the device-timed arm
         up = lib.Program()
@@ -355,6 +358,27 @@ def main():
         if world > 1:
             gather_states(results[i % len(results)][0])
 
+    # e2e arm: the final states reach the pinned host buffer from INSIDE the scan kernel (the host buffer is one more
+    # "peer" of the fused all-gather: UVA stores over PCIe during the last scan step) instead of a device-to-host copy
+    # after the kernels; --d2h-copy restores the copy
+    if not args.d2h_copy:
+        D = WORKLOAD["D"]
+        for k, (res, e2e_prog, host_out, _, _) in enumerate(results):
+            fin = res.plan.final
+            if symm_hdl is not None:
+                off = ((k & 1) * world + rank) * max_rows * D
+                ptr_list = [int(p) for p in symm_hdl.buffer_ptrs] + [host_out.data_ptr() - 4 * off]
+            else:
+                off = 0
+                ptr_list = [host_out.data_ptr()]
+            ptr_t = torch.tensor(ptr_list, dtype=torch.int64, device=dev)
+            e2e_prog.keepalive.append(ptr_t)
+            e2e_prog.enable_peer_push(ptr_t.data_ptr(), len(ptr_list), off, fin.row0, fin.row1)
+        results[0][2].zero_()
+        results[0][1].run()
+        torch.cuda.synchronize()
+        if not torch.equal(results[0][2], results[0][0].out.cpu()):
+            raise RuntimeError("fused device-to-host stores differ from the device result")
     for i in range(W):
         step_device(i)
         step_e2e(i)
@@ -471,6 +495,8 @@ def main():
             "e2e": {"value": tot_edges / max_e2e, "unit": "edges/s", "h2d_bytes_per_step": int(results[0][3]),
                     "d2h_bytes_per_step": int(results[0][4]), "ms_per_step": 1e3 * max_e2e / K,
                     "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms,
+                    "d2h": "cudaMemcpyAsync after the kernels" if args.d2h_copy else
+                           "stores to pinned host memory from inside the scan kernel (verified against the device result)",
                     "encode_call_ms_per_step": api_ms,
                     "encode_call_edges_per_s": (edges_local / K) / (api_ms * 1e-3) if api_ms else None,
                     "encode_call_note": "model.encode(t_list) with NOTHING pre-built: window planning + launch-program "

@@ -36,7 +36,7 @@ extern "C" {
 #define TEMP_MAX_D 256     /* embed_size == hidden_size upper bound of the SIMT path  */
 #define TEMP_MAX_TERMS 3
 #define TEMP_MAX_SCAN_STEPS 16
-#define TEMP_MAX_PUSH_PEERS 8
+#define TEMP_MAX_PUSH_PEERS 16
 
 #define TEMP_ACT_NONE 0
 #define TEMP_ACT_RELU 1
@@ -164,7 +164,8 @@ typedef struct {
    * every value they write to row r also to  push_bufs[k] + push_offset + (r - push_row0) * d  for all k <
    * push_world, where push_bufs is a DEVICE array of peer-mapped buffer bases (this rank's own buffer included), e.g.
    * from torch.distributed._symmetric_memory.  The caller separates the launch from the consumers on the other GPUs
-   * with a cross-GPU barrier.  push_bufs == null: no peer stores.                                                  */
+   * with a cross-GPU barrier.  A "peer" may also be pinned host memory (UVA): the final states then reach the host
+   * from inside the scan kernel, without a device-to-host copy after it.  push_bufs == null: no peer stores.       */
   int32_t push_world;
   float* const* push_bufs;
   int64_t push_offset;
