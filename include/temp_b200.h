@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 12
+#define TEMP_ABI_VERSION 13
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -233,6 +233,28 @@ typedef struct {
   float* loss;               /* [n_pos]                                                                      */
 } TempScoreLossArgs;
 
+/* Filtered ranking of one target graph's test triples against all entities:
+ *   rank[q] = 1 + #{ j != target[q] :  v(q, j) > v(q, target[q])  or  (v(q, j) == v(q, target[q]) and j < target[q]) }
+ * with v(q, j) = sigmoid(score(q, j)) for ordinary entities and sigmoid(-10e6) = 0 for the entities of the query's filter
+ * list -- the position of the target in the stable descending sort of utils/evaluation.py:53-106
+ * (perturb_and_get_rank: calc_score over all entities, torch.where(mask, -10e6, score), sigmoid, sort_and_rank;
+ * "+ 1" of calc_metrics_single_graph line 49).  Replaces the [n_query, num_ents] score / mask / sort tensors; the filter
+ * is a CSR list per query (mask_eval_set lines 82-99: known true answers of the same (timestamp, query), target
+ * excluded, each id once) instead of a dense byte mask.  corrupt_tail: score mode 'tail' (candidates replace the
+ * object), else 'head'.  d % 32 == 0, d <= 256.                                                             */
+typedef struct {
+  int32_t n_query, num_ents, d;
+  int32_t score_fn, corrupt_tail;
+  const float* ent_embed;    /* [n_nodes, d] states of the target graph's nodes (local ids)                  */
+  const float* rel_embeds;   /* [2 * num_rels, d]                                                            */
+  const float* table;        /* [num_ents, d] all-entity table of the graph (get_all_embeds_Gt)              */
+  const int64_t* triples;    /* [n_query, 3] (subject, relation, object), local node ids                     */
+  const int64_t* target;     /* [n_query] global id of the true entity on the corrupted side                 */
+  const int32_t* filter_ptr; /* [n_query + 1] offsets into filter_ids (nullable: nothing filtered)           */
+  const int32_t* filter_ids; /* global entity ids scored as -10e6                                            */
+  int64_t* rank;             /* [n_query] 1-indexed                                                          */
+} TempRankArgs;
+
 enum { TEMP_OP_LAYER = 1, TEMP_OP_GRU = 2, TEMP_OP_ATTN = 3, TEMP_OP_GATHER = 4, TEMP_OP_SCATTER = 5,
        TEMP_OP_MEMCPY_H2D = 6, TEMP_OP_MEMCPY_D2H = 7, TEMP_OP_GRU_SCAN = 8 };
 
@@ -308,6 +330,7 @@ int temp_gather_rows(const TempGatherArgs* args, void* stream);
 int temp_scatter_rows(const TempScatterArgs* args, void* stream);
 /* out[c, r] = in[r, c]  (weight preparation: weight_ih / weight_hh / q,k,v -> K-major-first)     */
 int temp_score_loss_fwd(const TempScoreLossArgs* args, void* stream);
+int temp_rank_filtered_fwd(const TempRankArgs* args, void* stream);
 int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream);
 /* Tensor-core operand images (d == 128).  A [k, n] row-major fp32 matrix (k == 128, n % 128 == 0) is split
  * into tf32 hi / lo parts and stored, per 128 output features x 32 k, in the K-major SWIZZLE_128B

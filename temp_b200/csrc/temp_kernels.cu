@@ -682,6 +682,58 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const TempAttnArgs p) {
 // score = -|q - cand|_1 with q = s + r (tail).
 constexpr int kScoreMaxPerLane = 32;  // d / 8 <= 32, i.e. d <= 256
 
+// query vector of one triple for this lane's channels [c0, c0 + per)
+__device__ __forceinline__ void score_query(float (&q)[kScoreMaxPerLane], const float* fixed, const float* rel, int c0,
+                                            int per, int half, int score_fn, int corrupt_tail) {
+#pragma unroll
+  for (int t = 0; t < kScoreMaxPerLane; ++t) {
+    q[t] = 0.f;
+    if (t < per) {
+      const int c = c0 + t;
+      if (score_fn == TEMP_SCORE_COMPLEX) {
+        const bool im = c >= half;               // the second half of the channels is the imaginary part
+        const int k = im ? c - half : c;
+        const float re_e = __ldg(fixed + k), im_e = __ldg(fixed + half + k);
+        const float re_r = __ldg(rel + k), im_r = __ldg(rel + half + k);
+        if (corrupt_tail) q[t] = im ? re_e * im_r + im_e * re_r : re_e * re_r - im_e * im_r;
+        else q[t] = im ? re_r * im_e - im_r * re_e : re_r * re_e + im_r * im_e;
+      } else if (score_fn == TEMP_SCORE_DISTMULT) {
+        q[t] = __ldg(fixed + c) * __ldg(rel + c);
+      } else {
+        q[t] = corrupt_tail ? __ldg(fixed + c) + __ldg(rel + c) : __ldg(fixed + c) - __ldg(rel + c);
+      }
+    }
+  }
+}
+
+// this lane's share of one candidate's score (row = the candidate's channels [c0, c0 + per)); the 8 lanes of a
+// candidate add their shares with score_reduce8
+__device__ __forceinline__ float score_partial(const float4* row, const float (&q)[kScoreMaxPerLane], int per, bool l1) {
+  float part = 0.f;
+#pragma unroll
+  for (int t4 = 0; t4 < kScoreMaxPerLane / 4; ++t4) {
+    if (4 * t4 < per) {
+      const float4 v = __ldg(row + t4);
+      if (l1) {  // head: |cand + r - o| = |cand - q| ; tail: |s + r - cand| = |q - cand|
+        part += fabsf(v.x - q[4 * t4]) + fabsf(v.y - q[4 * t4 + 1]) + fabsf(v.z - q[4 * t4 + 2]) + fabsf(v.w - q[4 * t4 + 3]);
+      } else {
+        part = fmaf(v.x, q[4 * t4], part);
+        part = fmaf(v.y, q[4 * t4 + 1], part);
+        part = fmaf(v.z, q[4 * t4 + 2], part);
+        part = fmaf(v.w, q[4 * t4 + 3], part);
+      }
+    }
+  }
+  return part;
+}
+
+__device__ __forceinline__ float score_reduce8(float part) {
+  part += __shfl_xor_sync(0xffffffffu, part, 4);
+  part += __shfl_xor_sync(0xffffffffu, part, 2);
+  part += __shfl_xor_sync(0xffffffffu, part, 1);
+  return part;
+}
+
 __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLossArgs p) {
   const int lane = threadIdx.x & 31;
   const int pos = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -693,51 +745,16 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
   const float* fixed = p.ent_embed + static_cast<size_t>(p.corrupt_tail ? s_id : o_id) * D;
   const float* rel = p.rel_embeds + static_cast<size_t>(r_id) * D;
   float q[kScoreMaxPerLane];
-#pragma unroll
-  for (int t = 0; t < kScoreMaxPerLane; ++t) {
-    q[t] = 0.f;
-    if (t < per) {
-      const int c = c0 + t;
-      if (p.score_fn == TEMP_SCORE_COMPLEX) {
-        const bool im = c >= half;               // the second half of the channels is the imaginary part
-        const int k = im ? c - half : c;
-        const float re_e = __ldg(fixed + k), im_e = __ldg(fixed + half + k);
-        const float re_r = __ldg(rel + k), im_r = __ldg(rel + half + k);
-        if (p.corrupt_tail) q[t] = im ? re_e * im_r + im_e * re_r : re_e * re_r - im_e * im_r;
-        else q[t] = im ? re_r * im_e - im_r * re_e : re_r * re_e + im_r * im_e;
-      } else if (p.score_fn == TEMP_SCORE_DISTMULT) {
-        q[t] = __ldg(fixed + c) * __ldg(rel + c);
-      } else {
-        q[t] = p.corrupt_tail ? __ldg(fixed + c) + __ldg(rel + c) : __ldg(fixed + c) - __ldg(rel + c);
-      }
-    }
-  }
+  score_query(q, fixed, rel, c0, per, half, p.score_fn, p.corrupt_tail);
   const bool l1 = p.score_fn == TEMP_SCORE_TRANSE;
   float mx = -INFINITY, den = 0.f, first = 0.f;
   const int64_t* cand = p.cand + static_cast<size_t>(pos) * p.n_cand;
   for (int base = 0; base < p.n_cand; base += 4) {
     const int c = base + grp;
     float part = 0.f;
-    if (c < p.n_cand) {
-      const float4* row = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(cand[c]) * D + c0);
-#pragma unroll
-      for (int t4 = 0; t4 < kScoreMaxPerLane / 4; ++t4) {
-        if (4 * t4 < per) {
-          const float4 v = __ldg(row + t4);
-          if (l1) {  // head: |cand + r - o| = |cand - q| ; tail: |s + r - cand| = |q - cand|
-            part += fabsf(v.x - q[4 * t4]) + fabsf(v.y - q[4 * t4 + 1]) + fabsf(v.z - q[4 * t4 + 2]) + fabsf(v.w - q[4 * t4 + 3]);
-          } else {
-            part = fmaf(v.x, q[4 * t4], part);
-            part = fmaf(v.y, q[4 * t4 + 1], part);
-            part = fmaf(v.z, q[4 * t4 + 2], part);
-            part = fmaf(v.w, q[4 * t4 + 3], part);
-          }
-        }
-      }
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    if (c < p.n_cand)
+      part = score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(cand[c]) * D + c0), q, per, l1);
+    part = score_reduce8(part);
     if (c < p.n_cand) {
       const float sc = l1 ? -part : part;
       if (c == 0) first = sc;
@@ -756,6 +773,69 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
   }
   first = __shfl_sync(0xffffffffu, first, 0);
   if (lane == 0) p.loss[pos] = (mx + logf(den)) - first;
+}
+
+// ------------------------------------------------------------------------------------------------
+// filtered ranking: position of the target in the stable descending sort of sigmoid(masked scores)
+// ------------------------------------------------------------------------------------------------
+// grid (query, entity chunk): the CTA's warps walk the chunk's rows of the all-entity table, 4 candidates per warp
+// iteration exactly like the scorer above (8 lanes per candidate, the query vector in registers), and count the
+// candidates that sort ahead of the target; every candidate is first counted with its real score, then the CTA of
+// chunk 0 walks the query's filter list and replaces each filtered entity's contribution by that of sigmoid(-10e6)
+// (= 0.f: ahead of the target only when the target's own sigmoid underflowed to 0 and the entity id is smaller).
+// Counts are integers added with atomics, so the result does not depend on the schedule.
+__device__ __forceinline__ float rank_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(kThreads) rank_filtered_kernel(const TempRankArgs p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x;
+  const int D = p.d, per = D >> 3, half = D >> 1;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int c0 = sub * per;
+  const long long s_id = p.triples[3 * qi], r_id = p.triples[3 * qi + 1], o_id = p.triples[3 * qi + 2];
+  const float* fixed = p.ent_embed + static_cast<size_t>(p.corrupt_tail ? s_id : o_id) * D;
+  const float* rel = p.rel_embeds + static_cast<size_t>(r_id) * D;
+  float q[kScoreMaxPerLane];
+  score_query(q, fixed, rel, c0, per, half, p.score_fn, p.corrupt_tail);
+  const bool l1 = p.score_fn == TEMP_SCORE_TRANSE;
+  const int tgt = static_cast<int>(p.target[qi]);
+  float vt = score_reduce8(score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(tgt) * D + c0), q, per, l1));
+  vt = rank_sigmoid(l1 ? -vt : vt);
+  const int chunk = (p.num_ents + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * chunk, hi = min(p.num_ents, lo + chunk);
+  int count = 0;
+  for (int base = lo + warp * 4; base < hi; base += (kThreads / 32) * 4) {
+    const int j = base + grp;
+    float part = 0.f;
+    if (j < hi) part = score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(j) * D + c0), q, per, l1);
+    part = score_reduce8(part);
+    if (j < hi && j != tgt && sub == 0) {
+      const float v = rank_sigmoid(l1 ? -part : part);
+      count += (v > vt || (v == vt && j < tgt)) ? 1 : 0;
+    }
+  }
+  if (blockIdx.y == 0 && p.filter_ptr != nullptr) {
+    const int f0 = p.filter_ptr[qi], f1 = p.filter_ptr[qi + 1];
+    for (int base = f0 + warp * 4; base < f1; base += (kThreads / 32) * 4) {
+      const int f = base + grp;
+      const int j = f < f1 ? p.filter_ids[f] : -1;
+      float part = 0.f;
+      if (j >= 0) part = score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(j) * D + c0), q, per, l1);
+      part = score_reduce8(part);
+      if (j >= 0 && j != tgt && sub == 0) {
+        const float v = rank_sigmoid(l1 ? -part : part);
+        const int real = (v > vt || (v == vt && j < tgt)) ? 1 : 0;
+        const int masked = (0.f == vt && j < tgt) ? 1 : 0;   // sigmoid(-10e6) == 0 exactly; 0 > vt never holds
+        count += masked - real;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
+  if (lane == 0) {
+    if (blockIdx.y == 0 && warp == 0) count += 1;   // 1-indexed
+    if (count != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.rank + qi), static_cast<unsigned long long>(static_cast<long long>(count)));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1014,6 +1094,27 @@ int launch_score_loss(const TempScoreLossArgs* a, cudaStream_t st) {
   return TEMP_OK;
 }
 
+int launch_rank_filtered(const TempRankArgs* a, cudaStream_t st) {
+  if (a == nullptr || a->n_query < 0 || a->num_ents <= 0) return fail(TEMP_EINVAL, "bad rank args%s", "");
+  if (a->n_query == 0) return TEMP_OK;
+  if (a->d <= 0 || (a->d & 31) || a->d / 8 > kScoreMaxPerLane) return fail(TEMP_EUNSUPPORTED, "rank: d must be a multiple of 32 up to %s%ld", "", 8L * kScoreMaxPerLane);
+  if (a->score_fn < TEMP_SCORE_DISTMULT || a->score_fn > TEMP_SCORE_TRANSE) return fail(TEMP_EINVAL, "bad score_fn%s", "");
+  if (!a->ent_embed || !a->rel_embeds || !a->table || !a->triples || !a->target || !a->rank) return fail(TEMP_EINVAL, "rank has null pointers%s", "");
+  if ((a->filter_ptr == nullptr) != (a->filter_ids == nullptr)) return fail(TEMP_EINVAL, "rank: filter_ptr and filter_ids go together%s", "");
+  if (!aligned16(a->table)) return fail(TEMP_EINVAL, "rank table misaligned%s", "");
+  cudaError_t e = cudaMemsetAsync(a->rank, 0, sizeof(int64_t) * static_cast<size_t>(a->n_query), st);
+  if (e != cudaSuccess) return cuda_fail(e, "rank memset");
+  // entity chunks: about four CTAs per SM over the whole grid, at least 32 table rows per warp
+  int chunks = (148 * 4 + a->n_query - 1) / a->n_query;
+  const int max_chunks = (a->num_ents + 32 * (kThreads / 32) - 1) / (32 * (kThreads / 32));
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  rank_filtered_kernel<<<dim3(a->n_query, chunks), kThreads, 0, st>>>(*a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "rank_filtered_kernel launch");
+  return TEMP_OK;
+}
+
 int grid_for(size_t work_items) {
   size_t g = (work_items + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -1088,6 +1189,10 @@ int temp_gather_rows(const TempGatherArgs* args, void* stream) {
 
 int temp_scatter_rows(const TempScatterArgs* args, void* stream) {
   return launch_scatter(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_rank_filtered_fwd(const TempRankArgs* args, void* stream) {
+  return launch_rank_filtered(args, static_cast<cudaStream_t>(stream));
 }
 
 int temp_score_loss_fwd(const TempScoreLossArgs* args, void* stream) {

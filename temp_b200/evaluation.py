@@ -1,6 +1,13 @@
-"""Filtered ranking of the reference (utils/evaluation.py:6-106) -- a "next" row
-kept in torch: scores of every query against all entities in batches of 100, known true answers of
-the same (timestamp, query) masked out, rank of the target by a descending sort."""
+"""Filtered ranking of the reference (utils/evaluation.py:6-106) -- a "next" row.
+
+``calc_metrics_single_graph`` runs on the CUDA path (``temp_rank_filtered_fwd``: scores of every query against all
+entities, known true answers of the same (timestamp, query) scored as -10e6, sigmoid, position of the target in the
+stable descending sort -- counted, never sorted; the filter is a CSR list per query instead of a dense
+[queries, entities] mask).  ``calc_metrics_single_graph_torch`` is the reference's own formulation in torch operators
+(batches of 100 queries, dense mask, ``torch.sort``): the statement the GPU tests hold the kernel to, and the route
+for embedding sizes the kernel does not take (d % 32 != 0)."""
+import ctypes as C
+
 from __future__ import annotations
 
 import numpy as np
@@ -39,7 +46,54 @@ class EvaluationFilter(object):
                 mask[i, int(ids[h])] = False
         return mask
 
+    def filter_lists(self, samples, t, graph, mode):
+        """CSR form of mask_eval_set (utils/evaluation.py:82-99): per query the global ids of the known true answers,
+        each once, the query's own target left out.  -> (ptr int32 [Q + 1], ids int32)"""
+        th, tt = self._true_sets(int(t))
+        ids = graph.node_ids
+        ptr, chunks = [0], []
+        for h, r, tl in samples.tolist():
+            if mode == "tail":
+                known, target = ids[tt[(h, r)]], int(ids[tl])
+            else:
+                known, target = ids[th[(r, tl)]], int(ids[h])
+            known = np.unique(known)
+            known = known[known != target]
+            chunks.append(known)
+            ptr.append(ptr[-1] + known.shape[0])
+        flat = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)
+        return np.asarray(ptr, dtype=np.int32), flat.astype(np.int32)
+
     def calc_metrics_single_graph(self, ent_mean, rel_enc_means, all_ent_embeds, samples, graph, time, eval_bz=100):
+        """utils/evaluation.py:35-51 -> ranks (subject side first, then object side), 1-indexed."""
+        D = int(all_ent_embeds.shape[1])
+        from .scores import complex_score, distmult, transE
+        fn = {distmult: "distmult", complex_score: "complex", transE: "transE"}.get(self.calc_score)
+        if fn is None or not all_ent_embeds.is_cuda or D % 32 or D > 256:
+            return self.calc_metrics_single_graph_torch(ent_mean, rel_enc_means, all_ent_embeds, samples, graph, time, eval_bz)
+        from . import lib
+        with torch.no_grad():
+            dev = all_ent_embeds.device
+            Q = int(samples.shape[0])
+            samples = samples.to(dev).long().contiguous()
+            samples_cpu = samples.cpu()
+            ids = torch.from_numpy(graph.node_ids).to(dev)
+            ent_mean, rel, table = ent_mean.contiguous(), rel_enc_means.detach().contiguous(), all_ent_embeds.contiguous()
+            out = torch.empty(2 * Q, dtype=torch.long, device=dev)
+            keep = []
+            for k, mode in enumerate(("head", "tail")):                # ranks_s first, then ranks_o (line 48)
+                ptr, flat = self.filter_lists(samples_cpu, time, graph, mode)
+                ptr_d, flat_d = torch.from_numpy(ptr).to(dev), torch.from_numpy(flat).to(dev)
+                target = ids[samples[:, 2 if mode == "tail" else 0]].contiguous()
+                keep.append((ptr_d, flat_d, target))
+                a = lib.RankArgs(Q, int(table.shape[0]), D, lib.SCORE_FN[fn], int(mode == "tail"), ent_mean.data_ptr(),
+                                 rel.data_ptr(), table.data_ptr(), samples.data_ptr(), target.data_ptr(), ptr_d.data_ptr(),
+                                 flat_d.data_ptr() if flat.shape[0] else ptr_d.data_ptr(), out[k * Q:].data_ptr())
+                lib.check(lib.load().temp_rank_filtered_fwd(C.byref(a), C.c_void_p(lib.current_stream())),
+                          "temp_rank_filtered_fwd")
+            return out
+
+    def calc_metrics_single_graph_torch(self, ent_mean, rel_enc_means, all_ent_embeds, samples, graph, time, eval_bz=100):
         with torch.no_grad():
             dev = all_ent_embeds.device
             samples_cpu = samples.cpu()
@@ -60,7 +114,7 @@ class EvaluationFilter(object):
                         target = ids[samples[sl, 0]]
                     score = torch.where(mask[sl], torch.full_like(score, -10e6), score)
                     score = torch.sigmoid(score)
-                    _, order = torch.sort(score, dim=1, descending=True)
+                    _, order = torch.sort(score, dim=1, descending=True, stable=True)
                     ranks.append(torch.nonzero(order == target.view(-1, 1))[:, 1].view(-1))
                 out.append(torch.cat(ranks))
             return torch.cat(out) + 1

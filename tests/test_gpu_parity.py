@@ -289,6 +289,96 @@ def test_reference_style_eval_calls_agree_with_the_fast_entry():
     assert torch.equal(ranks, ranks2) and abs(loss - loss2) < 1e-6
 
 
+def _rank_bounds(model, fn, ent_mean, rel, table, samples, graph, t, mode, eps):
+    """[lowest, highest] 1-indexed rank of every query's target when sigmoid values closer than eps count as ties --
+    evaluated in float64 from the reference's formulation (utils/evaluation.py:53-80)."""
+    from temp_b200 import scores
+    f = {"complex": scores.complex_score, "distmult": scores.distmult, "transE": scores.transE}[fn]
+    ids = torch.from_numpy(graph.node_ids).cuda()
+    mask = model.evaluater._mask(samples.cpu(), table.shape[0], t, graph, mode).cuda()
+    r = rel.double()[samples[:, 1]]
+    if mode == "tail":
+        sc, target = f(ent_mean.double()[samples[:, 0]], r, table.double(), mode=mode), ids[samples[:, 2]]
+    else:
+        sc, target = f(table.double(), r, ent_mean.double()[samples[:, 2]], mode=mode), ids[samples[:, 0]]
+    v = torch.sigmoid(torch.where(mask, torch.full_like(sc, -10e6), sc))
+    vt = v.gather(1, target.view(-1, 1))
+    lo = (v > vt + eps).sum(1) + 1
+    hi = (v >= vt - eps).sum(1)                      # includes the target itself
+    return lo, hi
+
+
+@pytest.mark.parametrize("fn", ["complex", "distmult", "transE"])
+@pytest.mark.parametrize("scale", [1.0, 6.0, 40.0])
+def test_filtered_rank_kernel_matches_the_stable_sort(fn, scale):
+    """temp_rank_filtered_fwd against the reference's formulation (dense mask, sigmoid, descending sort; torch operators)
+    on the validation triples of a golden case's target graphs.  Ranks are integers: equal wherever the target is not
+    within rounding of another entity's sigmoid value, and inside the float64 tie interval everywhere.  scale 6 / 40
+    drive the sigmoid into saturation (exact ties at 1.0, and at 0.0 for TransE, where the filtered entities tie with
+    the target and the lower entity id sorts first)."""
+    from tests.helpers import CASE_BY_NAME
+    from temp_b200.evaluation import EvaluationFilter
+    from temp_b200 import scores
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    model = product_model(case)
+    model.args.score_function = fn
+    model.calc_score = {"complex": scores.complex_score, "distmult": scores.distmult, "transE": scores.transE}[fn]
+    model.evaluater = EvaluationFilter(model.args, model.calc_score, model.graph_dict_train, model.graph_dict_val,
+                                       model.graph_dict_test)
+    res = model.encode(case["t_list"])
+    n_checked = n_equal = 0
+    for i, t in enumerate(res.plan.final_times):
+        g = model.graph_dict_val.get(t)
+        if g is None or g.num_edges == 0:
+            continue
+        table = (model.all_embeds(res, i) * scale).contiguous()
+        ent_mean = (res.per_graph[i] * scale).contiguous()
+        rel = model.rel_embeds.detach()
+        src, dst = g.edges()
+        samples = torch.stack([src, g.edata["type_s"], dst]).transpose(0, 1).cuda()
+        got = model.evaluater.calc_metrics_single_graph(ent_mean, rel, table, samples, g, t)
+        want = model.evaluater.calc_metrics_single_graph_torch(ent_mean, rel, table, samples, g, t)
+        assert got.dtype == torch.long and got.shape == want.shape == (2 * samples.shape[0],)
+        Q = samples.shape[0]
+        for k, mode in enumerate(("head", "tail")):
+            lo, hi = _rank_bounds(model, fn, ent_mean, rel, table, samples, g, t, mode, eps=1e-6)
+            gk, wk = got[k * Q:(k + 1) * Q], want[k * Q:(k + 1) * Q]
+            assert bool(((gk >= lo) & (gk <= hi)).all()), (mode, gk, lo, hi)
+            assert bool(((wk >= lo) & (wk <= hi)).all())
+            sharp = lo == hi
+            assert torch.equal(gk[sharp], wk[sharp])
+            n_checked += Q
+            n_equal += int((gk == wk).sum())
+    assert n_checked >= 20 and n_equal >= 0.9 * n_checked
+
+
+def test_filtered_rank_kernel_without_a_filter_and_on_exact_ties():
+    """Integer-valued embeddings make every score exact in fp32, so the kernel and the sort see identical sigmoid values:
+    ranks must be EQUAL, ties included (lower entity id first); a null filter ranks against every entity."""
+    import ctypes as C
+    from temp_b200 import lib
+    g = torch.Generator().manual_seed(7)
+    M, D, Q = 1000, 64, 37
+    table = torch.randint(-2, 3, (M, D), generator=g).float().cuda()
+    table[500:] = table[:500]                                             # every row has an exact twin
+    rel = torch.randint(-1, 2, (6, D), generator=g).float().cuda()
+    tri = torch.stack([torch.randint(0, M, (Q,), generator=g), torch.randint(0, 6, (Q,), generator=g),
+                       torch.randint(0, M, (Q,), generator=g)], 1).cuda()
+    from temp_b200 import scores
+    for fn, f in (("distmult", scores.distmult), ("complex", scores.complex_score), ("transE", scores.transE)):
+        for tail in (1, 0):
+            target = tri[:, 2 if tail else 0].contiguous()
+            out = torch.empty(Q, dtype=torch.long, device="cuda")
+            a = lib.RankArgs(Q, M, D, lib.SCORE_FN[fn], tail, table.data_ptr(), rel.data_ptr(), table.data_ptr(),
+                             tri.data_ptr(), target.data_ptr(), 0, 0, out.data_ptr())
+            lib.check(lib.load().temp_rank_filtered_fwd(C.byref(a), C.c_void_p(lib.current_stream())), "rank")
+            r = rel[tri[:, 1]]
+            sc = f(table[tri[:, 0]], r, table, mode="tail") if tail else f(table, r, table[tri[:, 2]], mode="head")
+            _, order = torch.sort(torch.sigmoid(sc), dim=1, descending=True, stable=True)
+            want = torch.nonzero(order == target.view(-1, 1))[:, 1] + 1
+            assert torch.equal(out, want), (fn, tail)
+
+
 @pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8"])
 def test_fused_peer_push_and_barrier_on_one_gpu(name):
     """The fused all-gather path with this GPU as its only peer: the scan step that writes the final states also stores
