@@ -11,8 +11,11 @@ It restates, on the packed window plan of temp_b200/planner.py (same ``prev_row`
   GRRGCNLayer / RRGCNLayer (rec-only layer 2)  models/RRGCN.py:77-89, 130-154; forward_isolated 91-104, 156-167
   RRGCN.forward / forward_isolated            models/RRGCN.py:192-217
   DynamicRGCN.forward, get_all_embeds_Gt      models/DynamicRGCN.py:56-64, 176-194
-Scope: GRRGCN / RRGCN with ``--rec-only-last-layer`` (the shipped uni-directional configurations); everything else
-raises.  The no-grad forward never comes here (it is the CUDA path and has no fallback).
+  BiGRRGCNLayer / BiRRGCNLayer, BiRRGCN       models/BiRRGCN.py:27-81, 115-186, 188-257
+  BiDynamicRGCN.forward, get_all_embeds_Gt    models/BiDynamicRGCN.py:102-112, 165-187
+Scope: the recurrent families (GRRGCN / RRGCN / BiGRRGCN / BiRRGCN, with or without ``--rec-only-last-layer``, torch GRU
+or --type1 cell, learnable lambda); the static and attention families raise.  The no-grad forward never comes here (it
+is the CUDA path and has no fallback).
 """
 from __future__ import annotations
 
@@ -24,9 +27,9 @@ import torch.nn.functional as F
 def _check(model):
     if model.ent_embeds.device.type != "cuda":
         raise RuntimeError("temp_b200: the model must live on a CUDA device")
-    if model.family != "recurrent" or model.bidirectional or not model.ent_encoder.rec_only_last_layer:
-        raise NotImplementedError("temp_b200: the autograd fallback covers GRRGCN / RRGCN with --rec-only-last-layer; "
-                                  "use torch.no_grad() for the forward of this configuration")
+    if model.family != "recurrent":
+        raise NotImplementedError("temp_b200: the autograd fallback covers the recurrent families (GRRGCN / RRGCN / "
+                                  "BiGRRGCN / BiRRGCN); use torch.no_grad() for the forward of this configuration")
 
 
 class _Ctx(object):
@@ -38,31 +41,40 @@ class _Ctx(object):
         self.plan = plan
         self.ent_id, self.row_time = t(plan.ent_id), t(plan.row_time)
         self.norm = t(plan.norm, torch.float32)
-        deg = np.diff(plan.row_ptr.astype(np.int64))
+        self.row_ptr = plan.row_ptr.astype(np.int64)
+        deg = np.diff(self.row_ptr)
         self.e_dst = t(np.repeat(np.arange(plan.R, dtype=np.int64), deg))
         self.e_src, self.e_rel = t(plan.e_src), t(plan.e_rel)
-        self.prev, self.dt = t(plan.prev_a), t(plan.dt_a, torch.float32)
+        self.prev = {"a": t(plan.prev_a)}
+        self.dt = {"a": t(plan.dt_a, torch.float32)}
+        if plan.bidirectional:                                   # second chain of the centre step (backward history)
+            self.prev["b"], self.dt["b"] = t(plan.prev_b), t(plan.dt_b, torch.float32)
 
 
-def _rgcn_graph(layer, h, c: _Ctx, training: bool):
-    """models/RGCN.py:53-104: block-diagonal messages, edge norm, sum, node norm, (+bias), + dropout(self loop), act."""
-    E, D = c.e_src.shape[0], h.shape[1]
-    nb, si, so = layer.num_bases, layer.submat_in, layer.submat_out
-    w = layer.weight.index_select(0, c.e_rel).view(-1, si, so)
-    msg = torch.bmm(h.index_select(0, c.e_src).view(-1, 1, si), w).view(E, D)
-    msg = msg * c.norm.index_select(0, c.e_dst).unsqueeze(1)
-    agg = torch.zeros(h.shape[0], D, dtype=h.dtype, device=h.device).index_add(0, c.e_dst, msg) * c.norm.unsqueeze(1)
-    loop = F.dropout(h @ layer.loop_weight, p=layer.dropout_p, training=training)
-    out = agg + (layer.h_bias if layer.bias else 0) + loop
-    return torch.relu(out) if layer.activation == "relu" else out
+def _act(x, relu: bool):
+    return torch.relu(x) if relu else x
 
 
-def _rgcn_isolated(layer, x, training: bool):
-    """models/RGCN.py:78-89 (note the residual)."""
+def _rgcn_pre(layer, h, c: _Ctx, row0: int, row1: int, training: bool):
+    """models/RGCN.py:53-104 for the packed rows [row0, row1) up to the activation: block-diagonal messages, edge norm,
+    sum, node norm, (+bias), + dropout(self loop).  ``h`` holds the layer input of every packed row."""
+    D = h.shape[1]
+    e0, e1 = int(c.row_ptr[row0]), int(c.row_ptr[row1])
+    src, rel, dst = c.e_src[e0:e1], c.e_rel[e0:e1], c.e_dst[e0:e1]
+    si, so = layer.submat_in, layer.submat_out
+    w = layer.weight.index_select(0, rel).view(-1, si, so)
+    msg = torch.bmm(h.index_select(0, src).view(-1, 1, si), w).view(e1 - e0, D)
+    msg = msg * c.norm.index_select(0, dst).unsqueeze(1)
+    agg = torch.zeros(row1 - row0, D, dtype=h.dtype, device=h.device).index_add(0, dst - row0, msg)
+    agg = agg * c.norm[row0:row1].unsqueeze(1)
+    loop = F.dropout(h[row0:row1] @ layer.loop_weight, p=layer.dropout_p, training=training)
+    return agg + (layer.h_bias if layer.bias else 0) + loop
+
+
+def _iso_pre(layer, x, training: bool):
+    """models/RGCN.py:78-89 up to the activation (note the residual)."""
     out = x + F.dropout(x @ layer.loop_weight, p=layer.dropout_p, training=training)
-    if layer.bias:
-        out = out + layer.h_bias
-    return torch.relu(out) if layer.activation == "relu" else out
+    return out + layer.h_bias if layer.bias else out
 
 
 def _decay(model, layer, dt):
@@ -84,68 +96,121 @@ def _gru(model, rnn, x, h0):
     return hn.squeeze(0)
 
 
+def _cell(model, layer, direction: str):
+    """Recurrent parameters of one direction: RRGCN.py:75, 126; BiRRGCN.py:21-25, 109-113."""
+    gru = model.args.module in ("GRRGCN", "BiGRRGCN")
+    if not model.bidirectional:
+        return layer.rnn if gru else layer.time_weight
+    if gru:
+        return layer.forward_rnn if direction == "f" else layer.backward_rnn
+    return layer.time_weight_forward if direction == "f" else layer.time_weight_backward
+
+
+def _recur(model, layer, pre, states, decays, dirs, relu: bool):
+    """The recurrent half of one layer given its pre-activation RGCN output ``pre`` and, per direction, the previous
+    state rows (zeros where there is none) and the decay arguments.  GRU flavour: RRGCN.py:77-89, BiRRGCN.py:27-81 (the
+    activation applies BEFORE the cells, the directions add); linear flavour: RRGCN.py:130-154 (the recurrent terms join
+    the sum before the activation)."""
+    gru = model.args.module in ("GRRGCN", "BiGRRGCN")
+    if gru:
+        x = _act(pre, relu)
+        out = 0
+        for d, raw, dt in zip(dirs, states, decays):
+            out = out + _gru(model, _cell(model, layer, d), x, raw * _decay(model, layer, dt))
+        return out
+    tot = pre
+    for d, raw, dt in zip(dirs, states, decays):
+        tot = tot + (raw @ _cell(model, layer, d)) * torch.exp(-dt.view(-1, 1) * float(model.args.inv_temperature))
+    return _act(tot, relu)
+
+
 def encode(model, plan):
-    """-> (state [R, D] of every packed row, ctx); differentiable w.r.t. the model parameters."""
+    """-> (state [R, D] of every packed row, ctx, layer-1 state or None); differentiable w.r.t. the model parameters.
+    Same launch structure as EncoderRuntime._build_recurrent (temp_b200/runtime.py), one torch statement per launch."""
     _check(model)
     c = _Ctx(model, plan)
     enc = model.ent_encoder
     l1, l2 = enc.layer_1, enc.layer_2
     training = model.training
-    gru = model.args.module == "GRRGCN"
-    h1 = _rgcn_graph(l1, model.ent_embeds.index_select(0, c.ent_id), c, training)
-    S = torch.zeros(plan.R, model.embed_size, dtype=h1.dtype, device=h1.device)
-    x2 = _rgcn_graph(l2, h1, c, training)       # layer 2 of the uni-directional models has no activation (RRGCN.py:186-187)
-    for seg in plan.segments:
+    gru = model.args.module in ("GRRGCN", "BiGRRGCN")
+    bi = plan.bidirectional
+    relu2 = bi                                   # BiRRGCN.py:202-203 vs RRGCN.py:186-187
+    use_te = enc.use_time_embedding
+    D = model.embed_size
+    h0 = model.ent_embeds.index_select(0, c.ent_id)
+    S = torch.zeros(plan.R, D, dtype=h0.dtype, device=h0.device)
+    S1 = None
+
+    def step(layer, seg, pre, state_prev, relu):
         rows = torch.arange(seg.row0, seg.row1, device=S.device)
-        prev = c.prev.index_select(0, rows)
-        has = (prev >= 0).unsqueeze(1)
-        raw = torch.where(has, S.index_select(0, prev.clamp(min=0)), torch.zeros((), device=S.device))
-        dec = _decay(model, l2, c.dt.index_select(0, rows))
-        x = x2.index_select(0, rows)
-        if gru:
-            hn = _gru(model, l2.rnn, x, raw * dec)                                     # RRGCN.py:79-85
-        else:
-            hn = x + (raw @ l2.time_weight) * torch.exp(-c.dt.index_select(0, rows).view(-1, 1)
-                                                        * float(model.args.inv_temperature))  # RRGCN.py:142
-        if enc.use_time_embedding:
-            hn = hn + l2.time_embed.index_select(0, c.row_time.index_select(0, rows))   # RRGCN.py:202-203
-        S = S.index_copy(0, rows, hn)
-    return S, c
+        dirs = ["f", "b"] if (seg.kind == "final" and bi) else [seg.kind[-1] if seg.kind != "final" else "f"]
+        states, decays = [], []
+        for d in dirs:
+            which = "b" if (d == "b" and seg.kind == "final") else "a"
+            prev = c.prev[which].index_select(0, rows)
+            has = (prev >= 0).unsqueeze(1)
+            states.append(torch.where(has, state_prev.index_select(0, prev.clamp(min=0)), torch.zeros((), device=S.device)))
+            decays.append(c.dt[which].index_select(0, rows))
+        hn = _recur(model, layer, pre, states, decays, dirs, relu)
+        if use_te:
+            hn = hn + layer.time_embed.index_select(0, c.row_time.index_select(0, rows))   # RRGCN.py:202-203
+        return rows, hn
+
+    if enc.rec_only_last_layer:
+        h1 = _rgcn_pre(l1, h0, c, 0, plan.R, training)          # plain RGCN layer, no activation (RRGCN.py:179-185)
+        x2 = _rgcn_pre(l2, h1, c, 0, plan.R, training)
+        for seg in plan.segments:
+            rows, hn = step(l2, seg, x2[seg.row0:seg.row1], S, relu2)
+            S = S.index_copy(0, rows, hn)
+    else:
+        # both layers recurrent, serial in the step index; the GRU flavours feed layer 1 with the previous LAYER-2 state
+        # (the reference's graph aliasing, SURVEY Appendix B-2), the linear flavours keep separate states
+        S1 = torch.zeros_like(S)
+        for seg in plan.segments:
+            rows, hn = step(l1, seg, _rgcn_pre(l1, h0, c, seg.row0, seg.row1, training), S if gru else S1, False)
+            S1 = S1.index_copy(0, rows, hn)
+            rows, hn = step(l2, seg, _rgcn_pre(l2, S1, c, seg.row0, seg.row1, training), S, relu2)
+            S = S.index_copy(0, rows, hn)
+    return S, c, S1
 
 
-def all_embeds(model, plan, S, i: int):
-    """get_all_embeds_Gt (models/DynamicRGCN.py:56-64): forward_isolated over all entities with item i's history, rows
-    of the target graph's entities overwritten by the graph states."""
+def all_embeds(model, plan, S, i: int, S1=None):
+    """get_all_embeds_Gt (models/DynamicRGCN.py:56-64, BiDynamicRGCN.py:102-112): forward_isolated over all entities
+    with item i's history ("history forgets": only the entities of the last history step carry a state, one step old),
+    rows of the target graph's entities overwritten by the graph states."""
     enc = model.ent_encoder
     l1, l2 = enc.layer_1, enc.layer_2
     training = model.training
-    M, D, L = model.num_ents, model.embed_size, plan.seq_len
+    gru = model.args.module in ("GRRGCN", "BiGRRGCN")
+    bi = plan.bidirectional
+    M, D = model.num_ents, model.embed_size
     dev = S.device
-    hist = torch.zeros(M, D, dtype=S.dtype, device=dev)
-    start = torch.zeros(M, dtype=S.dtype, device=dev)
-    for seg in plan.segments:                                    # start_time: last history step an entity was active in
-        if seg.kind != "hist_f":
-            continue
-        for inst in seg.instances:
-            if inst.item == i:
-                start[torch.as_tensor(inst.snapshot.node_ids, device=dev)] = float(inst.step)
-    last = plan.last_hist_f[i]
-    if last is not None:                                         # "history forgets": only the last step's entities
-        ids = torch.as_tensor(last.snapshot.node_ids, device=dev)
-        hist = hist.index_copy(0, ids, S[last.row0:last.row0 + last.n])
-    dt = (L - 1) - start
-    t = plan.final_times[i]
-    first = _rgcn_isolated(l1, model.ent_embeds, training)
-    if model.args.module == "GRRGCN":
-        x = _rgcn_isolated(l2, first, training)
-        second = _gru(model, l2.rnn, x, hist * _decay(model, l2, dt))                   # RRGCN.py:91-98
+    dirs = ["f", "b"] if bi else ["f"]
+    lasts = [plan.last_hist_f[i]] + ([plan.last_hist_b[i]] if bi else [])
+    ones = torch.ones(M, dtype=S.dtype, device=dev)
+    t = int(plan.final_times[i])
+
+    def hist_of(state):
+        out = []
+        for last in lasts:
+            h = torch.zeros(M, D, dtype=S.dtype, device=dev)
+            if last is not None:
+                ids = torch.as_tensor(last.snapshot.node_ids, device=dev).long()
+                h = h.index_copy(0, ids, state[last.row0:last.row0 + last.n])
+            out.append(h)
+        return out
+
+    def rec_iso(layer, x, state, relu):
+        out = _recur(model, layer, _iso_pre(layer, x, training), hist_of(state), [ones] * len(dirs), dirs, relu)
+        return out + layer.time_embed[t] if enc.use_time_embedding else out
+
+    if enc.rec_only_last_layer:
+        first = _iso_pre(l1, model.ent_embeds, training)
     else:
-        second = first + F.dropout(first @ l2.loop_weight, p=l2.dropout_p, training=training)
-        second = second + (hist @ l2.time_weight) * torch.exp(-dt.view(-1, 1) * float(model.args.inv_temperature))
-    if enc.use_time_embedding:
-        second = second + l2.time_embed[int(t)]
+        first = rec_iso(l1, model.ent_embeds, S if gru else S1, False)
+    second = rec_iso(l2, first, S, bi)
     fin = plan.final.instances[i]
-    ids = torch.as_tensor(fin.snapshot.node_ids, device=dev)
+    ids = torch.as_tensor(fin.snapshot.node_ids, device=dev).long()
     return second.index_copy(0, ids, S[fin.row0:fin.row0 + fin.n])
 
 
@@ -154,7 +219,7 @@ def training_loss(model, t_list):
     tail + head cross-entropy through the torch scorers."""
     _check(model)
     plan = model.plan(t_list, transform=model.train_edge_sampler() if model.training else None)
-    S, _ = encode(model, plan)
+    S, _, S1 = encode(model, plan)
     dev = S.device
     loss = 0
     for i, (t, g) in enumerate(zip(plan.final_times, plan.final_snapshots)):
@@ -162,7 +227,7 @@ def training_loss(model, t_list):
         ent_embed = S[fin.row0:fin.row0 + fin.n]
         triplets, neg_tail, neg_head, labels = model.corrupter.single_graph_negative_sampling(t, g, model.num_ents)
         triplets, neg_tail, neg_head, labels = (x.to(dev) for x in (triplets, neg_tail, neg_head, labels))
-        all_g = all_embeds(model, plan, S, i)
+        all_g = all_embeds(model, plan, S, i, S1)
         loss = loss + model.train_link_prediction(ent_embed, triplets, neg_tail, labels, all_g, corrupt_tail=True)
         loss = loss + model.train_link_prediction(ent_embed, triplets, neg_head, labels, all_g, corrupt_tail=False)
     return loss

@@ -230,32 +230,28 @@ def test_autograd_fallback_loss_equals_cuda_forward(name):
     assert abs(float(got) - want) <= RTOL * abs(want)
 
 
-@pytest.mark.parametrize("tc", [c for c in __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES
-                                if "icews" not in c["name"] and "bigrrgcn" not in c["name"]], ids=lambda c: c["name"])
-def test_autograd_fallback_gradients_match_oracle(tc):
-    """loss.backward() through the fallback gives the gradients of the (reference-pinned) oracle's training loss:
-    train mode, sub-sampled window, dropout p = 0, same global seeds."""
+def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None):
     from tests.helpers import CASE_BY_NAME
-    case = dict(CASE_BY_NAME[tc["base"]])
-    gold = load_golden(tc["name"])
+    case = dict(CASE_BY_NAME[base])
     oracle = oracle_model(case)
     for v in oracle.p.values():
         v.requires_grad_(True)
-    np.random.seed(tc["seed"])
-    torch.manual_seed(tc["seed"])
+    np.random.seed(seed)
+    torch.manual_seed(seed)
     lo = oracle.train_loss(case["t_list"], case.get("negative_rate", 5), case.get("num_pos_facts", 3000),
-                           random_dropout=tc["random_dropout"])
+                           random_dropout=random_dropout)
     lo.backward()
+    want_loss = float(lo.detach()) if gold_loss is None else float(gold_loss)
     model = product_model(case)
     model.args.dropout = 0.0
     for layer in (model.ent_encoder.layer_1, model.ent_encoder.layer_2):
         layer.dropout_p = 0.0
-    model.args.random_dropout = tc["random_dropout"]
+    model.args.random_dropout = random_dropout
     model.train()
-    np.random.seed(tc["seed"])
-    torch.manual_seed(tc["seed"])
+    np.random.seed(seed)
+    torch.manual_seed(seed)
     loss = model.forward(torch.tensor(case["t_list"]))
-    assert abs(float(loss) - float(gold["loss"])) <= RTOL * abs(float(gold["loss"]))
+    assert abs(float(loss.detach()) - want_loss) <= RTOL * abs(want_loss)
     loss.backward()
     checked = 0
     for name, prm in model.named_parameters():
@@ -270,6 +266,23 @@ def test_autograd_fallback_gradients_match_oracle(tc):
         checked += 1
     assert checked >= 6
     torch.optim.Adam(model.parameters(), lr=1e-3).step()       # a main.py-style update runs
+
+
+@pytest.mark.parametrize("tc", [c for c in __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES
+                                if "icews" not in c["name"]], ids=lambda c: c["name"])
+def test_autograd_fallback_gradients_match_oracle(tc):
+    """loss.backward() through the fallback gives the gradients of the (reference-pinned) oracle's training loss:
+    train mode, sub-sampled window, dropout p = 0, same global seeds; the loss also matches the committed golden value.
+    Uni- and bidirectional cases."""
+    _autograd_against_oracle(tc["base"], tc["seed"], tc["random_dropout"], load_golden(tc["name"])["loss"])
+
+
+@pytest.mark.parametrize("base", ["grrgcn_tiny_d128_full", "rrgcn_tiny_d128_full", "bigrrgcn_tiny_d128_full",
+                                  "birrgcn_tiny_d128_full", "grrgcn_tiny_d32_nb8_type1", "grrgcn_tiny_d128_lambda"])
+def test_autograd_fallback_covers_every_recurrent_configuration(base):
+    """Both layers recurrent (graph aliasing of the GRU flavours, separate states of the linear ones), the Bi linear
+    recurrence, the --type1 cell and the learnable decay: loss and gradients against the oracle on the same seeds."""
+    _autograd_against_oracle(base, 31, True)
 
 
 def test_reference_style_eval_calls_agree_with_the_fast_entry():
