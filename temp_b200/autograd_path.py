@@ -84,7 +84,8 @@ def _decay(model, layer, dt):
 
 
 def _gru(model, rnn, x, h0):
-    """torch.nn.GRU with sequence length 1 (models/RRGCN.py:84) or the --type1 cell (models/GRU_cell.py:18-31)."""
+    """torch.nn.GRU with sequence length 1 (models/RRGCN.py:84) or the --type1 cell
+    (models/GRU_cell.py:18-31)."""
     if bool(getattr(model.args, "type1", False)):
         D = h0.shape[1]
         i_n = x @ rnn.weight_ih.t() + rnn.bias_ih
@@ -92,8 +93,15 @@ def _gru(model, rnn, x, h0):
         r, z = torch.sigmoid(gh[:, :D]), torch.sigmoid(gh[:, D:2 * D])
         n = torch.tanh(i_n + r * gh[:, 2 * D:])
         return n + z * (h0 - n)
-    _, hn = rnn(x.unsqueeze(0), h0.unsqueeze(0).contiguous())
-    return hn.squeeze(0)
+    # the nn.GRU equations written out (gate order r, z, n): plain fp32 matmuls in the forward AND the backward pass --
+    # the cuDNN RNN routes both through TF32 unless torch.backends.cudnn.allow_tf32 is cleared globally
+    D = h0.shape[1]
+    gi = x @ rnn.weight_ih_l0.t() + rnn.bias_ih_l0
+    gh = h0 @ rnn.weight_hh_l0.t() + rnn.bias_hh_l0
+    r = torch.sigmoid(gi[:, :D] + gh[:, :D])
+    z = torch.sigmoid(gi[:, D:2 * D] + gh[:, D:2 * D])
+    n = torch.tanh(gi[:, 2 * D:] + r * gh[:, 2 * D:])
+    return (1 - z) * n + z * h0
 
 
 def _cell(model, layer, direction: str):

@@ -6,9 +6,9 @@ stable descending sort -- counted, never sorted; the filter is a CSR list per qu
 [queries, entities] mask).  ``calc_metrics_single_graph_torch`` is the reference's own formulation in torch operators
 (batches of 100 queries, dense mask, ``torch.sort``): the statement the GPU tests hold the kernel to, and the route
 for embedding sizes the kernel does not take (d % 32 != 0)."""
-import ctypes as C
-
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch

@@ -184,6 +184,40 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     assert got == want
 
 
+def test_every_package_module_imports():
+    import importlib
+    import pkgutil
+    import temp_b200
+    names = [m.name for m in pkgutil.iter_modules(temp_b200.__path__) if not m.name.startswith("libtemp")]   # the C-ABI .so
+    assert {"evaluation", "autograd_path", "isolated", "sharding", "planner", "runtime", "models", "lib"} <= set(names)
+    for name in names:
+        importlib.import_module("temp_b200." + name)
+
+
+def test_filter_lists_are_the_csr_form_of_the_dense_mask():
+    """EvaluationFilter.filter_lists (the rank kernel's input) == the rows of the dense mask of utils/evaluation.py:82-99."""
+    import torch
+    from temp_b200.evaluation import EvaluationFilter
+    from temp_b200.scores import complex_score
+    from tests.helpers import product_store
+    store = product_store("tiny")
+    ev = EvaluationFilter(None, complex_score, store.train, store.valid, store.test)
+    checked = 0
+    for t, g in store.valid.items():
+        if g.num_edges == 0:
+            continue
+        src, dst = g.edges()
+        samples = torch.stack([src, g.edata["type_s"], dst]).transpose(0, 1)
+        for mode in ("head", "tail"):
+            ptr, flat = ev.filter_lists(samples, t, g, mode)
+            mask = ev._mask(samples, store.num_ents, t, g, mode).numpy()
+            assert ptr.dtype == np.int32 and flat.dtype == np.int32 and ptr.shape[0] == samples.shape[0] + 1
+            for q in range(samples.shape[0]):
+                assert np.array_equal(flat[ptr[q]:ptr[q + 1]], np.nonzero(mask[q])[0])
+            checked += samples.shape[0]
+    assert checked > 0
+
+
 def test_encoder_refuses_to_run_without_cuda():
     """No CPU fallback: the product path must fail loudly."""
     if torch.cuda.is_available():
