@@ -122,6 +122,17 @@ class RGCN(_TwoLayer):
         args.rec_only_last_layer = getattr(args, "rec_only_last_layer", False)
         super().__init__(args, RGCNLayer, RGCNLayer, hidden_size, embed_size, num_rels, total_times, True, "relu")
 
+    # per-step calls of the reference's drivers, on the CUDA path (temp_b200/stepwise.py)
+    def forward(self, batched_graph, time_batched_list_t, node_sizes=None):
+        """models/RGCN.py:154-159 -> the batched graph, ``ndata['h']`` = layer-2 output (+ time embedding)."""
+        from .stepwise import static_graph_step
+        return static_graph_step(self, batched_graph, time_batched_list_t)
+
+    def forward_isolated(self, ent_embeds, time):
+        """models/RGCN.py:161-164."""
+        from .stepwise import static_isolated_step
+        return static_isolated_step(self, ent_embeds, time)
+
 
 class RRGCN(_TwoLayer):
     """models/RRGCN.py:170-190."""
@@ -133,6 +144,20 @@ class RRGCN(_TwoLayer):
         self.impute = bool(getattr(args, "impute", False))
         if self.impute:
             self.impute_weight = nn.Linear(1, 1)
+
+    # per-step calls of the reference's drivers, on the CUDA path (temp_b200/stepwise.py)
+    def forward(self, batched_graph, first_prev_graph_embeds, second_prev_graph_embeds, time_diff_tensor,
+                time_batched_list_t, node_sizes=None):
+        """models/RRGCN.py:192-204 -> (first, second) node states of the batched graph."""
+        from .stepwise import graph_step
+        return graph_step(self, batched_graph, time_batched_list_t, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                          [time_diff_tensor], ["f"])
+
+    def forward_isolated(self, ent_embeds, first_prev_graph_embeds, second_prev_graph_embeds, time_diff_tensor, time):
+        """models/RRGCN.py:206-217 -> second-layer states of all rows of ``ent_embeds``."""
+        from .stepwise import isolated_step
+        return isolated_step(self, ent_embeds, time, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                             [time_diff_tensor], ["f"])
 
 
 class BiRRGCN(_TwoLayer):
@@ -146,6 +171,34 @@ class BiRRGCN(_TwoLayer):
         if self.impute:
             self.impute_weight_forward = nn.Linear(1, 1)
             self.impute_weight_backward = nn.Linear(1, 1)
+
+    # per-step calls of the reference's drivers, on the CUDA path (temp_b200/stepwise.py)
+    def forward(self, batched_graph, first_prev_graph_embeds_forward, second_prev_graph_embeds_forward,
+                time_diff_tensor_forward, first_prev_graph_embeds_backward, second_prev_graph_embeds_backward,
+                time_diff_tensor_backward, time_batched_list_t, node_sizes=None):
+        """models/BiRRGCN.py:210-226 (the centre step: both directions' cells on one RGCN pass) -> second."""
+        from .stepwise import graph_step
+        return graph_step(self, batched_graph, time_batched_list_t,
+                          [first_prev_graph_embeds_forward, first_prev_graph_embeds_backward],
+                          [second_prev_graph_embeds_forward, second_prev_graph_embeds_backward],
+                          [time_diff_tensor_forward, time_diff_tensor_backward], ["f", "b"])[1]
+
+    def forward_one_direction(self, batched_graph, first_prev_graph_embeds, second_prev_graph_embeds, time_diff_tensor,
+                              time_batched_list_t, node_sizes=None, forward=True):
+        """models/BiRRGCN.py:228-240 (history steps) -> (first, second)."""
+        from .stepwise import graph_step
+        return graph_step(self, batched_graph, time_batched_list_t, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                          [time_diff_tensor], ["f" if forward else "b"])
+
+    def forward_isolated(self, ent_embeds, first_prev_graph_embeds_forward, second_prev_graph_embeds_forward,
+                         time_diff_tensor_forward, first_prev_graph_embeds_backward, second_prev_graph_embeds_backward,
+                         time_diff_tensor_backward, time):
+        """models/BiRRGCN.py:242-257."""
+        from .stepwise import isolated_step
+        return isolated_step(self, ent_embeds, time,
+                             [first_prev_graph_embeds_forward, first_prev_graph_embeds_backward],
+                             [second_prev_graph_embeds_forward, second_prev_graph_embeds_backward],
+                             [time_diff_tensor_forward, time_diff_tensor_backward], ["f", "b"])
 
 
 class SARGCN(_TwoLayer):

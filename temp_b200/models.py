@@ -75,6 +75,8 @@ class TKG_Module(nn.Module):
         nn.init.xavier_uniform_(self.ent_embeds, gain=_GAIN)
         nn.init.xavier_uniform_(self.rel_embeds, gain=_GAIN)
         self.build_model()
+        from .stepwise import bind
+        bind(self.ent_encoder, self)                                # the encoder's per-step calls run on this shell's runtime
         self._runtime: Optional[EncoderRuntime] = None
         self._corrupter = None
 

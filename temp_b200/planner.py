@@ -492,12 +492,18 @@ def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], s
 
 def plan_static(graph_dict: Dict[int, Snapshot], t_list: Sequence[int]) -> WindowPlan:
     """StaticRGCN (baselines/StaticRGCN.py:23-28): one snapshot per target, t_list order kept."""
+    return plan_snapshots([graph_dict[int(t)] for t in t_list], t_list)
+
+
+def plan_snapshots(snaps: Sequence[Snapshot], times: Sequence[int]) -> WindowPlan:
+    """One step over a list of snapshots in the given order -- what ``dgl.batch(list)`` is to one encoder call
+    (models/DynamicRGCN.py:92): rows = the snapshots' nodes back to back, edges in list order, no history maps.
+    ``times[i]`` is the timestamp the rows of snapshot i take their time embedding from."""
     plan = WindowPlan()
-    plan.seq_len, plan.batch = 1, len(t_list)
+    plan.seq_len, plan.batch = 1, len(snaps)
     pk = _Packer()
     seg = Segment("final", 0, 0, 0)
-    for i, t in enumerate(t_list):
-        snap = graph_dict[int(t)]
+    for i, (snap, t) in enumerate(zip(snaps, times)):
         inst = Instance(i, 0, "c", int(t), pk.add(snap), snap.num_nodes, snap)
         pk.add_prev(snap.num_nodes, None, 0.0)
         seg.instances.append(inst)
@@ -506,7 +512,11 @@ def plan_static(graph_dict: Dict[int, Snapshot], t_list: Sequence[int]) -> Windo
         plan.final_snapshots.append(snap)
     seg.row1 = pk.R
     plan.segments.append(seg)
-    plan.last_hist_f = [None] * len(t_list)
-    plan.last_hist_b = [None] * len(t_list)
+    plan.last_hist_f = [None] * len(snaps)
+    plan.last_hist_b = [None] * len(snaps)
     pk.finish(plan)
+    want = np.repeat(np.asarray([int(t) for t in times], dtype=np.int32), [s.num_nodes for s in snaps]) if len(snaps) \
+        else np.zeros(0, dtype=np.int32)
+    if not np.array_equal(plan.row_time, want):
+        plan.row_time = want
     return plan

@@ -1,0 +1,277 @@
+"""The reference's per-step ENCODER calls on the CUDA path ("the encoder object must answer
+forward / forward_isolated / forward_one_direction ...").
+
+``model.encode()`` runs a whole window batch as one launch program and is the fast entry.  Code written against the
+reference's encoder objects -- its own ``DynamicRGCN`` / ``BiDynamicRGCN`` / ``StaticRGCN`` drivers, the Aggregator --
+instead calls the encoder once per time step with dense tensors:
+
+    RGCN.forward(batched_graph, time_batched_list_t, node_sizes)                              models/RGCN.py:154-159
+    RGCN.forward_isolated(ent_embeds, time)                                                   models/RGCN.py:161-164
+    RRGCN.forward(batched_graph, first_prev, second_prev, time_diff, times, node_sizes)       models/RRGCN.py:192-204
+    RRGCN.forward_isolated(ent_embeds, first_prev, second_prev, time_diff, time)              models/RRGCN.py:206-217
+    BiRRGCN.forward(batched_graph, first_prev_f, second_prev_f, dt_f, first_prev_b, second_prev_b, dt_b, times,
+                    node_sizes)                                                               models/BiRRGCN.py:210-226
+    BiRRGCN.forward_one_direction(batched_graph, first_prev, second_prev, dt, times, node_sizes, forward)   228-240
+    BiRRGCN.forward_isolated(ent_embeds, first_prev_f, second_prev_f, dt_f, first_prev_b, second_prev_b, dt_b, time)
+                                                                                              models/BiRRGCN.py:242-257
+
+Those methods (temp_b200/encoder.py) land here: one call = one short launch program of the same kernels
+(``temp_rgcn_layer_fwd`` with the chained input-gate GEMM, ``temp_gru_fwd``), previous states read from the caller's
+dense ``[N, D]`` tensors through an identity row map.  ``batched_graph`` is a ``BatchedSnapshots`` (the subset of
+``dgl.batch`` the encoders use: ``ndata['h']``, ``ndata['id']``, ``number_of_nodes()``, ``local_var()``).
+The graph-aliasing quirk of the GRU flavours (``first`` and ``second`` are the same tensor) is kept.
+Inference only (no autograd); the post-ensemble / impute variants are not built.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib
+from .planner import plan_snapshots
+
+_OWNERS = weakref.WeakKeyDictionary()          # encoder object -> weakref(model shell)
+
+
+def bind(encoder, model) -> None:
+    _OWNERS[encoder] = weakref.ref(model)
+
+
+def owner_of(encoder):
+    ref = _OWNERS.get(encoder)
+    model = ref() if ref is not None else None
+    if model is None:
+        raise RuntimeError("temp_b200: this encoder object is not attached to a TKG_Module shell (the per-step calls run "
+                           "through the shell's CUDA runtime)")
+    return model
+
+
+class BatchedSnapshots(object):
+    """``dgl.batch(g_list)`` as the encoder calls see it (models/DynamicRGCN.py:92-93)."""
+
+    def __init__(self, snapshots: Sequence, times: Optional[Sequence[int]] = None, ndata: Optional[dict] = None):
+        self.snapshots = list(snapshots)
+        self.times = [int(t) for t in (times if times is not None else [s.time for s in self.snapshots])]
+        self.node_sizes = [s.num_nodes for s in self.snapshots]
+        self.ndata = {} if ndata is None else ndata
+        self._plan = None
+
+    @property
+    def ids(self) -> np.ndarray:
+        """global entity id of every batched node"""
+        return np.concatenate([s.node_ids for s in self.snapshots]) if self.snapshots else np.zeros(0, dtype=np.int64)
+
+    def number_of_nodes(self) -> int:
+        return int(sum(self.node_sizes))
+
+    def nodes(self):
+        return torch.arange(self.number_of_nodes())
+
+    def local_var(self):
+        g = BatchedSnapshots(self.snapshots, self.times, dict(self.ndata))
+        g._plan = self._plan
+        return g
+
+    def plan(self, times: Optional[Sequence[int]] = None):
+        times = self.times if times is None else [int(t) for t in times]
+        if self._plan is None or self._plan.final_times != times:
+            self._plan = plan_snapshots(self.snapshots, times)
+        return self._plan
+
+
+def batch(snapshots: Sequence, model=None) -> BatchedSnapshots:
+    """dgl.batch + ``ndata['h'] = ent_embeds[ndata['id']]`` when a model is given (models/DynamicRGCN.py:92-93)."""
+    g = BatchedSnapshots(snapshots)
+    if model is not None:
+        ids = torch.from_numpy(g.ids).to(model.ent_embeds.device).long()
+        g.ndata["id"] = ids.view(-1, 1)
+        g.ndata["h"] = model.ent_embeds.detach().index_select(0, ids)
+    return g
+
+
+def _times_list(times) -> List[int]:
+    if torch.is_tensor(times):
+        return [int(t) for t in times.reshape(-1).tolist()]
+    return [int(t.item()) if torch.is_tensor(t) else int(t) for t in times]
+
+
+def _dense(x, rows: int, cols: int, dev) -> torch.Tensor:
+    x = torch.as_tensor(x, device=dev).detach().to(torch.float32).reshape(rows, cols).contiguous()
+    return x
+
+
+class _Step(object):
+    """Shared scaffolding of one encoder call."""
+
+    def __init__(self, encoder):
+        self.enc = encoder
+        self.m = m = owner_of(encoder)
+        self.rt = m.runtime                                   # raises without a CUDA device: no CPU route
+        self.dev = m.ent_embeds.device
+        self.D = m.embed_size
+        self.gru = m.args.module in ("GRRGCN", "BiGRRGCN")
+        self.bi = m.bidirectional
+        self.type1 = bool(getattr(m.args, "type1", False))
+        self.G = self.D if self.type1 else 3 * self.D
+        self.prog = lib.Program()
+        torch.cuda.current_stream(self.dev).synchronize()     # the pinned staging buffers below are reused call to call
+
+    def cell(self, layer, d):
+        if not self.bi:
+            return ("rnn", layer.rnn) if self.gru else ("time_weight", layer.time_weight)
+        if self.gru:
+            return ("forward_rnn", layer.forward_rnn) if d == "f" else ("backward_rnn", layer.backward_rnn)
+        return (("time_weight_forward", layer.time_weight_forward) if d == "f"
+                else ("time_weight_backward", layer.time_weight_backward))
+
+    def recurrent(self, layer, lname, rows, dirs, prevs, dts, ident, make_layer, out, relu, te, gru_kw):
+        """One recurrent layer over ``rows``: ``make_layer(terms=..., **outputs)`` builds its RGCN / isolated half."""
+        rt, n = self.rt, rows[1] - rows[0]
+        if self.gru:
+            cells = [self.cell(layer, d) for d in dirs]
+            w, b = rt._wih(lname, cells)
+            GL = self.G * len(dirs)
+            gi = torch.empty(max(n, 1), GL, dtype=torch.float32, device=self.dev)
+            self.prog.keepalive.append(gi)
+            self.prog.add(lib.OP_LAYER, make_layer(layer, relu, [], chain=(w, b, gi, GL)))
+            for j, d in enumerate(dirs):
+                self.prog.add(lib.OP_GRU, rt._gru(layer, cells[j][1], cells[j][0], rows, gi=gi, gi_ld=GL, gi_off=j * self.G,
+                                                  state=prevs[j], prev=ident.data_ptr(), dt=dts[j].data_ptr(), out=out,
+                                                  te=te and j == len(dirs) - 1, accumulate=j > 0, layer_name=lname,
+                                                  **gru_kw))
+        else:
+            extra = [rt._term(prevs[j], self.cell(layer, d)[1], index=ident.data_ptr(), dt=dts[j].data_ptr())
+                     for j, d in enumerate(dirs)]
+            self.prog.add(lib.OP_LAYER, make_layer(layer, relu, extra, h_out=out, te_out=te))
+
+
+def graph_step(encoder, bg: BatchedSnapshots, times, prev1, prev2, dts, dirs):
+    """One encoder call on a batch of snapshots.  prev1 / prev2 / dts: per direction in ``dirs`` the dense previous
+    states of layer 1 / layer 2 ``[N, D]`` and the time differences ``[N]`` (prev1 may be None with
+    --rec-only-last-layer).  -> (first, second)."""
+    st = _Step(encoder)
+    m, rt, D, dev = st.m, st.rt, st.D, st.dev
+    if m.family != "recurrent":
+        raise NotImplementedError("graph_step serves the recurrent encoders")
+    plan = bg.plan(_times_list(times))
+    R = plan.R
+    rows = (0, R)
+    x = _dense(bg.ndata["h"], R, D, dev)
+    first = torch.empty(R, D, dtype=torch.float32, device=dev)
+    second = torch.empty(R, D, dtype=torch.float32, device=dev)
+    if R == 0:
+        return first, second
+    dptr = rt.stage_plan(plan, st.prog, tag="step")
+    ident = torch.arange(R, dtype=torch.int32, device=dev)
+    prev2 = [_dense(p, R, D, dev) for p in prev2]
+    dts = [_dense(t, R, 1, dev).view(-1) for t in dts]
+    st.prog.keepalive += [x, ident, first, second] + prev2 + dts
+    l1, l2 = encoder.layer_1, encoder.layer_2
+    use_te = encoder.use_time_embedding
+    relu2 = st.bi                                             # BiRRGCN.py:202-203 vs RRGCN.py:186-187
+
+    def graph_layer(x_in):
+        def make(layer, relu, extra, **outputs):
+            return rt._layer(layer, rows, dptr, x=x_in, x_is_embed=False, act=relu,
+                             terms=[rt._term(x_in, layer.loop_weight)] + extra, **outputs)
+        return make
+
+    if encoder.rec_only_last_layer:
+        st.prog.add(lib.OP_LAYER, graph_layer(x)(l1, False, [], h_out=first))
+    else:
+        prev1 = [_dense(p, R, D, dev) for p in prev1]
+        st.prog.keepalive += prev1
+        st.recurrent(l1, "layer_1", rows, dirs, prev1, dts, ident, graph_layer(x), first, False, use_te, dict(dptr=dptr))
+    st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, graph_layer(first), second, relu2, use_te, dict(dptr=dptr))
+    st.prog.run()
+    if st.gru:
+        first = second                                        # the layer-2 GRU writes into the shared graph
+    return first, second
+
+
+def isolated_step(encoder, ent_embeds, t: int, prev1, prev2, dts, dirs):
+    """``forward_isolated`` over all rows of ``ent_embeds`` (RRGCN.py:206-217, BiRRGCN.py:242-257) -> second [M, D]."""
+    st = _Step(encoder)
+    m, rt, D, dev = st.m, st.rt, st.D, st.dev
+    if m.family != "recurrent":
+        raise NotImplementedError("isolated_step serves the recurrent encoders")
+    M = int(ent_embeds.shape[0])
+    rows = (0, M)
+    t = int(t.item()) if torch.is_tensor(t) else int(t)
+    x = _dense(ent_embeds, M, D, dev)
+    first = torch.empty(M, D, dtype=torch.float32, device=dev)
+    second = torch.empty(M, D, dtype=torch.float32, device=dev)
+    ident = torch.arange(M, dtype=torch.int32, device=dev)
+    prev2 = [_dense(p, M, D, dev) for p in prev2]
+    dts = [_dense(v, M, 1, dev).view(-1) for v in dts]
+    st.prog.keepalive += [x, ident, first, second] + prev2 + dts
+    rt._live = st.prog.keepalive
+    l1, l2 = encoder.layer_1, encoder.layer_2
+    use_te = encoder.use_time_embedding
+
+    def iso_layer(x_in):
+        def make(layer, relu, extra, **outputs):
+            return rt._layer(layer, rows, None, x=None, x_is_embed=False, graph=False, residual=True, act=relu,
+                             terms=[rt._term(x_in, layer.loop_weight)] + extra, row_time_scalar=t, **outputs)
+        return make
+
+    if encoder.rec_only_last_layer:
+        st.prog.add(lib.OP_LAYER, iso_layer(x)(l1, False, [], h_out=first))
+    else:
+        prev1 = [_dense(p, M, D, dev) for p in prev1]
+        st.prog.keepalive += prev1
+        st.recurrent(l1, "layer_1", rows, dirs, prev1, dts, ident, iso_layer(x), first, False, use_te,
+                     dict(row_time_scalar=t))
+    st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, iso_layer(first), second, st.bi, use_te,
+                 dict(row_time_scalar=t))
+    st.prog.run()
+    return second
+
+
+def static_graph_step(encoder, bg: BatchedSnapshots, times):
+    """RGCN.forward (models/RGCN.py:154-159): returns the batched graph with ``ndata['h']`` = layer-2 output (+ te)."""
+    st = _Step(encoder)
+    m, rt, D, dev = st.m, st.rt, st.D, st.dev
+    plan = bg.plan(_times_list(times))
+    R = plan.R
+    rows = (0, R)
+    out_g = bg.local_var()
+    x = _dense(bg.ndata["h"], R, D, dev)
+    h1 = torch.empty(R, D, dtype=torch.float32, device=dev)
+    out = torch.empty(R, D, dtype=torch.float32, device=dev)
+    if R > 0:
+        dptr = rt.stage_plan(plan, st.prog, tag="step")
+        st.prog.keepalive += [x, h1, out]
+        l1, l2 = encoder.layer_1, encoder.layer_2
+        st.prog.add(lib.OP_LAYER, rt._layer(l1, rows, dptr, x=x, x_is_embed=False, act=False,
+                                            terms=[rt._term(x, l1.loop_weight)], h_out=h1))
+        st.prog.add(lib.OP_LAYER, rt._layer(l2, rows, dptr, x=h1, x_is_embed=False, act=True,
+                                            terms=[rt._term(h1, l2.loop_weight)], h_out=out,
+                                            te_out=encoder.use_time_embedding))
+        st.prog.run()
+    out_g.ndata["h"] = out
+    return out_g
+
+
+def static_isolated_step(encoder, ent_embeds, t):
+    """RGCN.forward_isolated (models/RGCN.py:161-164)."""
+    st = _Step(encoder)
+    rt, D, dev = st.rt, st.D, st.dev
+    M = int(ent_embeds.shape[0])
+    rows = (0, M)
+    t = int(t.item()) if torch.is_tensor(t) else int(t)
+    x = _dense(ent_embeds, M, D, dev)
+    y1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+    out = torch.empty(M, D, dtype=torch.float32, device=dev)
+    st.prog.keepalive += [x, y1, out]
+    rt._live = st.prog.keepalive
+    l1, l2 = encoder.layer_1, encoder.layer_2
+    kw = dict(x=None, x_is_embed=False, graph=False, residual=True)
+    st.prog.add(lib.OP_LAYER, rt._layer(l1, rows, None, act=False, terms=[rt._term(x, l1.loop_weight)], h_out=y1, **kw))
+    st.prog.add(lib.OP_LAYER, rt._layer(l2, rows, None, act=True, terms=[rt._term(y1, l2.loop_weight)], h_out=out,
+                                        te_out=encoder.use_time_embedding, row_time_scalar=t, **kw))
+    st.prog.run()
+    return out
