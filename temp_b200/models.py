@@ -137,6 +137,7 @@ class TKG_Module(nn.Module):
             plan = self.plan(t_list)
         res = self.runtime.build(plan)
         res.program.run()
+        self.runtime.mark_run()
         return res
 
     @torch.no_grad()
@@ -158,6 +159,8 @@ class TKG_Module(nn.Module):
         res.programs[0].run()
         exchange_blocks(res.bufs["gi"], shard.row_bounds, group)
         res.programs[1].run()
+        if prepared is None:
+            self.runtime.mark_run()
         exchange_rows(res.state, shard.final_rows, rank, group, shard.cache)
         return res
 

@@ -152,6 +152,7 @@ class EncoderRuntime(object):
         self.fuse_scan = True      # consecutive GRU steps -> one persistent scan launch (chain-partitioned on the tcgen05 path)
         self._agg_rows = 1
         self._live = []
+        self._staged = {}
         # tcgen05 path where the shapes allow it (d == 128); False: fp32 SIMT kernels only.  The 3xTF32 tensor-core GEMMs
         # are ~5x noisier than fp32 FFMA arithmetic (7.6e-7 against 1.8e-7 relative to an fp64 evaluation on the bench
         # shape).  That is irrelevant for the torch GRU / linear cells, but the --type1 cell is torch.randn-initialised
@@ -167,6 +168,9 @@ class EncoderRuntime(object):
         self._plan = plan
         self._live = program.keepalive
         lay, total = plan.blob_layout()
+        pending = self._staged.pop(tag, None)
+        if pending is not None:
+            pending.synchronize()           # the last program staged under this tag still reads the pinned buffer
         host = self.ws.pinned(tag + "_host", total)
         plan.to_blob(host.numpy())
         dev = self.ws.get(tag + "_dev", total, torch.uint8)
@@ -174,6 +178,14 @@ class EncoderRuntime(object):
         program.keepalive += [host, dev]
         program.h2d_bytes = getattr(program, "h2d_bytes", 0) + total
         return {name: dev.data_ptr() + off for name, (off, _) in lay.items()}
+
+    def mark_run(self, tag: str = "plan") -> None:
+        """Call after launching a program staged under ``tag`` that will NOT be re-run once the tag is staged again
+        (``model.encode`` per call, the per-step encoder calls): the next ``stage_plan(tag)`` waits for this point
+        before it overwrites the pinned staging buffer the program's H2D copy reads."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._staged[tag] = ev
 
     # ---- op constructors ---------------------------------------------------------------------------
     def _layer(self, layer, rows, dptr, *, x, x_is_embed, terms, act, h_out=None, chain=None, te_out=False,

@@ -117,7 +117,10 @@ class _Step(object):
         self.type1 = bool(getattr(m.args, "type1", False))
         self.G = self.D if self.type1 else 3 * self.D
         self.prog = lib.Program()
-        torch.cuda.current_stream(self.dev).synchronize()     # the pinned staging buffers below are reused call to call
+
+    def run(self):
+        self.prog.run()
+        self.rt.mark_run("step")                              # the pinned staging buffer is reused call to call
 
     def cell(self, layer, d):
         if not self.bi:
@@ -186,7 +189,7 @@ def graph_step(encoder, bg: BatchedSnapshots, times, prev1, prev2, dts, dirs):
         st.prog.keepalive += prev1
         st.recurrent(l1, "layer_1", rows, dirs, prev1, dts, ident, graph_layer(x), first, False, use_te, dict(dptr=dptr))
     st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, graph_layer(first), second, relu2, use_te, dict(dptr=dptr))
-    st.prog.run()
+    st.run()
     if st.gru:
         first = second                                        # the layer-2 GRU writes into the shared graph
     return first, second
@@ -227,7 +230,7 @@ def isolated_step(encoder, ent_embeds, t: int, prev1, prev2, dts, dirs):
                      dict(row_time_scalar=t))
     st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, iso_layer(first), second, st.bi, use_te,
                  dict(row_time_scalar=t))
-    st.prog.run()
+    st.run()
     return second
 
 
@@ -251,7 +254,7 @@ def static_graph_step(encoder, bg: BatchedSnapshots, times):
         st.prog.add(lib.OP_LAYER, rt._layer(l2, rows, dptr, x=h1, x_is_embed=False, act=True,
                                             terms=[rt._term(h1, l2.loop_weight)], h_out=out,
                                             te_out=encoder.use_time_embedding))
-        st.prog.run()
+        st.run()
     out_g.ndata["h"] = out
     return out_g
 
@@ -273,5 +276,5 @@ def static_isolated_step(encoder, ent_embeds, t):
     st.prog.add(lib.OP_LAYER, rt._layer(l1, rows, None, act=False, terms=[rt._term(x, l1.loop_weight)], h_out=y1, **kw))
     st.prog.add(lib.OP_LAYER, rt._layer(l2, rows, None, act=True, terms=[rt._term(y1, l2.loop_weight)], h_out=out,
                                         te_out=encoder.use_time_embedding, row_time_scalar=t, **kw))
-    st.prog.run()
+    st.run()
     return out
