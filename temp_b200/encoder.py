@@ -208,3 +208,24 @@ class SARGCN(_TwoLayer):
         args.use_time_embedding = True
         l1 = RGCNLayer if args.rec_only_last_layer else SARGCNLayer
         super().__init__(args, l1, SARGCNLayer, hidden_size, embed_size, num_rels, total_time, True, "relu")
+
+    # per-step calls of the reference's drivers, on the CUDA path (temp_b200/stepwise.py)
+    def forward(self, batched_graph, time_batched_list_t, node_sizes=None):
+        """models/SARGCN.py:103-107 (history steps) -> (first + te, second + te)."""
+        from .stepwise import attention_history_step
+        return attention_history_step(self, batched_graph, time_batched_list_t)
+
+    def forward_final(self, batched_graph, first_layer_prev_embeddings, second_layer_prev_embeddings, time_diff,
+                      local_attn_mask, time_batched_list_t, node_sizes=None):
+        """models/SARGCN.py:109-117: attention of the current step over the dense history ``[N, T, D]`` under the
+        additive mask ``[N, T + 1]``."""
+        from .stepwise import attention_final_step
+        return attention_final_step(self, batched_graph, first_layer_prev_embeddings, second_layer_prev_embeddings,
+                                    time_diff, local_attn_mask, time_batched_list_t)
+
+    def forward_isolated(self, ent_embeds, first_layer_prev_embeddings, second_layer_prev_embeddings, time_diff,
+                         local_attn_mask, time):
+        """models/SARGCN.py:119-125."""
+        from .stepwise import attention_isolated_step
+        return attention_isolated_step(self, ent_embeds, first_layer_prev_embeddings, second_layer_prev_embeddings,
+                                       time_diff, local_attn_mask, time)

@@ -14,13 +14,16 @@ instead calls the encoder once per time step with dense tensors:
     BiRRGCN.forward_one_direction(batched_graph, first_prev, second_prev, dt, times, node_sizes, forward)   228-240
     BiRRGCN.forward_isolated(ent_embeds, first_prev_f, second_prev_f, dt_f, first_prev_b, second_prev_b, dt_b, time)
                                                                                               models/BiRRGCN.py:242-257
+    SARGCN.forward(batched_graph, times, node_sizes)                                          models/SARGCN.py:103-107
+    SARGCN.forward_final(batched_graph, prev1, prev2, time_diff, local_attn_mask, times, node_sizes)       109-117
+    SARGCN.forward_isolated(ent_embeds, prev1, prev2, time_diff, local_attn_mask, time)                    119-125
 
 Those methods (temp_b200/encoder.py) land here: one call = one short launch program of the same kernels
 (``temp_rgcn_layer_fwd`` with the chained input-gate GEMM, ``temp_gru_fwd``), previous states read from the caller's
 dense ``[N, D]`` tensors through an identity row map.  ``batched_graph`` is a ``BatchedSnapshots`` (the subset of
 ``dgl.batch`` the encoders use: ``ndata['h']``, ``ndata['id']``, ``number_of_nodes()``, ``local_var()``).
 The graph-aliasing quirk of the GRU flavours (``first`` and ``second`` are the same tensor) is kept.
-Inference only (no autograd); the post-ensemble / impute variants are not built.
+Inference only (no autograd); the post-ensemble / impute / EMA variants are not built.
 """
 from __future__ import annotations
 
@@ -276,5 +279,154 @@ def static_isolated_step(encoder, ent_embeds, t):
     st.prog.add(lib.OP_LAYER, rt._layer(l1, rows, None, act=False, terms=[rt._term(x, l1.loop_weight)], h_out=y1, **kw))
     st.prog.add(lib.OP_LAYER, rt._layer(l2, rows, None, act=True, terms=[rt._term(y1, l2.loop_weight)], h_out=out,
                                         te_out=encoder.use_time_embedding, row_time_scalar=t, **kw))
+    st.run()
+    return out
+
+
+# ---- SARGCN (models/SARGCN.py:103-125) -----------------------------------------------------------------------------
+def _attn_inputs(st, prevs, mask, time_diff, n):
+    """Dense ``prev [n, T, D]`` histories + additive ``mask [n, T + 1]`` (0 = active slot, -10e9 = inactive;
+    models/SelfAttentionRGCN.py:104-120) -> flattened history rows, slot map (-1 = inactive), tau."""
+    D, dev = st.D, st.dev
+    prevs = [None if p is None else torch.as_tensor(p, device=dev).detach().float().contiguous() for p in prevs]
+    T = int(next(p for p in prevs if p is not None).shape[1])
+    mask = torch.as_tensor(mask, device=dev).detach().float().reshape(n, T + 1)
+    rows = torch.arange(n * T, dtype=torch.int32, device=dev).view(n, T)
+    slot = torch.where(mask[:, :T] > -1.0, rows, torch.full_like(rows, -1)).contiguous()
+    tau = torch.as_tensor(time_diff, device=dev).detach().float().reshape(-1).contiguous()
+    if tau.numel() != T + 1:
+        raise ValueError("time_diff must have one entry per history slot plus the current step")
+    flat = [None if p is None else p.reshape(n * T, D) for p in prevs]
+    st.prog.keepalive += [slot, tau] + [f for f in flat if f is not None]
+    return flat, slot, tau, T
+
+
+def _attn_layer(st, layer, lname, make_layer, hist_flat, slot, tau, T, n, out, combine, h_out=None):
+    """q, k, v of the current rows by the chained GEMM of the layer launch (time embedding added on the way in), k, v of
+    the dense history rows by one library GEMM, then the attention kernel (SARGCN.py:25-53)."""
+    rt, D, dev = st.rt, st.D, st.dev
+    kvw = [layer.k_linear.weight, layer.v_linear.weight]
+    qkvw = [layer.q_linear.weight] + kvw
+    kv_t = rt.prep.cat_t(lname + ".kv_t", kvw)
+    qkv_t = rt.prep.cat_t(lname + ".qkv_t", qkvw)
+    if rt.use_tc:
+        rt._chain_packed[qkv_t.data_ptr()] = rt.prep.packed(lname + ".qkv_packed", qkv_t, qkvw)
+    qkv = torch.empty(max(n, 1), 3 * D, dtype=torch.float32, device=dev)
+    kv_hist = torch.mm(hist_flat, kv_t) if T > 0 else None
+    st.prog.keepalive += [qkv, kv_hist]
+    kw = dict(te_chain=True, chain=(qkv_t, None, qkv, 3 * D))
+    if h_out is not None:
+        kw["h_out"] = h_out
+    st.prog.add(lib.OP_LAYER, make_layer(layer, **kw))
+    a = lib.AttnArgs()
+    a.row0, a.row1, a.d, a.heads = 0, n, D, layer.h
+    a.qkv = qkv.data_ptr()
+    a.kv_hist = kv_hist.data_ptr() if T > 0 else None
+    a.slot_row = slot.data_ptr() if T > 0 else None
+    a.n_slots = T
+    a.tau = tau.data_ptr()
+    wb = rt._decay_wb(layer, lname)
+    a.decay_wb = None if wb is None else wb.data_ptr()
+    a.combine_max = int(combine)
+    a.out = out.data_ptr()
+    st.prog.add(lib.OP_ATTN, a)
+
+
+def attention_history_step(encoder, bg: BatchedSnapshots, times):
+    """SARGCN.forward (models/SARGCN.py:103-107): two plain layers; both outputs carry their time embedding, layer 2
+    consumes layer 1 WITHOUT it.  -> (first + te1, second + te2)."""
+    st = _Step(encoder)
+    rt, D, dev = st.rt, st.D, st.dev
+    plan = bg.plan(_times_list(times))
+    R = plan.R
+    rows = (0, R)
+    x = _dense(bg.ndata["h"], R, D, dev)
+    h1 = torch.empty(R, D, dtype=torch.float32, device=dev)
+    first = torch.empty(R, D, dtype=torch.float32, device=dev)
+    second = torch.empty(R, D, dtype=torch.float32, device=dev)
+    if R == 0:
+        return first, second
+    dptr = rt.stage_plan(plan, st.prog, tag="step")
+    st.prog.keepalive += [x, h1, first, second]
+    l1, l2 = encoder.layer_1, encoder.layer_2
+    st.prog.add(lib.OP_LAYER, rt._layer(l1, rows, dptr, x=x, x_is_embed=False, act=False,
+                                        terms=[rt._term(x, l1.loop_weight)], h_out=h1))
+    st.prog.add(lib.OP_LAYER, rt._layer(l2, rows, dptr, x=h1, x_is_embed=False, act=True,
+                                        terms=[rt._term(h1, l2.loop_weight)], h_out=second, te_out=True))
+    for inst in plan.final.instances:                       # first = h1 + te1[t_g], one row-block copy per graph
+        a = lib.ScatterArgs()
+        a.n, a.d = int(inst.n), D
+        a.src = h1.data_ptr() + inst.row0 * D * 4
+        a.dst = first.data_ptr() + inst.row0 * D * 4
+        a.src_index = a.dst_index = None
+        a.add_row = l1.time_embed.data_ptr() + int(inst.time) * D * 4
+        st.prog.add(lib.OP_SCATTER, a)
+    st.run()
+    return first, second
+
+
+def attention_final_step(encoder, bg: BatchedSnapshots, prev1, prev2, time_diff, mask, times):
+    """SARGCN.forward_final (models/SARGCN.py:109-117) -> attention output of the batched nodes."""
+    st = _Step(encoder)
+    rt, D, dev = st.rt, st.D, st.dev
+    plan = bg.plan(_times_list(times))
+    R = plan.R
+    rows = (0, R)
+    out = torch.empty(R, D, dtype=torch.float32, device=dev)
+    if R == 0:
+        return out
+    x = _dense(bg.ndata["h"], R, D, dev)
+    h1 = torch.empty(R, D, dtype=torch.float32, device=dev)
+    dptr = rt.stage_plan(plan, st.prog, tag="step")
+    (f1, f2), slot, tau, T = _attn_inputs(st, [None if encoder.rec_only_last_layer else prev1, prev2], mask, time_diff, R)
+    st.prog.keepalive += [x, h1, out]
+    l1, l2 = encoder.layer_1, encoder.layer_2
+
+    def graph_layer(x_in, act):
+        def make(layer, **outputs):
+            return rt._layer(layer, rows, dptr, x=x_in, x_is_embed=False, act=act,
+                             terms=[rt._term(x_in, layer.loop_weight)], **outputs)
+        return make
+
+    if encoder.rec_only_last_layer:
+        st.prog.add(lib.OP_LAYER, graph_layer(x, False)(l1, h_out=h1))
+    else:
+        _attn_layer(st, l1, "layer_1", graph_layer(x, False), f1, slot, tau, T, R, out, False, h_out=h1)
+    _attn_layer(st, l2, "layer_2", graph_layer(h1, True), f2, slot, tau, T, R, out, not encoder.rec_only_last_layer)   # JK max
+    st.run()
+    return out
+
+
+def attention_isolated_step(encoder, ent_embeds, prev1, prev2, time_diff, mask, t):
+    """SARGCN.forward_isolated (models/SARGCN.py:119-125)."""
+    st = _Step(encoder)
+    rt, D, dev = st.rt, st.D, st.dev
+    M = int(ent_embeds.shape[0])
+    rows = (0, M)
+    t = int(t.item()) if torch.is_tensor(t) else int(t)
+    x = _dense(ent_embeds, M, D, dev)
+    first = torch.empty(M, D, dtype=torch.float32, device=dev)
+    out = torch.empty(M, D, dtype=torch.float32, device=dev)
+    (f1, f2), slot, tau, T = _attn_inputs(st, [None if encoder.rec_only_last_layer else prev1, prev2], mask, time_diff, M)
+    st.prog.keepalive += [x, first, out]
+    rt._live = st.prog.keepalive
+    l1, l2 = encoder.layer_1, encoder.layer_2
+
+    def iso_layer(x_in, act):
+        def make(layer, **outputs):
+            return rt._layer(layer, rows, None, x=None, x_is_embed=False, graph=False, residual=True, act=act,
+                             terms=[rt._term(x_in, layer.loop_weight)], row_time_scalar=t, **outputs)
+        return make
+
+    if encoder.rec_only_last_layer:
+        st.prog.add(lib.OP_LAYER, iso_layer(x, False)(l1, h_out=first))
+        _attn_layer(st, l2, "layer_2", iso_layer(first, True), f2, slot, tau, T, M, out, False)
+    else:
+        _attn_layer(st, l1, "layer_1", iso_layer(x, False), f1, slot, tau, T, M, first, False)
+        a = lib.ScatterArgs()                                # out = first, then max with the layer-2 attention (SARGCN.py:125)
+        a.n, a.d, a.src, a.dst = M, D, first.data_ptr(), out.data_ptr()
+        a.src_index = a.dst_index = a.add_row = None
+        st.prog.add(lib.OP_SCATTER, a)
+        _attn_layer(st, l2, "layer_2", iso_layer(first, True), f2, slot, tau, T, M, out, True)
     st.run()
     return out

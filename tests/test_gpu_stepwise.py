@@ -109,6 +109,46 @@ def test_static_encoder_step_calls_match_oracle(name):
         _close(enc.forward_isolated(model.ent_embeds, times[2]), oracle.enc_static_isolated(times[2]))
 
 
+@pytest.mark.parametrize("name", ["sargcn_tiny_d128_last", "sargcn_tiny_d128_full", "sargcn_tiny_d128_lambda",
+                                  "bisargcn_tiny_d128_last", "bisargcn_tiny_d64_full", "bisargcn_icews_d128_L8"])
+def test_attention_encoder_step_calls_match_oracle(name):
+    """SARGCN.forward / forward_final / forward_isolated (models/SARGCN.py:103-125) with dense [N, T, D] histories and
+    the additive mask of models/SelfAttentionRGCN.py:104-120 (0 active, -10e9 inactive)."""
+    case = CASE_BY_NAME[name]
+    model, oracle = product_model(case), oracle_model(case)
+    enc = model.ent_encoder
+    times, snaps, bg, _, _, ograph = _inputs(model, oracle, 3, 6)
+    D, M = model.embed_size, model.num_ents
+    tau = oracle._tau()
+    T = tau.numel() - 1
+    g = torch.Generator().manual_seed(9)
+
+    def dense(n):
+        mask = torch.where(torch.rand(n, T + 1, generator=g) < 0.4, torch.tensor(-10e9), torch.tensor(0.0))
+        mask[:, T] = 0.0                                                   # the current step always attends to itself
+        mask[: n // 4, :T] = -10e9                                         # rows without any history
+        prev = [torch.randn(n, T, D, generator=g) * 0.1 * (mask[:, :T] == 0).unsqueeze(-1) for _ in range(2)]
+        return prev, mask
+
+    cu = lambda x: x.cuda()
+    first, second = enc.forward(bg, torch.tensor(times), bg.node_sizes)
+    with torch.no_grad():
+        of, os_ = oracle.enc_attention_history(ograph, times)
+    _close(first, of)
+    _close(second, os_)
+    n = bg.number_of_nodes()
+    prev, mask = dense(n)
+    got = enc.forward_final(bg, cu(prev[0]), cu(prev[1]), cu(tau), cu(mask), torch.tensor(times), bg.node_sizes)
+    with torch.no_grad():
+        want = oracle.enc_attention_final(ograph, times, prev[0], prev[1], tau, mask)
+    _close(got, want)
+    prev, mask = dense(M)
+    got = enc.forward_isolated(model.ent_embeds, cu(prev[0]), cu(prev[1]), cu(tau), cu(mask), times[1])
+    with torch.no_grad():
+        want = oracle.enc_attention_isolated(times[1], prev[0], prev[1], tau, mask)
+    _close(got, want)
+
+
 @pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "grrgcn_tiny_d128_full", "rrgcn_tiny_d128_full"])
 def test_window_driven_step_by_step_equals_the_one_program_forward(name):
     """models/DynamicRGCN.py:156-174 restated over the per-step calls: dense [B, 2, M, D] history re-zeroed every step
