@@ -132,13 +132,50 @@ class TKG_Module(nn.Module):
 
     @torch.no_grad()
     def encode(self, t_list=None, plan: Optional[WindowPlan] = None) -> EncodeResult:
-        """The hot path (region R1 of SURVEY section 8d): history steps + final step -> per-graph states."""
-        if plan is None:
-            plan = self.plan(t_list)
-        res = self.runtime.build(plan)
+        """The hot path (region R1 of SURVEY section 8d): history steps + final step -> per-graph states.
+
+        Called with timestamps, the planned window batch and its launch program are kept (``encode_cache_size`` most
+        recent batches, each with its own staged plan copy on the device): evaluation walks the same batches every epoch,
+        and a repeat costs the kernels only.  The cache is dropped whenever a parameter changed or moved (the programs
+        hold pointers to prepared weight images).  Results live in the runtime's workspace: consume ``res.out`` before
+        the next call."""
+        if plan is not None:
+            res = self.runtime.build(plan)
+            res.program.run()
+            self.runtime.mark_run()
+            return res
+        key = tuple(_as_int_list(t_list))
+        cache = self._encode_cache_for_current_weights()
+        hit = cache.get(key) if self.encode_cache_size > 0 else None
+        if hit is not None:
+            hit.replay.run()
+            return hit
+        plan = self.plan(t_list)
+        if self.encode_cache_size <= 0:
+            return self.encode(plan=plan)
+        slot = self._encode_slot = (getattr(self, "_encode_slot", -1) + 1) % self.encode_cache_size
+        for k in [k for k, v in cache.items() if v.cache_slot == slot]:
+            del cache[k]                                                 # the slot's staged plan copy is about to be overwritten
+        tag = "plan_c%d" % slot
+        res = self.runtime.build(plan, tag=tag)
         res.program.run()
-        self.runtime.mark_run()
+        self.runtime.mark_run(tag)
+        res.cache_slot = slot
+        res.replay = lib.Program()                                       # the same launches without the plan upload
+        res.replay.ops = [o for o in res.program.ops if o.kind != lib.OP_H2D]
+        res.replay.keepalive = res.program.keepalive
+        cache[key] = res
         return res
+
+    encode_cache_size = 128
+
+    def _encode_cache_for_current_weights(self) -> dict:
+        rt = self.runtime
+        stamp = (id(self.graph_dict_train), len(self.graph_dict_train), self.train_seq_len, self.use_native_planner,
+                 id(rt), rt.use_tc, rt.fuse_scan) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_encode_cache_stamp", None) != stamp:
+            self._encode_cache, self._encode_cache_stamp = {}, stamp
+        return self._encode_cache
 
     @torch.no_grad()
     def encode_sharded(self, t_list=None, plan: Optional[WindowPlan] = None, group=None, prepared=None) -> EncodeResult:

@@ -302,11 +302,11 @@ class EncoderRuntime(object):
         return w, self.prep.cat(tag + ".b_ih", bs)
 
     # ---- programs ----------------------------------------------------------------------------------
-    def build(self, plan: WindowPlan, with_h2d: bool = True) -> EncodeResult:
+    def build(self, plan: WindowPlan, with_h2d: bool = True, tag: str = "plan") -> EncodeResult:
         m = self.model
         fam = m.family
         prog = lib.Program()
-        dptr = self.stage_plan(plan, prog)
+        dptr = self.stage_plan(plan, prog, tag)
         if not with_h2d:
             prog.ops = [o for o in prog.ops if o.kind != lib.OP_H2D]
         if fam == "static":

@@ -302,6 +302,33 @@ def test_reference_style_eval_calls_agree_with_the_fast_entry():
     assert torch.equal(ranks, ranks2) and abs(loss - loss2) < 1e-6
 
 
+def test_encode_keeps_launch_programs_of_seen_batches_and_drops_them_with_the_weights():
+    """model.encode(t_list) replays the kept launch program of a batch it has seen (no planning, no plan upload); a
+    parameter update or a full slot ring must never serve stale results."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    model = product_model(case)
+    times = sorted(model.graph_dict_train.keys())
+    batches = [case["t_list"], times[4:7], times[8:12], times[3:5]]
+    model.encode_cache_size = 0
+    want = [model.encode(b).out.clone() for b in batches]
+    model.encode_cache_size = 2                                    # smaller than the number of batches: slots get reused
+    for _ in range(3):
+        for b, w in zip(batches, want):
+            assert torch.equal(model.encode(b).out, w)
+    model.encode_cache_size = 128
+    first = model.encode(batches[0])
+    again = model.encode(batches[0])
+    assert again is first and torch.equal(again.out, want[0])      # a replay, bit-identical
+    assert all(o.kind != __import__("temp_b200.lib", fromlist=["OP_H2D"]).OP_H2D for o in first.replay.ops)
+    with torch.no_grad():
+        model.ent_encoder.layer_2.loop_weight.mul_(1.5)            # an optimizer step bumps the parameter version
+    changed = model.encode(batches[0])
+    assert changed is not first and not torch.equal(changed.out, want[0])
+    model.encode_cache_size = 0
+    assert torch.equal(model.encode(batches[0]).out, changed.out)
+
+
 def _rank_bounds(model, fn, ent_mean, rel, table, samples, graph, t, mode, eps):
     """[lowest, highest] 1-indexed rank of every query's target when sigmoid values closer than eps count as ties --
     evaluated in float64 from the reference's formulation (utils/evaluation.py:53-80)."""
