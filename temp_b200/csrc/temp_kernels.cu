@@ -727,6 +727,30 @@ __device__ __forceinline__ float score_partial(const float4* row, const float (&
   return part;
 }
 
+// compile-time width (PER4 float4 loads per lane): branch-free, so that independent candidates' loads can be batched
+template <int PER4>
+__device__ __forceinline__ void score_load(float4 (&v)[PER4], const float4* row) {
+#pragma unroll
+  for (int t4 = 0; t4 < PER4; ++t4) v[t4] = __ldg(row + t4);
+}
+
+template <int PER4>
+__device__ __forceinline__ float score_dot(const float4 (&v)[PER4], const float (&q)[kScoreMaxPerLane], bool l1) {
+  float part = 0.f;
+#pragma unroll
+  for (int t4 = 0; t4 < PER4; ++t4) {
+    if (l1) {
+      part += fabsf(v[t4].x - q[4 * t4]) + fabsf(v[t4].y - q[4 * t4 + 1]) + fabsf(v[t4].z - q[4 * t4 + 2]) + fabsf(v[t4].w - q[4 * t4 + 3]);
+    } else {
+      part = fmaf(v[t4].x, q[4 * t4], part);
+      part = fmaf(v[t4].y, q[4 * t4 + 1], part);
+      part = fmaf(v[t4].z, q[4 * t4 + 2], part);
+      part = fmaf(v[t4].w, q[4 * t4 + 3], part);
+    }
+  }
+  return part;
+}
+
 __device__ __forceinline__ float score_reduce8(float part) {
   part += __shfl_xor_sync(0xffffffffu, part, 4);
   part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -786,6 +810,7 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
 // Counts are integers added with atomics, so the result does not depend on the schedule.
 __device__ __forceinline__ float rank_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+template <int PER4>
 __global__ void __launch_bounds__(kThreads) rank_filtered_kernel(const TempRankArgs p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qi = blockIdx.x;
@@ -804,14 +829,25 @@ __global__ void __launch_bounds__(kThreads) rank_filtered_kernel(const TempRankA
   const int chunk = (p.num_ents + gridDim.y - 1) / gridDim.y;
   const int lo = blockIdx.y * chunk, hi = min(p.num_ents, lo + chunk);
   int count = 0;
-  for (int base = lo + warp * 4; base < hi; base += (kThreads / 32) * 4) {
-    const int j = base + grp;
-    float part = 0.f;
-    if (j < hi) part = score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(j) * D + c0), q, per, l1);
-    part = score_reduce8(part);
-    if (j < hi && j != tgt && sub == 0) {
-      const float v = rank_sigmoid(l1 ? -part : part);
-      count += (v > vt || (v == vt && j < tgt)) ? 1 : 0;
+  // kRankUnroll independent candidate groups per warp iteration: their row loads are all in flight before the first
+  // reduction (one group of 4 rows per warp does not cover the L2 latency)
+  constexpr int kRankUnroll = PER4 <= 4 ? 4 : 2;
+  constexpr int kStride = (kThreads / 32) * 4;
+  for (int base = lo + warp * 4; base < hi; base += kStride * kRankUnroll) {
+    float4 v[kRankUnroll][PER4];
+#pragma unroll
+    for (int u = 0; u < kRankUnroll; ++u) {
+      const int j = min(base + u * kStride + grp, hi - 1);          // clamped: the load is always in range, the count is not taken
+      score_load<PER4>(v[u], reinterpret_cast<const float4*>(p.table + static_cast<size_t>(j) * D + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < kRankUnroll; ++u) {
+      const int j = base + u * kStride + grp;
+      const float tot = score_reduce8(score_dot<PER4>(v[u], q, l1));
+      if (j < hi && j != tgt && sub == 0) {
+        const float val = rank_sigmoid(l1 ? -tot : tot);
+        count += (val > vt || (val == vt && j < tgt)) ? 1 : 0;
+      }
     }
   }
   if (blockIdx.y == 0 && p.filter_ptr != nullptr) {
@@ -1109,7 +1145,17 @@ int launch_rank_filtered(const TempRankArgs* a, cudaStream_t st) {
   const int max_chunks = (a->num_ents + 32 * (kThreads / 32) - 1) / (32 * (kThreads / 32));
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
-  rank_filtered_kernel<<<dim3(a->n_query, chunks), kThreads, 0, st>>>(*a);
+  const dim3 grid(a->n_query, chunks);
+  switch (a->d / 32) {
+    case 1: rank_filtered_kernel<1><<<grid, kThreads, 0, st>>>(*a); break;
+    case 2: rank_filtered_kernel<2><<<grid, kThreads, 0, st>>>(*a); break;
+    case 3: rank_filtered_kernel<3><<<grid, kThreads, 0, st>>>(*a); break;
+    case 4: rank_filtered_kernel<4><<<grid, kThreads, 0, st>>>(*a); break;
+    case 5: rank_filtered_kernel<5><<<grid, kThreads, 0, st>>>(*a); break;
+    case 6: rank_filtered_kernel<6><<<grid, kThreads, 0, st>>>(*a); break;
+    case 7: rank_filtered_kernel<7><<<grid, kThreads, 0, st>>>(*a); break;
+    default: rank_filtered_kernel<8><<<grid, kThreads, 0, st>>>(*a); break;
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "rank_filtered_kernel launch");
   return TEMP_OK;

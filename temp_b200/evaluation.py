@@ -21,6 +21,7 @@ class EvaluationFilter(object):
         self.args, self.calc_score = args, calc_score
         self.graph_dict_train, self.graph_dict_val, self.graph_dict_test = graph_dict_train, graph_dict_val, graph_dict_test
         self.true_heads, self.true_tails = {}, {}
+        self._filter_cache = {}
 
     def _true_sets(self, t):
         if t not in self.true_heads:
@@ -81,14 +82,23 @@ class EvaluationFilter(object):
             ent_mean, rel, table = ent_mean.contiguous(), rel_enc_means.detach().contiguous(), all_ent_embeds.contiguous()
             out = torch.empty(2 * Q, dtype=torch.long, device=dev)
             keep = []
+            digest = hash(samples_cpu.numpy().tobytes())
             for k, mode in enumerate(("head", "tail")):                # ranks_s first, then ranks_o (line 48)
-                ptr, flat = self.filter_lists(samples_cpu, time, graph, mode)
-                ptr_d, flat_d = torch.from_numpy(ptr).to(dev), torch.from_numpy(flat).to(dev)
+                # the lists depend on (timestamp, queries) only: evaluation asks for the same ones every epoch
+                ck = (int(time), mode, Q, digest, id(graph), str(dev))
+                hit = self._filter_cache.get(ck)
+                if hit is None:
+                    ptr, flat = self.filter_lists(samples_cpu, time, graph, mode)
+                    hit = (torch.from_numpy(ptr).to(dev), torch.from_numpy(flat).to(dev), int(flat.shape[0]))
+                    if len(self._filter_cache) >= 4096:
+                        self._filter_cache.clear()
+                    self._filter_cache[ck] = hit
+                ptr_d, flat_d, n_flat = hit
                 target = ids[samples[:, 2 if mode == "tail" else 0]].contiguous()
                 keep.append((ptr_d, flat_d, target))
                 a = lib.RankArgs(Q, int(table.shape[0]), D, lib.SCORE_FN[fn], int(mode == "tail"), ent_mean.data_ptr(),
                                  rel.data_ptr(), table.data_ptr(), samples.data_ptr(), target.data_ptr(), ptr_d.data_ptr(),
-                                 flat_d.data_ptr() if flat.shape[0] else ptr_d.data_ptr(), out[k * Q:].data_ptr())
+                                 flat_d.data_ptr() if n_flat else ptr_d.data_ptr(), out[k * Q:].data_ptr())
                 lib.check(lib.load().temp_rank_filtered_fwd(C.byref(a), C.c_void_p(lib.current_stream())),
                           "temp_rank_filtered_fwd")
             return out
