@@ -735,20 +735,23 @@ __device__ __forceinline__ void score_load(float4 (&v)[PER4], const float4* row)
 }
 
 template <int PER4>
-__device__ __forceinline__ float score_dot(const float4 (&v)[PER4], const float (&q)[kScoreMaxPerLane], bool l1) {
-  float part = 0.f;
+__device__ __forceinline__ float score_dot(const float4 (&v)[PER4], const float (&q)[4 * PER4], bool l1) {
+  float a = 0.f, b = 0.f, c = 0.f, d = 0.f;   // four short chains instead of one of 4 * PER4 dependent operations
 #pragma unroll
   for (int t4 = 0; t4 < PER4; ++t4) {
     if (l1) {
-      part += fabsf(v[t4].x - q[4 * t4]) + fabsf(v[t4].y - q[4 * t4 + 1]) + fabsf(v[t4].z - q[4 * t4 + 2]) + fabsf(v[t4].w - q[4 * t4 + 3]);
+      a += fabsf(v[t4].x - q[4 * t4]);
+      b += fabsf(v[t4].y - q[4 * t4 + 1]);
+      c += fabsf(v[t4].z - q[4 * t4 + 2]);
+      d += fabsf(v[t4].w - q[4 * t4 + 3]);
     } else {
-      part = fmaf(v[t4].x, q[4 * t4], part);
-      part = fmaf(v[t4].y, q[4 * t4 + 1], part);
-      part = fmaf(v[t4].z, q[4 * t4 + 2], part);
-      part = fmaf(v[t4].w, q[4 * t4 + 3], part);
+      a = fmaf(v[t4].x, q[4 * t4], a);
+      b = fmaf(v[t4].y, q[4 * t4 + 1], b);
+      c = fmaf(v[t4].z, q[4 * t4 + 2], c);
+      d = fmaf(v[t4].w, q[4 * t4 + 3], d);
     }
   }
-  return part;
+  return (a + b) + (c + d);
 }
 
 __device__ __forceinline__ float score_reduce8(float part) {
@@ -802,7 +805,8 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
 // ------------------------------------------------------------------------------------------------
 // filtered ranking: position of the target in the stable descending sort of sigmoid(masked scores)
 // ------------------------------------------------------------------------------------------------
-// grid (query, entity chunk): the CTA's warps walk the chunk's rows of the all-entity table, 4 candidates per warp
+// grid (group of kRankQ queries, entity chunk): the CTA's warps walk the chunk's rows of the all-entity table once for
+// the group's queries, 4 candidates per warp
 // iteration exactly like the scorer above (8 lanes per candidate, the query vector in registers), and count the
 // candidates that sort ahead of the target; every candidate is first counted with its real score, then the CTA of
 // chunk 0 walks the query's filter list and replaces each filtered entity's contribution by that of sigmoid(-10e6)
@@ -810,28 +814,64 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
 // Counts are integers added with atomics, so the result does not depend on the schedule.
 __device__ __forceinline__ float rank_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+constexpr int kRankQ = 4;   // queries that share one pass over the table rows (the pass is L2-bandwidth bound per query)
+
 template <int PER4>
-__global__ void __launch_bounds__(kThreads) rank_filtered_kernel(const TempRankArgs p) {
+__global__ void __launch_bounds__(kThreads, PER4 <= 4 ? 2 : 1) rank_filtered_kernel(const TempRankArgs p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int qi = blockIdx.x;
   const int D = p.d, per = D >> 3, half = D >> 1;
   const int grp = lane >> 3, sub = lane & 7;
   const int c0 = sub * per;
-  const long long s_id = p.triples[3 * qi], r_id = p.triples[3 * qi + 1], o_id = p.triples[3 * qi + 2];
-  const float* fixed = p.ent_embed + static_cast<size_t>(p.corrupt_tail ? s_id : o_id) * D;
-  const float* rel = p.rel_embeds + static_cast<size_t>(r_id) * D;
-  float q[kScoreMaxPerLane];
-  score_query(q, fixed, rel, c0, per, half, p.score_fn, p.corrupt_tail);
   const bool l1 = p.score_fn == TEMP_SCORE_TRANSE;
-  const int tgt = static_cast<int>(p.target[qi]);
-  float vt = score_reduce8(score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(tgt) * D + c0), q, per, l1));
-  vt = rank_sigmoid(l1 ? -vt : vt);
+  // warp n < kRankQ forms query n's vector and the target's sigmoid once for the CTA; everybody picks them up from smem
+  __shared__ __align__(16) float sq[kRankQ][8 * kScoreMaxPerLane];
+  __shared__ float svt[kRankQ];
+  __shared__ int stgt[kRankQ];
+  if (warp < kRankQ) {
+    const int qi = min(blockIdx.x * kRankQ + warp, p.n_query - 1);   // a short last group repeats its last query (not written)
+    const long long s_id = p.triples[3 * qi], r_id = p.triples[3 * qi + 1], o_id = p.triples[3 * qi + 2];
+    const float* fixed = p.ent_embed + static_cast<size_t>(p.corrupt_tail ? s_id : o_id) * D;
+    const float* rel = p.rel_embeds + static_cast<size_t>(r_id) * D;
+    float full[kScoreMaxPerLane];
+    score_query(full, fixed, rel, c0, per, half, p.score_fn, p.corrupt_tail);
+    float qn[4 * PER4];
+#pragma unroll
+    for (int t = 0; t < 4 * PER4; ++t) qn[t] = full[t];
+    const int target = static_cast<int>(p.target[qi]);
+    float4 v[PER4];
+    score_load<PER4>(v, reinterpret_cast<const float4*>(p.table + static_cast<size_t>(target) * D + c0));
+    const float tot = score_reduce8(score_dot<PER4>(v, qn, l1));
+    if (grp == 0) {
+#pragma unroll
+      for (int t = 0; t < 4 * PER4; ++t) sq[warp][c0 + t] = qn[t];
+    }
+    if (lane == 0) {
+      svt[warp] = rank_sigmoid(l1 ? -tot : tot);
+      stgt[warp] = target;
+    }
+  }
+  __syncthreads();
+  float q[kRankQ][4 * PER4];
+#pragma unroll
+  for (int n = 0; n < kRankQ; ++n) {
+#pragma unroll
+    for (int t4 = 0; t4 < PER4; ++t4) {
+      const float4 w = *reinterpret_cast<const float4*>(&sq[n][c0 + 4 * t4]);
+      q[n][4 * t4] = w.x, q[n][4 * t4 + 1] = w.y, q[n][4 * t4 + 2] = w.z, q[n][4 * t4 + 3] = w.w;
+    }
+  }
+  // after the 8-lane reduction every lane of a candidate's group holds all kRankQ totals: lane sub == n finishes query n
+  // (sigmoid, comparison, count), so the kRankQ sigmoids of a candidate cost one pass instead of kRankQ
+  static_assert(kRankQ <= 8, "one finishing lane per query");
+  const int mine = sub < kRankQ ? sub : 0;
+  const bool finisher = sub < kRankQ;
+  const float vt = svt[mine];
+  const int tgt = stgt[mine];
+  int count = 0;
   const int chunk = (p.num_ents + gridDim.y - 1) / gridDim.y;
   const int lo = blockIdx.y * chunk, hi = min(p.num_ents, lo + chunk);
-  int count = 0;
-  // kRankUnroll independent candidate groups per warp iteration: their row loads are all in flight before the first
-  // reduction (one group of 4 rows per warp does not cover the L2 latency)
-  constexpr int kRankUnroll = PER4 <= 4 ? 4 : 2;
+  // two independent candidate groups per warp iteration: both groups' row loads are in flight before the first reduction
+  constexpr int kRankUnroll = 2;
   constexpr int kStride = (kThreads / 32) * 4;
   for (int base = lo + warp * 4; base < hi; base += kStride * kRankUnroll) {
     float4 v[kRankUnroll][PER4];
@@ -843,33 +883,46 @@ __global__ void __launch_bounds__(kThreads) rank_filtered_kernel(const TempRankA
 #pragma unroll
     for (int u = 0; u < kRankUnroll; ++u) {
       const int j = base + u * kStride + grp;
-      const float tot = score_reduce8(score_dot<PER4>(v[u], q, l1));
-      if (j < hi && j != tgt && sub == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int n = 0; n < kRankQ; ++n) {
+        const float tn = score_reduce8(score_dot<PER4>(v[u], q[n], l1));
+        tot = sub == n ? tn : tot;
+      }
+      if (finisher && j < hi && j != tgt) {
         const float val = rank_sigmoid(l1 ? -tot : tot);
         count += (val > vt || (val == vt && j < tgt)) ? 1 : 0;
       }
     }
   }
   if (blockIdx.y == 0 && p.filter_ptr != nullptr) {
-    const int f0 = p.filter_ptr[qi], f1 = p.filter_ptr[qi + 1];
-    for (int base = f0 + warp * 4; base < f1; base += (kThreads / 32) * 4) {
-      const int f = base + grp;
-      const int j = f < f1 ? p.filter_ids[f] : -1;
-      float part = 0.f;
-      if (j >= 0) part = score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(j) * D + c0), q, per, l1);
-      part = score_reduce8(part);
-      if (j >= 0 && j != tgt && sub == 0) {
-        const float v = rank_sigmoid(l1 ? -part : part);
-        const int real = (v > vt || (v == vt && j < tgt)) ? 1 : 0;
-        const int masked = (0.f == vt && j < tgt) ? 1 : 0;   // sigmoid(-10e6) == 0 exactly; 0 > vt never holds
-        count += masked - real;
+#pragma unroll
+    for (int n = 0; n < kRankQ; ++n) {
+      const int qi = blockIdx.x * kRankQ + n;
+      if (qi >= p.n_query) break;
+      const float vtn = svt[n];
+      const int tgn = stgt[n];
+      const int f0 = p.filter_ptr[qi], f1 = p.filter_ptr[qi + 1];
+      for (int base = f0 + warp * 4; base < f1; base += (kThreads / 32) * 4) {
+        const int f = base + grp;
+        const int j = f < f1 ? p.filter_ids[f] : -1;
+        float4 v[PER4];
+        score_load<PER4>(v, reinterpret_cast<const float4*>(p.table + static_cast<size_t>(max(j, 0)) * D + c0));
+        const float tot = score_reduce8(score_dot<PER4>(v, q[n], l1));
+        if (j >= 0 && j != tgn && sub == n) {                   // counted on query n's finishing lane
+          const float val = rank_sigmoid(l1 ? -tot : tot);
+          const int real = (val > vtn || (val == vtn && j < tgn)) ? 1 : 0;
+          const int masked = (0.f == vtn && j < tgn) ? 1 : 0;    // sigmoid(-10e6) == 0 exactly; 0 > vt never holds
+          count += masked - real;
+        }
       }
     }
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
-  if (lane == 0) {
-    if (blockIdx.y == 0 && warp == 0) count += 1;   // 1-indexed
+  count += __shfl_xor_sync(0xffffffffu, count, 8);              // the four candidate groups of the warp
+  count += __shfl_xor_sync(0xffffffffu, count, 16);
+  const int qi = blockIdx.x * kRankQ + lane;
+  if (lane < kRankQ && qi < p.n_query) {
+    if (blockIdx.y == 0 && warp == 0) count += 1;               // 1-indexed
     if (count != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.rank + qi), static_cast<unsigned long long>(static_cast<long long>(count)));
   }
 }
@@ -1140,12 +1193,13 @@ int launch_rank_filtered(const TempRankArgs* a, cudaStream_t st) {
   if (!aligned16(a->table)) return fail(TEMP_EINVAL, "rank table misaligned%s", "");
   cudaError_t e = cudaMemsetAsync(a->rank, 0, sizeof(int64_t) * static_cast<size_t>(a->n_query), st);
   if (e != cudaSuccess) return cuda_fail(e, "rank memset");
-  // entity chunks: about four CTAs per SM over the whole grid, at least 32 table rows per warp
-  int chunks = (148 * 4 + a->n_query - 1) / a->n_query;
+  // entity chunks: about two CTAs per SM over the whole grid, at least 32 table rows per warp
+  const int groups = (a->n_query + kRankQ - 1) / kRankQ;
+  int chunks = (148 * 2) / groups;                         // one wave of two CTAs per SM: never a few CTAs left for a second
   const int max_chunks = (a->num_ents + 32 * (kThreads / 32) - 1) / (32 * (kThreads / 32));
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
-  const dim3 grid(a->n_query, chunks);
+  const dim3 grid(groups, chunks);
   switch (a->d / 32) {
     case 1: rank_filtered_kernel<1><<<grid, kThreads, 0, st>>>(*a); break;
     case 2: rank_filtered_kernel<2><<<grid, kThreads, 0, st>>>(*a); break;
