@@ -241,6 +241,25 @@ class TKG_Module(nn.Module):
         return torch.mean(1.0 / rf), torch.mean((ranks <= 1).float()), torch.mean((ranks <= 3).float()), \
             torch.mean((ranks <= 10).float())
 
+    # ---- checkpoints of the reference (test.py:403-406: torch.load -> load_state_dict -> on_load_checkpoint) ----------
+    def on_load_checkpoint(self, checkpoint) -> None:
+        """pytorch-lightning hook the reference's test.py:406 calls after ``load_state_dict``; nothing to restore
+        beyond the parameters (prepared weight images and kept launch programs are keyed on parameter versions)."""
+
+    def on_save_checkpoint(self, checkpoint) -> None:
+        """pytorch-lightning hook; the checkpoint needs nothing beyond ``state_dict``."""
+
+    def load_reference_checkpoint(self, checkpoint, strict: bool = True):
+        """Loads a checkpoint written by the reference's trainer (a pytorch-lightning dict with ``state_dict``, or a
+        path to one) -- the parameter names are the reference's own, so the authors' published
+        checkpoints load unchanged."""
+        if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__"):
+            checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=False)   # holds an argparse.Namespace
+        state = checkpoint["state_dict"] if "state_dict" in checkpoint else checkpoint
+        out = self.load_state_dict(state, strict=strict)
+        self.on_load_checkpoint(checkpoint)
+        return out
+
     def configure_optimizers(self):
         return torch.optim.Adam(self.parameters(), lr=self.args.lr, weight_decay=0.0001)
 

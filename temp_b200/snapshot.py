@@ -169,6 +169,36 @@ class SnapshotStore(object):
                                     part[:, 1])
         return cls(num_ents, num_rels, train, valid, test, name=os.path.basename(os.path.normpath(path)))
 
+    # ---- binary cache of a parsed dataset (quadruple text -> cached binary) -------
+    def to_npz(self, path: str) -> None:
+        """One compressed .npz holding the three splits as flat arrays (per split: times, node / edge offsets per
+        snapshot, node ids, local src / dst, relation ids).  ``from_npz`` rebuilds the same snapshots without parsing
+        text; norms and CSR orders are derived data and recomputed on load exactly as from text."""
+        out = {"meta": np.asarray([self.num_ents, self.num_rels], dtype=np.int64), "name": np.asarray(self.name)}
+        for split, gd in (("train", self.train), ("valid", self.valid), ("test", self.test)):
+            snaps = list(gd.values())
+            cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)
+            out[split + "_times"] = np.asarray([s.time for s in snaps], dtype=np.int64)
+            out[split + "_node_off"] = np.cumsum([0] + [s.num_nodes for s in snaps]).astype(np.int64)
+            out[split + "_edge_off"] = np.cumsum([0] + [s.num_edges for s in snaps]).astype(np.int64)
+            out[split + "_node_ids"] = cat([s.node_ids for s in snaps])
+            out[split + "_src"] = cat([s.src for s in snaps])
+            out[split + "_dst"] = cat([s.dst for s in snaps])
+            out[split + "_rel"] = cat([s.rel for s in snaps])
+        np.savez_compressed(path, **out)
+
+    @classmethod
+    def from_npz(cls, path: str) -> "SnapshotStore":
+        with np.load(path, allow_pickle=False) as z:
+            num_ents, num_rels = (int(x) for x in z["meta"])
+            splits = []
+            for split in ("train", "valid", "test"):
+                times, no, eo = z[split + "_times"], z[split + "_node_off"], z[split + "_edge_off"]
+                ids, src, dst, rel = (z[split + "_" + k] for k in ("node_ids", "src", "dst", "rel"))
+                splits.append({int(t): Snapshot(int(t), ids[no[k]:no[k + 1]], src[eo[k]:eo[k + 1]], dst[eo[k]:eo[k + 1]],
+                                                rel[eo[k]:eo[k + 1]]) for k, t in enumerate(times.tolist())})
+            return cls(num_ents, num_rels, *splits, name=str(z["name"]))
+
     # ---- seeded synthetic sequences of the benchmark (SURVEY section 8d) ------------------------------
     @classmethod
     def synthetic(cls, shape: str = "icews14", num_times: int = 16, scale: int = 1, seed: int = 20201116,

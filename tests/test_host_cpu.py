@@ -184,6 +184,41 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     assert got == want
 
 
+def test_snapshot_store_binary_cache_round_trip(tmp_path):
+    from temp_b200.snapshot import SnapshotStore
+    from tests.helpers import product_store
+    store = product_store("tiny")
+    path = str(tmp_path / "tiny.npz")
+    store.to_npz(path)
+    back = SnapshotStore.from_npz(path)
+    assert (back.num_ents, back.num_rels, back.name) == (store.num_ents, store.num_rels, store.name)
+    for a, b in ((store.train, back.train), (store.valid, back.valid), (store.test, back.test)):
+        assert list(a.keys()) == list(b.keys())
+        for t in a:
+            for field in ("node_ids", "src", "dst", "rel", "norm", "row_ptr", "csr_src", "csr_rel"):
+                assert np.array_equal(getattr(a[t], field), getattr(b[t], field)), (t, field)
+
+
+def test_reference_style_checkpoint_loads(tmp_path):
+    """test.py:403-406: torch.load(path) -> load_state_dict(checkpoint['state_dict']) -> on_load_checkpoint(checkpoint)."""
+    import torch
+    from argparse import Namespace
+    from tests.helpers import CASE_BY_NAME, product_model
+    case = CASE_BY_NAME["bigrrgcn_tiny_d128_last"]
+    src = product_model(case, device="cpu")
+    ckpt = {"epoch": 3, "global_step": 17, "state_dict": {k: v.clone() + 0.25 for k, v in src.state_dict().items()},
+            "hparams": Namespace(module="BiGRRGCN"), "optimizer_states": []}
+    path = str(tmp_path / "ref.ckpt")
+    torch.save(ckpt, path)
+    dst = product_model(case, device="cpu")
+    res = dst.load_reference_checkpoint(path)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, ckpt["state_dict"][k]), k
+    dst.load_state_dict(ckpt["state_dict"])                      # the reference's own three calls also work
+    dst.on_load_checkpoint(ckpt)
+
+
 def test_every_package_module_imports():
     import importlib
     import pkgutil
