@@ -1017,6 +1017,19 @@ int ensure_smem(K kernel, size_t bytes, const char* name) {
   return TEMP_OK;
 }
 
+// SM count of the current device (148 on a B200), looked up once per process (one CUDA device per process)
+int sm_count_cached() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+    else
+      return 148;
+  }
+  return sms;
+}
+
 int launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   if (a == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
   if (int rc = check_d(a->d)) return rc;
@@ -1075,7 +1088,7 @@ int launch_gru(const TempGruArgs* a, cudaStream_t st) {
   const int jblocks = (a->d + kGJ - 1) / kGJ;
   cudaError_t e;
   // small steps: 32-row tiles so that the step still spreads over all SMs
-  if (rows <= 148 * 32) {
+  if (rows <= sm_count_cached() * 32) {
     const size_t smem = (static_cast<size_t>(32) * (a->d + 4) + static_cast<size_t>(a->d) * 3 * kGJ) * sizeof(float);
     if (int rc = ensure_smem<1>(gru_kernel<4>, smem, "gru_kernel<4>")) return rc;
     dim3 grid((rows + 31) / 32, jblocks);
@@ -1146,7 +1159,7 @@ int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   if (temp_internal::tc_scan_supported(a)) return temp_internal::tc_launch_scan(a, st);
   if (a->push_bufs != nullptr) return fail(TEMP_EUNSUPPORTED, "the fused peer all-gather needs the tcgen05 scan (d == 128, partition table)%s", "");
   if (a->barrier == nullptr) return fail(TEMP_EINVAL, "scan needs a zero-initialised 8-byte barrier word%s", "");
-  if (max_rows <= 148 * 64) return launch_scan_t<4, 3>(a, max_rows, st);
+  if (max_rows <= sm_count_cached() * 64) return launch_scan_t<4, 3>(a, max_rows, st);
   return launch_scan_t<8, 4>(a, max_rows, st);
 }
 
@@ -1195,7 +1208,7 @@ int launch_rank_filtered(const TempRankArgs* a, cudaStream_t st) {
   if (e != cudaSuccess) return cuda_fail(e, "rank memset");
   // entity chunks: about two CTAs per SM over the whole grid, at least 32 table rows per warp
   const int groups = (a->n_query + kRankQ - 1) / kRankQ;
-  int chunks = (148 * 2) / groups;                         // one wave of two CTAs per SM: never a few CTAs left for a second
+  int chunks = (sm_count_cached() * 2) / groups;           // one wave of two CTAs per SM: never a few CTAs left for a second
   const int max_chunks = (a->num_ents + 32 * (kThreads / 32) - 1) / (32 * (kThreads / 32));
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -1217,7 +1230,8 @@ int launch_rank_filtered(const TempRankArgs* a, cudaStream_t st) {
 
 int grid_for(size_t work_items) {
   size_t g = (work_items + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
+  const size_t cap = static_cast<size_t>(sm_count_cached()) * 8;
+  if (g > cap) g = cap;
   return static_cast<int>(g == 0 ? 1 : g);
 }
 

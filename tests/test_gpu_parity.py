@@ -227,7 +227,7 @@ def test_autograd_fallback_loss_equals_cuda_forward(name):
     torch.manual_seed(3)
     got = model.forward(tl)
     assert got.requires_grad
-    assert abs(float(got) - want) <= RTOL * abs(want)
+    assert abs(float(got.detach()) - want) <= RTOL * abs(want)
 
 
 def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None):
