@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 13
+#define TEMP_ABI_VERSION 14
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -233,6 +233,26 @@ typedef struct {
   float* loss;               /* [n_pos]                                                                      */
 } TempScoreLossArgs;
 
+/* Backward of temp_score_loss_fwd (training through the fused scorer; the reference back-propagates through the
+ * materialised [n_pos, n_cand, d] gather of models/TKG_Module.py:202-213):  given grad_loss[p] = dL / d loss[p], ADDS
+ *   dL/d table[cand[p, c]]  +=  grad_loss[p] * (softmax_c(score(p, .)) - [c == 0]) * d score / d candidate row
+ *   dL/d ent_embed[fixed_p], dL/d rel_embeds[r_p]  +=  the same through the triple's query vector
+ * into the three caller-zeroed gradient buffers (vector float atomics: summation order is not fixed).  The scores are
+ * recomputed from the inputs (nothing is saved by the forward).  Same shapes and restrictions as the forward.     */
+typedef struct {
+  int32_t n_pos, n_cand, d;
+  int32_t score_fn, corrupt_tail;
+  const float* ent_embed;
+  const float* rel_embeds;
+  const float* table;
+  const int64_t* triples;
+  const int64_t* cand;
+  const float* grad_loss;    /* [n_pos]                                                                      */
+  float* grad_ent_embed;     /* [n_nodes, d]      accumulated into                                           */
+  float* grad_rel_embeds;    /* [2 * num_rels, d] accumulated into                                           */
+  float* grad_table;         /* [num_ents, d]     accumulated into                                           */
+} TempScoreLossBwdArgs;
+
 /* Filtered ranking of one target graph's test triples against all entities:
  *   rank[q] = 1 + #{ j != target[q] :  v(q, j) > v(q, target[q])  or  (v(q, j) == v(q, target[q]) and j < target[q]) }
  * with v(q, j) = sigmoid(score(q, j)) for ordinary entities and sigmoid(-10e6) = 0 for the entities of the query's filter
@@ -330,6 +350,7 @@ int temp_gather_rows(const TempGatherArgs* args, void* stream);
 int temp_scatter_rows(const TempScatterArgs* args, void* stream);
 /* out[c, r] = in[r, c]  (weight preparation: weight_ih / weight_hh / q,k,v -> K-major-first)     */
 int temp_score_loss_fwd(const TempScoreLossArgs* args, void* stream);
+int temp_score_loss_bwd(const TempScoreLossBwdArgs* args, void* stream);
 int temp_rank_filtered_fwd(const TempRankArgs* args, void* stream);
 int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream);
 /* Tensor-core operand images (d == 128).  A [k, n] row-major fp32 matrix (k == 128, n % 128 == 0) is split

@@ -803,6 +803,165 @@ __global__ void __launch_bounds__(kThreads) score_loss_kernel(const TempScoreLos
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward of the fused scorer
+// ------------------------------------------------------------------------------------------------
+// Same work split as the forward (one warp per positive, 8 lanes per candidate, 4 candidates per warp iteration).  Pass 1
+// recomputes the logsumexp of the positive's candidate scores, pass 2 walks the candidates again: the weight
+// w = softmax - [c == 0] times the upstream gradient scales (i) the candidate row's gradient -- q for the bilinear
+// scores, -sign(row - q) for TransE -- added to grad_table with one 16-byte vector atomic per 4 channels, and (ii) the
+// query vector's gradient, kept in registers, reduced over the warp's 4 candidate groups at the end and pushed through
+// the query's definition into grad_ent_embed / grad_rel_embeds.
+__global__ void __launch_bounds__(kThreads) score_loss_bwd_kernel(const TempScoreLossBwdArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (pos >= p.n_pos) return;
+  const int D = p.d, per = D >> 3, half = D >> 1;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int c0 = sub * per;
+  const long long s_id = p.triples[3 * pos], r_id = p.triples[3 * pos + 1], o_id = p.triples[3 * pos + 2];
+  const size_t fixed_row = static_cast<size_t>(p.corrupt_tail ? s_id : o_id) * D;
+  const float* fixed = p.ent_embed + fixed_row;
+  const float* rel = p.rel_embeds + static_cast<size_t>(r_id) * D;
+  float q[kScoreMaxPerLane], gq[kScoreMaxPerLane];
+  score_query(q, fixed, rel, c0, per, half, p.score_fn, p.corrupt_tail);
+#pragma unroll
+  for (int t = 0; t < kScoreMaxPerLane; ++t) gq[t] = 0.f;
+  const bool l1 = p.score_fn == TEMP_SCORE_TRANSE;
+  const int64_t* cand = p.cand + static_cast<size_t>(pos) * p.n_cand;
+  // ---- pass 1: logsumexp (the forward's arithmetic) -------------------------------------------------------------------
+  float mx = -INFINITY, den = 0.f;
+  for (int base = 0; base < p.n_cand; base += 4) {
+    const int c = base + grp;
+    float part = 0.f;
+    if (c < p.n_cand)
+      part = score_partial(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(cand[c]) * D + c0), q, per, l1);
+    part = score_reduce8(part);
+    if (c < p.n_cand) {
+      const float sc = l1 ? -part : part;
+      const float mnew = fmaxf(mx, sc);
+      den = den * expf(mx - mnew) + expf(sc - mnew);
+      mx = mnew;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 8; off >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, off), oden = __shfl_xor_sync(0xffffffffu, den, off);
+    const float mnew = fmaxf(mx, omx);
+    den = (mx == -INFINITY ? 0.f : den * expf(mx - mnew)) + (omx == -INFINITY ? 0.f : oden * expf(omx - mnew));
+    mx = mnew;
+  }
+  const float lse = mx + logf(den);
+  const float g = __ldg(p.grad_loss + pos);
+  // ---- pass 2: gradients -------------------------------------------------------------------------------------------------
+  for (int base = 0; base < p.n_cand; base += 4) {
+    const int c = base + grp;
+    const bool on = c < p.n_cand;
+    const size_t row_off = on ? static_cast<size_t>(cand[c]) * D + c0 : 0;
+    const float4* row = reinterpret_cast<const float4*>(p.table + row_off);
+    float4 v[kScoreMaxPerLane / 4];
+    float part = 0.f;
+#pragma unroll
+    for (int t4 = 0; t4 < kScoreMaxPerLane / 4; ++t4) {
+      if (on && 4 * t4 < per) {
+        v[t4] = __ldg(row + t4);
+        if (l1) {
+          part += fabsf(v[t4].x - q[4 * t4]) + fabsf(v[t4].y - q[4 * t4 + 1]) + fabsf(v[t4].z - q[4 * t4 + 2]) + fabsf(v[t4].w - q[4 * t4 + 3]);
+        } else {
+          part = fmaf(v[t4].x, q[4 * t4], part);
+          part = fmaf(v[t4].y, q[4 * t4 + 1], part);
+          part = fmaf(v[t4].z, q[4 * t4 + 2], part);
+          part = fmaf(v[t4].w, q[4 * t4 + 3], part);
+        }
+      }
+    }
+    part = score_reduce8(part);
+    if (!on) continue;                                   // (after the shuffles: they need the whole warp)
+    const float sc = l1 ? -part : part;
+    const float coef = g * (expf(sc - lse) - (c == 0 ? 1.f : 0.f));
+    float* grow = p.grad_table + row_off;
+#pragma unroll
+    for (int t4 = 0; t4 < kScoreMaxPerLane / 4; ++t4) {
+      if (4 * t4 < per) {
+        float4 d;
+        if (l1) {  // score = -|row - q|_1:  d/d row = -sign(row - q),  d/d q = +sign(row - q)   (sign(0) = 0 like torch)
+          const float sx = (v[t4].x > q[4 * t4]) - (v[t4].x < q[4 * t4]);
+          const float sy = (v[t4].y > q[4 * t4 + 1]) - (v[t4].y < q[4 * t4 + 1]);
+          const float sz = (v[t4].z > q[4 * t4 + 2]) - (v[t4].z < q[4 * t4 + 2]);
+          const float sw = (v[t4].w > q[4 * t4 + 3]) - (v[t4].w < q[4 * t4 + 3]);
+          d = make_float4(-coef * sx, -coef * sy, -coef * sz, -coef * sw);
+          gq[4 * t4] = fmaf(coef, sx, gq[4 * t4]);
+          gq[4 * t4 + 1] = fmaf(coef, sy, gq[4 * t4 + 1]);
+          gq[4 * t4 + 2] = fmaf(coef, sz, gq[4 * t4 + 2]);
+          gq[4 * t4 + 3] = fmaf(coef, sw, gq[4 * t4 + 3]);
+        } else {   // score = <q, row>
+          d = make_float4(coef * q[4 * t4], coef * q[4 * t4 + 1], coef * q[4 * t4 + 2], coef * q[4 * t4 + 3]);
+          gq[4 * t4] = fmaf(coef, v[t4].x, gq[4 * t4]);
+          gq[4 * t4 + 1] = fmaf(coef, v[t4].y, gq[4 * t4 + 1]);
+          gq[4 * t4 + 2] = fmaf(coef, v[t4].z, gq[4 * t4 + 2]);
+          gq[4 * t4 + 3] = fmaf(coef, v[t4].w, gq[4 * t4 + 3]);
+        }
+        atomicAdd(reinterpret_cast<float4*>(grow + 4 * t4), d);
+      }
+    }
+  }
+  // ---- the query's gradient: sum over the 4 candidate groups, then through q's definition ---------------------------------
+#pragma unroll
+  for (int t = 0; t < kScoreMaxPerLane; ++t) {
+    if (t < per) {
+      gq[t] += __shfl_xor_sync(0xffffffffu, gq[t], 8);
+      gq[t] += __shfl_xor_sync(0xffffffffu, gq[t], 16);
+    }
+  }
+  if (grp != 0) return;
+  float* g_ent = p.grad_ent_embed + fixed_row;
+  float* g_rel = p.grad_rel_embeds + static_cast<size_t>(r_id) * D;
+#pragma unroll
+  for (int t = 0; t < kScoreMaxPerLane; ++t) {
+    if (t < per) {
+      const int c = c0 + t;
+      const float gv = gq[t];
+      if (p.score_fn == TEMP_SCORE_COMPLEX) {
+        const bool im = c >= half;
+        const int k = im ? c - half : c;
+        const float re_e = __ldg(fixed + k), im_e = __ldg(fixed + half + k);
+        const float re_r = __ldg(rel + k), im_r = __ldg(rel + half + k);
+        if (p.corrupt_tail) {   // q_re = re_e re_r - im_e im_r ; q_im = re_e im_r + im_e re_r
+          if (!im) {
+            atomicAdd(g_ent + k, gv * re_r);
+            atomicAdd(g_ent + half + k, -gv * im_r);
+            atomicAdd(g_rel + k, gv * re_e);
+            atomicAdd(g_rel + half + k, -gv * im_e);
+          } else {
+            atomicAdd(g_ent + k, gv * im_r);
+            atomicAdd(g_ent + half + k, gv * re_r);
+            atomicAdd(g_rel + k, gv * im_e);
+            atomicAdd(g_rel + half + k, gv * re_e);
+          }
+        } else {                // q_re = re_r re_e + im_r im_e ; q_im = re_r im_e - im_r re_e
+          if (!im) {
+            atomicAdd(g_ent + k, gv * re_r);
+            atomicAdd(g_ent + half + k, gv * im_r);
+            atomicAdd(g_rel + k, gv * re_e);
+            atomicAdd(g_rel + half + k, gv * im_e);
+          } else {
+            atomicAdd(g_ent + k, -gv * im_r);
+            atomicAdd(g_ent + half + k, gv * re_r);
+            atomicAdd(g_rel + k, gv * im_e);
+            atomicAdd(g_rel + half + k, -gv * re_e);
+          }
+        }
+      } else if (p.score_fn == TEMP_SCORE_DISTMULT) {
+        atomicAdd(g_ent + c, gv * __ldg(rel + c));
+        atomicAdd(g_rel + c, gv * __ldg(fixed + c));
+      } else {                  // q = s + r (tail) | o - r (head)
+        atomicAdd(g_ent + c, gv);
+        atomicAdd(g_rel + c, p.corrupt_tail ? gv : -gv);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // filtered ranking: position of the target in the stable descending sort of sigmoid(masked scores)
 // ------------------------------------------------------------------------------------------------
 // grid (group of kRankQ queries, entity chunk): the CTA's warps walk the chunk's rows of the all-entity table once for
@@ -1014,6 +1173,22 @@ int ensure_smem(K kernel, size_t bytes, const char* name) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
   if (e != cudaSuccess) return cuda_fail(e, name);
   configured = bytes;
+  return TEMP_OK;
+}
+
+int launch_score_loss_bwd(const TempScoreLossBwdArgs* a, cudaStream_t st) {
+  if (a == nullptr || a->n_pos < 0 || a->n_cand <= 0) return fail(TEMP_EINVAL, "bad score args%s", "");
+  if (a->n_pos == 0) return TEMP_OK;
+  if (a->d <= 0 || (a->d & 31) || a->d / 8 > kScoreMaxPerLane) return fail(TEMP_EUNSUPPORTED, "score: d must be a multiple of 32 up to %s%ld", "", 8L * kScoreMaxPerLane);
+  if (a->score_fn < TEMP_SCORE_DISTMULT || a->score_fn > TEMP_SCORE_TRANSE) return fail(TEMP_EINVAL, "bad score_fn%s", "");
+  if (!a->ent_embed || !a->rel_embeds || !a->table || !a->triples || !a->cand || !a->grad_loss || !a->grad_ent_embed ||
+      !a->grad_rel_embeds || !a->grad_table)
+    return fail(TEMP_EINVAL, "score backward has null pointers%s", "");
+  if (!aligned16(a->table) || !aligned16(a->grad_table)) return fail(TEMP_EINVAL, "score table / grad_table misaligned%s", "");
+  const int per_cta = kThreads / 32;
+  score_loss_bwd_kernel<<<(a->n_pos + per_cta - 1) / per_cta, kThreads, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "score_loss_bwd_kernel launch");
   return TEMP_OK;
 }
 
@@ -1303,6 +1478,10 @@ int temp_gather_rows(const TempGatherArgs* args, void* stream) {
 
 int temp_scatter_rows(const TempScatterArgs* args, void* stream) {
   return launch_scatter(args, static_cast<cudaStream_t>(stream));
+}
+
+int temp_score_loss_bwd(const TempScoreLossBwdArgs* args, void* stream) {
+  return launch_score_loss_bwd(args, static_cast<cudaStream_t>(stream));
 }
 
 int temp_rank_filtered_fwd(const TempRankArgs* args, void* stream) {

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -81,6 +81,12 @@ class ScoreLossArgs(C.Structure):
                 ("ent_embed", _p), ("rel_embeds", _p), ("table", _p), ("triples", _p), ("cand", _p), ("loss", _p)]
 
 
+class ScoreLossBwdArgs(C.Structure):
+    _fields_ = [("n_pos", _i32), ("n_cand", _i32), ("d", _i32), ("score_fn", _i32), ("corrupt_tail", _i32),
+                ("ent_embed", _p), ("rel_embeds", _p), ("table", _p), ("triples", _p), ("cand", _p), ("grad_loss", _p),
+                ("grad_ent_embed", _p), ("grad_rel_embeds", _p), ("grad_table", _p)]
+
+
 class RankArgs(C.Structure):
     _fields_ = [("n_query", _i32), ("num_ents", _i32), ("d", _i32), ("score_fn", _i32), ("corrupt_tail", _i32),
                 ("ent_embed", _p), ("rel_embeds", _p), ("table", _p), ("triples", _p), ("target", _p),
@@ -121,7 +127,7 @@ class Op(C.Structure):
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
-           "temp_program_kernel_count", "temp_score_loss_fwd", "temp_rank_filtered_fwd", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
+           "temp_program_kernel_count", "temp_score_loss_fwd", "temp_score_loss_bwd", "temp_rank_filtered_fwd", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
            "temp_plan_array", "temp_graph_create", "temp_graph_launch", "temp_graph_destroy", "temp_peer_barrier", "temp_plan_blob_layout",
            "temp_plan_write_blob")
 
@@ -155,6 +161,7 @@ def load(path: Optional[str] = None):
     lib.temp_program_kernel_count.argtypes = [C.POINTER(Op), _i32]
     lib.temp_score_loss_fwd.argtypes = [C.POINTER(ScoreLossArgs), _p]
     lib.temp_rank_filtered_fwd.argtypes = [C.POINTER(RankArgs), _p]
+    lib.temp_score_loss_bwd.argtypes = [C.POINTER(ScoreLossBwdArgs), _p]
     lib.temp_peer_barrier.argtypes = [_p, _p, _i32, _i32, C.c_uint32, _p]
     lib.temp_graph_create.argtypes = [C.POINTER(Op), _i32, C.POINTER(_p)]
     lib.temp_graph_launch.argtypes = [_p, _p]

@@ -230,6 +230,35 @@ def test_autograd_fallback_loss_equals_cuda_forward(name):
     assert abs(float(got.detach()) - want) <= RTOL * abs(want)
 
 
+@pytest.mark.parametrize("fn", ["complex", "distmult", "transE"])
+@pytest.mark.parametrize("corrupt_tail", [True, False])
+@pytest.mark.parametrize("D", [32, 128, 224])
+def test_fused_scorer_backward_matches_torch_autograd(fn, corrupt_tail, D):
+    """temp_score_loss_bwd (scores recomputed, candidate-row gradients by vector atomics) against autograd through the
+    reference's materialised formulation (models/TKG_Module.py:202-213): gradients w.r.t. the graph's node states, the
+    relation embeddings and the all-entity table, with repeated candidates and repeated subjects."""
+    from temp_b200 import scores
+    g = torch.Generator().manual_seed(100 + D)
+    N, M, R2, P, C = 40, 300, 12, 77, 23
+    ent = (torch.randn(N, D, generator=g) * 0.3).cuda().requires_grad_(True)
+    rel = (torch.randn(R2, D, generator=g) * 0.3).cuda().requires_grad_(True)
+    table = (torch.randn(M, D, generator=g) * 0.3).cuda().requires_grad_(True)
+    tri = torch.stack([torch.randint(0, N, (P,), generator=g), torch.randint(0, R2, (P,), generator=g),
+                       torch.randint(0, N, (P,), generator=g)], 1).cuda()
+    cand = torch.randint(0, M // 4, (P, C), generator=g).cuda()            # a quarter of the table: many repeats
+    f = {"complex": scores.complex_score, "distmult": scores.distmult, "transE": scores.transE}[fn]
+    r = rel[tri[:, 1]]
+    sc = f(ent[tri[:, 0]], r, table[cand], mode="tail") if corrupt_tail else f(table[cand], r, ent[tri[:, 2]], mode="head")
+    want = torch.nn.functional.cross_entropy(sc, torch.zeros(P, dtype=torch.long, device="cuda"))
+    gw = torch.autograd.grad(want * 3.0, [ent, rel, table])
+    got = scores.fused_link_prediction_loss(ent, rel, tri, cand, table, fn, corrupt_tail)
+    assert got.requires_grad and abs(float(got.detach()) - float(want.detach())) <= RTOL * abs(float(want.detach()))
+    gg = torch.autograd.grad(got * 3.0, [ent, rel, table])
+    for name, a, b in zip(("ent_embed", "rel_embeds", "table"), gg, gw):
+        scale = float(b.abs().max())
+        assert scale > 0 and float((a - b).abs().max()) / scale < RTOL, (name, float((a - b).abs().max()) / scale)
+
+
 def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None):
     from tests.helpers import CASE_BY_NAME
     case = dict(CASE_BY_NAME[base])

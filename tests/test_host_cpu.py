@@ -167,11 +167,11 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     from temp_b200 import lib
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "temp_b200.h"\nint main(){'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(TempDenseTerm), sizeof(TempRgcnLayerArgs),'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(TempDenseTerm), sizeof(TempRgcnLayerArgs),'
                    'sizeof(TempGruArgs), sizeof(TempAttnArgs), sizeof(TempGatherArgs), sizeof(TempScatterArgs), sizeof(TempOp),'
                    'offsetof(TempRgcnLayerArgs, chain_ld), offsetof(TempGruArgs, out), offsetof(TempOp, u),'
                    'sizeof(TempGruScanArgs), offsetof(TempGruScanArgs, steps), sizeof(TempScoreLossArgs), sizeof(TempSnapshotView),'
-                   'sizeof(TempPlanCounts), offsetof(TempRgcnLayerArgs, agg_lists), sizeof(TempRankArgs), offsetof(TempRankArgs, rank));return 0;}')
+                   'sizeof(TempPlanCounts), offsetof(TempRgcnLayerArgs, agg_lists), sizeof(TempRankArgs), offsetof(TempRankArgs, rank), sizeof(TempScoreLossBwdArgs), offsetof(TempScoreLossBwdArgs, grad_table));return 0;}')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
@@ -180,7 +180,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
             ctypes.sizeof(lib.Op), lib.RgcnLayerArgs.chain_ld.offset, lib.GruArgs.out.offset, lib.Op.u.offset,
             ctypes.sizeof(lib.GruScanArgs), lib.GruScanArgs.steps.offset, ctypes.sizeof(lib.ScoreLossArgs),
             ctypes.sizeof(lib.SnapshotView), ctypes.sizeof(lib.PlanCounts), lib.RgcnLayerArgs.agg_lists.offset,
-            ctypes.sizeof(lib.RankArgs), lib.RankArgs.rank.offset]
+            ctypes.sizeof(lib.RankArgs), lib.RankArgs.rank.offset, ctypes.sizeof(lib.ScoreLossBwdArgs),
+            lib.ScoreLossBwdArgs.grad_table.offset]
     assert got == want
 
 
