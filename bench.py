@@ -183,7 +183,7 @@ def run_reference(args, rank, world):
                              "sample": "%d forwards (oracle port of the reference's DGL-CPU path; the reference "
                                        "needs dgl==0.4.1 + pytorch_lightning==0.5.2, not installable)" % steps},
             "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def bench_config(world):
@@ -540,7 +540,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             base, _ = cpu_baseline(store, model.state_dict(), t_lists)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -683,5 +683,26 @@ def scaled_roofline(scale, dev, peak):
     return out
 
 
+def _emit(line) -> None:
+    """The ONE JSON line, on the real stdout (see _quiet_stdout)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """Everything any library writes to file descriptor 1 during the run (NCCL prints its version banner there when
+    NCCL_DEBUG is set in the environment) goes to stderr; stdout carries the JSON line only."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
