@@ -358,6 +358,70 @@ def test_encode_keeps_launch_programs_of_seen_batches_and_drops_them_with_the_we
     assert torch.equal(model.encode(batches[0]).out, changed.out)
 
 
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8", "bisargcn_icews_d128_L8", "srgcn_tiny_d128",
+                                  "rrgcn_tiny_d128_full", "grrgcn_tiny_d200_nb100"])
+def test_evaluate_ranks_every_family_like_the_sort_formulation(name):
+    """model.evaluate(t_list) (the validation_step / test_step body, models/DynamicRGCN.py:118-130) with the ranking kernel
+    against the same call with the reference's dense-mask + sort formulation in torch: same shape and dtype, equal ranks
+    except where another entity's sigmoid is within rounding of the target's (there: off by a few places at most).
+    d = 200 is outside the kernel's shapes (d % 32 != 0) and must take the torch route by itself."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME[name]
+    model = product_model(case)
+    tl = case["t_list"]
+    ranks, loss = model.evaluate(tl, val=True)
+    ev = model.evaluater
+    fast = ev.calc_metrics_single_graph
+    ev.calc_metrics_single_graph = ev.calc_metrics_single_graph_torch
+    try:
+        ranks_t, loss_t = model.evaluate(tl, val=True)
+    finally:
+        ev.calc_metrics_single_graph = fast
+    assert ranks.dtype == torch.long and ranks.shape == ranks_t.shape and ranks.numel() > 0
+    assert int(ranks.min()) >= 1 and int(ranks.max()) <= model.num_ents
+    assert abs(loss - loss_t) <= 1e-6 * max(1.0, abs(loss_t))
+    same = (ranks == ranks_t).float().mean().item()
+    assert same >= 0.95 and int((ranks - ranks_t).abs().max()) <= 3, (same, int((ranks - ranks_t).abs().max()))
+    mrr, mrr_t = (1.0 / ranks.float()).mean().item(), (1.0 / ranks_t.float()).mean().item()
+    assert abs(mrr - mrr_t) <= 2e-3 * mrr_t
+
+
+def test_training_loop_runs_on_the_fused_scorer_and_reduces_the_loss():
+    """main.py-style training: train() mode, loss = model(t_list), backward, Adam step -- encoder through the torch
+    autograd fallback, link-prediction loss through temp_score_loss_fwd / temp_score_loss_bwd.  The loss on a fixed
+    batch goes down, and one step's gradients equal those of the all-torch route (fused_scorer = False)."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    grads = {}
+    for fused in (True, False):
+        model = product_model(case)
+        model.fused_scorer = fused
+        model.train()
+        np.random.seed(1)
+        torch.manual_seed(1)
+        model.zero_grad()
+        model.forward(torch.tensor(case["t_list"])).backward()
+        grads[fused] = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    assert grads[True].keys() == grads[False].keys()
+    for n in grads[True]:
+        scale = float(grads[False][n].abs().max())
+        if scale > 0:
+            assert float((grads[True][n] - grads[False][n]).abs().max()) / scale < 1e-3, n
+    model = product_model(case)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    losses = []
+    for step in range(6):
+        np.random.seed(2)                   # the same sub-sampled window and negatives every step
+        torch.manual_seed(2)
+        opt.zero_grad()
+        loss = model.forward(torch.tensor(case["t_list"]))
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0] and all(np.isfinite(losses))
+
+
 def _rank_bounds(model, fn, ent_mean, rel, table, samples, graph, t, mode, eps):
     """[lowest, highest] 1-indexed rank of every query's target when sigmoid values closer than eps count as ties --
     evaluated in float64 from the reference's formulation (utils/evaluation.py:53-80)."""
