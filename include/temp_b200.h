@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 14
+#define TEMP_ABI_VERSION 15
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -336,6 +336,17 @@ const void* temp_plan_array(const TempPlan* plan, int32_t which, int64_t* n_byte
  * offsets[i] = -1 for arrays the plan does not have.  Returns the blob size (negative on bad arguments).           */
 int64_t temp_plan_blob_layout(const TempPlan* plan, int64_t* offsets, int64_t* sizes, int32_t align);
 int temp_plan_write_blob(const TempPlan* plan, uint8_t* dst, int32_t align);
+
+/* Host side of the negative sampler (utils/CorrptTriples.py:61-85), continuing NumPy's global legacy generator: mt_key
+ * [624] / mt_pos are the MT19937 state of np.random.get_state() and are advanced in place (hand them back with
+ * np.random.set_state).  Slot s (tail corruption of triple s/2 for even s, head corruption for odd s) draws rounds of
+ * `neg` candidates -- np.random.randint(num_entities, size=neg) -- until it holds `neg` of them outside its filter list
+ * fids[fptr[s] .. fptr[s+1]); they are written to out_even / out_odd + (s/2) * out_stride.  sort_min_f: smallest
+ * filter-list length for which numpy's in1d takes its merge-sort path (ceil(10 * neg ** 0.145)).  Returns the number of
+ * rounds drawn, TEMP_EINVAL on bad arguments.  No CUDA.                                                            */
+int64_t temp_negative_sample(uint32_t* mt_key, int32_t* mt_pos, int64_t num_entities, int32_t neg, const int64_t* fptr,
+                             const int64_t* fids, int32_t n_slots, int32_t sort_min_f, int64_t* out_even, int64_t* out_odd,
+                             int64_t out_stride);
 
 int temp_abi_version(void);
 const char* temp_last_error_string(void);

@@ -388,4 +388,129 @@ int temp_plan_write_blob(const TempPlan* plan, uint8_t* dst, int32_t align) {
   return TEMP_OK;
 }
 
+// ---- filtered negative sampling on the reference's own random stream --------------------------------------------------
+// The reference draws `np.random.randint(num_entities, size=negative_rate)` once per round (utils/CorrptTriples.py:61-85)
+// from NumPy's global legacy generator.  That stream is frozen by NumPy's compatibility policy: MT19937, and for a range
+// below 2^32 one tempered 32-bit output per attempt, masked to the next power of two and redrawn while above the range
+// (numpy/random/src/distributions/distributions.c, buffered_bounded_masked_uint32 under RandomState's use_masked mode).
+// temp_negative_sample continues that generator from the state np.random.get_state() reports and hands the advanced
+// state back, so the candidates AND every later draw of the process are bit-identical to the reference's.
+//
+// Per slot it restates the reference's loop (rounds filtered by np.in1d(cand, true_ids, assume_unique=True, invert=True),
+// concatenated, truncated) INCLUDING which of numpy's three in1d algorithms the call takes
+// (numpy/lib/_arraysetops_impl.py, numpy 2.x): the integer table and the per-value loop are plain membership tests; the
+// merge-sort path with assume_unique=True additionally drops every candidate that has an equal candidate LATER in the
+// same round (the stable sort places it before its twin, and the "next element differs" test then fails).
+namespace {
+struct Mt19937 {
+  uint32_t* key;
+  int32_t pos;
+  void refill() {
+    constexpr int N = 624, M = 397;
+    constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
+    int kk = 0;
+    uint32_t y;
+    for (; kk < N - M; ++kk) {
+      y = (key[kk] & kUpper) | (key[kk + 1] & kLower);
+      key[kk] = key[kk + M] ^ (y >> 1) ^ ((y & 1u) ? kMatrixA : 0u);
+    }
+    for (; kk < N - 1; ++kk) {
+      y = (key[kk] & kUpper) | (key[kk + 1] & kLower);
+      key[kk] = key[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? kMatrixA : 0u);
+    }
+    y = (key[N - 1] & kUpper) | (key[0] & kLower);
+    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((y & 1u) ? kMatrixA : 0u);
+    pos = 0;
+  }
+  uint32_t next() {
+    if (pos >= 624) refill();
+    uint32_t y = key[pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+}  // namespace
+
+int64_t temp_negative_sample(uint32_t* mt_key, int32_t* mt_pos, int64_t num_entities, int32_t neg, const int64_t* fptr,
+                             const int64_t* fids, int32_t n_slots, int32_t sort_min_f, int64_t* out_even, int64_t* out_odd,
+                             int64_t out_stride) {
+  if (mt_key == nullptr || mt_pos == nullptr || fptr == nullptr || (fids == nullptr && fptr[n_slots] > 0) ||
+      out_even == nullptr || out_odd == nullptr || neg <= 0 || n_slots < 0 || num_entities <= 0 ||
+      num_entities > 0xFFFFFFFFll || *mt_pos < 0 || *mt_pos > 624)
+    return TEMP_EINVAL;
+  Mt19937 mt{mt_key, *mt_pos};
+  const uint32_t rng = static_cast<uint32_t>(num_entities - 1);
+  uint32_t mask = rng;
+  mask |= mask >> 1;
+  mask |= mask >> 2;
+  mask |= mask >> 4;
+  mask |= mask >> 8;
+  mask |= mask >> 16;
+  int64_t rounds = 0;
+  std::vector<int64_t> forb, cand(static_cast<size_t>(neg));
+  std::vector<uint8_t> keep(static_cast<size_t>(neg));
+  std::vector<int32_t> order(static_cast<size_t>(neg));
+  for (int32_t s = 0; s < n_slots; ++s) {
+    const int64_t f = fptr[s + 1] - fptr[s];
+    forb.assign(fids + fptr[s], fids + fptr[s + 1]);
+    std::sort(forb.begin(), forb.end());
+    bool sort_path = false;
+    if (f > 0) {
+      const int64_t range = forb.back() - forb.front();
+      const bool table = range <= 6 * (static_cast<int64_t>(neg) + f);
+      sort_path = !table && f >= sort_min_f;
+    }
+    int64_t* dst = ((s & 1) ? out_odd : out_even) + static_cast<int64_t>(s >> 1) * out_stride;
+    int32_t filled = 0;
+    const int64_t* fb = forb.data();
+    while (filled < neg) {
+      ++rounds;
+      if (!sort_path) {
+        // one round of np.random.randint(num_entities, size=neg): every draw is taken from the stream, the ones outside
+        // the filter list are kept while the slot still has room
+        for (int32_t i = 0; i < neg; ++i) {
+          uint32_t v = 0;
+          if (rng != 0) {
+            do {
+              v = mt.next() & mask;
+            } while (v > rng);
+          }
+          const int64_t c = static_cast<int64_t>(v);
+          bool in = false;
+          if (f <= 8) {
+            for (int64_t k = 0; k < f; ++k) in |= fb[k] == c;
+          } else {
+            in = std::binary_search(forb.begin(), forb.end(), c);
+          }
+          if (!in && filled < neg) dst[filled++] = c;
+        }
+        continue;
+      }
+      for (int32_t i = 0; i < neg; ++i) {
+        uint32_t v = 0;
+        if (rng != 0) {
+          do {
+            v = mt.next() & mask;
+          } while (v > rng);
+        }
+        cand[static_cast<size_t>(i)] = static_cast<int64_t>(v);
+        keep[static_cast<size_t>(i)] = std::binary_search(forb.begin(), forb.end(), static_cast<int64_t>(v)) ? 0 : 1;
+      }
+      // drop every candidate with an equal candidate later in the round
+      for (int32_t i = 0; i < neg; ++i) order[static_cast<size_t>(i)] = i;
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cand[static_cast<size_t>(a)] < cand[static_cast<size_t>(b)]; });
+      for (int32_t k = 0; k + 1 < neg; ++k)
+        if (cand[static_cast<size_t>(order[static_cast<size_t>(k)])] == cand[static_cast<size_t>(order[static_cast<size_t>(k + 1)])])
+          keep[static_cast<size_t>(order[static_cast<size_t>(k)])] = 0;
+      for (int32_t i = 0; i < neg && filled < neg; ++i)
+        if (keep[static_cast<size_t>(i)]) dst[filled++] = cand[static_cast<size_t>(i)];
+    }
+  }
+  *mt_pos = mt.pos;
+  return rounds;
+}
+
 }  // extern "C"

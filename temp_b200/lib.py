@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -127,7 +127,7 @@ class Op(C.Structure):
 EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
-           "temp_program_kernel_count", "temp_score_loss_fwd", "temp_score_loss_bwd", "temp_rank_filtered_fwd", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
+           "temp_program_kernel_count", "temp_score_loss_fwd", "temp_score_loss_bwd", "temp_rank_filtered_fwd", "temp_negative_sample", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
            "temp_plan_array", "temp_graph_create", "temp_graph_launch", "temp_graph_destroy", "temp_peer_barrier", "temp_plan_blob_layout",
            "temp_plan_write_blob")
 
@@ -162,6 +162,8 @@ def load(path: Optional[str] = None):
     lib.temp_score_loss_fwd.argtypes = [C.POINTER(ScoreLossArgs), _p]
     lib.temp_rank_filtered_fwd.argtypes = [C.POINTER(RankArgs), _p]
     lib.temp_score_loss_bwd.argtypes = [C.POINTER(ScoreLossBwdArgs), _p]
+    lib.temp_negative_sample.argtypes = [_p, _p, C.c_int64, _i32, _p, _p, _i32, _i32, _p, _p, C.c_int64]
+    lib.temp_negative_sample.restype = C.c_int64
     lib.temp_peer_barrier.argtypes = [_p, _p, _i32, _i32, C.c_uint32, _p]
     lib.temp_graph_create.argtypes = [C.POINTER(Op), _i32, C.POINTER(_p)]
     lib.temp_graph_launch.argtypes = [_p, _p]

@@ -185,6 +185,40 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     assert got == want
 
 
+@pytest.mark.parametrize("neg,num_ents,spread", [(500, 7128, True), (500, 7128, False), (64, 900, True), (5, 40, False)])
+def test_native_negative_sampler_is_bit_identical_to_the_python_loop(neg, num_ents, spread):
+    """temp_negative_sample continues NumPy's legacy MT19937 stream natively: the sample matrices AND the generator state
+    afterwards equal the reference-style python loop (np.random.randint per round + np.isin) -- on a graph whose filter
+    lists hit all three of numpy's in1d algorithms: short lists (per-value loop), long lists over a narrow id range
+    (integer table), long lists over a wide id range (merge sort with assume_unique: candidates with a later twin in the
+    round are dropped too)."""
+    import torch
+    from argparse import Namespace
+    from temp_b200.sampler import CorruptTriples
+    from temp_b200.snapshot import Snapshot
+    rng = np.random.default_rng(neg + num_ents)
+    n = min(300, num_ents)
+    ids = np.sort(rng.choice(num_ents, size=n, replace=False)) if spread else np.arange(n) + (num_ents - n) // 2
+    hub_tails = rng.choice(n, size=min(60, n - 1), replace=False)               # (h = 0, r = 0) has up to 60 true tails
+    hub_heads = rng.choice(n, size=min(40, n - 1), replace=False)               # (r = 1, t = 1) has up to 40 true heads
+    src = np.concatenate([np.zeros(hub_tails.size, dtype=np.int64), hub_heads, rng.integers(0, n, 80)])
+    dst = np.concatenate([hub_tails, np.ones(hub_heads.size, dtype=np.int64), rng.integers(0, n, 80)])
+    rel = np.concatenate([np.zeros(hub_tails.size, dtype=np.int64), np.ones(hub_heads.size, dtype=np.int64), rng.integers(0, 4, 80)])
+    g = Snapshot(7, ids, src, dst, rel)
+    for num_pos_facts in (3000, 50):                                            # 50 < E: torch.randperm subsampling first
+        c = CorruptTriples(Namespace(negative_rate=neg, num_pos_facts=num_pos_facts), {7: g})
+        for seed in (0, 1, 2):
+            np.random.seed(seed); torch.manual_seed(seed); np.random.randn(seed + 1)
+            a = c.single_graph_negative_sampling_python(7, g, num_ents)
+            end_a = (np.random.randint(1 << 30, size=3).tolist(), np.random.randn(), torch.rand(2))
+            np.random.seed(seed); torch.manual_seed(seed); np.random.randn(seed + 1)
+            b = c.single_graph_negative_sampling(7, g, num_ents)
+            end_b = (np.random.randint(1 << 30, size=3).tolist(), np.random.randn(), torch.rand(2))
+            for x, y in zip(a, b):
+                assert x.dtype == y.dtype and torch.equal(x, y)
+            assert end_a[0] == end_b[0] and end_a[1] == end_b[1] and torch.equal(end_a[2], end_b[2])
+
+
 def test_snapshot_store_binary_cache_round_trip(tmp_path):
     from temp_b200.snapshot import SnapshotStore
     from tests.helpers import product_store
