@@ -182,10 +182,15 @@ def encode(model, plan):
     return S, c, S1
 
 
-def all_embeds(model, plan, S, i: int, S1=None):
+def all_embeds(model, plan, S, i: int, S1=None, shared=None):
     """get_all_embeds_Gt (models/DynamicRGCN.py:56-64, BiDynamicRGCN.py:102-112): forward_isolated over all entities
     with item i's history ("history forgets": only the entities of the last history step carry a state, one step old),
-    rows of the target graph's entities overwritten by the graph states."""
+    rows of the target graph's entities overwritten by the graph states.
+
+    ``shared`` (a dict kept across the items of one batch) enables the zero-history de-duplication of
+    temp_b200/isolated.py for the GRU flavours with --rec-only-last-layer: an entity without history has the same
+    isolated state for every item up to ``+ time_embed[t]``, so that state is evaluated once per batch for all entities
+    and only the entities of the item's last history step go through the cells again with their states."""
     enc = model.ent_encoder
     l1, l2 = enc.layer_1, enc.layer_2
     training = model.training
@@ -195,8 +200,39 @@ def all_embeds(model, plan, S, i: int, S1=None):
     dev = S.device
     dirs = ["f", "b"] if bi else ["f"]
     lasts = [plan.last_hist_f[i]] + ([plan.last_hist_b[i]] if bi else [])
-    ones = torch.ones(M, dtype=S.dtype, device=dev)
     t = int(plan.final_times[i])
+    fin = plan.final.instances[i]
+    fin_ids = torch.as_tensor(fin.snapshot.node_ids, device=dev).long()
+
+    if gru and enc.rec_only_last_layer and shared is not None and not (training and l1.dropout_p > 0):
+        if "base" not in shared:
+            x = _act(_iso_pre(l2, _iso_pre(l1, model.ent_embeds, training), training), bi)
+            zero = torch.zeros(M, D, dtype=S.dtype, device=dev)
+            base = 0
+            for d in dirs:
+                base = base + _gru(model, _cell(model, l2, d), x, zero)
+            shared["x"], shared["base"] = x, base
+        x, out = shared["x"], shared["base"]
+        if enc.use_time_embedding:
+            out = out + l2.time_embed[t]
+        sets = [torch.as_tensor(last.snapshot.node_ids, device=dev).long() for last in lasts if last is not None]
+        if sets:
+            ents = torch.unique(torch.cat(sets))
+            val = 0
+            for d, last in zip(dirs, lasts):
+                h = torch.zeros(M, D, dtype=S.dtype, device=dev)
+                if last is not None:
+                    ids = torch.as_tensor(last.snapshot.node_ids, device=dev).long()
+                    h = h.index_copy(0, ids, S[last.row0:last.row0 + last.n])
+                h = h.index_select(0, ents)
+                val = val + _gru(model, _cell(model, l2, d), x.index_select(0, ents),
+                                 h * _decay(model, l2, torch.ones(ents.shape[0], dtype=S.dtype, device=dev)))
+            if enc.use_time_embedding:
+                val = val + l2.time_embed[t]
+            out = out.index_copy(0, ents, val)
+        return out.index_copy(0, fin_ids, S[fin.row0:fin.row0 + fin.n])
+
+    ones = torch.ones(M, dtype=S.dtype, device=dev)
 
     def hist_of(state):
         out = []
@@ -217,9 +253,7 @@ def all_embeds(model, plan, S, i: int, S1=None):
     else:
         first = rec_iso(l1, model.ent_embeds, S if gru else S1, False)
     second = rec_iso(l2, first, S, bi)
-    fin = plan.final.instances[i]
-    ids = torch.as_tensor(fin.snapshot.node_ids, device=dev).long()
-    return second.index_copy(0, ids, S[fin.row0:fin.row0 + fin.n])
+    return second.index_copy(0, fin_ids, S[fin.row0:fin.row0 + fin.n])
 
 
 def training_loss(model, t_list):
@@ -230,12 +264,13 @@ def training_loss(model, t_list):
     S, _, S1 = encode(model, plan)
     dev = S.device
     loss = 0
+    shared = {}
     for i, (t, g) in enumerate(zip(plan.final_times, plan.final_snapshots)):
         fin = plan.final.instances[i]
         ent_embed = S[fin.row0:fin.row0 + fin.n]
         triplets, neg_tail, neg_head, labels = model.corrupter.single_graph_negative_sampling(t, g, model.num_ents)
         triplets, neg_tail, neg_head, labels = (x.to(dev) for x in (triplets, neg_tail, neg_head, labels))
-        all_g = all_embeds(model, plan, S, i, S1)
+        all_g = all_embeds(model, plan, S, i, S1, shared)
         loss = loss + model.train_link_prediction(ent_embed, triplets, neg_tail, labels, all_g, corrupt_tail=True)
         loss = loss + model.train_link_prediction(ent_embed, triplets, neg_head, labels, all_g, corrupt_tail=False)
     return loss

@@ -50,3 +50,13 @@ for fused in (True, False):
     out["fused_scorer" if fused else "torch_scorer"] = {"s_per_step": (time.perf_counter() - t0) / n, "loss": last,
                                                         "peak_bytes": int(torch.cuda.max_memory_allocated())}
 print(json.dumps(out))
+if os.environ.get("TEMP_PROFILE"):
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
