@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) rgcn_layer_kernel(const TempRgcnL
           const int trow = p.row_time != nullptr ? __ldg(p.row_time + r) : p.row_time_scalar;
           te = ldg4(p.time_embed + static_cast<size_t>(trow) * D + c);
         }
-        if (p.h_out != nullptr) {
+        if (p.h_out != nullptr && blockIdx.y == 0) {   // (with grid.y > 1 every column block recomputes the tile; one writes it)
           float4 o = v;
           if (p.te_out) { o.x += te.x; o.y += te.y; o.z += te.z; o.w += te.w; }
           *reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(r) * D + c) = o;
@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(kThreads, 2) rgcn_layer_kernel(const TempRgcnL
     __syncthreads();
     const int NCn = p.chain_n;
     const int chunks2 = (NCn + kNC - 1) / kNC;
-    for (int ch = 0; ch < chunks2; ++ch) {
+    // launches with few row tiles spread the chained GEMM's column chunks over grid.y (each y block rebuilds the small
+    // input tile above, then takes every gridDim.y-th chunk)
+    for (int ch = blockIdx.y; ch < chunks2; ch += gridDim.y) {
       const int c = ch * kNC + tx * 4;
       float4 acc[8];
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1237,7 +1239,14 @@ int launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   const size_t smem = (static_cast<size_t>(kTM) * (Kp + 4) * (a->chain_w ? 2 : 1) + 2 * kKC * kNC) * sizeof(float);
   if (int rc = ensure_smem<0>(rgcn_layer_kernel, smem, "rgcn_layer_kernel")) return rc;
   const int grid = (rows + kTM - 1) / kTM;
-  rgcn_layer_kernel<<<grid, kThreads, smem, st>>>(*a);
+  int gy = 1;
+  if (a->chain_w != nullptr) {   // few row tiles (the Bi centre step, the last steps of a window): fill the SMs with column blocks
+    const int chunks2 = (a->chain_n + kNC - 1) / kNC;
+    gy = sm_count_cached() / grid;
+    if (gy > chunks2) gy = chunks2;
+    if (gy < 1) gy = 1;
+  }
+  rgcn_layer_kernel<<<dim3(grid, gy), kThreads, smem, st>>>(*a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_kernel launch");
   return TEMP_OK;
