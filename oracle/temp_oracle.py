@@ -663,6 +663,105 @@ class OracleModel:
         return out
 
 
+    def all_embeds_with_history_of(self, res, i: int, hist_item: int) -> Tensor:
+        """get_all_embeds_Gt of target graph i evaluated with the history tensors of batch item ``hist_item`` -- what
+        the reference's calc_metrics computes when an earlier evaluation graph of the batch had no edges (see
+        ``evaluate``).  Rows of graph i's entities still come from graph i's states, the time embedding from its time."""
+        if hist_item == i or self.cfg.module == "SRGCN":
+            return self.all_embeds(res, i)
+        shifted = dict(res)
+        for key in ("hist", "start", "hist_f", "start_f", "hist_b", "start_b", "mask"):
+            if key in res:
+                v = res[key]
+                if self.cfg.attention:                                    # [L-1, B, ...]: item axis is 1
+                    v = v.clone()
+                    v[:, i] = res[key][:, hist_item]
+                else:                                                     # [B, ...]
+                    v = v.clone()
+                    v[i] = res[key][hist_item]
+                shifted[key] = v
+        return self.all_embeds(shifted, i)
+
+    def evaluate(self, t_list: Sequence[int], valid, test=None, val: bool = True, score_function: str = "complex"):
+        """``evaluate(t_list, val)`` of the reference -> (ranks LongTensor, mean link-classification loss):
+        models/DynamicRGCN.py:118-130 + calc_metrics 196-220 (BiDynamicRGCN.py:176-209, SelfAttentionRGCN.py:141-176,
+        baselines/StaticRGCN.py:20-22, 91-113) over utils/evaluation.py:6-106.
+
+        Quirk kept: in the dynamic models' calc_metrics the history index ``i`` only advances for evaluation graphs
+        that HAVE edges (``continue`` sits before ``i += 1``), so after an empty graph every later graph of the batch
+        is scored with the history of the item before it.  StaticRGCN has no history and no such index."""
+        cfg = self.cfg
+        res = self.evaluate_embed(t_list)
+        graph_dict = valid if val else test
+        score = {"complex": score_complex, "distmult": score_distmult, "transE": score_transe}[score_function]
+        rel = self.p["rel_embeds"]
+        ranks, losses = [], []
+        i = 0
+        for pos, (t, ent) in enumerate(zip(res["times"], res["per_graph"])):
+            g = graph_dict[int(t)]
+            alls = self.all_embeds(res, pos) if cfg.module == "SRGCN" else self.all_embeds_with_history_of(res, pos, i)
+            if g.num_edges == 0:
+                continue
+            samples = torch.from_numpy(np.stack([g.src, g.rel, g.dst], axis=1)).long()
+            parts = [x for x in (self.gd.get(int(t)), valid.get(int(t)), test.get(int(t)) if test is not None else None)
+                     if x is not None]
+            ranks.append(filtered_ranks(score, ent, rel, alls, samples, g, parts))
+            s, r, o = ent[samples[:, 0]], rel[samples[:, 1]], ent[samples[:, 2]]
+            losses.append(float(torch.nn.functional.binary_cross_entropy_with_logits(score(s, r, o), torch.ones(samples.shape[0]))))
+            i += 1
+        ranks = torch.cat(ranks) if ranks else torch.zeros(0, dtype=torch.long)
+        return ranks, (float(np.mean(losses)) if losses else float("nan"))
+
+
+def filtered_ranks(score, ent: Tensor, rel: Tensor, alls: Tensor, samples: Tensor, g: "SnapGraph", splits) -> Tensor:
+    """utils/evaluation.py:35-106 for one evaluation graph: true heads / tails from the train + valid + test triples of
+    the timestamp in LOCAL node ids (lines 17-33; the three graphs of a timestamp share one node set), per query the
+    known answers masked except the query's own target (82-99), scores against all entities in batches of 100,
+    torch.where(mask, -10e6, score), sigmoid, descending sort, position of the target (53-80, 101-106); subject side
+    first, then object side, + 1 (47-49)."""
+    tri = np.concatenate([np.stack([x.src, x.rel, x.dst], axis=1) for x in splits], axis=0)
+    th, tt = {}, {}
+    for h, r, t in tri.tolist():
+        tt.setdefault((h, r), []).append(t)
+        th.setdefault((r, t), []).append(h)
+    th = {k: np.array(list(set(v))) for k, v in th.items()}
+    tt = {k: np.array(list(set(v))) for k, v in tt.items()}
+    ids = g.ids
+    M = alls.shape[0]
+    n = samples.shape[0]
+
+    def mask_of(mode):
+        mask = torch.zeros(n, M, dtype=torch.bool)
+        for q, (h, r, t) in enumerate(samples.tolist()):
+            if mode == "tail":
+                mask[q, torch.from_numpy(ids[tt[(h, r)]])] = True
+                mask[q, int(ids[t])] = False
+            else:
+                mask[q, torch.from_numpy(ids[th[(r, t)]])] = True
+                mask[q, int(ids[h])] = False
+        return mask
+
+    gids = torch.from_numpy(ids)
+    out = {}
+    for mode in ("tail", "head"):                                         # ranks_o is computed first (lines 44-47)
+        mask = mask_of(mode)
+        rk = []
+        for lo in range(0, n, 100):
+            sl = slice(lo, min(n, lo + 100))
+            r = rel[samples[sl, 1]]
+            if mode == "tail":
+                sc = score(ent[samples[sl, 0]], r, alls, mode="tail")
+                target = gids[samples[sl, 2]]
+            else:
+                sc = score(alls, r, ent[samples[sl, 2]], mode="head")
+                target = gids[samples[sl, 0]]
+            sc = torch.sigmoid(torch.where(mask[sl], -10e6 * torch.ones_like(sc), sc))
+            _, order = torch.sort(sc, dim=1, descending=True)
+            rk.append(torch.nonzero(order == target.view(-1, 1))[:, 1].view(-1))
+        out[mode] = torch.cat(rk)
+    return torch.cat([out["head"], out["tail"]]) + 1
+
+
 # --------------------------------------------------------------------------------------------
 # scores and the negative sampler (kept host-side and bit-exact)
 # --------------------------------------------------------------------------------------------

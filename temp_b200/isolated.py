@@ -66,8 +66,13 @@ def _scatter(src, dst, n, d, src_index=None, dst_index=None, add_row=None):
     return a
 
 
-def all_embeds_item(model, res: EncodeResult, i: int) -> torch.Tensor:
+def all_embeds_item(model, res: EncodeResult, i: int, hist_item=None) -> torch.Tensor:
+    """All-entity table of target graph ``i``.  ``hist_item`` (default ``i``): the batch item whose history feeds the
+    isolated pass -- the reference's calc_metrics uses a lagging index there after an evaluation graph without edges
+    (models/DynamicRGCN.py:196-220: ``continue`` before ``i += 1``); the overwritten rows and the time embedding are
+    always graph i's."""
     rt = model.runtime
+    h = i if hist_item is None else int(hist_item)
     plan, D, M = res.plan, model.embed_size, model.num_ents
     enc = model.ent_encoder
     l1, l2 = enc.layer_1, enc.layer_2
@@ -91,7 +96,7 @@ def all_embeds_item(model, res: EncodeResult, i: int) -> torch.Tensor:
         prog.add(lib.OP_LAYER, iso_layer(l2, y1, True, h_out=out, te_out=use_te, row_time_scalar=t))
     elif fam == "attention":
         maps = _iso_maps(model, res)
-        slot_ptr = maps["slots"][i].data_ptr()
+        slot_ptr = maps["slots"][h].data_ptr()
         tau = torch.tensor(model.time_diff(plan), dtype=torch.float32, device=dev)
         prog.keepalive.append(tau)
         qkv = ws.get("iso_qkv", M * 3 * D)[:M * 3 * D].view(M, 3 * D)
@@ -130,7 +135,7 @@ def all_embeds_item(model, res: EncodeResult, i: int) -> torch.Tensor:
         gru = model.args.module in ("GRRGCN", "BiGRRGCN")
         bi = plan.bidirectional
         dirs = ["f", "b"] if bi else ["f"]
-        prev = [maps["prev"][d][i].data_ptr() for d in range(len(dirs))]
+        prev = [maps["prev"][d][h].data_ptr() for d in range(len(dirs))]
         ones = maps["ones"].data_ptr()
         type1 = bool(getattr(model.args, "type1", False))
         G = D if type1 else 3 * D
@@ -179,7 +184,7 @@ def all_embeds_item(model, res: EncodeResult, i: int) -> torch.Tensor:
             bs, gi = base
             te_row = l2.time_embed.data_ptr() + t * D * _F32 if use_te else None
             prog.add(lib.OP_SCATTER, _scatter(bs.data_ptr(), out.data_ptr(), M, D, add_row=te_row))
-            lasts = [plan.last_hist_f[i]] + ([plan.last_hist_b[i]] if bi else [])
+            lasts = [plan.last_hist_f[h]] + ([plan.last_hist_b[h]] if bi else [])
             ent_sets = [x.snapshot.node_ids for x in lasts if x is not None]
             if ent_sets:
                 ents = torch.from_numpy(np.unique(np.concatenate(ent_sets)).astype(np.int32)).to(dev)
@@ -189,7 +194,7 @@ def all_embeds_item(model, res: EncodeResult, i: int) -> torch.Tensor:
                 ga = lib.GatherArgs()
                 ga.n, ga.d, ga.table, ga.index, ga.out = nc, 2 * G, gi.data_ptr(), ents.data_ptr(), gic.data_ptr()
                 prog.add(lib.OP_GATHER, ga)
-                prev_c = [maps["prev"][j][i][ents.long()].contiguous() for j in range(len(dirs))]
+                prev_c = [maps["prev"][j][h][ents.long()].contiguous() for j in range(len(dirs))]
                 prog.keepalive += [ents, gic, outc] + prev_c
                 for j, d in enumerate(dirs):
                     prog.add(lib.OP_GRU, rt._gru(l2, rnns[j][1], rnns[j][0], (0, nc), gi=gic, gi_ld=2 * G, gi_off=j * G,

@@ -335,10 +335,13 @@ class TKG_Module(nn.Module):
                                               self.graph_dict_test)
         dev = self.ent_embeds.device
         ranks, losses = [], []
+        lag = 0                      # evaluation graphs without edges so far: the reference's history index lags by that many
         for g, t, ent_embed in zip(g_list, t_list, per_graph_ent_embeds):
             if g is None or g.num_edges == 0:
+                lag += 1
                 continue
-            all_g = self.all_embeds(self.last_result, self._item_of(t))
+            item = self._item_of(t)
+            all_g = self.all_embeds(self.last_result, item, hist_item=self._lagged(item, lag))
             src, dst = g.edges()
             index_sample = torch.stack([src, g.edata["type_s"], dst]).transpose(0, 1).to(dev)
             label = torch.ones(index_sample.shape[0], device=dev)
@@ -347,6 +350,14 @@ class TKG_Module(nn.Module):
         ranks = torch.cat(ranks) if ranks else torch.zeros(0, dtype=torch.long, device=dev)
         return ranks, (float(np.mean(losses)) if losses else float("nan"))
 
+    def _lagged(self, item: int, lag: int):
+        """History index the reference's calc_metrics uses for batch item ``item`` after ``lag`` evaluation graphs
+        without edges: its counter only advances for graphs that have edges (models/DynamicRGCN.py:196-220,
+        BiDynamicRGCN.py:186-209, SelfAttentionRGCN.py:154-176), so later graphs are scored with the history of an
+        earlier item.  Kept for parity (pinned by tests/golden/rank_*_empty_first.npz); the static model has no
+        history index (baselines/StaticRGCN.py:91-113)."""
+        return None if (lag == 0 or self.family == "static") else item - lag
+
     def validation_end(self, outputs):
         mrr, h1, h3, h10 = self.get_metrics(torch.cat([x["ranks"] for x in outputs]))
         return {"mrr": mrr, "avg_val_loss": np.mean([x["val_loss"] for x in outputs]), "hit_10": h10, "hit_3": h3,
@@ -354,10 +365,10 @@ class TKG_Module(nn.Module):
 
     # ---- all-entity table (region R2) ---------------------------------------------------------------
     @torch.no_grad()
-    def all_embeds(self, res: EncodeResult, i: int) -> torch.Tensor:
-        """``get_all_embeds_Gt`` for batch item i from the compact window state."""
+    def all_embeds(self, res: EncodeResult, i: int, hist_item=None) -> torch.Tensor:
+        """``get_all_embeds_Gt`` for batch item i from the compact window state (``hist_item``: see ``evaluate``)."""
         from .isolated import all_embeds_item
-        return all_embeds_item(self, res, i)
+        return all_embeds_item(self, res, i, hist_item)
 
     def _targets(self, res: EncodeResult, graph_dict):
         return [graph_dict[t] for t in res.plan.final_times]
@@ -405,11 +416,13 @@ class TKG_Module(nn.Module):
         graph_dict = self.graph_dict_val if val else self.graph_dict_test
         dev = self.ent_embeds.device
         ranks, losses = [], []
+        lag = 0
         for i, (t, ent_embed) in enumerate(zip(res.plan.final_times, res.per_graph)):
             g = graph_dict[t]
             if g.num_edges == 0:
+                lag += 1             # the reference's calc_metrics: `continue` before `i += 1` (models/DynamicRGCN.py:209-214)
                 continue
-            all_g = self.all_embeds(res, i)
+            all_g = self.all_embeds(res, i, hist_item=self._lagged(i, lag))
             src, dst = g.edges()
             index_sample = torch.stack([src, g.edata["type_s"], dst]).transpose(0, 1).to(dev)
             label = torch.ones(index_sample.shape[0], device=dev)

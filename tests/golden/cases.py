@@ -67,3 +67,23 @@ TRAIN_CASES = [
     dict(name="train_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last", seed=21, random_dropout=False),
     dict(name="train_bigrrgcn_tiny_random_dropout", base="bigrrgcn_tiny_d128_last", seed=22, random_dropout=True),
 ]
+
+# evaluate(t_list, val=True) of the unmodified reference -> filtered ranks (subject side then object side per graph) and the
+# mean link-classification loss (models/DynamicRGCN.py:118-130, 196-220 over utils/evaluation.py:6-106).  ``empty_first``:
+# the validation graph of the latest target timestamp -- the first one calc_metrics visits -- has its edges removed, which
+# makes the reference's history index lag for every later graph of the batch (`continue` before `i += 1`).
+RANK_CASES = [
+    dict(name="rank_grrgcn_tiny", base="grrgcn_tiny_d128_last"),
+    dict(name="rank_rrgcn_tiny_full", base="rrgcn_tiny_d128_full"),
+    dict(name="rank_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last"),
+    dict(name="rank_sargcn_tiny", base="sargcn_tiny_d128_last"),
+    dict(name="rank_bisargcn_tiny", base="bisargcn_tiny_d128_last"),
+    dict(name="rank_srgcn_tiny", base="srgcn_tiny_d128"),
+    dict(name="rank_grrgcn_icews", base="grrgcn_icews_d128_L8"),
+    dict(name="rank_bigrrgcn_icews", base="bigrrgcn_icews_d128_L8"),
+    dict(name="rank_bisargcn_icews", base="bisargcn_icews_d128_L8"),
+    dict(name="rank_grrgcn_tiny_empty_first", base="grrgcn_tiny_d128_last", empty_first=True),
+    dict(name="rank_bigrrgcn_tiny_empty_first", base="bigrrgcn_tiny_d128_last", empty_first=True),
+    dict(name="rank_sargcn_tiny_empty_first", base="sargcn_tiny_d128_last", empty_first=True),
+    dict(name="rank_grrgcn_icews_empty_first", base="grrgcn_icews_d128_L8", empty_first=True),
+]

@@ -20,7 +20,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from tests.golden.cases import CASES, SAMPLER_CASES, TRAIN_CASES, dataset_path  # noqa: E402
+from tests.golden.cases import CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES, dataset_path  # noqa: E402
 from oracle.temp_oracle import fill_values  # noqa: E402
 
 
@@ -173,10 +173,39 @@ def run_sampler_case(case):
     return out
 
 
+def run_rank_case(rc):
+    """ranks, loss = model.evaluate(t_list, val=True) of the unmodified reference."""
+    case = next(c for c in CASES if c["name"] == rc["base"])
+    model, (_, gva, _) = ref_model(case)
+    if rc.get("empty_first"):
+        t_empty = max(int(t) for t in case["t_list"])
+        g = gva[t_empty]
+        sub = g.edge_subgraph(torch.zeros(0, dtype=torch.long), preserve_nodes=True)
+        sub.ids = g.ids
+        for k in ("id", "norm"):
+            if k in g.ndata:
+                sub.ndata[k] = g.ndata[k]
+        for k in g.edata:
+            sub.edata[k] = g.edata[k][:0]
+        model.graph_dict_val = dict(gva)
+        model.graph_dict_val[t_empty] = sub
+    with torch.no_grad():
+        ranks, loss = model.evaluate(torch.tensor(case["t_list"], dtype=torch.long), val=True)
+    return {"ranks": ranks.numpy().astype(np.int64), "loss": np.asarray(float(loss), dtype=np.float64)}
+
+
 def main():
     warnings.filterwarnings("ignore")
     reference_on_path()
     only_train = "--train-only" in sys.argv
+    only_rank = "--rank-only" in sys.argv
+    for rc in ([] if only_train else RANK_CASES):
+        res = run_rank_case(rc)
+        path = os.path.join(HERE, rc["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print("%-40s ranks=%d loss=%.9g" % (rc["name"], res["ranks"].shape[0], float(res["loss"])))
+    if only_rank:
+        return
     for case in ([] if only_train else CASES):
         res = run_case(case)
         path = os.path.join(HERE, case["name"] + ".npz")

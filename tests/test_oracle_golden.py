@@ -93,3 +93,29 @@ def test_training_forward_loss_matches_reference(tc):
                                 tc.get("num_pos_facts", case.get("num_pos_facts", 3000)),
                                 random_dropout=tc["random_dropout"])
     assert abs(float(loss) - float(gold["loss"])) <= 2e-5 * abs(float(gold["loss"]))
+
+
+def _valid_with_empty_first(case, valid):
+    """The validation dict of a RANK_CASES entry with ``empty_first``: the latest target's graph without edges."""
+    t_empty = max(int(t) for t in case["t_list"])
+    g = valid[t_empty]
+    out = dict(valid)
+    out[t_empty] = orc.SnapGraph(ids=g.ids, src=g.src[:0], dst=g.dst[:0], rel=g.rel[:0], norm=np.zeros_like(g.norm), time=g.time)
+    return out
+
+
+@pytest.mark.parametrize("rc", __import__("tests.golden.cases", fromlist=["RANK_CASES"]).RANK_CASES, ids=lambda c: c["name"])
+def test_evaluate_ranks_match_reference(rc):
+    """oracle.evaluate == the reference's evaluate(t_list, val=True): filtered ranks (integer-exact, same torch CPU sort on
+    both sides) and the mean link-classification loss -- including the batches whose first evaluation graph is empty,
+    where the reference's history index lags behind the graph index."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME[rc["base"]]
+    gold = load_golden(rc["name"])
+    _, _, _, valid, test = oracle_graphs(case["dataset"])
+    if rc.get("empty_first"):
+        valid = _valid_with_empty_first(case, valid)
+    with torch.no_grad():
+        ranks, loss = oracle_model(case).evaluate(case["t_list"], valid, test, val=True)
+    assert ranks.dtype == torch.long and np.array_equal(ranks.numpy(), gold["ranks"])
+    assert abs(loss - float(gold["loss"])) <= 1e-6 * abs(float(gold["loss"]))
