@@ -446,9 +446,8 @@ def test_evaluate_matches_the_reference_ranks(rc):
     same = (ranks == want).float().mean().item()
     assert same >= 0.95 and int((ranks - want).abs().max()) <= 2, (same, (ranks - want).abs().max().item())
     # the reference-style entry (evaluate_embed -> calc_metrics) walks the same graphs with the same lag
-    out = model.evaluate_embed(torch.tensor(case["t_list"]), val=True)
     if model.family == "recurrent" and not model.bidirectional:
-        per_graph, graphs, time_list, hist, start = out
+        per_graph, graphs, time_list, hist, start = model.evaluate_embed(torch.tensor(case["t_list"]), val=True)
         ranks2, _ = model.calc_metrics(per_graph, graphs, time_list[-1], hist, start, model.test_seq_len - 1)
         assert torch.equal(ranks2, ranks)
 
