@@ -563,9 +563,34 @@ class OracleModel:
         graph and the tail + head cross-entropy (TKG_Module.py:202-213).  Global NumPy / torch RNG order as in the
         reference."""
         cfg = self.cfg
-        assert not cfg.attention and cfg.module != "SRGCN"
         L = cfg.seq_len
         rate_hist = 0.8 if random_dropout else None
+        if cfg.module == "SRGCN":
+            # baselines/StaticRGCN.py:36-47, 60-89: the target graphs in the CALLER's order, each on a 50 % edge subset
+            ts = [int(t) for t in t_list]
+            full_graphs = [self.gd[t] for t in ts]
+            out = self.enc_static([sample_edges(g, 0.5) for g in full_graphs], ts)
+            res = {"times": ts, "graphs": full_graphs, "per_graph": list(out.split([g.num_nodes for g in full_graphs]))}
+            return self._link_prediction_loss(res, full_graphs, negative_rate, num_pos_facts)
+        if cfg.attention:
+            # models/SelfAttentionRGCN.py:122-139 (history sub-sampled at 0.8 only with --random-dropout) and
+            # models/BiSelfAttentionRGCN.py:48-69 (history always on full graphs); the final step on a 50 % edge subset
+            tb = window_forward(t_list, L, self.times)
+            ts = tb[-1]
+            full_graphs = [self.gd[t] for t in ts]
+            hist, mask = self._attention_history(t_list, sample_rate=None if cfg.bidirectional else rate_hist)
+            p1, p2, lm = [], [], []
+            for i, g in enumerate(full_graphs):
+                idx = torch.from_numpy(g.ids)
+                p1.append(hist[:, i, 0][:, idx])
+                p2.append(hist[:, i, 1][:, idx])
+                lm.append(mask[:, i][:, idx])
+            graphs = [sample_edges(g, 0.5) for g in full_graphs]
+            out = self.enc_attention_final(graphs, ts, torch.cat(p1, 1).transpose(0, 1), torch.cat(p2, 1).transpose(0, 1),
+                                           self._tau(), torch.cat(lm, 1).transpose(0, 1))
+            res = {"times": ts, "graphs": full_graphs, "hist": hist, "mask": mask,
+                   "per_graph": list(out.split([g.num_nodes for g in full_graphs]))}
+            return self._link_prediction_loss(res, full_graphs, negative_rate, num_pos_facts)
         tb = window_forward(t_list, L, self.times)
         ts = tb[-1]
         full_graphs = [self.gd[t] for t in ts]
@@ -585,6 +610,11 @@ class OracleModel:
             graphs = [sample_edges(g, 0.5) for g in full_graphs]
             _, out = self.enc_recurrent(graphs, ts, [p1], [p2], [dt], "forward")
             res = {"times": ts, "graphs": full_graphs, "hist": hist, "start": start, "per_graph": list(out.split(sizes))}
+        return self._link_prediction_loss(res, full_graphs, negative_rate, num_pos_facts)
+
+    def _link_prediction_loss(self, res, full_graphs, negative_rate: int, num_pos_facts: int) -> Tensor:
+        """Per target graph: the negative sampler on the FULL graph, then tail + head cross-entropy against the
+        all-entity table (models/TKG_Module.py:202-213)."""
         score = {"complex": score_complex, "distmult": score_distmult, "transE": score_transe}["complex"]
         rel = self.p["rel_embeds"]
         loss = torch.zeros(())
@@ -604,8 +634,9 @@ class OracleModel:
             return torch.tensor(list(range(L - 1, 0, -1)) * 2 + [0.0])
         return torch.tensor(list(range(L - 1, -1, -1))).float()           # SelfAttentionRGCN.py:22-23
 
-    def _attention_scan(self, time_batched, flip: bool):
-        """models/SelfAttentionRGCN.py:104-120 / BiSelfAttentionRGCN.py:25-46."""
+    def _attention_scan(self, time_batched, flip: bool, sample_rate: Optional[float] = None):
+        """models/SelfAttentionRGCN.py:104-120 / BiSelfAttentionRGCN.py:25-46 (sample_rate: the uni model's
+        --random-dropout history sub-sampling in train mode, SelfAttentionRGCN.py:111, 118)."""
         L, bsz = self.cfg.seq_len, len(time_batched[0])
         hist = torch.zeros(L - 1, bsz, 2, self.M, self.D)
         mask = torch.zeros(L - 1, bsz, self.M) - 10e9
@@ -614,6 +645,8 @@ class OracleModel:
             if not ts:
                 continue
             graphs = [self.gd[t] for t in ts]
+            if sample_rate is not None:
+                graphs = [sample_edges(g, sample_rate) for g in graphs]
             first, second = self.enc_attention_history(graphs, ts)
             off = 0
             for i, g in enumerate(graphs):
@@ -626,9 +659,9 @@ class OracleModel:
             hist, mask = torch.flip(hist, [1]), torch.flip(mask, [1])
         return hist, mask
 
-    def _attention_history(self, t_list):
+    def _attention_history(self, t_list, sample_rate: Optional[float] = None):
         L = self.cfg.seq_len
-        hist, mask = self._attention_scan(window_forward(t_list, L, self.times), flip=False)
+        hist, mask = self._attention_scan(window_forward(t_list, L, self.times), flip=False, sample_rate=sample_rate)
         if self.cfg.bidirectional:                                        # BiSelfAttentionRGCN.py:82-84
             hb, mb = self._attention_scan(window_backward(t_list, L, self.times), flip=True)
             hist = torch.cat([hist, hb], dim=0)

@@ -113,6 +113,8 @@ class TKG_Module(nn.Module):
         NumPy stream in the reference's call order, the drawn order is the new edge order and the
         norms are recomputed on the sub-graph."""
         random_dropout = bool(getattr(self.args, "random_dropout", False))
+        if self.family == "attention" and self.bidirectional:
+            random_dropout = False              # BiSelfAttentionRGCN.py:42-43: the history always runs on full graphs
 
         def transform(kind, snap):
             if kind == "hist" and not random_dropout:
@@ -387,9 +389,9 @@ class TKG_Module(nn.Module):
 
     def _forward_no_grad(self, t_list):
         if self.training:
-            if self.family != "recurrent":
-                raise NotImplementedError("temp_b200: the training-mode edge sub-sampling is implemented for the recurrent "
-                                          "families ((Bi)GRRGCN / (Bi)RRGCN); call .eval() for the deterministic forward")
+            # every family sub-samples the final step at 0.5 (history steps at 0.8 with --random-dropout, except the Bi
+            # attention model): models/DynamicRGCN.py:176-194, BiDynamicRGCN.py:165-187, SelfAttentionRGCN.py:122-139,
+            # BiSelfAttentionRGCN.py:48-69, baselines/StaticRGCN.py:36-47, 60-80
             # (the self-loop dropout of models/RGCN.py:58-59 is not applied by the CUDA forward: parity holds at p = 0)
             res = self.encode(plan=self.plan(t_list, transform=self.train_edge_sampler()))
         else:
@@ -537,8 +539,17 @@ class StaticRGCN(TKG_Module):
     def build_model(self):
         self.ent_encoder = enc_mod.RGCN(self.args, self.hidden_size, self.embed_size, self.num_rels, self.total_time)
 
-    def plan(self, t_list, seq_len=None) -> WindowPlan:
-        return plan_static(self.graph_dict_train, _as_int_list(t_list))
+    def plan(self, t_list, seq_len=None, transform=None) -> WindowPlan:
+        """One snapshot per target in the caller's order (baselines/StaticRGCN.py:23-28); ``transform``: the training-mode
+        edge sub-sampling (StaticRGCN.py:60-80), the full graphs stay in ``plan.final_snapshots`` for the sampler."""
+        ts = _as_int_list(t_list)
+        if transform is None:
+            return plan_static(self.graph_dict_train, ts)
+        from .planner import plan_snapshots
+        full = [self.graph_dict_train[t] for t in ts]
+        plan = plan_snapshots([transform("final", g) for g in full], ts)
+        plan.final_snapshots = full
+        return plan
 
     @torch.no_grad()
     def get_all_embeds_Gt(self, t, g, convoluted_embeds):

@@ -66,6 +66,13 @@ TRAIN_CASES = [
     # bidirectional (models/BiDynamicRGCN.py:165-187): forward history, backward history, centre step
     dict(name="train_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last", seed=21, random_dropout=False),
     dict(name="train_bigrrgcn_tiny_random_dropout", base="bigrrgcn_tiny_d128_last", seed=22, random_dropout=True),
+    # static and attention families (baselines/StaticRGCN.py:36-47, models/SelfAttentionRGCN.py:122-139,
+    # models/BiSelfAttentionRGCN.py:48-69)
+    dict(name="train_srgcn_tiny", base="srgcn_tiny_d128", seed=31, random_dropout=False),
+    dict(name="train_sargcn_tiny", base="sargcn_tiny_d128_last", seed=32, random_dropout=False),
+    dict(name="train_sargcn_tiny_full_random_dropout", base="sargcn_tiny_d128_full", seed=33, random_dropout=True),
+    dict(name="train_bisargcn_tiny_random_dropout", base="bisargcn_tiny_d128_last", seed=34, random_dropout=True),
+    dict(name="train_bisargcn_icews", base="bisargcn_icews_d128_L8", seed=35, random_dropout=False, negative_rate=20),
 ]
 
 # evaluate(t_list, val=True) of the unmodified reference -> filtered ranks (subject side then object side per graph) and the

@@ -298,7 +298,8 @@ def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None):
 
 
 @pytest.mark.parametrize("tc", [c for c in __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES
-                                if "icews" not in c["name"]], ids=lambda c: c["name"])
+                                if "icews" not in c["name"] and "sargcn" not in c["name"] and "srgcn" not in c["name"]],
+                         ids=lambda c: c["name"])
 def test_autograd_fallback_gradients_match_oracle(tc):
     """loss.backward() through the fallback gives the gradients of the (reference-pinned) oracle's training loss:
     train mode, sub-sampled window, dropout p = 0, same global seeds; the loss also matches the committed golden value.
