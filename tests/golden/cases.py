@@ -48,6 +48,10 @@ CASES = [
     _c("grrgcn_icews_d128_L8", "GRRGCN", dataset="icews14_head", L=8, t_list=(11, 10, 3)),
     _c("bigrrgcn_icews_d128_L8", "BiGRRGCN", dataset="icews14_head", L=8, t_list=(11, 6, 3)),
     _c("bisargcn_icews_d128_L8", "BiSARGCN", dataset="icews14_head", L=8, t_list=(11, 5)),
+    # --- the whole real ICEWS14 split: windows at the start, in the middle and at the very end of the timeline
+    #     (t in {0, 3, 7, 200, 364})
+    _c("grrgcn_icews14_real_L8", "GRRGCN", dataset="icews14", L=8, t_list=(364, 200, 7, 3, 0)),
+    _c("bigrrgcn_icews14_real_L8", "BiGRRGCN", dataset="icews14", L=8, t_list=(364, 200, 7, 3, 0)),
 ]
 
 SAMPLER_CASES = [
@@ -89,6 +93,7 @@ RANK_CASES = [
     dict(name="rank_grrgcn_icews", base="grrgcn_icews_d128_L8"),
     dict(name="rank_bigrrgcn_icews", base="bigrrgcn_icews_d128_L8"),
     dict(name="rank_bisargcn_icews", base="bisargcn_icews_d128_L8"),
+    dict(name="rank_grrgcn_icews14_real", base="grrgcn_icews14_real_L8"),
     dict(name="rank_grrgcn_tiny_empty_first", base="grrgcn_tiny_d128_last", empty_first=True),
     dict(name="rank_bigrrgcn_tiny_empty_first", base="bigrrgcn_tiny_d128_last", empty_first=True),
     dict(name="rank_sargcn_tiny_empty_first", base="sargcn_tiny_d128_last", empty_first=True),

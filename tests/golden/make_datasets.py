@@ -3,6 +3,7 @@
   data/tiny/         seeded synthetic: 40 entities, 6 relations, 10 timestamps; contains
                      multi-edges, zero-in-degree nodes, a near-empty snapshot and entities that
                      only occur in valid/test (exercises utils/dataset.py:151-232 of the reference).
+  data/icews14/      the whole public ICEWS14 interpolation split (365 timestamps), same source, ids unchanged
   data/icews14_head/ the first 12 timestamps of the public ICEWS14 interpolation split as shipped
                      with the reference (/root/reference/interpolation/icews14, DATA not source),
                      ids unchanged (M = 7128, 230 relations).
@@ -47,8 +48,8 @@ def make_tiny():
         f.write("%d\t%d\t%d\n" % (M, R, T))
 
 
-def make_icews_head(src="/root/reference/interpolation/icews14", n_times=12):
-    out = os.path.join(HERE, "data", "icews14_head")
+def make_icews_head(src="/root/reference/interpolation/icews14", n_times=12, name="icews14_head"):
+    out = os.path.join(HERE, "data", name)
     os.makedirs(out, exist_ok=True)
     for mode in ("train", "valid", "test"):
         quads = []
@@ -68,3 +69,4 @@ if __name__ == "__main__":
     make_tiny()
     if os.path.isdir("/root/reference/interpolation/icews14"):
         make_icews_head()
+        make_icews_head(n_times=365, name="icews14")      # the whole public split (1.5 MB of text): real windows at any t

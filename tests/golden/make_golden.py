@@ -199,6 +199,17 @@ def main():
     reference_on_path()
     only_train = "--train-only" in sys.argv
     only_rank = "--rank-only" in sys.argv
+    if "--only" in sys.argv:                       # --only name1,name2: just these cases (of any kind)
+        names = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+        for fn, cases in ((run_rank_case, RANK_CASES), (run_case, CASES), (run_train_case, TRAIN_CASES),
+                          (run_sampler_case, SAMPLER_CASES)):
+            for case in cases:
+                if case["name"] in names:
+                    res = fn(case)
+                    path = os.path.join(HERE, case["name"] + ".npz")
+                    np.savez_compressed(path, **res)
+                    print("%-40s %.1f KB" % (case["name"], os.path.getsize(path) / 1024))
+        return
     for rc in ([] if only_train else RANK_CASES):
         res = run_rank_case(rc)
         path = os.path.join(HERE, rc["name"] + ".npz")
