@@ -20,7 +20,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from tests.golden.cases import CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES, dataset_path  # noqa: E402
+from tests.golden.cases import CASES, CPU_CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES, dataset_path  # noqa: E402
 from oracle.temp_oracle import fill_values  # noqa: E402
 
 
@@ -201,7 +201,7 @@ def main():
     only_rank = "--rank-only" in sys.argv
     if "--only" in sys.argv:                       # --only name1,name2: just these cases (of any kind)
         names = set(sys.argv[sys.argv.index("--only") + 1].split(","))
-        for fn, cases in ((run_rank_case, RANK_CASES), (run_case, CASES), (run_train_case, TRAIN_CASES),
+        for fn, cases in ((run_rank_case, RANK_CASES), (run_case, CASES + CPU_CASES), (run_train_case, TRAIN_CASES),
                           (run_sampler_case, SAMPLER_CASES)):
             for case in cases:
                 if case["name"] in names:
@@ -217,7 +217,7 @@ def main():
         print("%-40s ranks=%d loss=%.9g" % (rc["name"], res["ranks"].shape[0], float(res["loss"])))
     if only_rank:
         return
-    for case in ([] if only_train else CASES):
+    for case in ([] if only_train else CASES + CPU_CASES):
         res = run_case(case)
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **res)

@@ -5,14 +5,14 @@ import pytest
 import torch
 
 from oracle import temp_oracle as orc
-from tests.golden.cases import CASES, SAMPLER_CASES
+from tests.golden.cases import CASES, CPU_CASES, SAMPLER_CASES
 from tests.helpers import load_golden, oracle_graphs, oracle_model, rel_err
 
 # same torch CPU kernels on both sides; only the op grouping differs slightly
 TOL = 2e-6
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("case", CASES + CPU_CASES, ids=[c["name"] for c in CASES + CPU_CASES])
 def test_forward_matches_reference(case):
     gold = load_golden(case["name"])
     model = oracle_model(case)
