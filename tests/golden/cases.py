@@ -59,6 +59,8 @@ CASES = [
 CPU_CASES = [
     # BASELINE config 5 on real data: GDELT snapshots (in-degrees in the hundreds, duplicate facts), seq_len 15, batch 2
     _c("grrgcn_gdelt_real_L15", "GRRGCN", dataset="gdelt_head", L=15, t_list=(16, 15)),
+    # BASELINE config 3 as the reference ships it (n_bases = 100 => D = 200, 2 x 2 blocks) on real ICEWS05-15 snapshots
+    _c("bigrrgcn_icews0515_real_nb100", "BiGRRGCN", dataset="icews0515_head", D=200, n_bases=100, L=8, t_list=(8, 7, 3)),
 ]
 
 SAMPLER_CASES = [

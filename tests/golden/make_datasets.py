@@ -4,6 +4,7 @@
                      multi-edges, zero-in-degree nodes, a near-empty snapshot and entities that
                      only occur in valid/test (exercises utils/dataset.py:151-232 of the reference).
   data/icews14/      the whole public ICEWS14 interpolation split (365 timestamps), same source, ids unchanged
+  data/icews0515_head/ the first 17 timestamps of the public ICEWS05-15 interpolation split (M = 10 488, 251 relations)
   data/gdelt_head/   the first 17 timestamps of the public GDELT interpolation split, same source
   data/icews14_head/ the first 12 timestamps of the public ICEWS14 interpolation split as shipped
                      with the reference (/root/reference/interpolation/icews14, DATA not source),
@@ -71,6 +72,8 @@ if __name__ == "__main__":
     if os.path.isdir("/root/reference/interpolation/icews14"):
         make_icews_head()
         make_icews_head(n_times=365, name="icews14")      # the whole public split (1.5 MB of text): real windows at any t
+    if os.path.isdir("/root/reference/interpolation/icews05-15"):
+        make_icews_head(src="/root/reference/interpolation/icews05-15", n_times=17, name="icews0515_head")
     if os.path.isdir("/root/reference/interpolation/gdelt"):
         # the first 17 timestamps of the public GDELT split (500 entities, ~7 500 train facts per snapshot, in-degrees in the
         # hundreds, ~20 % duplicate facts): room for seq_len = 15 windows (BASELINE config 5)
