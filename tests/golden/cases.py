@@ -108,3 +108,15 @@ RANK_CASES = [
     dict(name="rank_sargcn_tiny_empty_first", base="sargcn_tiny_d128_last", empty_first=True),
     dict(name="rank_grrgcn_icews_empty_first", base="grrgcn_icews_d128_L8", empty_first=True),
 ]
+
+# Training-loss pins the oracle alone is held to for now (the GPU suite reaches these configurations through the oracle:
+# tests/test_gpu_parity.py::test_autograd_fallback_covers_every_recurrent_configuration).
+CPU_TRAIN_CASES = [
+    dict(name="train_grrgcn_tiny_full", base="grrgcn_tiny_d128_full", seed=41, random_dropout=True),
+    dict(name="train_rrgcn_tiny_full", base="rrgcn_tiny_d128_full", seed=42, random_dropout=True),
+    dict(name="train_bigrrgcn_tiny_full", base="bigrrgcn_tiny_d128_full", seed=43, random_dropout=True),
+    dict(name="train_birrgcn_tiny_full", base="birrgcn_tiny_d128_full", seed=44, random_dropout=False),
+    dict(name="train_grrgcn_tiny_type1", base="grrgcn_tiny_d32_nb8_type1", seed=45, random_dropout=True),
+    dict(name="train_grrgcn_tiny_lambda", base="grrgcn_tiny_d128_lambda", seed=46, random_dropout=True),
+    dict(name="train_bigrrgcn_tiny_nb100", base="bigrrgcn_tiny_d200_nb100", seed=47, random_dropout=False),
+]

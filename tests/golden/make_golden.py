@@ -20,7 +20,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from tests.golden.cases import CASES, CPU_CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES, dataset_path  # noqa: E402
+from tests.golden.cases import (CASES, CPU_CASES, CPU_TRAIN_CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES,  # noqa: E402
+                                dataset_path)
 from oracle.temp_oracle import fill_values  # noqa: E402
 
 
@@ -201,7 +202,7 @@ def main():
     only_rank = "--rank-only" in sys.argv
     if "--only" in sys.argv:                       # --only name1,name2: just these cases (of any kind)
         names = set(sys.argv[sys.argv.index("--only") + 1].split(","))
-        for fn, cases in ((run_rank_case, RANK_CASES), (run_case, CASES + CPU_CASES), (run_train_case, TRAIN_CASES),
+        for fn, cases in ((run_rank_case, RANK_CASES), (run_case, CASES + CPU_CASES), (run_train_case, TRAIN_CASES + CPU_TRAIN_CASES),
                           (run_sampler_case, SAMPLER_CASES)):
             for case in cases:
                 if case["name"] in names:
@@ -222,7 +223,7 @@ def main():
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **res)
         print("%-40s rows=%d  %.1f KB" % (case["name"], res["per_graph"].shape[0], os.path.getsize(path) / 1024))
-    for case in TRAIN_CASES:
+    for case in TRAIN_CASES + CPU_TRAIN_CASES:
         res = run_train_case(case)
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **res)

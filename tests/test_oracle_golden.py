@@ -77,8 +77,10 @@ def test_hand_computed_micro_graph():
     assert torch.allclose(agg[2], want2, rtol=1e-6)
 
 
-@pytest.mark.parametrize("tc", __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES,
-                         ids=lambda c: c["name"])
+_TC = __import__("tests.golden.cases", fromlist=["TRAIN_CASES"])
+
+
+@pytest.mark.parametrize("tc", _TC.TRAIN_CASES + _TC.CPU_TRAIN_CASES, ids=lambda c: c["name"])
 def test_training_forward_loss_matches_reference(tc):
     """Training-mode forward (edge sub-sampling of the window, negative sampling, tail + head cross-entropy) against
     the loss of the unmodified reference under the same global seeds (dropout p = 0)."""
