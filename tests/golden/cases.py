@@ -52,16 +52,14 @@ CASES = [
     #     (t in {0, 3, 7, 200, 364})
     _c("grrgcn_icews14_real_L8", "GRRGCN", dataset="icews14", L=8, t_list=(364, 200, 7, 3, 0)),
     _c("bigrrgcn_icews14_real_L8", "BiGRRGCN", dataset="icews14", L=8, t_list=(364, 200, 7, 3, 0)),
-]
-
-# Oracle-only pins (tests/test_oracle_golden.py): reference outputs the CPU restatement is held to but that the GPU suite
-# does not iterate over yet.
-CPU_CASES = [
     # BASELINE config 5 on real data: GDELT snapshots (in-degrees in the hundreds, duplicate facts), seq_len 15, batch 2
     _c("grrgcn_gdelt_real_L15", "GRRGCN", dataset="gdelt_head", L=15, t_list=(16, 15)),
     # BASELINE config 3 as the reference ships it (n_bases = 100 => D = 200, 2 x 2 blocks) on real ICEWS05-15 snapshots
     _c("bigrrgcn_icews0515_real_nb100", "BiGRRGCN", dataset="icews0515_head", D=200, n_bases=100, L=8, t_list=(8, 7, 3)),
 ]
+
+# (round 1 kept the two real-data cases above as oracle-only pins; both suites iterate over them now)
+CPU_CASES = []
 
 SAMPLER_CASES = [
     dict(name="sampler_tiny_seed123", dataset="tiny", times=[0, 4, 7], seed=123, negative_rate=5, num_pos_facts=3000),
@@ -86,6 +84,11 @@ TRAIN_CASES = [
     dict(name="train_sargcn_tiny_full_random_dropout", base="sargcn_tiny_d128_full", seed=33, random_dropout=True),
     dict(name="train_bisargcn_tiny_random_dropout", base="bisargcn_tiny_d128_last", seed=34, random_dropout=True),
     dict(name="train_bisargcn_icews", base="bisargcn_icews_d128_L8", seed=35, random_dropout=False, negative_rate=20),
+    # BASELINE configs 5 and 3 on real snapshots (GDELT seq_len 15; ICEWS05-15 at D = 200 / n_bases = 100)
+    dict(name="train_grrgcn_gdelt_real", base="grrgcn_gdelt_real_L15", seed=51, random_dropout=True, negative_rate=20,
+         num_pos_facts=500),
+    dict(name="train_bigrrgcn_icews0515_real_nb100", base="bigrrgcn_icews0515_real_nb100", seed=52, random_dropout=False,
+         negative_rate=20),
 ]
 
 # evaluate(t_list, val=True) of the unmodified reference -> filtered ranks (subject side then object side per graph) and the
@@ -107,6 +110,8 @@ RANK_CASES = [
     dict(name="rank_bigrrgcn_tiny_empty_first", base="bigrrgcn_tiny_d128_last", empty_first=True),
     dict(name="rank_sargcn_tiny_empty_first", base="sargcn_tiny_d128_last", empty_first=True),
     dict(name="rank_grrgcn_icews_empty_first", base="grrgcn_icews_d128_L8", empty_first=True),
+    dict(name="rank_grrgcn_gdelt_real", base="grrgcn_gdelt_real_L15"),
+    dict(name="rank_bigrrgcn_icews0515_real_nb100", base="bigrrgcn_icews0515_real_nb100"),
 ]
 
 # Training-loss pins the oracle alone is held to for now (the GPU suite reaches these configurations through the oracle:

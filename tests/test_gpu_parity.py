@@ -9,14 +9,37 @@ from tests.helpers import load_golden, oracle_model, product_model, rel_err
 
 pytestmark = pytest.mark.gpu
 
-RTOL = 1e-4
+RTOL = 1e-4          # the north-star tolerance (BASELINE.json): element-wise relative, fp32
+# Asserted at the levels MEASURED on B200 over all golden cases (gpurun_out/parity_stats.jsonl, round 2): max |err| / max |want|
+# <= 4.2e-6 (tcgen05 3xTF32 path; 5.5e-7 on the fp32 SIMT path; the CPU oracle itself sits at <= 2e-6 against the reference),
+# error on entries below 1e-3 * max <= 1.9e-6 * max (summation-order noise: an element-wise RELATIVE bound cannot hold there).
+TOL_SCALE = 1e-5     # max |err| / max |want|
+ATOL_SCALE = 4e-6    # BASELINE.md section 3 parity gate: allclose(rtol = 1e-4, atol = 4e-6 * max |want|)
+BIG = 0.1            # entries above BIG * max |want| are also held to the element-wise relative 1e-4 of the north star
 
 
-def _close(got, want):
+def _close(got, want, what=""):
+    """The parity bar: (1) max abs error relative to the largest reference value below TOL_SCALE, (2) the BASELINE.md gate
+    allclose(rtol 1e-4, atol 4e-6 * scale), (3) element-wise relative error below 1e-4 on every entry above 0.1 * scale.
+    Every comparison appends its measured levels to gpurun_out/parity_stats.jsonl (the evidence the bounds are set from)."""
+    import json, os
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
     scale = max(np.abs(want).max(), 1e-30)
-    assert np.abs(got - want).max() / scale < RTOL, "max rel-to-scale err %.3e" % (np.abs(got - want).max() / scale)
-    assert np.allclose(got, want, rtol=RTOL, atol=1e-5 * scale)
+    err = np.abs(got - want)
+    big = np.abs(want) > BIG * scale
+    rel_big = float((err[big] / np.abs(want[big])).max()) if big.any() else 0.0
+    stats = {"what": what or os.environ.get("PYTEST_CURRENT_TEST", ""), "n": int(want.size), "max_err_over_scale": float(err.max() / scale),
+             "max_rel_above_0.1_scale": rel_big, "max_err_small_over_scale": float(err[~big].max() / scale) if (~big).any() else 0.0}
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_stats.jsonl", "a") as f:
+            f.write(json.dumps(stats) + "\n")
+    except OSError:
+        pass
+    assert err.max() / scale < TOL_SCALE, "max rel-to-scale err %.3e" % (err.max() / scale)
+    assert np.allclose(got, want, rtol=RTOL, atol=ATOL_SCALE * scale), stats
+    assert rel_big < RTOL, stats
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
@@ -259,9 +282,10 @@ def test_fused_scorer_backward_matches_torch_autograd(fn, corrupt_tail, D):
         assert scale > 0 and float((a - b).abs().max()) / scale < RTOL, (name, float((a - b).abs().max()) / scale)
 
 
-def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None):
+def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None, overrides=None):
     from tests.helpers import CASE_BY_NAME
     case = dict(CASE_BY_NAME[base])
+    case.update(overrides or {})
     oracle = oracle_model(case)
     for v in oracle.p.values():
         v.requires_grad_(True)
@@ -304,7 +328,8 @@ def test_autograd_fallback_gradients_match_oracle(tc):
     """loss.backward() through the fallback gives the gradients of the (reference-pinned) oracle's training loss:
     train mode, sub-sampled window, dropout p = 0, same global seeds; the loss also matches the committed golden value.
     Uni- and bidirectional cases."""
-    _autograd_against_oracle(tc["base"], tc["seed"], tc["random_dropout"], load_golden(tc["name"])["loss"])
+    _autograd_against_oracle(tc["base"], tc["seed"], tc["random_dropout"], load_golden(tc["name"])["loss"],
+                             {k: v for k, v in tc.items() if k in ("negative_rate", "num_pos_facts")})
 
 
 @pytest.mark.parametrize("base", ["grrgcn_tiny_d128_full", "rrgcn_tiny_d128_full", "bigrrgcn_tiny_d128_full",
@@ -444,8 +469,9 @@ def test_evaluate_matches_the_reference_ranks(rc):
     want = torch.from_numpy(gold["ranks"]).cuda()
     assert ranks.dtype == torch.long and ranks.shape == want.shape
     assert abs(loss - float(gold["loss"])) <= RTOL * abs(float(gold["loss"]))
+    # measured on B200 (profiles/r1_ranking.json): 402 / 402 ranks equal; the bound leaves room for an fp32 near-tie only
     same = (ranks == want).float().mean().item()
-    assert same >= 0.95 and int((ranks - want).abs().max()) <= 2, (same, (ranks - want).abs().max().item())
+    assert same >= 0.995 and int((ranks - want).abs().max()) <= 2, (same, (ranks - want).abs().max().item())
     # the reference-style entry (evaluate_embed -> calc_metrics) walks the same graphs with the same lag
     if model.family == "recurrent" and not model.bidirectional:
         per_graph, graphs, time_list, hist, start = model.evaluate_embed(torch.tensor(case["t_list"]), val=True)
