@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 15
+#define TEMP_ABI_VERSION 16
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -149,9 +149,10 @@ typedef struct {
  *            couples a packed row only with the row of the same entity in the same batch item at the previous
  *            step (DynamicRGCN.py:35-54), so a batch item cut into entity-id ranges gives independent
  *            chains: entry (p, steps[s].part_col) = the packed-row range [lo, hi) of partition p at step s,
- *            at most 96 rows (lo == hi: nothing).  The tcgen05 path (d == 128) gives every partition to
- *            one 4-CTA cluster and separates steps by a cluster barrier; without the table (or d != 128)
- *            steps are separated by a grid-wide barrier (cooperative launch).
+ *            at most part_rows rows (lo == hi: nothing).  The tcgen05 path (d == 128) gives every partition to
+ *            one 4-CTA cluster (to one of its four pipelines when part_rows <= 48) and separates the steps of a
+ *            partition by cluster-scope barriers; without the table (or d != 128) steps are separated by a
+ *            grid-wide barrier (cooperative launch).
  *   barrier: 8 bytes of device memory for the grid-wide barrier, zero before the first use; the kernel
  *            leaves it zeroed.  Launches sharing one barrier word must not run concurrently.        */
 typedef struct {
@@ -169,7 +170,10 @@ typedef struct {
   int32_t push_world;
   float* const* push_bufs;
   int64_t push_offset;
-  int32_t push_row0, reserved;
+  int32_t push_row0;
+  int32_t part_rows;         /* upper bound of the rows of one partition step in `parts` (0: the legacy bound, 96).  Tables cut
+                                at <= 48 rows whose steps all use ONE recurrent cell run on gru_scan_tm_kernel (W_hh in
+                                tensor memory, four partition pipelines per CTA), the others on gru_scan_tc_kernel            */
   float* push_multicast;     /* nullable: NVLS multicast address of the same symmetric buffer -- one multimem.st per
                                 value instead of one store per peer (the switch replicates it to every GPU)           */
   TempGruArgs steps[TEMP_MAX_SCAN_STEPS];

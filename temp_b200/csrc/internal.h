@@ -19,6 +19,9 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st);
 int tc_gather_grid(const TempRgcnLayerArgs* a);
 bool tc_scan_supported(const TempGruScanArgs* a);
 int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
+// gru_scan_tm_kernel (tc_scan2.cu): one recurrent cell, partitions of <= 48 rows per step; tc_launch_scan dispatches to it
+bool tc_scan2_supported(const TempGruScanArgs* a);
+int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st);
 int tc_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st);
 int tc_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st);
 

@@ -24,6 +24,9 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// high word of every K-major SWIZZLE_128B UMMA descriptor of this library (SBO 1024 B, version 1, layout type 2)
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -189,6 +192,74 @@ __host__ __device__ __forceinline__ void split_tf32(float a, float& hi, float& l
   lo = a - hi;
 }
 
+// ---- TMEM-resident A operand ("TS" form): A[m, k] lives on TMEM lane m, one fp32 column per k -----------------------
+// 32 consecutive columns (v[0..31]) of the warp's 32 TMEM lanes (warp-collective)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]),
+        "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]),
+        "r"(u[18]), "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]),
+        "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32: a_tmem = TMEM address of the first of the 8 k-columns of this k-step
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+
+// ---- cluster-scope mbarrier signalling (a CTA arrives on a barrier in a PEER CTA's shared memory) -------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+// named barrier over `count` threads (a multiple of 32) with an OR reduction of a predicate
+__device__ __forceinline__ bool bar_red_or(int name, int count, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "barrier.cta.red.or.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(name), "r"(count), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return r != 0;
+}
+__device__ __forceinline__ void bar_named(int name, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(name), "r"(count) : "memory");
+}
+
 constexpr int kAtomK = 32;                          // fp32 elements of K per 128-byte swizzle atom
 constexpr int kUmmaK = 8;                           // K per tcgen05.mma kind::tf32
 constexpr int kWChunkBytes = 2 * 128 * 128;         // packed weight chunk: 128 features x 32 k, hi image then lo image
@@ -196,7 +267,6 @@ constexpr int kWChunkBytes = 2 * 128 * 128;         // packed weight chunk: 128 
 // The descriptors of one kernel differ only in the 14-bit address field of the low word, so the issuing thread
 // keeps 32-bit low words and pairs them with the constant high word (the MMA issue loop of a single thread is on the
 // critical path of the small-N GEMMs: 64-bit descriptor arithmetic per MMA made it issue-bound).
-constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

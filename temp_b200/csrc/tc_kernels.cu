@@ -947,7 +947,9 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
 }
 
 bool tc_scan_supported(const TempGruScanArgs* a) {
+  if (tc_scan2_supported(a)) return true;
   if (a->n_steps <= 0) return false;
+  if (a->parts != nullptr && a->part_rows > kScanN) return false;
   if (a->parts == nullptr && a->n_steps != 1) return false;  // several steps need the chain partition table
   for (int s = 0; s < a->n_steps; ++s) {
     const TempGruArgs& g = a->steps[s];
@@ -960,6 +962,7 @@ bool tc_scan_supported(const TempGruScanArgs* a) {
 }
 
 int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
+  if (tc_scan2_supported(a)) return tc_launch_scan2(a, st);
   static bool configured = false;
   if (int rc = ensure_smem_once(gru_scan_tc_kernel, kScanSmem, "gru_scan_tc_kernel", configured)) return rc;
   int n_parts = a->n_parts;

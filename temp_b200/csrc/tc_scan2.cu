@@ -1,0 +1,530 @@
+// temp_b200 -- gru_scan_tm_kernel: the chain-partitioned GRU scan with W_hh resident in TENSOR MEMORY and four
+// independent partition pipelines per CTA (round 2; replaces gru_scan_tc_kernel for scans that use ONE recurrent cell).
+//
+// What the recurrence is (reference models/RRGCN.py:77-89, models/DynamicRGCN.py:156-174): per window step,
+//     h0 = decay(state[prev_row[r]]);  gh = h0 . W_hh^T + b_hh;  gates with the precomputed gi;  state[r] = h' (+ te)
+// where prev_row links a packed row only to the row of the same entity in the same batch item one step earlier, so the
+// planner's chain partitions (entity-id ranges, <= 48 rows per step) are independent dependency chains.
+//
+// Why this shape (round-1 kernel: one <= 96-row tile in flight per 4-CTA cluster, W_hh as a 128 KB shared-memory image,
+// 8.7 % / 10 % of the HBM roofline, the step chain = cluster barrier -> L2 gather -> MMA -> gates -> release fence):
+//   * a step of ONE chain is latency (barrier, L2 round trip, MMA commit, fence), not work -- throughput comes from
+//     running several chains at once.  A CTA therefore runs kPipes = 4 pipelines, one warp group of 4 warps each; a
+//     pipeline owns its operand tile, its TMEM accumulator, its barriers, issues its own tcgen05.mma batch from one of
+//     its threads and never synchronises with the other pipelines (named barriers + mbarriers, no __syncthreads in the
+//     loop).  While one pipeline waits for its peers' state columns, the others gather / multiply / apply gates.
+//   * W_hh lives in TMEM as the A operand (tcgen05.mma "TS" form): 128 lanes (r|z|n rows of this CTA's 32 hidden
+//     columns, 32 pad rows) x 128 k columns, hi and lo tf32 parts = 256 of the 512 columns.  An MMA then reads only its
+//     N x 8 activation slice from shared memory (1.5 KB at N = 48 instead of 4 KB + 1.5 KB), which is what makes
+//     small-N batches run at the tensor-pipe floor, and the 128 KB of shared memory the weight image used to take now
+//     holds the four operand tiles.
+//   * the cluster-wide step barrier (one hardware barrier per cluster, all 16 warps) is replaced by per-pipeline
+//     mbarriers signalled across the cluster: after its state stores a pipeline's elected thread issues one
+//     cluster-scope release fence and arrives on the pipeline's barrier in all four CTAs (mapa + mbarrier.arrive
+//     .release.cluster.shared::cluster); the consumers wait with acquire.cluster.  Two barriers per pipeline alternate
+//     so that a fast CTA's arrival for step t + 1 can never be counted into step t.
+//   * gate exchange without a second barrier: the accumulator holds gate g on TMEM lane quadrant g (rows = packed rows
+//     on columns); the three gate warps park their quadrant in the k-atoms of the dead operand image OTHER than this
+//     CTA's own (k-atom cb holds the h0 values of this CTA's hidden columns, which the z-gate still needs).
+//
+// Layout conventions are those of tc_common.cuh: D^T[feature, row] ("features on TMEM lanes"), B = activations K-major
+// SWIZZLE_128B in shared memory, 3xTF32 operand split.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "internal.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kD = 128;
+constexpr int kCluster = 4;                       // CTAs per cluster = blocks of 32 hidden columns
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;             // 512 -> 128 registers per thread
+constexpr int kRows = 48;                         // max packed rows per partition step = UMMA N
+constexpr int kAtomBytes = kRows * 128;           // one k-atom block (32 k) of an operand image
+constexpr int kImage = 4 * kAtomBytes;            // hi (or lo) image of a tile: 24 KB
+constexpr int kPipeSmem = 2 * kImage;
+constexpr int kMaxPipes = 4;
+constexpr int kSmem = kMaxPipes * kPipeSmem + 1024;
+constexpr int kTmemCols = 512;
+constexpr int kColWLo = 128;                      // W_hh hi parts at columns [0, 128), lo parts at [128, 256)
+constexpr int kColD = 256, kColDStride = 64;      // accumulator of pipeline p: columns [256 + 64 p, +48)
+static_assert(kAtomBytes % 1024 == 0, "k-atom blocks must keep the 1024-byte swizzle period");
+static_assert(kColD + (kMaxPipes - 1) * kColDStride + kRows <= kTmemCols, "TMEM budget");
+
+struct Bars {
+  uint64_t mma_done[kMaxPipes];
+  uint64_t step[kMaxPipes][2];
+  uint32_t tmem_base;
+  float* push[TEMP_MAX_PUSH_PEERS];
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
+}
+__device__ __forceinline__ float decay_factor(float dt, const float* wb, float inv_temperature) {
+  if (wb != nullptr) return expf(-fmaxf(fmaf(__ldg(wb), dt, __ldg(wb + 1)), 0.f));
+  return expf(-dt * inv_temperature);
+}
+// ex2.approx / rcp.approx based gate math, absolute error ~1e-7 (as gru_scan_tc_kernel)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// Development-only phase timeline (tools/probe_timeline2.py builds a separate library with -DTEMP_TIMELINE): lane 0 of
+// every warp stores clock64() per phase slot; slot 63 holds %globaltimer at kernel entry.
+#ifdef TEMP_TIMELINE
+__device__ unsigned long long* g_timeline2 = nullptr;
+constexpr int kTlWarps = 16, kTlSlots = 64;
+__device__ __forceinline__ void tl_mark(int slot) {
+  if (g_timeline2 != nullptr && (threadIdx.x & 31) == 0 && slot < 63)
+    g_timeline2[(static_cast<size_t>(blockIdx.x) * kTlWarps + (threadIdx.x >> 5)) * kTlSlots + slot] = clock64();
+}
+__device__ __forceinline__ void tl_start() {
+  if (g_timeline2 != nullptr && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_timeline2[(static_cast<size_t>(blockIdx.x) * kTlWarps + (threadIdx.x >> 5)) * kTlSlots + 63] = t;
+  }
+  tl_mark(0);
+}
+#define TL(slot) tl_mark(slot)
+#define TLS(k) do { if (t >= 2 && t < 7) tl_mark(3 + 12 * (t - 2) + (k)); } while (0)
+#define TL_START() tl_start()
+#else
+#define TL(slot)
+#define TLS(k)
+#define TL_START()
+#endif
+
+// kPipes in {1, 2, 4}: independent partition pipelines per CTA, 16 / kPipes warps each.  The launcher takes the smallest
+// count that gives every chain partition its own pipeline (latency: more warps per tile), 4 when there are more partitions
+// than pipelines anyway (throughput: more chains in flight).
+template <int kPipes>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
+    gru_scan_tm_kernel(const TempGruScanArgs P, const int n_parts, const void* __restrict__ w_packed) {
+  constexpr int kPW = kWarps / kPipes;              // warps per pipeline
+  constexpr int kPT = kPW * 32;
+  constexpr int kU = (kRows + kPW - 1) / kPW;       // row slots per thread: tile row gw + kPW * u
+  constexpr int kH = kPW / 4;                       // warps per TMEM lane quadrant inside a pipeline
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  __shared__ Bars S;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the broadcast makes the warp index (and everything derived from it: operand addresses, descriptors) provably
+  // warp-uniform, so the MMA issue below runs on uniform registers instead of a per-operand R2UR election loop
+  const int warp = __shfl_sync(kFull, tid >> 5, 0);
+  const int pipe = warp / kPW, gw = warp % kPW;
+  const int quad = warp & 3;                                        // TMEM lane quadrant this warp can access
+  const int cb = blockIdx.x & (kCluster - 1), jb = 32 * cb;         // == %cluster_ctarank for a 1-D grid
+  const int cid = blockIdx.x / kCluster, n_clusters = gridDim.x / kCluster;
+  const int bar_id = 1 + pipe;                                      // named barrier of this pipeline
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxPipes; ++i) {
+      mbar_init(&S.mma_done[i], 1);
+      mbar_init(&S.step[i][0], kCluster);
+      mbar_init(&S.step[i][1], kCluster);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&S.tmem_base, kTmemCols);
+  if (P.push_bufs != nullptr && tid < P.push_world) S.push[tid] = P.push_bufs[tid] + P.push_offset;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = __shfl_sync(kFull, S.tmem_base, 0);
+  pdl_launch_dependents();
+  TL_START();
+  cluster_sync_all();   // every CTA's barriers exist before a peer may arrive on them
+  TL(1);
+
+  // ---- this CTA's W_hh slice -> tensor memory (parameters: not produced by the predecessor kernels) -----------------
+  // warp (quad, kq = warp >> 2): TMEM lanes 32 quad .. + 31 (feature rows m), k columns 32 kq .. + 31, read from the packed
+  // image of temp_pack_gru_weights (chunk (cb, kq): hi image, lo image 16 KB later, SWIZZLE_128B rows)
+  if (w_packed != nullptr) {
+    const int m = 32 * quad + lane, kq = warp >> 2;
+    const uint8_t* chunk = static_cast<const uint8_t*>(w_packed) + static_cast<size_t>(cb * 4 + kq) * kWChunkBytes;
+#pragma unroll
+    for (int img = 0; img < 2; ++img) {
+      const uint8_t* rowp = chunk + img * (128 * 128) + (m >> 3) * 1024 + (m & 7) * 128;
+      float v[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(rowp + ((c ^ (m & 7)) << 4)));
+        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+      }
+      tmem_st32(tbase + (static_cast<uint32_t>(32 * quad) << 16) + img * kColWLo + kq * 32, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- this pipeline's tile steps: its partitions vc, vc + NV, ... ; all steps of a partition, then the next --------
+  const int vc = pipe * n_clusters + cid, NV = kPipes * n_clusters;
+  const uint32_t s_bhi = smem_u32(smem + pipe * kPipeSmem), s_blo = s_bhi + kImage;
+  const uint32_t dcol = tbase + kColD + pipe * kColDStride;
+  const uint32_t ex_base = s_bhi;   // gate g is parked in k-atom (cb + 1 + g) & 3 of the (dead) hi image, plain [row][32] rows
+
+  // lane l < n_steps keeps the packed-row range of a partition at step l: one load per partition, fetched one partition
+  // ahead, so that walking the tile steps never waits for the table
+  auto load_ranges = [&](int pt) -> int2 {
+    int2 r = make_int2(0, 0);
+    if (pt < n_parts && lane < P.n_steps) {
+      if (P.parts != nullptr) {
+        r = __ldg(reinterpret_cast<const int2*>(P.parts) + static_cast<size_t>(pt) * P.part_stride + P.steps[lane].part_col);
+      } else {   // single step without a partition table: plain row tiles
+        r.x = P.steps[0].row0 + pt * kRows;
+        r.y = min(r.x + kRows, P.steps[0].row1);
+      }
+    }
+    return r;
+  };
+  auto first_step = [&](int2 r, int from) -> int {   // first step >= from at which the partition has rows, -1: none
+    unsigned m = __ballot_sync(kFull, r.y > r.x);
+    m = from < 32 ? ((m >> from) << from) : 0u;
+    return m != 0u ? __ffs(m) - 1 : -1;
+  };
+  // next tile step after (pt, st): further steps of the partition, then the pipeline's next partitions
+  auto advance = [&](int& pt, int& st, int2& r, int2& r_next) {
+    st = first_step(r, st + 1);
+    while (st < 0 && pt < n_parts) {
+      pt += NV;
+      r = r_next;
+      r_next = load_ranges(pt + NV);
+      st = first_step(r, 0);
+    }
+  };
+  // lanes 0 .. kU-1: previous-state row (-1: none) and time gap of this warp's u-th tile row;
+  // lanes 16, 17: time-embedding row of the first / last row of the tile
+  auto load_pre = [&](const TempGruArgs& q, int g0, int g1, int& pv, float& dv) {
+    pv = -1;
+    dv = 0.f;
+    if (lane < kU) {
+      const int r = g0 + gw + kPW * lane;
+      if (r < g1 && q.prev_row != nullptr) {
+        pv = __ldg(q.prev_row + r);
+        if (q.dt != nullptr) dv = __ldg(q.dt + r);
+      }
+    } else if (lane == 16 || lane == 17) {
+      pv = q.row_time_scalar;
+      if (q.time_embed != nullptr && q.row_time != nullptr) pv = __ldg(q.row_time + (lane == 16 ? g0 : g1 - 1));
+    }
+  };
+
+  int part = vc, s = -1;
+  int2 rgs = load_ranges(part), rgs_next = load_ranges(part + NV);
+  advance(part, s, rgs, rgs_next);
+  bool have = part < n_parts;
+  int prv = -1;
+  float dtv = 0.f;
+  if (have) load_pre(P.steps[s], __shfl_sync(kFull, rgs.x, s), __shfl_sync(kFull, rgs.y, s), prv, dtv);
+  TL(2);
+  pdl_wait();   // gi (and, for a single step, the previous state) come from the predecessor kernels
+
+  uint32_t t = 0;          // tile steps this pipeline has published
+  uint32_t mma_par = 0;
+#pragma unroll 1
+  while (have) {
+    const TempGruArgs& p = P.steps[s];
+    const int rb = __shfl_sync(kFull, rgs.x, s), r1 = __shfl_sync(kFull, rgs.y, s);
+    const int nmma = (r1 - rb + 15) & ~15;                 // UMMA N: 16, 32 or 48
+    int n_part = part, n_s = s;
+    int2 n_rgs = rgs, n_rgs_next = rgs_next;
+    advance(n_part, n_s, n_rgs, n_rgs_next);
+    const bool more = n_part < n_parts;
+
+    // the peers' state columns of this pipeline's previous tile step are visible after this wait; it also means every
+    // CTA is past its reads of that step (a pipeline's tile steps are totally ordered across the cluster)
+    TLS(0);
+    if (t > 0) mbar_wait_cluster(&S.step[pipe][(t - 1) & 1], ((t - 1) >> 1) & 1);
+    TLS(1);
+
+    // ---- previous-state rows -> shared-memory operand (decay, hi / lo split) ------------------------------------
+    {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pr = __shfl_sync(kFull, prv, u);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pr >= 0) v[u] = __ldcg(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
+      }
+      const float dec = p.dt != nullptr ? decay_factor(dtv, p.decay_wb, p.inv_temperature) : 1.f;
+      TLS(2);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = gw + kPW * u;
+        const float dv = __shfl_sync(kFull, dec, u);
+        if (i >= nmma) continue;   // warp-uniform: beyond the rows this step's MMA reads
+        float4 hi, lo;
+        split_tf32(v[u].x * dv, hi.x, lo.x);
+        split_tf32(v[u].y * dv, hi.y, lo.y);
+        split_tf32(v[u].z * dv, hi.z, lo.z);
+        split_tf32(v[u].w * dv, hi.w, lo.w);
+        const uint32_t off = static_cast<uint32_t>(lane >> 3) * kAtomBytes + (i >> 3) * 1024u + (i & 7) * 128u +
+                             (((lane & 7) ^ (i & 7)) << 4);
+        sts_f32x4(s_bhi + off, hi);
+        sts_f32x4(s_blo + off, lo);
+      }
+      fence_proxy_async();
+    }
+    TLS(3);
+    const bool any_prev = bar_red_or(bar_id, kPT, __any_sync(kFull, lane < kU && prv >= 0));
+    TLS(4);
+
+    // ---- gh^T = W_hh . h0^T : 16 k-steps x 3 split passes, A from tensor memory -----------------------------------
+    if (any_prev && gw == 0) {   // warp-uniform
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_tf32(128, nmma);
+#pragma unroll
+        for (int ka = 0; ka < 4; ++ka) {
+          const uint32_t bh0 = umma_desc_lo(s_bhi + ka * kAtomBytes), bl0 = umma_desc_lo(s_blo + ka * kAtomBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = tbase + ka * 32 + ks * 8, a_lo = a_hi + kColWLo;
+            const uint32_t bh = bh0 + 2 * ks, bl = bl0 + 2 * ks;          // +32 bytes per k-step inside the atom
+            umma_tf32_ts(dcol, a_lo, bh, idesc, (ka | ks) != 0 ? 1u : 0u);  // small terms first
+            umma_tf32_ts(dcol, a_hi, bl, idesc, 1u);
+            umma_tf32_ts(dcol, a_hi, bh, idesc, 1u);
+          }
+        }
+        umma_commit(&S.mma_done[pipe]);
+      }
+      __syncwarp();
+    }
+    TLS(5);
+
+    // ---- while the MMA runs: this thread's h0 values, input gates, biases; the NEXT tile step's indices ------------
+    const int j = jb + lane;
+    float h0[kU], gi_r[kU], gi_z[kU], gi_n[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = gw + kPW * u;
+      const int r = rb + i;
+      h0[u] = gi_r[u] = gi_z[u] = gi_n[u] = 0.f;
+      if (r < r1) {
+        if (any_prev) {
+          const uint32_t off = static_cast<uint32_t>(cb) * kAtomBytes + sw128_off(i, lane);
+          h0[u] = lds_f32(s_bhi + off) + lds_f32(s_blo + off);
+        }
+        const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
+        gi_r[u] = __ldg(gi);
+        gi_z[u] = __ldg(gi + kD);
+        gi_n[u] = __ldg(gi + 2 * kD);
+      }
+    }
+    const float br = __ldg(p.b_hh + j), bz = __ldg(p.b_hh + kD + j), bn = __ldg(p.b_hh + 2 * kD + j);
+    // rows of one partition step belong to one snapshot instance (one time-embedding row); plain tiles may mix
+    float te_uni = 0.f;
+    bool te_rows = false;
+    if (p.time_embed != nullptr) {
+      const int trow0 = __shfl_sync(kFull, prv, 16), trow1 = __shfl_sync(kFull, prv, 17);
+      te_rows = trow0 != trow1;
+      if (!te_rows) te_uni = __ldg(p.time_embed + static_cast<size_t>(trow0) * kD + j);
+    }
+    int n_prv = -1;
+    float n_dtv = 0.f;
+    if (more) load_pre(P.steps[n_s], __shfl_sync(kFull, n_rgs.x, n_s), __shfl_sync(kFull, n_rgs.y, n_s), n_prv, n_dtv);
+
+    // ---- accumulator (gate = lane quadrant, rows on columns) -> exchange rows, one barrier --------------------------
+    TLS(6);
+    if (any_prev) {
+      mbar_wait(&S.mma_done[pipe], mma_par);
+      mma_par ^= 1;
+      tc_fence_after();
+      TLS(7);
+      if (quad < 3) {
+        const int h = gw >> 2;   // the kH warps of a quadrant take the 16-column chunks round robin
+        const uint32_t ta = dcol + (static_cast<uint32_t>(32 * quad) << 16);
+        const uint32_t exw = ex_base + ((cb + 1 + quad) & 3) * kAtomBytes + lane * 4;
+#pragma unroll
+        for (int c = 0; c < kRows / 16; ++c) {
+          if (c % kH == h && 16 * c < nmma) {   // warp-uniform
+            float v[16];
+            tmem_ld16(ta + 16 * c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sts_f32(exw + (16 * c + i) * 128, v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      bar_named(bar_id, kPT);
+    }
+    TLS(8);
+
+    // ---- gates, state store (+ fused all-gather peer stores) -------------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = gw + kPW * u;
+      const int r = rb + i;
+      if (r < r1) {   // warp-uniform
+        float hr = br, hz = bz, hn = bn;
+        if (any_prev) {
+          const uint32_t ea = ex_base + i * 128 + lane * 4;
+          hr += lds_f32(ea + ((cb + 1) & 3) * kAtomBytes);
+          hz += lds_f32(ea + ((cb + 2) & 3) * kAtomBytes);
+          hn += lds_f32(ea + ((cb + 3) & 3) * kAtomBytes);
+        }
+        // torch.nn.GRU, gate order r, z, n
+        const float rg_ = fast_sigmoid(gi_r[u] + hr);
+        const float zg = fast_sigmoid(gi_z[u] + hz);
+        const float ng = fast_tanh(gi_n[u] + rg_ * hn);
+        float hy = (1.f - zg) * ng + zg * h0[u];
+        hy += te_rows ? __ldg(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j) : te_uni;
+        float* o = p.out + static_cast<size_t>(r) * kD + j;
+        if (p.accumulate) hy += __ldcg(o);
+        *o = hy;
+        if (p.push != 0 && P.push_bufs != nullptr) {   // NVLink stores into every peer's slab (TempGruScanArgs.push_*)
+          const size_t po = static_cast<size_t>(r - P.push_row0) * kD + j;
+          if (P.push_multicast != nullptr) {
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.push_multicast + P.push_offset + po), "f"(hy)
+                         : "memory");
+          } else {
+            for (int k = 0; k < P.push_world; ++k) S.push[k][po] = hy;
+          }
+        }
+      }
+    }
+
+    // ---- publish: the pipeline's stores -> ONE cluster-scope release fence -> relaxed arrives on the pipeline's barrier
+    // in all four CTAs (an arrive.release per peer would repeat the full memory barrier four times)
+    TLS(9);
+    bar_named(bar_id, kPT);   // also: every exchange / operand read of this step is done
+    TLS(10);
+    if (more && gw == 0) {    // (nobody waits for the last tile step of a pipeline)
+      if (elect_one()) {
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        const uint32_t bar = smem_u32(&S.step[pipe][t & 1]);
+#pragma unroll
+        for (int k = 0; k < kCluster; ++k) mbar_arrive_remote_relaxed(mapa_u32(bar, k));
+      }
+      __syncwarp();
+    }
+    TLS(11);
+    ++t;
+    prv = n_prv;
+    dtv = n_dtv;
+    part = n_part;
+    s = n_s;
+    rgs = n_rgs;
+    rgs_next = n_rgs_next;
+    have = more;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
+  if (warp == 0) tmem_dealloc(tbase, kTmemCols);
+}
+
+}  // namespace
+
+#ifdef TEMP_TIMELINE
+extern "C" int temp_debug_timeline2(void* device_buffer) {  // [ctas][16 warps][64 slots] u64, or null to disable
+  unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+  return cudaMemcpyToSymbol(g_timeline2, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
+#endif
+
+namespace temp_internal {
+
+// One recurrent cell (torch GRU equations) for every step that reads a previous state, d == 128, chain partitions of at
+// most 48 rows per step (TempGruScanArgs.part_rows) or a single step of plain row tiles.
+bool tc_scan2_supported(const TempGruScanArgs* a) {
+  static const bool disabled = getenv("TEMP_SCAN_V1") != nullptr;
+  if (disabled || a->n_steps <= 0) return false;
+  if (a->parts == nullptr && a->n_steps != 1) return false;
+  if (a->parts != nullptr && (a->part_rows <= 0 || a->part_rows > kRows)) return false;
+  const void* w = nullptr;
+  for (int s = 0; s < a->n_steps; ++s) {
+    const TempGruArgs& g = a->steps[s];
+    if (g.d != kD || g.cell_type != TEMP_CELL_TORCH_GRU) return false;
+    if (a->parts != nullptr && (g.part_col < 0 || g.part_col >= a->part_stride)) return false;
+    if (g.prev_row != nullptr) {
+      if (g.whh_packed == nullptr) return false;
+      if (w != nullptr && g.whh_packed != w) return false;
+      w = g.whh_packed;
+    }
+  }
+  if (a->push_bufs != nullptr && (a->push_world <= 0 || a->push_world > TEMP_MAX_PUSH_PEERS)) return false;
+  return true;
+}
+
+template <int kPipes>
+int launch_scan2_t(const TempGruScanArgs* a, int n_parts, int clusters, const void* w, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gru_scan_tm_kernel<kPipes>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tm_kernel");
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = st;
+  cfg.gridDim = dim3(kCluster * clusters);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tm_kernel<kPipes>, *a, n_parts, w);
+  if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tm_kernel launch");
+  return TEMP_OK;
+}
+
+int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st) {
+  int n_parts = a->n_parts;
+  if (a->parts == nullptr) n_parts = (a->steps[0].row1 - a->steps[0].row0 + kRows - 1) / kRows;
+  if (n_parts <= 0) return TEMP_OK;
+  const void* w = nullptr;
+  for (int s = 0; s < a->n_steps; ++s)
+    if (a->steps[s].prev_row != nullptr) w = a->steps[s].whh_packed;
+  static int max_clusters = 0;   // co-resident 4-CTA clusters (one CTA per SM)
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.gridDim = dim3(kCluster * 64);
+    cudaFuncSetAttribute(gru_scan_tm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, gru_scan_tm_kernel<4>, &cfg);
+    if (e != cudaSuccess || max_clusters <= 0) {
+      cudaGetLastError();
+      max_clusters = 32;
+    }
+  }
+  static const int force = getenv("TEMP_SCAN_PIPES") != nullptr ? atoi(getenv("TEMP_SCAN_PIPES")) : 0;   // development knob
+  // spread first: as many clusters as there are partitions; then the fewest pipelines per CTA that still give every
+  // partition its own (more warps per tile = a shorter step chain), four when partitions queue anyway
+  const int clusters = n_parts < max_clusters ? n_parts : max_clusters;
+  int pipes = n_parts <= clusters ? 1 : (n_parts <= 2 * clusters ? 2 : 4);
+  if (force == 1 || force == 2 || force == 4) pipes = force;
+  if (pipes == 1) return launch_scan2_t<1>(a, n_parts, clusters, w, st);
+  if (pipes == 2) return launch_scan2_t<2>(a, n_parts, clusters, w, st);
+  return launch_scan2_t<4>(a, n_parts, clusters, w, st);
+}
+
+}  // namespace temp_internal

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -55,7 +55,7 @@ class GruArgs(C.Structure):
 
 class GruScanArgs(C.Structure):
     _fields_ = [("n_steps", _i32), ("n_parts", _i32), ("barrier", _p), ("parts", _p), ("part_stride", _i32),
-                ("push_world", _i32), ("push_bufs", _p), ("push_offset", C.c_int64), ("push_row0", _i32), ("reserved", _i32),
+                ("push_world", _i32), ("push_bufs", _p), ("push_offset", C.c_int64), ("push_row0", _i32), ("part_rows", _i32),
                 ("push_multicast", _p), ("steps", GruArgs * MAX_SCAN_STEPS)]
 
 
@@ -240,7 +240,8 @@ class Program(object):
     def __len__(self):
         return len(self.ops)
 
-    def fuse_gru_scans(self, barrier_ptr: int, parts_ptr: Optional[int] = None, n_parts: int = 0, part_stride: int = 0) -> None:
+    def fuse_gru_scans(self, barrier_ptr: int, parts_ptr: Optional[int] = None, n_parts: int = 0, part_stride: int = 0,
+                       part_rows: int = 0) -> None:
         """Replaces every run of >= 2 consecutive GRU ops by ONE scan launch (chain-partitioned when the plan's
         partition table is given, see TempGruScanArgs)."""
         out, run = [], []
@@ -254,7 +255,7 @@ class Program(object):
                     a = GruScanArgs()
                     a.n_steps, a.barrier = len(chunk), barrier_ptr
                     if parts_ptr is not None:
-                        a.parts, a.n_parts, a.part_stride = parts_ptr, n_parts, part_stride
+                        a.parts, a.n_parts, a.part_stride, a.part_rows = parts_ptr, n_parts, part_stride, part_rows
                     for i, o in enumerate(chunk):
                         a.steps[i] = o.u.gru
                     op = Op()

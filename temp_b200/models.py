@@ -100,12 +100,18 @@ class TKG_Module(nn.Module):
         """Packs the window batch: the native planner of libtemp_b200.so, or its python statement when the graphs are
         transformed on the fly (training-mode edge sub-sampling)."""
         from .planner import plan_window_native
-        kw = dict(bidirectional=self.bidirectional, attention=self.family == "attention")
+        kw = dict(bidirectional=self.bidirectional, attention=self.family == "attention", scan_tile=self.scan_tile())
         if transform is None and self.use_native_planner:
             return plan_window_native(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len, **kw)
         return plan_window(self.graph_dict_train, _as_int_list(t_list), seq_len or self.train_seq_len, transform=transform, **kw)
 
     use_native_planner = True
+
+    def scan_tile(self) -> int:
+        """Row bound of a chain-partition step: 48 for the scans that use ONE recurrent cell (uni-directional GRU families:
+        gru_scan_tm_kernel), 96 for the scans that alternate between the two cells of the Bi models (gru_scan_tc_kernel)."""
+        from .planner import SCAN_TILE, SCAN_TILE_TM
+        return SCAN_TILE_TM if (self.family == "recurrent" and not self.bidirectional) else SCAN_TILE
 
     def train_edge_sampler(self):
         """Training-mode edge sub-sampling of the window (models/DynamicRGCN.py:76-94, 161-171): the final step keeps

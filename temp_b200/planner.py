@@ -66,6 +66,7 @@ class WindowPlan(object):
         self.R = 0
         self.E = 0
         self.n_slots = 0
+        self.scan_tile = 0            # row bound of one chain-partition step in scan_parts (0: no table)
         self.final_times: List[int] = []
         self.final_sizes: List[int] = []
         self.final_snapshots: List[Snapshot] = []
@@ -189,7 +190,7 @@ def _match_prev(cur: Snapshot, prev_inst: Optional[Instance]) -> Optional[np.nda
 
 
 def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len: int, bidirectional: bool = False,
-                attention: bool = False, transform=None) -> WindowPlan:
+                attention: bool = False, transform=None, scan_tile: Optional[int] = None) -> WindowPlan:
     """Plan the forward of (Bi)DynamicRGCN / (Bi)SelfAttentionRGCN for the target timestamps ``t_list``.
 
     Row order: forward history steps 0..L-2, then (Bi) backward history steps 0..L-2, then the final
@@ -273,7 +274,8 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
     plan.last_hist_b = [last_b[B - 1 - i] for i in range(B)] if bidirectional else [None] * B
     pk.finish(plan)
     if not attention:
-        plan.scan_parts = chain_partitions(plan)
+        plan.scan_tile = int(scan_tile or SCAN_TILE)
+        plan.scan_parts = chain_partitions(plan, plan.scan_tile)
     if attention:
         plan.n_slots = (L - 1) * (2 if bidirectional else 1)
         plan.slot_row = np.ascontiguousarray(np.concatenate(slot_rows, axis=0), dtype=np.int32)
@@ -281,7 +283,8 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
     return plan
 
 
-SCAN_TILE = 96   # rows per chain partition and step (UMMA N of the scan kernel, temp_b200/csrc/tc_kernels.cu)
+SCAN_TILE = 96      # rows per chain partition and step of gru_scan_tc_kernel (scans that mix recurrent cells: the Bi models)
+SCAN_TILE_TM = 48   # ... of gru_scan_tm_kernel (one recurrent cell, W_hh in tensor memory; temp_b200/csrc/tc_scan2.cu)
 
 
 def chain_partitions(plan: WindowPlan, tile: int = SCAN_TILE) -> np.ndarray:
@@ -447,7 +450,7 @@ class NativeWindowPlan(WindowPlan):
 
 
 def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len: int, bidirectional: bool = False,
-                       attention: bool = False) -> WindowPlan:
+                       attention: bool = False, scan_tile: Optional[int] = None) -> WindowPlan:
     """``plan_window`` through the native planner of libtemp_b200.so (no ``transform``: the training-mode edge
     sub-sampling builds new snapshots and goes through the python planner)."""
     import ctypes as C
@@ -456,14 +459,15 @@ def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], s
     (views, _keep, times), index = _snapshot_views(graph_dict)
     B = len(t_list)
     targets = (C.c_int32 * B)(*[index[int(t)] for t in t_list])
-    handle = L.temp_plan_window(views, len(times), targets, B, int(seq_len), int(bidirectional), int(attention), SCAN_TILE,
-                                AGG_HEAVY_DEGREE)
+    handle = L.temp_plan_window(views, len(times), targets, B, int(seq_len), int(bidirectional), int(attention),
+                                int(scan_tile or SCAN_TILE), AGG_HEAVY_DEGREE)
     if not handle:
         raise RuntimeError("temp_b200: temp_plan_window rejected its arguments")
     plan = NativeWindowPlan(handle, lib)
     cnt = lib.PlanCounts()
     lib.check(L.temp_plan_counts(handle, C.byref(cnt)), "temp_plan_counts")
     plan.seq_len, plan.batch, plan.bidirectional = int(seq_len), B, bool(bidirectional)
+    plan.scan_tile = int(scan_tile or SCAN_TILE)
     plan.R, plan.E = int(cnt.rows), int(cnt.edges)
     plan._n_parts = int(cnt.n_parts)
     if not bidirectional:
