@@ -48,8 +48,9 @@ constexpr int kThreads = kWarps * 32;             // 512 -> 128 registers per th
 constexpr int kRows = 48;                         // max packed rows per partition step = UMMA N
 constexpr int kAtomBytes = kRows * 128;           // one k-atom block (32 k) of an operand image
 constexpr int kImage = 4 * kAtomBytes;            // hi (or lo) image of a tile: 24 KB
-constexpr int kPipeSmem = 2 * kImage;
-constexpr int kMaxPipes = 4;
+constexpr int kBufBytes = 2 * kImage;             // one operand tile: hi image, lo image
+constexpr int kPipeSmem = 2 * kBufBytes;          // two operand tiles per pipeline (steps alternate)
+constexpr int kMaxPipes = 2;
 constexpr int kSmem = kMaxPipes * kPipeSmem + 1024;
 constexpr int kTmemCols = 512;
 constexpr int kColWLo = 128;                      // W_hh hi parts at columns [0, 128), lo parts at [128, 256)
@@ -59,7 +60,7 @@ static_assert(kColD + (kMaxPipes - 1) * kColDStride + kRows <= kTmemCols, "TMEM 
 
 struct Bars {
   uint64_t mma_done[kMaxPipes];
-  uint64_t step[kMaxPipes][2];
+  uint64_t ready[kMaxPipes][2];   // operand tile b of a pipeline is complete (bytes counted: st.async from the four CTAs)
   uint32_t tmem_base;
   float* push[TEMP_MAX_PUSH_PEERS];
 };
@@ -105,7 +106,7 @@ __device__ __forceinline__ void tl_start() {
   tl_mark(0);
 }
 #define TL(slot) tl_mark(slot)
-#define TLS(k) do { if (t >= 2 && t < 7) tl_mark(3 + 12 * (t - 2) + (k)); } while (0)
+#define TLS(k) do { if (t >= 2 && t < 9) tl_mark(3 + 8 * (t - 2) + (k)); } while (0)   // (first partition of a pipeline)
 #define TL_START() tl_start()
 #else
 #define TL(slot)
@@ -113,16 +114,36 @@ __device__ __forceinline__ void tl_start() {
 #define TL_START()
 #endif
 
-// kPipes in {1, 2, 4}: independent partition pipelines per CTA, 16 / kPipes warps each.  The launcher takes the smallest
-// count that gives every chain partition its own pipeline (latency: more warps per tile), 4 when there are more partitions
-// than pipelines anyway (throughput: more chains in flight).
-template <int kPipes>
+__device__ __forceinline__ void st_async_f32x4(uint32_t cluster_addr, float4 v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(cluster_mbar)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+// kPipes in {1, 2}: independent partition pipelines per CTA, 16 / kPipes warps each (the launcher takes one pipeline while
+// that still gives every chain partition its own, else two).
+// kChained (a chain-partition table is given): the steps of a partition hand the state over through DISTRIBUTED SHARED
+// MEMORY -- each CTA stores its 32 hidden columns of the new state, already split into tf32 hi / lo parts, straight into
+// the next step's operand tile of all four CTAs with st.async (completion counted in bytes on the consumer's mbarrier):
+// no release fence, no L2 round trip, no conversion pass on the step chain.  The operand keeps the PREVIOUS step's row
+// order; a row reads its accumulator column / h0 values through prev_row, and the decay factor -- a per-row scalar -- is
+// applied to the gathered values after the MMA (W . (c h) = c (W . h)).  The global state store only serves the callers.
+// !kChained (one step, plain row tiles, state read from global memory through prev_row): the operand is gathered by the
+// CTA itself; tiles are independent, nothing is exchanged.
+template <int kPipes, bool kChained>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     gru_scan_tm_kernel(const TempGruScanArgs P, const int n_parts, const void* __restrict__ w_packed) {
-  constexpr int kPW = kWarps / kPipes;              // warps per pipeline
+  constexpr int kPW = kWarps / kPipes;              // warps per pipeline (16 or 8)
   constexpr int kPT = kPW * 32;
-  constexpr int kU = (kRows + kPW - 1) / kPW;       // row slots per thread: tile row gw + kPW * u
   constexpr int kH = kPW / 4;                       // warps per TMEM lane quadrant inside a pipeline
+  constexpr int kRP = 4 * kPW;                      // gate phase: rows per pass (a thread = one row x 4 hidden columns)
+  constexpr int kUg = (kRows + kRP - 1) / kRP;      // passes: 1 or 2
+  constexpr int kU = kRows / kPW;                   // gather phase (!kChained): rows per warp, a lane = 4 of 128 columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   __shared__ Bars S;
@@ -136,12 +157,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const int cb = blockIdx.x & (kCluster - 1), jb = 32 * cb;         // == %cluster_ctarank for a 1-D grid
   const int cid = blockIdx.x / kCluster, n_clusters = gridDim.x / kCluster;
   const int bar_id = 1 + pipe;                                      // named barrier of this pipeline
+  const int rsub = lane >> 3, cq = lane & 7;                        // gate phase: row inside the warp's 4, column quad
 
   if (tid == 0) {
     for (int i = 0; i < kMaxPipes; ++i) {
       mbar_init(&S.mma_done[i], 1);
-      mbar_init(&S.step[i][0], kCluster);
-      mbar_init(&S.step[i][1], kCluster);
+      mbar_init(&S.ready[i][0], 1);
+      mbar_init(&S.ready[i][1], 1);
     }
     fence_mbar_init();
   }
@@ -153,7 +175,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t tbase = __shfl_sync(kFull, S.tmem_base, 0);
   pdl_launch_dependents();
   TL_START();
-  cluster_sync_all();   // every CTA's barriers exist before a peer may arrive on them
+  cluster_sync_all();   // every CTA's barriers exist before a peer may signal them
   TL(1);
 
   // ---- this CTA's W_hh slice -> tensor memory (parameters: not produced by the predecessor kernels) -----------------
@@ -181,16 +203,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
   // ---- this pipeline's tile steps: its partitions vc, vc + NV, ... ; all steps of a partition, then the next --------
   const int vc = pipe * n_clusters + cid, NV = kPipes * n_clusters;
-  const uint32_t s_bhi = smem_u32(smem + pipe * kPipeSmem), s_blo = s_bhi + kImage;
+  const uint32_t s_buf0 = smem_u32(smem + pipe * kPipeSmem);   // operand tile b: hi image at s_buf0 + b * kBufBytes, lo kImage later
   const uint32_t dcol = tbase + kColD + pipe * kColDStride;
-  const uint32_t ex_base = s_bhi;   // gate g is parked in k-atom (cb + 1 + g) & 3 of the (dead) hi image, plain [row][32] rows
 
   // lane l < n_steps keeps the packed-row range of a partition at step l: one load per partition, fetched one partition
   // ahead, so that walking the tile steps never waits for the table
   auto load_ranges = [&](int pt) -> int2 {
     int2 r = make_int2(0, 0);
     if (pt < n_parts && lane < P.n_steps) {
-      if (P.parts != nullptr) {
+      if (kChained) {
         r = __ldg(reinterpret_cast<const int2*>(P.parts) + static_cast<size_t>(pt) * P.part_stride + P.steps[lane].part_col);
       } else {   // single step without a partition table: plain row tiles
         r.x = P.steps[0].row0 + pt * kRows;
@@ -214,20 +235,34 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       st = first_step(r, 0);
     }
   };
-  // lanes 0 .. kU-1: previous-state row (-1: none) and time gap of this warp's u-th tile row;
-  // lanes 16, 17: time-embedding row of the first / last row of the tile
-  auto load_pre = [&](const TempGruArgs& q, int g0, int g1, int& pv, float& dv) {
-    pv = -1;
-    dv = 0.f;
-    if (lane < kU) {
-      const int r = g0 + gw + kPW * lane;
+  // what a tile step needs from the plan, fetched one tile step ahead: per gate-phase row the previous-state row (-1:
+  // none) and the time gap; the time-embedding rows of the first / last row; (!kChained) the gather phase's rows on lanes
+  struct Pre {
+    int prv[kUg];
+    float dt[kUg];
+    int tr0, tr1;
+    int gprv;     // !kChained: lanes 0 .. kU-1 = previous-state row of this warp's u-th gather row
+  };
+  auto load_pre = [&](const TempGruArgs& q, int g0, int g1, Pre& f) {
+#pragma unroll
+    for (int u = 0; u < kUg; ++u) {
+      const int r = g0 + 4 * gw + rsub + kRP * u;
+      f.prv[u] = -1;
+      f.dt[u] = 0.f;
       if (r < g1 && q.prev_row != nullptr) {
-        pv = __ldg(q.prev_row + r);
-        if (q.dt != nullptr) dv = __ldg(q.dt + r);
+        f.prv[u] = __ldg(q.prev_row + r);
+        if (q.dt != nullptr) f.dt[u] = __ldg(q.dt + r);
       }
-    } else if (lane == 16 || lane == 17) {
-      pv = q.row_time_scalar;
-      if (q.time_embed != nullptr && q.row_time != nullptr) pv = __ldg(q.row_time + (lane == 16 ? g0 : g1 - 1));
+    }
+    f.tr0 = f.tr1 = q.row_time_scalar;
+    if (q.time_embed != nullptr && q.row_time != nullptr) {
+      f.tr0 = __ldg(q.row_time + g0);
+      f.tr1 = __ldg(q.row_time + g1 - 1);
+    }
+    f.gprv = -1;
+    if (!kChained && lane < kU) {
+      const int r = g0 + gw + kPW * lane;
+      if (r < g1 && q.prev_row != nullptr) f.gprv = __ldg(q.prev_row + r);
     }
   };
 
@@ -235,64 +270,110 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   int2 rgs = load_ranges(part), rgs_next = load_ranges(part + NV);
   advance(part, s, rgs, rgs_next);
   bool have = part < n_parts;
-  int prv = -1;
-  float dtv = 0.f;
-  if (have) load_pre(P.steps[s], __shfl_sync(kFull, rgs.x, s), __shfl_sync(kFull, rgs.y, s), prv, dtv);
+  Pre cur;
+  if (have) load_pre(P.steps[s], __shfl_sync(kFull, rgs.x, s), __shfl_sync(kFull, rgs.y, s), cur);
   TL(2);
   pdl_wait();   // gi (and, for a single step, the previous state) come from the predecessor kernels
 
-  uint32_t t = 0;          // tile steps this pipeline has published
-  uint32_t mma_par = 0;
+  uint32_t t = 0;                    // tile steps done by this pipeline (operand tile of step t: t & 1)
+  uint32_t mma_par = 0, ready_par = 0;   // ready_par bit b: phase parity of S.ready[pipe][b]
+  int chain_part = -1, prev_rb = 0, prev_rows = 0;   // the previous tile step (same partition <=> its state is the operand)
 #pragma unroll 1
   while (have) {
     const TempGruArgs& p = P.steps[s];
     const int rb = __shfl_sync(kFull, rgs.x, s), r1 = __shfl_sync(kFull, rgs.y, s);
-    const int nmma = (r1 - rb + 15) & ~15;                 // UMMA N: 16, 32 or 48
     int n_part = part, n_s = s;
     int2 n_rgs = rgs, n_rgs_next = rgs_next;
     advance(n_part, n_s, n_rgs, n_rgs_next);
     const bool more = n_part < n_parts;
-
-    // the peers' state columns of this pipeline's previous tile step are visible after this wait; it also means every
-    // CTA is past its reads of that step (a pipeline's tile steps are totally ordered across the cluster)
+    const bool cont_next = kChained && more && n_part == part;   // the next tile step consumes this one's state
+    const uint32_t b = t & 1;
+    // chained: the operand tile is region 0, the two fp32 staging tiles share region 1; plain: regions alternate as operand
+    const uint32_t s_bhi = kChained ? s_buf0 : s_buf0 + b * kBufBytes, s_blo = s_bhi + kImage;
+    const uint32_t s_stage = s_buf0 + kBufBytes + b * kImage;          // (chained) fp32 [row][128] state of the previous step
+    const uint32_t ex_base = s_bhi;   // gate g parks in k-atom (cb + 1 + g) & 3 of the (dead) hi image, plain [row][32] rows
+    bool has_prev;
+    int nmma;
     TLS(0);
-    if (t > 0) mbar_wait_cluster(&S.step[pipe][(t - 1) & 1], ((t - 1) >> 1) & 1);
-    TLS(1);
 
-    // ---- previous-state rows -> shared-memory operand (decay, hi / lo split) ------------------------------------
+    // ---- everything that does not depend on the previous step is requested first: input gates, biases, time embedding --
+    const int j4 = jb + 4 * cq;
+    float4 gr[kUg], gz[kUg], gn[kUg];
+#pragma unroll
+    for (int u = 0; u < kUg; ++u) {
+      const int r = rb + 4 * gw + rsub + kRP * u;
+      gr[u] = gz[u] = gn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < r1) {
+        const float4* gi = reinterpret_cast<const float4*>(p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j4);
+        gr[u] = __ldg(gi);
+        gz[u] = __ldg(gi + kD / 4);
+        gn[u] = __ldg(gi + 2 * (kD / 4));
+      }
+    }
+    const float4 br = __ldg(reinterpret_cast<const float4*>(p.b_hh + j4));
+    const float4 bz = __ldg(reinterpret_cast<const float4*>(p.b_hh + kD + j4));
+    const float4 bn = __ldg(reinterpret_cast<const float4*>(p.b_hh + 2 * kD + j4));
+    // rows of one partition step belong to one snapshot instance (one time-embedding row); plain tiles may mix
+    float4 te_uni = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool te_rows = p.time_embed != nullptr && cur.tr0 != cur.tr1;
+    if (p.time_embed != nullptr && !te_rows)
+      te_uni = __ldg(reinterpret_cast<const float4*>(p.time_embed + static_cast<size_t>(cur.tr0) * kD + j4));
+
+    // ---- the previous state -> shared-memory operand (tf32 hi / lo parts; the decay is applied after the MMA) ----------
     {
       float4 v[kU];
+      if (kChained) {
+        has_prev = chain_part == part;
+        nmma = (prev_rows + 15) & ~15;
+        // arm the barrier the next step waits on: the bytes this step's rows will bring from the four CTAs
+        if (cont_next && gw == 0 && elect_one()) mbar_expect_tx(&S.ready[pipe][b ^ 1], static_cast<uint32_t>(r1 - rb) * 512u);
+        if (has_prev) {
+          mbar_wait(&S.ready[pipe][b], (ready_par >> b) & 1u);   // the staging tile is complete (all 4 CTAs' columns)
+          ready_par ^= 1u << b;
+          TLS(1);
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int pr = __shfl_sync(kFull, prv, u);
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pr >= 0) v[u] = __ldcg(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
-      }
-      const float dec = p.dt != nullptr ? decay_factor(dtv, p.decay_wb, p.inv_temperature) : 1.f;
-      TLS(2);
+          for (int u = 0; u < kU; ++u) {
+            const int n = gw + kPW * u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < prev_rows) v[u] = lds_f32x4(s_stage + n * 512 + lane * 16);
+          }
+        }
+      } else {
+        nmma = (r1 - rb + 15) & ~15;
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = gw + kPW * u;
-        const float dv = __shfl_sync(kFull, dec, u);
-        if (i >= nmma) continue;   // warp-uniform: beyond the rows this step's MMA reads
-        float4 hi, lo;
-        split_tf32(v[u].x * dv, hi.x, lo.x);
-        split_tf32(v[u].y * dv, hi.y, lo.y);
-        split_tf32(v[u].z * dv, hi.z, lo.z);
-        split_tf32(v[u].w * dv, hi.w, lo.w);
-        const uint32_t off = static_cast<uint32_t>(lane >> 3) * kAtomBytes + (i >> 3) * 1024u + (i & 7) * 128u +
-                             (((lane & 7) ^ (i & 7)) << 4);
-        sts_f32x4(s_bhi + off, hi);
-        sts_f32x4(s_blo + off, lo);
+        for (int u = 0; u < kU; ++u) {
+          const int pr = __shfl_sync(kFull, cur.gprv, u);
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pr >= 0) v[u] = __ldcg(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
+        }
+        has_prev = true;   // (decided below by the reduction)
       }
-      fence_proxy_async();
+      if (has_prev) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int i = gw + kPW * u;
+          if (i >= nmma) continue;   // warp-uniform: beyond the rows this step's MMA reads
+          float4 hi, lo;
+          split_tf32(v[u].x, hi.x, lo.x);
+          split_tf32(v[u].y, hi.y, lo.y);
+          split_tf32(v[u].z, hi.z, lo.z);
+          split_tf32(v[u].w, hi.w, lo.w);
+          const uint32_t off = static_cast<uint32_t>(lane >> 3) * kAtomBytes + (i >> 3) * 1024u + (i & 7) * 128u +
+                               (((lane & 7) ^ (i & 7)) << 4);
+          sts_f32x4(s_bhi + off, hi);
+          sts_f32x4(s_blo + off, lo);
+        }
+        fence_proxy_async();
+        if (kChained)
+          bar_named(bar_id, kPT);
+        else
+          has_prev = bar_red_or(bar_id, kPT, __any_sync(kFull, lane < kU && cur.gprv >= 0));
+      }
     }
-    TLS(3);
-    const bool any_prev = bar_red_or(bar_id, kPT, __any_sync(kFull, lane < kU && prv >= 0));
-    TLS(4);
+    TLS(2);
 
     // ---- gh^T = W_hh . h0^T : 16 k-steps x 3 split passes, A from tensor memory -----------------------------------
-    if (any_prev && gw == 0) {   // warp-uniform
+    if (has_prev && gw == 0) {   // warp-uniform
       tc_fence_after();
       if (elect_one()) {
         const uint32_t idesc = umma_idesc_tf32(128, nmma);
@@ -312,47 +393,38 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       }
       __syncwarp();
     }
-    TLS(5);
+    TLS(3);
 
-    // ---- while the MMA runs: this thread's h0 values, input gates, biases; the NEXT tile step's indices ------------
-    const int j = jb + lane;
-    float h0[kU], gi_r[kU], gi_z[kU], gi_n[kU];
+    // ---- while the MMA runs: h0 of this thread's (row, 4 columns); the NEXT tile step's indices ------------------------
+    float4 h0[kUg];
+    int nrow[kUg];   // operand / accumulator row of this thread's row: prev_row relative to the previous step (-1: no state)
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int i = gw + kPW * u;
-      const int r = rb + i;
-      h0[u] = gi_r[u] = gi_z[u] = gi_n[u] = 0.f;
-      if (r < r1) {
-        if (any_prev) {
-          const uint32_t off = static_cast<uint32_t>(cb) * kAtomBytes + sw128_off(i, lane);
-          h0[u] = lds_f32(s_bhi + off) + lds_f32(s_blo + off);
+    for (int u = 0; u < kUg; ++u) {
+      const int i = 4 * gw + rsub + kRP * u;
+      h0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      nrow[u] = -1;
+      if (rb + i < r1 && has_prev && cur.prv[u] >= 0) {
+        const int n = kChained ? cur.prv[u] - prev_rb : i;
+        if (kChained && (n < 0 || n >= prev_rows)) __trap();   // a state row outside the previous step of this partition
+        nrow[u] = n;
+        if (kChained) {
+          h0[u] = lds_f32x4(s_stage + n * 512 + cb * 128 + cq * 16);
+        } else {
+          const uint32_t off = static_cast<uint32_t>(cb) * kAtomBytes + (n >> 3) * 1024u + (n & 7) * 128u + ((cq ^ (n & 7)) << 4);
+          const float4 a = lds_f32x4(s_bhi + off), c = lds_f32x4(s_blo + off);
+          h0[u] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
         }
-        const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
-        gi_r[u] = __ldg(gi);
-        gi_z[u] = __ldg(gi + kD);
-        gi_n[u] = __ldg(gi + 2 * kD);
       }
     }
-    const float br = __ldg(p.b_hh + j), bz = __ldg(p.b_hh + kD + j), bn = __ldg(p.b_hh + 2 * kD + j);
-    // rows of one partition step belong to one snapshot instance (one time-embedding row); plain tiles may mix
-    float te_uni = 0.f;
-    bool te_rows = false;
-    if (p.time_embed != nullptr) {
-      const int trow0 = __shfl_sync(kFull, prv, 16), trow1 = __shfl_sync(kFull, prv, 17);
-      te_rows = trow0 != trow1;
-      if (!te_rows) te_uni = __ldg(p.time_embed + static_cast<size_t>(trow0) * kD + j);
-    }
-    int n_prv = -1;
-    float n_dtv = 0.f;
-    if (more) load_pre(P.steps[n_s], __shfl_sync(kFull, n_rgs.x, n_s), __shfl_sync(kFull, n_rgs.y, n_s), n_prv, n_dtv);
+    Pre nxt;
+    if (more) load_pre(P.steps[n_s], __shfl_sync(kFull, n_rgs.x, n_s), __shfl_sync(kFull, n_rgs.y, n_s), nxt);
 
     // ---- accumulator (gate = lane quadrant, rows on columns) -> exchange rows, one barrier --------------------------
-    TLS(6);
-    if (any_prev) {
+    if (has_prev) {
       mbar_wait(&S.mma_done[pipe], mma_par);
       mma_par ^= 1;
       tc_fence_after();
-      TLS(7);
+      TLS(4);
       if (quad < 3) {
         const int h = gw >> 2;   // the kH warps of a quadrant take the 16-column chunks round robin
         const uint32_t ta = dcol + (static_cast<uint32_t>(32 * quad) << 16);
@@ -371,60 +443,91 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       tc_fence_before();
       bar_named(bar_id, kPT);
     }
-    TLS(8);
+    TLS(5);
 
-    // ---- gates, state store (+ fused all-gather peer stores) -------------------------------------------------------
+    // ---- gates, state store, hand-over to the next step (+ fused all-gather peer stores) ------------------------------
+    uint32_t peer_stage[kCluster], peer_bar[kCluster];
+    if (cont_next) {
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int i = gw + kPW * u;
+      for (int k = 0; k < kCluster; ++k) {
+        peer_stage[k] = mapa_u32(s_buf0 + kBufBytes + (b ^ 1) * kImage, k);
+        peer_bar[k] = mapa_u32(smem_u32(&S.ready[pipe][b ^ 1]), k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUg; ++u) {
+      const int i = 4 * gw + rsub + kRP * u;
       const int r = rb + i;
-      if (r < r1) {   // warp-uniform
-        float hr = br, hz = bz, hn = bn;
-        if (any_prev) {
-          const uint32_t ea = ex_base + i * 128 + lane * 4;
-          hr += lds_f32(ea + ((cb + 1) & 3) * kAtomBytes);
-          hz += lds_f32(ea + ((cb + 2) & 3) * kAtomBytes);
-          hn += lds_f32(ea + ((cb + 3) & 3) * kAtomBytes);
+      if (r < r1) {
+        float4 hr = br, hz = bz, hn = bn;
+        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nrow[u] >= 0) {
+          const float dec = p.dt != nullptr ? decay_factor(cur.dt[u], p.decay_wb, p.inv_temperature) : 1.f;
+          const uint32_t ea = ex_base + nrow[u] * 128 + cq * 16;
+          const float4 xr = lds_f32x4(ea + ((cb + 1) & 3) * kAtomBytes);
+          const float4 xz = lds_f32x4(ea + ((cb + 2) & 3) * kAtomBytes);
+          const float4 xn = lds_f32x4(ea + ((cb + 3) & 3) * kAtomBytes);
+          hr.x = fmaf(dec, xr.x, hr.x); hr.y = fmaf(dec, xr.y, hr.y); hr.z = fmaf(dec, xr.z, hr.z); hr.w = fmaf(dec, xr.w, hr.w);
+          hz.x = fmaf(dec, xz.x, hz.x); hz.y = fmaf(dec, xz.y, hz.y); hz.z = fmaf(dec, xz.z, hz.z); hz.w = fmaf(dec, xz.w, hz.w);
+          hn.x = fmaf(dec, xn.x, hn.x); hn.y = fmaf(dec, xn.y, hn.y); hn.z = fmaf(dec, xn.z, hn.z); hn.w = fmaf(dec, xn.w, hn.w);
+          hp = make_float4(dec * h0[u].x, dec * h0[u].y, dec * h0[u].z, dec * h0[u].w);
         }
         // torch.nn.GRU, gate order r, z, n
-        const float rg_ = fast_sigmoid(gi_r[u] + hr);
-        const float zg = fast_sigmoid(gi_z[u] + hz);
-        const float ng = fast_tanh(gi_n[u] + rg_ * hn);
-        float hy = (1.f - zg) * ng + zg * h0[u];
-        hy += te_rows ? __ldg(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j) : te_uni;
-        float* o = p.out + static_cast<size_t>(r) * kD + j;
-        if (p.accumulate) hy += __ldcg(o);
+        float4 hy;
+        {
+          const float rg_ = fast_sigmoid(gr[u].x + hr.x), zg = fast_sigmoid(gz[u].x + hz.x);
+          const float ng = fast_tanh(gn[u].x + rg_ * hn.x);
+          hy.x = (1.f - zg) * ng + zg * hp.x;
+        }
+        {
+          const float rg_ = fast_sigmoid(gr[u].y + hr.y), zg = fast_sigmoid(gz[u].y + hz.y);
+          const float ng = fast_tanh(gn[u].y + rg_ * hn.y);
+          hy.y = (1.f - zg) * ng + zg * hp.y;
+        }
+        {
+          const float rg_ = fast_sigmoid(gr[u].z + hr.z), zg = fast_sigmoid(gz[u].z + hz.z);
+          const float ng = fast_tanh(gn[u].z + rg_ * hn.z);
+          hy.z = (1.f - zg) * ng + zg * hp.z;
+        }
+        {
+          const float rg_ = fast_sigmoid(gr[u].w + hr.w), zg = fast_sigmoid(gz[u].w + hz.w);
+          const float ng = fast_tanh(gn[u].w + rg_ * hn.w);
+          hy.w = (1.f - zg) * ng + zg * hp.w;
+        }
+        float4 te = te_uni;
+        if (te_rows) te = __ldg(reinterpret_cast<const float4*>(p.time_embed + static_cast<size_t>(__ldg(p.row_time + r)) * kD + j4));
+        hy.x += te.x; hy.y += te.y; hy.z += te.z; hy.w += te.w;
+        float4* o = reinterpret_cast<float4*>(p.out + static_cast<size_t>(r) * kD + j4);
+        if (p.accumulate) {
+          const float4 a = __ldcg(o);
+          hy.x += a.x; hy.y += a.y; hy.z += a.z; hy.w += a.w;
+        }
+        if (cont_next) {   // this CTA's 32 columns of the next step's staging tile, in all four CTAs (row order of THIS step)
+          const uint32_t off = static_cast<uint32_t>(i) * 512u + cb * 128u + cq * 16u;
+#pragma unroll
+          for (int k = 0; k < kCluster; ++k) st_async_f32x4(peer_stage[k] + off, hy, peer_bar[k]);
+        }
         *o = hy;
         if (p.push != 0 && P.push_bufs != nullptr) {   // NVLink stores into every peer's slab (TempGruScanArgs.push_*)
-          const size_t po = static_cast<size_t>(r - P.push_row0) * kD + j;
+          const size_t po = static_cast<size_t>(r - P.push_row0) * kD + j4;
           if (P.push_multicast != nullptr) {
-            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.push_multicast + P.push_offset + po), "f"(hy)
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.push_multicast + P.push_offset + po),
+                         "f"(hy.x), "f"(hy.y), "f"(hy.z), "f"(hy.w)
                          : "memory");
           } else {
-            for (int k = 0; k < P.push_world; ++k) S.push[k][po] = hy;
+            for (int k = 0; k < P.push_world; ++k) *reinterpret_cast<float4*>(S.push[k] + po) = hy;
           }
         }
       }
     }
-
-    // ---- publish: the pipeline's stores -> ONE cluster-scope release fence -> relaxed arrives on the pipeline's barrier
-    // in all four CTAs (an arrive.release per peer would repeat the full memory barrier four times)
-    TLS(9);
-    bar_named(bar_id, kPT);   // also: every exchange / operand read of this step is done
-    TLS(10);
-    if (more && gw == 0) {    // (nobody waits for the last tile step of a pipeline)
-      if (elect_one()) {
-        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-        const uint32_t bar = smem_u32(&S.step[pipe][t & 1]);
-#pragma unroll
-        for (int k = 0; k < kCluster; ++k) mbar_arrive_remote_relaxed(mapa_u32(bar, k));
-      }
-      __syncwarp();
-    }
-    TLS(11);
-    ++t;
-    prv = n_prv;
-    dtv = n_dtv;
+    TLS(6);
+    chain_part = part;
+    prev_rb = rb;
+    prev_rows = r1 - rb;
+    // A partition's first step sends without waiting for anything; skipping one tile parity at a partition switch keeps
+    // those stores away from the staging tile a slower peer may still read for the partition that just ended.
+    t += (kChained && !cont_next) ? 2 : 1;
+    cur = nxt;
     part = n_part;
     s = n_s;
     rgs = n_rgs;
@@ -434,7 +537,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
+  cluster_sync_all();   // no CTA leaves while a peer may still signal its barriers / write its operand tiles
   if (warp == 0) tmem_dealloc(tbase, kTmemCols);
 }
 
@@ -461,6 +564,9 @@ bool tc_scan2_supported(const TempGruScanArgs* a) {
     const TempGruArgs& g = a->steps[s];
     if (g.d != kD || g.cell_type != TEMP_CELL_TORCH_GRU) return false;
     if (a->parts != nullptr && (g.part_col < 0 || g.part_col >= a->part_stride)) return false;
+    // chained steps hand the state over on chip: what a step reads through prev_row must be what its predecessor wrote
+    if (a->parts != nullptr && (g.accumulate != 0 || (g.prev_row != nullptr && g.state != a->steps[0].out) || g.out != a->steps[0].out))
+      return false;
     if (g.prev_row != nullptr) {
       if (g.whh_packed == nullptr) return false;
       if (w != nullptr && g.whh_packed != w) return false;
@@ -471,11 +577,11 @@ bool tc_scan2_supported(const TempGruScanArgs* a) {
   return true;
 }
 
-template <int kPipes>
+template <int kPipes, bool kChained>
 int launch_scan2_t(const TempGruScanArgs* a, int n_parts, int clusters, const void* w, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gru_scan_tm_kernel<kPipes>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gru_scan_tm_kernel<kPipes, kChained>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tm_kernel");
     configured = true;
   }
@@ -490,7 +596,7 @@ int launch_scan2_t(const TempGruScanArgs* a, int n_parts, int clusters, const vo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tm_kernel<kPipes>, *a, n_parts, w);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tm_kernel<kPipes, kChained>, *a, n_parts, w);
   if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tm_kernel launch");
   return TEMP_OK;
 }
@@ -509,22 +615,22 @@ int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmem;
     cfg.gridDim = dim3(kCluster * 64);
-    cudaFuncSetAttribute(gru_scan_tm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, gru_scan_tm_kernel<4>, &cfg);
+    cudaFuncSetAttribute(gru_scan_tm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, gru_scan_tm_kernel<2, true>, &cfg);
     if (e != cudaSuccess || max_clusters <= 0) {
       cudaGetLastError();
       max_clusters = 32;
     }
   }
   static const int force = getenv("TEMP_SCAN_PIPES") != nullptr ? atoi(getenv("TEMP_SCAN_PIPES")) : 0;   // development knob
-  // spread first: as many clusters as there are partitions; then the fewest pipelines per CTA that still give every
-  // partition its own (more warps per tile = a shorter step chain), four when partitions queue anyway
+  // spread first: as many clusters as there are partitions; one pipeline per CTA while that gives every partition its
+  // own (16 warps per tile = the shortest step chain), two when partitions queue anyway
   const int clusters = n_parts < max_clusters ? n_parts : max_clusters;
-  int pipes = n_parts <= clusters ? 1 : (n_parts <= 2 * clusters ? 2 : 4);
-  if (force == 1 || force == 2 || force == 4) pipes = force;
-  if (pipes == 1) return launch_scan2_t<1>(a, n_parts, clusters, w, st);
-  if (pipes == 2) return launch_scan2_t<2>(a, n_parts, clusters, w, st);
-  return launch_scan2_t<4>(a, n_parts, clusters, w, st);
+  int pipes = n_parts <= clusters ? 1 : 2;
+  if (force == 1 || force == 2) pipes = force;
+  if (a->parts != nullptr)
+    return pipes == 1 ? launch_scan2_t<1, true>(a, n_parts, clusters, w, st) : launch_scan2_t<2, true>(a, n_parts, clusters, w, st);
+  return pipes == 1 ? launch_scan2_t<1, false>(a, n_parts, clusters, w, st) : launch_scan2_t<2, false>(a, n_parts, clusters, w, st);
 }
 
 }  // namespace temp_internal

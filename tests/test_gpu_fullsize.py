@@ -149,6 +149,7 @@ def test_scan_walks_more_than_32_partitions_per_cluster_in_rounds():
     want = model.encode(t_list).out.clone()
     plan = plan_window(model.graph_dict_train, t_list, model.train_seq_len)       # the python planner: arrays are plain numpy
     plan.scan_parts = chain_partitions(plan, tile=8)
+    plan.scan_tile = 8                    # the row bound the scan launch is told (TempGruScanArgs.part_rows)
     assert plan.scan_parts.shape[0] > 32 * 37
     got = model.encode(plan=plan).out
     assert torch.equal(got, want)

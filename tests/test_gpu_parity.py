@@ -84,7 +84,10 @@ def test_dense_history_api_matches_oracle():
 
 @pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_tiny_d128_last", "grrgcn_tiny_d32_nb8_type1"])
 def test_cooperative_scan_equals_per_step_launches(name):
-    """One persistent cooperative launch for all GRU steps must be bit-identical to one launch per step."""
+    """One persistent launch for all GRU steps against one launch per step: bit-identical where both run the same kernel
+    family (uni-directional tcgen05 scans: gru_scan_tm_kernel, fp32 SIMT scans); the Bi models' fused scan alternates
+    between two recurrent cells and runs on gru_scan_tc_kernel (decay applied BEFORE the product) while their single
+    steps run on gru_scan_tm_kernel (decay applied to the product: W.(c h) = c (W.h)) -- equal up to fp32 rounding."""
     from tests.helpers import CASE_BY_NAME
     case = CASE_BY_NAME[name]
     model = product_model(case)
@@ -95,8 +98,12 @@ def test_cooperative_scan_equals_per_step_launches(name):
     model.runtime.fuse_scan = True
     b = model.encode(case["t_list"])
     assert b.program.count() < n_a
-    assert torch.equal(a, b.out)
-    for _ in range(3):                      # the barrier word is self-cleaning: repeated launches stay correct
+    if case["module"].startswith("Bi") and case["D"] == 128:
+        assert float((a - b.out).abs().max()) <= 2e-6 * float(a.abs().max())
+        a = b.out.clone()
+    else:
+        assert torch.equal(a, b.out)
+    for _ in range(3):                      # repeated launches stay correct (self-cleaning barriers) and deterministic
         assert torch.equal(a, model.encode(case["t_list"]).out)
 
 

@@ -40,8 +40,8 @@ MAXCTA = 1024
 buf = torch.zeros(MAXCTA * WARPS * SLOTS, dtype=torch.int64, device=dev)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 L.temp_debug_timeline2.argtypes = [C.c_void_p]
-PH = ["top", "step-wait", "gather-ld", "split+sts", "bar-or", "mma-issue", "gi/h0 loads", "mma-wait", "tmem->ex+bar", "gates+st",
-      "bar", "fence+arrive"]
+PH = ["top", "gi-req+stage-wait", "convert+bar", "mma-issue", "h0+mma-wait", "tmem->ex+bar", "gates+st+send"]
+NPH, STRIDE, NST = 7, 8, 7
 for o in [o for o in res.program.ops if o.kind == lib.OP_GRU_SCAN]:
     one = lib.Program()
     one.ops = [o]
@@ -65,22 +65,23 @@ for o in [o for o in res.program.ops if o.kind == lib.OP_GRU_SCAN]:
         t = t[used].astype(np.float64)
         for w in (0, 1, 3, 4, 8, 12):
             tw = t[:, w, :]
-            ok = tw[:, 3 + 12 * 1] != 0           # CTAs whose pipeline reached tile step 3
+            ok = tw[:, 3 + STRIDE * 1] != 0           # CTAs whose pipeline reached tile step 3
             if ok.sum() == 0:
                 print("   warp %2d: pipeline idle" % w)
                 continue
             tw = tw[ok]
             print("   warp %2d (pipe %d, %d CTAs): prologue cluster-sync %.0f, W->TMEM+indices %.0f" %
                   (w, w // 4, int(ok.sum()), np.median(tw[:, 1] - tw[:, 0]), np.median(tw[:, 2] - tw[:, 1])))
-            for st in range(5):
-                base = 3 + 12 * st
-                if (tw[:, base] == 0).any() or (tw[:, base + 11] == 0).any():
+            for st in range(NST):
+                base = 3 + STRIDE * st
+                if (tw[:, base] == 0).any() or (tw[:, base + NPH - 1] == 0).any():
                     continue
                 seg = []
-                for k in range(1, 12):
+                for k in range(1, NPH):
                     a, b = tw[:, base + k - 1], tw[:, base + k]
                     good = (a != 0) & (b != 0)
                     seg.append("%s %.0f" % (PH[k], np.median((b - a)[good])) if good.any() else "%s -" % PH[k])
-                nxt = tw[:, base + 12] if base + 12 < 63 else None
-                tot = np.median(tw[:, base + 11] - tw[:, base])
+                tot = np.median(tw[:, base + NPH - 1] - tw[:, base])
+                if st + 1 < NST and (tw[:, base + STRIDE] != 0).all():
+                    tot = np.median(tw[:, base + STRIDE] - tw[:, base])        # top to top: the whole tile step
                 print("      tile step %d: total %.0f | %s" % (st + 2, tot, " | ".join(seg)))
