@@ -160,6 +160,7 @@ def run_reference(args, rank, world):
     store = SnapshotStore.synthetic(WORKLOAD["shape"], num_times=WORKLOAD["num_times"], scale=1, seed=SEED)
     model = init_state(store)
     t_lists = batches(store, 8)
+    n_edges = [count_edges(store, tl) for tl in t_lists]     # (outside the clock: the repo's planner is not the reference's work)
     import torch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -170,15 +171,14 @@ def run_reference(args, rank, world):
         steps = min(args.steps, 60)              # bounded sample: each step is one full forward of the workload
         edges, t0 = 0, time.perf_counter()
         for k in range(steps):
-            tl = t_lists[k % len(t_lists)]
-            oracle.evaluate_embed(tl)
-            edges += count_edges(store, tl)
+            oracle.evaluate_embed(t_lists[k % len(t_lists)])
+            edges += n_edges[k % len(t_lists)]
         dt = time.perf_counter() - t0
     val = edges / dt
     line = {"impl": "reference", "metric": "edges_per_sec_rgcn_gru_forward", "value": val, "unit": "edges/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(1),
+            "config": bench_config(args.gpus),
             "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port",
                              "sample": "%d forwards (oracle port of the reference's DGL-CPU path; the reference "
                                        "needs dgl==0.4.1 + pytorch_lightning==0.5.2, not installable)" % steps},
@@ -187,10 +187,28 @@ def run_reference(args, rank, world):
 
 
 def bench_config(world):
+    """Identical in both arms (the driver compares the dicts)."""
     return {"workload": "GRRGCN rec-only-last-layer + time-embedding, ICEWS14-shaped synthetic x1, seq_len=8, "
                         "batch=8 windows (64 snapshot instances), D=128, n_bases=128, region R1 (evaluate_embed)",
-            "l2": "flushed between timed steps (256 MiB write)", "parallelism": "dp%d over target timestamps" % world,
+            "l2": "GPU arm: flushed between timed steps (256 MiB write)", "parallelism": "dp%d over target timestamps" % world,
             "seed": SEED}
+
+
+def parity_gate(model, store, t_list):
+    """every timed GPU run is preceded by a comparison of the CUDA path with the CPU oracle on the
+    same inputs (allclose rtol 1e-4, atol 4e-6 * max |ref|, the level tests/test_gpu_parity.py asserts)."""
+    import torch
+    oracle = oracle_model_for(store, model.state_dict())
+    with torch.no_grad():
+        want = torch.cat(oracle.evaluate_embed(t_list)["per_graph"]).double().numpy()
+    got = model.encode(t_list).out.double().cpu().numpy()
+    scale = float(np.abs(want).max())
+    err = float(np.abs(got - want).max() / scale)
+    ok = bool(np.allclose(got, want, rtol=1e-4, atol=4e-6 * scale))
+    if not ok:
+        raise RuntimeError("bench: the CUDA forward differs from the oracle (max err / scale %.3e) -- nothing is timed" % err)
+    return {"checked": "model.encode(t_lists[0]) against the CPU oracle on the same snapshots and parameters, before timing",
+            "allclose_rtol_1e-4_atol_4e-6_scale": ok, "max_err_over_scale": err, "rows": int(want.shape[0])}
 
 
 def main():
@@ -200,12 +218,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--d2h-copy", action="store_true", help="e2e arm: cudaMemcpyAsync of the result after the kernels instead "
-                                                            "of stores to pinned host memory from inside the scan kernel")
-    ap.add_argument("--graph", action="store_true", help="one CUDA graph per launch program instead of direct launches "
-                                                         "(measured: no gain, the step is bound on the device)")
-    ap.add_argument("--multimem", action="store_true", help="N > 1: NVLS multimem.st instead of one store per peer (measured "
-                                                            "slower at 4 bytes per lane: 0.152 vs 0.143 ms per step at N = 8)")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the fused peer stores")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
@@ -228,197 +240,103 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = args.steps
+    D = WORKLOAD["D"]
 
     store = SnapshotStore.synthetic(WORKLOAD["shape"], num_times=WORKLOAD["num_times"], scale=1, seed=SEED + 1000 * rank)
     model = init_state(store).to(dev).eval()
-    rt = model.runtime
     t_lists = batches(store, 8, rank)
     model.plan(t_lists[0])                       # one-time: snapshot view table of the native planner
     t0 = time.perf_counter()
     plans = [model.plan(tl) for tl in t_lists]
     plan_ms = 1e3 * (time.perf_counter() - t0) / len(plans)
-
-    # one program per distinct batch; separate workspaces would only change addresses, so programs are
-    # rebuilt (cheap) per step group: build all, each with its own plan blob
-    # the largest plan first: the runtime's grow-only workspace is then sized once and every program's pointers stay valid
+    # the largest batch first: the runtime's grow-only workspace is then sized once
     order = sorted(range(len(plans)), key=lambda i: -plans[i].R)
-    plans = [plans[i] for i in order]
     t_lists = [t_lists[i] for i in order]
-    results = []
-    for i, p in enumerate(plans):
-        prog = lib.Program()
-        dptr = rt.stage_plan(p, prog, tag="plan%d" % i)
-        h2d = prog.ops[0]
-        prog.ops = []
-        res = rt._build_recurrent(p, prog, dptr)
-        nf = p.final.row1 - p.final.row0
-        host_out = torch.empty(nf, WORKLOAD["D"], dtype=torch.float32, pin_memory=True)
-        d2h = lib.Op()
-        d2h.kind = lib.OP_D2H
-        d2h.u.copy = lib.CopyArgs(host_out.data_ptr(), res.out.data_ptr(), nf * WORKLOAD["D"] * 4)
-        e2e_prog = lib.Program()
-        # own copies of the ops: the e2e program gets the host buffer as an extra "peer" of the fused all-gather below
-        e2e_prog.ops = [h2d] + [lib.Op.from_buffer_copy(o) for o in res.program.ops] + ([d2h] if args.d2h_copy else [])
-        e2e_prog.keepalive = list(res.program.keepalive) + [host_out]
-        # make the plan resident for the device-timed arm
-        up = lib.Program()
-        up.ops = [h2d]
-        up.run()
-        results.append((res, e2e_prog, host_out, h2d.u.copy.bytes, nf * WORKLOAD["D"] * 4))
-    torch.cuda.synchronize()
+    n_edges = [plans[i].E for i in order]
+    n_final = [plans[i].final.row1 - plans[i].final.row0 for i in order]
+    del plans
 
-    # all-gather of the final-layer states (N > 1): fused into the scan kernel as NVLink stores into every peer's
-    # slab of a symmetric buffer + one cross-GPU barrier; NCCL all_gather_into_tensor when symmetric memory is unavailable
-    # (and once, to verify the fused path)
+    parity = parity_gate(model, store, t_lists[0]) if rank == 0 else None
+
+    # N > 1: all-gather of the final-layer states of all ranks, fused into the scan kernel (temp_b200/exchange.py)
+    ex = None
     exchange = "none"
-    symm_hdl = None
     if world > 1:
-        D = WORKLOAD["D"]
-        max_rows = max(r[0].plan.final.row1 - r[0].plan.final.row0 for r in results)
-        rows_t = torch.tensor([max_rows], device=dev)
+        from temp_b200.exchange import FinalStateAllGather
+        rows_t = torch.tensor([max(n_final)], device=dev)
         dist.all_reduce(rows_t, op=dist.ReduceOp.MAX)
-        max_rows = int(rows_t.item())
-        send = torch.zeros(max_rows, D, device=dev)
-        recv = torch.empty(world * max_rows, D, device=dev)
-        exchange = "nccl all_gather_into_tensor"
-        if not args.nccl_exchange:
-            try:
-                import torch.distributed._symmetric_memory as symm
-                # two slabs per peer, used alternately: a rank may start pushing step s + 1 while a slower peer still
-                # reads step s (it cannot get further ahead: the barrier of step s + 1 needs that peer's signal)
-                sym_recv = symm.empty((2, world, max_rows, D), dtype=torch.float32, device=dev)
-                sym_recv.zero_()
-                symm_hdl = symm.rendezvous(sym_recv, group=dist.group.WORLD)
-                peer_ptrs = torch.tensor([int(p) for p in symm_hdl.buffer_ptrs], dtype=torch.int64, device=dev)
-                sym_flags = symm.empty((32,), dtype=torch.int32, device=dev)
-                sym_flags.zero_()
-                flag_hdl = symm.rendezvous(sym_flags, group=dist.group.WORLD)
-                flag_ptrs = torch.tensor([int(p) for p in flag_hdl.buffer_ptrs], dtype=torch.int64, device=dev)
-                torch.cuda.synchronize()
-                symm_hdl.barrier()
-                mc_ptr = 0
-                if args.multimem:
-                    try:
-                        if symm_hdl.has_multicast_support:
-                            mc_ptr = int(symm_hdl.multicast_ptr)
-                    except Exception:
-                        mc_ptr = 0
-                for k, (res, e2e_prog, _, _, _) in enumerate(results):
-                    fin = res.plan.final
-                    res.program.enable_peer_push(peer_ptrs.data_ptr(), world, ((k & 1) * world + rank) * max_rows * D,
-                                                 fin.row0, fin.row1, multicast_ptr=mc_ptr)
-                    e2e_prog._arr = None
-                barrier_seq = [0]
-
-                def peer_barrier():
-                    barrier_seq[0] += 1
-                    lib.check(lib.load().temp_peer_barrier(sym_flags.data_ptr(), flag_ptrs.data_ptr(), world, rank,
-                                                           barrier_seq[0], lib.current_stream()), "temp_peer_barrier")
-                # verify once against NCCL
-                results[0][0].program.run()
-                peer_barrier()
-                nf0 = results[0][0].out.shape[0]
-                send.zero_()
-                send[:nf0].copy_(results[0][0].out)
-                dist.all_gather_into_tensor(recv, send)
-                torch.cuda.synchronize()
-                nfs = [torch.zeros(1, dtype=torch.long, device=dev) for _ in range(world)]
-                dist.all_gather(nfs, torch.tensor([nf0], device=dev))
-                ok = all(torch.equal(sym_recv[0, k, :int(nfs[k])], recv.view(world, max_rows, D)[k, :int(nfs[k])]) for k in range(world))
-                flag = torch.tensor([int(ok)], device=dev)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                if int(flag.item()) != 1:
-                    raise RuntimeError("fused peer all-gather differs from the NCCL all-gather")
-                exchange = ("fused into the scan kernel: %s into double-buffered symmetric memory + one signal/wait launch "
-                            "(temp_peer_barrier); verified against NCCL"
-                            % ("NVLS multimem.st (one store, switch-replicated)" if mc_ptr else "one NVLink store per peer"))
-            except Exception as ex:
-                if symm_hdl is not None:
-                    raise
-                exchange = "nccl all_gather_into_tensor (symmetric memory unavailable: %r)" % (ex,)
+        ex = FinalStateAllGather(dev, int(rows_t.item()), D, nccl=args.nccl_exchange)
+        exchange = ex.how
+        if ex.fused:                                             # verify once against NCCL
+            r0 = model.encode(t_lists[0], exchange=ex)
+            torch.cuda.synchronize()
+            send = torch.zeros(ex.max_rows, D, device=dev)
+            send[:n_final[0]].copy_(r0.out)
+            recv = torch.empty(world * ex.max_rows, D, device=dev)
+            dist.all_gather_into_tensor(recv, send)
+            nfs = [torch.zeros(1, dtype=torch.long, device=dev) for _ in range(world)]
+            dist.all_gather(nfs, torch.tensor([n_final[0]], device=dev))
+            ok = all(torch.equal(ex.gathered(k, int(nfs[k])), recv.view(world, ex.max_rows, D)[k, :int(nfs[k])]) for k in range(world))
+            flag = torch.tensor([int(ok)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) != 1:
+                raise RuntimeError("fused peer all-gather differs from the NCCL all-gather")
+            exchange += "; verified against NCCL"
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
-    def gather_states(res):
-        if symm_hdl is not None:
-            peer_barrier()                # every rank's scan (and its peer stores) has completed
-        else:
-            nf = res.out.shape[0]
-            send[:nf].copy_(res.out)
-            dist.all_gather_into_tensor(recv, send)
-
+    # Both arms go through the public call.  device arm: model.encode(t_list) on batches it has seen (plan resident on the
+    # device, kernels only); e2e arm: the packed plan is re-copied from pinned host memory every step and the final states
+    # land in pinned host memory (written from inside the scan kernel).
     def step_device(i):
-        res = results[i % len(results)][0]
-        res.program.run()
-        if world > 1:
-            gather_states(res)
+        return model.encode(t_lists[i % len(t_lists)], exchange=ex)
 
     def step_e2e(i):
-        results[i % len(results)][1].run()
-        if world > 1:
-            gather_states(results[i % len(results)][0])
+        return model.encode(t_lists[i % len(t_lists)], to_host=True, reupload=True, exchange=ex)
 
-    # e2e arm: the final states reach the pinned host buffer from INSIDE the scan kernel (the host buffer is one more
-    # "peer" of the fused all-gather: UVA stores over PCIe during the last scan step) instead of a device-to-host copy
-    # after the kernels; --d2h-copy restores the copy
-    if not args.d2h_copy:
-        D = WORKLOAD["D"]
-        for k, (res, e2e_prog, host_out, _, _) in enumerate(results):
-            fin = res.plan.final
-            if symm_hdl is not None:
-                off = ((k & 1) * world + rank) * max_rows * D
-                ptr_list = [int(p) for p in symm_hdl.buffer_ptrs] + [host_out.data_ptr() - 4 * off]
-            else:
-                off = 0
-                ptr_list = [host_out.data_ptr()]
-            ptr_t = torch.tensor(ptr_list, dtype=torch.int64, device=dev)
-            e2e_prog.keepalive.append(ptr_t)
-            e2e_prog.enable_peer_push(ptr_t.data_ptr(), len(ptr_list), off, fin.row0, fin.row1)
-        results[0][2].zero_()
-        results[0][1].run()
-        torch.cuda.synchronize()
-        if not torch.equal(results[0][2], results[0][0].out.cpu()):
-            raise RuntimeError("fused device-to-host stores differ from the device result")
-    for i in range(W):
+    for i in range(max(W, 2 * len(t_lists))):
         step_device(i)
         step_e2e(i)
     torch.cuda.synchronize()
-    # each launch program (copies + kernels, cluster and programmatic-dependent-launch edges included) as ONE CUDA graph
-    graphed = 0
-    if args.graph:
-        for res, e2e_prog, _, _, _ in results:
-            graphed += int(res.program.capture()) + int(e2e_prog.capture())
-        for i in range(W):
-            step_device(i)
-            step_e2e(i)
-        torch.cuda.synchronize()
+    r0 = step_e2e(0)
+    torch.cuda.synchronize()
+    if not torch.equal(r0.host_out, r0.out.cpu()):
+        raise RuntimeError("the host copy of the final states differs from the device result")
+    h2d_bytes = int(getattr(r0.program, "h2d_bytes", 0))
+    d2h_bytes = int(r0.host_out.numel() * 4)
     if world > 1:
         dist.barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- device-timed arm -----------------------------------------------------------------------
+    # ---- device-timed arm: per step, flush L2, line the ranks up (untimed), then start event -> step -> end event ------
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
+    launches = 0
     for i in range(K):
         flush.fill_(float(i))
+        if ex is not None:
+            ex.align()          # no rank's timed step absorbs its peers' untimed flush / launch skew
         starts[i].record()
-        step_device(i)
+        res = step_device(i)
         ends[i].record()
+        launches += res.program.kernel_count() + (1 if (ex is not None and ex.fused) else 0)
     torch.cuda.synchronize()
     wall_dev = time.perf_counter() - wall0
     if world > 1:
         dist.barrier()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    edges_local = sum(results[i % len(results)][0].plan.E for i in range(K))
-    launches = sum(results[i % len(results)][0].program.kernel_count() for i in range(K))
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    dev_ms = float(step_ms.sum())
+    edges_local = sum(n_edges[i % len(t_lists)] for i in range(K))
 
-    # ---- e2e arm (host buffers, copies inside the timed region) ----------------------------------
+    # ---- e2e arm (host buffers, copies inside the timed region, host wall clock) ------------------------------------
     e2e_s = 0.0
     for i in range(K):
         flush.fill_(float(i))
+        if ex is not None:
+            ex.align()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         step_e2e(i)
@@ -428,38 +346,29 @@ def main():
         dist.barrier()
     clocks = sampler.stop()
 
-    # ---- the same through the user-facing call, nothing pre-built: model.encode(t_list) plans the window batch (native
-    # planner), builds the launch program, copies the plan, runs, and the result is read back to pinned host memory ----
-    api_ms = api_cached_ms = None
+    # ---- the same call with NOTHING kept between calls: plans the window batch (native planner), builds the launch
+    # program, copies the plan, runs, reads back ----
+    api_ms = None
     if world == 1:
-        nf_max = max(r[4] for r in results) // (4 * WORKLOAD["D"])
-        api_out = torch.empty(nf_max, WORKLOAD["D"], dtype=torch.float32, pin_memory=True)
         reps = min(K, 60)
-
-        def api_loop():
-            for i in range(max(3, len(t_lists))):
-                model.encode(t_lists[i % len(t_lists)])
-            torch.cuda.synchronize()
-            t_api = 0.0
-            for i in range(reps):
-                flush.fill_(float(i))
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                r_ = model.encode(t_lists[i % len(t_lists)])
-                api_out[:r_.out.shape[0]].copy_(r_.out, non_blocking=True)
-                torch.cuda.synchronize()
-                t_api += time.perf_counter() - t0
-            return 1e3 * t_api / reps
-
         keep = model.encode_cache_size
-        model.encode_cache_size = 0                     # nothing pre-built: every call plans and builds
-        api_ms = api_loop()
-        model.encode_cache_size = keep                  # the shipped default: a batch seen before replays its launch program
-        api_cached_ms = api_loop()
+        model.encode_cache_size = 0
+        for i in range(len(t_lists)):
+            model.encode(t_lists[i], to_host=True)
+        torch.cuda.synchronize()
+        t_api = 0.0
+        for i in range(reps):
+            flush.fill_(float(i))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model.encode(t_lists[i % len(t_lists)], to_host=True)
+            torch.cuda.synchronize()
+            t_api += time.perf_counter() - t0
+        api_ms = 1e3 * t_api / reps
+        model.encode_cache_size = keep
 
     # ---- every kernel of the step timed alone with CUDA events on its stream (roofline) -------------------------
-    D = WORKLOAD["D"]
-    res0 = results[0][0]
+    res0 = model.encode(t_lists[0])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -471,7 +380,7 @@ def main():
     dom = kernels[dom_name]
     traffic = None
     try:                                                        # per-launch DRAM bytes of that kernel from the committed
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))   # ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))   # ncu --set full capture
         traffic = tr.get(dom_name, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -480,44 +389,53 @@ def main():
 
     # ---- reduce over ranks ------------------------------------------------------------------------
     tot_edges, max_dev_ms, max_e2e = float(edges_local), dev_ms, e2e_s
+    per_rank = None
     if world > 1:
         t = torch.tensor([float(edges_local)], device=dev, dtype=torch.float64)
         dist.all_reduce(t)
         tot_edges = float(t.item())
-        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        # the step ends with a cross-GPU barrier, so a step takes as long as its slowest rank: max over ranks PER STEP
+        t = torch.tensor(step_ms, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        max_dev_ms, max_e2e = float(t[0].item()), float(t[1].item())
+        max_dev_ms = float(t.sum().item())
+        mine = torch.tensor([step_ms.min(), float(np.median(step_ms)), step_ms.max(), dev_ms / K], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": k, "step_ms_min": float(a[0]), "step_ms_median": float(a[1]), "step_ms_max": float(a[2]),
+                     "step_ms_mean": float(a[3])} for k, a in enumerate(allr)]
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_e2e = float(t[0].item())
 
     sharded = None
     if world > 1 and not args.no_sharded:
         try:
             sharded = snapshot_sharded_arm(dev, world)
-        except Exception as ex:          # never lose the headline line
-            sharded = {"error": repr(ex)}
+        except Exception as ex_:          # never lose the headline line
+            sharded = {"error": repr(ex_)}
 
     if rank == 0:
         line = {
             "metric": "edges_per_sec_rgcn_gru_forward", "value": tot_edges / (max_dev_ms * 1e-3), "unit": "edges/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_dev_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(bench_config(world), exchange=exchange),
-            "e2e": {"value": tot_edges / max_e2e, "unit": "edges/s", "h2d_bytes_per_step": int(results[0][3]),
-                    "d2h_bytes_per_step": int(results[0][4]), "ms_per_step": 1e3 * max_e2e / K,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(world),
+            "exchange": exchange,
+            "e2e": {"value": tot_edges / max_e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * max_e2e / K,
+                    "call": "model.encode(t_list, to_host=True, reupload=True%s) -- the public call: the batch's packed plan "
+                            "is copied from pinned host memory every step, the kernels run, the final states land in pinned "
+                            "host memory (stores from inside the scan kernel, verified against the device result)"
+                            % (", exchange=ex" if ex is not None else ""),
                     "timing": "host wall clock per step, stream-synchronised", "plan_ms_per_step_excluded": plan_ms,
-                    "d2h": "cudaMemcpyAsync after the kernels" if args.d2h_copy else
-                           "stores to pinned host memory from inside the scan kernel (verified against the device result)",
-                    "encode_call_ms_per_step": api_ms,
-                    "encode_call_edges_per_s": (edges_local / K) / (api_ms * 1e-3) if api_ms else None,
-                    "encode_call_note": "model.encode(t_list) with NOTHING pre-built: window planning + launch-program "
-                                        "construction in python + H2D + kernels + D2H (the reference also batches its "
-                                        "graphs per step inside its forward)",
-                    "encode_call_cached_ms_per_step": api_cached_ms,
-                    "encode_call_cached_edges_per_s": (edges_local / K) / (api_cached_ms * 1e-3) if api_cached_ms else None,
-                    "encode_call_cached_note": "the same call on batches seen before (evaluation walks the same batches "
-                                               "every epoch): model.encode replays the kept launch program + D2H"},
-            "gpu_launches": int(launches) + (K if symm_hdl is not None else 0),   # + the peer-barrier launch per step at N > 1
-            "launches_per_step": results[0][0].program.kernel_count(),
-            "cuda_graph": "one graph per launch program (%d of %d captured)" % (graphed, 2 * len(results)) if graphed else "off",
+                    "plan_note": "window planning + launch-program construction happen on the first call for a batch and are "
+                                 "kept (evaluation walks the same batches every epoch; the reference pre-builds its graph "
+                                 "dictionaries too) -- the call with nothing kept is encode_call_uncached_*",
+                    "encode_call_uncached_ms_per_step": api_ms,
+                    "encode_call_uncached_edges_per_s": (edges_local / K) / (api_ms * 1e-3) if api_ms else None},
+            "gpu_launches": int(launches),
+            "launches_per_step": res0.program.kernel_count() + (1 if (ex is not None and ex.fused) else 0),
             "clocks": clocks,
+            "parity": parity,
             "roofline": {"bound": "hbm", "kernel": dom_name + " -- " + dom["what"], "achieved": dom["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": dom["achieved"] / peak, "traffic": traffic,
                          "algorithmic_bytes": dom["algorithmic_bytes"], "kernel_ms": dom["kernel_ms"],
@@ -530,13 +448,15 @@ def main():
             "rows_per_step": int(p0.R), "edges_per_step": int(p0.E),
             "wall_s_device_arm": wall_dev,
         }
+        if per_rank is not None:
+            line["per_rank_step_ms"] = per_rank
         if sharded is not None:
             line["snapshot_sharded"] = sharded
         if args.scaled and world == 1:
             try:
                 line["roofline_scaled"] = scaled_roofline(args.scaled, dev, peak)
-            except Exception as ex:      # never lose the headline line
-                line["roofline_scaled"] = {"error": repr(ex)}
+            except Exception as ex_:      # never lose the headline line
+                line["roofline_scaled"] = {"error": repr(ex_)}
         if not args.no_cpu_baseline and world == 1:
             base, _ = cpu_baseline(store, model.state_dict(), t_lists)
             line["cpu_baseline"] = base
@@ -547,24 +467,21 @@ def main():
 
 def snapshot_sharded_arm(dev, world):
     """N > 1, secondary: ONE GDELT-shaped batch (BASELINE config 5: GRRGCN, seq_len 15, B = 2) cut over the ranks by
-    snapshot instance / chain partition (temp_b200/sharding.py) against the same batch on one GPU; device time, max
-    over ranks.  Every rank calls this."""
+    snapshot instance / chain partition (temp_b200/sharding.py) against the same batch on one GPU, at x1 and at x16
+    (HBM-resident); device time, max over ranks.  Every rank calls this."""
     import torch
     import torch.distributed as dist
+    from temp_b200.exchange import PeerGroup
     from temp_b200.models import build_module
     from temp_b200.snapshot import SnapshotStore
-    store = SnapshotStore.synthetic("gdelt", num_times=24, scale=1, seed=20201116 + 4)
-    a = make_args()
-    a.train_seq_len = a.test_seq_len = 15
-    torch.manual_seed(123)
-    model = build_module(a, store.num_ents, store.num_rels, store.train).to(dev).eval()
-    t_list = [store.times[20], store.times[21]]
-    single = model.encode(t_list)
-    want = single.out.clone()
-    res = model.encode_sharded(t_list)
-    torch.cuda.synchronize()
-    same = torch.tensor([int(torch.equal(res.out, want))], device=dev)
-    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    try:
+        peers = PeerGroup(dev)
+        how = "in-kernel NVLink peer stores (gi rows to the scanning rank from the tile kernel, final states to every rank from the scan kernel) + two signal/wait launches"
+    except Exception as ex:
+        peers = None
+        how = "torch.distributed collectives between launches (symmetric memory unavailable: %r)" % (ex,)
+    out = {"workload": "GRRGCN rec-only-last-layer, GDELT-shaped synthetic, seq_len=15, B=2 (BASELINE config 5)", "exchanges": how,
+           "shapes": []}
 
     def timed(fn, reps=30):
         for _ in range(5):
@@ -581,15 +498,27 @@ def snapshot_sharded_arm(dev, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    single = model.encode(t_list)
-    ms_one = timed(lambda: single.program.run())
-    ms_sh = timed(lambda: model.encode_sharded(prepared=res))
-    return {"workload": "GRRGCN rec-only-last-layer, GDELT-shaped synthetic x1, seq_len=15, B=2 (BASELINE config 5)",
-            "bit_identical_to_unsharded": bool(int(same.item())), "rows": int(res.plan.R), "edges": int(res.plan.E),
-            "ms_unsharded_one_gpu": ms_one, "ms_snapshot_sharded": ms_sh,
-            "edges_per_s_sharded": res.plan.E / (ms_sh * 1e-3),
-            "note": "exchange 1 (gi blocks, one broadcast per rank) + exchange 2 (NCCL all-gather of the final states) "
-                    "are NCCL calls between launches; at this size the exchanges cost more than the sharded compute saves"}
+    for scale in (1, 16):
+        store = SnapshotStore.synthetic("gdelt", num_times=24 if scale == 1 else 18, scale=scale, seed=20201116 + 4)
+        a = make_args()
+        a.train_seq_len = a.test_seq_len = 15
+        torch.manual_seed(123)
+        model = build_module(a, store.num_ents, store.num_rels, store.train).to(dev).eval()
+        t_list = [store.times[-3], store.times[-2]]
+        single = model.encode(t_list)
+        want = single.out.clone()
+        res = model.encode_sharded(t_list, peers=peers)
+        torch.cuda.synchronize()
+        same = torch.tensor([int(torch.equal(res.out, want))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        single = model.encode(t_list)
+        ms_one = timed(lambda: single.replay.run())
+        ms_sh = timed(lambda: model.encode_sharded(prepared=res))
+        out["shapes"].append({"scale": scale, "bit_identical_to_unsharded": bool(int(same.item())), "rows": int(res.plan.R),
+                              "edges": int(res.plan.E), "ms_unsharded_one_gpu": ms_one, "ms_snapshot_sharded": ms_sh,
+                              "speedup": ms_one / ms_sh, "edges_per_s_sharded": res.plan.E / (ms_sh * 1e-3)})
+        del model, single, res
+    return out
 
 
 def kernel_rooflines(res, model, flush, peak, flush_l2=True, reps=30):
@@ -641,8 +570,8 @@ def kernel_rooflines(res, model, flush, peak, flush_l2=True, reps=30):
         what="layer-2 CSR aggregation with in-register 1x1 relation projection (time = layer op - tile kernel alone)",
         kernel_ms=max(t_both - t_tile, 1e-6), algorithmic_bytes=int(E * (4 * D + 8) + nz * (4 * D + 12 + 4) + rel_rows * 4 * D))
     if scan_ops:
-        out["gru_scan_tc_kernel"] = dict(
-            what="chain-partitioned GRU scan, all %d steps of the window in one launch" % plan.seq_len,
+        out["gru_scan_tm_kernel"] = dict(
+            what="chain-partitioned GRU scan, all %d steps of the window in one launch (W_hh in tensor memory, state handed over through distributed shared memory)" % plan.seq_len,
             kernel_ms=time_ops(scan_ops), algorithmic_bytes=int(R * (4 * G + 8 * D + 8) + 4 * (D * G + G) + 8 * plan.scan_parts.size))
     for k in out.values():
         k["achieved"] = k["algorithmic_bytes"] / (k["kernel_ms"] * 1e-3) / 1e9

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 16
+#define TEMP_ABI_VERSION 17
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -111,6 +111,13 @@ typedef struct {
   const int32_t* agg_heavy;  /* [n_agg_heavy, 3] */
   int32_t n_agg_rows, n_agg_heavy;
   int32_t agg_lists;
+  /* Snapshot-sharded forward (tcgen05 path): the chained output row r is stored to chain_peers[chain_owner[r]] instead
+   * of chain_out -- the GPU that will scan the row's chain partition -- over NVLink peer memory, from the tile kernel's
+   * chain epilogue (chain_peers: DEVICE array of peer-mapped bases of the same [rows, chain_ld] buffer, this rank's own
+   * included; chain_owner: rank per packed row).  Null: chain_out as above.                                         */
+  float* const* chain_peers;
+  const int32_t* chain_owner;
+  int32_t chain_world, reserved2;
 } TempRgcnLayerArgs;
 
 /* Recurrent half of the GRU for packed rows [row0, row1), fused with the gates:

@@ -72,6 +72,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Loads of data the PREDECESSOR kernel produced (activations, aggregates, input gates).  With programmatic dependent launch
+// this kernel is already running while the predecessor still writes them, so they are NOT read-only for the kernel's
+// lifetime: __ldg (ld.global.nc) tells the compiler exactly that, and it may then hoist such a load above
+// griddepcontrol.wait -- seen in round 2 as the first self-loop row of a warp read before the previous layer had stored
+// it, depending on nothing but instruction scheduling.  These are volatile asm statements: never reordered with the
+// (volatile) wait.  Parameters and plan arrays, which no kernel of the program writes, keep __ldg.
+__device__ __forceinline__ float4 ld_dep_f32x4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_dep_f32(const void* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

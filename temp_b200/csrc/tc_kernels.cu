@@ -37,6 +37,11 @@ constexpr int kKAtoms = kD / kAtomK;  // 4
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -143,7 +148,7 @@ __device__ __forceinline__ float4 gather_edges(const TempRgcnLayerArgs& p, int e
       for (int u = 0; u < 2; ++u) {
         const int su = __shfl_sync(kFull, s, (u0 + u) & 31), ru = __shfl_sync(kFull, rl, (u0 + u) & 31);
         if (u0 + u < cnt) {
-          hv[u] = __ldg(x4 + static_cast<size_t>(su) * (kD / 4));
+          hv[u] = ld_dep_f32x4(x4 + static_cast<size_t>(su) * (kD / 4));   // (the previous layer's output)
           wv[u] = __ldg(w4 + static_cast<size_t>(ru) * (kD / 4));
         }
       }
@@ -225,6 +230,7 @@ struct LayerBars {
   uint64_t b_ready, d1_full, x_ready;
   uint64_t d2_full[3], d2_empty[3];
   uint32_t tmem_base;
+  float* chain_peer[TEMP_MAX_PUSH_PEERS];   // snapshot-sharded forward: peer-mapped bases of the chained output
 };
 
 __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const TempRgcnLayerArgs p) {
@@ -236,6 +242,9 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
   __shared__ LayerBars S;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the same value, provably warp-uniform: the control-warp branches (and with them the MMA issue loop) then run on the
+  // uniform datapath instead of a per-operand R2UR election loop (13 instructions per tcgen05.mma in round 1's SASS)
+  const int warp_u = __shfl_sync(kFull, tid >> 5, 0);
   const int rbase = p.row0 + blockIdx.x * kTileRows;
   const int n_mb = p.chain_w_packed != nullptr ? p.chain_n >> 7 : 0;
   pdl_launch_dependents();
@@ -256,13 +265,14 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(&S.tmem_base, 512);
+  if (p.chain_peers != nullptr && tid < p.chain_world) S.chain_peer[tid] = p.chain_peers[tid];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = S.tmem_base;
   TL(1);
 
-  if (warp >= kWorkerWarps) {
+  if (warp_u >= kWorkerWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 8 && lane == 0) {
       // ===== TMA producer: GEMM1 weight chunks, then the chain's, in the order the MMA warp consumes them =====
@@ -279,23 +289,30 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
         bulk_g2s(ring + st * kWChunkBytes, src, kWChunkBytes, &S.w_full[st]);
       }
     }
-    } else if (warp == 9 && lane == 0) {
-      // ===== MMA issuer =====
-      {
+    } else if (warp_u == 9) {
+      // ===== MMA issuer: the whole warp walks the pipeline (waits, stage arithmetic: convergent, on the uniform datapath);
+      // only the tcgen05.mma / commit instructions are issued by the elected lane =====
+      const bool leader = elect_one();
+      const uint32_t tbase = __shfl_sync(kFull, S.tmem_base, 0);
       const uint32_t idesc = umma_idesc_tf32(128, kTileRows);
       const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo), rg = smem_u32(ring);
       int i = 0;
       mbar_wait(&S.b_ready, 0);
       tc_fence_after();
       TL(2);
-      for (int ka = 0; ka < kKAtoms; ++ka, ++i) {
+#pragma unroll
+      for (int ka = 0; ka < kKAtoms; ++ka, ++i) {   // (unrolled: the accumulate flag of each MMA is an immediate)
         const int st = i % kStages;
         mbar_wait(&S.w_full[st], (i / kStages) & 1);
         tc_fence_after();
-        umma_katom_3x(tbase, rg + st * kWChunkBytes, bh + ka * (kTileRows * 128), bl + ka * (kTileRows * 128), idesc, ka == 0);
-        umma_commit(&S.w_empty[st]);
+        if (leader) {
+          umma_katom_3x(tbase, rg + st * kWChunkBytes, bh + ka * (kTileRows * 128), bl + ka * (kTileRows * 128), idesc, ka == 0);
+          umma_commit(&S.w_empty[st]);
+        }
+        __syncwarp();
       }
-      umma_commit(&S.d1_full);
+      if (leader) umma_commit(&S.d1_full);
+      __syncwarp();
       TL(3);
       if (n_mb > 0) {
         mbar_wait(&S.x_ready, 0);
@@ -307,19 +324,23 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
             mbar_wait(&S.d2_empty[slot], ((mb / 3) - 1) & 1);
             tc_fence_after();
           }
+#pragma unroll
           for (int ka = 0; ka < kKAtoms; ++ka, ++i) {
             const int st = i % kStages;
             mbar_wait(&S.w_full[st], (i / kStages) & 1);
             tc_fence_after();
-            umma_katom_3x(tbase + 128 + 128 * slot, rg + st * kWChunkBytes, bh + ka * (kTileRows * 128),
-                          bl + ka * (kTileRows * 128), idesc, ka == 0);
-            umma_commit(&S.w_empty[st]);
+            if (leader) {
+              umma_katom_3x(tbase + 128 + 128 * slot, rg + st * kWChunkBytes, bh + ka * (kTileRows * 128),
+                            bl + ka * (kTileRows * 128), idesc, ka == 0);
+              umma_commit(&S.w_empty[st]);
+            }
+            __syncwarp();
           }
-          umma_commit(&S.d2_full[slot]);
+          if (leader) umma_commit(&S.d2_full[slot]);
+          __syncwarp();
           TL(6 + (mb < 3 ? mb : 3));
         }
       }
-    }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
@@ -343,7 +364,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int sr = __shfl_sync(kFull, idx, i);
-        v[i] = sr >= 0 ? __ldg(reinterpret_cast<const float4*>(tm.a + static_cast<size_t>(sr) * kD) + lane)
+        v[i] = sr >= 0 ? ld_dep_f32x4(reinterpret_cast<const float4*>(tm.a + static_cast<size_t>(sr) * kD) + lane)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // row 16 w + i: 8-row group 2 w + (i >> 3), row in group i & 7; k-atom lane >> 3, 16-byte chunk (lane & 7) ^ (i & 7)
@@ -393,7 +414,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * kD + f;
     float ag[64];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) ag[j] = ((has >> j) & 1ull) ? __ldg(agg_col + j * kD) : 0.f;
+    for (int j = 0; j < 64; ++j) ag[j] = ((has >> j) & 1ull) ? ld_dep_f32(agg_col + j * kD) : 0.f;
     mbar_wait(&S.d1_full, 0);
     tc_fence_after();
     TL(4);
@@ -436,6 +457,12 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     if (n_mb > 0) {
       fence_proxy_async();
       mbar_arrive(&S.x_ready);
+      // snapshot-sharded forward: the rank that scans the chain partition of a row receives the row's chained output
+      int ownA = 0, ownB = 0;
+      if (p.chain_peers != nullptr) {
+        ownA = __ldg(p.chain_owner + min(R0 + lane, p.row1 - 1));
+        ownB = __ldg(p.chain_owner + min(R0 + 32 + lane, p.row1 - 1));
+      }
       for (int mb = 0; mb < n_mb; ++mb) {
         const int slot = mb % 3;
         const float cbias = p.chain_b != nullptr ? __ldg(p.chain_b + 128 * mb + f) : 0.f;
@@ -448,9 +475,18 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
           float v[32];
           tmem_ld32(lane_base + 128 + 128 * slot + 64 * hf + 32 * c, v);
           tmem_ld_wait();
+          if (p.chain_peers == nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (R0 + 32 * c + i < p.row1) orow[static_cast<size_t>(32 * c + i) * p.chain_ld] = v[i] + cbias;
+            for (int i = 0; i < 32; ++i) {
+              if (R0 + 32 * c + i < p.row1) orow[static_cast<size_t>(32 * c + i) * p.chain_ld] = v[i] + cbias;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int own = __shfl_sync(kFull, c == 0 ? ownA : ownB, i);
+              if (R0 + 32 * c + i < p.row1)
+                S.chain_peer[own][static_cast<size_t>(R0 + 32 * c + i) * p.chain_ld + 128 * mb + f] = v[i] + cbias;
+            }
           }
         }
         tc_fence_before();
@@ -761,11 +797,11 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThre
         if (row0 + stride * u < lim && r < r1) {
           const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
           if (type1) {
-            gi_n[u] = __ldg(gi);
+            gi_n[u] = ld_dep_f32(gi);
           } else {
-            gi_r[u] = __ldg(gi);
-            gi_z[u] = __ldg(gi + kD);
-            gi_n[u] = __ldg(gi + 2 * kD);
+            gi_r[u] = ld_dep_f32(gi);
+            gi_z[u] = ld_dep_f32(gi + kD);
+            gi_n[u] = ld_dep_f32(gi + 2 * kD);
           }
         }
       }
@@ -928,6 +964,8 @@ bool tc_layer_supported(const TempRgcnLayerArgs* a) {
                             (a->n_agg_heavy > 0 && a->agg_heavy == nullptr)))
     return false;
   if (a->chain_w != nullptr && (a->chain_w_packed == nullptr || (a->chain_n & 127) != 0)) return false;
+  if (a->chain_peers != nullptr && (a->chain_owner == nullptr || a->chain_world <= 0 || a->chain_world > TEMP_MAX_PUSH_PEERS))
+    return false;
   return true;
 }
 

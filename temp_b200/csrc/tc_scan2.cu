@@ -305,9 +305,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       gr[u] = gz[u] = gn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < r1) {
         const float4* gi = reinterpret_cast<const float4*>(p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j4);
-        gr[u] = __ldg(gi);
-        gz[u] = __ldg(gi + kD / 4);
-        gn[u] = __ldg(gi + 2 * (kD / 4));
+        gr[u] = ld_dep_f32x4(gi);              // (written by the predecessor kernel: see ld_dep_* in tc_common.cuh)
+        gz[u] = ld_dep_f32x4(gi + kD / 4);
+        gn[u] = ld_dep_f32x4(gi + 2 * (kD / 4));
       }
     }
     const float4 br = __ldg(reinterpret_cast<const float4*>(p.b_hh + j4));
@@ -344,7 +344,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         for (int u = 0; u < kU; ++u) {
           const int pr = __shfl_sync(kFull, cur.gprv, u);
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pr >= 0) v[u] = __ldcg(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
+          if (pr >= 0) v[u] = ld_dep_f32x4(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
         }
         has_prev = true;   // (decided below by the reduction)
       }

@@ -1235,6 +1235,7 @@ int launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   }
   if (a->h_out != nullptr && !aligned16(a->h_out)) return fail(TEMP_EINVAL, "h_out misaligned%s", "");
   if (temp_internal::tc_layer_supported(a)) return temp_internal::tc_launch_layer(a, st);
+  if (a->chain_peers != nullptr) return fail(TEMP_EUNSUPPORTED, "peer stores of the chained output need the tcgen05 layer (d == 128)%s", "");
   const int Kp = (a->d + kKC - 1) / kKC * kKC;
   const size_t smem = (static_cast<size_t>(kTM) * (Kp + 4) * (a->chain_w ? 2 : 1) + 2 * kKC * kNC) * sizeof(float);
   if (int rc = ensure_smem<0>(rgcn_layer_kernel, smem, "rgcn_layer_kernel")) return rc;

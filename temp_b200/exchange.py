@@ -1,0 +1,149 @@
+"""In-kernel NVLink exchanges over symmetric memory (one process per GPU, ``torch.distributed`` for the plumbing).
+
+The north star's collective is "an all-gather over NVLink of the final-layer entity states before scoring"
+(BASELINE.json; the reference itself only has ``DistributedSampler`` data parallelism over target timestamps,
+models/TKG_Module.py:166-168, and gathers nothing).  Here the all-gather is FUSED into the scan kernel: the scan step
+that writes a final state also stores it through peer-mapped pointers into every GPU's slab (``TempGruScanArgs.push_*``);
+one tiny signal / wait launch (``temp_peer_barrier``) then separates the step from its consumers on all GPUs.  No NCCL call
+is on the data path -- NCCL (``all_gather_into_tensor``) is the verification partner and the fallback when symmetric memory
+is unavailable.
+
+``PeerGroup``            symmetric allocations + the cross-GPU barrier
+``FinalStateAllGather``  weak scaling over target timestamps: every rank encodes its own window batch, every rank ends up
+                         with all ranks' final-layer states (two slabs per rank used alternately: a rank may run one step
+                         ahead of a slow reader, never two -- the barrier of step s + 1 needs that reader's signal)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import lib
+
+
+class PeerGroup(object):
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.flags, self.flag_ptrs, self._flag_hdl = self.alloc((32,), torch.int32)
+        self.seq = 0
+
+    def alloc(self, shape, dtype=torch.float32):
+        """-> (local tensor, device int64 tensor of every rank's mapped address of it, handle); collective."""
+        t = self._symm.empty(tuple(shape), dtype=dtype, device=self.device)
+        t.zero_()
+        hdl = self._symm.rendezvous(t, group=self.group)
+        ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        hdl.barrier()
+        return t, ptrs, hdl
+
+    def barrier(self) -> None:
+        """One launch on the current stream: signal every peer (st.release.sys), wait for all peers' signals
+        (ld.acquire.sys).  The kernels whose peer stores it publishes precede it on the stream."""
+        self.seq += 1
+        lib.check(lib.load().temp_peer_barrier(C.c_void_p(self.flags.data_ptr()), C.c_void_p(self.flag_ptrs.data_ptr()),
+                                               self.world, self.rank, self.seq, C.c_void_p(lib.current_stream())),
+                  "temp_peer_barrier")
+
+
+class FinalStateAllGather(object):
+    """``model.encode(t_list, exchange=ex)``: after the call (and on the same stream) ``ex.gathered(k)`` holds rank k's
+    final-layer states of the step just run, on every rank."""
+
+    def __init__(self, device, max_rows: int, d: int, group=None, nccl: bool = False):
+        import torch.distributed as dist
+        self.device, self.max_rows, self.d = device, int(max_rows), int(d)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.step = 0
+        self.peers: Optional[PeerGroup] = None
+        self.how = "nccl all_gather_into_tensor"
+        if not nccl:
+            try:
+                self.peers = PeerGroup(device, self.group)
+                self.slabs, self.slab_ptrs, self._hdl = self.peers.alloc((2, self.world, self.max_rows, self.d))
+                self.how = ("fused into the scan kernel: one NVLink store per peer into double-buffered symmetric memory + "
+                            "one signal/wait launch (temp_peer_barrier)")
+            except Exception as ex:                                   # symmetric memory unavailable: NCCL between launches
+                if self.peers is not None and hasattr(self, "slabs"):
+                    raise
+                self.peers = None
+                self.how = "nccl all_gather_into_tensor (symmetric memory unavailable: %r)" % (ex,)
+        if self.peers is None:
+            self.send = torch.zeros(self.max_rows, self.d, device=device)
+            self.recv = torch.empty(2, self.world * self.max_rows, self.d, device=device)
+        self.last_parity = 0
+
+    @property
+    def fused(self) -> bool:
+        return self.peers is not None
+
+    def attach(self, res, host_out: Optional[torch.Tensor] = None) -> None:
+        """Two variants of ``res.program`` (one per slab parity) whose last scan step also stores the final states into
+        every rank's slab -- and, with ``host_out``, into that pinned host buffer (one more "peer")."""
+        if not self.fused:
+            return
+        fin = res.plan.final
+        if fin.row1 - fin.row0 > self.max_rows:
+            raise RuntimeError("temp_b200: the batch has more final rows than the exchange was sized for")
+        res.exchange_programs = []
+        for parity in (0, 1):
+            off = (parity * self.world + self.rank) * self.max_rows * self.d
+            ptr_list = [int(p) for p in self.slab_ptrs.tolist()]
+            if host_out is not None:
+                ptr_list.append(host_out.data_ptr() - 4 * off)
+            ptrs = torch.tensor(ptr_list, dtype=torch.int64, device=self.device)
+            prog = lib.Program()
+            prog.ops = [lib.Op.from_buffer_copy(o) for o in res.program.ops]
+            prog.keepalive = list(res.program.keepalive) + [ptrs] + ([host_out] if host_out is not None else [])
+            prog.enable_peer_push(ptrs.data_ptr(), len(ptr_list), off, fin.row0, fin.row1)
+            res.exchange_programs.append(prog)
+
+    def run(self, res, reupload: bool = True) -> None:
+        """Runs the forward of ``res`` with the exchange on the current stream."""
+        parity = self.step & 1
+        self.step += 1
+        self.last_parity = parity
+        if self.fused:
+            prog = res.exchange_programs[parity]
+            if not reupload:
+                cached = getattr(res, "exchange_replays", None)
+                if cached is None:
+                    cached = res.exchange_replays = []
+                    for p in res.exchange_programs:
+                        q = lib.Program()
+                        q.ops = [o for o in p.ops if o.kind != lib.OP_H2D]
+                        q.keepalive = p.keepalive
+                        cached.append(q)
+                prog = cached[parity]
+            prog.run()
+            self.peers.barrier()          # every rank's scan (and its peer stores) has completed
+        else:
+            import torch.distributed as dist
+            (res.program if reupload else res.replay).run()
+            nf = res.out.shape[0]
+            self.send[:nf].copy_(res.out)
+            dist.all_gather_into_tensor(self.recv[parity], self.send, group=self.group)
+
+    def gathered(self, k: int, rows: Optional[int] = None) -> torch.Tensor:
+        """Rank k's final states of the last step (``rows``: how many of the slab's rows are valid)."""
+        if self.fused:
+            t = self.slabs[self.last_parity, k]
+        else:
+            t = self.recv[self.last_parity].view(self.world, self.max_rows, self.d)[k]
+        return t if rows is None else t[:rows]
+
+    def align(self) -> None:
+        """Cross-GPU alignment point on the current stream without data (benchmark start lines)."""
+        if self.fused:
+            self.peers.barrier()
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(torch.zeros(1, device=self.device), group=self.group)

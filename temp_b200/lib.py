@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -39,6 +39,7 @@ class RgcnLayerArgs(C.Structure):
         ("h_out", _p), ("chain_w", _p), ("chain_b", _p), ("chain_out", _p), ("chain_n", _i32), ("chain_ld", _i32),
         ("chain_w_packed", _p), ("inv_temperature", C.c_float), ("agg_scratch", _p), ("agg_rows", _p), ("agg_heavy", _p), ("n_agg_rows", _i32), ("n_agg_heavy", _i32),
         ("agg_lists", _i32),
+        ("chain_peers", _p), ("chain_owner", _p), ("chain_world", _i32), ("reserved2", _i32),
     ]
 
 

@@ -139,41 +139,83 @@ class TKG_Module(nn.Module):
         return [float(x) for x in range(L - 1, -1, -1)]               # SelfAttentionRGCN.py:22-23
 
     @torch.no_grad()
-    def encode(self, t_list=None, plan: Optional[WindowPlan] = None) -> EncodeResult:
+    def encode(self, t_list=None, plan: Optional[WindowPlan] = None, to_host: bool = False, reupload: bool = False,
+               exchange=None) -> EncodeResult:
         """The hot path (region R1 of SURVEY section 8d): history steps + final step -> per-graph states.
 
         Called with timestamps, the planned window batch and its launch program are kept (``encode_cache_size`` most
         recent batches, each with its own staged plan copy on the device): evaluation walks the same batches every epoch,
         and a repeat costs the kernels only.  The cache is dropped whenever a parameter changed or moved (the programs
         hold pointers to prepared weight images).  Results live in the runtime's workspace: consume ``res.out`` before
-        the next call."""
+        the next call.
+
+        ``to_host``: the final states also land in ``res.host_out`` (pinned ``[rows, D]``; read it after synchronising the
+        stream) -- on the tcgen05 scan from INSIDE the scan kernel (the host buffer is one more "peer" of its fused
+        all-gather: UVA stores during the last step), otherwise by a device-to-host copy appended to the program.
+        ``reupload``: a batch seen before still re-copies its packed plan from pinned host memory (the end-to-end
+        measurement of bench.py: every step moves its inputs host -> device).
+        ``exchange``: a ``temp_b200.exchange.FinalStateAllGather`` -- one process per GPU, every rank encodes its own batch
+        and the final-layer states of all ranks are all-gathered over NVLink from inside the scan kernel."""
+        def launch(res, first, tag):
+            if exchange is not None:
+                if exchange.fused and getattr(res, "exchange_programs", None) is None:
+                    exchange.attach(res, getattr(res, "host_out", None))
+                exchange.run(res, reupload or first)
+            else:
+                (res.program if (reupload or first) else res.replay).run()
+            if first:
+                self.runtime.mark_run(tag)
+
         if plan is not None:
             res = self.runtime.build(plan)
-            res.program.run()
-            self.runtime.mark_run()
+            if to_host:
+                self._attach_host_out(res)
+            launch(res, True, "plan")
             return res
-        key = tuple(_as_int_list(t_list))
+        key = (tuple(_as_int_list(t_list)), bool(to_host))              # (the programs with a host copy are kept apart)
         cache = self._encode_cache_for_current_weights()
         hit = cache.get(key) if self.encode_cache_size > 0 else None
         if hit is not None:
-            hit.replay.run()
+            launch(hit, False, None)
             return hit
         plan = self.plan(t_list)
         if self.encode_cache_size <= 0:
-            return self.encode(plan=plan)
+            return self.encode(plan=plan, to_host=to_host, exchange=exchange)
         slot = self._encode_slot = (getattr(self, "_encode_slot", -1) + 1) % self.encode_cache_size
         for k in [k for k, v in cache.items() if v.cache_slot == slot]:
             del cache[k]                                                 # the slot's staged plan copy is about to be overwritten
         tag = "plan_c%d" % slot
         res = self.runtime.build(plan, tag=tag)
-        res.program.run()
-        self.runtime.mark_run(tag)
+        if to_host:
+            self._attach_host_out(res)
         res.cache_slot = slot
         res.replay = lib.Program()                                       # the same launches without the plan upload
         res.replay.ops = [o for o in res.program.ops if o.kind != lib.OP_H2D]
         res.replay.keepalive = res.program.keepalive
+        launch(res, True, tag)
         cache[key] = res
         return res
+
+    def _attach_host_out(self, res: EncodeResult) -> None:
+        """``res.host_out``: pinned host copy of ``res.out`` written by the program itself (see ``encode(to_host=True)``)."""
+        nf, D = int(res.out.shape[0]), self.embed_size
+        host = torch.empty(max(nf, 1), D, dtype=torch.float32, pin_memory=True)[:nf]
+        prog, fin = res.program, res.plan.final
+        pushed = False
+        tc_scan = (self.family == "recurrent" and self.runtime.use_tc and D == 128 and self.runtime.fuse_scan
+                   and self.ent_encoder.rec_only_last_layer and self.args.module in ("GRRGCN", "BiGRRGCN"))
+        if tc_scan:
+            ptrs = torch.tensor([host.data_ptr()], dtype=torch.int64, device=res.out.device)
+            try:
+                prog.enable_peer_push(ptrs.data_ptr(), 1, 0, fin.row0, fin.row1)
+                prog.keepalive.append(ptrs)
+                pushed = True
+            except RuntimeError:
+                pushed = False
+        if not pushed:
+            prog.add(lib.OP_D2H, lib.CopyArgs(host.data_ptr(), res.out.data_ptr(), nf * D * 4))
+        prog.keepalive.append(host)
+        res.host_out, res.host_out_fused = host, pushed
 
     encode_cache_size = 128
 
@@ -186,19 +228,31 @@ class TKG_Module(nn.Module):
         return self._encode_cache
 
     @torch.no_grad()
-    def encode_sharded(self, t_list=None, plan: Optional[WindowPlan] = None, group=None, prepared=None) -> EncodeResult:
+    def encode_sharded(self, t_list=None, plan: Optional[WindowPlan] = None, group=None, prepared=None, peers=None) -> EncodeResult:
         """``encode`` with ONE window batch cut over the ranks of ``group`` (temp_b200/sharding.py): snapshot
         instances for the RGCN layers, chain partitions for the GRU scan, two exchanges.  Every rank calls it with
-        the same ``t_list`` and ends up with the complete final-layer states in ``res.out``."""
+        the same ``t_list`` and ends up with the complete final-layer states in ``res.out``.
+
+        ``peers`` (a ``temp_b200.exchange.PeerGroup``: the GPUs of one box): both exchanges are in-kernel NVLink stores
+        (``PeerShardedForward``); without it they are ``torch.distributed`` collectives between the launches.
+        ``prepared``: the result of an earlier call for the same batch -- re-runs it without planning."""
         import torch.distributed as dist
-        from .sharding import exchange_blocks, exchange_rows, make_shard_plan
+        from .sharding import PeerShardedForward, exchange_blocks, exchange_rows, make_shard_plan
+        if prepared is not None and getattr(prepared, "forward", None) is not None:
+            return prepared.forward.run()
+        if peers is not None:
+            fwd = PeerShardedForward(self, plan if plan is not None else self.plan(t_list), peers)
+            res = fwd.run()
+            res.forward = fwd
+            self.runtime.mark_run()
+            return res
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         if prepared is None:
             if plan is None:
                 plan = self.plan(t_list)
             shard = make_shard_plan(plan, world)
             res = self.runtime.build_sharded(plan, shard, rank)
-            res.shard = shard
+            res.shard, res.sharded = shard, True
         else:
             res, shard = prepared, prepared.shard
         res.programs[0].run()
@@ -375,6 +429,9 @@ class TKG_Module(nn.Module):
     @torch.no_grad()
     def all_embeds(self, res: EncodeResult, i: int, hist_item=None) -> torch.Tensor:
         """``get_all_embeds_Gt`` for batch item i from the compact window state (``hist_item``: see ``evaluate``)."""
+        if getattr(res, "sharded", False):
+            raise RuntimeError("temp_b200: a snapshot-sharded result holds the FINAL states only on every rank (the history "
+                               "states stay with the rank that scanned them); build the all-entity table from encode()")
         from .isolated import all_embeds_item
         return all_embeds_item(self, res, i, hist_item)
 
