@@ -159,6 +159,33 @@ class RRGCN(_TwoLayer):
         return isolated_step(self, ent_embeds, time, [first_prev_graph_embeds], [second_prev_graph_embeds],
                              [time_diff_tensor], ["f"])
 
+    # post-ensemble / impute calls (the Impute* / PostEnsemble* drivers of models/PostDynamicRGCN.py; GRU flavour)
+    def forward_post_ensemble(self, batched_graph, first_prev_graph_embeds, second_prev_graph_embeds, time_diff_tensor,
+                              time_batched_list_t, node_sizes=None):
+        """models/RRGCN.py:219-234 -> (second_local, first, second): the layer-2 output BEFORE the cell ("local"
+        stream) next to the recurrent states, every one with the layer-2 time embedding."""
+        from .stepwise import graph_step
+        return graph_step(self, batched_graph, time_batched_list_t, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                          [time_diff_tensor], ["f"], want_local=True)
+
+    def forward_post_ensemble_isolated(self, ent_embeds, first_prev_graph_embeds, second_prev_graph_embeds, time_diff_tensor,
+                                       time, pre_embeds_loc):
+        """models/RRGCN.py:236-254 -> (second_local, second) over all rows of ``ent_embeds``."""
+        from .stepwise import isolated_step
+        return isolated_step(self, ent_embeds, time, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                             [time_diff_tensor], ["f"], mode="post", locs=[pre_embeds_loc])
+
+    def forward_isolated_impute(self, ent_embeds, first_prev_graph_embeds, second_prev_graph_embeds, time_diff_tensor, time,
+                                pre_embeds_loc):
+        """models/RRGCN.py:256-269."""
+        from .stepwise import isolated_step
+        return isolated_step(self, ent_embeds, time, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                             [time_diff_tensor], ["f"], mode="impute", locs=[pre_embeds_loc])
+
+    def calc_impute_weight(self, time_diff_tensor):
+        """models/RRGCN.py:271-272."""
+        return torch.exp(-torch.clamp(self.impute_weight(time_diff_tensor), min=0))
+
 
 class BiRRGCN(_TwoLayer):
     """models/BiRRGCN.py:188-208 (layer 2 uses relu, unlike RRGCN)."""
@@ -200,6 +227,48 @@ class BiRRGCN(_TwoLayer):
                              [second_prev_graph_embeds_forward, second_prev_graph_embeds_backward],
                              [time_diff_tensor_forward, time_diff_tensor_backward], ["f", "b"])
 
+    # post-ensemble / impute calls (the Impute* / PostEnsemble* drivers of models/PostBiDynamicRGCN.py; GRU flavour)
+    def forward_post_ensemble(self, batched_graph, first_prev_graph_embeds_forward, second_prev_graph_embeds_forward,
+                              time_diff_tensor_forward, first_prev_graph_embeds_backward, second_prev_graph_embeds_backward,
+                              time_diff_tensor_backward, time_batched_list_t, node_sizes=None):
+        """models/BiRRGCN.py:259-275 (centre step) -> (second_local, second)."""
+        from .stepwise import graph_step
+        local, _, second = graph_step(self, batched_graph, time_batched_list_t,
+                                      [first_prev_graph_embeds_forward, first_prev_graph_embeds_backward],
+                                      [second_prev_graph_embeds_forward, second_prev_graph_embeds_backward],
+                                      [time_diff_tensor_forward, time_diff_tensor_backward], ["f", "b"], want_local=True)
+        return local, second
+
+    def forward_post_ensemble_one_direction(self, batched_graph, first_prev_graph_embeds, second_prev_graph_embeds,
+                                            time_diff_tensor, time_batched_list_t, node_sizes=None, forward=True):
+        """models/BiRRGCN.py:277-293 (history steps) -> (second_local, first, second)."""
+        from .stepwise import graph_step
+        return graph_step(self, batched_graph, time_batched_list_t, [first_prev_graph_embeds], [second_prev_graph_embeds],
+                          [time_diff_tensor], ["f" if forward else "b"], want_local=True)
+
+    def forward_post_ensemble_isolated(self, ent_embeds, first_prev_graph_embeds_forward, second_prev_graph_embeds_forward,
+                                       time_diff_tensor_forward, first_prev_graph_embeds_backward,
+                                       second_prev_graph_embeds_backward, time_diff_tensor_backward, time,
+                                       second_embeds_forward_loc, second_embeds_backward_loc):
+        """models/BiRRGCN.py:295-319 -> (second_local, second)."""
+        from .stepwise import isolated_step
+        return isolated_step(self, ent_embeds, time,
+                             [first_prev_graph_embeds_forward, first_prev_graph_embeds_backward],
+                             [second_prev_graph_embeds_forward, second_prev_graph_embeds_backward],
+                             [time_diff_tensor_forward, time_diff_tensor_backward], ["f", "b"], mode="post",
+                             locs=[second_embeds_forward_loc, second_embeds_backward_loc])
+
+    def forward_isolated_impute(self, ent_embeds, first_prev_graph_embeds_forward, second_prev_graph_embeds_forward,
+                                time_diff_tensor_forward, first_prev_graph_embeds_backward, second_prev_graph_embeds_backward,
+                                time_diff_tensor_backward, time, second_embeds_forward_loc, second_embeds_backward_loc):
+        """models/BiRRGCN.py:321-338."""
+        from .stepwise import isolated_step
+        return isolated_step(self, ent_embeds, time,
+                             [first_prev_graph_embeds_forward, first_prev_graph_embeds_backward],
+                             [second_prev_graph_embeds_forward, second_prev_graph_embeds_backward],
+                             [time_diff_tensor_forward, time_diff_tensor_backward], ["f", "b"], mode="impute",
+                             locs=[second_embeds_forward_loc, second_embeds_backward_loc])
+
 
 class SARGCN(_TwoLayer):
     """models/SARGCN.py:86-101 (forces use_time_embedding, line 92)."""
@@ -229,3 +298,15 @@ class SARGCN(_TwoLayer):
         from .stepwise import attention_isolated_step
         return attention_isolated_step(self, ent_embeds, first_layer_prev_embeddings, second_layer_prev_embeddings,
                                        time_diff, local_attn_mask, time)
+
+    def forward_post_ensemble(self, batched_graph, second_layer_prev_embeddings, time_diff, local_attn_mask, time_batched_list_t,
+                              node_sizes=None):
+        """models/SARGCN.py:137-141 (the --post-aggregation return of the layer, SARGCN.py:44-45) -> (second_local, attention)."""
+        from .stepwise import attention_post_ensemble_step
+        return attention_post_ensemble_step(self, batched_graph, second_layer_prev_embeddings, time_diff, local_attn_mask,
+                                            time_batched_list_t)
+
+    def forward_isolated_post_ensemble(self, ent_embeds, second_layer_prev_embeddings, time_diff, local_attn_mask, time):
+        """models/SARGCN.py:143-146 -> (second_local, attention) over all rows of ``ent_embeds``."""
+        from .stepwise import attention_isolated_post_ensemble_step
+        return attention_isolated_post_ensemble_step(self, ent_embeds, second_layer_prev_embeddings, time_diff, local_attn_mask, time)

@@ -63,6 +63,15 @@ class TKG_Module(nn.Module):
                              "models/DynamicRGCN.py:41-48)")
         if self.embed_size % args.n_bases != 0:
             raise ValueError("n_bases must divide embed_size (models/RGCN.py:25-26)")
+        # reference hyper-parameters that change the computation and are NOT built: refuse instead of returning different numbers
+        for flag, why in (("use_embed_for_non_active", "the all-entity table always runs forward_isolated"),
+                          ("edge_dropout", "frequency-driven edge dropout (utils/DropEdge.py:84-146) is not built"),
+                          ("EMA", "the exponential-moving-average variants (models/SARGCN.py:64-82) are not built")):
+            if getattr(args, flag, False):
+                raise NotImplementedError("temp_b200: --%s is not supported: %s" % (flag.replace("_", "-"), why))
+        if int(getattr(args, "num_layers", 1)) != 1:
+            raise NotImplementedError("temp_b200: num_layers must be 1 (the kernels implement the one-layer GRU of every shipped "
+                                      "configuration; a stacked nn.GRU would be accepted by the reference, models/RRGCN.py:75)")
         self.use_cuda = getattr(args, "use_cuda", True)
         self.num_pos_facts = getattr(args, "num_pos_facts", 3000)
         self.negative_rate = getattr(args, "negative_rate", 500)
@@ -633,5 +642,21 @@ MODULES = {"SRGCN": StaticRGCN, "GRRGCN": DynamicRGCN, "RRGCN": DynamicRGCN, "Bi
 
 
 def build_module(args, num_ents, num_rels, graph_dict_train, graph_dict_val=None, graph_dict_test=None):
-    """The module table of main.py:42-55 restricted to the families on the hot path."""
-    return MODULES[args.module](args, num_ents, num_rels, graph_dict_train, graph_dict_val, graph_dict_test)
+    """The module table of main.py:42-79 restricted to the families on the hot path: ``--post-ensemble`` / ``--impute`` select
+    the PostEnsemble* / Impute* shells for the (Bi)DynamicRGCN modules and are ignored for the attention models, exactly as
+    main.py:57-79 does; ``--post-aggregation`` (PostDynamicRGCN / PostSelfAttentionRGCN proper) is not built."""
+    cls = MODULES[args.module]
+    if getattr(args, "post_aggregation", False):
+        raise NotImplementedError("temp_b200: --post-aggregation (models/PostDynamicRGCN.py:146-322, PostSelfAttentionRGCN.py) "
+                                  "is not built; --post-ensemble and --impute are")
+    if cls in (DynamicRGCN, BiDynamicRGCN) and (getattr(args, "post_ensemble", False) or getattr(args, "impute", False)):
+        from . import post
+        if args.module not in ("GRRGCN", "BiGRRGCN"):
+            raise NotImplementedError("temp_b200: --post-ensemble / --impute exist for the GRU flavours only (the reference's "
+                                      "linear RRGCNLayer returns two values where the post-ensemble callers unpack three)")
+        bi = cls is BiDynamicRGCN
+        if getattr(args, "post_ensemble", False):
+            cls = post.PostEnsembleBiDynamicRGCN if bi else post.PostEnsembleDynamicRGCN
+        else:
+            cls = post.ImputeBiDynamicRGCN if bi else post.ImputeDynamicRGCN
+    return cls(args, num_ents, num_rels, graph_dict_train, graph_dict_val, graph_dict_test)

@@ -159,6 +159,9 @@ class EncoderRuntime(object):
         # (models/GRU_cell.py:12-15): pre-activations of magnitude ~10 make its recurrence ill-conditioned (fp32 itself is
         # only good to ~1.5e-4 after 8 steps), so that flag stays on the exact-fp32 kernels.
         self.use_tc = not bool(getattr(model.args, "type1", False))
+        # post-ensemble / impute shells: the layer-2 launches also store their output BEFORE the cells (+ time embedding),
+        # the "local" stream of models/RRGCN.py:227-233, into bufs["local"]
+        self.want_local = False
 
     # ---- plan upload -----------------------------------------------------------------------------
     def stage_plan(self, plan: WindowPlan, program: lib.Program, tag: str = "plan"):
@@ -381,6 +384,13 @@ class EncoderRuntime(object):
         S = self.ws.get("state", R * D)[:R * D].view(R, D)
         S1 = None
         bufs = {"h1": h1}
+        local_kw = {}
+        if self.want_local:
+            if not gru:
+                raise NotImplementedError("temp_b200: the local (post-ensemble) stream exists for the GRU flavours only")
+            bufs["local"] = self.ws.get("local", R * D)[:R * D].view(R, D)
+            self._live.append(self.ws.get("local", R * D))
+            local_kw = dict(h_out=bufs["local"], te_out=use_te)
 
         def rnn_of(layer, direction):
             if not bi:
@@ -404,9 +414,10 @@ class EncoderRuntime(object):
                 rnns = [rnn_of(layer, d) for d in dirs]
                 w, b = self._wih(lname, rnns)
                 gi = self.ws.get("gi_" + lname, R * GL)[:R * GL].view(R, GL)
+                self._live.append(gi)                    # a kept program must keep the buffers it addresses (grow-only workspace)
                 prog.add(lib.OP_LAYER, self._layer(layer, rows, dptr, x=x_in, x_is_embed=x_is_embed, act=relu,
                                                    terms=[self._term(x_in, layer.loop_weight, index=index)],
-                                                   chain=(w, b, gi, GL)))
+                                                   chain=(w, b, gi, GL), **(local_kw if layer is l2 else {})))
                 for j, d in enumerate(dirs):
                     pv, dt = prev_ptrs(d, seg)
                     prog.add(lib.OP_GRU, self._gru(layer, rnns[j][1], rnns[j][0], rows, gi=gi, gi_ld=GL, gi_off=j * G,
@@ -440,7 +451,7 @@ class EncoderRuntime(object):
                     rnns = [rnn_of(l2, d) for d in dirs]
                     w, b = self._wih("layer_2", rnns)
                     prog.add(lib.OP_LAYER, self._layer(l2, mine(rows), dptr, x=h1, x_is_embed=False, act=relu2,
-                                                       terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, GL)))
+                                                       terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, GL), **local_kw))
                 protos = {}          # one fully built GruArgs per (cell, variant); the steps copy it and patch the rows
                 for g, seg in enumerate(plan.segments):
                     dirs = dirs_of(seg)
@@ -507,6 +518,7 @@ class EncoderRuntime(object):
                 self._chain_packed[qkv.data_ptr()] = self.prep.packed(lname + ".qkv_packed", qkv, qkvw)
             kvb = self.ws.get("kv_" + lname, max(Rh, 1) * 2 * D)[:Rh * 2 * D].view(Rh, 2 * D)
             qkvb = self.ws.get("qkv_" + lname, max(nf, 1) * 3 * D)[:nf * 3 * D].view(nf, 3 * D)
+            prog.keepalive += [kvb, qkvb]                # a kept program must keep the buffers it addresses
             return kv, qkv, kvb, qkvb
 
         def attend(layer, lname, kvb, qkvb, combine):

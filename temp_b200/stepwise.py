@@ -133,16 +133,25 @@ class _Step(object):
         return (("time_weight_forward", layer.time_weight_forward) if d == "f"
                 else ("time_weight_backward", layer.time_weight_backward))
 
-    def recurrent(self, layer, lname, rows, dirs, prevs, dts, ident, make_layer, out, relu, te, gru_kw):
-        """One recurrent layer over ``rows``: ``make_layer(terms=..., **outputs)`` builds its RGCN / isolated half."""
+    def recurrent(self, layer, lname, rows, dirs, prevs, dts, ident, make_layer, out, relu, te, gru_kw, local=None,
+                  local_te=False, gi_override=None):
+        """One recurrent layer over ``rows``: ``make_layer(terms=..., **outputs)`` builds its RGCN / isolated half.
+        ``local``: also store the layer's pre-recurrence output (the post-ensemble "local" stream, RRGCN.py:227-233), with the
+        time embedding when ``local_te``.  ``gi_override``: input pre-activations computed by the caller (impute)."""
         rt, n = self.rt, rows[1] - rows[0]
         if self.gru:
             cells = [self.cell(layer, d) for d in dirs]
             w, b = rt._wih(lname, cells)
             GL = self.G * len(dirs)
-            gi = torch.empty(max(n, 1), GL, dtype=torch.float32, device=self.dev)
-            self.prog.keepalive.append(gi)
-            self.prog.add(lib.OP_LAYER, make_layer(layer, relu, [], chain=(w, b, gi, GL)))
+            if gi_override is not None:
+                gi = gi_override
+            else:
+                gi = torch.empty(max(n, 1), GL, dtype=torch.float32, device=self.dev)
+                self.prog.keepalive.append(gi)
+                outputs = dict(chain=(w, b, gi, GL))
+                if local is not None:
+                    outputs.update(h_out=local, te_out=local_te)
+                self.prog.add(lib.OP_LAYER, make_layer(layer, relu, [], **outputs))
             for j, d in enumerate(dirs):
                 self.prog.add(lib.OP_GRU, rt._gru(layer, cells[j][1], cells[j][0], rows, gi=gi, gi_ld=GL, gi_off=j * self.G,
                                                   state=prevs[j], prev=ident.data_ptr(), dt=dts[j].data_ptr(), out=out,
@@ -154,10 +163,11 @@ class _Step(object):
             self.prog.add(lib.OP_LAYER, make_layer(layer, relu, extra, h_out=out, te_out=te))
 
 
-def graph_step(encoder, bg: BatchedSnapshots, times, prev1, prev2, dts, dirs):
+def graph_step(encoder, bg: BatchedSnapshots, times, prev1, prev2, dts, dirs, want_local=False):
     """One encoder call on a batch of snapshots.  prev1 / prev2 / dts: per direction in ``dirs`` the dense previous
     states of layer 1 / layer 2 ``[N, D]`` and the time differences ``[N]`` (prev1 may be None with
-    --rec-only-last-layer).  -> (first, second)."""
+    --rec-only-last-layer).  -> (first, second), or (local, first, second) with ``want_local`` (the post-ensemble calls:
+    local = the layer-2 RGCN output before the cells, + its time embedding; GRU flavours only)."""
     st = _Step(encoder)
     m, rt, D, dev = st.m, st.rt, st.D, st.dev
     if m.family != "recurrent":
@@ -168,8 +178,11 @@ def graph_step(encoder, bg: BatchedSnapshots, times, prev1, prev2, dts, dirs):
     x = _dense(bg.ndata["h"], R, D, dev)
     first = torch.empty(R, D, dtype=torch.float32, device=dev)
     second = torch.empty(R, D, dtype=torch.float32, device=dev)
+    local = torch.empty(R, D, dtype=torch.float32, device=dev) if want_local else None
+    if want_local and not st.gru:
+        raise NotImplementedError("the post-ensemble calls exist for the GRU flavours only (models/RRGCN.py:219-234)")
     if R == 0:
-        return first, second
+        return (local, first, second) if want_local else (first, second)
     dptr = rt.stage_plan(plan, st.prog, tag="step")
     ident = torch.arange(R, dtype=torch.int32, device=dev)
     prev2 = [_dense(p, R, D, dev) for p in prev2]
@@ -191,15 +204,45 @@ def graph_step(encoder, bg: BatchedSnapshots, times, prev1, prev2, dts, dirs):
         prev1 = [_dense(p, R, D, dev) for p in prev1]
         st.prog.keepalive += prev1
         st.recurrent(l1, "layer_1", rows, dirs, prev1, dts, ident, graph_layer(x), first, False, use_te, dict(dptr=dptr))
-    st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, graph_layer(first), second, relu2, use_te, dict(dptr=dptr))
+    st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, graph_layer(first), second, relu2, use_te, dict(dptr=dptr),
+                 local=local, local_te=use_te)
+    if local is not None:
+        st.prog.keepalive.append(local)
     st.run()
     if st.gru:
         first = second                                        # the layer-2 GRU writes into the shared graph
-    return first, second
+    return (local, first, second) if want_local else (first, second)
 
 
-def isolated_step(encoder, ent_embeds, t: int, prev1, prev2, dts, dirs):
-    """``forward_isolated`` over all rows of ``ent_embeds`` (RRGCN.py:206-217, BiRRGCN.py:242-257) -> second [M, D]."""
+def impute_weights(encoder, dts, dirs):
+    """RRGCN.calc_impute_weight (models/RRGCN.py:271-272); the Bi model halves each direction's weight
+    (models/BiRRGCN.py:309-310, 331-332).  dts: per direction ``[M]`` -> per direction ``[M, 1]``."""
+    if len(dirs) == 1:
+        lin = encoder.impute_weight
+        return [torch.exp(-torch.clamp(dts[0].view(-1, 1) * lin.weight.detach().view(()) + lin.bias.detach().view(()), min=0))]
+    out = []
+    for dt, lin in zip(dts, (encoder.impute_weight_forward, encoder.impute_weight_backward)):
+        out.append(torch.exp(-torch.clamp(dt.view(-1, 1) * lin.weight.detach().view(()) + lin.bias.detach().view(()), min=0)) / 2)
+    return out
+
+
+def _blend(ws, locs, x):
+    acc, rest = 0, 1
+    for w, loc in zip(ws, locs):
+        acc = acc + w * loc
+        rest = rest - w
+    return acc + rest * x
+
+
+def isolated_step(encoder, ent_embeds, t: int, prev1, prev2, dts, dirs, mode="plain", locs=None):
+    """``forward_isolated`` over all rows of ``ent_embeds`` (RRGCN.py:206-217, BiRRGCN.py:242-257) -> second [M, D].
+
+    mode 'post': ``forward_post_ensemble_isolated`` (RRGCN.py:236-254, BiRRGCN.py:295-319) -> (local, second): the layer
+        launch also stores the layer-2 output before the cells; with an impute encoder that local stream is blended with the
+        history's local rows ``locs`` (element-wise, torch) before the time embedding is added.
+    mode 'impute': ``forward_isolated_impute`` (RRGCN.py:256-269, BiRRGCN.py:321-338): the layer-2 cells read the BLENDED
+        stream, so their input pre-activations are one library GEMM on the blended rows (torch.addmm) between the layer
+        launch and the recurrent launch -- a "next" row, not the hot path."""
     st = _Step(encoder)
     m, rt, D, dev = st.m, st.rt, st.D, st.dev
     if m.family != "recurrent":
@@ -231,9 +274,35 @@ def isolated_step(encoder, ent_embeds, t: int, prev1, prev2, dts, dirs):
         st.prog.keepalive += prev1
         st.recurrent(l1, "layer_1", rows, dirs, prev1, dts, ident, iso_layer(x), first, False, use_te,
                      dict(row_time_scalar=t))
-    st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, iso_layer(first), second, st.bi, use_te,
-                 dict(row_time_scalar=t))
+    if mode == "plain":
+        st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, iso_layer(first), second, st.bi, use_te,
+                     dict(row_time_scalar=t))
+        st.run()
+        return second
+    if not st.gru:
+        raise NotImplementedError("the post-ensemble / impute calls exist for the GRU flavours only (models/RRGCN.py:219-272)")
+    local = torch.empty(M, D, dtype=torch.float32, device=dev)
+    st.prog.keepalive.append(local)
+    te2 = l2.time_embed.detach()[t] if use_te else None
+    if mode == "post":
+        st.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, iso_layer(first), second, st.bi, use_te,
+                     dict(row_time_scalar=t), local=local, local_te=False)
+        st.run()
+        if encoder.impute:
+            local = _blend(impute_weights(encoder, dts, dirs), [_dense(x_, M, D, dev) for x_ in locs], local)
+        return (local + te2 if use_te else local), second
+    # impute: layer launch (no chained GEMM) -> blend -> gi by a library GEMM -> the cells
+    st.prog.add(lib.OP_LAYER, iso_layer(first)(l2, st.bi, [], h_out=local))
     st.run()
+    x = _blend(impute_weights(encoder, dts, dirs), [_dense(x_, M, D, dev) for x_ in locs], local)
+    st2 = _Step(encoder)
+    cells = [st2.cell(l2, d) for d in dirs]
+    w, b = rt._wih("layer_2", cells)
+    gi = torch.addmm(b, x, w)
+    st2.prog.keepalive += [x, gi, ident, second] + prev2 + dts
+    st2.recurrent(l2, "layer_2", rows, dirs, prev2, dts, ident, None, second, st.bi, use_te, dict(row_time_scalar=t),
+                  gi_override=gi)
+    st2.run()
     return second
 
 
@@ -301,7 +370,7 @@ def _attn_inputs(st, prevs, mask, time_diff, n):
     return flat, slot, tau, T
 
 
-def _attn_layer(st, layer, lname, make_layer, hist_flat, slot, tau, T, n, out, combine, h_out=None):
+def _attn_layer(st, layer, lname, make_layer, hist_flat, slot, tau, T, n, out, combine, h_out=None, h_out_te=False):
     """q, k, v of the current rows by the chained GEMM of the layer launch (time embedding added on the way in), k, v of
     the dense history rows by one library GEMM, then the attention kernel (SARGCN.py:25-53)."""
     rt, D, dev = st.rt, st.D, st.dev
@@ -317,6 +386,7 @@ def _attn_layer(st, layer, lname, make_layer, hist_flat, slot, tau, T, n, out, c
     kw = dict(te_chain=True, chain=(qkv_t, None, qkv, 3 * D))
     if h_out is not None:
         kw["h_out"] = h_out
+        kw["te_out"] = h_out_te
     st.prog.add(lib.OP_LAYER, make_layer(layer, **kw))
     a = lib.AttnArgs()
     a.row0, a.row1, a.d, a.heads = 0, n, D, layer.h
@@ -430,3 +500,58 @@ def attention_isolated_step(encoder, ent_embeds, prev1, prev2, time_diff, mask, 
         _attn_layer(st, l2, "layer_2", iso_layer(first, True), f2, slot, tau, T, M, out, True)
     st.run()
     return out
+
+
+def attention_post_ensemble_step(encoder, bg: BatchedSnapshots, prev2, time_diff, mask, times):
+    """SARGCN.forward_post_ensemble (models/SARGCN.py:137-141, the --post-aggregation layer return of SARGCN.py:44-45):
+    plain layer 1, then layer 2 with its attention -> (second_local = layer-2 output + time embedding, attention output)."""
+    st = _Step(encoder)
+    rt, D, dev = st.rt, st.D, st.dev
+    plan = bg.plan(_times_list(times))
+    R = plan.R
+    rows = (0, R)
+    out = torch.empty(R, D, dtype=torch.float32, device=dev)
+    local = torch.empty(R, D, dtype=torch.float32, device=dev)
+    if R == 0:
+        return local, out
+    x = _dense(bg.ndata["h"], R, D, dev)
+    h1 = torch.empty(R, D, dtype=torch.float32, device=dev)
+    dptr = rt.stage_plan(plan, st.prog, tag="step")
+    (f2,), slot, tau, T = _attn_inputs(st, [prev2], mask, time_diff, R)
+    st.prog.keepalive += [x, h1, out, local]
+    l1, l2 = encoder.layer_1, encoder.layer_2
+    st.prog.add(lib.OP_LAYER, rt._layer(l1, rows, dptr, x=x, x_is_embed=False, act=False,
+                                        terms=[rt._term(x, l1.loop_weight)], h_out=h1))
+
+    def make(layer, **outputs):
+        return rt._layer(layer, rows, dptr, x=h1, x_is_embed=False, act=True, terms=[rt._term(h1, layer.loop_weight)], **outputs)
+    _attn_layer(st, l2, "layer_2", make, f2, slot, tau, T, R, out, False, h_out=local, h_out_te=True)
+    st.run()
+    return local, out
+
+
+def attention_isolated_post_ensemble_step(encoder, ent_embeds, prev2, time_diff, mask, t):
+    """SARGCN.forward_isolated_post_ensemble (models/SARGCN.py:143-146) -> (second_local, attention output)."""
+    st = _Step(encoder)
+    rt, D, dev = st.rt, st.D, st.dev
+    M = int(ent_embeds.shape[0])
+    rows = (0, M)
+    t = int(t.item()) if torch.is_tensor(t) else int(t)
+    x = _dense(ent_embeds, M, D, dev)
+    first = torch.empty(M, D, dtype=torch.float32, device=dev)
+    out = torch.empty(M, D, dtype=torch.float32, device=dev)
+    local = torch.empty(M, D, dtype=torch.float32, device=dev)
+    (f2,), slot, tau, T = _attn_inputs(st, [prev2], mask, time_diff, M)
+    st.prog.keepalive += [x, first, out, local]
+    rt._live = st.prog.keepalive
+    l1, l2 = encoder.layer_1, encoder.layer_2
+
+    def iso(x_in, act):
+        def make(layer, **outputs):
+            return rt._layer(layer, rows, None, x=None, x_is_embed=False, graph=False, residual=True, act=act,
+                             terms=[rt._term(x_in, layer.loop_weight)], row_time_scalar=t, **outputs)
+        return make
+    st.prog.add(lib.OP_LAYER, iso(x, False)(l1, h_out=first))
+    _attn_layer(st, l2, "layer_2", iso(first, True), f2, slot, tau, T, M, out, False, h_out=local, h_out_te=True)
+    st.run()
+    return local, out

@@ -125,3 +125,17 @@ CPU_TRAIN_CASES = [
     dict(name="train_grrgcn_tiny_lambda", base="grrgcn_tiny_d128_lambda", seed=46, random_dropout=True),
     dict(name="train_bigrrgcn_tiny_nb100", base="bigrrgcn_tiny_d200_nb100", seed=47, random_dropout=False),
 ]
+
+
+# Post-ensemble / impute variants of the GRU families (models/PostDynamicRGCN.py, models/PostBiDynamicRGCN.py; main.py:57-72
+# selects them with --post-ensemble / --impute): evaluate_embed (local + recurrent stream of the target graphs),
+# get_all_embeds_Gt of every batch item (the imputed table, or the local / recurrent pair) and evaluate() ranks.
+POST_CASES = [
+    dict(name="impute_grrgcn_tiny", base="grrgcn_tiny_d128_last", impute=True, post_ensemble=False),
+    dict(name="post_grrgcn_tiny", base="grrgcn_tiny_d128_last", impute=False, post_ensemble=True),
+    dict(name="post_impute_grrgcn_tiny_full", base="grrgcn_tiny_d128_full", impute=True, post_ensemble=True),
+    dict(name="impute_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last", impute=True, post_ensemble=False),
+    dict(name="post_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last", impute=False, post_ensemble=True),
+    dict(name="post_impute_bigrrgcn_tiny_full", base="bigrrgcn_tiny_d128_full", impute=True, post_ensemble=True),
+    dict(name="post_impute_grrgcn_icews", base="grrgcn_icews_d128_L8", impute=True, post_ensemble=True),
+]

@@ -20,7 +20,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from tests.golden.cases import (CASES, CPU_CASES, CPU_TRAIN_CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES,  # noqa: E402
+from tests.golden.cases import (CASES, CPU_CASES, CPU_TRAIN_CASES, POST_CASES, RANK_CASES, SAMPLER_CASES, TRAIN_CASES,  # noqa: E402
                                 dataset_path)
 from oracle.temp_oracle import fill_values  # noqa: E402
 
@@ -195,6 +195,67 @@ def run_rank_case(rc):
     return {"ranks": ranks.numpy().astype(np.int64), "loss": np.asarray(float(loss), dtype=np.float64)}
 
 
+def run_post_case(pc):
+    """evaluate_embed / get_all_embeds_Gt / evaluate of the unmodified Impute* / PostEnsemble* model classes."""
+    from models.PostBiDynamicRGCN import ImputeBiDynamicRGCN, PostEnsembleBiDynamicRGCN
+    from models.PostDynamicRGCN import ImputeDynamicRGCN, PostEnsembleDynamicRGCN
+    case = next(c for c in CASES if c["name"] == pc["base"])
+    bi = case["module"].startswith("Bi")
+    cls = ((PostEnsembleBiDynamicRGCN if bi else PostEnsembleDynamicRGCN) if pc["post_ensemble"]
+           else (ImputeBiDynamicRGCN if bi else ImputeDynamicRGCN))
+    args = ref_args(case)
+    args.impute, args.post_ensemble = pc["impute"], pc["post_ensemble"]
+    num_e, num_r, gtr, gva, gte = ref_graph_dicts(args)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        model = cls(args, num_e, num_r, gtr, gva, gte)
+        for name, prm in model.state_dict().items():
+            prm.copy_(torch.from_numpy(fill_values(name, tuple(prm.shape))))
+    model.eval()
+    t_list = torch.tensor(case["t_list"], dtype=torch.long)
+    L = case["L"]
+    out = {}
+    with torch.no_grad():
+        ev = model.evaluate_embed(t_list, val=True)
+        if not bi:
+            if pc["post_ensemble"]:
+                loc, rec, graphs, time_list, hl, hr, st = ev
+                tl = time_list[-1]
+                alls = [model.get_all_embeds_Gt(loc[i], rec[i], graphs[i], tl[i], hl[i], hr[i][0], hr[i][1], L - 1 - st[i])
+                        for i in range(len(tl))]
+            else:
+                rec, graphs, time_list, hl, hr, st = ev
+                loc, tl = None, time_list[-1]
+                alls = [model.get_all_embeds_Gt(rec[i], graphs[i], tl[i], hl[i], hr[i][0], hr[i][1], L - 1 - st[i])
+                        for i in range(len(tl))]
+        else:
+            if pc["post_ensemble"]:
+                loc, rec, graphs, tl, hfl, hfr, sf, hbl, hbr, sb = ev
+                alls = [model.get_all_embeds_Gt(loc[i], rec[i], graphs[i], tl[i], hfl[i], hfr[i][0], hfr[i][1], L - 1 - sf[i],
+                                                hbl[i], hbr[i][0], hbr[i][1], L - 1 - sb[i]) for i in range(len(tl))]
+            else:
+                rec, graphs, tl, hfl, hfr, sf, hbl, hbr, sb = ev
+                loc = None
+                alls = [model.get_all_embeds_Gt(rec[i], graphs[i], tl[i], hfl[i], hfr[i][0], hfr[i][1], L - 1 - sf[i],
+                                                hbl[i], hbr[i][0], hbr[i][1], L - 1 - sb[i]) for i in range(len(tl))]
+        ranks, _ = model.evaluate(t_list, val=True)
+    out["times"] = np.asarray([int(t) for t in tl], dtype=np.int64)
+    out["sizes"] = np.asarray([p.shape[0] for p in rec], dtype=np.int64)
+    out["per_graph"] = torch.cat(list(rec), dim=0).numpy()
+    if loc is not None:
+        out["per_graph_loc"] = torch.cat(list(loc), dim=0).numpy()
+    M = alls[0][0].shape[0] if pc["post_ensemble"] else alls[0].shape[0]
+    rows = np.asarray(case_rows(case, M), dtype=np.int64)
+    out["all_rows"] = rows
+    if pc["post_ensemble"]:
+        out["all_embeds_loc"] = torch.stack([a[0] for a in alls], dim=0)[:, rows].numpy()
+        out["all_embeds"] = torch.stack([a[1] for a in alls], dim=0)[:, rows].numpy()
+    else:
+        out["all_embeds"] = torch.stack(alls, dim=0)[:, rows].numpy()
+    out["ranks"] = ranks.numpy().astype(np.int64)
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     reference_on_path()
@@ -202,7 +263,7 @@ def main():
     only_rank = "--rank-only" in sys.argv
     if "--only" in sys.argv:                       # --only name1,name2: just these cases (of any kind)
         names = set(sys.argv[sys.argv.index("--only") + 1].split(","))
-        for fn, cases in ((run_rank_case, RANK_CASES), (run_case, CASES + CPU_CASES), (run_train_case, TRAIN_CASES + CPU_TRAIN_CASES),
+        for fn, cases in ((run_post_case, POST_CASES), (run_rank_case, RANK_CASES), (run_case, CASES + CPU_CASES), (run_train_case, TRAIN_CASES + CPU_TRAIN_CASES),
                           (run_sampler_case, SAMPLER_CASES)):
             for case in cases:
                 if case["name"] in names:
@@ -233,6 +294,11 @@ def main():
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **res)
         print("%-40s %.1f KB" % (case["name"], os.path.getsize(path) / 1024))
+    for case in POST_CASES:
+        res = run_post_case(case)
+        path = os.path.join(HERE, case["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print("%-40s ranks=%d  %.1f KB" % (case["name"], res["ranks"].shape[0], os.path.getsize(path) / 1024))
 
 
 if __name__ == "__main__":

@@ -53,23 +53,24 @@ def product_store(dataset):
     return SnapshotStore.from_quadruple_dir(dataset_path(dataset))
 
 
-def product_args(case):
+def product_args(case, impute=False, post_ensemble=False):
     return Namespace(module=case["module"], embed_size=case["D"], hidden_size=case["D"], n_bases=case["n_bases"],
                      train_seq_len=case["L"], test_seq_len=case["L"], dropout=0.1, num_layers=1, lr=1e-3,
                      rec_only_last_layer=case["rec_only_last_layer"], use_time_embedding=case["use_time_embedding"],
                      inv_temperature=0.1, type1=case.get("type1", False),
                      learnable_lambda=case.get("learnable_lambda", False), score_function="complex",
                      negative_rate=case.get("negative_rate", 5), num_pos_facts=case.get("num_pos_facts", 3000),
-                     use_cuda=True, impute=False, post_ensemble=False, post_aggregation=False)
+                     use_cuda=True, impute=impute, post_ensemble=post_ensemble, post_aggregation=False)
 
 
-def product_model(case, device="cuda"):
+def product_model(case, device="cuda", impute=False, post_ensemble=False):
     """The CUDA-backed shell for a golden case, parameters filled with the same exact-integer hash the
     golden generator and the oracle use (keyed by state_dict name)."""
     import torch
     from temp_b200.models import build_module
     store = product_store(case["dataset"])
-    model = build_module(product_args(case), store.num_ents, store.num_rels, store.train, store.valid, store.test)
+    model = build_module(product_args(case, impute, post_ensemble), store.num_ents, store.num_rels, store.train, store.valid,
+                         store.test)
     with torch.no_grad():
         for name, prm in model.state_dict().items():
             prm.copy_(torch.from_numpy(orc.fill_values(name, tuple(prm.shape))))

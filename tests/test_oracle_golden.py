@@ -128,3 +128,42 @@ def test_evaluate_ranks_match_reference(rc):
     else:
         assert np.array_equal(ranks.numpy(), gold["ranks"])
     assert abs(loss - float(gold["loss"])) <= 1e-6 * abs(float(gold["loss"]))
+
+
+def _post_oracle(pc):
+    """The post-ensemble / impute oracle (oracle/temp_oracle_post.py) for a POST_CASES entry."""
+    from oracle import temp_oracle_post as post
+    from tests.golden.cases import dataset_path
+    from tests.helpers import CASE_BY_NAME, oracle_config
+    case = CASE_BY_NAME[pc["base"]]
+    cfg = oracle_config(case)
+    _, _, train, _, _ = oracle_graphs(case["dataset"])
+    params = {k: torch.from_numpy(orc.fill_values(k, s)) for k, s in post.post_param_shapes(cfg, pc["impute"], pc["post_ensemble"]).items()}
+    quads = np.loadtxt(dataset_path(case["dataset"]) + "/train.txt", dtype=np.int64)[:, :4]
+    return case, post.PostOracle(cfg, params, train, pc["impute"], pc["post_ensemble"], quads)
+
+
+@pytest.mark.parametrize("pc", __import__("tests.golden.cases", fromlist=["POST_CASES"]).POST_CASES, ids=lambda c: c["name"])
+def test_post_ensemble_and_impute_match_reference(pc):
+    """The Impute* / PostEnsemble* model classes of the unmodified reference (models/PostDynamicRGCN.py,
+    models/PostBiDynamicRGCN.py): local + recurrent stream of the target graphs, the all-entity tables and the ranks."""
+    gold = load_golden(pc["name"])
+    case, model = _post_oracle(pc)
+    _, _, _, valid, test = oracle_graphs(case["dataset"])
+    with torch.no_grad():
+        res = model.evaluate_embed_post(case["t_list"])
+        assert res["times"] == gold["times"].tolist()
+        assert rel_err(torch.cat(res["per_graph"]).numpy(), gold["per_graph"]) < TOL
+        rows = gold["all_rows"]
+        n = len(res["times"])
+        if pc["post_ensemble"]:
+            assert rel_err(torch.cat(res["per_graph_loc"]).numpy(), gold["per_graph_loc"]) < TOL
+            alls = [model.all_embeds_post(res, i) for i in range(n)]
+            assert rel_err(np.stack([a[0].numpy()[rows] for a in alls]), gold["all_embeds_loc"]) < TOL
+            assert rel_err(np.stack([a[1].numpy()[rows] for a in alls]), gold["all_embeds"]) < TOL
+        else:
+            alls = np.stack([model.all_embeds_impute(res, i).numpy()[rows] for i in range(n)])
+            assert rel_err(alls, gold["all_embeds"]) < TOL
+        ranks, _ = model.evaluate_post(case["t_list"], valid, test, val=True)
+    diff = np.abs(ranks.numpy() - gold["ranks"])
+    assert ranks.shape[0] == gold["ranks"].shape[0] and diff.max() <= 1 and (diff != 0).mean() <= 2e-3, (diff.max(), (diff != 0).sum())
