@@ -306,6 +306,9 @@ def main():
     d2h_bytes = int(r0.host_out.numel() * 4)
     if world > 1:
         dist.barrier()
+    for i in range(4):               # (untimed: the first steps after a host-synchronising collective run cold)
+        step_device(i)
+    torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -13,9 +13,12 @@ It restates, on the packed window plan of temp_b200/planner.py (same ``prev_row`
   DynamicRGCN.forward, get_all_embeds_Gt      models/DynamicRGCN.py:56-64, 176-194
   BiGRRGCNLayer / BiRRGCNLayer, BiRRGCN       models/BiRRGCN.py:27-81, 115-186, 188-257
   BiDynamicRGCN.forward, get_all_embeds_Gt    models/BiDynamicRGCN.py:102-112, 165-187
-Scope: the recurrent families (GRRGCN / RRGCN / BiGRRGCN / BiRRGCN, with or without ``--rec-only-last-layer``, torch GRU
-or --type1 cell, learnable lambda); the static and attention families raise.  The no-grad forward never comes here (it
-is the CUDA path and has no fallback).
+  RGCN (static)                               models/RGCN.py:154-164, baselines/StaticRGCN.py:36-89
+  SARGCNLayer / SARGCN, (Bi)SelfAttentionRGCN models/SARGCN.py:25-62, 103-125; models/SelfAttentionRGCN.py:26-43, 73-139;
+                                              models/BiSelfAttentionRGCN.py:17-87
+Scope: every family of the module table (GRRGCN / RRGCN / BiGRRGCN / BiRRGCN with or without ``--rec-only-last-layer``, torch
+GRU or --type1 cell, learnable lambda; SRGCN; SARGCN / BiSARGCN); the post-ensemble / impute shells raise.  The no-grad
+forward never comes here (it is the CUDA path and has no fallback).
 """
 from __future__ import annotations
 
@@ -27,9 +30,6 @@ import torch.nn.functional as F
 def _check(model):
     if model.ent_embeds.device.type != "cuda":
         raise RuntimeError("temp_b200: the model must live on a CUDA device")
-    if model.family != "recurrent":
-        raise NotImplementedError("temp_b200: the autograd fallback covers the recurrent families (GRRGCN / RRGCN / "
-                                  "BiGRRGCN / BiRRGCN); use torch.no_grad() for the forward of this configuration")
 
 
 class _Ctx(object):
@@ -256,21 +256,138 @@ def all_embeds(model, plan, S, i: int, S1=None, shared=None):
     return second.index_copy(0, fin_ids, S[fin.row0:fin.row0 + fin.n])
 
 
+# ---- static and attention families (baselines/StaticRGCN.py:36-89; models/SelfAttentionRGCN.py:26-43, 73-139,
+# models/BiSelfAttentionRGCN.py:17-87 over models/SARGCN.py:25-62, 103-125) ------------------------------------------------
+def encode_static(model, plan):
+    """models/RGCN.py:154-159 on the packed target snapshots -> [R, D]."""
+    c = _Ctx(model, plan)
+    enc = model.ent_encoder
+    h0 = model.ent_embeds.index_select(0, c.ent_id)
+    h1 = _rgcn_pre(enc.layer_1, h0, c, 0, plan.R, model.training)
+    out = torch.relu(_rgcn_pre(enc.layer_2, h1, c, 0, plan.R, model.training))
+    if enc.use_time_embedding:
+        out = out + enc.layer_2.time_embed.index_select(0, c.row_time)
+    return out
+
+
+def all_embeds_static(model, plan, out, i: int):
+    """baselines/StaticRGCN.py:48-58 over models/RGCN.py:161-164."""
+    enc = model.ent_encoder
+    t = int(plan.final_times[i])
+    y = torch.relu(_iso_pre(enc.layer_2, _iso_pre(enc.layer_1, model.ent_embeds, model.training), model.training))
+    if enc.use_time_embedding:
+        y = y + enc.layer_2.time_embed[t]
+    fin = plan.final.instances[i]
+    ids = torch.as_tensor(fin.snapshot.node_ids, device=out.device).long()
+    return y.index_copy(0, ids, out[fin.row0:fin.row0 + fin.n])
+
+
+def _attend(layer, cur, prev, tau, mask):
+    """models/SARGCN.py:25-53: cur [N, D], prev [N, T, D], additive mask [N, T + 1], slot ages tau [T + 1]; the output
+    channel order is [d_k major, head minor]."""
+    N, D = cur.shape
+    H = layer.h
+    dk = D // H
+    dec = 0
+    if layer.learnable_lambda:
+        dec = -torch.clamp(layer.exponential_decay(tau.view(-1, 1)), min=0).view(-1)
+    allv = torch.cat([prev, cur.unsqueeze(1)], dim=1)
+    q = (cur @ layer.q_linear.weight.t()).view(N, 1, H, dk).transpose(1, 2)
+    k = (allv @ layer.k_linear.weight.t()).view(N, -1, H, dk).transpose(1, 2)
+    v = (allv @ layer.v_linear.weight.t()).view(N, -1, H, dk).transpose(1, 2)
+    sc = torch.matmul(q, k.transpose(-2, -1)).view(N, H, -1) / (dk ** 0.5) + mask.unsqueeze(1) + dec
+    o = torch.matmul(torch.softmax(sc, dim=-1).unsqueeze(2), v).view(N, H, dk)
+    return o.transpose(1, 2).contiguous().view(N, D)
+
+
+def _slot_gather(values, slots):
+    """values [R, D], slots [N, T] packed rows (-1: inactive) -> ([N, T, D] with zero rows, additive mask [N, T + 1])."""
+    has = slots >= 0
+    prev = torch.where(has.unsqueeze(-1), values.index_select(0, slots.clamp(min=0).reshape(-1)).view(*slots.shape, -1),
+                       torch.zeros((), device=values.device))
+    mask = torch.where(has, 0.0, -10e9).to(values.dtype)
+    return prev, torch.cat([mask, torch.zeros(slots.shape[0], 1, dtype=values.dtype, device=values.device)], dim=1)
+
+
+def encode_attention(model, plan):
+    """History snapshots: two plain layers, both outputs with their time embedding (SARGCN.py:103-107); final rows: attention
+    over the history slots (SARGCN.py:109-117) -> (out [n_final, D], first_te [R, D], second_te [R, D], tau)."""
+    c = _Ctx(model, plan)
+    enc = model.ent_encoder
+    l1, l2 = enc.layer_1, enc.layer_2
+    dev = model.ent_embeds.device
+    h0 = model.ent_embeds.index_select(0, c.ent_id)
+    h1 = _rgcn_pre(l1, h0, c, 0, plan.R, model.training)
+    first_te = h1 + l1.time_embed.index_select(0, c.row_time)
+    second_te = torch.relu(_rgcn_pre(l2, h1, c, 0, plan.R, model.training)) + l2.time_embed.index_select(0, c.row_time)
+    fin = plan.final
+    tau = torch.tensor(model.time_diff(plan), dtype=torch.float32, device=dev)
+    slots = torch.as_tensor(np.ascontiguousarray(plan.slot_row), device=dev).long().view(fin.row1 - fin.row0, -1)
+    prev2, mask = _slot_gather(second_te, slots)
+    out = _attend(l2, second_te[fin.row0:fin.row1], prev2, tau, mask)
+    if not enc.rec_only_last_layer:                       # JK max over the two layers (SARGCN.py:117)
+        prev1, _ = _slot_gather(first_te, slots)
+        out = torch.max(_attend(l1, first_te[fin.row0:fin.row1], prev1, tau, mask), out)
+    return out, first_te, second_te, tau
+
+
+def all_embeds_attention(model, plan, out, first_te, second_te, tau, i: int):
+    """models/SelfAttentionRGCN.py:26-43 / BiSelfAttentionRGCN.py (get_all_embeds_Gt) over SARGCN.py:55-62, 119-125."""
+    enc = model.ent_encoder
+    l1, l2 = enc.layer_1, enc.layer_2
+    dev = out.device
+    M, L = model.num_ents, plan.seq_len
+    t = int(plan.final_times[i])
+    slots = np.full((M, plan.n_slots), -1, dtype=np.int64)
+    for k in range(L - 1):
+        inst = plan.steps_f[k].get(i)
+        if inst is not None:
+            slots[inst.snapshot.node_ids, k] = np.arange(inst.row0, inst.row0 + inst.n)
+        if plan.bidirectional:
+            inst = plan.steps_b[k].get(plan.batch - 1 - i)
+            if inst is not None:
+                slots[inst.snapshot.node_ids, L - 1 + k] = np.arange(inst.row0, inst.row0 + inst.n)
+    slots = torch.as_tensor(slots, device=dev)
+    prev2, mask = _slot_gather(second_te, slots)
+    if enc.rec_only_last_layer:
+        first = _iso_pre(l1, model.ent_embeds, model.training)
+    else:
+        prev1, _ = _slot_gather(first_te, slots)
+        first = _attend(l1, _iso_pre(l1, model.ent_embeds, model.training) + l1.time_embed[t], prev1, tau, mask)
+    second = _attend(l2, torch.relu(_iso_pre(l2, first, model.training)) + l2.time_embed[t], prev2, tau, mask)
+    table = second if enc.rec_only_last_layer else torch.max(first, second)
+    fin = plan.final.instances[i]
+    ids = torch.as_tensor(fin.snapshot.node_ids, device=dev).long()
+    return table.index_copy(0, ids, out[fin.row0 - plan.final.row0:fin.row0 - plan.final.row0 + fin.n])
+
+
 def training_loss(model, t_list):
-    """models/DynamicRGCN.py:176-194 with autograd: sub-sampled window in train() mode, bit-exact negative sampling,
-    tail + head cross-entropy through the torch scorers."""
+    """models/DynamicRGCN.py:176-194 (and the Bi / attention / static twins) with autograd: sub-sampled window in train()
+    mode, bit-exact negative sampling, tail + head cross-entropy through the torch scorers."""
     _check(model)
     plan = model.plan(t_list, transform=model.train_edge_sampler() if model.training else None)
-    S, _, S1 = encode(model, plan)
+    fam = model.family
+    if fam == "static":
+        S = encode_static(model, plan)
+    elif fam == "attention":
+        S, first_te, second_te, tau = encode_attention(model, plan)
+    else:
+        S, _, S1 = encode(model, plan)
     dev = S.device
     loss = 0
     shared = {}
     for i, (t, g) in enumerate(zip(plan.final_times, plan.final_snapshots)):
         fin = plan.final.instances[i]
-        ent_embed = S[fin.row0:fin.row0 + fin.n]
+        off = plan.final.row0 if fam == "attention" else 0           # (the attention output holds the final rows only)
+        ent_embed = S[fin.row0 - off:fin.row0 - off + fin.n]
         triplets, neg_tail, neg_head, labels = model.corrupter.single_graph_negative_sampling(t, g, model.num_ents)
         triplets, neg_tail, neg_head, labels = (x.to(dev) for x in (triplets, neg_tail, neg_head, labels))
-        all_g = all_embeds(model, plan, S, i, S1, shared)
+        if fam == "static":
+            all_g = all_embeds_static(model, plan, S, i)
+        elif fam == "attention":
+            all_g = all_embeds_attention(model, plan, S, first_te, second_te, tau, i)
+        else:
+            all_g = all_embeds(model, plan, S, i, S1, shared)
         loss = loss + model.train_link_prediction(ent_embed, triplets, neg_tail, labels, all_g, corrupt_tail=True)
         loss = loss + model.train_link_prediction(ent_embed, triplets, neg_head, labels, all_g, corrupt_tail=False)
     return loss

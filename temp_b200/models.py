@@ -460,11 +460,16 @@ class TKG_Module(nn.Module):
             return self._forward_no_grad(t_list)
 
     def _forward_no_grad(self, t_list):
+        if self.training and float(getattr(self.args, "dropout", 0.0) or 0.0) > 0.0:
+            # the CUDA forward does not draw the self-loop dropout mask (models/RGCN.py:58-59); so that a train()-mode call
+            # returns the same kind of loss with and without gradients, it takes the torch statement (which applies it)
+            from .autograd_path import training_loss
+            return training_loss(self, t_list)
         if self.training:
             # every family sub-samples the final step at 0.5 (history steps at 0.8 with --random-dropout, except the Bi
             # attention model): models/DynamicRGCN.py:176-194, BiDynamicRGCN.py:165-187, SelfAttentionRGCN.py:122-139,
             # BiSelfAttentionRGCN.py:48-69, baselines/StaticRGCN.py:36-47, 60-80
-            # (the self-loop dropout of models/RGCN.py:58-59 is not applied by the CUDA forward: parity holds at p = 0)
+            # (reached with dropout p = 0 only: see above)
             res = self.encode(plan=self.plan(t_list, transform=self.train_edge_sampler()))
         else:
             res = self.encode(t_list)

@@ -319,8 +319,11 @@ def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None, overrid
         if go is None:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
             continue
-        g = prm.grad.detach().cpu().double().numpy()
         w = go.double().numpy()
+        if prm.grad is None:                                   # (a parameter the loss reaches only through exact zeros)
+            assert float(np.abs(w).max()) == 0.0, name
+            continue
+        g = prm.grad.detach().cpu().double().numpy()
         scale = max(np.abs(w).max(), 1e-12)
         assert np.abs(g - w).max() / scale < 1e-3, (name, np.abs(g - w).max() / scale)
         checked += 1
@@ -329,12 +332,12 @@ def _autograd_against_oracle(base, seed, random_dropout, gold_loss=None, overrid
 
 
 @pytest.mark.parametrize("tc", [c for c in __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES
-                                if "icews" not in c["name"] and "sargcn" not in c["name"] and "srgcn" not in c["name"]],
-                         ids=lambda c: c["name"])
+                                if "icews" not in c["name"]], ids=lambda c: c["name"])
 def test_autograd_fallback_gradients_match_oracle(tc):
     """loss.backward() through the fallback gives the gradients of the (reference-pinned) oracle's training loss:
     train mode, sub-sampled window, dropout p = 0, same global seeds; the loss also matches the committed golden value.
-    Uni- and bidirectional cases."""
+    Uni- and bidirectional recurrent cases, the static model and the attention models (BASELINE configs 1 and 4 train
+    through this path)."""
     _autograd_against_oracle(tc["base"], tc["seed"], tc["random_dropout"], load_golden(tc["name"])["loss"],
                              {k: v for k, v in tc.items() if k in ("negative_rate", "num_pos_facts")})
 
