@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 17
+#define TEMP_ABI_VERSION 18
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -365,6 +365,9 @@ const char* temp_last_error_string(void);
 int temp_device_info(int32_t* sm_count, int32_t* max_smem, int32_t* cc);
 
 int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream);
+/* The aggregation half alone (tcgen05 path, d == 128, 1x1 relation blocks): agg_scratch[v] = norm_v^2 * sum_e W[rel_e] (.)
+ * x[src_e] for the rows of [row0, row1) with in-edges -- the DGL update_all / fn.sum / apply of models/RGCN.py:100-104. */
+int temp_rgcn_gather_fwd(const TempRgcnLayerArgs* args, void* stream);
 int temp_gru_fwd(const TempGruArgs* args, void* stream);
 int temp_gru_scan_fwd(const TempGruScanArgs* args, void* stream);
 int temp_attention_fwd(const TempAttnArgs* args, void* stream);

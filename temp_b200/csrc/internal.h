@@ -17,6 +17,8 @@ int cuda_fail(cudaError_t e, const char* what);
 bool tc_layer_supported(const TempRgcnLayerArgs* a);
 int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st);
 int tc_gather_grid(const TempRgcnLayerArgs* a);
+int tc_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st);
+int tc_gather_launches(const TempRgcnLayerArgs* a);
 bool tc_scan_supported(const TempGruScanArgs* a);
 int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
 // gru_scan_tm_kernel (tc_scan2.cu): one recurrent cell, partitions of <= 48 rows per step; tc_launch_scan dispatches to it

@@ -19,6 +19,7 @@
 //        columns) of a 4-CTA cluster, tiles of <= 96 rows per partition step; its W_hh slice (r|z|n rows, hi/lo) stays
 //        in shared memory for the whole scan; steps are separated by the hardware cluster barrier.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <utility>
@@ -210,6 +211,134 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 5) rgcn_gather_kernel(const
   float4 a = gather_edges(p, p0, p1, nrm, lane);
   a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;  // apply_func (RGCN.py:103-104)
   reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * kD)[lane] = a;
+}
+
+// The same aggregation with the neighbour rows STREAMED INTO SHARED MEMORY BY THE TMA ENGINE (cp.async.bulk, one 512-byte
+// row per copy, completion counted in bytes on an mbarrier) -- the north star's formulation.  A warp takes four light
+// destination rows at a time; their (<= 32) edges are spread over the lanes, every lane issues the bulk copy of its own
+// source row into the warp's 16-slot ring, so up to 16 rows (8 KB) per warp are in flight without holding registers;
+// the reduction then walks the slots in edge order: the arithmetic (and therefore every bit of the result) is that of
+// rgcn_gather_kernel.  High in-degree rows keep the thread-block path.  Which of the two runs is a measured choice
+// (DESIGN.md section 8): TEMP_GATHER=ldg|bulk overrides it.
+constexpr int kBulkSlots = 16;                  // 512-byte row slots per warp
+constexpr int kBulkRows = 4;                    // destination rows per warp batch
+constexpr int kBulkSmem = kGatherWarps * kBulkSlots * 512;   // 64 KB per CTA -> 3 CTAs (24 warps) per SM
+
+__global__ void __launch_bounds__(kGatherWarps * 32, 3) rgcn_gather_bulk_kernel(const TempRgcnLayerArgs p) {
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ uint64_t bars[kGatherWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  if (static_cast<int>(blockIdx.x) < p.n_agg_heavy) {
+    // ---- a high in-degree row: the block's 8 warps sum contiguous edge chunks, partials added in chunk order ----
+    __shared__ float4 part[kGatherWarps][32];
+    const int t = lane < 3 ? __ldg(p.agg_heavy + 3 * static_cast<size_t>(blockIdx.x) + lane) : 0;
+    const int r = __shfl_sync(kFull, t, 0), p0 = __shfl_sync(kFull, t, 1), p1 = __shfl_sync(kFull, t, 2);
+    const float nrm = __ldg(p.norm + r);
+    const int chunk = (p1 - p0 + kGatherWarps - 1) / kGatherWarps;
+    const int e0 = min(p0 + warp * chunk, p1), e1 = min(e0 + chunk, p1);
+    part[warp][lane] = gather_edges(p, e0, e1, nrm, lane);
+    __syncthreads();
+    if (warp == 0) {
+      float4 a = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < kGatherWarps; ++w) {
+        const float4 b = part[w][lane];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;
+      reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * kD)[lane] = a;
+    }
+    return;
+  }
+  if (lane == 0) {
+    mbar_init(&bars[warp], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const int batch = (static_cast<int>(blockIdx.x) - p.n_agg_heavy) * kGatherWarps + warp;
+  const int item0 = batch * kBulkRows;
+  if (item0 >= p.n_agg_rows) return;
+  const int n_rows = min(kBulkRows, p.n_agg_rows - item0);
+  // lane k < n_rows: work-list entry k of the batch (row, first edge, end edge) and the row's norm
+  int row = 0, e0 = 0, deg = 0;
+  float nrm = 0.f;
+  if (lane < n_rows) {
+    const int* it = p.agg_rows + 3 * static_cast<size_t>(item0 + lane);
+    row = __ldg(it);
+    e0 = __ldg(it + 1);
+    deg = __ldg(it + 2) - e0;
+    nrm = __ldg(p.norm + row);
+  }
+  int off[kBulkRows + 1];
+  off[0] = 0;
+#pragma unroll
+  for (int k = 0; k < kBulkRows; ++k) off[k + 1] = off[k] + __shfl_sync(kFull, deg, k);
+  const int total = off[kBulkRows];            // <= 4 * 8 = 32 edges: one per lane
+  // lane q < total: edge q of the batch -> (row slot, source row, relation)
+  int k_of = 0, src = 0, rel = 0;
+  if (lane < total) {
+#pragma unroll
+    for (int k = 1; k < kBulkRows; ++k) k_of += lane >= off[k] ? 1 : 0;
+  }
+  const int e0_of = __shfl_sync(kFull, e0, k_of);
+  int off_of = 0;
+#pragma unroll
+  for (int k = 1; k < kBulkRows; ++k) off_of = k_of >= k ? off[k] : off_of;
+  if (lane < total) {
+    const int e = e0_of + (lane - off_of);
+    src = __ldg(p.e_src + e);
+    rel = __ldg(p.e_rel + e);
+  }
+  const uint32_t ring = smem_u32(ring_raw) + warp * (kBulkSlots * 512);
+  const float4* w4 = reinterpret_cast<const float4*>(p.weight) + lane;
+  float4 acc[kBulkRows];
+#pragma unroll
+  for (int k = 0; k < kBulkRows; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();   // the source rows are the previous layer's output
+  uint32_t phase = 0;
+  for (int base = 0; base < total; base += kBulkSlots) {
+    const int cnt = min(kBulkSlots, total - base);
+    fence_proxy_async();   // the slots' previous readers (generic proxy) before the engine's writes
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&bars[warp], static_cast<uint32_t>(cnt) * 512u);
+    __syncwarp();
+    if (lane >= base && lane < base + cnt) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       ring + (lane - base) * 512),
+                   "l"(p.x + static_cast<size_t>(src) * kD), "r"(512), "r"(smem_u32(&bars[warp]))
+                   : "memory");
+    }
+    mbar_wait(&bars[warp], phase);
+    phase ^= 1;
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const int q = base + j;
+      const int kq = __shfl_sync(kFull, k_of, q), rq = __shfl_sync(kFull, rel, q);
+      const float nq = __shfl_sync(kFull, nrm, kq);
+      float4 hv;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(hv.x), "=f"(hv.y), "=f"(hv.z), "=f"(hv.w) : "r"(ring + j * 512 + lane * 16));
+      const float4 wv = __ldg(w4 + static_cast<size_t>(rq) * (kD / 4));
+      // msg = (h * w) * norm_e, summed in edge order (RGCN.py:92-97)
+      const float mx = (hv.x * wv.x) * nq, my = (hv.y * wv.y) * nq, mz = (hv.z * wv.z) * nq, mw = (hv.w * wv.w) * nq;
+#pragma unroll
+      for (int k = 0; k < kBulkRows; ++k) {
+        if (kq == k) {   // warp-uniform
+          acc[k].x += mx; acc[k].y += my; acc[k].z += mz; acc[k].w += mw;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kBulkRows; ++k) {
+    const int rk = __shfl_sync(kFull, row, k);
+    const float nk = __shfl_sync(kFull, nrm, k);
+    if (k < n_rows) {
+      float4 a = acc[k];
+      a.x *= nk; a.y *= nk; a.z *= nk; a.w *= nk;  // apply_func (RGCN.py:103-104)
+      reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(rk) * kD)[lane] = a;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -955,6 +1084,33 @@ int tc_gather_grid(const TempRgcnLayerArgs* a) {
   return (a->row1 - a->row0 + kGatherWarps - 1) / kGatherWarps;
 }
 
+// kernel launches of the aggregation (0 or 1)
+int tc_gather_launches(const TempRgcnLayerArgs* a) { return tc_gather_grid(a) > 0 ? 1 : 0; }
+
+// the aggregation launch alone (also behind temp_rgcn_gather_fwd).  LDG rows (a warp per destination row, two feature
+// rows in flight) or the TMA bulk-copy ring: measured on B200 (tools/bench_gather.py, x16 shapes, L2 flushed) the ring is
+// 5 % faster on ICEWS14-shaped rows (55.3 vs 58.3 us) and 33 % slower on GDELT-shaped rows (697 vs 523 us: 64 KB of ring per
+// CTA leaves 24 instead of 40 warps per SM for the high in-degree rows) -- LDG is the default, TEMP_GATHER=bulk opts in.
+int tc_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st) {
+  static const char* mode = getenv("TEMP_GATHER");
+  const bool bulk = mode != nullptr && strcmp(mode, "bulk") == 0;
+  if (bulk && a->agg_lists != 0) {
+    static bool configured = false;
+    if (int rc = ensure_smem_once(rgcn_gather_bulk_kernel, kBulkSmem, "rgcn_gather_bulk_kernel", configured)) return rc;
+    const int batches = (a->n_agg_rows + kBulkRows - 1) / kBulkRows;
+    const int grid = a->n_agg_heavy + (batches + kGatherWarps - 1) / kGatherWarps;
+    if (grid <= 0) return TEMP_OK;
+    cudaError_t e = launch_pdl(rgcn_gather_bulk_kernel, grid, kGatherWarps * 32, kBulkSmem, st, *a);
+    if (e != cudaSuccess) return cuda_fail(e, "rgcn_gather_bulk_kernel launch");
+    return TEMP_OK;
+  }
+  const int grid = tc_gather_grid(a);
+  if (grid <= 0) return TEMP_OK;
+  cudaError_t e = launch_pdl(rgcn_gather_kernel, grid, kGatherWarps * 32, 0, st, *a);
+  if (e != cudaSuccess) return cuda_fail(e, "rgcn_gather_kernel launch");
+  return TEMP_OK;
+}
+
 bool tc_layer_supported(const TempRgcnLayerArgs* a) {
   if (a->d != kD || a->n_terms != 1) return false;
   const TempDenseTerm& t = a->terms[0];
@@ -975,8 +1131,7 @@ int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   const int rows = a->row1 - a->row0;
   const int gather_grid = tc_gather_grid(a);
   if (gather_grid > 0) {
-    cudaError_t eg = launch_pdl(rgcn_gather_kernel, gather_grid, kGatherWarps * 32, 0, st, *a);
-    if (eg != cudaSuccess) return cuda_fail(eg, "rgcn_gather_kernel launch");
+    if (int rc = tc_launch_gather(a, st)) return rc;
   }
   const int grid = (rows + kTileRows - 1) / kTileRows;
   cudaError_t e = launch_pdl(rgcn_layer_tc_kernel, grid, kLayerThreads, kLayerSmem, st, *a);

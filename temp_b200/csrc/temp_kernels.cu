@@ -1474,6 +1474,14 @@ int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream) {
 
 int temp_gru_fwd(const TempGruArgs* args, void* stream) { return launch_gru(args, static_cast<cudaStream_t>(stream)); }
 
+int temp_rgcn_gather_fwd(const TempRgcnLayerArgs* args, void* stream) {
+  if (args == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
+  if (args->d != 128 || args->row_ptr == nullptr || args->si != 1 || args->so != 1 || args->agg_scratch == nullptr ||
+      args->x == nullptr || args->weight == nullptr || args->norm == nullptr || args->e_src == nullptr || args->e_rel == nullptr)
+    return fail(TEMP_EUNSUPPORTED, "temp_rgcn_gather_fwd: d == 128, 1x1 relation blocks and an aggregate buffer are required%s", "");
+  return temp_internal::tc_launch_gather(args, static_cast<cudaStream_t>(stream));
+}
+
 int temp_gru_scan_fwd(const TempGruScanArgs* args, void* stream) {
   return launch_scan(args, static_cast<cudaStream_t>(stream));
 }
@@ -1534,7 +1542,7 @@ int temp_program_kernel_count(const TempOp* ops, int32_t n) {
       case TEMP_OP_LAYER: {
         const TempRgcnLayerArgs& a = ops[i].u.layer;
         if (a.row1 > a.row0)
-          k += (temp_internal::tc_layer_supported(&a) && temp_internal::tc_gather_grid(&a) > 0) ? 2 : 1;
+          k += 1 + (temp_internal::tc_layer_supported(&a) ? temp_internal::tc_gather_launches(&a) : 0);
         break;
       }
       case TEMP_OP_GRU: k += ops[i].u.gru.row1 > ops[i].u.gru.row0 ? 1 : 0; break;

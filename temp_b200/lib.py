@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -125,7 +125,7 @@ class Op(C.Structure):
     _fields_ = [("kind", _i32), ("reserved", _i32), ("u", _OpUnion)]
 
 
-EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_gru_fwd",
+EXPORTS = ("temp_abi_version", "temp_last_error_string", "temp_device_info", "temp_rgcn_layer_fwd", "temp_rgcn_gather_fwd", "temp_gru_fwd",
            "temp_gru_scan_fwd", "temp_attention_fwd", "temp_gather_rows", "temp_scatter_rows", "temp_transpose", "temp_run_program",
            "temp_packed_weights_bytes", "temp_pack_weights", "temp_packed_gru_bytes", "temp_pack_gru_weights",
            "temp_program_kernel_count", "temp_score_loss_fwd", "temp_score_loss_bwd", "temp_rank_filtered_fwd", "temp_negative_sample", "temp_plan_window", "temp_plan_destroy", "temp_plan_counts",
@@ -152,6 +152,7 @@ def load(path: Optional[str] = None):
     lib.temp_last_error_string.restype = C.c_char_p
     lib.temp_device_info.argtypes = [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]
     lib.temp_rgcn_layer_fwd.argtypes = [C.POINTER(RgcnLayerArgs), _p]
+    lib.temp_rgcn_gather_fwd.argtypes = [C.POINTER(RgcnLayerArgs), _p]
     lib.temp_gru_fwd.argtypes = [C.POINTER(GruArgs), _p]
     lib.temp_gru_scan_fwd.argtypes = [C.POINTER(GruScanArgs), _p]
     lib.temp_attention_fwd.argtypes = [C.POINTER(AttnArgs), _p]
