@@ -70,8 +70,12 @@ class EvaluationFilter(object):
         D = int(all_ent_embeds.shape[1])
         from .scores import complex_score, distmult, transE
         fn = {distmult: "distmult", complex_score: "complex", transE: "transE"}.get(self.calc_score)
-        if fn is None or not all_ent_embeds.is_cuda or D % 32 or D > 256:
+        if fn is None or not all_ent_embeds.is_cuda or D % 4 or D > 256:
             return self.calc_metrics_single_graph_torch(ent_mean, rel_enc_means, all_ent_embeds, samples, graph, time, eval_bz)
+        if D % 32:                                  # e.g. d = 200 (n_bases = 100): zero-padded channels, see scores.pad_channels
+            from .scores import pad_channels
+            ent_mean, rel_enc_means, all_ent_embeds = (pad_channels(x.detach(), fn) for x in (ent_mean, rel_enc_means, all_ent_embeds))
+            D = int(all_ent_embeds.shape[1])
         from . import lib
         with torch.no_grad():
             dev = all_ent_embeds.device

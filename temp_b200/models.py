@@ -288,9 +288,10 @@ class TKG_Module(nn.Module):
     fused_scorer = True          # False: the reference's materialised torch formulation (kept for comparison / other sizes)
 
     def train_link_prediction(self, ent_embed, triplets, neg_samples, labels, all_embeds_g, corrupt_tail=True):
-        """models/TKG_Module.py:202-213.  On CUDA (d % 32 == 0) the gather + score + cross-entropy run fused in one
-        kernel (``scores.fused_link_prediction_loss``; the labels of the reference's sampler are all zero)."""
-        if all_embeds_g.is_cuda and self.embed_size % 32 == 0 and self.embed_size <= 256 and self.fused_scorer:
+        """models/TKG_Module.py:202-213.  On CUDA the gather + score + cross-entropy run fused in one kernel
+        (``scores.fused_link_prediction_loss``; the labels of the reference's sampler are all zero; widths that are not a
+        multiple of 32 -- d = 200 of the n_bases = 100 configuration -- run zero-padded)."""
+        if all_embeds_g.is_cuda and self.embed_size % 4 == 0 and self.embed_size <= 256 and self.fused_scorer:
             from .scores import fused_link_prediction_loss
             return fused_link_prediction_loss(ent_embed, self.rel_embeds, triplets, neg_samples, all_embeds_g,
                                               getattr(self.args, "score_function", "complex"), corrupt_tail)

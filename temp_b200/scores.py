@@ -5,6 +5,7 @@ materialised -- with its backward ``temp_score_loss_bwd`` for training."""
 import ctypes as C
 
 import torch
+import torch.nn.functional as F
 
 
 def _per_positive_loss(ent_embed, rel_embeds, table, triplets, cand, score_function, corrupt_tail):
@@ -46,12 +47,29 @@ class _FusedLinkPredictionLoss(torch.autograd.Function):
         return g_ent, g_rel, g_table, None, None, None, None
 
 
+def pad_channels(x, score_function="complex"):
+    """Zero-pads the channel axis of ``x [n, d]`` to the next multiple of 32 -- the width the scorer / ranking kernels split
+    over the lanes of a warp (e.g. d = 200, the reference's n_bases = 100 configuration, -> 224).  ComplEx keeps its
+    (real | imaginary) halves: each half is padded on its own.  Zero channels add nothing to any of the three scores
+    (bilinear products, or |0 + 0 - 0| for TransE), and the padding is a differentiable torch op."""
+    d = int(x.shape[-1])
+    if d % 32 == 0:
+        return x
+    d_pad = (d + 31) // 32 * 32
+    if score_function == "complex":
+        h, hp = d // 2, d_pad // 2
+        return torch.cat([F.pad(x[..., :h], (0, hp - h)), F.pad(x[..., h:], (0, hp - h))], dim=-1)
+    return F.pad(x, (0, d_pad - d))
+
+
 def fused_link_prediction_loss(ent_embed, rel_embeds, triplets, cand, table, score_function="complex", corrupt_tail=True):
     """mean_p [ logsumexp_c score(p, c) - score(p, 0) ]  ==  F.cross_entropy(calc_score(...), zeros)  of
     TKG_Module.train_link_prediction.  ``triplets`` [P, 3] and ``cand`` [P, 1 + neg] are int64 CUDA tensors.
     Differentiable w.r.t. ``ent_embed``, ``rel_embeds`` and ``table`` when gradients are enabled."""
     if int(cand.shape[0]) == 0:
         return table.new_zeros(())
+    if int(table.shape[-1]) % 32 != 0:
+        ent_embed, rel_embeds, table = (pad_channels(x, score_function) for x in (ent_embed, rel_embeds, table))
     if torch.is_grad_enabled() and (ent_embed.requires_grad or rel_embeds.requires_grad or table.requires_grad):
         return _FusedLinkPredictionLoss.apply(ent_embed, rel_embeds, table, triplets, cand, score_function, corrupt_tail)
     return _per_positive_loss(ent_embed.detach().contiguous(), rel_embeds.detach().contiguous(), table.detach().contiguous(),

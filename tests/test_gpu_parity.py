@@ -178,7 +178,7 @@ def test_training_forward_loss_matches_reference(tc):
 
 @pytest.mark.parametrize("score_fn", ["complex", "distmult", "transE"])
 @pytest.mark.parametrize("corrupt_tail", [True, False])
-@pytest.mark.parametrize("shape", [(37, 11, 128, 300), (1, 501, 128, 7128), (513, 64, 64, 50)])
+@pytest.mark.parametrize("shape", [(37, 11, 128, 300), (1, 501, 128, 7128), (513, 64, 64, 50), (29, 21, 200, 310)])
 def test_fused_scorer_matches_torch_reference_path(score_fn, corrupt_tail, shape):
     """temp_score_loss_fwd (gather + score + cross-entropy fused) against the reference's formulation
     (TKG_Module.train_link_prediction: materialised gather, utils/scores.py, F.cross_entropy) in torch fp32."""
@@ -220,7 +220,7 @@ def test_fused_peer_all_gather_matches_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert "verified against NCCL" in line["config"]["exchange"]
+    assert "verified against NCCL" in line["exchange"]
 
 
 def test_launch_program_as_cuda_graph_is_bit_identical():
@@ -262,7 +262,7 @@ def test_autograd_fallback_loss_equals_cuda_forward(name):
 
 @pytest.mark.parametrize("fn", ["complex", "distmult", "transE"])
 @pytest.mark.parametrize("corrupt_tail", [True, False])
-@pytest.mark.parametrize("D", [32, 128, 224])
+@pytest.mark.parametrize("D", [32, 128, 224, 200])
 def test_fused_scorer_backward_matches_torch_autograd(fn, corrupt_tail, D):
     """temp_score_loss_bwd (scores recomputed, candidate-row gradients by vector atomics) against autograd through the
     reference's materialised formulation (models/TKG_Module.py:202-213): gradients w.r.t. the graph's node states, the
