@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the fused peer stores")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
+    ap.add_argument("--multimem", action="store_true", help="N > 1: NVLS multimem.st.v4 (one switch-replicated store) instead of "
+                                                            "one NVLink store per peer")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -265,7 +267,7 @@ def main():
         from temp_b200.exchange import FinalStateAllGather
         rows_t = torch.tensor([max(n_final)], device=dev)
         dist.all_reduce(rows_t, op=dist.ReduceOp.MAX)
-        ex = FinalStateAllGather(dev, int(rows_t.item()), D, nccl=args.nccl_exchange)
+        ex = FinalStateAllGather(dev, int(rows_t.item()), D, nccl=args.nccl_exchange, multimem=args.multimem)
         exchange = ex.how
         if ex.fused:                                             # verify once against NCCL
             r0 = model.encode(t_lists[0], exchange=ex)
@@ -306,10 +308,6 @@ def main():
     d2h_bytes = int(r0.host_out.numel() * 4)
     if world > 1:
         dist.barrier()
-    for i in range(4):               # (untimed: the first steps after a host-synchronising collective run cold)
-        step_device(i)
-    torch.cuda.synchronize()
-
     sampler = ClockSampler(local_rank)
     sampler.start()
     # ---- device-timed arm: per step, flush L2, line the ranks up (untimed), then start event -> step -> end event ------
@@ -318,14 +316,16 @@ def main():
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
     launches = 0
-    for i in range(K):
-        flush.fill_(float(i))
+    for i in range(-4, K):           # the same loop body for 4 untimed lead-in steps (the first steps after the host was
+        flush.fill_(float(i))        # idle in a synchronise run cold: clocks, instruction caches) and the K timed ones
         if ex is not None:
-            ex.align()          # no rank's timed step absorbs its peers' untimed flush / launch skew
-        starts[i].record()
-        res = step_device(i)
-        ends[i].record()
-        launches += res.program.kernel_count() + (1 if (ex is not None and ex.fused) else 0)
+            ex.align()               # no rank's timed step absorbs its peers' untimed flush / launch skew
+        if i >= 0:
+            starts[i].record()
+        res = step_device(i % len(t_lists))
+        if i >= 0:
+            ends[i].record()
+            launches += res.program.kernel_count() + (1 if (ex is not None and ex.fused) else 0)
     torch.cuda.synchronize()
     wall_dev = time.perf_counter() - wall0
     if world > 1:
@@ -406,6 +406,7 @@ def main():
         dist.all_gather(allr, mine)
         per_rank = [{"rank": k, "step_ms_min": float(a[0]), "step_ms_median": float(a[1]), "step_ms_max": float(a[2]),
                      "step_ms_mean": float(a[3])} for k, a in enumerate(allr)]
+        per_rank[0]["step_ms_first_24"] = [round(float(x), 4) for x in step_ms[:24]]
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         max_e2e = float(t[0].item())

@@ -182,7 +182,8 @@ typedef struct {
                                 at <= 48 rows whose steps all use ONE recurrent cell run on gru_scan_tm_kernel (W_hh in
                                 tensor memory, four partition pipelines per CTA), the others on gru_scan_tc_kernel            */
   float* push_multicast;     /* nullable: NVLS multicast address of the same symmetric buffer -- one multimem.st per
-                                value instead of one store per peer (the switch replicates it to every GPU)           */
+                                value instead of one store per peer (the switch replicates it to every GPU); push_bufs then
+                                lists only buffers OUTSIDE the multicast group (e.g. a pinned host buffer; push_world >= 0) */
   TempGruArgs steps[TEMP_MAX_SCAN_STEPS];
 } TempGruScanArgs;
 

@@ -508,15 +508,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           for (int k = 0; k < kCluster; ++k) st_async_f32x4(peer_stage[k] + off, hy, peer_bar[k]);
         }
         *o = hy;
-        if (p.push != 0 && P.push_bufs != nullptr) {   // NVLink stores into every peer's slab (TempGruScanArgs.push_*)
+        if (p.push != 0 && (P.push_bufs != nullptr || P.push_multicast != nullptr)) {   // NVLink stores into every peer's slab
           const size_t po = static_cast<size_t>(r - P.push_row0) * kD + j4;
-          if (P.push_multicast != nullptr) {
+          if (P.push_multicast != nullptr) {   // one 16-byte store, replicated to every GPU by the NVSwitch (NVLS)
             asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.push_multicast + P.push_offset + po),
                          "f"(hy.x), "f"(hy.y), "f"(hy.z), "f"(hy.w)
                          : "memory");
-          } else {
-            for (int k = 0; k < P.push_world; ++k) *reinterpret_cast<float4*>(S.push[k] + po) = hy;
           }
+          // (with a multicast address push_bufs lists only the buffers OUTSIDE the multicast group, e.g. a host buffer)
+          for (int k = 0; k < P.push_world; ++k) *reinterpret_cast<float4*>(S.push[k] + po) = hy;
         }
       }
     }
@@ -573,7 +573,8 @@ bool tc_scan2_supported(const TempGruScanArgs* a) {
       w = g.whh_packed;
     }
   }
-  if (a->push_bufs != nullptr && (a->push_world <= 0 || a->push_world > TEMP_MAX_PUSH_PEERS)) return false;
+  if (a->push_bufs != nullptr && (a->push_world < 0 || a->push_world > TEMP_MAX_PUSH_PEERS)) return false;
+  if (a->push_bufs != nullptr && a->push_world == 0 && a->push_multicast == nullptr) return false;
   return true;
 }
 

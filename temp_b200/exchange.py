@@ -57,7 +57,7 @@ class FinalStateAllGather(object):
     """``model.encode(t_list, exchange=ex)``: after the call (and on the same stream) ``ex.gathered(k)`` holds rank k's
     final-layer states of the step just run, on every rank."""
 
-    def __init__(self, device, max_rows: int, d: int, group=None, nccl: bool = False):
+    def __init__(self, device, max_rows: int, d: int, group=None, nccl: bool = False, multimem: bool = False):
         import torch.distributed as dist
         self.device, self.max_rows, self.d = device, int(max_rows), int(d)
         self.group = group if group is not None else dist.group.WORLD
@@ -69,8 +69,16 @@ class FinalStateAllGather(object):
             try:
                 self.peers = PeerGroup(device, self.group)
                 self.slabs, self.slab_ptrs, self._hdl = self.peers.alloc((2, self.world, self.max_rows, self.d))
-                self.how = ("fused into the scan kernel: one NVLink store per peer into double-buffered symmetric memory + "
-                            "one signal/wait launch (temp_peer_barrier)")
+                self.multicast = 0
+                if multimem:
+                    try:
+                        if self._hdl.has_multicast_support:
+                            self.multicast = int(self._hdl.multicast_ptr)
+                    except Exception:
+                        self.multicast = 0
+                self.how = ("fused into the scan kernel: %s into double-buffered symmetric memory + one signal/wait launch "
+                            "(temp_peer_barrier)" % ("NVLS multimem.st.v4 (one 16-byte store, replicated by the NVSwitch)"
+                                                     if self.multicast else "one NVLink store per peer"))
             except Exception as ex:                                   # symmetric memory unavailable: NCCL between launches
                 if self.peers is not None and hasattr(self, "slabs"):
                     raise
@@ -96,14 +104,15 @@ class FinalStateAllGather(object):
         res.exchange_programs = []
         for parity in (0, 1):
             off = (parity * self.world + self.rank) * self.max_rows * self.d
-            ptr_list = [int(p) for p in self.slab_ptrs.tolist()]
+            ptr_list = [] if self.multicast else [int(p) for p in self.slab_ptrs.tolist()]
             if host_out is not None:
                 ptr_list.append(host_out.data_ptr() - 4 * off)
-            ptrs = torch.tensor(ptr_list, dtype=torch.int64, device=self.device)
+            ptrs = torch.tensor(ptr_list or [0], dtype=torch.int64, device=self.device)
             prog = lib.Program()
             prog.ops = [lib.Op.from_buffer_copy(o) for o in res.program.ops]
             prog.keepalive = list(res.program.keepalive) + [ptrs] + ([host_out] if host_out is not None else [])
-            prog.enable_peer_push(ptrs.data_ptr(), len(ptr_list), off, fin.row0, fin.row1)
+            prog.enable_peer_push(ptrs.data_ptr() if ptr_list else 0, len(ptr_list), off, fin.row0, fin.row1,
+                                  multicast_ptr=self.multicast)
             res.exchange_programs.append(prog)
 
     def run(self, res, reupload: bool = True) -> None:

@@ -293,7 +293,7 @@ class Program(object):
         for i in range(sc.n_steps):
             sc.steps[i].push = 0
         sc.steps[last[-1]].push = 1
-        sc.push_bufs, sc.push_world, sc.push_offset, sc.push_row0 = bufs_dev_ptr, int(world), int(offset_elems), int(row0)
+        sc.push_bufs, sc.push_world, sc.push_offset, sc.push_row0 = bufs_dev_ptr or None, int(world), int(offset_elems), int(row0)
         sc.push_multicast = multicast_ptr or None
         self._arr = None
 
