@@ -15,8 +15,10 @@ final-layer entity states) over one batch of 8 windows = 64 snapshot instances.
           around each step (stream-synchronised); window planning is pre-built, as the reference
           pre-builds its graph dictionaries -- its cost per step is reported separately as plan_ms
   N > 1 : one process per GPU (torchrun); every rank runs its own batch of windows (weak scaling, the
-          reference's DistributedSampler sharding of target timestamps) and the step ends with an NCCL
-          all-gather of the final-layer states of all ranks; value = edges of all ranks / max time.
+          reference's DistributedSampler sharding of target timestamps) and the step ends with the all-gather of
+          the final-layer states of all ranks, FUSED into the scan kernel (NVLS multimem / peer stores into
+          symmetric memory + one signal/wait launch; --nccl-exchange = the NCCL partner); value = edges of all
+          ranks / max-over-ranks time.  A secondary arm times the snapshot-sharded split of config 5.
 """
 import argparse
 import json
@@ -220,8 +222,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the fused peer stores")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the secondary snapshot-sharded measurement")
-    ap.add_argument("--multimem", action="store_true", help="N > 1: NVLS multimem.st.v4 (one switch-replicated store) instead of "
-                                                            "one NVLink store per peer")
+    ap.add_argument("--no-multimem", action="store_true", help="N > 1: one NVLink store per peer instead of the NVLS "
+                    "multimem.st.v4 store (one 16-byte store replicated by the switch; the default where supported)")
     ap.add_argument("--scaled", type=int, default=16, help="extra roofline measurement at this scale (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -267,7 +269,7 @@ def main():
         from temp_b200.exchange import FinalStateAllGather
         rows_t = torch.tensor([max(n_final)], device=dev)
         dist.all_reduce(rows_t, op=dist.ReduceOp.MAX)
-        ex = FinalStateAllGather(dev, int(rows_t.item()), D, nccl=args.nccl_exchange, multimem=args.multimem)
+        ex = FinalStateAllGather(dev, int(rows_t.item()), D, nccl=args.nccl_exchange, multimem=not args.no_multimem)
         exchange = ex.how
         if ex.fused:                                             # verify once against NCCL
             r0 = model.encode(t_lists[0], exchange=ex)

@@ -1094,7 +1094,13 @@ __global__ void __launch_bounds__(kThreads, PER4 <= 4 ? 2 : 1) rank_filtered_ker
 __global__ void peer_barrier_kernel(uint32_t* flags_local, uint32_t* const* flag_peers, int world, int rank, uint32_t seq) {
   const int k = threadIdx.x;
   if (k >= world) return;
-  uint32_t* remote = flag_peers[k] + rank;
+  uint32_t* remote = flag_peers[k] + rank;   // (kernel parameters and this table are not written by the predecessor)
+  // launched with programmatic stream serialization: resident while the step's last kernel still runs, so the signal
+  // leaves as soon as that grid has completed and flushed instead of one launch latency later
+  // (and the next step's first kernel may become resident behind it: every kernel of this library reads predecessor data
+  // only after its own griddepcontrol.wait, which waits for THIS grid's completion, i.e. for all peers' signals)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(seq) : "memory");
   const uint32_t* mine = flags_local + k;
   uint32_t v;
@@ -1589,8 +1595,16 @@ int temp_peer_barrier(uint32_t* flags_local, uint32_t* const* flag_peers, int32_
                       void* stream) {
   if (flags_local == nullptr || flag_peers == nullptr || world <= 0 || world > 32 || rank < 0 || rank >= world)
     return fail(TEMP_EINVAL, "bad peer barrier args%s", "");
-  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags_local, flag_peers, world, rank, seq);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(32);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, peer_barrier_kernel, flags_local, flag_peers, world, rank, seq);
   if (e != cudaSuccess) return cuda_fail(e, "peer_barrier_kernel launch");
   return TEMP_OK;
 }

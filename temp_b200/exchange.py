@@ -57,7 +57,7 @@ class FinalStateAllGather(object):
     """``model.encode(t_list, exchange=ex)``: after the call (and on the same stream) ``ex.gathered(k)`` holds rank k's
     final-layer states of the step just run, on every rank."""
 
-    def __init__(self, device, max_rows: int, d: int, group=None, nccl: bool = False, multimem: bool = False):
+    def __init__(self, device, max_rows: int, d: int, group=None, nccl: bool = False, multimem: bool = True):
         import torch.distributed as dist
         self.device, self.max_rows, self.d = device, int(max_rows), int(d)
         self.group = group if group is not None else dist.group.WORLD
