@@ -24,6 +24,8 @@
 
 #include <utility>
 
+#include <type_traits>
+
 #include "internal.h"
 #include "tc_common.cuh"
 
@@ -536,9 +538,22 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
       rtA = __ldg(p.row_time + min(R0 + lane, p.row1 - 1));
       rtB = __ldg(p.row_time + min(R0 + 32 + lane, p.row1 - 1));
     }
-    // rows of a tile mostly share a snapshot, i.e. a time-embedding row: reload on change only
-    int cur_trow = need_te ? __shfl_sync(kFull, rtA, 0) : -1;
-    float cur_te = need_te ? __ldg(p.time_embed + static_cast<size_t>(cur_trow) * kD + f) : 0.f;
+    // Rows are packed snapshot by snapshot, so the 64 rows of this thread see one or two time-embedding rows almost
+    // always: both are fetched up front and a row picks one by its index (fast path, no per-row shuffle / branch / load).
+    // Spans with three or more snapshots (tiny graphs) take the general walk that reloads on change.
+    const int t_first = need_te ? __shfl_sync(kFull, rtA, 0) : -1, t_last = need_te ? __shfl_sync(kFull, rtB, 31) : -1;
+    float te_a = 0.f, te_b = 0.f;
+    int te_split = 64;      // rows [0, te_split) of the span use te_a, the rest te_b
+    bool te_fast = true;
+    if (need_te) {
+      te_a = __ldg(p.time_embed + static_cast<size_t>(t_first) * kD + f);
+      te_b = __ldg(p.time_embed + static_cast<size_t>(t_last) * kD + f);
+      const unsigned long long is_first = static_cast<unsigned long long>(__ballot_sync(kFull, rtA == t_first)) |
+                                          (static_cast<unsigned long long>(__ballot_sync(kFull, rtB == t_first)) << 32);
+      const bool two = __all_sync(kFull, (rtA == t_first || rtA == t_last) && (rtB == t_first || rtB == t_last));
+      te_split = __popcll(is_first);
+      te_fast = two && is_first == (te_split >= 64 ? ~0ull : ((1ull << te_split) - 1ull));
+    }
     // the aggregate rows of this thread's 64 rows: all loads in flight while the self-loop MMA completes
     const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * kD + f;
     float ag[64];
@@ -547,39 +562,52 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     mbar_wait(&S.d1_full, 0);
     tc_fence_after();
     TL(4);
+    int cur_trow = t_first;
+    float cur_te = te_a;
+    auto epilogue1 = [&](auto fast_tag) {
+      constexpr bool kFast = decltype(fast_tag)::value;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v[16];
-      tmem_ld16(lane_base + 64 * hf + 16 * c, v);
-      tmem_ld_wait();
-      const int rt = c < 2 ? rtA : rtB;
-      const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * c)) * 1024u;
+      for (int c = 0; c < 4; ++c) {
+        float v[16];
+        tmem_ld16(lane_base + 64 * hf + 16 * c, v);
+        tmem_ld_wait();
+        const int rt = c < 2 ? rtA : rtB;
+        const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * c)) * 1024u;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = R0 + 16 * c + i;
-        const uint32_t off = grp + sw128_off(i, lane);
-        if (need_te) {
-          const int trow = __shfl_sync(kFull, rt, (16 * c + i) & 31);  // warp-uniform
-          if (trow != cur_trow) {
-            cur_trow = trow;
-            cur_te = __ldg(p.time_embed + static_cast<size_t>(trow) * kD + f);
+        for (int i = 0; i < 16; ++i) {
+          const int r = R0 + 16 * c + i;
+          const uint32_t off = grp + sw128_off(i, lane);
+          float te;
+          if (kFast) {
+            te = 16 * c + i < te_split ? te_a : te_b;
+          } else {
+            const int trow = __shfl_sync(kFull, rt, (16 * c + i) & 31);  // warp-uniform
+            if (trow != cur_trow) {
+              cur_trow = trow;
+              cur_te = __ldg(p.time_embed + static_cast<size_t>(trow) * kD + f);
+            }
+            te = cur_te;
+          }
+          float val = ag[16 * c + i];
+          if (p.residual) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
+          val += v[i];
+          val += bias;
+          if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
+          if (r < p.row1 && p.h_out != nullptr) p.h_out[static_cast<size_t>(r) * kD + f] = p.te_out ? val + te : val;
+          if (n_mb > 0) {
+            const float xx = r < p.row1 ? (p.te_chain ? val + te : val) : 0.f;
+            float hi, lo;
+            split_tf32(xx, hi, lo);
+            sts_f32(sb_hi + off, hi);
+            sts_f32(sb_lo + off, lo);
           }
         }
-        float val = ag[16 * c + i];
-        if (p.residual) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
-        val += v[i];
-        val += bias;
-        if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
-        if (r < p.row1 && p.h_out != nullptr) p.h_out[static_cast<size_t>(r) * kD + f] = p.te_out ? val + cur_te : val;
-        if (n_mb > 0) {
-          const float xx = r < p.row1 ? (p.te_chain ? val + cur_te : val) : 0.f;
-          float hi, lo;
-          split_tf32(xx, hi, lo);
-          sts_f32(sb_hi + off, hi);
-          sts_f32(sb_lo + off, lo);
-        }
       }
-    }
+    };
+    if (te_fast)
+      epilogue1(std::true_type{});
+    else
+      epilogue1(std::false_type{});
 
     TL(5);
     // ---- 4. chain epilogues: chain_out[r, 128 mb + f] = D2 + chain_b -----------------------------------
