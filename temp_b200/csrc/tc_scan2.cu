@@ -51,7 +51,10 @@ constexpr int kImage = 4 * kAtomBytes;            // hi (or lo) image of a tile:
 constexpr int kBufBytes = 2 * kImage;             // one operand tile: hi image, lo image
 constexpr int kPipeSmem = 2 * kBufBytes;          // two operand tiles per pipeline (steps alternate)
 constexpr int kMaxPipes = 2;
-constexpr int kSmem = kMaxPipes * kPipeSmem + 1024;
+constexpr int kWExtra = 32 * 1024;                // with the two operand regions (48 KB each): room for the 128 KB W_hh slice
+constexpr int kSmem = kMaxPipes * kPipeSmem + kWExtra + 1024;
+static_assert(2 * kBufBytes + kWExtra == 4 * kWChunkBytes, "the W_hh slice lands in the operand regions + the extra block");
+static_assert(kSmem <= 227 * 1024, "shared memory per CTA");
 constexpr int kTmemCols = 512;
 constexpr int kColWLo = 128;                      // W_hh hi parts at columns [0, 128), lo parts at [128, 256)
 constexpr int kColD = 256, kColDStride = 64;      // accumulator of pipeline p: columns [256 + 64 p, +48)
@@ -59,6 +62,7 @@ static_assert(kAtomBytes % 1024 == 0, "k-atom blocks must keep the 1024-byte swi
 static_assert(kColD + (kMaxPipes - 1) * kColDStride + kRows <= kTmemCols, "TMEM budget");
 
 struct Bars {
+  uint64_t w_full;                // the W_hh slice has landed in shared memory (bulk copies, bytes counted)
   uint64_t mma_done[kMaxPipes];
   uint64_t ready[kMaxPipes][2];   // operand tile b of a pipeline is complete (bytes counted: st.async from the four CTAs)
   uint32_t tmem_base;
@@ -160,6 +164,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const int rsub = lane >> 3, cq = lane & 7;                        // gate phase: row inside the warp's 4, column quad
 
   if (tid == 0) {
+    mbar_init(&S.w_full, 1);
     for (int i = 0; i < kMaxPipes; ++i) {
       mbar_init(&S.mma_done[i], 1);
       mbar_init(&S.ready[i][0], 1);
@@ -179,27 +184,52 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   TL(1);
 
   // ---- this CTA's W_hh slice -> tensor memory (parameters: not produced by the predecessor kernels) -----------------
-  // warp (quad, kq = warp >> 2): TMEM lanes 32 quad .. + 31 (feature rows m), k columns 32 kq .. + 31, read from the packed
-  // image of temp_pack_gru_weights (chunk (cb, kq): hi image, lo image 16 KB later, SWIZZLE_128B rows)
-  if (w_packed != nullptr) {
-    const int m = 32 * quad + lane, kq = warp >> 2;
-    const uint8_t* chunk = static_cast<const uint8_t*>(w_packed) + static_cast<size_t>(cb * 4 + kq) * kWChunkBytes;
+  // The slice (4 k-chunks x (hi image, lo image) x 16 KB, contiguous in temp_pack_gru_weights' layout) is fetched by the
+  // copy engine into shared memory that the FIRST tile step of a chained pipeline does not touch -- a partition's first
+  // step has no previous state, hence no operand tile and no MMA -- so the 128 KB L2 read overlaps that step instead of
+  // standing in front of it; install_w() (all warps, once) then moves it to TMEM: warp (quad, kq = warp >> 2) writes
+  // TMEM lanes 32 quad .. + 31 (feature rows m), k columns 32 kq .. + 31 of the hi and lo parts.
+  // 16 KB piece g = 2 kq + img: pieces 0-2 -> pipeline 0's operand region, 3-5 -> pipeline 1's, 6-7 -> the extra block.
+  auto w_piece = [&](int g) -> uint32_t {
+    const uint32_t base = smem_u32(smem);
+    return g < 3 ? base + g * 16384 : g < 6 ? base + kPipeSmem + (g - 3) * 16384 : base + kMaxPipes * kPipeSmem + (g - 6) * 16384;
+  };
+  if (w_packed != nullptr && tid == 0) {
+    const uint8_t* slice = static_cast<const uint8_t*>(w_packed) + static_cast<size_t>(cb) * 4 * kWChunkBytes;
+    mbar_expect_tx(&S.w_full, 4 * kWChunkBytes);
 #pragma unroll
-    for (int img = 0; img < 2; ++img) {
-      const uint8_t* rowp = chunk + img * (128 * 128) + (m >> 3) * 1024 + (m & 7) * 128;
-      float v[32];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(rowp + ((c ^ (m & 7)) << 4)));
-        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-      }
-      tmem_st32(tbase + (static_cast<uint32_t>(32 * quad) << 16) + img * kColWLo + kq * 32, v);
+    for (int g = 0; g < 8; ++g) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(w_piece(g)),
+                   "l"(slice + g * 16384), "r"(16384), "r"(smem_u32(&S.w_full))
+                   : "memory");
     }
-    tmem_st_wait();
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  auto install_w = [&]() {
+    if (w_packed != nullptr) {
+      const int m = 32 * quad + lane, kq = warp >> 2;
+      mbar_wait(&S.w_full, 0);
+#pragma unroll
+      for (int img = 0; img < 2; ++img) {
+        const uint32_t rowp = w_piece(2 * kq + img) + (m >> 3) * 1024 + (m & 7) * 128;
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = lds_f32x4(rowp + ((c ^ (m & 7)) << 4));
+          v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+        }
+        tmem_st32(tbase + (static_cast<uint32_t>(32 * quad) << 16) + img * kColWLo + kq * 32, v);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();   // every warp's part is in TMEM; the shared-memory copy may now be overwritten by operand tiles
+    tc_fence_after();
+  };
+  bool w_installed = false;
+  if (!kChained) {     // plain row tiles read a previous state (and multiply) in their first tile step already
+    install_w();
+    w_installed = true;
+  }
 
   // ---- this pipeline's tile steps: its partitions vc, vc + NV, ... ; all steps of a partition, then the next --------
   const int vc = pipe * n_clusters + cid, NV = kPipes * n_clusters;
@@ -533,7 +563,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     rgs = n_rgs;
     rgs_next = n_rgs_next;
     have = more;
+    if (!w_installed) {   // (pipeline-uniform; both pipelines meet here after their first tile step)
+      install_w();
+      w_installed = true;
+    }
   }
+  if (!w_installed) install_w();   // a pipeline without any tile step still takes part
 
   tc_fence_before();
   __syncthreads();
