@@ -31,7 +31,7 @@ def is_stale():
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    cmd = [nvcc_path(), "--threads", "4", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

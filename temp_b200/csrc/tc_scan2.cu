@@ -1,5 +1,6 @@
-// temp_b200 -- gru_scan_tm_kernel: the chain-partitioned GRU scan with W_hh resident in TENSOR MEMORY and four
-// independent partition pipelines per CTA (round 2; replaces gru_scan_tc_kernel for scans that use ONE recurrent cell).
+// temp_b200 -- gru_scan_tm_kernel: the chain-partitioned GRU scan with W_hh resident in TENSOR MEMORY, one or two
+// independent partition pipelines per CTA and the state handed from step to step through DISTRIBUTED SHARED MEMORY
+// (round 2; replaces gru_scan_tc_kernel for scans that use ONE recurrent cell).
 //
 // What the recurrence is (reference models/RRGCN.py:77-89, models/DynamicRGCN.py:156-174): per window step,
 //     h0 = decay(state[prev_row[r]]);  gh = h0 . W_hh^T + b_hh;  gates with the precomputed gi;  state[r] = h' (+ te)
@@ -8,24 +9,21 @@
 //
 // Why this shape (round-1 kernel: one <= 96-row tile in flight per 4-CTA cluster, W_hh as a 128 KB shared-memory image,
 // 8.7 % / 10 % of the HBM roofline, the step chain = cluster barrier -> L2 gather -> MMA -> gates -> release fence):
-//   * a step of ONE chain is latency (barrier, L2 round trip, MMA commit, fence), not work -- throughput comes from
-//     running several chains at once.  A CTA therefore runs kPipes = 4 pipelines, one warp group of 4 warps each; a
-//     pipeline owns its operand tile, its TMEM accumulator, its barriers, issues its own tcgen05.mma batch from one of
-//     its threads and never synchronises with the other pipelines (named barriers + mbarriers, no __syncthreads in the
-//     loop).  While one pipeline waits for its peers' state columns, the others gather / multiply / apply gates.
+//   * a step of ONE chain is latency, not work -- throughput comes from running several chains at once.  A CTA runs
+//     kPipes pipelines (16 / kPipes warps each); a pipeline owns its operand tile, its staging tiles, its TMEM
+//     accumulator and its barriers, issues its own tcgen05.mma batch and never synchronises with the other pipeline
+//     (named barriers + mbarriers, no __syncthreads and no cluster barrier in the loop).
 //   * W_hh lives in TMEM as the A operand (tcgen05.mma "TS" form): 128 lanes (r|z|n rows of this CTA's 32 hidden
 //     columns, 32 pad rows) x 128 k columns, hi and lo tf32 parts = 256 of the 512 columns.  An MMA then reads only its
-//     N x 8 activation slice from shared memory (1.5 KB at N = 48 instead of 4 KB + 1.5 KB), which is what makes
-//     small-N batches run at the tensor-pipe floor, and the 128 KB of shared memory the weight image used to take now
-//     holds the four operand tiles.
-//   * the cluster-wide step barrier (one hardware barrier per cluster, all 16 warps) is replaced by per-pipeline
-//     mbarriers signalled across the cluster: after its state stores a pipeline's elected thread issues one
-//     cluster-scope release fence and arrives on the pipeline's barrier in all four CTAs (mapa + mbarrier.arrive
-//     .release.cluster.shared::cluster); the consumers wait with acquire.cluster.  Two barriers per pipeline alternate
-//     so that a fast CTA's arrival for step t + 1 can never be counted into step t.
-//   * gate exchange without a second barrier: the accumulator holds gate g on TMEM lane quadrant g (rows = packed rows
-//     on columns); the three gate warps park their quadrant in the k-atoms of the dead operand image OTHER than this
-//     CTA's own (k-atom cb holds the h0 values of this CTA's hidden columns, which the z-gate still needs).
+//     N x 8 activation slice from shared memory, which is what makes N <= 48 batches run at the tensor-pipe floor
+//     (34.7 cycles per MMA, tools/probes/mma_probe.cu), and the shared memory the weight image used to take holds the
+//     pipelines' tiles.  The slice is fetched by bulk copies during the first tile step (which multiplies nothing).
+//   * the state never goes through L2 between the steps of a partition: every CTA stores its 32 columns of the new
+//     state into the next step's fp32 staging tile of all four CTAs with st.async; the consumer's mbarrier counts the
+//     bytes (no fence, no arrive instruction, no cluster barrier).  Two staging tiles alternate, and the parity skips
+//     one at a partition switch, so a fast CTA never writes a tile a slow peer still reads.
+//   * gate exchange without a second tile: the accumulator holds gate g on TMEM lane quadrant g (rows on columns); the
+//     three gate warps park their quadrant in the k-atoms of the dead operand image OTHER than this CTA's own.
 //
 // Layout conventions are those of tc_common.cuh: D^T[feature, row] ("features on TMEM lanes"), B = activations K-major
 // SWIZZLE_128B in shared memory, 3xTF32 operand split.
@@ -87,9 +85,6 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
-}
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // Development-only phase timeline (tools/probe_timeline2.py builds a separate library with -DTEMP_TIMELINE): lane 0 of
