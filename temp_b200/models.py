@@ -45,6 +45,17 @@ def _as_int_list(t_list) -> List[int]:
     return [int(t) for t in t_list]
 
 
+_PARAM_EPOCH = [0]
+
+
+def _bump_param_epoch(module, name, param):
+    _PARAM_EPOCH[0] += 1
+    return None
+
+
+torch.nn.modules.module.register_module_parameter_registration_hook(_bump_param_epoch)
+
+
 class TKG_Module(nn.Module):
     family = "recurrent"
 
@@ -230,8 +241,14 @@ class TKG_Module(nn.Module):
 
     def _encode_cache_for_current_weights(self) -> dict:
         rt = self.runtime
+        # the flat parameter list is kept between calls (walking the module tree costs more than the rest of a cached
+        # encode); any parameter registered anywhere since -- Module.__setattr__ goes through register_parameter -- bumps a
+        # global epoch and the list is rebuilt.  In-place updates (optimizer steps, load_state_dict, .to()) keep the
+        # Parameter objects and show up as a new version / data pointer below.
+        if getattr(self, "_param_list_epoch", None) != _PARAM_EPOCH[0]:
+            self._param_list, self._param_list_epoch = list(self.parameters()), _PARAM_EPOCH[0]
         stamp = (id(self.graph_dict_train), len(self.graph_dict_train), self.train_seq_len, self.use_native_planner,
-                 id(rt), rt.use_tc, rt.fuse_scan) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+                 id(rt), rt.use_tc, rt.fuse_scan) + tuple((p.data_ptr(), p._version) for p in self._param_list)
         if getattr(self, "_encode_cache_stamp", None) != stamp:
             self._encode_cache, self._encode_cache_stamp = {}, stamp
         return self._encode_cache

@@ -392,6 +392,17 @@ def test_encode_keeps_launch_programs_of_seen_batches_and_drops_them_with_the_we
     assert changed is not first and not torch.equal(changed.out, want[0])
     model.encode_cache_size = 0
     assert torch.equal(model.encode(batches[0]).out, changed.out)
+    # a parameter OBJECT replaced on a sub-module (the kept flat parameter list is stale) must drop the programs as well
+    model.encode_cache_size = 128
+    kept = model.encode(batches[0])
+    before = kept.out.clone()                                      # (results live in the runtime's workspace)
+    lw = model.ent_encoder.layer_1.loop_weight
+    model.ent_encoder.layer_1.loop_weight = torch.nn.Parameter(lw.detach() * 0.5)
+    swapped = model.encode(batches[0])
+    after = swapped.out.clone()
+    assert swapped is not kept and not torch.equal(after, before)
+    model.encode_cache_size = 0
+    assert torch.equal(model.encode(batches[0]).out, after)
 
 
 @pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8", "bisargcn_icews_d128_L8", "srgcn_tiny_d128",
