@@ -231,6 +231,14 @@ TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const
     for (int32_t i = 0; i < B; ++i) P->last_b[i] = last_b[B - 1 - i];
 
   // ---- aggregation work lists: (row, first edge, end edge) of the rows with in-edges, split at heavy_degree --------
+  // (heavy_degree <= 0: four times the mean in-degree of the rows that have in-edges, within [8, 64] --
+  // temp_b200/planner.py::agg_heavy_degree)
+  if (heavy_degree <= 0) {
+    int64_t nz = 0;
+    for (int32_t r = 0; r < b.R; ++r) nz += P->row_ptr[r + 1] > P->row_ptr[r];
+    const int64_t e = b.R > 0 ? P->row_ptr[b.R] : 0;
+    heavy_degree = nz > 0 ? static_cast<int32_t>(std::min<int64_t>(64, std::max<int64_t>(8, (4 * e) / nz))) : 8;
+  }
   for (int32_t r = 0; r < b.R; ++r) {
     const int32_t p0 = P->row_ptr[r], p1 = P->row_ptr[r + 1];
     if (p1 <= p0) continue;

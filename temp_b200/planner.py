@@ -28,7 +28,9 @@ from .snapshot import Snapshot
 __all__ = ["Instance", "Segment", "WindowPlan", "plan_window", "plan_static"]
 
 _ALIGN = 256
-AGG_HEAVY_DEGREE = 8   # in-degree above which the aggregation kernel gives a destination row a whole thread block
+# in-degree above which the aggregation kernel gives a destination row a whole thread block (0 = chosen per batch by its
+# mean in-degree, see agg_heavy_degree; TEMP_AGG_HEAVY pins it for experiments)
+AGG_HEAVY_DEGREE = int(__import__('os').environ.get('TEMP_AGG_HEAVY', '0'))
 
 
 @dataclass
@@ -49,6 +51,19 @@ class Segment:
     row0: int
     row1: int
     instances: List[Instance] = field(default_factory=list)
+
+
+def agg_heavy_degree(n_edges: int, n_rows_with_edges: int) -> int:
+    """In-degree above which the aggregation kernel gives a destination row a whole thread block instead of a warp: four
+    times the batch's mean in-degree over the rows that have in-edges, within [8, 64] (csrc/planner.cpp computes the same).
+    Measured on a B200 (tools/probe_config.py): sparse snapshots (ICEWS14, mean 1.6) want 8 -- a lone warp walking a 30-edge
+    row is the tail of a 5 us launch (forward 86 -> 92 us at 32); dense ones (GDELT, mean 16.5) want 64 -- at 8 nearly every
+    row takes a block of 8 warps for two edges each (forward 160 -> 139 us at 64, 154 us at 128)."""
+    if AGG_HEAVY_DEGREE > 0:
+        return AGG_HEAVY_DEGREE
+    if n_rows_with_edges <= 0:
+        return 8
+    return int(min(64, max(8, (4 * n_edges) // n_rows_with_edges)))
 
 
 class WindowPlan(object):
@@ -166,8 +181,9 @@ class _Packer(object):
         # work list of the aggregation kernel: (packed row, first edge, end edge) of every row WITH in-edges
         # (a warp each), split by in-degree: rows above AGG_HEAVY_DEGREE get a whole thread block
         deg = rp[1:] - rp[:-1]
-        for name, nz in (("agg_rows", np.nonzero((deg > 0) & (deg <= AGG_HEAVY_DEGREE))[0]),
-                         ("agg_heavy", np.nonzero(deg > AGG_HEAVY_DEGREE)[0])):
+        heavy = agg_heavy_degree(int(rp[-1]), int(np.count_nonzero(deg)))
+        for name, nz in (("agg_rows", np.nonzero((deg > 0) & (deg <= heavy))[0]),
+                         ("agg_heavy", np.nonzero(deg > heavy)[0])):
             setattr(plan, name, np.ascontiguousarray(np.stack([nz, rp[nz], rp[nz + 1]], axis=1), dtype=np.int32)
                     if nz.size else np.zeros((0, 3), dtype=np.int32))
             setattr(plan, name + "_ids", nz.astype(np.int64))

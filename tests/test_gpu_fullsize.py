@@ -119,9 +119,16 @@ def test_gdelt_shaped_heavy_rows_use_the_block_path():
     cfg = CONFIGS[5]
     model, oracle, t_list = _build(cfg)
     plan = model.plan(t_list)
+    from temp_b200.planner import agg_heavy_degree
     deg = np.diff(plan.row_ptr)
-    assert plan.agg_heavy.shape[0] == int((deg > 8).sum()) and deg.max() > 256
-    assert plan.agg_rows.shape[0] == int(((deg > 0) & (deg <= 8)).sum())
+    heavy = agg_heavy_degree(int(plan.E), int((deg > 0).sum()))
+    assert heavy == 64                                  # an edge-dense batch: 4 x the mean in-degree, capped (ICEWS-shaped: 8)
+    assert plan.agg_heavy.shape[0] == int((deg > heavy).sum()) > 0 and deg.max() > 256
+    assert plan.agg_rows.shape[0] == int(((deg > 0) & (deg <= heavy)).sum())
+    icews = _build(CONFIGS[1])
+    p2 = icews[0].plan(icews[2])
+    d2 = np.diff(p2.row_ptr)
+    assert agg_heavy_degree(int(p2.E), int((d2 > 0).sum())) == 8 and p2.agg_heavy.shape[0] == int((d2 > 8).sum())
 
 
 @pytest.mark.parametrize("cfg_index,scale", [(1, 6), (3, 10), (5, 8)],
