@@ -595,8 +595,8 @@ bool tc_scan2_supported(const TempGruScanArgs* a) {
     if (g.d != kD || g.cell_type != TEMP_CELL_TORCH_GRU) return false;
     if (a->parts != nullptr && (g.part_col < 0 || g.part_col >= a->part_stride)) return false;
     // chained steps hand the state over on chip: what a step reads through prev_row must be what its predecessor wrote
-    if (a->parts != nullptr && (g.accumulate != 0 || (g.prev_row != nullptr && g.state != a->steps[0].out) || g.out != a->steps[0].out))
-      return false;
+    // (an accumulating step -- the Bi centre step of the backward cell -- adds to what an EARLIER launch wrote)
+    if (a->parts != nullptr && ((g.prev_row != nullptr && g.state != a->steps[0].out) || g.out != a->steps[0].out)) return false;
     if (g.prev_row != nullptr) {
       if (g.whh_packed == nullptr) return false;
       if (w != nullptr && g.whh_packed != w) return false;

@@ -248,9 +248,10 @@ class Program(object):
         return len(self.ops)
 
     def fuse_gru_scans(self, barrier_ptr: int, parts_ptr: Optional[int] = None, n_parts: int = 0, part_stride: int = 0,
-                       part_rows: int = 0) -> None:
+                       part_rows: int = 0, split_cells: bool = False) -> None:
         """Replaces every run of >= 2 consecutive GRU ops by ONE scan launch (chain-partitioned when the plan's
-        partition table is given, see TempGruScanArgs)."""
+        partition table is given, see TempGruScanArgs).  ``split_cells``: a run also ends where the recurrent cell changes
+        (the Bi models: one single-cell scan per direction)."""
         out, run = [], []
 
         def flush():
@@ -273,6 +274,8 @@ class Program(object):
 
         for o in self.ops:
             if o.kind == OP_GRU:
+                if split_cells and run and run[-1].u.gru.b_hh != o.u.gru.b_hh:
+                    flush()
                 run.append(o)
             else:
                 flush()

@@ -128,10 +128,10 @@ class TKG_Module(nn.Module):
     use_native_planner = True
 
     def scan_tile(self) -> int:
-        """Row bound of a chain-partition step: 48 for the scans that use ONE recurrent cell (uni-directional GRU families:
-        gru_scan_tm_kernel), 96 for the scans that alternate between the two cells of the Bi models (gru_scan_tc_kernel)."""
+        """Row bound of a chain-partition step: 48 for the GRU families -- every scan launch uses ONE recurrent cell
+        (gru_scan_tm_kernel; the Bi models run one scan per direction) -- 96 otherwise (no chain-partitioned scan)."""
         from .planner import SCAN_TILE, SCAN_TILE_TM
-        return SCAN_TILE_TM if (self.family == "recurrent" and not self.bidirectional) else SCAN_TILE
+        return SCAN_TILE_TM if self.family == "recurrent" else SCAN_TILE
 
     def train_edge_sampler(self):
         """Training-mode edge sub-sampling of the window (models/DynamicRGCN.py:76-94, 161-171): the final step keeps

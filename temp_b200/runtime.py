@@ -453,9 +453,15 @@ class EncoderRuntime(object):
                     prog.add(lib.OP_LAYER, self._layer(l2, mine(rows), dptr, x=h1, x_is_embed=False, act=relu2,
                                                        terms=[self._term(h1, l2.loop_weight)], chain=(w, b, gi, GL), **local_kw))
                 protos = {}          # one fully built GruArgs per (cell, variant); the steps copy it and patch the rows
-                for g, seg in enumerate(plan.segments):
+                # Bi: the forward chain (forward history, then the centre step with the forward cell) before the backward
+                # chain (backward history, centre step with the backward cell, ACCUMULATING into the forward result): two
+                # runs of one cell each, i.e. two launches of the single-cell scan kernel instead of one two-cell scan
+                steps = [(g, seg, j, d) for g, seg in enumerate(plan.segments) for j, d in enumerate(dirs_of(seg))]
+                if bi:
+                    steps = [s_ for s_ in steps if s_[3] == "f"] + [s_ for s_ in steps if s_[3] == "b"]
+                for g, seg, j, d in steps:
                     dirs = dirs_of(seg)
-                    for j, d in enumerate(dirs):
+                    if True:
                         pv, dt = prev_ptrs(d, seg)
                         key = (d, j, len(dirs), pv, dt)
                         proto = protos.get(key)
@@ -490,7 +496,7 @@ class EncoderRuntime(object):
                 p_lo, p_hi = (0, int(parts.shape[0])) if shard is None else shard.parts_of(rank)
                 stride = int(parts.shape[1])
                 prog.fuse_gru_scans(self.scan_barrier(), dptr["scan_parts"] + 8 * stride * p_lo, p_hi - p_lo, stride,
-                                    int(getattr(plan, "scan_tile", 0)))
+                                    int(getattr(plan, "scan_tile", 0)), split_cells=True)
             else:
                 prog.fuse_gru_scans(self.scan_barrier())
         return EncodeResult(plan, out, S, prog, bufs)
