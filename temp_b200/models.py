@@ -577,7 +577,7 @@ class DynamicRGCN(TKG_Module):
         _, time_list = self.get_batch_graph_list(t_list, self.test_seq_len, self.graph_dict_train)
         hist, start = self.dense_history(res)
         self.last_result = res
-        return res.per_graph, [graph_dict.get(t) for t in res.plan.final_times], time_list, hist, start
+        return res.per_graph_copy(), [graph_dict.get(t) for t in res.plan.final_times], time_list, hist, start
 
     @torch.no_grad()
     def get_all_embeds_Gt(self, convoluted_embeds, g, t, *history):
@@ -592,7 +592,7 @@ class DynamicRGCN(TKG_Module):
         _, time_list = self.get_batch_graph_list(t_list, self.test_seq_len, self.graph_dict_train)
         hist, start = self.dense_history(res)
         self.last_result = res
-        return res.per_graph, list(res.plan.final_snapshots), time_list, hist, start
+        return res.per_graph_copy(), list(res.plan.final_snapshots), time_list, hist, start
 
 
 class BiDynamicRGCN(DynamicRGCN):
@@ -610,7 +610,7 @@ class BiDynamicRGCN(DynamicRGCN):
         hf, sf = self.dense_history(res, "f")
         hb, sb = self.dense_history(res, "b")
         self.last_result = res
-        return (res.per_graph, [graph_dict.get(t) for t in res.plan.final_times], list(res.plan.final_times),
+        return (res.per_graph_copy(), [graph_dict.get(t) for t in res.plan.final_times], list(res.plan.final_times),
                 hf, sf, hb, sb)
 
 
@@ -657,7 +657,7 @@ class StaticRGCN(TKG_Module):
         res = self.encode(t_list)
         graph_dict = self.graph_dict_val if val else self.graph_dict_test
         self.last_result = res
-        return res.per_graph, [graph_dict.get(t) for t in res.plan.final_times]
+        return res.per_graph_copy(), [graph_dict.get(t) for t in res.plan.final_times]
 
 
 MODULES = {"SRGCN": StaticRGCN, "GRRGCN": DynamicRGCN, "RRGCN": DynamicRGCN, "BiGRRGCN": BiDynamicRGCN,

@@ -129,7 +129,13 @@ class EncodeResult(object):
 
     @property
     def per_graph(self):
+        """Views into the runtime's workspace: valid until the next forward of the model."""
         return tuple(self.out.split(self.plan.final_sizes))
+
+    def per_graph_copy(self):
+        """Fresh tensors, like the reference returns (one device copy): what the reference-API calls hand out, so that a
+        caller collecting embeddings over several batches (test.py, the analysis scripts) keeps them."""
+        return tuple(self.out.clone().split(self.plan.final_sizes))
 
 
 def _p(t, off_bytes=0):

@@ -367,6 +367,43 @@ def test_reference_style_eval_calls_agree_with_the_fast_entry():
     assert torch.equal(ranks, ranks2) and abs(loss - loss2) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["grrgcn_tiny_d128_full_note", "sargcn_tiny_d128_full", "bigrrgcn_icews_d128_L8"])
+def test_kept_programs_survive_a_growing_workspace(name):
+    """A kept launch program holds raw pointers into the grow-only workspace: a later, larger batch reallocates buffers, and
+    the replay of the earlier batch must still compute on live memory (every buffer a program addresses is kept alive by it:
+    gi / kv / qkv of the both-layers-recurrent and attention programs included)."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME[name]
+    model = product_model(case)
+    tl = list(case["t_list"])
+    small, large = tl[:1], tl
+    model.encode_cache_size = 0
+    want_small = model.encode(small).out.clone()
+    model = product_model(case)                                    # fresh runtime: the workspace starts small
+    model.encode_cache_size = 128
+    assert torch.equal(model.encode(small).out, want_small)
+    big = model.encode(large).out.clone()                          # grows the workspace
+    junk = [torch.full((1 << 18,), float("nan"), device=big.device) for _ in range(8)]   # reuse whatever was freed
+    again = model.encode(small)
+    assert torch.equal(again.out, want_small)
+    assert torch.equal(model.encode(large).out, big)
+    del junk
+
+
+def test_reference_api_calls_hand_out_fresh_tensors():
+    """evaluate_embed / train_embed return tensors the caller may keep across batches, as the reference's do (test.py and
+    the analysis scripts collect them); only model.encode() hands out views into the runtime's workspace."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME["grrgcn_icews_d128_L8"]
+    model = product_model(case)
+    times = sorted(model.graph_dict_train.keys())
+    first = model.evaluate_embed(case["t_list"], val=True)[0]
+    kept = [t.clone() for t in first]
+    model.evaluate_embed(times[4:7], val=True)
+    model.train_embed(times[8:12])
+    assert all(torch.equal(a, b) for a, b in zip(first, kept))
+
+
 def test_encode_keeps_launch_programs_of_seen_batches_and_drops_them_with_the_weights():
     """model.encode(t_list) replays the kept launch program of a batch it has seen (no planning, no plan upload); a
     parameter update or a full slot ring must never serve stale results."""
