@@ -156,9 +156,9 @@ class PeerShardedForward(object):
         res.programs[0]._arr = None
         fin = plan.final                              # exchange 2: final states into every rank's state buffer
         scans = [o for o in res.programs[1].ops if o.kind == lib.OP_GRU_SCAN]
-        if len(scans) != 1:
-            raise RuntimeError("temp_b200: the sharded forward expects one fused scan launch")
-        sc = scans[0].u.scan
+        if not scans:
+            raise RuntimeError("temp_b200: the sharded forward expects the fused scan launch")
+        sc = scans[-1].u.scan                        # (the Bi models run one scan per direction: the last one writes the result)
         for i in range(sc.n_steps):
             sc.steps[i].push = 1 if (sc.steps[i].row0 == fin.row0 and sc.steps[i].row1 == fin.row1 and
                                       i == max(k for k in range(sc.n_steps)
