@@ -157,7 +157,7 @@ typedef struct {
  *            step (DynamicRGCN.py:35-54), so a batch item cut into entity-id ranges gives independent
  *            chains: entry (p, steps[s].part_col) = the packed-row range [lo, hi) of partition p at step s,
  *            at most part_rows rows (lo == hi: nothing).  The tcgen05 path (d == 128) gives every partition to
- *            one 4-CTA cluster (to one of its four pipelines when part_rows <= 48) and separates the steps of a
+ *            one 4-CTA cluster (to one of its one or two pipelines when part_rows <= 48) and separates the steps of a
  *            partition by cluster-scope barriers; without the table (or d != 128) steps are separated by a
  *            grid-wide barrier (cooperative launch).
  *   barrier: 8 bytes of device memory for the grid-wide barrier, zero before the first use; the kernel
@@ -180,7 +180,7 @@ typedef struct {
   int32_t push_row0;
   int32_t part_rows;         /* upper bound of the rows of one partition step in `parts` (0: the legacy bound, 96).  Tables cut
                                 at <= 48 rows whose steps all use ONE recurrent cell run on gru_scan_tm_kernel (W_hh in
-                                tensor memory, four partition pipelines per CTA), the others on gru_scan_tc_kernel            */
+                                tensor memory, one or two partition pipelines per CTA), the others on gru_scan_tc_kernel        */
   float* push_multicast;     /* nullable: NVLS multicast address of the same symmetric buffer -- one multimem.st per
                                 value instead of one store per peer (the switch replicates it to every GPU); push_bufs then
                                 lists only buffers OUTSIDE the multicast group (e.g. a pinned host buffer; push_world >= 0) */

@@ -299,7 +299,7 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
     return plan
 
 
-SCAN_TILE = 96      # rows per chain partition and step of gru_scan_tc_kernel (scans that mix recurrent cells: the Bi models)
+SCAN_TILE = 96      # rows per chain partition and step of gru_scan_tc_kernel (round-1 scan; the default when no model asks for 48)
 SCAN_TILE_TM = 48   # ... of gru_scan_tm_kernel (one recurrent cell, W_hh in tensor memory; temp_b200/csrc/tc_scan2.cu)
 
 
