@@ -502,7 +502,7 @@ class EncoderRuntime(object):
                 p_lo, p_hi = (0, int(parts.shape[0])) if shard is None else shard.parts_of(rank)
                 stride = int(parts.shape[1])
                 prog.fuse_gru_scans(self.scan_barrier(), dptr["scan_parts"] + 8 * stride * p_lo, p_hi - p_lo, stride,
-                                    int(getattr(plan, "scan_tile", 0)), split_cells=True)
+                                    int(getattr(plan, "scan_tile", 0)), split_cells=(D == 128))   # (the SIMT scan takes both cells in one launch)
             else:
                 prog.fuse_gru_scans(self.scan_barrier())
         return EncodeResult(plan, out, S, prog, bufs)
