@@ -43,26 +43,29 @@ constexpr int kD = 128;
 constexpr int kCluster = 4;                       // CTAs per cluster = blocks of 32 hidden columns
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;             // 512 -> 128 registers per thread
-constexpr int kRows = 48;                         // max packed rows per partition step = UMMA N
-constexpr int kAtomBytes = kRows * 128;           // one k-atom block (32 k) of an operand image
-constexpr int kImage = 4 * kAtomBytes;            // hi (or lo) image of a tile: 24 KB
-constexpr int kBufBytes = 2 * kImage;             // one operand tile: hi image, lo image
-constexpr int kPipeSmem = 2 * kBufBytes;          // two operand tiles per pipeline (steps alternate)
+// kR = max packed rows per partition step = UMMA N: 48 (the widest N at the tensor-pipe floor: latency regime, few
+// partitions) or 64 (chained scans with more partitions than pipelines: 25 % fewer tile steps for 20 % more MMA time each).
+// Per pipeline 96 KB: chained = operand tile (hi | lo image, 2 x kR x 512 bytes) at +0, ONE fp32 staging tile at +64 KB;
+// plain (kR = 48 only) = two operand tiles of 48 KB that alternate.
+constexpr int kRowsPlain = 48;
+constexpr int kRowsMax = 64;
+constexpr int kPipeSmem = 96 * 1024;
+constexpr int kStageOff = 64 * 1024;
 constexpr int kMaxPipes = 2;
-constexpr int kWExtra = 32 * 1024;                // with the two operand regions (48 KB each): room for the 128 KB W_hh slice
+constexpr int kWExtra = 32 * 1024;                // with 48 KB of each pipeline's operand region: room for the 128 KB W_hh slice
 constexpr int kSmem = kMaxPipes * kPipeSmem + kWExtra + 1024;
-static_assert(2 * kBufBytes + kWExtra == 4 * kWChunkBytes, "the W_hh slice lands in the operand regions + the extra block");
+static_assert(2 * 3 * 16384 + kWExtra == 4 * kWChunkBytes, "the W_hh slice lands in the operand regions + the extra block");
 static_assert(kSmem <= 227 * 1024, "shared memory per CTA");
 constexpr int kTmemCols = 512;
 constexpr int kColWLo = 128;                      // W_hh hi parts at columns [0, 128), lo parts at [128, 256)
-constexpr int kColD = 256, kColDStride = 64;      // accumulator of pipeline p: columns [256 + 64 p, +48)
-static_assert(kAtomBytes % 1024 == 0, "k-atom blocks must keep the 1024-byte swizzle period");
-static_assert(kColD + (kMaxPipes - 1) * kColDStride + kRows <= kTmemCols, "TMEM budget");
+constexpr int kColD = 256, kColDStride = 64;      // accumulator of pipeline p: columns [256 + 64 p, + kR)
+static_assert(kColD + (kMaxPipes - 1) * kColDStride + kRowsMax <= kTmemCols, "TMEM budget");
 
 struct Bars {
   uint64_t w_full;                // the W_hh slice has landed in shared memory (bulk copies, bytes counted)
   uint64_t mma_done[kMaxPipes];
-  uint64_t ready[kMaxPipes][2];   // operand tile b of a pipeline is complete (bytes counted: st.async from the four CTAs)
+  uint64_t ready[kMaxPipes];      // the staging tile of a pipeline is complete (bytes counted: st.async from the four CTAs)
+  uint64_t vacant[kMaxPipes];     // all four CTAs have finished reading their staging tile of the current tile step
   uint32_t tmem_base;
   float* push[TEMP_MAX_PUSH_PEERS];
 };
@@ -80,6 +83,9 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -127,16 +133,25 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
 // kPipes in {1, 2}: independent partition pipelines per CTA, 16 / kPipes warps each (the launcher takes one pipeline while
 // that still gives every chain partition its own, else two).
 // kChained (a chain-partition table is given): the steps of a partition hand the state over through DISTRIBUTED SHARED
-// MEMORY -- each CTA stores its 32 hidden columns of the new state, already split into tf32 hi / lo parts, straight into
-// the next step's operand tile of all four CTAs with st.async (completion counted in bytes on the consumer's mbarrier):
-// no release fence, no L2 round trip, no conversion pass on the step chain.  The operand keeps the PREVIOUS step's row
-// order; a row reads its accumulator column / h0 values through prev_row, and the decay factor -- a per-row scalar -- is
-// applied to the gathered values after the MMA (W . (c h) = c (W . h)).  The global state store only serves the callers.
+// MEMORY -- each CTA stores its 32 hidden columns of the new state (fp32) straight into the staging tile of all four CTAs
+// with st.async (completion counted in bytes on the consumer's `ready` mbarrier): no release fence, no L2 round trip.
+// ONE staging tile per pipeline: a tile step converts it into the tf32 hi / lo operand first thing (h0 is read back from
+// the operand: hi + lo is the fp32 value exactly), then tells all four CTAs that its staging tile is vacant (`vacant`
+// mbarrier, four arrivals per tile step); the gate phase waits for that before it sends the next state.  The operand keeps
+// the PREVIOUS step's row order; a row reads its accumulator column / h0 values through prev_row, and the decay factor -- a
+// per-row scalar -- is applied to the gathered values after the MMA (W . (c h) = c (W . h)).  The global state store only
+// serves the callers.
 // !kChained (one step, plain row tiles, state read from global memory through prev_row): the operand is gathered by the
 // CTA itself; tiles are independent, nothing is exchanged.
-template <int kPipes, bool kChained>
+template <int kPipes, bool kChained, int kRows>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     gru_scan_tm_kernel(const TempGruScanArgs P, const int n_parts, const void* __restrict__ w_packed) {
+  static_assert(kRows == 48 || (kRows == 64 && kChained), "tile rows");
+  constexpr int kAtomBytes = kRows * 128;           // one k-atom block (32 k) of an operand image
+  constexpr int kImage = 4 * kAtomBytes;            // hi (or lo) image of a tile = one fp32 staging tile: kRows x 512 bytes
+  constexpr int kBufBytes = 2 * kImage;             // one operand tile: hi image, lo image
+  static_assert(kAtomBytes % 1024 == 0, "k-atom blocks must keep the 1024-byte swizzle period");
+  static_assert(kChained ? (kBufBytes <= kStageOff && kStageOff + kImage <= kPipeSmem) : 2 * kBufBytes <= kPipeSmem, "pipeline memory");
   constexpr int kPW = kWarps / kPipes;              // warps per pipeline (16 or 8)
   constexpr int kPT = kPW * 32;
   constexpr int kH = kPW / 4;                       // warps per TMEM lane quadrant inside a pipeline
@@ -162,8 +177,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     mbar_init(&S.w_full, 1);
     for (int i = 0; i < kMaxPipes; ++i) {
       mbar_init(&S.mma_done[i], 1);
-      mbar_init(&S.ready[i][0], 1);
-      mbar_init(&S.ready[i][1], 1);
+      mbar_init(&S.ready[i], 1);
+      mbar_init(&S.vacant[i], kCluster);
     }
     fence_mbar_init();
   }
@@ -228,7 +243,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
   // ---- this pipeline's tile steps: its partitions vc, vc + NV, ... ; all steps of a partition, then the next --------
   const int vc = pipe * n_clusters + cid, NV = kPipes * n_clusters;
-  const uint32_t s_buf0 = smem_u32(smem + pipe * kPipeSmem);   // operand tile b: hi image at s_buf0 + b * kBufBytes, lo kImage later
+  const uint32_t s_buf0 = smem_u32(smem + pipe * kPipeSmem);   // (plain) operand tile b: hi image at s_buf0 + b * kBufBytes, lo kImage later
+  const uint32_t s_stage = s_buf0 + kStageOff;                 // (chained) fp32 [row][128] state of the previous step
   const uint32_t dcol = tbase + kColD + pipe * kColDStride;
 
   // lane l < n_steps keeps the packed-row range of a partition at step l: one load per partition, fetched one partition
@@ -301,7 +317,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   pdl_wait();   // gi (and, for a single step, the previous state) come from the predecessor kernels
 
   uint32_t t = 0;                    // tile steps done by this pipeline (operand tile of step t: t & 1)
-  uint32_t mma_par = 0, ready_par = 0;   // ready_par bit b: phase parity of S.ready[pipe][b]
+  uint32_t mma_par = 0, ready_par = 0, vacant_par = 0;   // phase parities of S.mma_done / S.ready / S.vacant of this pipeline
   int chain_part = -1, prev_rb = 0, prev_rows = 0;   // the previous tile step (same partition <=> its state is the operand)
 #pragma unroll 1
   while (have) {
@@ -313,9 +329,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     const bool more = n_part < n_parts;
     const bool cont_next = kChained && more && n_part == part;   // the next tile step consumes this one's state
     const uint32_t b = t & 1;
-    // chained: the operand tile is region 0, the two fp32 staging tiles share region 1; plain: regions alternate as operand
+    // chained: ONE operand tile (and one staging tile); plain: two operand tiles alternate
     const uint32_t s_bhi = kChained ? s_buf0 : s_buf0 + b * kBufBytes, s_blo = s_bhi + kImage;
-    const uint32_t s_stage = s_buf0 + kBufBytes + b * kImage;          // (chained) fp32 [row][128] state of the previous step
     const uint32_t ex_base = s_bhi;   // gate g parks in k-atom (cb + 1 + g) & 3 of the (dead) hi image, plain [row][32] rows
     bool has_prev;
     int nmma;
@@ -350,11 +365,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       if (kChained) {
         has_prev = chain_part == part;
         nmma = (prev_rows + 15) & ~15;
-        // arm the barrier the next step waits on: the bytes this step's rows will bring from the four CTAs
-        if (cont_next && gw == 0 && elect_one()) mbar_expect_tx(&S.ready[pipe][b ^ 1], static_cast<uint32_t>(r1 - rb) * 512u);
         if (has_prev) {
-          mbar_wait(&S.ready[pipe][b], (ready_par >> b) & 1u);   // the staging tile is complete (all 4 CTAs' columns)
-          ready_par ^= 1u << b;
+          mbar_wait(&S.ready[pipe], ready_par);   // the staging tile is complete (all 4 CTAs' columns)
+          ready_par ^= 1u;
           TLS(1);
 #pragma unroll
           for (int u = 0; u < kU; ++u) {
@@ -397,6 +410,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     }
     TLS(2);
 
+    // ---- the staging tile has been consumed (or was never read: a partition's first step): arm `ready` for the bytes this
+    // step's rows will bring, then tell all four CTAs that this CTA's staging tile is vacant ----------------------------
+    if (kChained && gw == 0) {   // warp-uniform
+      if (elect_one()) {
+        if (cont_next) mbar_expect_tx(&S.ready[pipe], static_cast<uint32_t>(r1 - rb) * 512u);
+        const uint32_t vb = smem_u32(&S.vacant[pipe]);
+#pragma unroll
+        for (int k = 0; k < kCluster; ++k) mbar_arrive_remote_relaxed(mapa_u32(vb, k));
+      }
+      __syncwarp();
+    }
+
     // ---- gh^T = W_hh . h0^T : 16 k-steps x 3 split passes, A from tensor memory -----------------------------------
     if (has_prev && gw == 0) {   // warp-uniform
       tc_fence_after();
@@ -432,9 +457,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const int n = kChained ? cur.prv[u] - prev_rb : i;
         if (kChained && (n < 0 || n >= prev_rows)) __trap();   // a state row outside the previous step of this partition
         nrow[u] = n;
-        if (kChained) {
-          h0[u] = lds_f32x4(s_stage + n * 512 + cb * 128 + cq * 16);
-        } else {
+        {   // from the operand images: hi + lo is the fp32 value exactly (k-atom cb = this CTA's own hidden columns)
           const uint32_t off = static_cast<uint32_t>(cb) * kAtomBytes + (n >> 3) * 1024u + (n & 7) * 128u + ((cq ^ (n & 7)) << 4);
           const float4 a = lds_f32x4(s_bhi + off), c = lds_f32x4(s_blo + off);
           h0[u] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
@@ -472,11 +495,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
     // ---- gates, state store, hand-over to the next step (+ fused all-gather peer stores) ------------------------------
     uint32_t peer_stage[kCluster], peer_bar[kCluster];
+    if (kChained) {   // every CTA of the cluster has converted its staging tile of this tile step: it may be overwritten
+      mbar_wait(&S.vacant[pipe], vacant_par);
+      vacant_par ^= 1u;
+    }
     if (cont_next) {
 #pragma unroll
       for (int k = 0; k < kCluster; ++k) {
-        peer_stage[k] = mapa_u32(s_buf0 + kBufBytes + (b ^ 1) * kImage, k);
-        peer_bar[k] = mapa_u32(smem_u32(&S.ready[pipe][b ^ 1]), k);
+        peer_stage[k] = mapa_u32(s_stage, k);
+        peer_bar[k] = mapa_u32(smem_u32(&S.ready[pipe]), k);
       }
     }
 #pragma unroll
@@ -549,9 +576,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     chain_part = part;
     prev_rb = rb;
     prev_rows = r1 - rb;
-    // A partition's first step sends without waiting for anything; skipping one tile parity at a partition switch keeps
-    // those stores away from the staging tile a slower peer may still read for the partition that just ended.
-    t += (kChained && !cont_next) ? 2 : 1;
+    t += 1;
     cur = nxt;
     part = n_part;
     s = n_s;
@@ -588,7 +613,7 @@ bool tc_scan2_supported(const TempGruScanArgs* a) {
   static const bool disabled = getenv("TEMP_SCAN_V1") != nullptr;
   if (disabled || a->n_steps <= 0) return false;
   if (a->parts == nullptr && a->n_steps != 1) return false;
-  if (a->parts != nullptr && (a->part_rows <= 0 || a->part_rows > kRows)) return false;
+  if (a->parts != nullptr && (a->part_rows <= 0 || a->part_rows > kRowsMax)) return false;
   const void* w = nullptr;
   for (int s = 0; s < a->n_steps; ++s) {
     const TempGruArgs& g = a->steps[s];
@@ -608,11 +633,11 @@ bool tc_scan2_supported(const TempGruScanArgs* a) {
   return true;
 }
 
-template <int kPipes, bool kChained>
+template <int kPipes, bool kChained, int kRows>
 int launch_scan2_t(const TempGruScanArgs* a, int n_parts, int clusters, const void* w, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gru_scan_tm_kernel<kPipes, kChained>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gru_scan_tm_kernel<kPipes, kChained, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tm_kernel");
     configured = true;
   }
@@ -627,14 +652,14 @@ int launch_scan2_t(const TempGruScanArgs* a, int n_parts, int clusters, const vo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tm_kernel<kPipes, kChained>, *a, n_parts, w);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_scan_tm_kernel<kPipes, kChained, kRows>, *a, n_parts, w);
   if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tm_kernel launch");
   return TEMP_OK;
 }
 
 int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st) {
   int n_parts = a->n_parts;
-  if (a->parts == nullptr) n_parts = (a->steps[0].row1 - a->steps[0].row0 + kRows - 1) / kRows;
+  if (a->parts == nullptr) n_parts = (a->steps[0].row1 - a->steps[0].row0 + kRowsPlain - 1) / kRowsPlain;
   if (n_parts <= 0) return TEMP_OK;
   const void* w = nullptr;
   for (int s = 0; s < a->n_steps; ++s)
@@ -646,8 +671,8 @@ int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmem;
     cfg.gridDim = dim3(kCluster * 64);
-    cudaFuncSetAttribute(gru_scan_tm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, gru_scan_tm_kernel<2, true>, &cfg);
+    cudaFuncSetAttribute(gru_scan_tm_kernel<2, true, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, gru_scan_tm_kernel<2, true, 48>, &cfg);
     if (e != cudaSuccess || max_clusters <= 0) {
       cudaGetLastError();
       max_clusters = 32;
@@ -659,9 +684,12 @@ int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st) {
   const int clusters = n_parts < max_clusters ? n_parts : max_clusters;
   int pipes = n_parts <= clusters ? 1 : 2;
   if (force == 1 || force == 2) pipes = force;
-  if (a->parts != nullptr)
-    return pipes == 1 ? launch_scan2_t<1, true>(a, n_parts, clusters, w, st) : launch_scan2_t<2, true>(a, n_parts, clusters, w, st);
-  return pipes == 1 ? launch_scan2_t<1, false>(a, n_parts, clusters, w, st) : launch_scan2_t<2, false>(a, n_parts, clusters, w, st);
+  if (a->parts != nullptr) {
+    if (a->part_rows <= 48)
+      return pipes == 1 ? launch_scan2_t<1, true, 48>(a, n_parts, clusters, w, st) : launch_scan2_t<2, true, 48>(a, n_parts, clusters, w, st);
+    return pipes == 1 ? launch_scan2_t<1, true, 64>(a, n_parts, clusters, w, st) : launch_scan2_t<2, true, 64>(a, n_parts, clusters, w, st);
+  }
+  return pipes == 1 ? launch_scan2_t<1, false, 48>(a, n_parts, clusters, w, st) : launch_scan2_t<2, false, 48>(a, n_parts, clusters, w, st);
 }
 
 }  // namespace temp_internal
