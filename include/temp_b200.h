@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 18
+#define TEMP_ABI_VERSION 19
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -325,6 +325,7 @@ typedef struct {
 
 typedef struct {
   int32_t rows, edges, n_segments, n_instances, n_parts, n_agg_rows, n_agg_heavy, n_slots, batch, seq_len;
+  int32_t scan_tile;   /* row bound of a partition step actually used (temp_plan_window's scan_tile < 0: chosen, 48 or 64) */
 } TempPlanCounts;
 
 enum { TEMP_PLAN_ENT_ID = 0, TEMP_PLAN_ROW_TIME, TEMP_PLAN_NORM, TEMP_PLAN_ROW_PTR, TEMP_PLAN_E_SRC, TEMP_PLAN_E_SRC_ENT,

@@ -114,7 +114,7 @@ extern "C" {
 
 TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const int32_t* targets, int32_t B, int32_t L,
                            int32_t bidirectional, int32_t attention, int32_t scan_tile, int32_t heavy_degree) {
-  if (snaps == nullptr || targets == nullptr || n_snaps <= 0 || B <= 0 || L <= 0 || scan_tile <= 0) return nullptr;
+  if (snaps == nullptr || targets == nullptr || n_snaps <= 0 || B <= 0 || L <= 0 || scan_tile == 0) return nullptr;
   for (int32_t i = 0; i < B; ++i)
     if (targets[i] < 0 || targets[i] >= n_snaps) return nullptr;
   TempPlan* P = new TempPlan();
@@ -251,6 +251,12 @@ TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const
   // ---- chain partitions (temp_b200/planner.py::chain_partitions) ----------------------------------------------------
   const int32_t n_seg = static_cast<int32_t>(P->segs.size());
   int32_t n_parts = 0;
+  // scan_tile < 0: |scan_tile| rows per partition step, widened to 64 when that leaves more partitions than two rounds of the
+  // scan kernel's pipelines (2 x 33 clusters x 2): the scan is then throughput bound and 25 % fewer, fuller tile steps win
+  // (x16 bench shape: 367 -> 334 us), while in the latency regime the narrower tile is faster (x1: 45 against 51 us)
+  const bool auto_tile = scan_tile < 0;
+  if (auto_tile) scan_tile = -scan_tile;
+  int32_t used_tile = scan_tile;
   if (!attention) {
     struct Part {
       std::vector<int32_t> rg;
@@ -261,35 +267,43 @@ TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const
     for (int32_t g = 0; g < n_seg; ++g)
       for (int32_t ii = P->segs[g].inst0; ii < P->segs[g].inst1; ++ii) per_item[P->insts[ii].item].push_back({g, ii});
     const int64_t big = std::numeric_limits<int64_t>::max();
-    for (int32_t item = 0; item < B; ++item) {
-      const auto& li = per_item[item];
-      const size_t K = li.size();
-      std::vector<int32_t> pos(K, 0);
-      while (true) {
-        bool any = false;
-        for (size_t k = 0; k < K; ++k) any = any || pos[k] < P->insts[li[k].second].n;
-        if (!any) break;
-        // the first entity id that would make some instance exceed `scan_tile` rows; everything below it joins
-        int64_t cut = big;
-        for (size_t k = 0; k < K; ++k) {
-          const Inst& in = P->insts[li[k].second];
-          if (pos[k] + scan_tile < in.n) cut = std::min<int64_t>(cut, snaps[in.snap].node_ids[pos[k] + scan_tile]);
+    auto cut_parts = [&](int32_t tile) {
+      parts.clear();
+      for (int32_t item = 0; item < B; ++item) {
+        const auto& li = per_item[item];
+        const size_t K = li.size();
+        std::vector<int32_t> pos(K, 0);
+        while (true) {
+          bool any = false;
+          for (size_t k = 0; k < K; ++k) any = any || pos[k] < P->insts[li[k].second].n;
+          if (!any) break;
+          // the first entity id that would make some instance exceed `tile` rows; everything below it joins
+          int64_t cut = big;
+          for (size_t k = 0; k < K; ++k) {
+            const Inst& in = P->insts[li[k].second];
+            if (pos[k] + tile < in.n) cut = std::min<int64_t>(cut, snaps[in.snap].node_ids[pos[k] + tile]);
+          }
+          Part pt;
+          pt.rg.assign(static_cast<size_t>(n_seg) * 2, 0);
+          pt.rows = 0;
+          for (size_t k = 0; k < K; ++k) {
+            const Inst& in = P->insts[li[k].second];
+            const int32_t* ids = snaps[in.snap].node_ids;
+            const int32_t nw = cut == big ? in.n
+                                          : static_cast<int32_t>(std::lower_bound(ids, ids + in.n, static_cast<int32_t>(cut)) - ids);
+            pt.rg[2 * li[k].first] = in.row0 + pos[k];
+            pt.rg[2 * li[k].first + 1] = in.row0 + nw;
+            pt.rows += nw - pos[k];
+            pos[k] = nw;
+          }
+          parts.push_back(std::move(pt));
         }
-        Part pt;
-        pt.rg.assign(static_cast<size_t>(n_seg) * 2, 0);
-        pt.rows = 0;
-        for (size_t k = 0; k < K; ++k) {
-          const Inst& in = P->insts[li[k].second];
-          const int32_t* ids = snaps[in.snap].node_ids;
-          const int32_t nw = cut == big ? in.n
-                                        : static_cast<int32_t>(std::lower_bound(ids, ids + in.n, static_cast<int32_t>(cut)) - ids);
-          pt.rg[2 * li[k].first] = in.row0 + pos[k];
-          pt.rg[2 * li[k].first + 1] = in.row0 + nw;
-          pt.rows += nw - pos[k];
-          pos[k] = nw;
-        }
-        parts.push_back(std::move(pt));
       }
+    };
+    cut_parts(scan_tile);
+    if (auto_tile && scan_tile < 64 && parts.size() > 132) {
+      used_tile = 64;
+      cut_parts(used_tile);
     }
     std::stable_sort(parts.begin(), parts.end(), [](const Part& x, const Part& y) { return x.rows > y.rows; });
     for (const Part& pt : parts) P->scan_parts.insert(P->scan_parts.end(), pt.rg.begin(), pt.rg.end());
@@ -310,6 +324,7 @@ TempPlan* temp_plan_window(const TempSnapshotView* snaps, int32_t n_snaps, const
   c.n_slots = n_slots;
   c.batch = B;
   c.seq_len = L;
+  c.scan_tile = used_tile;
   return P;
 }
 

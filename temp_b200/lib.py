@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -104,7 +104,7 @@ class SnapshotView(C.Structure):
 
 class PlanCounts(C.Structure):
     _fields_ = [(n, _i32) for n in ("rows", "edges", "n_segments", "n_instances", "n_parts", "n_agg_rows", "n_agg_heavy",
-                                    "n_slots", "batch", "seq_len")]
+                                    "n_slots", "batch", "seq_len", "scan_tile")]
 
 
 PLAN_ARRAYS = ("ent_id", "row_time", "norm", "row_ptr", "e_src", "e_src_ent", "e_rel", "prev_a", "dt_a", "prev_b", "dt_b",

@@ -128,12 +128,14 @@ class TKG_Module(nn.Module):
     use_native_planner = True
 
     def scan_tile(self) -> int:
-        """Row bound of a chain-partition step: 48 for the GRU families -- every scan launch uses ONE recurrent cell
-        (gru_scan_tm_kernel; the Bi models run one scan per direction) -- 96 otherwise (no chain-partitioned scan)."""
+        """Row bound of a chain-partition step for the planner: -48 for the GRU families = 48 rows (every scan launch uses ONE
+        recurrent cell: gru_scan_tm_kernel; the Bi models run one scan per direction), widened to 64 by the planner when the
+        batch has more partitions than two rounds of the kernel's pipelines (planner.partition_scan); 96 otherwise (no
+        chain-partitioned scan)."""
         import os
         from .planner import SCAN_TILE, SCAN_TILE_TM
-        forced = int(os.environ.get("TEMP_SCAN_TILE", "0"))          # development knob
-        return (forced or SCAN_TILE_TM) if self.family == "recurrent" else SCAN_TILE
+        forced = int(os.environ.get("TEMP_SCAN_TILE", "0"))          # development knob: a fixed tile
+        return (forced or -SCAN_TILE_TM) if self.family == "recurrent" else SCAN_TILE
 
     def train_edge_sampler(self):
         """Training-mode edge sub-sampling of the window (models/DynamicRGCN.py:76-94, 161-171): the final step keeps

@@ -290,8 +290,7 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
     plan.last_hist_b = [last_b[B - 1 - i] for i in range(B)] if bidirectional else [None] * B
     pk.finish(plan)
     if not attention:
-        plan.scan_tile = int(scan_tile or SCAN_TILE)
-        plan.scan_parts = chain_partitions(plan, plan.scan_tile)
+        plan.scan_tile, plan.scan_parts = partition_scan(plan, int(scan_tile or SCAN_TILE))
     if attention:
         plan.n_slots = (L - 1) * (2 if bidirectional else 1)
         plan.slot_row = np.ascontiguousarray(np.concatenate(slot_rows, axis=0), dtype=np.int32)
@@ -301,6 +300,23 @@ def plan_window(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], seq_len:
 
 SCAN_TILE = 96      # rows per chain partition and step of gru_scan_tc_kernel (round-1 scan; the default when no model asks for 48)
 SCAN_TILE_TM = 48   # ... of gru_scan_tm_kernel (one recurrent cell, W_hh in tensor memory; temp_b200/csrc/tc_scan2.cu)
+
+
+AUTO_TILE_PARTS = 132     # 2 rounds of the scan kernel's pipelines (2 x 33 clusters x 2)
+
+
+def partition_scan(plan: WindowPlan, tile: int):
+    """-> (tile used, partition table).  ``tile`` < 0: |tile| rows per partition step, widened to 64 when that leaves more
+    than AUTO_TILE_PARTS partitions -- the scan is then throughput bound and 25 % fewer, fuller tile steps win (x16 bench
+    shape: 367 -> 334 us), while in the latency regime the narrower tile is faster (x1: 45 against 51 us).  Same rule as
+    csrc/planner.cpp."""
+    auto = tile < 0
+    tile = abs(tile)
+    parts = chain_partitions(plan, tile)
+    if auto and tile < 64 and parts.shape[0] > AUTO_TILE_PARTS:
+        tile = 64
+        parts = chain_partitions(plan, tile)
+    return tile, parts
 
 
 def chain_partitions(plan: WindowPlan, tile: int = SCAN_TILE) -> np.ndarray:
@@ -483,7 +499,7 @@ def plan_window_native(graph_dict: Dict[int, Snapshot], t_list: Sequence[int], s
     cnt = lib.PlanCounts()
     lib.check(L.temp_plan_counts(handle, C.byref(cnt)), "temp_plan_counts")
     plan.seq_len, plan.batch, plan.bidirectional = int(seq_len), B, bool(bidirectional)
-    plan.scan_tile = int(scan_tile or SCAN_TILE)
+    plan.scan_tile = int(cnt.scan_tile)
     plan.R, plan.E = int(cnt.rows), int(cnt.edges)
     plan._n_parts = int(cnt.n_parts)
     if not bidirectional:

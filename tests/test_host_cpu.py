@@ -424,6 +424,24 @@ def test_native_planner_equals_python_planner_on_synthetic_shapes(shape, L, B, b
                      plan_window(store.train, t_list, L, bidirectional=bi, attention=att))
 
 
+def test_planners_agree_on_the_chosen_scan_tile():
+    """scan_tile < 0 = "48 rows per partition step, 64 when that leaves more than two rounds of the scan kernel's pipelines":
+    both planners apply the rule alike -- a small batch keeps 48, a x5 batch is cut at 64 -- and report the tile they used."""
+    from temp_b200.planner import AUTO_TILE_PARTS, chain_partitions, plan_window, plan_window_native
+    from temp_b200.snapshot import SnapshotStore
+    for scale, want_tile in ((1, 48), (5, 64)):
+        store = SnapshotStore.synthetic("icews14", num_times=20, scale=scale, seed=7)
+        t_list = [int(t) for t in store.times[8:16]]
+        a = plan_window_native(store.train, t_list, 8, scan_tile=-48)
+        b = plan_window(store.train, t_list, 8, scan_tile=-48)
+        assert a.scan_tile == b.scan_tile == want_tile
+        _plans_equal(a, b)
+        n48 = chain_partitions(b, 48).shape[0]
+        assert (n48 > AUTO_TILE_PARTS) == (want_tile == 64)
+        rows = b.scan_parts[:, :, 1] - b.scan_parts[:, :, 0]
+        assert rows.max() <= want_tile and (want_tile == 48 or rows.max() > 48)
+
+
 def test_model_shell_answers_the_reference_hook_names_and_loaders():
     """The hook / loader surface PL and test.py call on a TKG_Module (models/TKG_Module.py:43-200) exists on the shells;
     the loaders yield batches of ``batch_size`` target timestamps."""
