@@ -19,9 +19,10 @@
 //     (34.7 cycles per MMA, tools/probes/mma_probe.cu), and the shared memory the weight image used to take holds the
 //     pipelines' tiles.  The slice is fetched by bulk copies during the first tile step (which multiplies nothing).
 //   * the state never goes through L2 between the steps of a partition: every CTA stores its 32 columns of the new
-//     state into the next step's fp32 staging tile of all four CTAs with st.async; the consumer's mbarrier counts the
-//     bytes (no fence, no arrive instruction, no cluster barrier).  Two staging tiles alternate, and the parity skips
-//     one at a partition switch, so a fast CTA never writes a tile a slow peer still reads.
+//     state into the fp32 staging tile of all four CTAs with st.async; the consumer's mbarrier counts the bytes (no
+//     fence, no cluster barrier).  One staging tile per pipeline: a tile step converts it into the operand first, then
+//     reports it vacant to the four CTAs; senders wait for the four reports of the step before they store (so a fast CTA
+//     never writes a tile a slow peer still reads, within a partition or across a partition switch).
 //   * gate exchange without a second tile: the accumulator holds gate g on TMEM lane quadrant g (rows on columns); the
 //     three gate warps park their quadrant in the k-atoms of the dead operand image OTHER than this CTA's own.
 //
