@@ -1,3 +1,8 @@
+"""Development probe (one GPU): per-rank launch programs of a snapshot-sharded forward (GDELT-shaped config 5) timed alone --
+how far phase 1 and the scan shrink with the rank's share of the rows (the exchanges are not run).
+
+    python tools/probe_sharded_single.py [scale]
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -34,5 +39,10 @@ for world in (2, 8):
         p0 = lib.Program(); p0.ops = [o for o in res.programs[0].ops if o.kind != lib.OP_H2D]
         res.programs[0].run(); torch.cuda.synchronize()
         lo, hi = shard.rows_of(r)
+        per_op = []
+        for o in p0.ops:
+            one = lib.Program()
+            one.ops = [o]
+            per_op.append(round(timeit(one), 1))
         print("world %d rank %d rows [%d,%d) of %d: phase-1 %.1f us (ops %s); scan %.1f us" % (world, r, lo, hi, plan.R, timeit(p0),
-              [round(timeit(type(p0)().__class__() if False else (lambda q: (setattr(q, 'ops', [o]) or q))(lib.Program())), 1) for o in p0.ops], timeit(res.programs[1])))
+                                                                                              per_op, timeit(res.programs[1])))
