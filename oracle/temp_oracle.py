@@ -53,6 +53,7 @@ class OracleConfig:
     learnable_lambda: bool = False
     inv_temperature: float = 0.1
     heads: int = 8                   # models/SARGCN.py:20
+    use_embed_for_non_active: bool = False   # get_all_embeds_Gt keeps ent_embeds for entities without an edge at t
 
     @property
     def bidirectional(self) -> bool:
@@ -677,7 +678,9 @@ class OracleModel:
         cfg = self.cfg
         g, t = res["graphs"][i], res["times"][i]
         L = cfg.seq_len
-        if cfg.module == "SRGCN":
+        if cfg.use_embed_for_non_active:       # DynamicRGCN.py:58-59, BiDynamicRGCN.py:105-106, SelfAttentionRGCN.py:31-32, StaticRGCN.py:51-52
+            out = self.p["ent_embeds"].clone()
+        elif cfg.module == "SRGCN":
             out = self.enc_static_isolated(t).clone()
         elif cfg.attention:
             hist, mask = res["hist"], res["mask"]

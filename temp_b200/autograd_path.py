@@ -191,6 +191,10 @@ def all_embeds(model, plan, S, i: int, S1=None, shared=None):
     temp_b200/isolated.py for the GRU flavours with --rec-only-last-layer: an entity without history has the same
     isolated state for every item up to ``+ time_embed[t]``, so that state is evaluated once per batch for all entities
     and only the entities of the item's last history step go through the cells again with their states."""
+    if bool(getattr(model.args, "use_embed_for_non_active", False)):      # DynamicRGCN.py:58-59: no isolated pass
+        fin = plan.final.instances[i]
+        ids = torch.as_tensor(fin.snapshot.node_ids, device=S.device).long()
+        return model.ent_embeds.index_copy(0, ids, S[fin.row0:fin.row0 + fin.n])
     enc = model.ent_encoder
     l1, l2 = enc.layer_1, enc.layer_2
     training = model.training
@@ -274,9 +278,12 @@ def all_embeds_static(model, plan, out, i: int):
     """baselines/StaticRGCN.py:48-58 over models/RGCN.py:161-164."""
     enc = model.ent_encoder
     t = int(plan.final_times[i])
-    y = torch.relu(_iso_pre(enc.layer_2, _iso_pre(enc.layer_1, model.ent_embeds, model.training), model.training))
-    if enc.use_time_embedding:
-        y = y + enc.layer_2.time_embed[t]
+    if bool(getattr(model.args, "use_embed_for_non_active", False)):      # StaticRGCN.py:51-52
+        y = model.ent_embeds
+    else:
+        y = torch.relu(_iso_pre(enc.layer_2, _iso_pre(enc.layer_1, model.ent_embeds, model.training), model.training))
+        if enc.use_time_embedding:
+            y = y + enc.layer_2.time_embed[t]
     fin = plan.final.instances[i]
     ids = torch.as_tensor(fin.snapshot.node_ids, device=out.device).long()
     return y.index_copy(0, ids, out[fin.row0:fin.row0 + fin.n])
@@ -338,6 +345,10 @@ def all_embeds_attention(model, plan, out, first_te, second_te, tau, i: int):
     dev = out.device
     M, L = model.num_ents, plan.seq_len
     t = int(plan.final_times[i])
+    if bool(getattr(model.args, "use_embed_for_non_active", False)):      # SelfAttentionRGCN.py:31-32: no isolated pass
+        fin = plan.final.instances[i]
+        ids = torch.as_tensor(fin.snapshot.node_ids, device=dev).long()
+        return model.ent_embeds.index_copy(0, ids, out[fin.row0 - plan.final.row0:fin.row0 - plan.final.row0 + fin.n])
     slots = np.full((M, plan.n_slots), -1, dtype=np.int64)
     for k in range(L - 1):
         inst = plan.steps_f[k].get(i)

@@ -91,7 +91,11 @@ def all_embeds_item(model, res: EncodeResult, i: int, hist_item=None) -> torch.T
         return rt._layer(layer, rows, None, x=None, x_is_embed=False, graph=False, residual=True, act=act,
                          terms=[rt._term(x, layer.loop_weight)] + list(extra_terms), **kw)
 
-    if fam == "static":
+    if bool(getattr(model.args, "use_embed_for_non_active", False)):
+        # --use-embed-for-non-active: entities without an edge at t keep their input embedding, no isolated pass
+        # (models/DynamicRGCN.py:58-59, BiDynamicRGCN.py:105-106, SelfAttentionRGCN.py:31-32, baselines/StaticRGCN.py:51-52)
+        prog.add(lib.OP_SCATTER, _scatter(E.data_ptr(), out.data_ptr(), M, D))
+    elif fam == "static":
         prog.add(lib.OP_LAYER, iso_layer(l1, E, False, h_out=y1))
         prog.add(lib.OP_LAYER, iso_layer(l2, y1, True, h_out=out, te_out=use_te, row_time_scalar=t))
     elif fam == "attention":

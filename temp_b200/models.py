@@ -75,8 +75,7 @@ class TKG_Module(nn.Module):
         if self.embed_size % args.n_bases != 0:
             raise ValueError("n_bases must divide embed_size (models/RGCN.py:25-26)")
         # reference hyper-parameters that change the computation and are NOT built: refuse instead of returning different numbers
-        for flag, why in (("use_embed_for_non_active", "the all-entity table always runs forward_isolated"),
-                          ("edge_dropout", "frequency-driven edge dropout (utils/DropEdge.py:84-146) is not built"),
+        for flag, why in (("edge_dropout", "frequency-driven edge dropout (utils/DropEdge.py:84-146) is not built"),
                           ("EMA", "the exponential-moving-average variants (models/SARGCN.py:64-82) are not built")):
             if getattr(args, flag, False):
                 raise NotImplementedError("temp_b200: --%s is not supported: %s" % (flag.replace("_", "-"), why))

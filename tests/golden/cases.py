@@ -30,6 +30,11 @@ CASES = [
     _c("grrgcn_tiny_d128_lambda", "GRRGCN", learnable_lambda=True, L=5),
     _c("grrgcn_tiny_d200_nb100", "GRRGCN", D=200, n_bases=100),
     _c("grrgcn_tiny_d128_L1", "GRRGCN", L=1, t_list=(6, 2)),
+    # --use-embed-for-non-active: entities without an edge at t keep their input embedding in the all-entity table
+    _c("grrgcn_tiny_d128_embed_nonactive", "GRRGCN", use_embed_for_non_active=True),
+    _c("bigrrgcn_tiny_d128_embed_nonactive", "BiGRRGCN", use_embed_for_non_active=True, t_list=(8, 4, 1)),
+    _c("sargcn_tiny_d128_embed_nonactive", "SARGCN", use_embed_for_non_active=True, t_list=(9, 3)),
+    _c("srgcn_tiny_d128_embed_nonactive", "SRGCN", L=1, t_list=(2, 7), use_embed_for_non_active=True),
     # --- linear recurrence flavour
     _c("rrgcn_tiny_d128_full", "RRGCN", rec_only_last_layer=False),
     _c("rrgcn_tiny_d128_last", "RRGCN"),
@@ -71,6 +76,7 @@ SAMPLER_CASES = [
 # the history steps with --random-dropout), negative sampling, tail + head cross-entropy -> the scalar loss.
 TRAIN_CASES = [
     dict(name="train_grrgcn_tiny", base="grrgcn_tiny_d128_last", seed=11, random_dropout=False),
+    dict(name="train_grrgcn_tiny_embed_nonactive", base="grrgcn_tiny_d128_embed_nonactive", seed=17, random_dropout=False),
     dict(name="train_grrgcn_tiny_random_dropout", base="grrgcn_tiny_d128_last", seed=12, random_dropout=True),
     dict(name="train_rrgcn_tiny", base="rrgcn_tiny_d128_last", seed=13, random_dropout=False),
     dict(name="train_grrgcn_icews", base="grrgcn_icews_d128_L8", seed=5, random_dropout=True, negative_rate=20),
@@ -97,6 +103,7 @@ TRAIN_CASES = [
 # makes the reference's history index lag for every later graph of the batch (`continue` before `i += 1`).
 RANK_CASES = [
     dict(name="rank_grrgcn_tiny", base="grrgcn_tiny_d128_last"),
+    dict(name="rank_grrgcn_tiny_embed_nonactive", base="grrgcn_tiny_d128_embed_nonactive"),
     dict(name="rank_rrgcn_tiny_full", base="rrgcn_tiny_d128_full"),
     dict(name="rank_bigrrgcn_tiny", base="bigrrgcn_tiny_d128_last"),
     dict(name="rank_sargcn_tiny", base="sargcn_tiny_d128_last"),

@@ -38,7 +38,7 @@ def ref_args(case):
         train_seq_len=case["L"], test_seq_len=case["L"], batch_size=len(case["t_list"]), seed=123,
         negative_rate=case.get("negative_rate", 5), num_pos_facts=case.get("num_pos_facts", 3000),
         debug=False, rec_only_last_layer=case["rec_only_last_layer"], use_time_embedding=case["use_time_embedding"],
-        inv_temperature=0.1, use_embed_for_non_active=False, edge_dropout=False, random_dropout=False,
+        inv_temperature=0.1, use_embed_for_non_active=case.get("use_embed_for_non_active", False), edge_dropout=False, random_dropout=False,
         type1=case.get("type1", False), post_ensemble=False, post_aggregation=False,
         learnable_lambda=case.get("learnable_lambda", False), impute=False, EMA=False,
         rate_lower=0.2, rate_upper=0.8, lambda_1=2, lambda_2=10, lambda_3=20)

@@ -25,7 +25,8 @@ def oracle_config(case):
                             embed_size=case["D"], n_bases=case["n_bases"], seq_len=case["L"],
                             rec_only_last_layer=case["rec_only_last_layer"],
                             use_time_embedding=True if case["module"].endswith("SARGCN") else case["use_time_embedding"],
-                            type1=case.get("type1", False), learnable_lambda=case.get("learnable_lambda", False))
+                            type1=case.get("type1", False), learnable_lambda=case.get("learnable_lambda", False),
+                            use_embed_for_non_active=case.get("use_embed_for_non_active", False))
 
 
 def oracle_model(case):
@@ -60,7 +61,8 @@ def product_args(case, impute=False, post_ensemble=False):
                      inv_temperature=0.1, type1=case.get("type1", False),
                      learnable_lambda=case.get("learnable_lambda", False), score_function="complex",
                      negative_rate=case.get("negative_rate", 5), num_pos_facts=case.get("num_pos_facts", 3000),
-                     use_cuda=True, impute=impute, post_ensemble=post_ensemble, post_aggregation=False)
+                     use_cuda=True, impute=impute, post_ensemble=post_ensemble, post_aggregation=False,
+                     use_embed_for_non_active=case.get("use_embed_for_non_active", False))
 
 
 def product_model(case, device="cuda", impute=False, post_ensemble=False):
