@@ -75,7 +75,8 @@ class TKG_Module(nn.Module):
         if self.embed_size % args.n_bases != 0:
             raise ValueError("n_bases must divide embed_size (models/RGCN.py:25-26)")
         # reference hyper-parameters that change the computation and are NOT built: refuse instead of returning different numbers
-        for flag, why in (("edge_dropout", "frequency-driven edge dropout (utils/DropEdge.py:84-146) is not built"),
+        for flag, why in (("edge_dropout", "frequency-driven edge dropout is dead code in the reference as shipped (utils/DropEdge.py:28-30: its "
+                                          "drop-rate cache is never initialised), so there is nothing to be identical to"),
                           ("EMA", "the exponential-moving-average variants (models/SARGCN.py:64-82) are not built")):
             if getattr(args, flag, False):
                 raise NotImplementedError("temp_b200: --%s is not supported: %s" % (flag.replace("_", "-"), why))
