@@ -454,6 +454,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       const int i = 4 * gw + rsub + kRP * u;
       h0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       nrow[u] = -1;
+      // (a partition's first tile step has no state to read: the planner links a row only to the previous step's rows)
+      if (kChained && !has_prev && rb + i < r1 && cur.prv[u] >= 0) __trap();
       if (rb + i < r1 && has_prev && cur.prv[u] >= 0) {
         const int n = kChained ? cur.prv[u] - prev_rb : i;
         if (kChained && (n < 0 || n >= prev_rows)) __trap();   // a state row outside the previous step of this partition

@@ -257,7 +257,7 @@ class Program(object):
         def flush():
             while run:
                 chunk, rest = run[:MAX_SCAN_STEPS], run[MAX_SCAN_STEPS:]
-                if len(chunk) == 1:
+                if len(chunk) == 1 and not split_cells:
                     out.append(chunk[0])
                 else:
                     a = GruScanArgs()
@@ -291,16 +291,27 @@ class Program(object):
                          multicast_ptr: int = 0) -> None:
         """Fused all-gather: the scan steps that write the FINAL value of rows [row0, row1) (the last op over exactly that
         range) also store it into every peer's buffer (TempGruScanArgs.push_*)."""
-        scans = [o for o in self.ops if o.kind == OP_GRU_SCAN]
-        if not scans:
+        # the LAST op that writes the rows must be a scan step over exactly that range (e.g. the Bi centre step of the
+        # backward cell, which accumulates into the forward cell's result): walk the program backwards
+        sc, last = None, None
+        for o in reversed(self.ops):
+            if o.kind == OP_GRU and o.u.gru.row0 < row1 and o.u.gru.row1 > row0:
+                raise RuntimeError("temp_b200: the pushed rows are last written by an unfused GRU step")
+            if o.kind == OP_GRU_SCAN:
+                hit = [i for i in range(o.u.scan.n_steps) if o.u.scan.steps[i].row0 < row1 and o.u.scan.steps[i].row1 > row0]
+                if hit:
+                    st = o.u.scan.steps[hit[-1]]
+                    if st.row0 != row0 or st.row1 != row1:
+                        raise RuntimeError("temp_b200: no scan step covers exactly the pushed row range")
+                    sc, last = o.u.scan, hit[-1]
+                    break
+        if sc is None:
             raise RuntimeError("temp_b200: peer push needs the fused GRU scan")
-        sc = scans[-1].u.scan
-        last = [i for i in range(sc.n_steps) if sc.steps[i].row0 == row0 and sc.steps[i].row1 == row1]
-        if not last:
-            raise RuntimeError("temp_b200: no scan step covers the pushed row range")
-        for i in range(sc.n_steps):
-            sc.steps[i].push = 0
-        sc.steps[last[-1]].push = 1
+        for o in self.ops:
+            if o.kind == OP_GRU_SCAN:
+                for i in range(o.u.scan.n_steps):
+                    o.u.scan.steps[i].push = 0
+        sc.steps[last].push = 1
         sc.push_bufs, sc.push_world, sc.push_offset, sc.push_row0 = bufs_dev_ptr or None, int(world), int(offset_elems), int(row0)
         sc.push_multicast = multicast_ptr or None
         self._arr = None

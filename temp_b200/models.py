@@ -210,9 +210,9 @@ class TKG_Module(nn.Module):
             del cache[k]                                                 # the slot's staged plan copy is about to be overwritten
         tag = "plan_c%d" % slot
         res = self.runtime.build(plan, tag=tag)
+        res.cache_slot = slot                                            # (a kept result owns its pinned host buffer)
         if to_host:
             self._attach_host_out(res)
-        res.cache_slot = slot
         res.replay = lib.Program()                                       # the same launches without the plan upload
         res.replay.ops = [o for o in res.program.ops if o.kind != lib.OP_H2D]
         res.replay.keepalive = res.program.keepalive
@@ -223,13 +223,25 @@ class TKG_Module(nn.Module):
     def _attach_host_out(self, res: EncodeResult) -> None:
         """``res.host_out``: pinned host copy of ``res.out`` written by the program itself (see ``encode(to_host=True)``)."""
         nf, D = int(res.out.shape[0]), self.embed_size
-        host = torch.empty(max(nf, 1), D, dtype=torch.float32, pin_memory=True)[:nf]
+        if getattr(res, "cache_slot", None) is None:
+            # a result that is not kept (encode_cache_size == 0, encode(plan=...)): ONE grow-only pinned buffer and its device
+            # pointer cell are reused -- a pinned allocation plus a pageable 8-byte upload cost 0.3 ms per call otherwise;
+            # the buffer is valid until the next such call, like ``res.out``
+            pool = getattr(self, "_host_out_pool", None)
+            if pool is None or pool[0].shape[0] < max(nf, 1) or pool[1].device != res.out.device:
+                buf = torch.empty(max(2 * nf, 1024), D, dtype=torch.float32, pin_memory=True)
+                pool = self._host_out_pool = (buf, torch.tensor([buf.data_ptr()], dtype=torch.int64, device=res.out.device))
+            host, ptrs = pool[0][:nf], pool[1]
+        else:
+            host = torch.empty(max(nf, 1), D, dtype=torch.float32, pin_memory=True)[:nf]
+            ptrs = None
         prog, fin = res.program, res.plan.final
         pushed = False
         tc_scan = (self.family == "recurrent" and self.runtime.use_tc and D == 128 and self.runtime.fuse_scan
                    and self.ent_encoder.rec_only_last_layer and self.args.module in ("GRRGCN", "BiGRRGCN"))
         if tc_scan:
-            ptrs = torch.tensor([host.data_ptr()], dtype=torch.int64, device=res.out.device)
+            if ptrs is None:
+                ptrs = torch.tensor([host.data_ptr()], dtype=torch.int64, device=res.out.device)
             try:
                 prog.enable_peer_push(ptrs.data_ptr(), 1, 0, fin.row0, fin.row1)
                 prog.keepalive.append(ptrs)

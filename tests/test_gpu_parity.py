@@ -390,6 +390,33 @@ def test_kept_programs_survive_a_growing_workspace(name):
     del junk
 
 
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_icews_d128_L8", "sargcn_tiny_d128_last", "grrgcn_tiny_d200_nb100"])
+def test_encode_to_host_lands_the_final_states_in_pinned_memory(name):
+    """encode(to_host=True): res.host_out equals res.out after a synchronise -- written from inside the scan kernel on the
+    tensor-memory path, by a device-to-host copy op elsewhere; kept results own their buffer, results that are not kept
+    share one grow-only buffer (valid until the next call)."""
+    from tests.helpers import CASE_BY_NAME
+    case = CASE_BY_NAME[name]
+    model = product_model(case)
+    tl = list(case["t_list"])
+    a = model.encode(tl, to_host=True)
+    torch.cuda.synchronize()
+    assert a.host_out.is_pinned() and torch.equal(a.host_out, a.out.cpu())
+    keep = a.host_out.clone()
+    b = model.encode(tl[:1], to_host=True)                      # another kept batch: its own buffer
+    torch.cuda.synchronize()
+    assert torch.equal(b.host_out, b.out.cpu()) and torch.equal(a.host_out, keep)
+    again = model.encode(tl, to_host=True, reupload=True)       # the kept program, plan re-copied from pinned memory
+    torch.cuda.synchronize()
+    assert again is a and torch.equal(a.host_out, keep)
+    model.encode_cache_size = 0
+    for t_list in (tl, tl[:1], tl):
+        r = model.encode(t_list, to_host=True)
+        torch.cuda.synchronize()
+        assert torch.equal(r.host_out, r.out.cpu())
+    assert torch.equal(r.host_out, keep)
+
+
 def test_reference_api_calls_hand_out_fresh_tensors():
     """evaluate_embed / train_embed return tensors the caller may keep across batches, as the reference's do (test.py and
     the analysis scripts collect them); only model.encode() hands out views into the runtime's workspace."""

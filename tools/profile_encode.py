@@ -38,7 +38,7 @@ print("build only: %.3f ms per call" % (1e3 * (time.perf_counter() - t0) / n))
 pr = cProfile.Profile()
 pr.enable()
 for i in range(n):
-    model.encode(t_lists[i % 8])
+    model.encode(t_lists[i % 8], to_host=True)
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
