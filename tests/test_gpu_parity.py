@@ -156,6 +156,23 @@ def test_snapshot_sharded_forward_over_nccl():
     assert "sharded ok" in out.stdout
 
 
+def test_bidirectional_model_through_both_multi_gpu_paths():
+    """2 GPUs: the BiGRRGCN forward (one scan per direction, the backward cell's centre step accumulating) sharded by
+    snapshot with in-kernel exchanges -- bit-identical to the unsharded forward, also for batches at the end of the timeline
+    whose backward chain is the centre step alone -- and its final states through the fused all-gather against NCCL."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(root, "tools", "check_bi_multi.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "bi multi ok" in out.stdout
+
+
 @pytest.mark.parametrize("tc", __import__("tests.golden.cases", fromlist=["TRAIN_CASES"]).TRAIN_CASES,
                          ids=lambda c: c["name"])
 def test_training_forward_loss_matches_reference(tc):
