@@ -360,54 +360,91 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     if (p.time_embed != nullptr && !te_rows)
       te_uni = __ldg(reinterpret_cast<const float4*>(p.time_embed + static_cast<size_t>(cur.tr0) * kD + j4));
 
-    // ---- the previous state -> shared-memory operand (tf32 hi / lo parts; the decay is applied after the MMA) ----------
-    {
-      float4 v[kU];
-      if (kChained) {
-        has_prev = chain_part == part;
-        nmma = (prev_rows + 15) & ~15;
-        if (has_prev) {
-          mbar_wait(&S.ready[pipe], ready_par);   // the staging tile is complete (all 4 CTAs' columns)
-          ready_par ^= 1u;
-          TLS(1);
+    // ---- the previous state -> shared-memory operand (tf32 hi / lo parts; the decay is applied after the MMA), and
+    // gh^T = W_hh . h0^T : 16 k-steps x 3 split passes, A from tensor memory -------------------------------------------
+    auto issue_atoms = [&](int ka0, int ka1, uint32_t s_hi, uint32_t s_lo) {   // (one elected lane) k-atoms [ka0, ka1)
+      const uint32_t idesc = umma_idesc_tf32(128, nmma);
 #pragma unroll
-          for (int u = 0; u < kU; ++u) {
-            const int n = gw + kPW * u;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < prev_rows) v[u] = lds_f32x4(s_stage + n * 512 + lane * 16);
-          }
-        }
-      } else {
-        nmma = (r1 - rb + 15) & ~15;
+      for (int ka = ka0; ka < ka1; ++ka) {
+        const uint32_t bh0 = umma_desc_lo(s_hi + ka * kAtomBytes), bl0 = umma_desc_lo(s_lo + ka * kAtomBytes);
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int pr = __shfl_sync(kFull, cur.gprv, u);
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pr >= 0) v[u] = ld_dep_f32x4(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a_hi = tbase + ka * 32 + ks * 8, a_lo = a_hi + kColWLo;
+          const uint32_t bh = bh0 + 2 * ks, bl = bl0 + 2 * ks;          // +32 bytes per k-step inside the atom
+          umma_tf32_ts(dcol, a_lo, bh, idesc, (ka | ks) != 0 ? 1u : 0u);  // small terms first
+          umma_tf32_ts(dcol, a_hi, bl, idesc, 1u);
+          umma_tf32_ts(dcol, a_hi, bh, idesc, 1u);
         }
-        has_prev = true;   // (decided below by the reduction)
       }
+    };
+    if (kChained) {
+      has_prev = chain_part == part;
+      nmma = (prev_rows + 15) & ~15;
       if (has_prev) {
+        mbar_wait(&S.ready[pipe], ready_par);   // the staging tile is complete (all 4 CTAs' columns)
+        ready_par ^= 1u;
+        TLS(1);
+        // Two stages of two k-atoms each: while the issuing warp feeds the tensor pipe with the first half (the issue loop
+        // is throttled to the pipe's rate, ~35 cycles per MMA), the other warps convert the second half.  A load covers two
+        // rows x 256 bytes (lane >> 4 = row of the pair, lane & 15 = 16-byte chunk = 2 atoms x 8 chunks).
+        const int rsel = lane >> 4, asel = (lane & 15) >> 3, cch = lane & 7;
+        auto convert = [&](int stage, int first, int stride, int count) {
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int i = gw + kPW * u;
-          if (i >= nmma) continue;   // warp-uniform: beyond the rows this step's MMA reads
-          float4 hi, lo;
-          split_tf32(v[u].x, hi.x, lo.x);
-          split_tf32(v[u].y, hi.y, lo.y);
-          split_tf32(v[u].z, hi.z, lo.z);
-          split_tf32(v[u].w, hi.w, lo.w);
-          const uint32_t off = static_cast<uint32_t>(lane >> 3) * kAtomBytes + (i >> 3) * 1024u + (i & 7) * 128u +
-                               (((lane & 7) ^ (i & 7)) << 4);
-          sts_f32x4(s_bhi + off, hi);
-          sts_f32x4(s_blo + off, lo);
-        }
+          for (int j = 0; j < count; ++j) {
+            const int q = first + stride * j;          // row pair
+            if (2 * q >= nmma) continue;               // warp-uniform: beyond the rows this step's MMA reads
+            const int i = 2 * q + rsel, ka = 2 * stage + asel;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < prev_rows) v = lds_f32x4(s_stage + i * 512 + ka * 128 + cch * 16);
+            float4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x);
+            split_tf32(v.y, hi.y, lo.y);
+            split_tf32(v.z, hi.z, lo.z);
+            split_tf32(v.w, hi.w, lo.w);
+            const uint32_t off = static_cast<uint32_t>(ka) * kAtomBytes + (i >> 3) * 1024u + (i & 7) * 128u + ((cch ^ (i & 7)) << 4);
+            sts_f32x4(s_bhi + off, hi);
+            sts_f32x4(s_blo + off, lo);
+          }
+        };
+        constexpr int kPairs = kRows / 2;
+        convert(0, gw, kPW, (kPairs + kPW - 1) / kPW);                                   // stage 0: all warps
         fence_proxy_async();
-        if (kChained)
-          bar_named(bar_id, kPT);
-        else
-          has_prev = bar_red_or(bar_id, kPT, __any_sync(kFull, lane < kU && cur.gprv >= 0));
+        bar_named(bar_id, kPT);
+        if (gw == 0) {   // warp-uniform: the issuing warp
+          tc_fence_after();
+          if (elect_one()) issue_atoms(0, 2, s_bhi, s_blo);
+          __syncwarp();
+        } else {
+          convert(1, gw - 1, kPW - 1, (kPairs + kPW - 2) / (kPW - 1));                    // stage 1: everyone else
+          fence_proxy_async();
+        }
+        bar_named(bar_id, kPT);
       }
+    } else {
+      float4 v[kU];
+      nmma = (r1 - rb + 15) & ~15;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pr = __shfl_sync(kFull, cur.gprv, u);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pr >= 0) v[u] = ld_dep_f32x4(reinterpret_cast<const float4*>(p.state + static_cast<size_t>(pr) * kD) + lane);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = gw + kPW * u;
+        if (i >= nmma) continue;   // warp-uniform: beyond the rows this step's MMA reads
+        float4 hi, lo;
+        split_tf32(v[u].x, hi.x, lo.x);
+        split_tf32(v[u].y, hi.y, lo.y);
+        split_tf32(v[u].z, hi.z, lo.z);
+        split_tf32(v[u].w, hi.w, lo.w);
+        const uint32_t off = static_cast<uint32_t>(lane >> 3) * kAtomBytes + (i >> 3) * 1024u + (i & 7) * 128u +
+                             (((lane & 7) ^ (i & 7)) << 4);
+        sts_f32x4(s_bhi + off, hi);
+        sts_f32x4(s_blo + off, lo);
+      }
+      fence_proxy_async();
+      has_prev = bar_red_or(bar_id, kPT, __any_sync(kFull, lane < kU && cur.gprv >= 0));
     }
     TLS(2);
 
@@ -423,23 +460,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
 
-    // ---- gh^T = W_hh . h0^T : 16 k-steps x 3 split passes, A from tensor memory -----------------------------------
+    // ---- the (rest of the) MMA batch ------------------------------------------------------------------------------
     if (has_prev && gw == 0) {   // warp-uniform
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t idesc = umma_idesc_tf32(128, nmma);
-#pragma unroll
-        for (int ka = 0; ka < 4; ++ka) {
-          const uint32_t bh0 = umma_desc_lo(s_bhi + ka * kAtomBytes), bl0 = umma_desc_lo(s_blo + ka * kAtomBytes);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t a_hi = tbase + ka * 32 + ks * 8, a_lo = a_hi + kColWLo;
-            const uint32_t bh = bh0 + 2 * ks, bl = bl0 + 2 * ks;          // +32 bytes per k-step inside the atom
-            umma_tf32_ts(dcol, a_lo, bh, idesc, (ka | ks) != 0 ? 1u : 0u);  // small terms first
-            umma_tf32_ts(dcol, a_hi, bl, idesc, 1u);
-            umma_tf32_ts(dcol, a_hi, bh, idesc, 1u);
-          }
-        }
+        if (kChained)
+          issue_atoms(2, 4, s_bhi, s_blo);
+        else
+          issue_atoms(0, 4, s_bhi, s_blo);
         umma_commit(&S.mma_done[pipe]);
       }
       __syncwarp();
