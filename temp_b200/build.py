@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("temp_kernels.cu", "tc_kernels.cu", "tc_scan2.cu", "planner.cpp")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("temp_kernels.cu", "tc_kernels.cu", "tc_scan2.cu", "tc_wide.cu", "planner.cpp")]
 HEADERS = [os.path.join(ROOT, "include", "temp_b200.h"), os.path.join(HERE, "csrc", "internal.h"),
            os.path.join(HERE, "csrc", "tc_common.cuh")]
 

@@ -25,6 +25,13 @@ int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
 bool tc_scan2_supported(const TempGruScanArgs* a);
 int tc_launch_scan2(const TempGruScanArgs* a, cudaStream_t st);
 int tc_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st);
+// 64-row tile kernel for the other widths (tc_wide.cu): d % 4 == 0, d <= 256, 1x1 / 2x2 / 4x4 relation blocks;
+// tc_layer_supported / tc_launch_layer / tc_launch_gather / tc_pack_weights dispatch to these
+bool tcw_layer_supported(const TempRgcnLayerArgs* a);
+int tcw_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st);
+int tcw_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st);
+int64_t tcw_packed_bytes(int k, int n);
+int tcw_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st);
 int tc_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st);
 
 }  // namespace temp_internal

@@ -1105,6 +1105,9 @@ extern "C" int temp_debug_timeline(void* device_buffer) {  // [ctas][20 warps][6
 
 namespace temp_internal {
 
+// d == 128 with 1x1 relation blocks: the 128-row tile kernel of this file; every other supported shape: tc_wide.cu
+static bool wide_shape(const TempRgcnLayerArgs* a) { return a->d != kD || (a->row_ptr != nullptr && a->si != 1); }
+
 // thread blocks of the aggregation launch that precedes the tile kernel (0: no launch)
 int tc_gather_grid(const TempRgcnLayerArgs* a) {
   if (a->row_ptr == nullptr || a->row1 <= a->row0) return 0;
@@ -1120,6 +1123,7 @@ int tc_gather_launches(const TempRgcnLayerArgs* a) { return tc_gather_grid(a) > 
 // 5 % faster on ICEWS14-shaped rows (55.3 vs 58.3 us) and 33 % slower on GDELT-shaped rows (697 vs 523 us: 64 KB of ring per
 // CTA leaves 24 instead of 40 warps per SM for the high in-degree rows) -- LDG is the default, TEMP_GATHER=bulk opts in.
 int tc_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st) {
+  if (wide_shape(a)) return tcw_launch_gather(a, st);
   static const char* mode = getenv("TEMP_GATHER");
   const bool bulk = mode != nullptr && strcmp(mode, "bulk") == 0;
   if (bulk && a->agg_lists != 0) {
@@ -1140,6 +1144,7 @@ int tc_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st) {
 }
 
 bool tc_layer_supported(const TempRgcnLayerArgs* a) {
+  if (wide_shape(a)) return tcw_layer_supported(a);
   if (a->d != kD || a->n_terms != 1) return false;
   const TempDenseTerm& t = a->terms[0];
   if (t.w_packed == nullptr || t.a_dt != nullptr) return false;
@@ -1154,6 +1159,7 @@ bool tc_layer_supported(const TempRgcnLayerArgs* a) {
 }
 
 int tc_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
+  if (wide_shape(a)) return tcw_launch_layer(a, st);
   static bool configured = false;
   if (int rc = ensure_smem_once(rgcn_layer_tc_kernel, kLayerSmem, "rgcn_layer_tc_kernel", configured)) return rc;
   const int rows = a->row1 - a->row0;
@@ -1216,6 +1222,7 @@ int tc_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
 }
 
 int tc_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st) {
+  if (k != kD || (n & 127) != 0) return tcw_pack_weights(w_kn, k, n, packed, st);   // (for k == 128, n % 128 == 0 the images coincide)
   if (w_kn == nullptr || packed == nullptr || k != kD || n <= 0 || (n & 127) != 0)
     return fail(TEMP_EINVAL, "temp_pack_weights: k must be 128 and n a positive multiple of 128%s", "");
   pack_weights_kernel<<<(kD * n + 255) / 256, 256, 0, st>>>(w_kn, n, static_cast<uint8_t*>(packed));

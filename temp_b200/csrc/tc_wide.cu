@@ -1,0 +1,588 @@
+// temp_b200 -- tcgen05 RGCN layer for every width the 128-wide kernels of tc_kernels.cu do not take: embed_size ==
+// hidden_size = d with d % 4 == 0, d <= 256 (BASELINE config 3 as the reference ships it: n_bases = 100 => d = 200,
+// 2x2 relation blocks, models/RGCN.py:25-26), and d == 128 with 2x2 / 4x4 relation blocks.
+//
+// Same conventions as tc_kernels.cu ("features on TMEM lanes", 3xTF32 operand split, packed weight chunks of 128
+// features x 32 k fetched by the TMA engine); what differs is the tiling:
+//   * K = d is padded to KA = ceil(d / 32) k-atoms (zero columns), the output features to ceil(d / 128) blocks of 128
+//     TMEM lanes (zero weight rows) -- pack_weights_wide_kernel writes the padded image;
+//   * a tile is 64 packed rows (UMMA N = 64): hi + lo operand images of 64 x 32 KA floats (112 KB at d = 200) next to
+//     the 3-stage weight ring (96 KB);
+//   * the self-loop GEMM fills up to two 64-column accumulators (feature blocks), the chained GEMM walks
+//     ceil(chain_n / 128) feature blocks through a ring of three.
+//
+//   rgcn_gather_wide_kernel<S> : the CSR-by-destination aggregation with S x S relation blocks (S = 1, 2, 4) applied in
+//        registers -- a lane owns float4 channel groups lane and lane + 32, a float4 holds whole blocks for these S, so
+//        the block product needs nothing from another lane.  Arithmetic (and summation order) of rgcn_layer_kernel's
+//        aggregation in temp_kernels.cu, to which the parity tests hold it.
+//   rgcn_layer_tcw_kernel      : one CTA per 64 packed rows; 8 worker warps (operand staging, both epilogues), a TMA
+//        warp (weight chunks), an MMA warp -- the structure of rgcn_layer_tc_kernel.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <utility>
+
+#include "internal.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWRows = 64;                       // packed rows per tile = UMMA N
+constexpr int kWMaxAtoms = 8;                    // d <= 256
+constexpr int kWStages = 3;
+constexpr int kWWorkerWarps = 8;
+constexpr int kWWorkers = kWWorkerWarps * 32;
+constexpr int kWThreads = kWWorkers + 128;       // + control warpgroup (TMA warp 8, MMA warp 9, two idle warps)
+constexpr int kWAtomBytes = kWRows * 128;        // 8 KB: one k-atom block of one operand image
+
+__host__ __device__ constexpr int wide_smem_bytes(int ka) { return 2 * ka * kWAtomBytes + kWStages * kWChunkBytes + 1024; }
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (once per parameter version)
+// ------------------------------------------------------------------------------------------------
+// w [k, n] row-major.  Chunk (mb, ka) at (mb * KA + ka) * 32 KB holds element (feature m of the 128-feature block mb,
+// k of k-atom ka), hi image then lo image; features >= n and k >= the matrix's k are zero.
+__global__ void pack_weights_wide_kernel(const float* __restrict__ w, int k_dim, int n, int KA, int n_mb,
+                                         uint8_t* __restrict__ out) {
+  const int total = n_mb * KA * 128 * 32;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int chunk = idx >> 12, rem = idx & 4095;        // 128 features x 32 k per chunk
+    const int kk = rem >> 7, m = rem & 127;               // consecutive threads: consecutive features (coalesced reads)
+    const int mb = chunk / KA, ka = chunk - mb * KA;
+    const int k = 32 * ka + kk, col = 128 * mb + m;
+    const float v = (k < k_dim && col < n) ? w[static_cast<size_t>(k) * n + col] : 0.f;
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    uint8_t* dst = out + static_cast<size_t>(chunk) * kWChunkBytes;
+    const uint32_t off = sw128_off(m, kk);
+    *reinterpret_cast<float*>(dst + off) = hi;
+    *reinterpret_cast<float*>(dst + 128 * 128 + off) = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregation with S x S relation blocks
+// ------------------------------------------------------------------------------------------------
+// msg[b * S + j] = sum_i x[b * S + i] * W[rel][(b * S + i) * S + j]   (RGCN.py:91-98: bmm over the blocks), accumulated
+// as m = fmaf(x_i, w_ij, m) from m = 0 in the order of i -- the statement of rgcn_layer_kernel (temp_kernels.cu).
+// `w` points at the first weight of the float4's first block: S * 4 consecutive floats serve the 4 channels.
+template <int S>
+__device__ __forceinline__ float4 block_msg(const float4 x, const float* __restrict__ w) {
+  float4 m;
+  if (S == 1) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w));
+    m.x = __fmul_rn(x.x, a.x);
+    m.y = __fmul_rn(x.y, a.y);
+    m.z = __fmul_rn(x.z, a.z);
+    m.w = __fmul_rn(x.w, a.w);
+  } else if (S == 2) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w));      // block 0: W00 W01 W10 W11
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w) + 1);  // block 1
+    m.x = __fmaf_rn(x.y, a.z, __fmul_rn(x.x, a.x));
+    m.y = __fmaf_rn(x.y, a.w, __fmul_rn(x.x, a.y));
+    m.z = __fmaf_rn(x.w, b.z, __fmul_rn(x.z, b.x));
+    m.w = __fmaf_rn(x.w, b.w, __fmul_rn(x.z, b.y));
+  } else {
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(w));     // W0j
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
+    const float4 r2 = __ldg(reinterpret_cast<const float4*>(w) + 2);
+    const float4 r3 = __ldg(reinterpret_cast<const float4*>(w) + 3);
+    m.x = __fmaf_rn(x.w, r3.x, __fmaf_rn(x.z, r2.x, __fmaf_rn(x.y, r1.x, __fmul_rn(x.x, r0.x))));
+    m.y = __fmaf_rn(x.w, r3.y, __fmaf_rn(x.z, r2.y, __fmaf_rn(x.y, r1.y, __fmul_rn(x.x, r0.y))));
+    m.z = __fmaf_rn(x.w, r3.z, __fmaf_rn(x.z, r2.z, __fmaf_rn(x.y, r1.z, __fmul_rn(x.x, r0.z))));
+    m.w = __fmaf_rn(x.w, r3.w, __fmaf_rn(x.z, r2.w, __fmaf_rn(x.y, r1.w, __fmul_rn(x.x, r0.w))));
+  }
+  return m;
+}
+
+constexpr int kGWWarps = 8;
+
+// sum over the edges [e0, e1) of msg * nrm for this lane's channel groups lane (a) and lane + 32 (b), in edge order.
+// The first chunk's indices are plan data and are fetched BEFORE pdl_wait(); the feature rows after it.
+template <int S>
+__device__ __forceinline__ void gather_edges_wide(const TempRgcnLayerArgs& p, int e0, int e1, float nrm, int lane, bool oka,
+                                                  bool okb, float4& acc_a, float4& acc_b) {
+  const int D = p.d;
+  const size_t wrow = static_cast<size_t>(D) * S;        // floats per relation: n_bases * S * S
+  acc_a = make_float4(0.f, 0.f, 0.f, 0.f);
+  acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s0 = 0, rl0 = 0;
+  if (e0 + lane < e1) {
+    s0 = __ldg(p.e_src + e0 + lane);
+    rl0 = __ldg(p.e_rel + e0 + lane);
+  }
+  pdl_wait();
+  for (int base = e0; base < e1; base += 32) {
+    const int cnt = min(32, e1 - base);
+    int s = s0, rl = rl0;
+    if (base != e0 && lane < cnt) {
+      s = __ldg(p.e_src + base + lane);
+      rl = __ldg(p.e_rel + base + lane);
+    }
+#pragma unroll 1
+    for (int u0 = 0; u0 < cnt; u0 += 2) {
+      float4 xa[2], xb[2];
+      int ru[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int su = __shfl_sync(kFull, s, (u0 + u) & 31);
+        ru[u] = __shfl_sync(kFull, rl, (u0 + u) & 31);
+        xa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u0 + u < cnt) {
+          const float* xr = p.x + static_cast<size_t>(su) * D;
+          if (oka) xa[u] = ld_dep_f32x4(xr + 4 * lane);              // (the previous layer's output)
+          if (okb) xb[u] = ld_dep_f32x4(xr + 4 * (lane + 32));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u0 + u < cnt) {                                          // msg * norm_e, summed in edge order (RGCN.py:92-97)
+          const float* wr = p.weight + static_cast<size_t>(ru[u]) * wrow;
+          if (oka) {
+            const float4 m = block_msg<S>(xa[u], wr + static_cast<size_t>(4 * S) * lane);
+            acc_a.x += m.x * nrm; acc_a.y += m.y * nrm; acc_a.z += m.z * nrm; acc_a.w += m.w * nrm;
+          }
+          if (okb) {
+            const float4 m = block_msg<S>(xb[u], wr + static_cast<size_t>(4 * S) * (lane + 32));
+            acc_b.x += m.x * nrm; acc_b.y += m.y * nrm; acc_b.z += m.z * nrm; acc_b.w += m.w * nrm;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kGWWarps * 32, 4) rgcn_gather_wide_kernel(const TempRgcnLayerArgs p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = p.d, nv = D >> 2;
+  const bool oka = lane < nv, okb = lane + 32 < nv;
+  pdl_launch_dependents();
+  if (p.agg_lists != 0 && static_cast<int>(blockIdx.x) < p.n_agg_heavy) {
+    // ---- a high in-degree row: the block's 8 warps sum contiguous edge chunks, partials added in chunk order ----
+    __shared__ float4 part[kGWWarps][2][32];
+    const int t = lane < 3 ? __ldg(p.agg_heavy + 3 * static_cast<size_t>(blockIdx.x) + lane) : 0;
+    const int r = __shfl_sync(kFull, t, 0), p0 = __shfl_sync(kFull, t, 1), p1 = __shfl_sync(kFull, t, 2);
+    const float nrm = __ldg(p.norm + r);
+    const int chunk = (p1 - p0 + kGWWarps - 1) / kGWWarps;
+    const int e0 = min(p0 + warp * chunk, p1), e1 = min(e0 + chunk, p1);
+    float4 a, b;
+    gather_edges_wide<S>(p, e0, e1, nrm, lane, oka, okb, a, b);
+    part[warp][0][lane] = a;
+    part[warp][1][lane] = b;
+    __syncthreads();
+    if (warp < 2) {
+      float4 v = part[0][warp][lane];
+#pragma unroll
+      for (int w = 1; w < kGWWarps; ++w) {
+        const float4 q = part[w][warp][lane];
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      v.x *= nrm; v.y *= nrm; v.z *= nrm; v.w *= nrm;  // apply_func (RGCN.py:103-104)
+      if (warp == 0 ? oka : okb)
+        reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * D)[lane + 32 * warp] = v;
+    }
+    return;
+  }
+  int r, p0, p1;
+  if (p.agg_lists != 0) {  // compact work list: rows with in-edges only, CSR range inline
+    const int item = (static_cast<int>(blockIdx.x) - p.n_agg_heavy) * kGWWarps + warp;
+    if (item >= p.n_agg_rows) return;
+    const int t = lane < 3 ? __ldg(p.agg_rows + 3 * static_cast<size_t>(item) + lane) : 0;
+    r = __shfl_sync(kFull, t, 0);
+    p0 = __shfl_sync(kFull, t, 1);
+    p1 = __shfl_sync(kFull, t, 2);
+  } else {
+    r = p.row0 + blockIdx.x * kGWWarps + warp;
+    if (r >= p.row1) return;
+    p0 = __ldg(p.row_ptr + r);
+    p1 = __ldg(p.row_ptr + r + 1);
+    if (p1 <= p0) return;
+  }
+  const float nrm = __ldg(p.norm + r);
+  float4 a, b;
+  gather_edges_wide<S>(p, p0, p1, nrm, lane, oka, okb, a, b);
+  float4* dst = reinterpret_cast<float4*>(p.agg_scratch + static_cast<size_t>(r) * D);
+  if (oka) {
+    a.x *= nrm; a.y *= nrm; a.z *= nrm; a.w *= nrm;  // apply_func (RGCN.py:103-104)
+    dst[lane] = a;
+  }
+  if (okb) {
+    b.x *= nrm; b.y *= nrm; b.z *= nrm; b.w *= nrm;
+    dst[lane + 32] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused RGCN layer, tcgen05, 64-row tiles
+// ------------------------------------------------------------------------------------------------
+struct WideBars {
+  uint64_t w_full[kWStages], w_empty[kWStages];
+  uint64_t b_ready, d1_full, x_ready;
+  uint64_t d2_full[3], d2_empty[3];
+  uint32_t tmem_base;
+};
+
+// TMEM columns: self-loop accumulators of feature blocks 0 / 1 at [0, 64) / [64, 128); chain ring slots at 128 + 64 s.
+__global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const TempRgcnLayerArgs p, const int KA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + KA * kWAtomBytes;
+  uint8_t* ring = smem + 2 * KA * kWAtomBytes;
+  __shared__ WideBars S;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(kFull, tid >> 5, 0);       // provably warp-uniform (see rgcn_layer_tc_kernel)
+  const int D = p.d;
+  const int rbase = p.row0 + blockIdx.x * kWRows;
+  const int n_fb = (D + 127) >> 7;
+  const int n_mb = p.chain_w_packed != nullptr ? (p.chain_n + 127) >> 7 : 0;
+  pdl_launch_dependents();
+
+  if (tid == 0) {
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&S.w_full[i], 1);
+      mbar_init(&S.w_empty[i], 1);
+    }
+    mbar_init(&S.b_ready, kWWorkers);
+    mbar_init(&S.d1_full, 1);
+    mbar_init(&S.x_ready, kWWorkers);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&S.d2_full[i], 1);
+      mbar_init(&S.d2_empty[i], kWWorkers);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&S.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = S.tmem_base;
+
+  if (warp_u >= kWWorkerWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == 8 && lane == 0) {
+      // ===== TMA producer: the self-loop weight chunks, then the chain's, in the order the MMA warp consumes them =====
+      const uint8_t* w1 = static_cast<const uint8_t*>(p.terms[0].w_packed);
+      const uint8_t* wc = static_cast<const uint8_t*>(p.chain_w_packed);
+      const int n1 = KA * n_fb, total = n1 + KA * n_mb;
+      for (int i = 0; i < total; ++i) {
+        const int st = i % kWStages;
+        if (i >= kWStages) mbar_wait(&S.w_empty[st], ((i / kWStages) - 1) & 1);
+        const uint8_t* src = i < n1 ? w1 + static_cast<size_t>(i) * kWChunkBytes : wc + static_cast<size_t>(i - n1) * kWChunkBytes;
+        mbar_expect_tx(&S.w_full[st], kWChunkBytes);
+        bulk_g2s(ring + st * kWChunkBytes, src, kWChunkBytes, &S.w_full[st]);
+      }
+    } else if (warp_u == 9) {
+      // ===== MMA issuer: the whole warp walks the pipeline, the elected lane issues =====
+      const bool leader = elect_one();
+      const uint32_t tb = __shfl_sync(kFull, S.tmem_base, 0);
+      const uint32_t idesc = umma_idesc_tf32(128, kWRows);
+      const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo), rg = smem_u32(ring);
+      int i = 0;
+      mbar_wait(&S.b_ready, 0);
+      tc_fence_after();
+      for (int fb = 0; fb < n_fb; ++fb) {
+#pragma unroll 1
+        for (int ka = 0; ka < KA; ++ka, ++i) {
+          const int st = i % kWStages;
+          mbar_wait(&S.w_full[st], (i / kWStages) & 1);
+          tc_fence_after();
+          if (leader) {
+            umma_katom_3x(tb + 64 * fb, rg + st * kWChunkBytes, bh + ka * kWAtomBytes, bl + ka * kWAtomBytes, idesc, ka == 0);
+            umma_commit(&S.w_empty[st]);
+          }
+          __syncwarp();
+        }
+      }
+      if (leader) umma_commit(&S.d1_full);
+      __syncwarp();
+      if (n_mb > 0) {
+        mbar_wait(&S.x_ready, 0);
+        tc_fence_after();
+        for (int mb = 0; mb < n_mb; ++mb) {
+          const int slot = mb % 3;
+          if (mb >= 3) {
+            mbar_wait(&S.d2_empty[slot], ((mb / 3) - 1) & 1);
+            tc_fence_after();
+          }
+#pragma unroll 1
+          for (int ka = 0; ka < KA; ++ka, ++i) {
+            const int st = i % kWStages;
+            mbar_wait(&S.w_full[st], (i / kWStages) & 1);
+            tc_fence_after();
+            if (leader) {
+              umma_katom_3x(tb + 128 + 64 * slot, rg + st * kWChunkBytes, bh + ka * kWAtomBytes, bl + ka * kWAtomBytes, idesc,
+                            ka == 0);
+              umma_commit(&S.w_empty[st]);
+            }
+            __syncwarp();
+          }
+          if (leader) umma_commit(&S.d2_full[slot]);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ===== workers: warp (q, hf) owns TMEM lane quadrant q (features 128 fb + 32 q + lane) of tile rows [32 hf, 32 hf + 32) =====
+    const int q = warp & 3, hf = warp >> 2;
+    const int R0 = rbase + 32 * hf;
+    const uint32_t s_hi = smem_u32(b_hi), s_lo = smem_u32(b_lo);
+    const uint32_t lane_base = tbase + (static_cast<uint32_t>(32 * q) << 16);
+
+    // ---- 1. self-loop operand rows -> shared memory (hi / lo): warp w stages tile rows 8 w .. 8 w + 7 (one 8-row swizzle
+    // group), a lane per float4 channel groups lane and lane + 32; channels >= d and rows >= row1 are zero ----
+    {
+      const TempDenseTerm& tm = p.terms[0];
+      const int rr = rbase + 8 * warp + (lane & 7);
+      const int idx = rr < p.row1 ? (tm.a_index != nullptr ? __ldg(tm.a_index + rr) : rr) : -1;
+      const int nv = D >> 2;
+      const bool oka = lane < nv, okb = lane + 32 < nv;
+      const bool ina = lane < 8 * KA, inb = lane + 32 < 8 * KA;      // inside the padded operand at all
+      pdl_wait();  // everything above (barriers, TMEM, plan indices) overlapped the predecessor
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int sr = __shfl_sync(kFull, idx, i);
+        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sr >= 0) {
+          const float* xr = tm.a + static_cast<size_t>(sr) * D;
+          if (oka) va[i] = ld_dep_f32x4(xr + 4 * lane);
+          if (okb) vb[i] = ld_dep_f32x4(xr + 4 * (lane + 32));
+        }
+      }
+      // float4 group c4: k-atom c4 >> 3, 16-byte chunk (c4 & 7) ^ (row & 7); tile row 8 w + i: swizzle group w, row in group i
+      const uint32_t off_a = static_cast<uint32_t>(lane >> 3) * kWAtomBytes + static_cast<uint32_t>(warp) * 1024u;
+      const uint32_t off_b = off_a + 4u * kWAtomBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = static_cast<uint32_t>(i) * 128u + (static_cast<uint32_t>((lane & 7) ^ i) << 4);
+        float4 hi, lo;
+        if (ina) {
+          split_tf32(va[i].x, hi.x, lo.x);
+          split_tf32(va[i].y, hi.y, lo.y);
+          split_tf32(va[i].z, hi.z, lo.z);
+          split_tf32(va[i].w, hi.w, lo.w);
+          sts_f32x4(s_hi + off_a + off, hi);
+          sts_f32x4(s_lo + off_a + off, lo);
+        }
+        if (inb) {
+          split_tf32(vb[i].x, hi.x, lo.x);
+          split_tf32(vb[i].y, hi.y, lo.y);
+          split_tf32(vb[i].z, hi.z, lo.z);
+          split_tf32(vb[i].w, hi.w, lo.w);
+          sts_f32x4(s_hi + off_b + off, hi);
+          sts_f32x4(s_lo + off_b + off, lo);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&S.b_ready);
+    }
+
+    // ---- 2. bit j of `has`: row R0 + j has in-edges (its aggregate was written by rgcn_gather_wide_kernel) ----
+    unsigned has = 0u;
+    if (p.row_ptr != nullptr) {
+      const int ra = min(R0 + lane, p.row1);
+      has = __ballot_sync(kFull, __ldg(p.row_ptr + min(ra + 1, p.row1)) > __ldg(p.row_ptr + ra));
+    }
+    const bool need_te = (p.te_out | p.te_chain) != 0;
+    int rt = p.row_time_scalar;
+    if (need_te && p.row_time != nullptr) rt = __ldg(p.row_time + min(R0 + lane, p.row1 - 1));
+
+    // ---- 3. epilogue 1: out = act(agg (+x) + x . W_loop + bias) ; h_out ; chain operand X in place ----
+    // the aggregate values of this thread's (feature, 32 rows) for both feature blocks: in flight while the MMAs complete
+    float ag[2][32];
+#pragma unroll
+    for (int fb = 0; fb < 2; ++fb) {
+      const int f = 128 * fb + 32 * q + lane;
+      const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * D + f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ag[fb][j] = (f < D && ((has >> j) & 1u)) ? ld_dep_f32(agg_col + static_cast<size_t>(j) * D) : 0.f;
+    }
+    mbar_wait(&S.d1_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int fb = 0; fb < 2; ++fb) {
+      const int atom = 4 * fb + q;
+      if (fb >= n_fb || atom >= KA) continue;          // warp-uniform: no feature of this warp in the block
+      const int f = 128 * fb + 32 * q + lane;
+      const bool fok = f < D;
+      const float bias = (fok && p.h_bias != nullptr) ? __ldg(p.h_bias + f) : 0.f;
+      float v[32];
+      tmem_ld32(lane_base + 64 * fb + 32 * hf, v);
+      const uint32_t ab = static_cast<uint32_t>(atom) * kWAtomBytes;
+      int cur_trow = -1;
+      float cur_te = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int r = R0 + i;
+        const uint32_t off = ab + sw128_off(static_cast<uint32_t>(32 * hf + i), static_cast<uint32_t>(lane));
+        float te = 0.f;
+        if (need_te) {
+          const int trow = __shfl_sync(kFull, rt, i);  // warp-uniform
+          if (trow != cur_trow) {
+            cur_trow = trow;
+            cur_te = fok ? __ldg(p.time_embed + static_cast<size_t>(trow) * D + f) : 0.f;
+          }
+          te = cur_te;
+        }
+        float val = ag[fb][i];
+        if (p.residual) val += lds_f32(s_hi + off) + lds_f32(s_lo + off);
+        val += v[i];
+        val += bias;
+        if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
+        if (fok && r < p.row1 && p.h_out != nullptr) p.h_out[static_cast<size_t>(r) * D + f] = p.te_out ? val + te : val;
+        if (n_mb > 0) {
+          const float xx = (fok && r < p.row1) ? (p.te_chain ? val + te : val) : 0.f;
+          float hi, lo;
+          split_tf32(xx, hi, lo);
+          sts_f32(s_hi + off, hi);
+          sts_f32(s_lo + off, lo);
+        }
+      }
+    }
+
+    // ---- 4. chain epilogues: chain_out[r, 128 mb + 32 q + lane] = D2 + chain_b ----
+    if (n_mb > 0) {
+      fence_proxy_async();
+      mbar_arrive(&S.x_ready);
+      for (int mb = 0; mb < n_mb; ++mb) {
+        const int slot = mb % 3;
+        const int cf = 128 * mb + 32 * q + lane;
+        const bool cok = cf < p.chain_n;
+        const float cbias = (cok && p.chain_b != nullptr) ? __ldg(p.chain_b + cf) : 0.f;
+        mbar_wait(&S.d2_full[slot], (mb / 3) & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(lane_base + 128 + 64 * slot + 32 * hf, v);
+        float* orow = p.chain_out + static_cast<size_t>(R0) * p.chain_ld + cf;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (cok && R0 + i < p.row1) orow[static_cast<size_t>(i) * p.chain_ld] = v[i] + cbias;
+        }
+        tc_fence_before();
+        mbar_arrive(&S.d2_empty[slot]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tbase, 512);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+bool wide_enabled() {
+  static const char* mode = getenv("TEMP_WIDE_TC");   // TEMP_WIDE_TC=0: these shapes stay on the fp32 SIMT kernels
+  return mode == nullptr || strcmp(mode, "0") != 0;
+}
+
+}  // namespace
+
+namespace temp_internal {
+
+int64_t tcw_packed_bytes(int k, int n) {
+  if (!wide_enabled() || k <= 0 || (k & 3) != 0 || k > 32 * kWMaxAtoms || n <= 0) return -1;
+  const int KA = (k + 31) / 32, n_mb = (n + 127) / 128;
+  return static_cast<int64_t>(n_mb) * KA * kWChunkBytes;
+}
+
+int tcw_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st) {
+  if (w_kn == nullptr || packed == nullptr || tcw_packed_bytes(k, n) <= 0)
+    return fail(TEMP_EINVAL, "temp_pack_weights: k must be a multiple of 4 in [4, 256] and n positive%s", "");
+  const int KA = (k + 31) / 32, n_mb = (n + 127) / 128;
+  const int total = n_mb * KA * 4096;
+  pack_weights_wide_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_kn, k, n, KA, n_mb, static_cast<uint8_t*>(packed));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pack_weights_wide_kernel launch");
+  return TEMP_OK;
+}
+
+// d % 4 == 0, d <= 256, one un-decayed dense term with its packed image, S x S relation blocks with S in {1, 2, 4}
+bool tcw_layer_supported(const TempRgcnLayerArgs* a) {
+  if (!wide_enabled()) return false;
+  if (a->d <= 0 || (a->d & 3) != 0 || a->d > 32 * kWMaxAtoms || a->n_terms != 1) return false;
+  const TempDenseTerm& t = a->terms[0];
+  if (t.w_packed == nullptr || t.a_dt != nullptr) return false;
+  if (a->row_ptr != nullptr) {
+    if (a->si != a->so || (a->si != 1 && a->si != 2 && a->si != 4) || a->agg_scratch == nullptr) return false;
+    if (a->agg_lists != 0 && (a->n_agg_rows < 0 || a->n_agg_heavy < 0 || (a->n_agg_rows > 0 && a->agg_rows == nullptr) ||
+                              (a->n_agg_heavy > 0 && a->agg_heavy == nullptr)))
+      return false;
+  }
+  if (a->chain_w != nullptr && a->chain_w_packed == nullptr) return false;
+  if (a->chain_peers != nullptr) return false;
+  return true;
+}
+
+int tcw_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st) {
+  const int grid = tc_gather_grid(a);
+  if (grid <= 0) return TEMP_OK;
+  cudaError_t e;
+  if (a->si == 1)
+    e = launch_pdl(rgcn_gather_wide_kernel<1>, grid, kGWWarps * 32, 0, st, *a);
+  else if (a->si == 2)
+    e = launch_pdl(rgcn_gather_wide_kernel<2>, grid, kGWWarps * 32, 0, st, *a);
+  else if (a->si == 4)
+    e = launch_pdl(rgcn_gather_wide_kernel<4>, grid, kGWWarps * 32, 0, st, *a);
+  else
+    return fail(TEMP_EUNSUPPORTED, "rgcn_gather_wide_kernel: relation blocks of 1, 2 or 4 channels%s", "");
+  if (e != cudaSuccess) return cuda_fail(e, "rgcn_gather_wide_kernel launch");
+  return TEMP_OK;
+}
+
+int tcw_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
+  const int KA = (a->d + 31) / 32;
+  static int configured = 0;      // largest dynamic shared memory size the kernel has been configured for
+  const int smem = wide_smem_bytes(KA);
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(rgcn_layer_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem_bytes(kWMaxAtoms));
+    if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_tcw_kernel");
+    configured = wide_smem_bytes(kWMaxAtoms);
+  }
+  const int rows = a->row1 - a->row0;
+  if (tc_gather_grid(a) > 0) {
+    if (int rc = tcw_launch_gather(a, st)) return rc;
+  }
+  const int grid = (rows + kWRows - 1) / kWRows;
+  cudaError_t e = launch_pdl(rgcn_layer_tcw_kernel, grid, kWThreads, static_cast<size_t>(smem), st, *a, KA);
+  if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_tcw_kernel launch");
+  return TEMP_OK;
+}
+
+}  // namespace temp_internal

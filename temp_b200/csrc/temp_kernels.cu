@@ -1482,9 +1482,10 @@ int temp_gru_fwd(const TempGruArgs* args, void* stream) { return launch_gru(args
 
 int temp_rgcn_gather_fwd(const TempRgcnLayerArgs* args, void* stream) {
   if (args == nullptr) return fail(TEMP_EINVAL, "null args%s", "");
-  if (args->d != 128 || args->row_ptr == nullptr || args->si != 1 || args->so != 1 || args->agg_scratch == nullptr ||
+  if (args->d <= 0 || (args->d & 3) != 0 || args->d > 256 || args->row_ptr == nullptr || args->si != args->so ||
+      (args->si != 1 && args->si != 2 && args->si != 4) || args->n_bases * args->si != args->d || args->agg_scratch == nullptr ||
       args->x == nullptr || args->weight == nullptr || args->norm == nullptr || args->e_src == nullptr || args->e_rel == nullptr)
-    return fail(TEMP_EUNSUPPORTED, "temp_rgcn_gather_fwd: d == 128, 1x1 relation blocks and an aggregate buffer are required%s", "");
+    return fail(TEMP_EUNSUPPORTED, "temp_rgcn_gather_fwd: d %% 4 == 0, d <= 256, 1x1 / 2x2 / 4x4 relation blocks and an aggregate buffer are required%s", "");
   return temp_internal::tc_launch_gather(args, static_cast<cudaStream_t>(stream));
 }
 
@@ -1526,7 +1527,7 @@ int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int3
 }
 
 int64_t temp_packed_weights_bytes(int32_t k, int32_t n) {
-  if (k != 128 || n <= 0 || (n & 127)) return -1;
+  if (k != 128 || n <= 0 || (n & 127)) return temp_internal::tcw_packed_bytes(k, n);
   return static_cast<int64_t>(n / 128) * 4 * 2 * 128 * 128;
 }
 

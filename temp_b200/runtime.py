@@ -79,8 +79,9 @@ class PreparedWeights(object):
         return hit[1]
 
     def packed(self, name: str, w_kn: torch.Tensor, src: List[torch.Tensor]) -> Optional[torch.Tensor]:
-        """tcgen05 operand image of a [128, n] row-major matrix (temp_pack_weights), None when the shape has no
-        tensor-core path (the launch then runs on the fp32 SIMT kernels)."""
+        """tcgen05 operand image of a [k, n] row-major matrix (temp_pack_weights; k = 128 for the 128-row tile kernel, any
+        k % 4 == 0 up to 256 for the 64-row one), None when the shape has no tensor-core path (the launch then runs on
+        the fp32 SIMT kernels)."""
         k, n = int(w_kn.shape[0]), int(w_kn.shape[1])
         nbytes = lib.load().temp_packed_weights_bytes(k, n)
         if nbytes <= 0:
@@ -159,7 +160,7 @@ class EncoderRuntime(object):
         self._agg_rows = 1
         self._live = []
         self._staged = {}
-        # tcgen05 path where the shapes allow it (d == 128); False: fp32 SIMT kernels only.  The 3xTF32 tensor-core GEMMs
+        # tcgen05 path where the shapes allow it (layers: d % 4 == 0, d <= 256; tensor-memory scan: d == 128); False: fp32 SIMT kernels only.  The 3xTF32 tensor-core GEMMs
         # are ~5x noisier than fp32 FFMA arithmetic (7.6e-7 against 1.8e-7 relative to an fp64 evaluation on the bench
         # shape).  That is irrelevant for the torch GRU / linear cells, but the --type1 cell is torch.randn-initialised
         # (models/GRU_cell.py:12-15): pre-activations of magnitude ~10 make its recurrence ill-conditioned (fp32 itself is
@@ -210,7 +211,7 @@ class EncoderRuntime(object):
             a.x = x.data_ptr()
             a.weight = layer.weight.data_ptr()
             a.n_bases, a.si, a.so = layer.num_bases, layer.submat_in, layer.submat_out
-            if self.use_tc and m.embed_size == 128:
+            if self.use_tc and lib.load().temp_packed_weights_bytes(m.embed_size, m.embed_size) > 0:
                 agg = self.ws.get("agg", self._agg_rows * m.embed_size)
                 self._live.append(agg)               # programs hold raw pointers: keep the buffer they were built on
                 a.agg_scratch = agg.data_ptr()
@@ -252,7 +253,7 @@ class EncoderRuntime(object):
     def _term(self, a, w, index=None, dt=None, decay_wb=None):
         t = lib.DenseTerm()
         t.a, t.w = a.data_ptr(), w.data_ptr()
-        if self.use_tc and dt is None and tuple(w.shape) == (128, 128):
+        if self.use_tc and dt is None and int(w.shape[0]) == int(w.shape[1]):
             pk = self.prep.packed("term.%d" % w.data_ptr(), w, [w])
             if pk is not None:
                 t.w_packed = pk.data_ptr()
