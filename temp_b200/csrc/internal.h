@@ -32,6 +32,14 @@ int tcw_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st);
 int tcw_launch_gather(const TempRgcnLayerArgs* a, cudaStream_t st);
 int64_t tcw_packed_bytes(int k, int n);
 int tcw_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t st);
+// gru_step_tcw_kernel: one GRU step per launch (64 rows x 32 hidden columns per CTA) for the widths the chain-partitioned
+// 128-wide scans do not take; a scan of such steps is a chain of programmatic dependent launches
+int64_t tcw_packed_gru_bytes(int d);
+int tcw_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st);
+bool tcw_gru_supported(const TempGruArgs* g);
+int tcw_launch_gru(const TempGruArgs* g, cudaStream_t st);
+bool tcw_scan_supported(const TempGruScanArgs* a);
+int tcw_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
 int tc_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st);
 
 }  // namespace temp_internal

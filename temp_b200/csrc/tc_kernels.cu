@@ -1232,7 +1232,8 @@ int tc_pack_weights(const float* w_kn, int k, int n, void* packed, cudaStream_t 
 }
 
 int tc_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st) {
-  if (whh_t == nullptr || packed == nullptr || d != kD) return fail(TEMP_EINVAL, "temp_pack_gru_weights: d must be 128%s", "");
+  if (d != kD) return tcw_pack_gru_weights(whh_t, d, packed, st);
+  if (whh_t == nullptr || packed == nullptr) return fail(TEMP_EINVAL, "temp_pack_gru_weights: null pointers%s", "");
   pack_gru_kernel<<<(4 * kD * 128 + 255) / 256, 256, 0, st>>>(whh_t, static_cast<uint8_t*>(packed));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pack_gru_kernel launch");

@@ -491,6 +491,240 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
   if (warp == 9) tmem_dealloc(tbase, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// GRU step, tcgen05, 64-row tiles x 32 hidden columns
+// ------------------------------------------------------------------------------------------------
+// whh_t [d, 3 d] row-major (= weight_hh transposed).  Block cb of 32 hidden columns: KA chunks of 32 KB at (cb * KA + ka);
+// feature row m = 32 * gate + jj  <->  column gate * d + 32 * cb + jj (the layout of pack_gru_kernel: the r | z | n
+// pre-activations of one hidden column sit on the same lane of TMEM lane quadrants 0, 1, 2); rows 96..127, hidden columns
+// >= d and k >= d are zero.
+__global__ void pack_gru_wide_kernel(const float* __restrict__ whh_t, int d, int KA, int CB, uint8_t* __restrict__ out) {
+  const int total = CB * KA * 4096;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int chunk = idx >> 12, rem = idx & 4095;
+    const int kk = rem >> 7, m = rem & 127;
+    const int cb = chunk / KA, ka = chunk - cb * KA;
+    const int k = 32 * ka + kk, gate = m >> 5, j = 32 * cb + (m & 31);
+    const float v = (gate < 3 && k < d && j < d) ? whh_t[static_cast<size_t>(k) * (3 * d) + gate * d + j] : 0.f;
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    uint8_t* dst = out + static_cast<size_t>(chunk) * kWChunkBytes;
+    const uint32_t off = sw128_off(m, kk);
+    *reinterpret_cast<float*>(dst + off) = hi;
+    *reinterpret_cast<float*>(dst + 128 * 128 + off) = lo;
+  }
+}
+
+struct GruWBars {
+  uint64_t w_full[kWStages], w_empty[kWStages];
+  uint64_t b_ready, d_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float decay_factor_w(float dt, const float* wb, float inv_temperature) {
+  if (wb != nullptr) return expf(-fmaxf(fmaf(__ldg(wb), dt, __ldg(wb + 1)), 0.f));
+  return expf(-dt * inv_temperature);
+}
+__device__ __forceinline__ float sigmoid_w(float x) { return 1.f / (1.f + expf(-x)); }
+
+// One GRU step (models/RRGCN.py:77-89, torch.nn.GRU equations) for packed rows [row0, row1): CTA (tile, cb) = 64 rows x the
+// 32 hidden columns [32 cb, 32 cb + 32).
+//   h0 = state[prev_row[r]] (zero row when prev_row[r] < 0)  ->  hi / lo operand in shared memory;
+//   gh^T[r|z|n of the 32 columns, row] = W_hh slice . h0^T on the tensor pipe (KA k-atoms x 12 MMAs, weight chunks streamed
+//   by the TMA warp); the decay is a per-row scalar and is applied after the MMA (W . (c h) = c (W . h));
+//   the three gate quadrants of the accumulator are parked in shared memory, then thread (warp w, lane) computes the gates
+//   of rows 8 w .. 8 w + 7 at hidden column 32 cb + lane (gi / out accesses: 128-byte lines) and stores state (+ te).
+// Steps of a window are separate launches chained by programmatic dependent launch: barriers, TMEM, the first weight
+// chunks and the plan's prev_row are set up while the previous step still runs.
+__global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGruArgs p, const int KA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + KA * kWAtomBytes;
+  uint8_t* ring = smem + 2 * KA * kWAtomBytes;
+  __shared__ GruWBars S;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(kFull, tid >> 5, 0);
+  const int D = p.d;
+  const int rbase = p.row0 + blockIdx.x * kWRows;
+  const int cb = blockIdx.y;
+  const bool rec = p.prev_row != nullptr;          // (launch-uniform) false: no row of the step has a previous state
+  pdl_launch_dependents();
+
+  if (tid == 0) {
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&S.w_full[i], 1);
+      mbar_init(&S.w_empty[i], 1);
+    }
+    mbar_init(&S.b_ready, kWWorkers);
+    mbar_init(&S.d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&S.tmem_base, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = S.tmem_base;
+
+  if (warp_u >= kWWorkerWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (rec && warp == 8 && lane == 0) {
+      const uint8_t* w = static_cast<const uint8_t*>(p.whh_packed) + static_cast<size_t>(cb) * KA * kWChunkBytes;
+      for (int i = 0; i < KA; ++i) {
+        const int st = i % kWStages;
+        if (i >= kWStages) mbar_wait(&S.w_empty[st], ((i / kWStages) - 1) & 1);
+        mbar_expect_tx(&S.w_full[st], kWChunkBytes);
+        bulk_g2s(ring + st * kWChunkBytes, w + static_cast<size_t>(i) * kWChunkBytes, kWChunkBytes, &S.w_full[st]);
+      }
+    } else if (rec && warp_u == 9) {
+      const bool leader = elect_one();
+      const uint32_t tb = __shfl_sync(kFull, S.tmem_base, 0);
+      const uint32_t idesc = umma_idesc_tf32(128, kWRows);
+      const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo), rg = smem_u32(ring);
+      mbar_wait(&S.b_ready, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ka = 0; ka < KA; ++ka) {
+        const int st = ka % kWStages;
+        mbar_wait(&S.w_full[st], (ka / kWStages) & 1);
+        tc_fence_after();
+        if (leader) {
+          umma_katom_3x(tb, rg + st * kWChunkBytes, bh + ka * kWAtomBytes, bl + ka * kWAtomBytes, idesc, ka == 0);
+          umma_commit(&S.w_empty[st]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(&S.d_full);
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int q = warp & 3, hf = warp >> 2;
+    const uint32_t s_hi = smem_u32(b_hi), s_lo = smem_u32(b_lo);
+    // lanes 0..7: previous-state row and time gap of tile row 8 w + lane (plan data: fetched before the dependency point)
+    const int rr = rbase + 8 * warp + (lane & 7);
+    int pr = -1;
+    float dt = 0.f;
+    if (rec && rr < p.row1) {
+      pr = __ldg(p.prev_row + rr);
+      if (p.dt != nullptr) dt = __ldg(p.dt + rr);
+    }
+    const int j = 32 * cb + lane;
+    const bool jok = j < D;
+    const float br = jok ? __ldg(p.b_hh + j) : 0.f, bz = jok ? __ldg(p.b_hh + D + j) : 0.f, bn = jok ? __ldg(p.b_hh + 2 * D + j) : 0.f;
+    int trow = p.row_time_scalar;
+    if (p.time_embed != nullptr && p.row_time != nullptr) trow = __ldg(p.row_time + min(rr, p.row1 - 1));
+    pdl_wait();   // gi, the previous state and (accumulate) out come from the predecessor kernels
+
+    // ---- 1. previous-state rows -> hi / lo operand (warp w: tile rows 8 w .. 8 w + 7, lanes = float4 groups lane, lane + 32) ----
+    if (rec) {
+      const int nv = D >> 2;
+      const bool oka = lane < nv, okb = lane + 32 < nv;
+      const bool ina = lane < 8 * KA, inb = lane + 32 < 8 * KA;
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int sr = __shfl_sync(kFull, pr, i);
+        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sr >= 0) {
+          const float* xr = p.state + static_cast<size_t>(sr) * D;
+          if (oka) va[i] = ld_dep_f32x4(xr + 4 * lane);
+          if (okb) vb[i] = ld_dep_f32x4(xr + 4 * (lane + 32));
+        }
+      }
+      const uint32_t off_a = static_cast<uint32_t>(lane >> 3) * kWAtomBytes + static_cast<uint32_t>(warp) * 1024u;
+      const uint32_t off_b = off_a + 4u * kWAtomBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = static_cast<uint32_t>(i) * 128u + (static_cast<uint32_t>((lane & 7) ^ i) << 4);
+        float4 hi, lo;
+        if (ina) {
+          split_tf32(va[i].x, hi.x, lo.x);
+          split_tf32(va[i].y, hi.y, lo.y);
+          split_tf32(va[i].z, hi.z, lo.z);
+          split_tf32(va[i].w, hi.w, lo.w);
+          sts_f32x4(s_hi + off_a + off, hi);
+          sts_f32x4(s_lo + off_a + off, lo);
+        }
+        if (inb) {
+          split_tf32(vb[i].x, hi.x, lo.x);
+          split_tf32(vb[i].y, hi.y, lo.y);
+          split_tf32(vb[i].z, hi.z, lo.z);
+          split_tf32(vb[i].w, hi.w, lo.w);
+          sts_f32x4(s_hi + off_b + off, hi);
+          sts_f32x4(s_lo + off_b + off, lo);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&S.b_ready);
+    }
+
+    // ---- 2. what the gates need besides gh: input gates, time embedding, accumulate target: in flight during the MMAs ----
+    float gir[8], giz[8], gin[8], tev[8], old[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rbase + 8 * warp + i;
+      gir[i] = giz[i] = gin[i] = tev[i] = old[i] = 0.f;
+      const int tr_i = __shfl_sync(kFull, trow, i);          // (lane i holds tile row 8 w + i)
+      if (jok && r < p.row1) {
+        const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
+        gir[i] = ld_dep_f32(gi);
+        giz[i] = ld_dep_f32(gi + D);
+        gin[i] = ld_dep_f32(gi + 2 * D);
+        if (p.time_embed != nullptr) tev[i] = __ldg(p.time_embed + static_cast<size_t>(tr_i) * D + j);
+        if (p.accumulate) old[i] = ld_dep_f32(p.out + static_cast<size_t>(r) * D + j);
+      }
+    }
+
+    // ---- 3. accumulator quadrants r | z | n -> exchange rows [gate][tile row][32] in the (now idle) weight ring ----
+    const uint32_t ex = smem_u32(ring);
+    if (rec) {
+      mbar_wait(&S.d_full, 0);
+      tc_fence_after();
+      if (q < 3) {
+        float v[32];
+        tmem_ld32(tbase + (static_cast<uint32_t>(32 * q) << 16) + 32 * hf, v);
+        const uint32_t exw = ex + static_cast<uint32_t>(q * kWRows + 32 * hf) * 128u + lane * 4u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sts_f32(exw + i * 128u, v[i]);
+      }
+      tc_fence_before();
+      bar_named(1, kWWorkers);
+    }
+
+    // ---- 4. gates (torch.nn.GRU, gate order r, z, n: SURVEY Appendix A.3), state store ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = 8 * warp + i, r = rbase + m;
+      const int pri = __shfl_sync(kFull, pr, i);
+      const float dti = __shfl_sync(kFull, dt, i);
+      if (!jok || r >= p.row1) continue;
+      float hr = br, hz = bz, hn = bn, hp = 0.f;
+      if (pri >= 0) {
+        const float dec = p.dt != nullptr ? decay_factor_w(dti, p.decay_wb, p.inv_temperature) : 1.f;
+        const uint32_t ea = ex + static_cast<uint32_t>(m) * 128u + lane * 4u;
+        hr = fmaf(dec, lds_f32(ea), hr);
+        hz = fmaf(dec, lds_f32(ea + kWRows * 128u), hz);
+        hn = fmaf(dec, lds_f32(ea + 2u * kWRows * 128u), hn);
+        const uint32_t off = static_cast<uint32_t>(cb) * kWAtomBytes + sw128_off(static_cast<uint32_t>(m), static_cast<uint32_t>(lane));
+        hp = dec * (lds_f32(s_hi + off) + lds_f32(s_lo + off));     // hi + lo is the fp32 value exactly
+      }
+      const float rg = sigmoid_w(gir[i] + hr), zg = sigmoid_w(giz[i] + hz);
+      const float ng = tanhf(gin[i] + rg * hn);
+      float hy = (1.f - zg) * ng + zg * hp;
+      hy += tev[i];
+      p.out[static_cast<size_t>(r) * D + j] = p.accumulate ? old[i] + hy : hy;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tbase, 64);
+}
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -582,6 +816,72 @@ int tcw_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
   const int grid = (rows + kWRows - 1) / kWRows;
   cudaError_t e = launch_pdl(rgcn_layer_tcw_kernel, grid, kWThreads, static_cast<size_t>(smem), st, *a, KA);
   if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_tcw_kernel launch");
+  return TEMP_OK;
+}
+
+int64_t tcw_packed_gru_bytes(int d) {
+  if (!wide_enabled() || d <= 0 || (d & 3) != 0 || d > 32 * kWMaxAtoms) return -1;
+  const int KA = (d + 31) / 32;
+  return static_cast<int64_t>(KA) * KA * kWChunkBytes;     // ceil(d / 32) column blocks x KA k-atoms
+}
+
+int tcw_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st) {
+  if (whh_t == nullptr || packed == nullptr || tcw_packed_gru_bytes(d) <= 0)
+    return fail(TEMP_EINVAL, "temp_pack_gru_weights: d must be a multiple of 4 in [4, 256]%s", "");
+  const int KA = (d + 31) / 32;
+  const int total = KA * KA * 4096;
+  pack_gru_wide_kernel<<<(total + 255) / 256, 256, 0, st>>>(whh_t, d, KA, KA, static_cast<uint8_t*>(packed));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pack_gru_wide_kernel launch");
+  return TEMP_OK;
+}
+
+// torch GRU cell, d % 4 == 0, d <= 256, the packed W_hh image when the step reads a previous state
+bool tcw_gru_supported(const TempGruArgs* g) {
+  if (!wide_enabled()) return false;
+  if (g->d <= 0 || (g->d & 3) != 0 || g->d > 32 * kWMaxAtoms || g->cell_type != TEMP_CELL_TORCH_GRU) return false;
+  if (g->prev_row != nullptr && (g->whh_packed == nullptr || g->state == nullptr)) return false;
+  if (g->push != 0) return false;
+  return g->gi != nullptr && g->b_hh != nullptr && g->out != nullptr;
+}
+
+int tcw_launch_gru(const TempGruArgs* g, cudaStream_t st) {
+  const int rows = g->row1 - g->row0;
+  if (rows <= 0) return TEMP_OK;
+  const int KA = (g->d + 31) / 32;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gru_step_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem_bytes(kWMaxAtoms));
+    if (e != cudaSuccess) return cuda_fail(e, "gru_step_tcw_kernel");
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((rows + kWRows - 1) / kWRows, KA);
+  cfg.blockDim = dim3(kWThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(wide_smem_bytes(KA));
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_step_tcw_kernel, *g, KA);
+  if (e != cudaSuccess) return cuda_fail(e, "gru_step_tcw_kernel launch");
+  return TEMP_OK;
+}
+
+// every step of the scan as its own gru_step_tcw_kernel launch (chained by programmatic dependent launch)
+bool tcw_scan_supported(const TempGruScanArgs* a) {
+  if (a->n_steps <= 0 || a->push_bufs != nullptr || a->push_multicast != nullptr) return false;
+  for (int s = 0; s < a->n_steps; ++s)
+    if (!tcw_gru_supported(&a->steps[s])) return false;
+  return true;
+}
+
+int tcw_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
+  for (int s = 0; s < a->n_steps; ++s)
+    if (int rc = tcw_launch_gru(&a->steps[s], st)) return rc;
   return TEMP_OK;
 }
 

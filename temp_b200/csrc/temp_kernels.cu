@@ -1276,6 +1276,7 @@ int launch_gru(const TempGruArgs* a, cudaStream_t st) {
     one.steps[0] = *a;
     if (temp_internal::tc_scan_supported(&one)) return temp_internal::tc_launch_scan(&one, st);
   }
+  if (a->d != 128 && temp_internal::tcw_gru_supported(a)) return temp_internal::tcw_launch_gru(a, st);
   const int jblocks = (a->d + kGJ - 1) / kGJ;
   cudaError_t e;
   // small steps: 32-row tiles so that the step still spreads over all SMs
@@ -1348,6 +1349,7 @@ int launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   }
   if (max_rows == 0) return TEMP_OK;
   if (temp_internal::tc_scan_supported(a)) return temp_internal::tc_launch_scan(a, st);
+  if (a->steps[0].d != 128 && temp_internal::tcw_scan_supported(a)) return temp_internal::tcw_launch_scan(a, st);
   if (a->push_bufs != nullptr) return fail(TEMP_EUNSUPPORTED, "the fused peer all-gather needs the tcgen05 scan (d == 128, partition table)%s", "");
   if (a->barrier == nullptr) return fail(TEMP_EINVAL, "scan needs a zero-initialised 8-byte barrier word%s", "");
   if (max_rows <= sm_count_cached() * 64) return launch_scan_t<4, 3>(a, max_rows, st);
@@ -1535,7 +1537,9 @@ int temp_pack_weights(const float* w_kn, int32_t k, int32_t n, void* packed, voi
   return temp_internal::tc_pack_weights(w_kn, k, n, packed, static_cast<cudaStream_t>(stream));
 }
 
-int64_t temp_packed_gru_bytes(int32_t d) { return d == 128 ? static_cast<int64_t>(4) * 4 * 2 * 128 * 128 : -1; }
+int64_t temp_packed_gru_bytes(int32_t d) {
+  return d == 128 ? static_cast<int64_t>(4) * 4 * 2 * 128 * 128 : temp_internal::tcw_packed_gru_bytes(d);
+}
 
 int temp_pack_gru_weights(const float* whh_t, int32_t d, void* packed, void* stream) {
   return temp_internal::tc_pack_gru_weights(whh_t, d, packed, static_cast<cudaStream_t>(stream));
@@ -1553,7 +1557,16 @@ int temp_program_kernel_count(const TempOp* ops, int32_t n) {
         break;
       }
       case TEMP_OP_GRU: k += ops[i].u.gru.row1 > ops[i].u.gru.row0 ? 1 : 0; break;
-      case TEMP_OP_GRU_SCAN: k += ops[i].u.scan.n_steps > 0 ? 1 : 0; break;
+      case TEMP_OP_GRU_SCAN: {
+        const TempGruScanArgs& sc = ops[i].u.scan;
+        if (sc.n_steps > 0 && sc.n_steps <= TEMP_MAX_SCAN_STEPS && sc.steps[0].d != 128 && !temp_internal::tc_scan_supported(&sc) &&
+            temp_internal::tcw_scan_supported(&sc)) {   // one gru_step_tcw_kernel launch per non-empty step
+          for (int s = 0; s < sc.n_steps; ++s) k += sc.steps[s].row1 > sc.steps[s].row0 ? 1 : 0;
+        } else {
+          k += sc.n_steps > 0 ? 1 : 0;
+        }
+        break;
+      }
       case TEMP_OP_ATTN: k += ops[i].u.attn.row1 > ops[i].u.attn.row0 ? 1 : 0; break;
       case TEMP_OP_GATHER: k += ops[i].u.gather.n > 0 ? 1 : 0; break;
       case TEMP_OP_SCATTER: k += ops[i].u.scatter.n > 0 ? 1 : 0; break;

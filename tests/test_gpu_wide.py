@@ -24,13 +24,14 @@ def _log(rec):
         pass
 
 
-def _problem(D, S, R, row0, chain_n, seed, heavy_at=8, max_deg=40, n_rel=12, T=5, n_src=None):
+def _problem(D, S, R, row0, chain_n, seed, heavy_at=8, max_deg=40, n_rel=12, T=5, n_src=None, n_heavy=3):
     """Random packed rows [0, R) with a CSR by destination; the launch covers [row0, R)."""
     g = np.random.default_rng(seed)
     n_src = n_src or R
     deg = g.integers(0, 7, size=R)
     deg[g.random(R) < 0.3] = 0
-    deg[g.integers(0, R, size=3)] = g.integers(heavy_at, max_deg, size=3)          # a few high in-degree rows
+    if n_heavy:
+        deg[g.integers(0, R, size=n_heavy)] = g.integers(heavy_at, max_deg, size=n_heavy)      # a few high in-degree rows
     deg[:row0] = 0
     row_ptr = np.zeros(R + 1, np.int32)
     row_ptr[1:] = np.cumsum(deg)
@@ -43,12 +44,12 @@ def _problem(D, S, R, row0, chain_n, seed, heavy_at=8, max_deg=40, n_rel=12, T=5
     light = rows[has & (deg < heavy_at)]
     heavy = rows[has & (deg >= heavy_at)]
     lists = {k: np.stack([v, row_ptr[v], row_ptr[v + 1]], 1).astype(np.int32).reshape(-1, 3) for k, v in (("rows", light), ("heavy", heavy))}
-    f = lambda *s: (g.standard_normal(s) * 0.5).astype(np.float32)
+    f = lambda *s, scale=0.5: (g.standard_normal(s) * scale).astype(np.float32)
     p = dict(D=D, S=S, R=R, row0=row0, chain_n=chain_n, row_ptr=row_ptr, e_src=e_src, e_rel=e_rel, norm=norm, lists=lists,
-             x=f(n_src, D), weight=f(n_rel, D * S), loop_w=f(D, D) * (1.0 / np.sqrt(D)), bias=f(D), te=f(T, D),
+             x=f(n_src, D), weight=f(n_rel, D * S), loop_w=f(D, D, scale=0.5 / np.sqrt(D)), bias=f(D), te=f(T, D),
              row_time=np.sort(g.integers(0, T, size=R)).astype(np.int32), a_index=g.permutation(n_src)[:R].astype(np.int32) if n_src != R else None)
     if chain_n:
-        p["chain_w"] = f(D, chain_n) * (1.0 / np.sqrt(D))
+        p["chain_w"] = f(D, chain_n, scale=0.5 / np.sqrt(D))
         p["chain_b"] = f(chain_n)
     return p
 
@@ -189,7 +190,7 @@ def test_wide_gather_entry_is_bit_identical_to_the_simt_aggregation():
     """temp_rgcn_gather_fwd at d = 200 / 2x2 blocks: the same arithmetic in the same order as rgcn_layer_kernel's
     aggregation -- with zero self-loop weights, zero bias and no activation the SIMT layer's output IS its aggregate."""
     from temp_b200 import lib
-    p = _problem(200, 2, 190, 0, 0, seed=11, heavy_at=1000)          # no heavy rows: one warp per row, edge order
+    p = _problem(200, 2, 190, 0, 0, seed=11, heavy_at=1000, n_heavy=0)          # no heavy rows: one warp per row, edge order
     p["loop_w"] = np.zeros_like(p["loop_w"])
     p["bias"] = np.zeros_like(p["bias"])
     simt, _ = _run(p, False, False, False, False, packed=False)
@@ -204,4 +205,80 @@ def test_wide_gather_entry_is_bit_identical_to_the_simt_aggregation():
     a.agg_scratch, a.agg_lists, a.agg_rows, a.n_agg_rows = agg.data_ptr(), 1, rows.data_ptr(), int(rows.shape[0])
     lib.check(L.temp_rgcn_gather_fwd(C.byref(a), C.c_void_p(lib.current_stream())), "temp_rgcn_gather_fwd")
     torch.cuda.synchronize()
-    assert np.array_equal(agg.cpu().numpy(), simt)
+    got = agg.cpu().numpy()
+    _log({"gather_entry_bit_identical_to_simt": bool(np.array_equal(got, simt)), "err": _err(got, simt.astype(np.float64))})
+    assert np.array_equal(got, simt)
+
+
+def _gru_case(D, R, row0, seed, rec=True, accumulate=False, dt=True):
+    g = np.random.default_rng(seed)
+    f = lambda *s, scale=0.5: (g.standard_normal(s) * scale).astype(np.float32)
+    n_prev = R + 17
+    prev = g.integers(0, n_prev, size=R).astype(np.int32)
+    prev[g.random(R) < 0.3] = -1
+    return dict(D=D, R=R, row0=row0, gi=f(R, 3 * D + 8), state=f(n_prev, D), prev=prev if rec else None,
+                dt=(g.integers(1, 5, size=R).astype(np.float32) if dt else None), whh_t=f(D, 3 * D, scale=1.0 / np.sqrt(D)),
+                b_hh=f(3 * D), te=f(4, D), row_time=np.sort(g.integers(0, 4, size=R)).astype(np.int32),
+                out0=f(R, D), accumulate=accumulate)
+
+
+def _gru_reference(c):
+    D, R = c["D"], c["R"]
+    gi = c["gi"].astype(np.float64)[:, 4:4 + 3 * D]
+    h0 = np.zeros((R, D))
+    if c["prev"] is not None:
+        ok = c["prev"] >= 0
+        h0[ok] = c["state"].astype(np.float64)[c["prev"][ok]]
+        if c["dt"] is not None:
+            h0 *= np.exp(-c["dt"].astype(np.float64) * 0.1)[:, None]
+    gh = h0 @ c["whh_t"].astype(np.float64) + c["b_hh"].astype(np.float64)
+    sg = lambda x: 1.0 / (1.0 + np.exp(-x))
+    r, z = sg(gi[:, :D] + gh[:, :D]), sg(gi[:, D:2 * D] + gh[:, D:2 * D])
+    n = np.tanh(gi[:, 2 * D:] + r * gh[:, 2 * D:])
+    hy = (1 - z) * n + z * h0 + c["te"].astype(np.float64)[c["row_time"]]
+    return c["out0"].astype(np.float64) + hy if c["accumulate"] else hy
+
+
+def _gru_run(c, packed):
+    from temp_b200 import lib
+    L = lib.load()
+    D, R = c["D"], c["R"]
+    t = {k: torch.from_numpy(v).cuda() for k, v in c.items() if isinstance(v, np.ndarray)}
+    out = t["out0"].clone()
+    a = lib.GruArgs()
+    a.row0, a.row1, a.d = c["row0"], R, D
+    a.gi, a.gi_ld, a.gi_off = t["gi"].data_ptr(), 3 * D + 8, 4
+    if c["prev"] is not None:
+        a.state, a.prev_row = t["state"].data_ptr(), t["prev"].data_ptr()
+        if c["dt"] is not None:
+            a.dt = t["dt"].data_ptr()
+    a.inv_temperature = 0.1
+    a.whh_t, a.b_hh = t["whh_t"].data_ptr(), t["b_hh"].data_ptr()
+    if packed:
+        nb = L.temp_packed_gru_bytes(D)
+        assert nb > 0
+        buf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        lib.check(L.temp_pack_gru_weights(C.c_void_p(t["whh_t"].data_ptr()), D, C.c_void_p(buf.data_ptr()), C.c_void_p(lib.current_stream())), "pack gru")
+        a.whh_packed = buf.data_ptr()
+    a.cell_type = lib.CELL_TORCH_GRU
+    a.time_embed, a.row_time = t["te"].data_ptr(), t["row_time"].data_ptr()
+    a.accumulate, a.out, a.out_index_is_row = int(c["accumulate"]), out.data_ptr(), 1
+    lib.check(L.temp_gru_fwd(C.byref(a), C.c_void_p(lib.current_stream())), "temp_gru_fwd")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("D,R,row0", [(200, 333, 37), (200, 64, 0), (32, 100, 3), (160, 70, 0), (256, 129, 1), (100, 90, 0)])
+def test_wide_gru_step_matches_fp64_and_the_simt_kernel(D, R, row0):
+    """temp_gru_fwd at d != 128: gru_step_tcw_kernel (packed W_hh image given) and the fp32 SIMT gru_kernel against an fp64
+    statement of the torch.nn.GRU step (models/RRGCN.py:77-89)."""
+    for kw in (dict(), dict(accumulate=True, dt=False), dict(rec=False)):
+        c = _gru_case(D, R, row0, seed=50 + D + R, **kw)
+        want = _gru_reference(c)
+        errs = {}
+        for packed in (True, False):
+            got = _gru_run(c, packed)
+            assert np.array_equal(got[:row0], c["out0"][:row0]), "rows below row0 were written"
+            errs["tc" if packed else "simt"] = _err(got[row0:], want[row0:])
+        _log({"gru": [D, R, row0], "case": {k: str(v) for k, v in kw.items()}, **errs})
+        assert errs["tc"] < 1e-5 and errs["simt"] < 1e-5, errs
