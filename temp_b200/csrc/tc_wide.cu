@@ -254,7 +254,16 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
   const int D = p.d;
   const int rbase = p.row0 + blockIdx.x * kWRows;
   const int n_fb = (D + 127) >> 7;
-  const int n_mb = p.chain_w_packed != nullptr ? (p.chain_n + 127) >> 7 : 0;
+  // Chain feature blocks (128 output columns each) of THIS CTA: launches with few row tiles spread them over grid.y (every
+  // y block rebuilds the tile's layer output, then takes blocks y, y + gridDim.y, ...; block y == 0 stores h_out).  The
+  // blocks are independent of each other, so every CTA walks its list from a different start (rotated by the tile index):
+  // CTAs that run in lock-step then stream DIFFERENT weight chunks instead of all hitting the same L2 lines at once.
+  const int n_mb_all = p.chain_w_packed != nullptr ? (p.chain_n + 127) >> 7 : 0;
+  const int gy = gridDim.y, by = blockIdx.y;
+  const int n_mb = n_mb_all > by ? (n_mb_all - by + gy - 1) / gy : 0;
+  const int rot = n_mb > 0 ? static_cast<int>(blockIdx.x % n_mb) : 0;
+  auto chain_block = [&](int k) -> int { int kk = k + rot; if (kk >= n_mb) kk -= n_mb; return by + kk * gy; };
+  const int fb_rot = static_cast<int>(blockIdx.x) & (n_fb - 1);      // (n_fb is 1 or 2) same idea for the self-loop blocks
   pdl_launch_dependents();
 
   if (tid == 0) {
@@ -287,7 +296,14 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
       for (int i = 0; i < total; ++i) {
         const int st = i % kWStages;
         if (i >= kWStages) mbar_wait(&S.w_empty[st], ((i / kWStages) - 1) & 1);
-        const uint8_t* src = i < n1 ? w1 + static_cast<size_t>(i) * kWChunkBytes : wc + static_cast<size_t>(i - n1) * kWChunkBytes;
+        const uint8_t* src;
+        if (i < n1) {
+          const int fb = (i / KA) ^ fb_rot, ka = i % KA;
+          src = w1 + static_cast<size_t>(fb * KA + ka) * kWChunkBytes;
+        } else {
+          const int k = (i - n1) / KA, ka = (i - n1) % KA;
+          src = wc + static_cast<size_t>(chain_block(k) * KA + ka) * kWChunkBytes;
+        }
         mbar_expect_tx(&S.w_full[st], kWChunkBytes);
         bulk_g2s(ring + st * kWChunkBytes, src, kWChunkBytes, &S.w_full[st]);
       }
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
           mbar_wait(&S.w_full[st], (i / kWStages) & 1);
           tc_fence_after();
           if (leader) {
-            umma_katom_3x(tb + 64 * fb, rg + st * kWChunkBytes, bh + ka * kWAtomBytes, bl + ka * kWAtomBytes, idesc, ka == 0);
+            umma_katom_3x(tb + 64 * (fb ^ fb_rot), rg + st * kWChunkBytes, bh + ka * kWAtomBytes, bl + ka * kWAtomBytes, idesc, ka == 0);
             umma_commit(&S.w_empty[st]);
           }
           __syncwarp();
@@ -451,7 +467,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
         val += v[i];
         val += bias;
         if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
-        if (fok && r < p.row1 && p.h_out != nullptr) p.h_out[static_cast<size_t>(r) * D + f] = p.te_out ? val + te : val;
+        if (fok && r < p.row1 && p.h_out != nullptr && by == 0) p.h_out[static_cast<size_t>(r) * D + f] = p.te_out ? val + te : val;
         if (n_mb > 0) {
           const float xx = (fok && r < p.row1) ? (p.te_chain ? val + te : val) : 0.f;
           float hi, lo;
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
       mbar_arrive(&S.x_ready);
       for (int mb = 0; mb < n_mb; ++mb) {
         const int slot = mb % 3;
-        const int cf = 128 * mb + 32 * q + lane;
+        const int cf = 128 * chain_block(mb) + 32 * q + lane;
         const bool cok = cf < p.chain_n;
         const float cbias = (cok && p.chain_b != nullptr) ? __ldg(p.chain_b + cf) : 0.f;
         mbar_wait(&S.d2_full[slot], (mb / 3) & 1);
@@ -814,7 +830,31 @@ int tcw_launch_layer(const TempRgcnLayerArgs* a, cudaStream_t st) {
     if (int rc = tcw_launch_gather(a, st)) return rc;
   }
   const int grid = (rows + kWRows - 1) / kWRows;
-  cudaError_t e = launch_pdl(rgcn_layer_tcw_kernel, grid, kWThreads, static_cast<size_t>(smem), st, *a, KA);
+  int gy = 1;
+  if (a->chain_w_packed != nullptr) {   // few row tiles (the Bi centre step, the last steps of a window): fill the SMs with chain blocks
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int n_mb = (a->chain_n + 127) / 128;
+    gy = sms / grid;
+    if (gy > n_mb) gy = n_mb;
+    if (gy < 1) gy = 1;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, gy);
+  cfg.blockDim = dim3(kWThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, rgcn_layer_tcw_kernel, *a, KA);
   if (e != cudaSuccess) return cuda_fail(e, "rgcn_layer_tcw_kernel launch");
   return TEMP_OK;
 }
