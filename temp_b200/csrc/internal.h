@@ -40,6 +40,7 @@ bool tcw_gru_supported(const TempGruArgs* g);
 int tcw_launch_gru(const TempGruArgs* g, cudaStream_t st);
 bool tcw_scan_supported(const TempGruScanArgs* a);
 int tcw_launch_scan(const TempGruScanArgs* a, cudaStream_t st);
+int tcw_scan_launches(const TempGruScanArgs* a);   // 1 (cooperative gru_scan_tcw_kernel, d <= 224) or one per non-empty step
 int tc_pack_gru_weights(const float* whh_t, int d, void* packed, cudaStream_t st);
 
 }  // namespace temp_internal

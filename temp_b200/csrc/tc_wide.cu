@@ -741,6 +741,333 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
   if (warp == 9) tmem_dealloc(tbase, 64);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// all GRU steps of a window in ONE cooperative launch, W_hh in tensor memory (d <= 224)
+// ------------------------------------------------------------------------------------------------
+// The per-step kernel above re-streams its 32 KB x KA weight slice from L2 for every step and pays a launch hand-over per
+// step.  Here CTA (slot, cb) keeps the r | z | n rows of hidden-column block cb in TENSOR MEMORY for the whole scan -- hi
+// parts at columns [0, 32 KA), lo parts at [32 KA, 64 KA), the 64-column accumulator behind them (64 KA + 64 <= 512 columns:
+// KA <= 7) -- and the MMAs take their A operand from there (tcgen05.mma "TS" form: an MMA then reads only its 64 x 8
+// activation slice from shared memory).  Steps are separated by a grid-wide barrier (cooperative launch: all CTAs resident);
+// the state goes through L2 (ld.global.cg: rows of consecutive steps share 128-byte lines, L1 may hold a stale copy).
+// The slice is (re)installed when the recurrent cell changes (the Bi models: forward cell steps, then backward cell steps).
+struct ScanWBars {
+  uint64_t w_full[kWStages], w_empty[kWStages];
+  uint64_t b_ready, d_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float4 ld_cg_f32x4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const void* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4_w(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cta_sync_w() { asm volatile("bar.sync 0, %0;" ::"n"(kWThreads) : "memory"); }
+
+// Both role loops below walk the same (step, tile) sequence and meet at the same CTA-wide barriers (barrier 0, all 384
+// threads: end of a weight install, the two halves of the grid barrier, end of a tile step); the roles are separated at the
+// top so that the register split (setmaxnreg 208 / 88) holds for each loop.
+__global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGruScanArgs P, const int KA, const int T) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + KA * kWAtomBytes;
+  uint8_t* ring = smem + 2 * KA * kWAtomBytes;
+  __shared__ ScanWBars S;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(kFull, tid >> 5, 0);
+  const int D = P.steps[0].d;
+  const int slot = blockIdx.x / KA, cb = blockIdx.x - slot * KA;
+  const int col_lo = 32 * KA, col_d = 64 * KA;     // TMEM columns: W lo parts, accumulator
+
+  if (tid == 0) {
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&S.w_full[i], 1);
+      mbar_init(&S.w_empty[i], kWWorkerWarps);
+    }
+    mbar_init(&S.b_ready, kWWorkers);
+    mbar_init(&S.d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&S.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = S.tmem_base;
+  const uint32_t s_hi = smem_u32(b_hi), s_lo = smem_u32(b_lo), ex = smem_u32(ring);
+  pdl_wait();   // (a no-op for the cooperative launch; gi comes from the preceding kernels in stream order)
+
+  if (warp_u >= kWWorkerWarps) {
+    // =============================== control warps: weight copies, MMA issue ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const void* cur_w = nullptr;
+    uint32_t wchunk = 0, mm = 0;
+#pragma unroll 1
+    for (int s = 0; s < P.n_steps; ++s) {
+      const TempGruArgs& p = P.steps[s];
+      const bool rec = p.prev_row != nullptr;
+      if (rec && p.whh_packed != cur_w) {
+        cur_w = p.whh_packed;
+        if (warp == 8 && lane == 0) {
+          const uint8_t* w = static_cast<const uint8_t*>(p.whh_packed) + static_cast<size_t>(cb) * KA * kWChunkBytes;
+          for (int i = 0; i < KA; ++i) {
+            const uint32_t c = wchunk + i, st = c % kWStages;
+            if (c >= kWStages) mbar_wait(&S.w_empty[st], ((c / kWStages) - 1) & 1);
+            mbar_expect_tx(&S.w_full[st], kWChunkBytes);
+            bulk_g2s(ring + st * kWChunkBytes, w + static_cast<size_t>(i) * kWChunkBytes, kWChunkBytes, &S.w_full[st]);
+          }
+        }
+        wchunk += KA;
+        tc_fence_before();
+        cta_sync_w();
+        tc_fence_after();
+      }
+      const int ntiles = (p.row1 - p.row0 + kWRows - 1) / kWRows;
+      bool need_bar = s > 0;
+#pragma unroll 1
+      for (int tile = slot; tile < ntiles || need_bar; tile += T) {
+        if (need_bar) {       // the grid barrier (its global part is thread 0's, a worker)
+          cta_sync_w();
+          cta_sync_w();
+          need_bar = false;
+        }
+        if (tile >= ntiles) break;
+        if (rec && warp_u == 9) {
+          // ===== MMA issuer: gh^T = W_hh slice (tensor memory) . h0^T =====
+          const bool leader = elect_one();
+          const uint32_t idesc = umma_idesc_tf32(128, kWRows);
+          mbar_wait(&S.b_ready, mm & 1);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t dcol = tbase + col_d;
+#pragma unroll 1
+            for (int ka = 0; ka < KA; ++ka) {
+              const uint32_t bh0 = umma_desc_lo(s_hi + ka * kWAtomBytes), bl0 = umma_desc_lo(s_lo + ka * kWAtomBytes);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t a_hi = tbase + ka * 32 + ks * 8, a_lo = a_hi + col_lo;
+                const uint32_t bh = bh0 + 2 * ks, bl = bl0 + 2 * ks;          // +32 bytes per k-step inside the atom
+                umma_tf32_ts(dcol, a_lo, bh, idesc, (ka | ks) != 0 ? 1u : 0u);  // small terms first
+                umma_tf32_ts(dcol, a_hi, bl, idesc, 1u);
+                umma_tf32_ts(dcol, a_hi, bh, idesc, 1u);
+              }
+            }
+            umma_commit(&S.d_full);
+          }
+          __syncwarp();
+        }
+        if (rec) mm += 1;
+        cta_sync_w();
+      }
+    }
+  } else {
+    // =============================== workers ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int q = warp & 3, hf = warp >> 2;
+    const int j = 32 * cb + lane;
+    const bool jok = j < D;
+    const void* cur_w = nullptr;
+    uint32_t wchunk = 0, mm = 0;
+    unsigned n_bar = 0;
+#pragma unroll 1
+    for (int s = 0; s < P.n_steps; ++s) {
+      const TempGruArgs& p = P.steps[s];
+      const bool rec = p.prev_row != nullptr;
+      if (rec && p.whh_packed != cur_w) {
+        // ---- this CTA's W_hh slice -> tensor memory: KA chunks through the ring; warp (q, img = hf) moves feature rows
+        // 32 q .. + 31 of the hi (img 0) / lo (img 1) image of each chunk ----
+        cur_w = p.whh_packed;
+        const int m = 32 * q + lane;
+#pragma unroll 1
+        for (int i = 0; i < KA; ++i) {
+          const uint32_t c = wchunk + i, st = c % kWStages;
+          mbar_wait(&S.w_full[st], (c / kWStages) & 1);
+          const uint32_t rowp = ex + st * kWChunkBytes + hf * (128 * 128) + (m >> 3) * 1024 + (m & 7) * 128;
+          float v[32];
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 x = lds_f32x4_w(rowp + ((c4 ^ (m & 7)) << 4));
+            v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
+          }
+          tmem_st32(tbase + (static_cast<uint32_t>(32 * q) << 16) + hf * col_lo + 32 * i, v);
+          tmem_st_wait();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.w_empty[st]);
+        }
+        wchunk += KA;
+        tc_fence_before();
+        cta_sync_w();   // every warp's part is in TMEM (and the ring is idle again: it doubles as the gate exchange buffer)
+        tc_fence_after();
+      }
+
+      const int ntiles = (p.row1 - p.row0 + kWRows - 1) / kWRows;
+      bool need_bar = s > 0;
+#pragma unroll 1
+      for (int tile = slot; tile < ntiles || need_bar; tile += T) {
+        const bool has = tile < ntiles;
+        const int rbase = p.row0 + tile * kWRows;
+        // plan data and parameters of the tile: fetched BEFORE the step's dependency point
+        const int rr = rbase + 8 * warp + (lane & 7);
+        int pr = -1, trow = p.row_time_scalar;
+        float dt = 0.f, br = 0.f, bz = 0.f, bn = 0.f;
+        if (has) {
+          if (rec && rr < p.row1) {
+            pr = __ldg(p.prev_row + rr);
+            if (p.dt != nullptr) dt = __ldg(p.dt + rr);
+          }
+          if (jok) {
+            br = __ldg(p.b_hh + j);
+            bz = __ldg(p.b_hh + D + j);
+            bn = __ldg(p.b_hh + 2 * D + j);
+          }
+          if (p.time_embed != nullptr && p.row_time != nullptr) trow = __ldg(p.row_time + min(rr, p.row1 - 1));
+        }
+        if (need_bar) {       // grid-wide: every CTA's state stores of the previous step are visible
+          const unsigned target = (++n_bar) * gridDim.x;
+          cta_sync_w();
+          if (tid == 0) {
+            __threadfence();
+            atomicAdd(P.barrier, 1u);
+            unsigned v, spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(P.barrier) : "memory");
+              if (++spins > (1u << 26)) __trap();
+            } while (static_cast<int>(v - target) < 0);
+            __threadfence();
+          }
+          cta_sync_w();
+          need_bar = false;
+        }
+        if (!has) break;
+
+        // ---- 1. previous-state rows -> hi / lo operand ----
+        if (rec) {
+          const int nv = D >> 2;
+          const bool oka = lane < nv, okb = lane + 32 < nv;
+          const bool ina = lane < 8 * KA, inb = lane + 32 < 8 * KA;
+          float4 va[8], vb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int sr = __shfl_sync(kFull, pr, i);
+            va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sr >= 0) {
+              const float* xr = p.state + static_cast<size_t>(sr) * D;
+              if (oka) va[i] = ld_cg_f32x4(xr + 4 * lane);
+              if (okb) vb[i] = ld_cg_f32x4(xr + 4 * (lane + 32));
+            }
+          }
+          const uint32_t off_a = static_cast<uint32_t>(lane >> 3) * kWAtomBytes + static_cast<uint32_t>(warp) * 1024u;
+          const uint32_t off_b = off_a + 4u * kWAtomBytes;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t off = static_cast<uint32_t>(i) * 128u + (static_cast<uint32_t>((lane & 7) ^ i) << 4);
+            float4 hi, lo;
+            if (ina) {
+              split_tf32(va[i].x, hi.x, lo.x);
+              split_tf32(va[i].y, hi.y, lo.y);
+              split_tf32(va[i].z, hi.z, lo.z);
+              split_tf32(va[i].w, hi.w, lo.w);
+              sts_f32x4(s_hi + off_a + off, hi);
+              sts_f32x4(s_lo + off_a + off, lo);
+            }
+            if (inb) {
+              split_tf32(vb[i].x, hi.x, lo.x);
+              split_tf32(vb[i].y, hi.y, lo.y);
+              split_tf32(vb[i].z, hi.z, lo.z);
+              split_tf32(vb[i].w, hi.w, lo.w);
+              sts_f32x4(s_hi + off_b + off, hi);
+              sts_f32x4(s_lo + off_b + off, lo);
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&S.b_ready);
+        }
+        // ---- 2. input gates, time embedding, accumulate target: in flight during the MMAs ----
+        float gir[8], giz[8], gin[8], tev[8], old[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rbase + 8 * warp + i;
+          gir[i] = giz[i] = gin[i] = tev[i] = old[i] = 0.f;
+          const int tr_i = __shfl_sync(kFull, trow, i);
+          if (jok && r < p.row1) {
+            const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
+            gir[i] = ld_dep_f32(gi);
+            giz[i] = ld_dep_f32(gi + D);
+            gin[i] = ld_dep_f32(gi + 2 * D);
+            if (p.time_embed != nullptr) tev[i] = __ldg(p.time_embed + static_cast<size_t>(tr_i) * D + j);
+            if (p.accumulate) old[i] = ld_cg_f32(p.out + static_cast<size_t>(r) * D + j);
+          }
+        }
+        // ---- 3. accumulator quadrants r | z | n -> exchange rows [gate][tile row][32] (the idle weight ring) ----
+        if (rec) {
+          mbar_wait(&S.d_full, mm & 1);
+          tc_fence_after();
+          if (q < 3) {
+            float v[32];
+            tmem_ld32(tbase + (static_cast<uint32_t>(32 * q) << 16) + col_d + 32 * hf, v);
+            const uint32_t exw = ex + static_cast<uint32_t>(q * kWRows + 32 * hf) * 128u + lane * 4u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sts_f32(exw + i * 128u, v[i]);
+          }
+          tc_fence_before();
+          bar_named(1, kWWorkers);
+        }
+        // ---- 4. gates, state store ----
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = 8 * warp + i, r = rbase + m;
+          const int pri = __shfl_sync(kFull, pr, i);
+          const float dti = __shfl_sync(kFull, dt, i);
+          if (!jok || r >= p.row1) continue;
+          float hr = br, hz = bz, hn = bn, hp = 0.f;
+          if (pri >= 0) {
+            const float dec = p.dt != nullptr ? decay_factor_w(dti, p.decay_wb, p.inv_temperature) : 1.f;
+            const uint32_t ea = ex + static_cast<uint32_t>(m) * 128u + lane * 4u;
+            hr = fmaf(dec, lds_f32(ea), hr);
+            hz = fmaf(dec, lds_f32(ea + kWRows * 128u), hz);
+            hn = fmaf(dec, lds_f32(ea + 2u * kWRows * 128u), hn);
+            const uint32_t off = static_cast<uint32_t>(cb) * kWAtomBytes + sw128_off(static_cast<uint32_t>(m), static_cast<uint32_t>(lane));
+            hp = dec * (lds_f32(s_hi + off) + lds_f32(s_lo + off));
+          }
+          const float rg = sigmoid_w(gir[i] + hr), zg = sigmoid_w(giz[i] + hz);
+          const float ng = tanhf(gin[i] + rg * hn);
+          float hy = (1.f - zg) * ng + zg * hp;
+          hy += tev[i];
+          p.out[static_cast<size_t>(r) * D + j] = p.accumulate ? old[i] + hy : hy;
+        }
+        if (rec) mm += 1;
+        cta_sync_w();   // the operand tile and the exchange rows are rewritten by the next tile step
+      }
+    }
+    // self-cleaning barrier words: the last CTA to leave resets them for the next launch
+    if (tid == 0) {
+      const unsigned done = atomicAdd(P.barrier + 1, 1u);
+      if (done == gridDim.x - 1) {
+        P.barrier[0] = 0u;
+        P.barrier[1] = 0u;
+        __threadfence();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tbase, 512);
+}
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -919,9 +1246,54 @@ bool tcw_scan_supported(const TempGruScanArgs* a) {
   return true;
 }
 
+// one cooperative gru_scan_tcw_kernel launch when the slice fits tensor memory (d <= 224), else a launch per step
+static bool scan_persistent(const TempGruScanArgs* a) {
+  static const char* mode = getenv("TEMP_WIDE_SCAN");      // TEMP_WIDE_SCAN=steps: always one launch per step
+  if (mode != nullptr && strcmp(mode, "steps") == 0) return false;
+  if (a->n_steps < 2 || a->barrier == nullptr || a->steps[0].d > 224) return false;
+  for (int s = 1; s < a->n_steps; ++s)
+    if (a->steps[s].d != a->steps[0].d) return false;
+  return true;
+}
+
+int tcw_scan_launches(const TempGruScanArgs* a) {
+  if (scan_persistent(a)) return 1;
+  int k = 0;
+  for (int s = 0; s < a->n_steps; ++s) k += a->steps[s].row1 > a->steps[s].row0 ? 1 : 0;
+  return k;
+}
+
 int tcw_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
-  for (int s = 0; s < a->n_steps; ++s)
-    if (int rc = tcw_launch_gru(&a->steps[s], st)) return rc;
+  if (!scan_persistent(a)) {
+    for (int s = 0; s < a->n_steps; ++s)
+      if (int rc = tcw_launch_gru(&a->steps[s], st)) return rc;
+    return TEMP_OK;
+  }
+  const int KA = (a->steps[0].d + 31) / 32;
+  static bool configured = false;
+  static int sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gru_scan_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem_bytes(kWMaxAtoms));
+    if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tcw_kernel");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    configured = true;
+  }
+  int max_rows = 0;
+  for (int s = 0; s < a->n_steps; ++s) {
+    const int rows = a->steps[s].row1 - a->steps[s].row0;
+    if (rows > max_rows) max_rows = rows;
+  }
+  if (max_rows <= 0) return TEMP_OK;
+  int T = (max_rows + kWRows - 1) / kWRows;
+  if (T > sms / KA) T = sms / KA;        // one CTA per SM (shared memory): the whole grid must be resident
+  if (T < 1) T = 1;
+  int ka = KA;
+  void* params[] = {const_cast<TempGruScanArgs*>(a), &ka, &T};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gru_scan_tcw_kernel), dim3(T * KA), dim3(kWThreads), params,
+                                              static_cast<size_t>(wide_smem_bytes(KA)), st);
+  if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tcw_kernel launch");
   return TEMP_OK;
 }
 

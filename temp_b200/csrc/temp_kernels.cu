@@ -1560,8 +1560,8 @@ int temp_program_kernel_count(const TempOp* ops, int32_t n) {
       case TEMP_OP_GRU_SCAN: {
         const TempGruScanArgs& sc = ops[i].u.scan;
         if (sc.n_steps > 0 && sc.n_steps <= TEMP_MAX_SCAN_STEPS && sc.steps[0].d != 128 && !temp_internal::tc_scan_supported(&sc) &&
-            temp_internal::tcw_scan_supported(&sc)) {   // one gru_step_tcw_kernel launch per non-empty step
-          for (int s = 0; s < sc.n_steps; ++s) k += sc.steps[s].row1 > sc.steps[s].row0 ? 1 : 0;
+            temp_internal::tcw_scan_supported(&sc)) {   // one cooperative launch, or one gru_step_tcw_kernel launch per non-empty step
+          k += temp_internal::tcw_scan_launches(&sc);
         } else {
           k += sc.n_steps > 0 ? 1 : 0;
         }

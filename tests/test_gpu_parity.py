@@ -82,7 +82,8 @@ def test_dense_history_api_matches_oracle():
     assert time_list[-1] == ref["times"]
 
 
-@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_tiny_d128_last", "grrgcn_tiny_d32_nb8_type1"])
+@pytest.mark.parametrize("name", ["grrgcn_icews_d128_L8", "bigrrgcn_tiny_d128_last", "grrgcn_tiny_d32_nb8_type1",
+                                  "grrgcn_tiny_d200_nb100", "bigrrgcn_tiny_d200_nb100", "bigrrgcn_icews0515_real_nb100"])
 def test_cooperative_scan_equals_per_step_launches(name):
     """One persistent launch for all GRU steps against one launch per step: bit-identical where both run the same kernel
     family (uni-directional tcgen05 scans: gru_scan_tm_kernel, fp32 SIMT scans); the Bi models' fused scan alternates
@@ -98,7 +99,9 @@ def test_cooperative_scan_equals_per_step_launches(name):
     model.runtime.fuse_scan = True
     b = model.encode(case["t_list"])
     assert b.program.count() < n_a
-    if case["module"].startswith("Bi") and case["D"] == 128:
+    if (case["module"].startswith("Bi") and case["D"] == 128) or (case["D"] != 128 and not case.get("type1")):
+        # (d != 128: gru_step_tcw_kernel multiplies from shared-memory weight chunks, the cooperative gru_scan_tcw_kernel from
+        # tensor memory -- the same products in the same order, held to fp32 rounding rather than to the bit)
         assert float((a - b.out).abs().max()) <= 2e-6 * float(a.abs().max())
         a = b.out.clone()
     else:
