@@ -33,7 +33,7 @@ extern "C" {
 #define TEMP_ECUDA (-2)    /* a CUDA runtime call / launch failed; see last error     */
 #define TEMP_EUNSUPPORTED (-3)
 
-#define TEMP_MAX_D 256     /* embed_size == hidden_size upper bound of the SIMT path  */
+#define TEMP_MAX_D 256     /* embed_size == hidden_size upper bound (SIMT path and the 64-row tcgen05 kernels) */
 #define TEMP_MAX_TERMS 3
 #define TEMP_MAX_SCAN_STEPS 16
 #define TEMP_MAX_PUSH_PEERS 16
@@ -54,8 +54,10 @@ extern "C" {
  *            reference models/RRGCN.py:83, models/RGCN.py:106-107.
  *   w        [d, d] row-major (in x out), e.g. loop_weight / time_weight as stored.
  *   w_packed nullable: the same matrix in the tensor-core operand image written by temp_pack_weights
- *            (d == 128 only).  When every operand of a launch has its packed image the layer runs on the
- *            tcgen05 path (3xTF32 split, fp32-level accuracy); otherwise on the fp32 SIMT path.         */
+ *            (d % 4 == 0, d <= 256).  When every operand of a launch has its packed image the layer runs on the
+ *            tcgen05 path (3xTF32 split, fp32-level accuracy: the 128-row tile kernel for d == 128 with 1x1 relation
+ *            blocks, the 64-row tile kernel of tc_wide.cu for every other width and for 2x2 / 4x4 blocks -- e.g.
+ *            d = 200, n_bases = 100 as the reference ships ICEWS05-15); otherwise on the fp32 SIMT path.   */
 typedef struct {
   const float* a;
   const int32_t* a_index;
@@ -99,7 +101,7 @@ typedef struct {
   const float* chain_b;      /* nullable [chain_n]                                                */
   float* chain_out;          /* [rows, chain_ld]; columns [0, chain_n) are written                */
   int32_t chain_n, chain_ld;
-  const void* chain_w_packed; /* nullable: chain_w in the temp_pack_weights image (chain_n % 128 == 0) */
+  const void* chain_w_packed; /* nullable: chain_w in the temp_pack_weights image (d == 128 with 1x1 blocks: chain_n % 128 == 0) */
   float inv_temperature;
   float* agg_scratch;        /* nullable [>= row1 rows, d] scratch indexed by packed row: the tcgen05 path runs the
                                 aggregation as its own HBM-bound launch and hands it over through this buffer      */
@@ -136,7 +138,7 @@ typedef struct {
   const float* decay_wb;     /* nullable (learnable lambda: weight, bias)                         */
   float inv_temperature;
   const float* whh_t;        /* [d, 3d] row-major = weight_hh transposed                          */
-  const void* whh_packed;    /* nullable: whh_t in the temp_pack_gru_weights image (d == 128)     */
+  const void* whh_packed;    /* nullable: whh_t in the temp_pack_gru_weights image (d % 4 == 0, d <= 256) */
   const float* b_hh;         /* [3d]                                                              */
   int32_t cell_type;
   const float* time_embed;   /* nullable                                                          */
@@ -159,7 +161,9 @@ typedef struct {
  *            at most part_rows rows (lo == hi: nothing).  The tcgen05 path (d == 128) gives every partition to
  *            one 4-CTA cluster (to one of its one or two pipelines when part_rows <= 48) and separates the steps of a
  *            partition by cluster-scope barriers; without the table (or d != 128) steps are separated by a
- *            grid-wide barrier (cooperative launch).
+ *            grid-wide barrier (cooperative launch: gru_scan_tcw_kernel with the W_hh slices in tensor memory when every
+ *            step has its packed image and d <= 224, else the fp32 SIMT gru_scan_kernel), or run as one
+ *            gru_step_tcw_kernel launch per step (224 < d <= 256).
  *   barrier: 8 bytes of device memory for the grid-wide barrier, zero before the first use; the kernel
  *            leaves it zeroed.  Launches sharing one barrier word must not run concurrently.        */
 typedef struct {
@@ -367,8 +371,9 @@ const char* temp_last_error_string(void);
 int temp_device_info(int32_t* sm_count, int32_t* max_smem, int32_t* cc);
 
 int temp_rgcn_layer_fwd(const TempRgcnLayerArgs* args, void* stream);
-/* The aggregation half alone (tcgen05 path, d == 128, 1x1 relation blocks): agg_scratch[v] = norm_v^2 * sum_e W[rel_e] (.)
- * x[src_e] for the rows of [row0, row1) with in-edges -- the DGL update_all / fn.sum / apply of models/RGCN.py:100-104. */
+/* The aggregation half alone (tcgen05 path; d % 4 == 0, d <= 256, 1x1 / 2x2 / 4x4 relation blocks): agg_scratch[v] =
+ * norm_v^2 * sum_e blockdiag(W[rel_e]) x[src_e] for the rows of [row0, row1) with in-edges -- the DGL update_all / fn.sum /
+ * apply of models/RGCN.py:91-104. */
 int temp_rgcn_gather_fwd(const TempRgcnLayerArgs* args, void* stream);
 int temp_gru_fwd(const TempGruArgs* args, void* stream);
 int temp_gru_scan_fwd(const TempGruScanArgs* args, void* stream);
@@ -380,10 +385,12 @@ int temp_score_loss_fwd(const TempScoreLossArgs* args, void* stream);
 int temp_score_loss_bwd(const TempScoreLossBwdArgs* args, void* stream);
 int temp_rank_filtered_fwd(const TempRankArgs* args, void* stream);
 int temp_transpose(const float* in, int32_t rows, int32_t cols, float* out, int32_t out_ld, void* stream);
-/* Tensor-core operand images (d == 128).  A [k, n] row-major fp32 matrix (k == 128, n % 128 == 0) is split
- * into tf32 hi / lo parts and stored, per 128 output features x 32 k, in the K-major SWIZZLE_128B
- * shared-memory layout the tcgen05 kernels fetch with cp.async.bulk (temp_b200/csrc/tc_common.cuh).
- * temp_pack_gru_weights packs whh_t [128, 384] per block of 32 hidden columns (rows r|z|n|zero pad).  */
+/* Tensor-core operand images.  A [k, n] row-major fp32 matrix (k % 4 == 0, k <= 256) is split into tf32 hi / lo
+ * parts and stored, per 128 output features x 32 k, in the K-major SWIZZLE_128B shared-memory layout the tcgen05
+ * kernels fetch with cp.async.bulk (temp_b200/csrc/tc_common.cuh); k is padded to whole 32-wide k-atoms and n to whole
+ * 128-feature blocks with zeros (for k == 128, n % 128 == 0 nothing is padded).
+ * temp_pack_gru_weights packs whh_t [d, 3 d] per block of 32 hidden columns (rows r|z|n|zero pad).
+ * *_bytes return the image size, or a negative value for shapes without a tensor-core path.  */
 int64_t temp_packed_weights_bytes(int32_t k, int32_t n);
 int temp_pack_weights(const float* w_kn, int32_t k, int32_t n, void* packed, void* stream);
 int64_t temp_packed_gru_bytes(int32_t d);

@@ -936,16 +936,14 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         }
         if (need_bar) {       // grid-wide: every CTA's state stores of the previous step are visible
           const unsigned target = (++n_bar) * gridDim.x;
-          cta_sync_w();
+          cta_sync_w();     // every thread's state stores are ordered before thread 0's release (cumulativity)
           if (tid == 0) {
-            __threadfence();
-            atomicAdd(P.barrier, 1u);
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.barrier) : "memory");
             unsigned v, spins = 0;
             do {
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(P.barrier) : "memory");
               if (++spins > (1u << 26)) __trap();
             } while (static_cast<int>(v - target) < 0);
-            __threadfence();
           }
           cta_sync_w();
           need_bar = false;

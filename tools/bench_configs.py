@@ -42,4 +42,5 @@ for cfg in T.CONFIGS[:6]:
                       "batch": len(t_list), "rows": int(res.plan.R), "edges": int(res.plan.E),
                       "kernel_launches": prog.kernel_count(), "gpu_ms": ms, "gpu_edges_per_s": res.plan.E / (ms * 1e-3),
                       "cpu_oracle_ms": cpu_ms, "cpu_edges_per_s": res.plan.E / (cpu_ms * 1e-3), "cpu_cores": os.cpu_count(),
-                      "path": "tcgen05" if cfg[3] == 128 else "fp32 SIMT (D != 128)"}))
+                      "path": "tcgen05" if cfg[3] == 128 else ("fp32 SIMT (TEMP_WIDE_TC=0)" if os.environ.get("TEMP_WIDE_TC") == "0"
+                                                                else "tcgen05, 64-row tiles (tc_wide.cu)")}))
