@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TEMP_ABI_VERSION 19
+#define TEMP_ABI_VERSION 20
 
 #define TEMP_OK 0
 #define TEMP_EINVAL (-1)   /* bad argument (null pointer, unsupported size, ...)      */
@@ -164,8 +164,8 @@ typedef struct {
  *            grid-wide barrier (cooperative launch: gru_scan_tcw_kernel with the W_hh slices in tensor memory when every
  *            step has its packed image and d <= 224, else the fp32 SIMT gru_scan_kernel), or run as one
  *            gru_step_tcw_kernel launch per step (224 < d <= 256).
- *   barrier: 8 bytes of device memory for the grid-wide barrier, zero before the first use; the kernel
- *            leaves it zeroed.  Launches sharing one barrier word must not run concurrently.        */
+ *   barrier: 8 bytes of device memory for the grid-wide barrier (more with barrier_words, below), zero before the
+ *            first use; the kernel leaves it zeroed.  Launches sharing one barrier word must not run concurrently. */
 typedef struct {
   int32_t n_steps;
   int32_t n_parts;
@@ -188,6 +188,11 @@ typedef struct {
   float* push_multicast;     /* nullable: NVLS multicast address of the same symmetric buffer -- one multimem.st per
                                 value instead of one store per peer (the switch replicates it to every GPU); push_bufs then
                                 lists only buffers OUTSIDE the multicast group (e.g. a pinned host buffer; push_world >= 0) */
+  int32_t barrier_words;     /* zeroed 32-bit words behind `barrier` (0 or 2: the two barrier words only).  With
+                                2 + n_steps * ceil(max step rows / 64) words or more, gru_scan_tcw_kernel (d != 128) replaces
+                                the grid-wide barrier between steps by per-tile completion counters: a tile step waits only
+                                for the tiles of the previous step that hold its prev_row rows.  Left zeroed by the kernel. */
+  int32_t reserved3;
   TempGruArgs steps[TEMP_MAX_SCAN_STEPS];
 } TempGruScanArgs;
 

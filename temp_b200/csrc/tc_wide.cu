@@ -778,7 +778,12 @@ __device__ __forceinline__ void cta_sync_w() { asm volatile("bar.sync 0, %0;" ::
 // Both role loops below walk the same (step, tile) sequence and meet at the same CTA-wide barriers (barrier 0, all 384
 // threads: end of a weight install, the two halves of the grid barrier, end of a tile step); the roles are separated at the
 // top so that the register split (setmaxnreg 208 / 88) holds for each loop.
-__global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGruScanArgs P, const int KA, const int T) {
+// tile_stride > 0: per-tile completion counters instead of the grid barrier -- word 2 + s * tile_stride + tile of P.barrier
+// counts the column-block CTAs that have stored (step s, tile); a worker warp waits, before it gathers its 8 rows' previous
+// states, only for the tiles of the producing step that hold those rows (dependencies point to earlier steps only and every
+// CTA walks its tile steps in order, so the waits cannot form a cycle; all CTAs are resident: cooperative launch).
+__global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGruScanArgs P, const int KA, const int T,
+                                                                     const int tile_stride) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* b_hi = smem;
@@ -835,7 +840,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         tc_fence_after();
       }
       const int ntiles = (p.row1 - p.row0 + kWRows - 1) / kWRows;
-      bool need_bar = s > 0;
+      bool need_bar = s > 0 && tile_stride == 0;
 #pragma unroll 1
       for (int tile = slot; tile < ntiles || need_bar; tile += T) {
         if (need_bar) {       // the grid barrier (its global part is thread 0's, a worker)
@@ -913,7 +918,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
       }
 
       const int ntiles = (p.row1 - p.row0 + kWRows - 1) / kWRows;
-      bool need_bar = s > 0;
+      bool need_bar = s > 0 && tile_stride == 0;
 #pragma unroll 1
       for (int tile = slot; tile < ntiles || need_bar; tile += T) {
         const bool has = tile < ntiles;
@@ -949,6 +954,48 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
           need_bar = false;
         }
         if (!has) break;
+
+        // ---- 0. (completion counters) this warp's 8 rows: wait for the tiles of the producing step that hold their states ----
+        if (rec && tile_stride > 0) {
+          int mn = (lane < 8 && pr >= 0) ? pr : 0x7fffffff, mx = lane < 8 ? pr : -1;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+            mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+          }
+          mn = __shfl_sync(kFull, mn, 0);
+          mx = __shfl_sync(kFull, mx, 0);
+          if (mx >= 0) {       // warp-uniform
+            // the producing step of a row: the latest earlier step of this launch that writes it into the buffer this step reads
+            int sa = -1, sb = -1;
+            for (int k = s - 1; k >= 0 && (sa < 0 || sb < 0); --k) {
+              const TempGruArgs& g = P.steps[k];
+              if (g.out != p.state) continue;
+              if (sa < 0 && mn >= g.row0 && mn < g.row1) sa = k;
+              if (sb < 0 && mx >= g.row0 && mx < g.row1) sb = k;
+            }
+            const unsigned* flags = P.barrier + 2;
+            auto wait_tiles = [&](int k, int lo_row, int hi_row) {   // tiles of step k covering rows [lo_row, hi_row]
+              const int r0 = P.steps[k].row0;
+              const int t0 = (lo_row - r0) / kWRows, t1 = (hi_row - r0) / kWRows;
+              for (int t = t0 + lane; t <= t1; t += 32) {
+                const unsigned* f = flags + static_cast<size_t>(k) * tile_stride + t;
+                unsigned v, spins = 0;
+                do {
+                  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+                  if (++spins > (1u << 26)) __trap();
+                } while (v < static_cast<unsigned>(KA));
+              }
+            };
+            if (sa >= 0 && sa == sb) {
+              wait_tiles(sa, mn, mx);
+            } else {             // rows of several producing steps (no planner emits this): every tile of each of them
+              if (sa >= 0) wait_tiles(sa, P.steps[sa].row0, P.steps[sa].row1 - 1);
+              if (sb >= 0) wait_tiles(sb, P.steps[sb].row0, P.steps[sb].row1 - 1);
+            }
+            __syncwarp();
+          }
+        }
 
         // ---- 1. previous-state rows -> hi / lo operand ----
         if (rec) {
@@ -1048,12 +1095,17 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         }
         if (rec) mm += 1;
         cta_sync_w();   // the operand tile and the exchange rows are rewritten by the next tile step
+        // (completion counters) every thread's state stores are ordered before thread 0's release by the barrier
+        if (tile_stride > 0 && tid == 0)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.barrier + 2 + static_cast<size_t>(s) * tile_stride + tile) : "memory");
       }
     }
-    // self-cleaning barrier words: the last CTA to leave resets them for the next launch
+    // self-cleaning barrier words and counters: the last CTA to leave resets them for the next launch
     if (tid == 0) {
       const unsigned done = atomicAdd(P.barrier + 1, 1u);
       if (done == gridDim.x - 1) {
+        __threadfence();
+        for (int i = 0; i < P.n_steps * tile_stride; ++i) P.barrier[2 + i] = 0u;
         P.barrier[0] = 0u;
         P.barrier[1] = 0u;
         __threadfence();
@@ -1287,8 +1339,13 @@ int tcw_launch_scan(const TempGruScanArgs* a, cudaStream_t st) {
   int T = (max_rows + kWRows - 1) / kWRows;
   if (T > sms / KA) T = sms / KA;        // one CTA per SM (shared memory): the whole grid must be resident
   if (T < 1) T = 1;
+  // per-tile completion counters when the caller's zeroed words hold them, else grid-wide barriers between the steps
+  const int max_tiles = (max_rows + kWRows - 1) / kWRows;
+  static const char* sync_mode = getenv("TEMP_WIDE_SCAN");      // TEMP_WIDE_SCAN=grid: always the grid barrier
+  int tile_stride = 0;
+  if (a->barrier_words >= 2 + a->n_steps * max_tiles && !(sync_mode != nullptr && strcmp(sync_mode, "grid") == 0)) tile_stride = max_tiles;
   int ka = KA;
-  void* params[] = {const_cast<TempGruScanArgs*>(a), &ka, &T};
+  void* params[] = {const_cast<TempGruScanArgs*>(a), &ka, &T, &tile_stride};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gru_scan_tcw_kernel), dim3(T * KA), dim3(kWThreads), params,
                                               static_cast<size_t>(wide_smem_bytes(KA)), st);
   if (e != cudaSuccess) return cuda_fail(e, "gru_scan_tcw_kernel launch");

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtemp_b200.so")
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 MAX_SCAN_STEPS = 16
 MAX_TERMS = 3
 ACT_NONE, ACT_RELU = 0, 1
@@ -57,7 +57,7 @@ class GruArgs(C.Structure):
 class GruScanArgs(C.Structure):
     _fields_ = [("n_steps", _i32), ("n_parts", _i32), ("barrier", _p), ("parts", _p), ("part_stride", _i32),
                 ("push_world", _i32), ("push_bufs", _p), ("push_offset", C.c_int64), ("push_row0", _i32), ("part_rows", _i32),
-                ("push_multicast", _p), ("steps", GruArgs * MAX_SCAN_STEPS)]
+                ("push_multicast", _p), ("barrier_words", _i32), ("reserved3", _i32), ("steps", GruArgs * MAX_SCAN_STEPS)]
 
 
 class AttnArgs(C.Structure):
@@ -248,7 +248,7 @@ class Program(object):
         return len(self.ops)
 
     def fuse_gru_scans(self, barrier_ptr: int, parts_ptr: Optional[int] = None, n_parts: int = 0, part_stride: int = 0,
-                       part_rows: int = 0, split_cells: bool = False) -> None:
+                       part_rows: int = 0, split_cells: bool = False, barrier_words: int = 2) -> None:
         """Replaces every run of >= 2 consecutive GRU ops by ONE scan launch (chain-partitioned when the plan's
         partition table is given, see TempGruScanArgs).  ``split_cells``: a run also ends where the recurrent cell changes
         (the Bi models: one single-cell scan per direction)."""
@@ -261,7 +261,7 @@ class Program(object):
                     out.append(chunk[0])
                 else:
                     a = GruScanArgs()
-                    a.n_steps, a.barrier = len(chunk), barrier_ptr
+                    a.n_steps, a.barrier, a.barrier_words = len(chunk), barrier_ptr, int(barrier_words)
                     if parts_ptr is not None:
                         a.parts, a.n_parts, a.part_stride, a.part_rows = parts_ptr, n_parts, part_stride, part_rows
                     for i, o in enumerate(chunk):

@@ -325,10 +325,13 @@ class EncoderRuntime(object):
             return self._build_attention(plan, prog, dptr)
         return self._build_recurrent(plan, prog, dptr)
 
+    SCAN_BARRIER_WORDS = 2 + 16 * 1024      # two grid-barrier words + per-(step, 64-row tile) completion counters
+
     def scan_barrier(self) -> int:
-        """8 zeroed bytes for the grid barrier of the SIMT scan (D != 128; self-cleaning, see temp_b200.h)."""
+        """Zeroed words for the cooperative scans at D != 128 (self-cleaning, see TempGruScanArgs.barrier / barrier_words):
+        the grid barrier, and the per-tile completion counters of gru_scan_tcw_kernel."""
         if getattr(self, "_barrier", None) is None:
-            self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._barrier = torch.zeros(self.SCAN_BARRIER_WORDS, dtype=torch.int32, device=self.device)
         return self._barrier.data_ptr()
 
     def _build_static(self, plan, prog, dptr):
@@ -503,9 +506,9 @@ class EncoderRuntime(object):
                 p_lo, p_hi = (0, int(parts.shape[0])) if shard is None else shard.parts_of(rank)
                 stride = int(parts.shape[1])
                 prog.fuse_gru_scans(self.scan_barrier(), dptr["scan_parts"] + 8 * stride * p_lo, p_hi - p_lo, stride,
-                                    int(getattr(plan, "scan_tile", 0)), split_cells=(D == 128))   # (the SIMT scan takes both cells in one launch)
+                                    int(getattr(plan, "scan_tile", 0)), split_cells=(D == 128), barrier_words=self.SCAN_BARRIER_WORDS)   # (the SIMT scan takes both cells in one launch)
             else:
-                prog.fuse_gru_scans(self.scan_barrier())
+                prog.fuse_gru_scans(self.scan_barrier(), barrier_words=self.SCAN_BARRIER_WORDS)
         return EncodeResult(plan, out, S, prog, bufs)
 
     def _build_attention(self, plan, prog, dptr):
