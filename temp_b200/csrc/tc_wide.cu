@@ -542,7 +542,11 @@ __device__ __forceinline__ float decay_factor_w(float dt, const float* wb, float
   if (wb != nullptr) return expf(-fmaxf(fmaf(__ldg(wb), dt, __ldg(wb + 1)), 0.f));
   return expf(-dt * inv_temperature);
 }
-__device__ __forceinline__ float sigmoid_w(float x) { return 1.f / (1.f + expf(-x)); }
+// ex2.approx / rcp.approx based gate math, absolute error ~1e-7 (as the 128-wide scans; the parity bar is 1e-4 relative).
+// The gate phase is on the serial chain of every step: with expf / tanhf it was 4.4 k of a step's 13 k cycles
+// (tools/probe_timeline_wide.py).
+__device__ __forceinline__ float sigmoid_w(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_w(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // One GRU step (models/RRGCN.py:77-89, torch.nn.GRU equations) for packed rows [row0, row1): CTA (tile, cb) = 64 rows x the
 // 32 hidden columns [32 cb, 32 cb + 32).
@@ -622,10 +626,10 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
     // lanes 0..7: previous-state row and time gap of tile row 8 w + lane (plan data: fetched before the dependency point)
     const int rr = rbase + 8 * warp + (lane & 7);
     int pr = -1;
-    float dt = 0.f;
+    float dt = 1.f;          // decay factor of tile row 8 w + (lane & 7)
     if (rec && rr < p.row1) {
       pr = __ldg(p.prev_row + rr);
-      if (p.dt != nullptr) dt = __ldg(p.dt + rr);
+      if (p.dt != nullptr) dt = decay_factor_w(__ldg(p.dt + rr), p.decay_wb, p.inv_temperature);   // (the factor, once per row)
     }
     const int j = 32 * cb + lane;
     const bool jok = j < D;
@@ -720,7 +724,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
       if (!jok || r >= p.row1) continue;
       float hr = br, hz = bz, hn = bn, hp = 0.f;
       if (pri >= 0) {
-        const float dec = p.dt != nullptr ? decay_factor_w(dti, p.decay_wb, p.inv_temperature) : 1.f;
+        const float dec = dti;
         const uint32_t ea = ex + static_cast<uint32_t>(m) * 128u + lane * 4u;
         hr = fmaf(dec, lds_f32(ea), hr);
         hz = fmaf(dec, lds_f32(ea + kWRows * 128u), hz);
@@ -729,7 +733,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
         hp = dec * (lds_f32(s_hi + off) + lds_f32(s_lo + off));     // hi + lo is the fp32 value exactly
       }
       const float rg = sigmoid_w(gir[i] + hr), zg = sigmoid_w(giz[i] + hz);
-      const float ng = tanhf(gin[i] + rg * hn);
+      const float ng = tanh_w(gin[i] + rg * hn);
       float hy = (1.f - zg) * ng + zg * hp;
       hy += tev[i];
       p.out[static_cast<size_t>(r) * D + j] = p.accumulate ? old[i] + hy : hy;
@@ -752,6 +756,19 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
 // activation slice from shared memory).  Steps are separated by a grid-wide barrier (cooperative launch: all CTAs resident);
 // the state goes through L2 (ld.global.cg: rows of consecutive steps share 128-byte lines, L1 may hold a stale copy).
 // The slice is (re)installed when the recurrent cell changes (the Bi models: forward cell steps, then backward cell steps).
+// Development-only phase timeline (tools/probe_timeline_wide.py builds a separate library with -DTEMP_TIMELINE): lane 0 of
+// every worker warp stores clock64() at mark m of step s into [cta][warp 0..7][step 0..15][mark 0..9].
+#ifdef TEMP_TIMELINE
+__device__ unsigned long long* g_timeline_w = nullptr;
+__device__ __forceinline__ void tlw(int warp, int step, int mark) {
+  if (g_timeline_w != nullptr && (threadIdx.x & 31) == 0 && warp < 8 && step < 16)
+    g_timeline_w[((static_cast<size_t>(blockIdx.x) * 8 + warp) * 16 + step) * 10 + mark] = clock64();
+}
+#define TLW(m) tlw(warp, s, m)
+#else
+#define TLW(m)
+#endif
+
 struct ScanWBars {
   uint64_t w_full[kWStages], w_empty[kWStages];
   uint64_t b_ready, d_full;
@@ -875,6 +892,10 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         }
         if (rec) mm += 1;
         cta_sync_w();
+        // (completion counters) every worker's state stores are ordered before this release by the barrier; an otherwise
+        // idle warp signals, so that no worker warp sits behind the release's memory barrier at the top of its next step
+        if (tile_stride > 0 && warp == 10 && lane == 0)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.barrier + 2 + static_cast<size_t>(s) * tile_stride + tile) : "memory");
       }
     }
   } else {
@@ -926,11 +947,11 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         // plan data and parameters of the tile: fetched BEFORE the step's dependency point
         const int rr = rbase + 8 * warp + (lane & 7);
         int pr = -1, trow = p.row_time_scalar;
-        float dt = 0.f, br = 0.f, bz = 0.f, bn = 0.f;
+        float dt = 1.f, br = 0.f, bz = 0.f, bn = 0.f;     // dt: the decay FACTOR of tile row 8 w + (lane & 7)
         if (has) {
           if (rec && rr < p.row1) {
             pr = __ldg(p.prev_row + rr);
-            if (p.dt != nullptr) dt = __ldg(p.dt + rr);
+            if (p.dt != nullptr) dt = decay_factor_w(__ldg(p.dt + rr), p.decay_wb, p.inv_temperature);
           }
           if (jok) {
             br = __ldg(p.b_hh + j);
@@ -955,6 +976,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         }
         if (!has) break;
 
+        TLW(0);
         // ---- 0. (completion counters) this warp's 8 rows: wait for the tiles of the producing step that hold their states ----
         if (rec && tile_stride > 0) {
           int mn = (lane < 8 && pr >= 0) ? pr : 0x7fffffff, mx = lane < 8 ? pr : -1;
@@ -997,6 +1019,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
           }
         }
 
+        TLW(1);
         // ---- 1. previous-state rows -> hi / lo operand ----
         if (rec) {
           const int nv = D >> 2;
@@ -1040,6 +1063,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
           fence_proxy_async();
           mbar_arrive(&S.b_ready);
         }
+        TLW(2);
         // ---- 2. input gates, time embedding, accumulate target: in flight during the MMAs ----
         float gir[8], giz[8], gin[8], tev[8], old[8];
 #pragma unroll
@@ -1056,10 +1080,12 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
             if (p.accumulate) old[i] = ld_cg_f32(p.out + static_cast<size_t>(r) * D + j);
           }
         }
+        TLW(3);
         // ---- 3. accumulator quadrants r | z | n -> exchange rows [gate][tile row][32] (the idle weight ring) ----
         if (rec) {
           mbar_wait(&S.d_full, mm & 1);
           tc_fence_after();
+          TLW(4);
           if (q < 3) {
             float v[32];
             tmem_ld32(tbase + (static_cast<uint32_t>(32 * q) << 16) + col_d + 32 * hf, v);
@@ -1070,6 +1096,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
           tc_fence_before();
           bar_named(1, kWWorkers);
         }
+        TLW(5);
         // ---- 4. gates, state store ----
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -1079,7 +1106,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
           if (!jok || r >= p.row1) continue;
           float hr = br, hz = bz, hn = bn, hp = 0.f;
           if (pri >= 0) {
-            const float dec = p.dt != nullptr ? decay_factor_w(dti, p.decay_wb, p.inv_temperature) : 1.f;
+            const float dec = dti;
             const uint32_t ea = ex + static_cast<uint32_t>(m) * 128u + lane * 4u;
             hr = fmaf(dec, lds_f32(ea), hr);
             hz = fmaf(dec, lds_f32(ea + kWRows * 128u), hz);
@@ -1088,16 +1115,15 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
             hp = dec * (lds_f32(s_hi + off) + lds_f32(s_lo + off));
           }
           const float rg = sigmoid_w(gir[i] + hr), zg = sigmoid_w(giz[i] + hz);
-          const float ng = tanhf(gin[i] + rg * hn);
+          const float ng = tanh_w(gin[i] + rg * hn);
           float hy = (1.f - zg) * ng + zg * hp;
           hy += tev[i];
           p.out[static_cast<size_t>(r) * D + j] = p.accumulate ? old[i] + hy : hy;
         }
+        TLW(6);
         if (rec) mm += 1;
         cta_sync_w();   // the operand tile and the exchange rows are rewritten by the next tile step
-        // (completion counters) every thread's state stores are ordered before thread 0's release by the barrier
-        if (tile_stride > 0 && tid == 0)
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.barrier + 2 + static_cast<size_t>(s) * tile_stride + tile) : "memory");
+        TLW(7);
       }
     }
     // self-cleaning barrier words and counters: the last CTA to leave resets them for the next launch
@@ -1140,6 +1166,13 @@ bool wide_enabled() {
 }
 
 }  // namespace
+
+#ifdef TEMP_TIMELINE
+extern "C" int temp_debug_timeline_wide(void* device_buffer) {  // [ctas][8 warps][16 steps][10 marks] u64, or null to disable
+  unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+  return cudaMemcpyToSymbol(g_timeline_w, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 namespace temp_internal {
 
