@@ -462,3 +462,38 @@ def test_model_shell_answers_the_reference_hook_names_and_loaders():
     assert sorted(int(t) for b in batches for t in b) == sorted(int(t) for t in store.times)
     out = model.test_end([{"ranks": torch.tensor([1, 2, 10]), "test_loss": 0.5, "batch_time": batches[0]}])
     assert abs(out["mrr"] - (1 + 0.5 + 0.1) / 3) < 1e-6 and out["hit_1"] == pytest.approx(1 / 3)
+
+
+def test_tensor_core_image_sizes_cover_the_wide_family_without_a_gpu():
+    """temp_packed_weights_bytes / temp_packed_gru_bytes (no CUDA call): 32 KB chunks of 128 features x 32 k (hi + lo image);
+    d = 128 keeps the round-1 image, every other d % 4 == 0 up to 256 pads k to whole k-atoms and n to whole 128-feature
+    blocks (tc_wide.cu); shapes without a tensor-core path answer with a negative size; a scan made of such steps counts one
+    launch (cooperative, d <= 224) and TempGruScanArgs carries the counters' word count."""
+    import ctypes as C
+    from temp_b200 import lib
+    L = lib.load()
+    chunk = 2 * 128 * 128
+    assert L.temp_packed_weights_bytes(128, 384) == 3 * 4 * chunk
+    assert L.temp_packed_weights_bytes(200, 200) == 2 * 7 * chunk
+    assert L.temp_packed_weights_bytes(200, 1200) == 10 * 7 * chunk
+    assert L.temp_packed_weights_bytes(32, 96) == 1 * 1 * chunk
+    assert L.temp_packed_weights_bytes(256, 768) == 6 * 8 * chunk
+    assert L.temp_packed_weights_bytes(130, 130) < 0 and L.temp_packed_weights_bytes(260, 260) < 0
+    assert L.temp_packed_gru_bytes(128) == 4 * 4 * chunk
+    assert L.temp_packed_gru_bytes(200) == 7 * 7 * chunk
+    assert L.temp_packed_gru_bytes(258) < 0
+    sc = lib.GruScanArgs()
+    sc.n_steps, sc.barrier, sc.barrier_words = 3, 0x1000, 2 + 3 * 8
+    for i in range(3):
+        g = sc.steps[i]
+        g.row0, g.row1, g.d = 64 * i, 64 * i + 50, 200
+        g.gi, g.b_hh, g.out, g.whh_packed, g.state = 0x2000, 0x3000, 0x4000, 0x5000, 0x4000
+        g.prev_row = 0x6000 if i else None
+        g.cell_type = lib.CELL_TORCH_GRU
+    op = lib.Op()
+    op.kind = lib.OP_GRU_SCAN
+    op.u.scan = sc
+    arr = (lib.Op * 1)(op)
+    assert L.temp_program_kernel_count(arr, 1) == 1
+    arr[0].u.scan.steps[0].d = arr[0].u.scan.steps[1].d = arr[0].u.scan.steps[2].d = 256      # W_hh slice beyond tensor memory
+    assert L.temp_program_kernel_count(arr, 1) == 3
