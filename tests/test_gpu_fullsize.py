@@ -31,6 +31,11 @@ CONFIGS = [
     ("bigrrgcn_icews14_type1", "BiGRRGCN", "icews14", 128, 128, 4, 5, {"type1": True}),
     ("rrgcn_icews14", "RRGCN", "icews14", 128, 128, 8, 8, {}),
     ("grrgcn_icews14_all_layers_recurrent", "GRRGCN", "icews14", 128, 128, 6, 4, {"rec_only_last_layer": False}),
+    # the other widths on the 64-row tensor-core kernels (tc_wide.cu): every program shape at D = 200 / 2x2 blocks, and D = 160
+    ("grrgcn_icews0515_d200_nb100", "GRRGCN", "icews05-15", 200, 100, 8, 8, {}),
+    ("grrgcn_icews14_d200_all_layers_recurrent", "GRRGCN", "icews14", 200, 100, 5, 4, {"rec_only_last_layer": False}),
+    ("bisargcn_icews14_d200_nb100", "BiSARGCN", "icews14", 200, 100, 6, 6, {}),
+    ("bigrrgcn_icews14_d160_nb40_lambda", "BiGRRGCN", "icews14", 160, 40, 6, 6, {"learnable_lambda": True}),
 ]
 
 
