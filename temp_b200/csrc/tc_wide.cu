@@ -17,6 +17,13 @@
 //        aggregation in temp_kernels.cu, to which the parity tests hold it.
 //   rgcn_layer_tcw_kernel      : one CTA per 64 packed rows; 8 worker warps (operand staging, both epilogues), a TMA
 //        warp (weight chunks), an MMA warp -- the structure of rgcn_layer_tc_kernel.
+//   gru_scan_tcw_kernel        : all GRU steps of a window in one cooperative launch; CTA (tile slot, block of 32 hidden
+//        columns) keeps its r | z | n slice of W_hh in TENSOR MEMORY for the whole scan (TS-form tcgen05.mma, d <= 224),
+//        the state goes through L2, steps are ordered by per-tile completion counters (or a grid barrier).
+//   gru_step_tcw_kernel        : one GRU step per launch (224 < d <= 256, single steps of the models whose two layers
+//        alternate), the weight slice streamed through the ring.
+// Reference statements: models/RGCN.py:53-104 (layer), models/RRGCN.py:77-89 and torch.nn.GRU (step), as cited on the
+// entry points in include/temp_b200.h.  Measurements (BASELINE config 3: 0.879 -> 0.287 ms) and bounds: DESIGN.md 3a.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
