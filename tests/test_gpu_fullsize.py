@@ -153,6 +153,26 @@ def test_scaled_shapes_with_many_partitions_per_cluster(cfg_index, scale):
     assert torch.equal(got, model.encode(t_list).out)
 
 
+@pytest.mark.parametrize("cfg_index,scale", [(2, 5), (11, 6)], ids=["bigrrgcn_icews0515_d200_x5", "grrgcn_icews0515_d200_x6"])
+def test_scaled_shapes_on_the_wide_kernels(cfg_index, scale):
+    """D = 200 at several times the BASELINE size: more 64-row tiles per step than gru_scan_tcw_kernel has tile slots (148 SMs /
+    7 column blocks = 21), so a CTA walks several tiles per step and the per-tile completion counters order tiles of different
+    rounds; the layer launches run in several waves.  Held to the oracle; repeated launches stay bit-identical (the counters
+    are left zeroed)."""
+    cfg = CONFIGS[cfg_index]
+    assert cfg[3] == 200
+    model, oracle, t_list = _build(cfg, scale=scale)
+    res = model.encode(t_list)
+    got = res.out.clone()
+    seg_rows = max(s.row1 - s.row0 for s in res.plan.segments)
+    assert seg_rows > 21 * 64
+    with torch.no_grad():
+        ref = oracle.evaluate_embed(t_list)
+    _close(got.cpu().numpy(), torch.cat(ref["per_graph"]).numpy())
+    for _ in range(2):
+        assert torch.equal(got, model.encode(t_list).out)
+
+
 def test_scan_walks_more_than_32_partitions_per_cluster_in_rounds():
     """A partition table with far more than 32 partitions per cluster (the same batch re-partitioned with an 8-row tile):
     the scan kernel then takes its partitions in rounds of 32; the result does not depend on the partitioning."""
