@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <utility>
 
 #include "internal.h"
@@ -240,6 +241,21 @@ __global__ void __launch_bounds__(kGWWarps * 32, 4) rgcn_gather_wide_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // fused RGCN layer, tcgen05, 64-row tiles
 // ------------------------------------------------------------------------------------------------
+// Development-only phase timeline (tools/probe_timeline_wide.py builds a separate library with -DTEMP_TIMELINE): lane 0 of
+// every worker warp stores clock64() at mark m of step s into [cta][warp 0..7][step 0..15][mark 0..9].
+#ifdef TEMP_TIMELINE
+__device__ unsigned long long* g_timeline_w = nullptr;
+__device__ __forceinline__ void tlw(int warp, int step, int mark) {
+  if (g_timeline_w != nullptr && (threadIdx.x & 31) == 0 && warp < 8 && step < 16)
+    g_timeline_w[((static_cast<size_t>(blockIdx.x) * 8 + warp) * 16 + step) * 10 + mark] = clock64();
+}
+#define TLW(m) tlw(warp, s, m)
+#define TLL(m) tlw(warp, 0, m)
+#else
+#define TLW(m)
+#define TLL(m)
+#endif
+
 struct WideBars {
   uint64_t w_full[kWStages], w_empty[kWStages];
   uint64_t b_ready, d1_full, x_ready;
@@ -371,6 +387,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
     const int R0 = rbase + 32 * hf;
     const uint32_t s_hi = smem_u32(b_hi), s_lo = smem_u32(b_lo);
     const uint32_t lane_base = tbase + (static_cast<uint32_t>(32 * q) << 16);
+    TLL(0);
 
     // ---- 1. self-loop operand rows -> shared memory (hi / lo): warp w stages tile rows 8 w .. 8 w + 7 (one 8-row swizzle
     // group), a lane per float4 channel groups lane and lane + 32; channels >= d and rows >= row1 are zero ----
@@ -382,6 +399,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
       const bool oka = lane < nv, okb = lane + 32 < nv;
       const bool ina = lane < 8 * KA, inb = lane + 32 < 8 * KA;      // inside the padded operand at all
       pdl_wait();  // everything above (barriers, TMEM, plan indices) overlapped the predecessor
+      TLL(1);
       float4 va[8], vb[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -421,6 +439,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
       fence_proxy_async();
       mbar_arrive(&S.b_ready);
     }
+    TLL(2);
 
     // ---- 2. bit j of `has`: row R0 + j has in-edges (its aggregate was written by rgcn_gather_wide_kernel) ----
     unsigned has = 0u;
@@ -433,62 +452,119 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
     if (need_te && p.row_time != nullptr) rt = __ldg(p.row_time + min(R0 + lane, p.row1 - 1));
 
     // ---- 3. epilogue 1: out = act(agg (+x) + x . W_loop + bias) ; h_out ; chain operand X in place ----
+    // Everything a row needs from the argument block is hoisted into registers / running pointers here: in the first
+    // version the row loop re-read the flags from the constant bank, rebuilt 64-bit row addresses and carried the general
+    // time-embedding walk in every unrolled iteration -- ~45 instructions and ~215 cycles per row (timeline probe: 13.9 k
+    // cycles for the 64 rows of a warp with two feature blocks, the longest phase of a tile without a chain).
+    const int rows_valid = max(0, min(32, p.row1 - R0));       // rows of this warp inside [row0, row1)
+    const bool relu = p.activation == TEMP_ACT_RELU, residual = p.residual != 0, te_o = p.te_out != 0, te_c = p.te_chain != 0;
+    const bool chain = n_mb > 0;
+    const bool store_h = p.h_out != nullptr && by == 0;
     // the aggregate values of this thread's (feature, 32 rows) for both feature blocks: in flight while the MMAs complete
     float ag[2][32];
 #pragma unroll
     for (int fb = 0; fb < 2; ++fb) {
       const int f = 128 * fb + 32 * q + lane;
-      const float* agg_col = p.agg_scratch + static_cast<size_t>(R0) * D + f;
+      const float* ap = p.agg_scratch + static_cast<size_t>(R0) * D + f;
+      const unsigned take = f < D ? has : 0u;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) ag[fb][j] = (f < D && ((has >> j) & 1u)) ? ld_dep_f32(agg_col + static_cast<size_t>(j) * D) : 0.f;
+      for (int j = 0; j < 32; ++j) {
+        ag[fb][j] = ((take >> j) & 1u) ? ld_dep_f32(ap) : 0.f;
+        ap += D;
+      }
     }
+    TLL(3);
     mbar_wait(&S.d1_full, 0);
     tc_fence_after();
-#pragma unroll
-    for (int fb = 0; fb < 2; ++fb) {
+    TLL(4);
+    // time embedding: rows are packed snapshot by snapshot, so the 32 rows of this warp see one or two time-embedding rows
+    // almost always -- both are fetched up front and a row picks one by its index (kFast); spans with three or more
+    // snapshots (tiny graphs) take the general walk that reloads on change
+    int t_first = 0, t_last = 0, te_split = 32;
+    bool te_fast = true;
+    if (need_te) {
+      t_first = __shfl_sync(kFull, rt, 0);
+      t_last = __shfl_sync(kFull, rt, 31);
+      const unsigned is_first = __ballot_sync(kFull, rt == t_first);
+      te_split = __popc(is_first);
+      te_fast = __all_sync(kFull, rt == t_first || rt == t_last) && is_first == (te_split >= 32 ? 0xffffffffu : ((1u << te_split) - 1u));
+    }
+    auto epilogue1 = [&](auto fast_tag, const int fb, const float (&agv)[32]) {
+      constexpr bool kFast = decltype(fast_tag)::value;
       const int atom = 4 * fb + q;
-      if (fb >= n_fb || atom >= KA) continue;          // warp-uniform: no feature of this warp in the block
       const int f = 128 * fb + 32 * q + lane;
       const bool fok = f < D;
       const float bias = (fok && p.h_bias != nullptr) ? __ldg(p.h_bias + f) : 0.f;
+      float te_a = 0.f, te_b = 0.f;
+      if (need_te && kFast && fok) {
+        te_a = __ldg(p.time_embed + static_cast<size_t>(t_first) * D + f);
+        te_b = __ldg(p.time_embed + static_cast<size_t>(t_last) * D + f);
+      }
       float v[32];
       tmem_ld32(lane_base + 64 * fb + 32 * hf, v);
-      const uint32_t ab = static_cast<uint32_t>(atom) * kWAtomBytes;
+      // operand address of (tile row 32 hf + i, k = f): k-atom `atom`, swizzle group 4 hf + (i >> 3), 16-byte chunk (lane >> 2) ^ (i & 7)
+      const uint32_t rb = static_cast<uint32_t>(atom) * kWAtomBytes + static_cast<uint32_t>(4 * hf) * 1024u + (static_cast<uint32_t>(lane & 3) << 2);
+      const uint32_t o_hi = s_hi + rb, o_lo = s_lo + rb, cx = static_cast<uint32_t>(lane) >> 2;
+      // (the empty asm statements make these values opaque: without them the compiler re-derives the 64-bit row address and
+      // re-reads the flags from the constant bank in every unrolled iteration rather than keeping them in registers)
+      float* hp = p.h_out + static_cast<size_t>(R0) * D + f;
+      size_t row_pitch = static_cast<size_t>(D) * sizeof(float);
+      asm volatile("" : "+l"(hp), "+l"(row_pitch));
+      int n_store = (store_h && fok) ? rows_valid : 0;           // rows of this thread that reach h_out
+      int n_keep = fok ? rows_valid : 0;                         // rows of this thread that are not operand padding
+      unsigned fl = (relu ? 1u : 0u) | (residual ? 2u : 0u) | (te_o ? 4u : 0u) | (te_c ? 8u : 0u) | (chain ? 16u : 0u);
+      asm volatile("" : "+r"(n_store), "+r"(n_keep), "+r"(fl));
+      const bool f_relu = fl & 1u, f_res = fl & 2u, f_teo = fl & 4u, f_tec = fl & 8u, f_chain = fl & 16u;
       int cur_trow = -1;
       float cur_te = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int r = R0 + i;
-        const uint32_t off = ab + sw128_off(static_cast<uint32_t>(32 * hf + i), static_cast<uint32_t>(lane));
+        const uint32_t off = static_cast<uint32_t>(i >> 3) * 1024u + static_cast<uint32_t>(i & 7) * 128u + ((cx ^ static_cast<uint32_t>(i & 7)) << 4);
         float te = 0.f;
         if (need_te) {
-          const int trow = __shfl_sync(kFull, rt, i);  // warp-uniform
-          if (trow != cur_trow) {
-            cur_trow = trow;
-            cur_te = fok ? __ldg(p.time_embed + static_cast<size_t>(trow) * D + f) : 0.f;
+          if (kFast) {
+            te = i < te_split ? te_a : te_b;
+          } else {
+            const int trow = __shfl_sync(kFull, rt, i);  // warp-uniform
+            if (trow != cur_trow) {
+              cur_trow = trow;
+              cur_te = fok ? __ldg(p.time_embed + static_cast<size_t>(trow) * D + f) : 0.f;
+            }
+            te = cur_te;
           }
-          te = cur_te;
         }
-        float val = ag[fb][i];
-        if (p.residual) val += lds_f32(s_hi + off) + lds_f32(s_lo + off);
+        float val = agv[i];
+        if (f_res) val += lds_f32(o_hi + off) + lds_f32(o_lo + off);
         val += v[i];
         val += bias;
-        if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
-        if (fok && r < p.row1 && p.h_out != nullptr && by == 0) p.h_out[static_cast<size_t>(r) * D + f] = p.te_out ? val + te : val;
-        if (n_mb > 0) {
-          const float xx = (fok && r < p.row1) ? (p.te_chain ? val + te : val) : 0.f;
+        if (f_relu) val = fmaxf(val, 0.f);
+        const float with_te = val + te;
+        if (i < n_store) *hp = f_teo ? with_te : val;
+        hp = reinterpret_cast<float*>(reinterpret_cast<char*>(hp) + row_pitch);
+        if (f_chain) {
+          const float xx = i < n_keep ? (f_tec ? with_te : val) : 0.f;
           float hi, lo;
           split_tf32(xx, hi, lo);
-          sts_f32(s_hi + off, hi);
-          sts_f32(s_lo + off, lo);
+          sts_f32(o_hi + off, hi);
+          sts_f32(o_lo + off, lo);
         }
       }
+    };
+#pragma unroll
+    for (int fb = 0; fb < 2; ++fb) {
+      if (fb >= n_fb || 4 * fb + q >= KA) continue;          // warp-uniform: no feature of this warp in the block
+      if (te_fast)
+        epilogue1(std::true_type{}, fb, ag[fb]);
+      else
+        epilogue1(std::false_type{}, fb, ag[fb]);
     }
 
+    TLL(5);
     // ---- 4. chain epilogues: chain_out[r, 128 mb + 32 q + lane] = D2 + chain_b ----
     if (n_mb > 0) {
       fence_proxy_async();
       mbar_arrive(&S.x_ready);
+      const size_t chain_ld = static_cast<size_t>(p.chain_ld);
       for (int mb = 0; mb < n_mb; ++mb) {
         const int slot = mb % 3;
         const int cf = 128 * chain_block(mb) + 32 * q + lane;
@@ -498,10 +574,12 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
         tc_fence_after();
         float v[32];
         tmem_ld32(lane_base + 128 + 64 * slot + 32 * hf, v);
-        float* orow = p.chain_out + static_cast<size_t>(R0) * p.chain_ld + cf;
+        float* orow = p.chain_out + static_cast<size_t>(R0) * chain_ld + cf;
+        const int n_out = cok ? rows_valid : 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (cok && R0 + i < p.row1) orow[static_cast<size_t>(i) * p.chain_ld] = v[i] + cbias;
+          if (i < n_out) *orow = v[i] + cbias;
+          orow += chain_ld;
         }
         tc_fence_before();
         mbar_arrive(&S.d2_empty[slot]);
@@ -509,6 +587,7 @@ __global__ void __launch_bounds__(kWThreads, 1) rgcn_layer_tcw_kernel(const Temp
     }
   }
 
+  TLL(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tbase, 512);
@@ -690,20 +769,28 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
     }
 
     // ---- 2. what the gates need besides gh: input gates, time embedding, accumulate target: in flight during the MMAs ----
+    // (running pointers and a row count kept opaque: the unrolled row loops otherwise rebuild 64-bit addresses and re-read the
+    // argument block from the constant bank per row -- the layer kernel's epilogue showed ~215 cycles per row that way)
+    const float* gp = p.gi + static_cast<size_t>(rbase + 8 * warp) * p.gi_ld + p.gi_off + j;
+    float* op = p.out + static_cast<size_t>(rbase + 8 * warp) * D + j;
+    size_t gi_pitch = static_cast<size_t>(p.gi_ld) * sizeof(float), out_pitch = static_cast<size_t>(D) * sizeof(float);
+    int n_rows = jok ? max(0, min(8, p.row1 - (rbase + 8 * warp))) : 0;      // rows of this thread inside [row0, row1)
+    unsigned gfl = (p.time_embed != nullptr ? 1u : 0u) | (p.accumulate ? 2u : 0u);
+    asm volatile("" : "+l"(gp), "+l"(op), "+l"(gi_pitch), "+l"(out_pitch), "+r"(n_rows), "+r"(gfl));
+    const bool has_te = gfl & 1u, accum = gfl & 2u;
     float gir[8], giz[8], gin[8], tev[8], old[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = rbase + 8 * warp + i;
       gir[i] = giz[i] = gin[i] = tev[i] = old[i] = 0.f;
       const int tr_i = __shfl_sync(kFull, trow, i);          // (lane i holds tile row 8 w + i)
-      if (jok && r < p.row1) {
-        const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
-        gir[i] = ld_dep_f32(gi);
-        giz[i] = ld_dep_f32(gi + D);
-        gin[i] = ld_dep_f32(gi + 2 * D);
-        if (p.time_embed != nullptr) tev[i] = __ldg(p.time_embed + static_cast<size_t>(tr_i) * D + j);
-        if (p.accumulate) old[i] = ld_dep_f32(p.out + static_cast<size_t>(r) * D + j);
+      if (i < n_rows) {
+        gir[i] = ld_dep_f32(gp);
+        giz[i] = ld_dep_f32(gp + D);
+        gin[i] = ld_dep_f32(gp + 2 * D);
+        if (has_te) tev[i] = __ldg(p.time_embed + static_cast<size_t>(tr_i) * D + j);
+        if (accum) old[i] = ld_dep_f32(reinterpret_cast<const char*>(op) + i * out_pitch);
       }
+      gp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(gp) + gi_pitch);
     }
 
     // ---- 3. accumulator quadrants r | z | n -> exchange rows [gate][tile row][32] in the (now idle) weight ring ----
@@ -725,10 +812,10 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
     // ---- 4. gates (torch.nn.GRU, gate order r, z, n: SURVEY Appendix A.3), state store ----
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int m = 8 * warp + i, r = rbase + m;
+      const int m = 8 * warp + i;
       const int pri = __shfl_sync(kFull, pr, i);
       const float dti = __shfl_sync(kFull, dt, i);
-      if (!jok || r >= p.row1) continue;
+      if (i >= n_rows) continue;
       float hr = br, hz = bz, hn = bn, hp = 0.f;
       if (pri >= 0) {
         const float dec = dti;
@@ -743,7 +830,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
       const float ng = tanh_w(gin[i] + rg * hn);
       float hy = (1.f - zg) * ng + zg * hp;
       hy += tev[i];
-      p.out[static_cast<size_t>(r) * D + j] = p.accumulate ? old[i] + hy : hy;
+      *reinterpret_cast<float*>(reinterpret_cast<char*>(op) + i * out_pitch) = accum ? old[i] + hy : hy;
     }
   }
 
@@ -763,19 +850,6 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_step_tcw_kernel(const TempGr
 // activation slice from shared memory).  Steps are separated by a grid-wide barrier (cooperative launch: all CTAs resident);
 // the state goes through L2 (ld.global.cg: rows of consecutive steps share 128-byte lines, L1 may hold a stale copy).
 // The slice is (re)installed when the recurrent cell changes (the Bi models: forward cell steps, then backward cell steps).
-// Development-only phase timeline (tools/probe_timeline_wide.py builds a separate library with -DTEMP_TIMELINE): lane 0 of
-// every worker warp stores clock64() at mark m of step s into [cta][warp 0..7][step 0..15][mark 0..9].
-#ifdef TEMP_TIMELINE
-__device__ unsigned long long* g_timeline_w = nullptr;
-__device__ __forceinline__ void tlw(int warp, int step, int mark) {
-  if (g_timeline_w != nullptr && (threadIdx.x & 31) == 0 && warp < 8 && step < 16)
-    g_timeline_w[((static_cast<size_t>(blockIdx.x) * 8 + warp) * 16 + step) * 10 + mark] = clock64();
-}
-#define TLW(m) tlw(warp, s, m)
-#else
-#define TLW(m)
-#endif
-
 struct ScanWBars {
   uint64_t w_full[kWStages], w_empty[kWStages];
   uint64_t b_ready, d_full;
@@ -1072,20 +1146,28 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         }
         TLW(2);
         // ---- 2. input gates, time embedding, accumulate target: in flight during the MMAs ----
+        // (running pointers and a row count kept opaque: the unrolled row loops otherwise rebuild 64-bit addresses and re-read the
+        // argument block from the constant bank per row -- the layer kernel's epilogue showed ~215 cycles per row that way)
+        const float* gp = p.gi + static_cast<size_t>(rbase + 8 * warp) * p.gi_ld + p.gi_off + j;
+        float* op = p.out + static_cast<size_t>(rbase + 8 * warp) * D + j;
+        size_t gi_pitch = static_cast<size_t>(p.gi_ld) * sizeof(float), out_pitch = static_cast<size_t>(D) * sizeof(float);
+        int n_rows = jok ? max(0, min(8, p.row1 - (rbase + 8 * warp))) : 0;      // rows of this thread inside [row0, row1)
+        unsigned gfl = (p.time_embed != nullptr ? 1u : 0u) | (p.accumulate ? 2u : 0u);
+        asm volatile("" : "+l"(gp), "+l"(op), "+l"(gi_pitch), "+l"(out_pitch), "+r"(n_rows), "+r"(gfl));
+        const bool has_te = gfl & 1u, accum = gfl & 2u;
         float gir[8], giz[8], gin[8], tev[8], old[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = rbase + 8 * warp + i;
           gir[i] = giz[i] = gin[i] = tev[i] = old[i] = 0.f;
-          const int tr_i = __shfl_sync(kFull, trow, i);
-          if (jok && r < p.row1) {
-            const float* gi = p.gi + static_cast<size_t>(r) * p.gi_ld + p.gi_off + j;
-            gir[i] = ld_dep_f32(gi);
-            giz[i] = ld_dep_f32(gi + D);
-            gin[i] = ld_dep_f32(gi + 2 * D);
-            if (p.time_embed != nullptr) tev[i] = __ldg(p.time_embed + static_cast<size_t>(tr_i) * D + j);
-            if (p.accumulate) old[i] = ld_cg_f32(p.out + static_cast<size_t>(r) * D + j);
+          const int tr_i = __shfl_sync(kFull, trow, i);          // (lane i holds tile row 8 w + i)
+          if (i < n_rows) {
+            gir[i] = ld_dep_f32(gp);
+            giz[i] = ld_dep_f32(gp + D);
+            gin[i] = ld_dep_f32(gp + 2 * D);
+            if (has_te) tev[i] = __ldg(p.time_embed + static_cast<size_t>(tr_i) * D + j);
+            if (accum) old[i] = ld_cg_f32(reinterpret_cast<const char*>(op) + i * out_pitch);
           }
+          gp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(gp) + gi_pitch);
         }
         TLW(3);
         // ---- 3. accumulator quadrants r | z | n -> exchange rows [gate][tile row][32] (the idle weight ring) ----
@@ -1107,10 +1189,10 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
         // ---- 4. gates, state store ----
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int m = 8 * warp + i, r = rbase + m;
+          const int m = 8 * warp + i;
           const int pri = __shfl_sync(kFull, pr, i);
           const float dti = __shfl_sync(kFull, dt, i);
-          if (!jok || r >= p.row1) continue;
+          if (i >= n_rows) continue;
           float hr = br, hz = bz, hn = bn, hp = 0.f;
           if (pri >= 0) {
             const float dec = dti;
@@ -1125,7 +1207,7 @@ __global__ void __launch_bounds__(kWThreads, 1) gru_scan_tcw_kernel(const TempGr
           const float ng = tanh_w(gin[i] + rg * hn);
           float hy = (1.f - zg) * ng + zg * hp;
           hy += tev[i];
-          p.out[static_cast<size_t>(r) * D + j] = p.accumulate ? old[i] + hy : hy;
+          *reinterpret_cast<float*>(reinterpret_cast<char*>(op) + i * out_pitch) = accum ? old[i] + hy : hy;
         }
         TLW(6);
         if (rec) mm += 1;
