@@ -564,6 +564,16 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     TL(4);
     int cur_trow = t_first;
     float cur_te = te_a;
+    // What a row needs from the argument block, hoisted and made opaque (the empty asm): left to itself the compiler re-reads
+    // the flags from the constant bank and rebuilds the 64-bit row address inside a reconvergence region for every one of
+    // the 64 unrolled rows (~35 instructions per row; found on the 64-row kernel of tc_wide.cu, same pattern here).
+    float* hp = p.h_out + static_cast<size_t>(R0) * kD + f;
+    int n_store = p.h_out != nullptr ? max(0, min(64, p.row1 - R0)) : 0;      // rows of this thread that reach h_out
+    int n_keep = max(0, min(64, p.row1 - R0));                                // rows that are not operand padding
+    unsigned fl = (p.activation == TEMP_ACT_RELU ? 1u : 0u) | (p.residual ? 2u : 0u) | (p.te_out ? 4u : 0u) | (p.te_chain ? 8u : 0u) |
+                  (n_mb > 0 ? 16u : 0u);
+    asm volatile("" : "+l"(hp), "+r"(n_store), "+r"(n_keep), "+r"(fl));
+    const bool f_relu = fl & 1u, f_res = fl & 2u, f_teo = fl & 4u, f_tec = fl & 8u, f_chain = fl & 16u;
     auto epilogue1 = [&](auto fast_tag) {
       constexpr bool kFast = decltype(fast_tag)::value;
 #pragma unroll
@@ -575,7 +585,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
         const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * c)) * 1024u;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int r = R0 + 16 * c + i;
           const uint32_t off = grp + sw128_off(i, lane);
           float te;
           if (kFast) {
@@ -589,13 +598,14 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
             te = cur_te;
           }
           float val = ag[16 * c + i];
-          if (p.residual) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
+          if (f_res) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
           val += v[i];
           val += bias;
-          if (p.activation == TEMP_ACT_RELU) val = fmaxf(val, 0.f);
-          if (r < p.row1 && p.h_out != nullptr) p.h_out[static_cast<size_t>(r) * kD + f] = p.te_out ? val + te : val;
-          if (n_mb > 0) {
-            const float xx = r < p.row1 ? (p.te_chain ? val + te : val) : 0.f;
+          if (f_relu) val = fmaxf(val, 0.f);
+          const float with_te = val + te;
+          if (16 * c + i < n_store) hp[(16 * c + i) * kD] = f_teo ? with_te : val;
+          if (f_chain) {
+            const float xx = 16 * c + i < n_keep ? (f_tec ? with_te : val) : 0.f;
             float hi, lo;
             split_tf32(xx, hi, lo);
             sts_f32(sb_hi + off, hi);
@@ -616,7 +626,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
       mbar_arrive(&S.x_ready);
       // snapshot-sharded forward: the rank that scans the chain partition of a row receives the row's chained output
       int ownA = 0, ownB = 0;
-      if (p.chain_peers != nullptr) {
+      const bool use_peers = p.chain_peers != nullptr;
+      if (use_peers) {
         ownA = __ldg(p.chain_owner + min(R0 + lane, p.row1 - 1));
         ownB = __ldg(p.chain_owner + min(R0 + 32 + lane, p.row1 - 1));
       }
@@ -627,15 +638,18 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
         tc_fence_after();
         TL(6 + 2 * (mb < 3 ? mb : 3));
         float* orow = p.chain_out + static_cast<size_t>(R0) * p.chain_ld + 128 * mb + f;
+        size_t chain_pitch = static_cast<size_t>(p.chain_ld) * sizeof(float);
+        asm volatile("" : "+l"(orow), "+l"(chain_pitch));      // (running pointer: see epilogue 1)
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           float v[32];
           tmem_ld32(lane_base + 128 + 128 * slot + 64 * hf + 32 * c, v);
           tmem_ld_wait();
-          if (p.chain_peers == nullptr) {
+          if (!use_peers) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              if (R0 + 32 * c + i < p.row1) orow[static_cast<size_t>(32 * c + i) * p.chain_ld] = v[i] + cbias;
+              if (32 * c + i < n_keep) *orow = v[i] + cbias;
+              orow = reinterpret_cast<float*>(reinterpret_cast<char*>(orow) + chain_pitch);
             }
           } else {
 #pragma unroll
