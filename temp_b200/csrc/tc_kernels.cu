@@ -577,35 +577,34 @@ __global__ void __launch_bounds__(kLayerThreads, 1) rgcn_layer_tc_kernel(const T
     auto epilogue1 = [&](auto fast_tag) {
       constexpr bool kFast = decltype(fast_tag)::value;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float v[16];
-        tmem_ld16(lane_base + 64 * hf + 16 * c, v);
-        tmem_ld_wait();
-        const int rt = c < 2 ? rtA : rtB;
-        const uint32_t grp = (static_cast<uint32_t>(8 * hf + 2 * c)) * 1024u;
+      for (int c = 0; c < 2; ++c) {          // 32 rows per TMEM load (two load latencies per thread instead of four)
+        float v[32];
+        tmem_ld32(lane_base + 64 * hf + 32 * c, v);
+        const int rt = c == 0 ? rtA : rtB;
+        const uint32_t grp = (static_cast<uint32_t>(8 * hf + 4 * c)) * 1024u;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) {
           const uint32_t off = grp + sw128_off(i, lane);
           float te;
           if (kFast) {
-            te = 16 * c + i < te_split ? te_a : te_b;
+            te = 32 * c + i < te_split ? te_a : te_b;
           } else {
-            const int trow = __shfl_sync(kFull, rt, (16 * c + i) & 31);  // warp-uniform
+            const int trow = __shfl_sync(kFull, rt, i);  // warp-uniform
             if (trow != cur_trow) {
               cur_trow = trow;
               cur_te = __ldg(p.time_embed + static_cast<size_t>(trow) * kD + f);
             }
             te = cur_te;
           }
-          float val = ag[16 * c + i];
+          float val = ag[32 * c + i];
           if (f_res) val += lds_f32(sb_hi + off) + lds_f32(sb_lo + off);
           val += v[i];
           val += bias;
           if (f_relu) val = fmaxf(val, 0.f);
           const float with_te = val + te;
-          if (16 * c + i < n_store) hp[(16 * c + i) * kD] = f_teo ? with_te : val;
+          if (32 * c + i < n_store) hp[(32 * c + i) * kD] = f_teo ? with_te : val;
           if (f_chain) {
-            const float xx = 16 * c + i < n_keep ? (f_tec ? with_te : val) : 0.f;
+            const float xx = 32 * c + i < n_keep ? (f_tec ? with_te : val) : 0.f;
             float hi, lo;
             split_tf32(xx, hi, lo);
             sts_f32(sb_hi + off, hi);
