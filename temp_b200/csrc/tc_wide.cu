@@ -23,7 +23,7 @@
 //   gru_step_tcw_kernel        : one GRU step per launch (224 < d <= 256, single steps of the models whose two layers
 //        alternate), the weight slice streamed through the ring.
 // Reference statements: models/RGCN.py:53-104 (layer), models/RRGCN.py:77-89 and torch.nn.GRU (step), as cited on the
-// entry points in include/temp_b200.h.  Measurements (BASELINE config 3: 0.879 -> 0.287 ms) and bounds: DESIGN.md 3a.
+// entry points in include/temp_b200.h.  Measurements (BASELINE config 3: 0.879 -> 0.264 ms) and bounds: DESIGN.md 3a.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
