@@ -497,3 +497,28 @@ def test_tensor_core_image_sizes_cover_the_wide_family_without_a_gpu():
     assert L.temp_program_kernel_count(arr, 1) == 1
     arr[0].u.scan.steps[0].d = arr[0].u.scan.steps[1].d = arr[0].u.scan.steps[2].d = 256      # W_hh slice beyond tensor memory
     assert L.temp_program_kernel_count(arr, 1) == 3
+
+
+def test_fused_scan_ops_carry_the_barrier_words():
+    """Program.fuse_gru_scans: consecutive GRU steps become one scan op that carries the barrier pointer and the number of
+    zeroed words behind it (TempGruScanArgs.barrier_words: what lets gru_scan_tcw_kernel use per-tile completion counters);
+    with split_cells a run also ends where the recurrent cell changes."""
+    from temp_b200 import lib
+    prog = lib.Program()
+    for i in range(5):
+        g = lib.GruArgs()
+        g.row0, g.row1, g.d, g.b_hh = 10 * i, 10 * i + 10, 200, 0x1000 if i < 3 else 0x2000
+        prog.add(lib.OP_GRU, g)
+    prog.fuse_gru_scans(0xabc0, barrier_words=2 + 16 * 1024)
+    assert [o.kind for o in prog.ops] == [lib.OP_GRU_SCAN]
+    sc = prog.ops[0].u.scan
+    assert sc.n_steps == 5 and sc.barrier == 0xabc0 and sc.barrier_words == 2 + 16 * 1024
+    assert [sc.steps[i].row0 for i in range(5)] == [0, 10, 20, 30, 40]
+    prog2 = lib.Program()
+    for i in range(5):
+        g = lib.GruArgs()
+        g.row0, g.row1, g.d, g.b_hh = 10 * i, 10 * i + 10, 128, 0x1000 if i < 3 else 0x2000
+        prog2.add(lib.OP_GRU, g)
+    prog2.fuse_gru_scans(0xabc0, split_cells=True)
+    assert [o.kind for o in prog2.ops] == [lib.OP_GRU_SCAN, lib.OP_GRU_SCAN]
+    assert [o.u.scan.n_steps for o in prog2.ops] == [3, 2] and prog2.ops[0].u.scan.barrier_words == 2
