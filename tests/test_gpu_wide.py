@@ -282,3 +282,33 @@ def test_wide_gru_step_matches_fp64_and_the_simt_kernel(D, R, row0):
             errs["tc" if packed else "simt"] = _err(got[row0:], want[row0:])
         _log({"gru": [D, R, row0], "case": {k: str(v) for k, v in kw.items()}, **errs})
         assert errs["tc"] < 1e-5 and errs["simt"] < 1e-5, errs
+
+
+@pytest.mark.parametrize("name", ["grrgcn_tiny_d200_nb100", "bigrrgcn_icews0515_real_nb100"])
+def test_wide_scan_synchronisation_modes_agree(name):
+    """gru_scan_tcw_kernel orders its steps by per-tile completion counters when the caller's zeroed words hold them
+    (TempGruScanArgs.barrier_words) and by a grid-wide barrier otherwise; without a barrier word the scan runs as one
+    gru_step_tcw_kernel launch per step.  Same arithmetic in the first two (bit-identical), fp32 rounding apart in the third."""
+    from temp_b200 import lib
+    from tests.helpers import CASE_BY_NAME, product_model
+    case = CASE_BY_NAME[name]
+    model = product_model(case)
+    res = model.encode(case["t_list"])
+    torch.cuda.synchronize()
+    want = res.out.clone()
+    scans = [o for o in res.program.ops if o.kind == lib.OP_GRU_SCAN]
+    assert scans and all(o.u.scan.barrier_words > 2 for o in scans)
+    for o in scans:
+        o.u.scan.barrier_words = 2                     # only the two barrier words: grid-wide barrier between the steps
+    res.program._arr = None
+    res.out.zero_()
+    res.program.run()
+    torch.cuda.synchronize()
+    assert torch.equal(res.out, want)
+    for o in scans:
+        o.u.scan.barrier = None                        # no barrier word at all: one launch per step
+    res.program._arr = None
+    res.out.zero_()
+    res.program.run()
+    torch.cuda.synchronize()
+    assert float((res.out - want).abs().max()) <= 2e-6 * float(want.abs().max())
