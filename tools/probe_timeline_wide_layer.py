@@ -1,6 +1,7 @@
 """Development probe (GPU): per-phase clock64 timeline of rgcn_layer_tcw_kernel (temp_b200/csrc/tc_wide.cu) for every layer
 launch of BASELINE config 3 (separate -DTEMP_TIMELINE library): median over CTAs of the cycles between the marks of worker
-warps 0 (rows 0..31, feature quadrant 0) and 7.
+warps 0 (rows 0..31, feature quadrant 0) and 7.  (The buffer is indexed by blockIdx.x only: for a launch whose chain blocks
+are spread over grid.y -- the Bi centre step -- the y blocks overwrite each other's marks and the line is meaningless.)
 
     python tools/probe_timeline_wide_layer.py
 """
